@@ -1,0 +1,251 @@
+/*
+ * nyxb.h — C ABI of the B200 batched orbit-propagation engine (libnyxb.so).
+ *
+ * This is the drop-in boundary for ONE path of nyx-space/nyx (reference paths are
+ * relative to /root/reference/nyx-core/src):
+ *
+ *   MonteCarlo::run_until_epoch            mc/montecarlo.rs:188-273
+ *     -> Propagator::with(..)              propagators/propagator.rs:88-108
+ *     -> PropInstance::until_epoch         propagators/instance.rs:279-282
+ *     -> PropInstance::propagate           propagators/instance.rs:87-262
+ *     -> PropInstance::derive              propagators/instance.rs:358-493
+ *     -> SpacecraftDynamics::eom           dynamics/spacecraft.rs:191-310
+ *
+ * A Rust shim packs `Vec<Spacecraft>` into the SoA arrays
+ * below, calls nyxb_propagate_batch through `extern "C"`, and unpacks the final
+ * states into `Results` / `Vec<Spacecraft>`.  Nothing here mentions torch or CUDA
+ * types: plain pointers, sizes and PODs only.  All pointers are HOST pointers
+ * unless the function name ends in `_dev`.
+ *
+ * Units follow the reference: km, km/s, kg, m^2, seconds; time is integer
+ * nanoseconds (hifitime::Duration / Epoch are integer-ns types).
+ */
+#ifndef NYXB_H
+#define NYXB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NYXB_ABI_VERSION 1
+
+/* ---- IntegratorMethod — propagators/rk_methods/mod.rs:65-79 (same order) ---- */
+enum nyxb_method {
+    NYXB_RK89 = 0,        /* RungeKutta89 (default)   rk_methods/rk.rs:89-252   */
+    NYXB_DP78 = 1,        /* DormandPrince78          rk_methods/dormand.rs:71-184 */
+    NYXB_DP45 = 2,        /* DormandPrince45          rk_methods/dormand.rs:23-69 */
+    NYXB_RK4 = 3,         /* RungeKutta4 (fixed)      rk_methods/rk.rs:60-81    */
+    NYXB_CK45 = 4,        /* CashKarp45               rk_methods/rk.rs:21-58    */
+    NYXB_V56 = 5          /* Verner56                 rk_methods/verner.rs:24-79 */
+};
+
+/* ---- ErrorControl — propagators/error_ctrl.rs:30-71 (same order) ---- */
+enum nyxb_error_ctrl {
+    NYXB_RSS_CARTESIAN_STATE = 0,
+    NYXB_RSS_CARTESIAN_STEP = 1, /* default */
+    NYXB_RSS_STATE = 2,
+    NYXB_RSS_STEP = 3,
+    NYXB_LARGEST_ERROR = 4,
+    NYXB_LARGEST_STATE = 5,
+    NYXB_LARGEST_STEP = 6
+};
+
+/* ---- IntegratorOptions — propagators/options.rs:42-60 ----
+ * Durations are hifitime integer nanoseconds.  `with_fixed_step` semantics
+ * (options.rs:100-111): fixed_step=1, min=max=init=step, tolerance=0, attempts=0. */
+typedef struct {
+    int32_t method;      /* enum nyxb_method */
+    int32_t error_ctrl;  /* enum nyxb_error_ctrl */
+    int64_t init_step_ns;
+    int64_t min_step_ns;
+    int64_t max_step_ns;
+    double tolerance;
+    int32_t attempts;    /* u8 in the reference */
+    int32_t fixed_step;  /* bool */
+} nyxb_integ_opts;
+
+/* ---- Body-fixed frame orientation (what anise `Almanac::rotate` supplies to
+ * gravity_field.rs:150-154,258-265 and drag.rs:184-189).  anise and its PCK data
+ * are absent from the reference tree, so the orientation is an explicit model:
+ *   kind 0: body-fixed axes == inertial axes (no rotation)
+ *   kind 1: IAU pole/prime-meridian, angles in degrees,
+ *           ra = ra0 + ra1*T, dec = dec0 + dec1*T, W = w0 + w1*d,
+ *           T = Julian centuries, d = days past the reference epoch (t = 0 ns),
+ *           DCM inertial->fixed = R3(W) R1(90deg-dec) R3(90deg+ra). */
+typedef struct {
+    int32_t kind;
+    int32_t _pad;
+    double ra0_deg, ra1_deg_cy;
+    double dec0_deg, dec1_deg_cy;
+    double w0_deg, w1_deg_day;
+} nyxb_rotation;
+
+/* ---- GravityField — dynamics/gravity_field.rs:36-48 + io/gravity.rs:90-96 ----
+ * c_nm/s_nm: normalised coefficients, row-major [(degree+1) x (degree+1)], entry
+ * (n,m) at n*(degree+1)+m.  mu and r_eq are passed explicitly because the reference
+ * takes them from the *frame* (gravity_field.rs:195-207), never from the file. */
+typedef struct {
+    int32_t degree;
+    int32_t order;
+    double mu_km3_s2;
+    double r_eq_km;
+    const double* c_nm;
+    const double* s_nm;
+    nyxb_rotation rot;
+} nyxb_gravity_field;
+
+/* ---- Ephemeris of one celestial body relative to the integration-frame centre,
+ * inertial axes: piecewise Chebyshev position series (what anise evaluates from an
+ * SPK for orbital.rs:230-234 / solarpressure.rs:138-143 / eclipse.rs:77).
+ * coeffs layout: [n_intervals][3][n_coeffs]; interval i covers
+ * [t0_ns + i*interval_ns, t0_ns + (i+1)*interval_ns). */
+typedef struct {
+    double mu_km3_s2;
+    double radius_km;      /* mean equatorial radius (shadow computations) */
+    int64_t t0_ns;
+    int64_t interval_ns;
+    int32_t n_intervals;
+    int32_t n_coeffs;
+    const double* coeffs;
+} nyxb_body;
+
+#define NYXB_MAX_BODIES 8
+#define NYXB_CENTRAL_BODY (-1)
+
+/* ---- SolarPressure + ShadowModel — dynamics/solarpressure.rs:43-49,135-165;
+ * cosmic/eclipse.rs:35-83.  Body indices refer to nyxb_dynamics.bodies;
+ * NYXB_CENTRAL_BODY designates the integration-frame centre. */
+typedef struct {
+    double phi_w_m2;        /* solar flux at 1 AU, default 1367 (solarpressure.rs:35) */
+    int32_t sun_body;       /* index of the light source in bodies[] */
+    int32_t n_shadow;
+    int32_t shadow_body[4];
+} nyxb_srp;
+
+/* ---- Drag — dynamics/drag.rs:36-42,123-130,181-284 ---- */
+enum nyxb_density {
+    NYXB_DENSITY_CONSTANT = 0,   /* AtmDensity::Constant(rho) */
+    NYXB_DENSITY_EXPONENTIAL = 1,/* AtmDensity::Exponential{rho0,r0,ref_alt_m} */
+    NYXB_DENSITY_STDATM = 2      /* AtmDensity::StdAtm{max_alt_m} */
+};
+typedef struct {
+    int32_t density;        /* enum nyxb_density */
+    int32_t _pad;
+    double rho0;            /* Constant: rho ; Exponential: rho0 */
+    double r0;              /* Exponential */
+    double ref_alt_m;       /* Exponential: ref_alt_m ; StdAtm: max_alt_m */
+    double r_eq_km;         /* frame.mean_equatorial_radius_km() */
+    nyxb_rotation rot;      /* drag frame orientation (IAU_EARTH in the reference) */
+} nyxb_drag;
+
+/* ---- SpacecraftDynamics — closed set of models the GPU path accepts
+ * (dynamics/sequence/config.rs:96-169 serialises exactly this set). ---- */
+typedef struct {
+    double mu_central_km3_s2;     /* osc.frame.mu_km3_s2()  orbital.rs:86-90 */
+    double central_radius_km;     /* used when the centre is a shadow body */
+    int32_t n_bodies;
+    int32_t _pad;
+    const nyxb_body* bodies;      /* ephemerides available to the models */
+    uint32_t point_mass_mask;     /* bit j set: bodies[j] acts as PointMasses member (orbital.rs:213-247) */
+    uint32_t _pad2;
+    const nyxb_gravity_field* gravity;  /* NULL: none */
+    const nyxb_srp* srp;                /* NULL: none */
+    const nyxb_drag* drag;              /* NULL: none */
+} nyxb_dynamics;
+
+/* ---- IntegrationDetails (propagators/mod.rs:49-56) + counters for the metric ---- */
+typedef struct {
+    int64_t step_ns;     /* details.step of the last step */
+    double error;        /* details.error of the last adaptive step */
+    int32_t attempts;    /* details.attempts of the last step */
+    int32_t _pad;
+    int64_t n_steps;     /* accepted steps incl. the final partial step */
+    int64_t n_rejected;  /* rejected attempts */
+    int64_t n_rhs;       /* RHS evaluations */
+} nyxb_details;
+
+/* ---- per-trajectory status: mirrors the reference's error variants ---- */
+enum nyxb_status {
+    NYXB_OK = 0,
+    NYXB_ERR_PROP_MATH = 1,      /* PropagationError::PropMathError (NaN)  instance.rs:432-439 */
+    NYXB_ERR_FUEL_EXHAUSTED = 2, /* DynamicsError::FuelExhausted           spacecraft.rs:163-168 */
+    NYXB_ERR_MASSLESS = 3,       /* DynamicsError::MasslessSpacecraft      spacecraft.rs:201-203 */
+    NYXB_ERR_EPHEMERIS = 4,      /* almanac error: epoch outside ephemeris coverage */
+    NYXB_WARN_MAX_ATTEMPTS = 0x100 /* OR-ed flag: instance.rs:440-445 (warn only) */
+};
+
+/* ---- execution mode ---- */
+enum nyxb_mode {
+    NYXB_MODE_STRICT = 0, /* reference operation order, no FMA contraction: bit-parity mode */
+    NYXB_MODE_FAST = 1    /* FMA + reordered cooperative harmonics: tolerance-parity mode */
+};
+
+/* ---- library-level return codes ---- */
+enum nyxb_rc {
+    NYXB_RC_OK = 0,
+    NYXB_RC_BAD_ARG = -1,
+    NYXB_RC_NO_DEVICE = -2,
+    NYXB_RC_CUDA = -3,
+    NYXB_RC_UNSUPPORTED = -4
+};
+
+typedef struct nyxb_engine nyxb_engine; /* opaque: device tables for one (dynamics, opts) pair */
+
+/* Build device-resident tables (tableau, harmonic coefficients, ephemerides) for a
+ * propagator setup == `Propagator::new(dynamics, method, opts)` (propagator.rs:55-61).
+ * `device` is the CUDA ordinal.  Returns NULL on failure (see nyxb_last_error). */
+nyxb_engine* nyxb_engine_create(const nyxb_dynamics* dyn, const nyxb_integ_opts* opts,
+                                int32_t mode, int32_t device);
+void nyxb_engine_destroy(nyxb_engine* eng);
+
+/* Propagate n independent spacecraft until `end_epoch_ns`
+ * == for each i: `prop.with(state_i, almanac).until_epoch(end_epoch)`
+ * (mc/montecarlo.rs:233-253; nyx-py many_until_epoch py_md.rs:224-271).
+ *
+ *  state_soa   [9][n]  x,y,z,vx,vy,vz,Cr,Cd,prop_mass   (cosmic/spacecraft.rs:449-473)
+ *  consts_soa  [4][n]  dry_mass_kg, extra_mass_kg, srp_area_m2, drag_area_m2
+ *  epoch0_ns   [n]     start epochs (ns past the reference epoch of the ephemerides)
+ *  step_ns     [n] or NULL: in/out adapted step of each PropInstance (instance.rs:56);
+ *                      NULL => every run starts from opts.init_step_ns
+ *  out_*       same layouts; out_epoch_ns [n]; details [n]; status [n]
+ * Per-trajectory failures are reported in out_status and never abort the batch
+ * (mc/results.rs:48-59).  Thread-safe for distinct engines. */
+int32_t nyxb_propagate_batch(nyxb_engine* eng, size_t n,
+                             const double* state_soa, const double* consts_soa,
+                             const int64_t* epoch0_ns, int64_t end_epoch_ns,
+                             int64_t* step_ns,
+                             double* out_state_soa, int64_t* out_epoch_ns,
+                             nyxb_details* out_details, int32_t* out_status);
+
+/* Same, but every array is a DEVICE pointer on the engine's device and the launch
+ * is enqueued on `cuda_stream` (a cudaStream_t passed as void*, NULL = default
+ * stream) without synchronising.  Used by bench.py's HBM-resident `value` leg and
+ * by the multi-GPU driver (final-state all-gather is stream-ordered after it). */
+int32_t nyxb_propagate_batch_dev(nyxb_engine* eng, size_t n,
+                                 const double* state_soa, const double* consts_soa,
+                                 const int64_t* epoch0_ns, int64_t end_epoch_ns,
+                                 int64_t* step_ns,
+                                 double* out_state_soa, int64_t* out_epoch_ns,
+                                 nyxb_details* out_details, int32_t* out_status,
+                                 void* cuda_stream);
+
+/* Tuning / introspection. */
+int32_t nyxb_engine_set_lanes(nyxb_engine* eng, int32_t lanes_per_trajectory); /* 0 = auto */
+int32_t nyxb_engine_get_lanes(const nyxb_engine* eng);
+int64_t nyxb_engine_launch_count(const nyxb_engine* eng); /* kernels launched so far */
+double nyxb_engine_last_kernel_ms(const nyxb_engine* eng); /* CUDA-event time of the last launch (host API only) */
+
+/* Register-resident DFMA throughput probe: returns achieved FP64 TFLOP/s (FMA = 2 flop)
+ * on `device`; the FP64 roof that bench.py reports against. */
+double nyxb_measure_fp64_tflops(int32_t device, int32_t iters);
+
+int32_t nyxb_abi_version(void);
+const char* nyxb_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NYXB_H */

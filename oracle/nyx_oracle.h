@@ -1,0 +1,34 @@
+/*
+ * nyx_oracle.h — TEST INFRASTRUCTURE (see nyx_oracle.c header).  CPU restatement of the
+ * reference algorithm; shares only the descriptor PODs of include/nyxb.h with the product.
+ */
+#ifndef NYX_ORACLE_H
+#define NYX_ORACLE_H
+#include "../include/nyxb.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct nyx_oracle_grav nyx_oracle_grav;
+
+int nyx_oracle_tableau(int method, int* order, int* stages, const double** a, const double** b);
+double nyx_oracle_dur_to_seconds(int64_t total_ns);
+int64_t nyx_oracle_dur_from_seconds(double s);
+void nyx_oracle_sincos(double x, double* s, double* c);
+void nyx_oracle_rotation(const nyxb_rotation* rot, int64_t t_ns, double R[9], double* wdot);
+int nyx_oracle_body_position(const nyxb_body* b, int64_t t_ns, double pos[3]);
+nyx_oracle_grav* nyx_oracle_grav_new(const nyxb_gravity_field* g);
+void nyx_oracle_grav_free(nyx_oracle_grav* h);
+void nyx_oracle_grav_accel(const nyx_oracle_grav* h, int64_t t_ns, const double r_in[3], double* scratch, double acc[3]);
+double nyx_oracle_occultation(const double r_eb[3], const double r_ls[3], double light_radius_km, double body_radius_km);
+double nyx_oracle_error_estimate(int ctrl, const double err[9], const double cand[9], const double cur[9]);
+int nyx_oracle_eom(const nyxb_dynamics* dyn, int64_t epoch_ns, double delta_t_s, const double y[9], const double consts[4], double dy[9]);
+int nyx_oracle_propagate_batch(const nyxb_dynamics* dyn, const nyxb_integ_opts* opts, size_t n,
+                               const double* state_soa, const double* consts_soa,
+                               const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
+                               double* out_state_soa, int64_t* out_epoch_ns,
+                               nyxb_details* out_details, int32_t* out_status, int n_threads);
+int nyx_oracle_num_threads(void);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,85 @@
+"""ctypes loader for the CPU oracle (TEST INFRASTRUCTURE — never imported by nyx_b200).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference legs use it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from nyx_b200 import abi
+
+_DIR = Path(__file__).resolve().parent
+_LIB = None
+
+
+def build(force: bool = False) -> Path:
+    so = _DIR / "libnyx_oracle.so"
+    src = _DIR / "nyx_oracle.c"
+    if force or not so.exists() or so.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["make", "-C", str(_DIR), "-B" if force else "-s"], check=True, capture_output=True)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = build()
+        L = C.CDLL(str(so))
+        vp = C.c_void_p
+        L.nyx_oracle_propagate_batch.restype = C.c_int
+        L.nyx_oracle_propagate_batch.argtypes = [
+            C.POINTER(abi.DynamicsC), C.POINTER(abi.IntegOpts), C.c_size_t, vp, vp, vp, C.c_int64, vp, vp, vp, vp, vp, C.c_int]
+        L.nyx_oracle_dur_to_seconds.restype = C.c_double
+        L.nyx_oracle_dur_to_seconds.argtypes = [C.c_int64]
+        L.nyx_oracle_dur_from_seconds.restype = C.c_int64
+        L.nyx_oracle_dur_from_seconds.argtypes = [C.c_double]
+        L.nyx_oracle_sincos.restype = None
+        L.nyx_oracle_sincos.argtypes = [C.c_double, abi.c_double_p, abi.c_double_p]
+        L.nyx_oracle_rotation.restype = None
+        L.nyx_oracle_rotation.argtypes = [C.POINTER(abi.Rotation), C.c_int64, abi.c_double_p, abi.c_double_p]
+        L.nyx_oracle_body_position.restype = C.c_int
+        L.nyx_oracle_body_position.argtypes = [C.POINTER(abi.BodyC), C.c_int64, abi.c_double_p]
+        L.nyx_oracle_occultation.restype = C.c_double
+        L.nyx_oracle_occultation.argtypes = [abi.c_double_p, abi.c_double_p, C.c_double, C.c_double]
+        L.nyx_oracle_error_estimate.restype = C.c_double
+        L.nyx_oracle_error_estimate.argtypes = [C.c_int, abi.c_double_p, abi.c_double_p, abi.c_double_p]
+        L.nyx_oracle_eom.restype = C.c_int
+        L.nyx_oracle_eom.argtypes = [C.POINTER(abi.DynamicsC), C.c_int64, C.c_double, abi.c_double_p, abi.c_double_p, abi.c_double_p]
+        L.nyx_oracle_tableau.restype = C.c_int
+        L.nyx_oracle_tableau.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(abi.c_double_p), C.POINTER(abi.c_double_p)]
+        L.nyx_oracle_num_threads.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def propagate_batch(dyn_c, opts_c, state_soa, consts_soa, epoch0_ns, end_epoch_ns, step_ns=None, n_threads=0):
+    """Same contract as nyxb_propagate_batch (include/nyxb.h) but on the CPU oracle."""
+    L = lib()
+    state_soa = np.ascontiguousarray(state_soa, dtype=np.float64)
+    consts_soa = np.ascontiguousarray(consts_soa, dtype=np.float64)
+    epoch0_ns = np.ascontiguousarray(epoch0_ns, dtype=np.int64)
+    n = state_soa.shape[1]
+    assert state_soa.shape == (9, n) and consts_soa.shape == (4, n) and epoch0_ns.shape == (n,)
+    out_state = np.empty((9, n), dtype=np.float64)
+    out_epoch = np.empty(n, dtype=np.int64)
+    details = np.zeros(n, dtype=abi.DETAILS_DTYPE)
+    status = np.zeros(n, dtype=np.int32)
+    step_ptr = None
+    if step_ns is not None:
+        assert step_ns.dtype == np.int64 and step_ns.shape == (n,)
+        step_ptr = step_ns.ctypes.data
+    rc = L.nyx_oracle_propagate_batch(
+        C.byref(dyn_c), C.byref(opts_c), n, state_soa.ctypes.data, consts_soa.ctypes.data, epoch0_ns.ctypes.data,
+        int(end_epoch_ns), step_ptr, out_state.ctypes.data, out_epoch.ctypes.data, details.ctypes.data,
+        status.ctypes.data, int(n_threads))
+    if rc != 0:
+        raise RuntimeError(f"oracle rejected the configuration (rc={rc})")
+    return out_state, out_epoch, details, status
+
+
+def num_threads() -> int:
+    return lib().nyx_oracle_num_threads()
