@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py — trajectory-steps/sec of the batched propagation hot path (BASELINE.json metric).
+
+A "step" of this benchmark is ONE pass of the hot path over one ensemble: every trajectory of the
+workload is propagated from t0 to the end epoch (MonteCarlo::run_until_epoch).  Workload at N=1 is
+BASELINE.json configs[1]: 10 000-trajectory LEO Monte Carlo, two-body + JGM-3 21x21 harmonics,
+adaptive RK89 (IntegratorOptions::default), 3-day span.  Multi-GPU is weak scaling: every rank
+integrates its own 10 000-trajectory shard (contiguous run indices) and the final states are
+exchanged with one all-gather inside the timed region.
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+S = 10**9
+DAY = 86400 * S
+
+# Algorithmic FP64 work per accepted RK89 step (SURVEY.md §8d / BASELINE.md §4; mul/add/div/sqrt = 1 flop):
+#   F_step = 16 * F_rhs + F_rk,  F_rk = 1308,
+#   F_rhs(two-body) = 12,  F_rhs(harmonics NxN) = 24*N(N+3)/2 + 4*N(N+1)/2 + 16*N + 60
+def flops_per_step(degree: int, stages: int = 16) -> float:
+    n = degree
+    f_rhs = 12.0 + (24.0 * n * (n + 3) / 2 + 4.0 * n * (n + 1) / 2 + 16.0 * n + 60.0 if n > 0 else 0.0)
+    return stages * f_rhs + 1308.0
+
+
+BYTES_PER_TRAJ = 13 * 8 + 8 + 9 * 8 + 24  # in: state+consts+epoch; out: state + details (208 B)
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=3)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="nyxb", choices=["nyxb", "reference"])
+    p.add_argument("--n-traj", type=int, default=10_000, help="trajectories per GPU")
+    p.add_argument("--span-days", type=float, default=3.0)
+    p.add_argument("--degree", type=int, default=21)
+    p.add_argument("--mode", default="fast", choices=["fast", "strict"])
+    p.add_argument("--lanes", type=int, default=0)
+    p.add_argument("--cpu-sample", type=int, default=192, help="trajectories in the bounded CPU-baseline sample")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def build_workload(args, n_total, nb):
+    """C2 of SURVEY.md §8(d): example-01 orbit + N(0, diag(1 km, 1 m/s)) dispersions, seed 0."""
+    frame = nb.EARTH_J2000
+    gd = nb.GravityFieldData.from_fixture("jgm3_70x70", args.degree, args.degree, nb.IAU_EARTH_FRAME)
+    dyn = nb.SpacecraftDynamics.new(nb.OrbitalDynamics.from_model(nb.GravityField.new(gd)))
+    # alt 300 km, e 0.015, i 68.5, RAAN 65.2, AoP 75, TA 0 (examples/01_orbit_prop/main.rs:52-53)
+    orbit = nb.Orbit.keplerian(6378.1363 + 300.0, 0.015, 68.5, 65.2, 75.0, 0.0, 0, frame)
+    template = nb.Spacecraft(orbit=orbit, mass=nb.Mass(1000.0, 0.0, 0.0))
+    mvn = nb.MvnSpacecraft.from_cartesian_std(template, 1.0, 1e-3)
+    rng = np.random.Generator(np.random.PCG64(0))
+    x = mvn.sample_vectors(rng, n_total)  # serial host stream, run index == draw order (montecarlo.rs:290-295)
+    st = np.ascontiguousarray((template.to_vector()[None, :] + x).T)  # [9][n]
+    cs = np.zeros((4, n_total))
+    cs[0] = template.mass.dry_mass_kg
+    ep = np.zeros(n_total, dtype=np.int64)
+    return frame, dyn, st, cs, ep
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_reference_leg(args, nb, sample_n, repeats=1):
+    """The reference's CPU path for the same workload: the C restatement of the reference algorithm
+    (oracle/, OpenMP over trajectories == the rayon par_iter of mc/montecarlo.rs:233-253), all host cores,
+    on a bounded sample of the same ensemble."""
+    from oracle import pyoracle
+
+    frame, dyn, st, cs, ep = build_workload(args, sample_n, nb)
+    prop = nb.Propagator.default(dyn)
+    packed = dyn.pack(frame, None)
+    end = int(args.span_days * DAY)
+    cores = pyoracle.num_threads()
+    times, steps = [], 0
+    out = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        out, _, det, status = pyoracle.propagate_batch(packed.c, prop.opts.to_c(prop.method), st, cs, ep, end)
+        times.append(time.perf_counter() - t0)
+        steps = int(det["n_steps"].sum())
+    return {"steps": steps, "times": times, "cores": cores, "final": out, "inputs": (st, cs, ep)}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import nyx_b200 as nb
+
+    workload = (f"C2: {args.n_traj} LEO trajectories/GPU (alt 300 km, e 0.015, i 68.5 deg; N(0, 1 km / 1 m/s) dispersions), "
+                f"two-body + JGM-3 {args.degree}x{args.degree}, adaptive RK89 (IntegratorOptions::default), {args.span_days:g}-day span")
+    fps = flops_per_step(args.degree)
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sample_n = args.cpu_sample
+        for _ in range(max(0, min(args.warmup, 1))):
+            cpu_reference_leg(args, nb, min(sample_n, 32))
+        leg = cpu_reference_leg(args, nb, sample_n, repeats=args.steps)
+        total_t = sum(leg["times"])
+        value = leg["steps"] * args.steps / total_t
+        line = {
+            "impl": "reference", "metric": "trajectory-steps/sec (ensemble)", "value": value, "unit": "trajectory-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "sample": f"{sample_n} trajectories of the same ensemble, full span"},
+            "cpu_baseline": {"value": value, "unit": "trajectory-steps/s", "cores": leg["cores"], "kind": "port",
+                             "sample": f"{sample_n} trajectories x {args.span_days:g} days per step, OpenMP over trajectories"},
+            "e2e": {"value": value, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ nyxb arm (GPU)
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl nyxb needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from nyx_b200.dist import all_gather_final_states, shard_bounds
+
+    n_total = args.n_traj * world  # weak scaling: per-GPU work fixed
+    frame, dyn, st, cs, ep = build_workload(args, n_total, nb)
+    lo, hi = shard_bounds(n_total, world, rank)
+    n = hi - lo
+    mode = nb.MODE_FAST if args.mode == "fast" else nb.MODE_STRICT
+    prop = nb.Propagator.default(dyn, mode=mode, device=local_rank)
+    eng = prop.engine(frame, None)
+    if args.lanes:
+        eng.set_lanes(args.lanes)
+    end = int(args.span_days * DAY)
+
+    # pinned host inputs of this rank's shard (e2e leg) and HBM-resident copies (value leg)
+    h_st = torch.from_numpy(np.ascontiguousarray(st[:, lo:hi])).pin_memory()
+    h_cs = torch.from_numpy(np.ascontiguousarray(cs[:, lo:hi])).pin_memory()
+    h_ep = torch.from_numpy(np.ascontiguousarray(ep[lo:hi])).pin_memory()
+    d_st, d_cs, d_ep = h_st.to(dev), h_cs.to(dev), h_ep.to(dev)
+    d_out = torch.empty((9, n), dtype=torch.float64, device=dev)
+    d_oep = torch.empty(n, dtype=torch.int64, device=dev)
+    d_det = torch.empty(n * 48, dtype=torch.uint8, device=dev)
+    d_status = torch.empty(n, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def one_pass():
+        stream = torch.cuda.current_stream(dev)
+        eng.propagate_batch_dev(n, d_st.data_ptr(), d_cs.data_ptr(), d_ep.data_ptr(), end, None, d_out.data_ptr(),
+                                d_oep.data_ptr(), d_det.data_ptr(), d_status.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            return all_gather_final_states(d_out, n_total)
+        return d_out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        one_pass()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = eng.launch_count()
+    total_ms = 0.0
+    kernel_ms = []
+    barrier()
+    for _ in range(args.steps):
+        flush.fill_(1)  # L2 flush between timed iterations (not timed)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        barrier()
+        e0.record()
+        stream = torch.cuda.current_stream(dev)
+        eng.propagate_batch_dev(n, d_st.data_ptr(), d_cs.data_ptr(), d_ep.data_ptr(), end, None, d_out.data_ptr(),
+                                d_oep.data_ptr(), d_det.data_ptr(), d_status.data_ptr(), stream.cuda_stream)
+        e1.record()
+        if world > 1:
+            all_gather_final_states(d_out, n_total)
+        e2.record()
+        barrier()
+        kernel_ms.append(e0.elapsed_time(e1))
+        total_ms += e0.elapsed_time(e2)
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop()
+
+    det = np.frombuffer(d_det.cpu().numpy().tobytes(), dtype=nb.abi.DETAILS_DTYPE)
+    local_steps = int(det["n_steps"].sum())
+    local_rej = int(det["n_rejected"].sum())
+    ok = int((d_status.cpu().numpy() == 0).sum())
+
+    # ---- e2e: the public host-buffer call (H2D of the inputs + kernel + D2H of results inside the timed region)
+    e2e_t = []
+    for it in range(2 + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        out_h, oep_h, det_h, st_h = eng.propagate_batch(h_st.numpy(), h_cs.numpy(), h_ep.numpy(), end)
+        barrier()
+        if it >= 2:
+            e2e_t.append(time.perf_counter() - t0)
+    e2e_s = float(np.mean(e2e_t))
+
+    # max over ranks / sums over ranks
+    t_dev = torch.tensor([total_ms, e2e_s, float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([local_steps, local_rej, ok, launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    total_ms, e2e_s, kern_ms = (float(v) for v in t_dev.cpu())
+    all_steps, all_rej, all_ok, all_launches = (int(v) for v in cnt.cpu())
+
+    if rank == 0:
+        value = all_steps * args.steps / (total_ms * 1e-3)
+        e2e_value = all_steps / e2e_s
+        # FP64 roofline of the dominant (only) kernel, measured live
+        fp64_peak = eng._lib.nyxb_measure_fp64_tflops(local_rank, 4096)
+        achieved_tf = local_steps * fps / (kern_ms * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_achieved = n * BYTES_PER_TRAJ / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": "trajectory-steps/sec (ensemble)", "value": value, "unit": "trajectory-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "trajectories_total": n_total, "accepted_steps_per_pass": all_steps,
+                       "rejected_attempts_per_pass": all_rej, "ok_trajectories": all_ok, "mode": args.mode,
+                       "lanes_per_trajectory": eng.lanes(), "l2": "flushed between timed iterations (256 MiB write)",
+                       "parallelism": f"ensemble-sharded x{world}, one all-gather of final states"},
+            "e2e": {"value": e2e_value, "unit": "trajectory-steps/s", "h2d_bytes_per_step": n * (13 * 8 + 8) * world,
+                    "d2h_bytes_per_step": n * (9 * 8 + 8 + 48 + 4) * world, "ms_per_step": e2e_s * 1e3},
+            "gpu_launches": all_launches,
+            "clocks": clocks,
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None, "traffic": None,
+                         "note": "FP64-pipe bound (no tensor-core or HBM-bound work on this path); peak = live DFMA probe "
+                                 f"(nyxb_measure_fp64_tflops); algorithmic {fps:.0f} flop per accepted step",
+                         "kernel_ms": kern_ms},
+            "roofline_hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": hbm_achieved / hbm_peak, "of": "measured" if peaks else "fallback",
+                             "note": f"{BYTES_PER_TRAJ} algorithmic bytes per trajectory, independent of step count"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            leg = cpu_reference_leg(args, nb, min(args.cpu_sample, n))
+            sample_n = min(args.cpu_sample, n)
+            cpu_value = leg["steps"] / leg["times"][0]
+            dr = np.sqrt(((out_h[:3, :sample_n] - leg["final"][:3]) ** 2).sum(0))
+            dv = np.sqrt(((out_h[3:6, :sample_n] - leg["final"][3:6]) ** 2).sum(0))
+            line["cpu_baseline"] = {"value": cpu_value, "unit": "trajectory-steps/s", "cores": leg["cores"], "kind": "port",
+                                    "sample": f"first {sample_n} trajectories of the same ensemble, full {args.span_days:g}-day span, "
+                                              f"{leg['times'][0]:.1f} s"}
+            line["max_dr_km"] = float(dr.max())
+            line["max_dv_km_s"] = float(dv.max())
+            line["parity_sample"] = sample_n
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

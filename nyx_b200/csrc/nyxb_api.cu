@@ -1,0 +1,350 @@
+// nyxb_api.cu — C-ABI implementation (include/nyxb.h): engine lifetime, table packing and
+// upload, launches.  Host side of `Propagator::new` + `MonteCarlo::run_until_epoch`'s fan-out.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "nyxb_device.cuh"
+#include "nyxb_tableaux.h"
+
+// kernels (nyxb_kernels.cu built twice, nyxb_coop.cu)
+extern "C" cudaError_t nyxb_launch_thread_strict(const DevSetup*, size_t, const double*, const double*, const long long*,
+                                                 long long, long long*, double*, long long*, nyxb_details*, int*, int,
+                                                 cudaStream_t);
+extern "C" cudaError_t nyxb_launch_thread_fast(const DevSetup*, size_t, const double*, const double*, const long long*,
+                                               long long, long long*, double*, long long*, nyxb_details*, int*, int,
+                                               cudaStream_t);
+extern "C" cudaError_t nyxb_launch_coop(const DevSetup*, int lanes, size_t, const double*, const double*, const long long*,
+                                        long long, long long*, double*, long long*, nyxb_details*, int*, cudaStream_t);
+extern "C" int nyxb_coop_supported(const DevSetup*, int lanes);
+extern "C" double nyxb_fp64_probe(int device, int iters);
+
+static thread_local std::string g_err;
+static void set_err(const std::string& s) { g_err = s; }
+#define CUDA_TRY(x)                                                                                   \
+    do {                                                                                              \
+        cudaError_t _e = (x);                                                                         \
+        if (_e != cudaSuccess) {                                                                      \
+            set_err(std::string(#x) + ": " + cudaGetErrorString(_e));                                 \
+            return NYXB_RC_CUDA;                                                                      \
+        }                                                                                             \
+    } while (0)
+
+struct nyxb_engine {
+    int device = 0;
+    int mode = NYXB_MODE_STRICT;
+    int lanes = 0;  // 0 = auto
+    DevSetup S;
+    std::vector<void*> dev_allocs;
+    long long launches = 0;
+    double last_ms = 0.0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ~nyxb_engine() {
+        for (void* p : dev_allocs) cudaFree(p);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+    }
+};
+
+static bool tableau_for(int method, int& order, int& stages, const double*& a, const double*& b) {
+    switch (method) {  // rk_methods/mod.rs:81-133
+    case NYXB_RK89: order = 9; stages = 16; a = NYXB_RK89_A; b = NYXB_RK89_B; return true;
+    case NYXB_DP78: order = 8; stages = 13; a = NYXB_DP78_A; b = NYXB_DP78_B; return true;
+    case NYXB_DP45: order = 5; stages = 7; a = NYXB_DP45_A; b = NYXB_DP45_B; return true;
+    case NYXB_RK4: order = 4; stages = 4; a = NYXB_RK4_A; b = NYXB_RK4_B; return true;
+    case NYXB_CK45: order = 5; stages = 6; a = NYXB_CK45_A; b = NYXB_CK45_B; return true;
+    case NYXB_V56: order = 6; stages = 8; a = NYXB_V56_A; b = NYXB_V56_B; return true;
+    default: return false;
+    }
+}
+
+static double host_dur_to_seconds(long long total_ns) {
+    const long long NPC = 3155760000000000000LL, NPS = 1000000000LL;
+    long long cent = total_ns / NPC;
+    if (total_ns % NPC < 0) cent -= 1;
+    long long nanos = total_ns - cent * NPC;
+    volatile double s = (double)(nanos / NPS);
+    volatile double f = (double)(nanos % NPS) * 1e-9;
+    if (cent == 0) return s + f;
+    volatile double c = (double)cent * 3155760000.0;
+    volatile double cs = c + s;
+    return cs + f;
+}
+
+static DevRotation pack_rot(const nyxb_rotation& r) {
+    DevRotation d;
+    d.kind = r.kind;
+    d.ra0 = r.ra0_deg; d.ra1 = r.ra1_deg_cy; d.dec0 = r.dec0_deg; d.dec1 = r.dec1_deg_cy; d.w0 = r.w0_deg; d.w1 = r.w1_deg_day;
+    volatile double w = r.w1_deg_day * 1.7453292519943295e-2;
+    d.wdot = (r.kind == 0) ? 0.0 : w / 86400.0;
+    return d;
+}
+
+template <typename T>
+static T* upload(nyxb_engine* e, const T* host, size_t count) {
+    T* d = nullptr;
+    if (cudaMalloc(&d, sizeof(T) * (count ? count : 1)) != cudaSuccess) return nullptr;
+    e->dev_allocs.push_back(d);
+    if (count && cudaMemcpy(d, host, sizeof(T) * count, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    return d;
+}
+
+extern "C" nyxb_engine* nyxb_engine_create(const nyxb_dynamics* dyn, const nyxb_integ_opts* opts, int32_t mode,
+                                            int32_t device) {
+    if (!dyn || !opts) { set_err("null dynamics/options"); return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_err("no CUDA device available: nyxb has no CPU fallback");
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) { set_err("bad device ordinal"); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { set_err("cudaSetDevice failed"); return nullptr; }
+    if (mode != NYXB_MODE_STRICT && mode != NYXB_MODE_FAST) { set_err("bad mode"); return nullptr; }
+    if (dyn->n_bodies < 0 || dyn->n_bodies > NYXB_MAX_BODIES) { set_err("n_bodies out of range"); return nullptr; }
+
+    nyxb_engine* e = new nyxb_engine();
+    e->device = device;
+    e->mode = mode;
+    DevSetup& S = e->S;
+    memset(&S, 0, sizeof(S));
+
+    // ---- tableau (dense rows, c accumulated left to right as instance.rs:379-386 does)
+    int order, stages;
+    const double *a, *b;
+    if (!tableau_for(opts->method, order, stages, a, b)) { set_err("unknown integration method"); delete e; return nullptr; }
+    S.tb.stages = stages;
+    S.tb.order = order;
+    int idx = 0;
+    for (int i = 0; i < stages - 1; ++i) {
+        volatile double ci = 0.0;
+        for (int j = 0; j <= i; ++j) {
+            double aij = a[idx++];
+            ci = ci + aij;
+            S.tb.a[i * NYXB_MAX_STAGES + j] = aij;
+        }
+        S.tb.c[i] = ci;
+    }
+    for (int i = 0; i < stages; ++i) {
+        S.tb.b[i] = b[i];
+        volatile double d = b[i] - b[i + stages];
+        S.tb.e[i] = d;
+    }
+    S.error_ctrl = opts->error_ctrl;
+    S.attempts = opts->attempts;
+    S.fixed_step = opts->fixed_step;
+    S.init_step_ns = opts->init_step_ns;
+    S.min_step_ns = opts->min_step_ns;
+    S.max_step_ns = opts->max_step_ns;
+    S.tolerance = opts->tolerance;
+    S.min_step_s = host_dur_to_seconds(opts->min_step_ns);
+    S.max_step_s = host_dur_to_seconds(opts->max_step_ns);
+    S.inv_order = 1.0 / (double)order;
+    S.inv_order_m1 = 1.0 / (double)(order - 1);
+
+    // ---- dynamics
+    S.mu_central = dyn->mu_central_km3_s2;
+    S.central_radius = dyn->central_radius_km;
+    S.n_bodies = dyn->n_bodies;
+    S.point_mass_mask = dyn->point_mass_mask;
+    for (int j = 0; j < dyn->n_bodies; ++j) {
+        const nyxb_body& hb = dyn->bodies[j];
+        DevBody& db = S.bodies[j];
+        db.mu = hb.mu_km3_s2; db.radius = hb.radius_km; db.t0_ns = hb.t0_ns; db.interval_ns = hb.interval_ns;
+        db.n_intervals = hb.n_intervals; db.n_coeffs = hb.n_coeffs;
+        db.inv_interval = 1.0 / (double)hb.interval_ns;
+        db.coeffs = upload(e, hb.coeffs, (size_t)hb.n_intervals * 3 * hb.n_coeffs);
+        if (!db.coeffs) { set_err("ephemeris upload failed"); delete e; return nullptr; }
+    }
+    if (dyn->gravity) {
+        const nyxb_gravity_field& g = *dyn->gravity;
+        if (g.degree < 1 || g.degree > NYXB_MAX_DEGREE || g.order < 0 || g.order > g.degree) {
+            set_err("gravity field degree/order out of range (1..96)"); delete e; return nullptr;
+        }
+        const int N = g.degree, np2 = N + 2;
+        S.has_grav = 1;
+        S.grav.N = N; S.grav.M = g.order; S.grav.mu = g.mu_km3_s2; S.grav.r_eq = g.r_eq_km;
+        S.grav.rot = pack_rot(g.rot);
+        // GravityField::new gravity_field.rs:52-92 (same formulas; sqrt and / are correctly rounded)
+        std::vector<double> adiag(N + 3), offd(N + 2);
+        adiag[0] = 1.0;
+        for (int n = 1; n <= np2; ++n) {
+            double nf = (double)n;
+            volatile double t = 1.0 + 1.0 / (2.0 * nf);
+            volatile double s = std::sqrt(t);
+            volatile double v = s * adiag[n - 1];
+            adiag[n] = v;
+        }
+        for (int n = 0; n <= N + 1; ++n) offd[n] = std::sqrt(2.0 * (double)n + 3.0);
+        std::vector<DevHarm> tab((size_t)(N + 2) * (N + 3) / 2);
+        const double sqrt2 = std::sqrt(2.0);
+        for (int n = 0; n <= N + 1; ++n) {
+            for (int m = 0; m <= n; ++m) {
+                double nf = (double)n, mf = (double)m;
+                DevHarm h;
+                volatile double cnum = (2.0 * nf + 1.0) * (nf + mf - 1.0) * (nf - mf - 1.0);
+                volatile double cden = (nf - mf) * (nf + mf) * (2.0 * nf - 3.0);
+                volatile double cq = cnum / cden;
+                h.c = std::sqrt(cq);
+                volatile double bnum = (2.0 * nf + 1.0) * (2.0 * nf - 1.0);
+                volatile double bden = (nf + mf) * (nf - mf);
+                volatile double bq = bnum / bden;
+                h.b = std::sqrt(bq);
+                volatile double v01 = (nf - mf) * (nf + mf + 1.0);
+                h.vr01 = std::sqrt(v01);
+                volatile double v11n = (2.0 * nf + 1.0) * (nf + mf + 2.0) * (nf + mf + 1.0);
+                volatile double v11 = v11n / (2.0 * nf + 3.0);
+                h.vr11 = std::sqrt(v11);
+                if (m == 0) { h.vr01 = h.vr01 / sqrt2; h.vr11 = h.vr11 / sqrt2; }
+                if (n <= N) { h.cbar = g.c_nm[(size_t)n * (N + 1) + m]; h.sbar = g.s_nm[(size_t)n * (N + 1) + m]; }
+                else { h.cbar = 0.0; h.sbar = 0.0; }
+                if (!(n >= m + 2)) { h.b = 0.0; h.c = 0.0; }  // never read; avoid NaN/inf noise
+                tab[(size_t)n * (n + 1) / 2 + m] = h;
+            }
+        }
+        S.grav.tab = upload(e, tab.data(), tab.size());
+        S.grav.a_diag = upload(e, adiag.data(), adiag.size());
+        S.grav.offdiag = upload(e, offd.data(), offd.size());
+        if (!S.grav.tab || !S.grav.a_diag || !S.grav.offdiag) { set_err("gravity table upload failed"); delete e; return nullptr; }
+    }
+    if (dyn->srp) {
+        const nyxb_srp& s = *dyn->srp;
+        if (s.sun_body < 0 || s.sun_body >= dyn->n_bodies || s.n_shadow < 0 || s.n_shadow > 4) {
+            set_err("bad SRP descriptor"); delete e; return nullptr;
+        }
+        S.has_srp = 1;
+        S.srp.phi = s.phi_w_m2; S.srp.sun_body = s.sun_body; S.srp.n_shadow = s.n_shadow;
+        for (int q = 0; q < 4; ++q) {
+            S.srp.shadow_body[q] = s.shadow_body[q];
+            if (q < s.n_shadow && s.shadow_body[q] != NYXB_CENTRAL_BODY && (s.shadow_body[q] < 0 || s.shadow_body[q] >= dyn->n_bodies)) {
+                set_err("bad shadow body index"); delete e; return nullptr;
+            }
+        }
+    }
+    if (dyn->drag) {
+        const nyxb_drag& d = *dyn->drag;
+        S.has_drag = 1;
+        S.drag.density = d.density; S.drag.rho0 = d.rho0; S.drag.r0 = d.r0; S.drag.ref_alt_m = d.ref_alt_m; S.drag.r_eq = d.r_eq_km;
+        S.drag.rot = pack_rot(d.rot);
+    }
+    cudaEventCreate(&e->ev0);
+    cudaEventCreate(&e->ev1);
+    return e;
+}
+
+extern "C" void nyxb_engine_destroy(nyxb_engine* eng) {
+    if (!eng) return;
+    cudaSetDevice(eng->device);
+    delete eng;
+}
+
+static int pick_lanes(const nyxb_engine* e, size_t n) {
+    if (e->mode == NYXB_MODE_STRICT) return 1;
+    if (e->lanes > 0) return e->lanes;
+    // auto: cooperative lanes only pay off when the harmonic sum dominates
+    if (!e->S.has_grav || e->S.grav.N < 8) return 1;
+    int lanes = (e->S.grav.N >= 40) ? 32 : 16;
+    (void)n;
+    while (lanes > 1 && !nyxb_coop_supported(&e->S, lanes)) lanes >>= 1;
+    return lanes;
+}
+
+static int32_t launch(nyxb_engine* e, size_t n, const double* state, const double* consts, const int64_t* epoch0,
+                      int64_t end_epoch, int64_t* step_io, double* out_state, int64_t* out_epoch,
+                      nyxb_details* out_details, int32_t* out_status, cudaStream_t stream) {
+    int lanes = pick_lanes(e, n);
+    cudaError_t err;
+    if (lanes > 1) {
+        err = nyxb_launch_coop(&e->S, lanes, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io,
+                               out_state, (long long*)out_epoch, out_details, out_status, stream);
+    } else if (e->mode == NYXB_MODE_STRICT) {
+        err = nyxb_launch_thread_strict(&e->S, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io,
+                                        out_state, (long long*)out_epoch, out_details, out_status, 64, stream);
+    } else {
+        err = nyxb_launch_thread_fast(&e->S, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io,
+                                      out_state, (long long*)out_epoch, out_details, out_status, 64, stream);
+    }
+    if (err != cudaSuccess) { set_err(std::string("kernel launch: ") + cudaGetErrorString(err)); return NYXB_RC_CUDA; }
+    e->launches += 1;
+    return NYXB_RC_OK;
+}
+
+extern "C" int32_t nyxb_propagate_batch_dev(nyxb_engine* eng, size_t n, const double* state_soa, const double* consts_soa,
+                                            const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
+                                            double* out_state_soa, int64_t* out_epoch_ns, nyxb_details* out_details,
+                                            int32_t* out_status, void* cuda_stream) {
+    if (!eng || !state_soa || !consts_soa || !epoch0_ns || !out_state_soa || !out_epoch_ns || !out_status) {
+        set_err("null argument");
+        return NYXB_RC_BAD_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(eng->device));
+    return launch(eng, n, state_soa, consts_soa, epoch0_ns, end_epoch_ns, step_ns, out_state_soa, out_epoch_ns, out_details,
+                  out_status, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int32_t nyxb_propagate_batch(nyxb_engine* eng, size_t n, const double* state_soa, const double* consts_soa,
+                                        const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
+                                        double* out_state_soa, int64_t* out_epoch_ns, nyxb_details* out_details,
+                                        int32_t* out_status) {
+    if (!eng || !state_soa || !consts_soa || !epoch0_ns || !out_state_soa || !out_epoch_ns || !out_status) {
+        set_err("null argument");
+        return NYXB_RC_BAD_ARG;
+    }
+    if (n == 0) return NYXB_RC_OK;
+    CUDA_TRY(cudaSetDevice(eng->device));
+    // one device slab: [state 9n | consts 4n | out_state 9n] doubles, [epoch0 n | out_epoch n | step n] i64, details, status
+    double* d_f64 = nullptr;
+    long long* d_i64 = nullptr;
+    nyxb_details* d_det = nullptr;
+    int* d_status = nullptr;
+    cudaStream_t st = 0;
+    int32_t rc = NYXB_RC_OK;
+    cudaError_t ce;
+#define TRY2(x) do { ce = (x); if (ce != cudaSuccess) { set_err(std::string(#x) + ": " + cudaGetErrorString(ce)); rc = NYXB_RC_CUDA; goto done; } } while (0)
+    TRY2(cudaMalloc(&d_f64, sizeof(double) * 22 * n));
+    TRY2(cudaMalloc(&d_i64, sizeof(long long) * 3 * n));
+    TRY2(cudaMalloc(&d_det, sizeof(nyxb_details) * n));
+    TRY2(cudaMalloc(&d_status, sizeof(int) * n));
+    TRY2(cudaMemcpyAsync(d_f64, state_soa, sizeof(double) * 9 * n, cudaMemcpyHostToDevice, st));
+    TRY2(cudaMemcpyAsync(d_f64 + 9 * n, consts_soa, sizeof(double) * 4 * n, cudaMemcpyHostToDevice, st));
+    TRY2(cudaMemcpyAsync(d_i64, epoch0_ns, sizeof(long long) * n, cudaMemcpyHostToDevice, st));
+    if (step_ns) TRY2(cudaMemcpyAsync(d_i64 + 2 * n, step_ns, sizeof(long long) * n, cudaMemcpyHostToDevice, st));
+    TRY2(cudaEventRecord(eng->ev0, st));
+    rc = launch(eng, n, d_f64, d_f64 + 9 * n, (const int64_t*)d_i64, end_epoch_ns, step_ns ? (int64_t*)(d_i64 + 2 * n) : nullptr,
+                d_f64 + 13 * n, (int64_t*)(d_i64 + n), d_det, d_status, st);
+    if (rc != NYXB_RC_OK) goto done;
+    TRY2(cudaEventRecord(eng->ev1, st));
+    TRY2(cudaMemcpyAsync(out_state_soa, d_f64 + 13 * n, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost, st));
+    TRY2(cudaMemcpyAsync(out_epoch_ns, d_i64 + n, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+    if (step_ns) TRY2(cudaMemcpyAsync(step_ns, d_i64 + 2 * n, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+    if (out_details) TRY2(cudaMemcpyAsync(out_details, d_det, sizeof(nyxb_details) * n, cudaMemcpyDeviceToHost, st));
+    TRY2(cudaMemcpyAsync(out_status, d_status, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    TRY2(cudaStreamSynchronize(st));
+    {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, eng->ev0, eng->ev1) == cudaSuccess) eng->last_ms = ms;
+    }
+done:
+    cudaFree(d_f64); cudaFree(d_i64); cudaFree(d_det); cudaFree(d_status);
+    return rc;
+#undef TRY2
+}
+
+extern "C" int32_t nyxb_engine_set_lanes(nyxb_engine* eng, int32_t lanes) {
+    if (!eng) return NYXB_RC_BAD_ARG;
+    if (lanes != 0 && lanes != 1 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) { set_err("lanes must be 0,1,4,8,16,32"); return NYXB_RC_BAD_ARG; }
+    if (lanes > 1 && (eng->mode == NYXB_MODE_STRICT || !nyxb_coop_supported(&eng->S, lanes))) {
+        set_err("cooperative lanes unsupported for this engine (strict mode or no gravity field)");
+        return NYXB_RC_UNSUPPORTED;
+    }
+    eng->lanes = lanes;
+    return NYXB_RC_OK;
+}
+extern "C" int32_t nyxb_engine_get_lanes(const nyxb_engine* eng) { return eng ? pick_lanes(eng, 0) : 0; }
+extern "C" int64_t nyxb_engine_launch_count(const nyxb_engine* eng) { return eng ? eng->launches : 0; }
+extern "C" double nyxb_engine_last_kernel_ms(const nyxb_engine* eng) { return eng ? eng->last_ms : 0.0; }
+extern "C" double nyxb_measure_fp64_tflops(int32_t device, int32_t iters) { return nyxb_fp64_probe(device, iters); }
+extern "C" int32_t nyxb_abi_version(void) { return NYXB_ABI_VERSION; }
+extern "C" const char* nyxb_last_error(void) { return g_err.c_str(); }

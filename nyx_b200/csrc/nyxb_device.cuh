@@ -1,0 +1,466 @@
+// nyxb_device.cuh — device-side data model and right-hand side (force models) of the
+// B200 batched propagator.  Shared by the per-thread kernel (nyxb_kernels.cu, built twice:
+// STRICT = no FMA contraction / reference operation order, FAST = FMA allowed) and by the
+// lane-cooperative kernel (nyxb_coop.cu).
+//
+// Reference behaviour implemented here (paths relative to /root/reference/nyx-core/src):
+//   SpacecraftDynamics::eom   dynamics/spacecraft.rs:191-310
+//   OrbitalDynamics::eom      dynamics/orbital.rs:80-114
+//   PointMasses::eom          dynamics/orbital.rs:213-247
+//   GravityField::eom         dynamics/gravity_field.rs:148-268
+//   SolarPressure::eom        dynamics/solarpressure.rs:135-165 (+ cosmic/eclipse.rs:69-83)
+//   Drag::eom                 dynamics/drag.rs:181-284
+//   ErrorControl::estimate    propagators/error_ctrl.rs:79-230
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/nyxb.h"
+
+#define NYXB_MAX_STAGES 16
+#define NYXB_MAX_DEGREE 96 /* rows of the per-thread Legendre scratch: degree + 3 <= 99 */
+
+struct DevRotation {
+    int kind;
+    double ra0, ra1, dec0, dec1, w0, w1;  // degrees
+    double wdot;                           // rad/s
+};
+
+struct DevBody {
+    double mu, radius;
+    long long t0_ns, interval_ns;
+    int n_intervals, n_coeffs;
+    const double* coeffs;  // device [n_intervals][3][n_coeffs]
+    double inv_interval;   // 1.0 / (double)interval_ns (FAST mode only)
+};
+
+// One record per (n, m), m <= n, n <= N+1, triangular index n(n+1)/2 + m.
+struct __align__(16) DevHarm {
+    double b, c;        // recursion factors   gravity_field.rs:69-81
+    double vr01, vr11;  //                     gravity_field.rs:83-90
+    double cbar, sbar;  // normalised coefficients (0 beyond N / beyond `order`)
+};
+
+struct DevGrav {
+    int N, M;
+    double mu, r_eq;
+    DevRotation rot;
+    const DevHarm* tab;      // (N+2)(N+3)/2 records
+    const double* a_diag;    // [N+3]   gravity_field.rs:61-66
+    const double* offdiag;   // [N+2]   sqrt(2n+3), n = 0..N+1   gravity_field.rs:168-173
+};
+
+struct DevSrp {
+    double phi;
+    int sun_body, n_shadow;
+    int shadow_body[4];
+};
+
+struct DevDrag {
+    int density;
+    double rho0, r0, ref_alt_m, r_eq;
+    DevRotation rot;
+};
+
+struct DevTableau {
+    int stages, order;
+    double a[NYXB_MAX_STAGES * NYXB_MAX_STAGES];  // dense, row i (stage i+1) uses a[i*16 + j], j <= i
+    double c[NYXB_MAX_STAGES];                    // c[i] = sum_j a_ij accumulated left to right (instance.rs:379-386)
+    double b[NYXB_MAX_STAGES];
+    double e[NYXB_MAX_STAGES];                    // b_i - b*_i
+};
+
+struct DevSetup {
+    // integrator
+    DevTableau tb;
+    int error_ctrl, attempts, fixed_step;
+    long long init_step_ns, min_step_ns, max_step_ns;
+    double tolerance, min_step_s, max_step_s;
+    double inv_order, inv_order_m1;
+    // dynamics
+    double mu_central, central_radius;
+    int n_bodies;
+    unsigned point_mass_mask;
+    DevBody bodies[NYXB_MAX_BODIES];
+    int has_grav, has_srp, has_drag;
+    DevGrav grav;
+    DevSrp srp;
+    DevDrag drag;
+};
+
+#define NYXB_NS_PER_S 1000000000LL
+#define NYXB_NS_PER_CENTURY 3155760000000000000LL
+
+// hifitime Duration::to_seconds (see oracle/nyx_oracle.c for the pinning)
+__device__ __forceinline__ double dur_to_seconds(long long total_ns) {
+    long long cent = total_ns / NYXB_NS_PER_CENTURY;
+    if (total_ns % NYXB_NS_PER_CENTURY < 0) cent -= 1;
+    long long nanos = total_ns - cent * NYXB_NS_PER_CENTURY;
+    long long sec = nanos / NYXB_NS_PER_S;
+    long long sub = nanos - sec * NYXB_NS_PER_S;
+    double s = __dadd_rn((double)sec, __dmul_rn((double)sub, 1e-9));
+    if (cent == 0) return s;
+    return __dadd_rn(__dadd_rn(__dmul_rn((double)cent, 3155760000.0), (double)sec), __dmul_rn((double)sub, 1e-9));
+}
+
+// f64 * Unit::Second -> Duration: truncation toward zero, NaN -> 0, saturating
+__device__ __forceinline__ long long dur_from_seconds(double s) {
+    double ns = __dmul_rn(s, 1e9);
+    if (ns != ns) return 0;
+    if (ns >= 9.2e18) return 0x7fffffffffffffffLL;
+    if (ns <= -9.2e18) return (long long)0x8000000000000000ULL;
+    return (long long)ns;  // cvt.rzi
+}
+
+__device__ __forceinline__ double norm3(double x, double y, double z) {
+#if NYXB_STRICT
+    return sqrt((x * x + y * y) + z * z);  // nalgebra order; -fmad=false build
+#else
+    return sqrt(fma(z, z, fma(y, y, x * x)));
+#endif
+}
+
+// Deterministic sin/cos: same operation sequence as oracle/nyx_oracle.c::nyx_oracle_sincos.
+__device__ __forceinline__ void det_sincos(double x, double& s, double& c) {
+    const double two_over_pi = 6.36619772367581382433e-01;
+    const double p1 = 1.57079632673412561417e+00;
+    const double p2 = 6.07710050630396597660e-11;
+    const double p3 = 2.02226624879595063154e-21;
+    double kf = rint(x * two_over_pi);
+    double r = ((x - kf * p1) - kf * p2) - kf * p3;
+    double z = r * r;
+    double ps = -1.66666666666666324348e-01 + z * (8.33333333332248946124e-03 + z * (-1.98412698298579493134e-04 + z * (2.75573137070700676789e-06 + z * (-2.50507602534068634195e-08 + z * 1.58969099521155010221e-10))));
+    double sn = r + (r * z) * ps;
+    double pc = 4.16666666666666019037e-02 + z * (-1.38888888888741095749e-03 + z * (2.48015872894767294178e-05 + z * (-2.75573143513906633035e-07 + z * (2.08757232129817482790e-09 + z * -1.13596475577881948265e-11))));
+    double cs = (1.0 - 0.5 * z) + (z * z) * pc;
+    long long k = (long long)kf;
+    switch (k & 3) {
+    case 0: s = sn; c = cs; break;
+    case 1: s = cs; c = -sn; break;
+    case 2: s = -sn; c = -cs; break;
+    default: s = -cs; c = sn; break;
+    }
+}
+
+#define NYXB_DEG2RAD 1.7453292519943295e-2
+
+// inertial -> body-fixed DCM (row-major R[9]) of the orientation model in nyxb.h
+__device__ __forceinline__ void rotation_dcm(const DevRotation& rot, long long t_ns, double R[9]) {
+    if (rot.kind == 0) {
+        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+        return;
+    }
+    double t_s = dur_to_seconds(t_ns);
+    double d = t_s / 86400.0;
+    double T = d / 36525.0;
+    double ra = (rot.ra0 + rot.ra1 * T) * NYXB_DEG2RAD;
+    double dec = (rot.dec0 + rot.dec1 * T) * NYXB_DEG2RAD;
+    double w = fmod(rot.w0 + rot.w1 * d, 360.0) * NYXB_DEG2RAD;
+    double sa, ca, sd, cd, sw, cw;
+    det_sincos(ra, sa, ca);
+    det_sincos(dec, sd, cd);
+    det_sincos(w, sw, cw);
+    double b00 = -sa, b01 = ca, b02 = 0.0;
+    double b10 = -(sd * ca), b11 = -(sd * sa), b12 = cd;
+    double b20 = cd * ca, b21 = cd * sa, b22 = sd;
+    R[0] = cw * b00 + sw * b10; R[1] = cw * b01 + sw * b11; R[2] = cw * b02 + sw * b12;
+    R[3] = cw * b10 - sw * b00; R[4] = cw * b11 - sw * b01; R[5] = cw * b12 - sw * b02;
+    R[6] = b20; R[7] = b21; R[8] = b22;
+}
+
+// Piecewise-Chebyshev body position (Clenshaw); returns false when outside coverage.
+__device__ __forceinline__ bool body_position(const DevBody& b, long long t_ns, double pos[3]) {
+    long long dt = t_ns - b.t0_ns;
+    if (dt < 0) return false;
+    long long idx = dt / b.interval_ns;
+    if (idx >= b.n_intervals) return false;
+    long long off = dt - idx * b.interval_ns;
+    double tau = 2.0 * ((double)off / (double)b.interval_ns) - 1.0;
+    double tau2 = 2.0 * tau;
+    int nc = b.n_coeffs;
+    const double* c = b.coeffs + (size_t)idx * 3 * (size_t)nc;
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        const double* ca = c + ax * nc;
+        double b1 = 0.0, b2 = 0.0;
+        for (int k = nc - 1; k >= 1; --k) {
+            double bk = (tau2 * b1 - b2) + __ldg(ca + k);
+            b2 = b1; b1 = bk;
+        }
+        pos[ax] = (tau * b1 - b2) + __ldg(ca);
+    }
+    return true;
+}
+
+// anise `occultation` restated (see oracle/nyx_oracle.c::nyx_oracle_occultation)
+__device__ __forceinline__ double circ_seg_area(double r, double d) {
+    return (r * r) * acos(d / r) - d * sqrt(r * r - d * d);
+}
+
+__device__ inline double occultation(const double r_eb[3], const double r_ls[3], double light_radius, double body_radius) {
+    double n_ls = norm3(r_ls[0], r_ls[1], r_ls[2]), n_eb = norm3(r_eb[0], r_eb[1], r_eb[2]);
+    double r_ls_prime = (light_radius >= n_ls) ? light_radius : asin(light_radius / n_ls);
+    double r_fobj_prime = (body_radius >= n_eb) ? body_radius : asin(body_radius / n_eb);
+    double dot = (r_ls[0] * r_eb[0] + r_ls[1] * r_eb[1]) + r_ls[2] * r_eb[2];
+    double d_prime = acos(-dot / (n_eb * n_ls));
+    if (d_prime - r_ls_prime > r_fobj_prime) return 0.0;
+    if (r_fobj_prime > d_prime + r_ls_prime) return 1.0;
+    if (fabs(r_ls_prime - r_fobj_prime) < d_prime && d_prime < r_ls_prime + r_fobj_prime) {
+        double d1 = (d_prime * d_prime - r_ls_prime * r_ls_prime + r_fobj_prime * r_fobj_prime) / (2.0 * d_prime);
+        double d2 = (d_prime * d_prime + r_ls_prime * r_ls_prime - r_fobj_prime * r_fobj_prime) / (2.0 * d_prime);
+        double shadow_area = circ_seg_area(r_fobj_prime, d1) + circ_seg_area(r_ls_prime, d2);
+        if (shadow_area != shadow_area) return 1.0;
+        double nominal_area = 3.14159265358979323846 * (r_ls_prime * r_ls_prime);
+        return shadow_area / nominal_area;
+    }
+    return (r_fobj_prime * r_fobj_prime) / (r_ls_prime * r_ls_prime);
+}
+
+__device__ __forceinline__ int tri(int n, int m) { return n * (n + 1) / 2 + m; }
+
+// GravityField::eom (gravity_field.rs:148-268) — reference summation order, per-thread
+// rolling rows of the derived-Legendre matrix: P = row n, Q = row n+1 (Q is overwritten
+// in place from row n-1).  Only the values are rolled; every A[n][m] equals the
+// reference's column-recursion value bit for bit (same recurrence, same operands).
+__device__ inline void grav_accel_rows(const DevGrav& g, long long t_ns, const double r_in[3], double acc[3]) {
+    const int N = g.N, M = g.M;
+    double R[9];
+    rotation_dcm(g.rot, t_ns, R);
+    double rb[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) rb[i] = (R[3 * i] * r_in[0] + R[3 * i + 1] * r_in[1]) + R[3 * i + 2] * r_in[2];
+    double r_ = norm3(rb[0], rb[1], rb[2]);
+    double s_ = rb[0] / r_, t_ = rb[1] / r_, u_ = rb[2] / r_;
+
+    double rowA[NYXB_MAX_DEGREE + 3], rowB[NYXB_MAX_DEGREE + 3];
+    double r_m[NYXB_MAX_DEGREE + 1], i_m[NYXB_MAX_DEGREE + 1];
+    double* P = rowA;  // row n
+    double* Q = rowB;  // row n-1, becomes row n+1
+    for (int m = 0; m <= N + 2; ++m) { rowA[m] = 0.0; rowB[m] = 0.0; }
+    // row 0 and row 1 (gravity_field.rs:61-66, 168)
+    Q[0] = 1.0;
+    P[0] = u_ * sqrt(3.0);
+    P[1] = __ldg(g.a_diag + 1);
+    const int mm = N < M ? N : M;
+    r_m[0] = 1.0; i_m[0] = 0.0;
+    for (int m = 1; m <= mm; ++m) {
+        r_m[m] = s_ * r_m[m - 1] - t_ * i_m[m - 1];
+        i_m[m] = s_ * i_m[m - 1] + t_ * r_m[m - 1];
+    }
+    double rho = g.r_eq / r_;
+    double rho_np1 = g.mu / r_ * rho;
+    double a4x = 0.0, a4y = 0.0, a4z = 0.0, a4w = 0.0;
+    const double sqrt2 = sqrt(2.0);
+    for (int n = 1; n <= N; ++n) {
+        // ---- build row n+1 into Q (holds row n-1): gravity_field.rs:168-181
+        {
+            const int np1 = n + 1;
+            const DevHarm* trow = g.tab + tri(np1, 0);
+            int mrec = np1 - 2;  // m <= (n+1) - 2
+            if (mrec > M + 1) mrec = M + 1;
+            for (int m = 0; m <= mrec; ++m) {
+                double bb = __ldg(&trow[m].b), cc = __ldg(&trow[m].c);
+                Q[m] = u_ * bb * P[m] - cc * Q[m];
+            }
+            for (int m = mrec + 1; m <= np1 - 2; ++m) Q[m] = 0.0;  // never read (m > M+1)
+            Q[n] = __ldg(g.offdiag + n) * u_ * __ldg(g.a_diag + n);  // A[n+1][n]
+            Q[np1] = __ldg(g.a_diag + np1);                           // A[n+1][n+1]
+        }
+        // ---- degree-n partial sums: gravity_field.rs:217-249
+        double sx = 0.0, sy = 0.0, sz = 0.0, sw = 0.0;
+        rho_np1 *= rho;
+        const DevHarm* trow = g.tab + tri(n, 0);
+        int mtop = n < M ? n : M;
+        for (int m = 0; m <= mtop; ++m) {
+            double cv = __ldg(&trow[m].cbar), sv = __ldg(&trow[m].sbar);
+            double d_ = (cv * r_m[m] + sv * i_m[m]) * sqrt2;
+            double e_ = 0.0, f_ = 0.0;
+            if (m != 0) {
+                e_ = (cv * r_m[m - 1] + sv * i_m[m - 1]) * sqrt2;
+                f_ = (sv * r_m[m - 1] - cv * i_m[m - 1]) * sqrt2;
+            }
+            double anm = P[m];
+            sx += (double)m * anm * e_;
+            sy += (double)m * anm * f_;
+            sz += __ldg(&trow[m].vr01) * P[m + 1] * d_;
+            sw -= __ldg(&trow[m].vr11) * Q[m + 1] * d_;
+        }
+        double rr = rho_np1 / g.r_eq;
+        a4x += rr * sx; a4y += rr * sy; a4z += rr * sz; a4w += rr * sw;
+        // roll: row n+1 becomes row n, row n becomes row n-1
+        double* tmp = P; P = Q; Q = tmp;
+    }
+    double ab0 = a4x + a4w * s_, ab1 = a4y + a4w * t_, ab2 = a4z + a4w * u_;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) acc[i] = (R[i] * ab0 + R[3 + i] * ab1) + R[6 + i] * ab2;
+}
+
+#define NYXB_AU_KM 149597870.700
+#define NYXB_C_M_S (299792.458 * 1e3)
+
+// SpacecraftDynamics::eom for one trajectory: y[9] -> dy[0..5] (dy[6..8] == 0).
+// Returns 0 or an nyxb_status error code.
+__device__ inline int eom_full(const DevSetup& S, long long epoch_ns, double delta_t_s, const double y[9],
+                               double dry_mass, double extra_mass, double srp_area, double drag_area, double dy[6]) {
+    long long t_ns = epoch_ns + dur_from_seconds(delta_t_s);
+    double cr = y[6] < 0.0 ? 0.0 : (y[6] > 2.0 ? 2.0 : y[6]);
+    double cd = y[7];
+    double mass = dry_mass + y[8] + extra_mass;
+    bool has_force = S.has_srp || S.has_drag;
+    if (has_force && !(mass > 0.0)) return NYXB_ERR_MASSLESS;
+
+    double rmag = norm3(y[0], y[1], y[2]);
+    double fac = -S.mu_central / (rmag * rmag * rmag);
+    double acc[3] = { fac * y[0], fac * y[1], fac * y[2] };
+
+    double bpos[NYXB_MAX_BODIES][3];
+    for (int j = 0; j < S.n_bodies; ++j)
+        if (!body_position(S.bodies[j], t_ns, bpos[j])) return NYXB_ERR_EPHEMERIS;
+
+    if (S.point_mass_mask) {
+        double dx[3] = {0.0, 0.0, 0.0};
+        for (int j = 0; j < S.n_bodies; ++j) {
+            if (!((S.point_mass_mask >> j) & 1u)) continue;
+            double n_ij = norm3(bpos[j][0], bpos[j][1], bpos[j][2]);
+            double r_ij3 = n_ij * n_ij * n_ij;
+            double rj0 = y[0] - bpos[j][0], rj1 = y[1] - bpos[j][1], rj2 = y[2] - bpos[j][2];
+            double n_j = norm3(rj0, rj1, rj2);
+            double r_j3 = n_j * n_j * n_j;
+            double nmu = -S.bodies[j].mu;
+            dx[0] += nmu * (rj0 / r_j3 + bpos[j][0] / r_ij3);
+            dx[1] += nmu * (rj1 / r_j3 + bpos[j][1] / r_ij3);
+            dx[2] += nmu * (rj2 / r_j3 + bpos[j][2] / r_ij3);
+        }
+        acc[0] += dx[0]; acc[1] += dx[1]; acc[2] += dx[2];
+    }
+    if (S.has_grav) {
+        double ga[3];
+        grav_accel_rows(S.grav, t_ns, y, ga);
+        acc[0] += ga[0]; acc[1] += ga[1]; acc[2] += ga[2];
+    }
+    if (S.has_srp) {
+        const double* sun = bpos[S.srp.sun_body];
+        double rs[3] = { y[0] - sun[0], y[1] - sun[1], y[2] - sun[2] };
+        double n_sun = norm3(rs[0], rs[1], rs[2]);
+        double unit[3] = { rs[0] / n_sun, rs[1] / n_sun, rs[2] / n_sun };
+        double occult = 0.0;
+        double r_ls[3] = { -rs[0], -rs[1], -rs[2] };
+        for (int q = 0; q < S.srp.n_shadow; ++q) {
+            int bi = S.srp.shadow_body[q];
+            double r_eb[3], rad;
+            if (bi == NYXB_CENTRAL_BODY) { r_eb[0] = y[0]; r_eb[1] = y[1]; r_eb[2] = y[2]; rad = S.central_radius; }
+            else { r_eb[0] = y[0] - bpos[bi][0]; r_eb[1] = y[1] - bpos[bi][1]; r_eb[2] = y[2] - bpos[bi][2]; rad = S.bodies[bi].radius; }
+            double p = occultation(r_eb, r_ls, S.bodies[S.srp.sun_body].radius, rad);
+            if (p > occult) occult = p;
+        }
+        double k = fabs(occult - 1.0);
+        double r_sun_au = n_sun / NYXB_AU_KM;
+        double inv = 1.0 / r_sun_au;
+        double flux_pressure = (k * S.srp.phi / NYXB_C_M_S) * (inv * inv);
+        double scal = 1e-3 * cr * srp_area * flux_pressure;
+        acc[0] += (scal * unit[0]) / mass; acc[1] += (scal * unit[1]) / mass; acc[2] += (scal * unit[2]) / mass;
+    }
+    if (S.has_drag) {
+        double R[9];
+        rotation_dcm(S.drag.rot, t_ns, R);
+        double wdot = S.drag.rot.wdot;
+        double rb[3], vb[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            rb[i] = (R[3 * i] * y[0] + R[3 * i + 1] * y[1]) + R[3 * i + 2] * y[2];
+            vb[i] = (R[3 * i] * y[3] + R[3 * i + 1] * y[4]) + R[3 * i + 2] * y[5];
+        }
+        vb[0] = vb[0] + wdot * rb[1];
+        vb[1] = vb[1] - wdot * rb[0];
+        double rho, vel[3];
+        if (S.drag.density == NYXB_DENSITY_CONSTANT) {
+            rho = S.drag.rho0;
+            vel[0] = vb[0]; vel[1] = vb[1]; vel[2] = vb[2];
+        } else {
+            double rmag_bf = norm3(rb[0], rb[1], rb[2]);
+            if (S.drag.density == NYXB_DENSITY_EXPONENTIAL) {
+                rho = S.drag.rho0 * exp(-(rmag_bf - (S.drag.r0 + S.drag.r_eq)) / S.drag.ref_alt_m);
+            } else {
+                double alt = rmag_bf - S.drag.r_eq;
+                if (alt > S.drag.ref_alt_m / 1000.0) {
+                    rho = pow(10.0, (-7e-5) * alt - 14.464);
+                } else {
+                    double sc = (alt - 526.8000) / 292.8563;
+                    double s2 = sc * sc, s3 = s2 * sc, s4 = s3 * sc, s5 = s4 * sc, s6 = s5 * sc;
+                    double logd = 0.34047 * s6 - 0.5889 * s5 - 0.5269 * s4 + 1.0036 * s3 + 0.60713 * s2 - 2.3024 * sc - 12.575;
+                    rho = pow(10.0, logd);
+                }
+            }
+            vel[0] = y[3] - vb[0]; vel[1] = y[4] - vb[1]; vel[2] = y[5] - vb[2];
+        }
+        double scal = -0.5 * 1e3 * rho * cd * drag_area * norm3(vel[0], vel[1], vel[2]);
+        acc[0] += (scal * vel[0]) / mass; acc[1] += (scal * vel[1]) / mass; acc[2] += (scal * vel[2]) / mass;
+    }
+    dy[0] = y[3]; dy[1] = y[4]; dy[2] = y[5];
+    dy[3] = acc[0]; dy[4] = acc[1]; dy[5] = acc[2];
+    return 0;
+}
+
+// ---- ErrorControl::estimate (error_ctrl.rs:79-230); err/cand/cur are 9-vectors whose
+// entries 6..8 carry zero error (their derivatives are zero without guidance).
+__device__ __forceinline__ double rss_step3(const double* e, const double* cand, const double* cur) {
+    double mag = norm3(cand[0] - cur[0], cand[1] - cur[1], cand[2] - cur[2]);
+    double err = norm3(e[0], e[1], e[2]);
+    return (mag > sqrt(0.1)) ? err / mag : err;
+}
+__device__ __forceinline__ double rss_state3(const double* e, const double* cand, const double* cur) {
+    double mag = 0.5 * norm3(cand[0] + cur[0], cand[1] + cur[1], cand[2] + cur[2]);
+    double err = norm3(e[0], e[1], e[2]);
+    return (mag > 0.1) ? err / mag : err;
+}
+__device__ __forceinline__ double fmax_rust(double a, double b) { return (a > b || b != b) ? a : b; }
+__device__ __forceinline__ double norm9_nalgebra(const double v[9]) {
+    // nalgebra generic dot: 8 interleaved accumulators (see oracle/nyx_oracle.c)
+    double a0 = __dadd_rn(__dmul_rn(v[0], v[0]), __dmul_rn(v[8], v[8]));
+    double res = 0.0;
+    res = __dadd_rn(res, __dadd_rn(a0, __dmul_rn(v[4], v[4])));
+    res = __dadd_rn(res, __dadd_rn(__dmul_rn(v[1], v[1]), __dmul_rn(v[5], v[5])));
+    res = __dadd_rn(res, __dadd_rn(__dmul_rn(v[2], v[2]), __dmul_rn(v[6], v[6])));
+    res = __dadd_rn(res, __dadd_rn(__dmul_rn(v[3], v[3]), __dmul_rn(v[7], v[7])));
+    return sqrt(res);
+}
+
+__device__ inline double error_estimate(int ctrl, const double err[9], const double cand[9], const double cur[9]) {
+    switch (ctrl) {
+    case NYXB_RSS_CARTESIAN_STATE:
+        return fmax_rust(rss_state3(err, cand, cur), rss_state3(err + 3, cand + 3, cur + 3));
+    case NYXB_RSS_CARTESIAN_STEP:
+        return fmax_rust(rss_step3(err, cand, cur), rss_step3(err + 3, cand + 3, cur + 3));
+    case NYXB_RSS_STATE: {
+        double s[9];
+        for (int i = 0; i < 9; ++i) s[i] = cand[i] + cur[i];
+        double mag = 0.5 * norm9_nalgebra(s), e = norm9_nalgebra(err);
+        return (mag > 0.1) ? e / mag : e;
+    }
+    case NYXB_RSS_STEP: {
+        double d[9];
+        for (int i = 0; i < 9; ++i) d[i] = cand[i] - cur[i];
+        double mag = norm9_nalgebra(d), e = norm9_nalgebra(err);
+        return (mag > sqrt(0.1)) ? e / mag : e;
+    }
+    case NYXB_LARGEST_ERROR: {
+        double max_err = 0.0;
+        for (int i = 0; i < 9; ++i) {
+            double delta = cand[i] - cur[i];
+            double e = (delta > 0.1) ? fabs(err[i] / delta) : fabs(err[i]);
+            if (e > max_err) max_err = e;
+        }
+        return max_err;
+    }
+    case NYXB_LARGEST_STATE: {
+        double mag = 0.0, e = 0.0;
+        for (int i = 0; i < 9; ++i) { mag += 0.5 * fabs(cand[i] + cur[i]); e += fabs(err[i]); }
+        return (mag > 0.1) ? e / mag : e;
+    }
+    default: {
+        double mag = 0.0, e = 0.0;
+        for (int i = 0; i < 9; ++i) { mag += fabs(cand[i] - cur[i]); e += fabs(err[i]); }
+        return (mag > 0.1) ? e / mag : e;
+    }
+    }
+}

@@ -1,0 +1,140 @@
+"""`MonteCarlo` / `MvnSpacecraft` / `Results` — host-side mirror of ``mc/*.rs``.
+
+`MonteCarlo::run_until_epoch` (mc/montecarlo.rs:188-273) fans the dispersed initial states
+out over a rayon pool; here the whole ensemble is ONE call of `nyxb_propagate_batch`
+(one GPU) or one call per shard (multi-GPU, see ``nyx_b200.dist``).  Dispersions are sampled
+on the host (mc/montecarlo.rs:277-296 is serial in the reference too) so that CPU oracle and
+GPU engine receive identical inputs.  The random stream is numpy's PCG64, not rand_pcg's
+Pcg64Mcg + ziggurat: draw-for-draw parity with the reference RNG is out of scope (the
+reference's own MC tests assert no numbers).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import abi
+from .cosmic import Spacecraft, pack_spacecraft
+from .frames import Almanac
+from .propagator import PropagationError, Propagator, status_error
+
+
+@dataclass
+class DispersedState:
+    """`DispersedState` (mc/generator.rs:56-67)."""
+
+    state: Spacecraft
+    actual_dispersions: List[Tuple[str, float]]
+
+
+_PARAMS = ("X", "Y", "Z", "VX", "VY", "VZ", "Cr", "Cd", "PropMass")
+
+
+class MvnSpacecraft:
+    """Multivariate-normal spacecraft state generator (mc/multivariate.rs:61-331), Cartesian form.
+
+    ``from_spacecraft_cov`` (multivariate.rs:213-296): x = sqrt_s_v · z + mean with
+    sqrt_s_v = V·sqrt(S) from the SVD of the 9x9 covariance; x is added to the template's
+    [r, v, Cr, Cd, prop mass] (multivariate.rs:298-331).
+    """
+
+    def __init__(self, template: Spacecraft, cov: np.ndarray, mean: Optional[np.ndarray] = None):
+        cov = np.asarray(cov, dtype=np.float64)
+        if cov.shape != (9, 9):
+            raise ValueError("covariance must be 9x9")
+        evals = np.linalg.eigvalsh(0.5 * (cov + cov.T))
+        if (evals < -1e-14 * max(1.0, abs(evals).max())).any():
+            raise ValueError("CovarianceMatrixNotPsd")
+        _, s, vt = np.linalg.svd(cov)
+        self.template = template
+        self.mean = np.zeros(9) if mean is None else np.asarray(mean, dtype=np.float64)
+        self.sqrt_s_v = vt.T * np.sqrt(s)[None, :]
+
+    @classmethod
+    def from_spacecraft_cov(cls, template: Spacecraft, cov, mean=None) -> "MvnSpacecraft":
+        return cls(template, cov, mean)
+
+    @classmethod
+    def from_cartesian_std(cls, template: Spacecraft, pos_std_km, vel_std_km_s, cr_std=0.0, cd_std=0.0,
+                           prop_std_kg=0.0) -> "MvnSpacecraft":
+        pos = np.broadcast_to(np.asarray(pos_std_km, dtype=float), (3,))
+        vel = np.broadcast_to(np.asarray(vel_std_km_s, dtype=float), (3,))
+        return cls(template, np.diag(np.concatenate([pos, vel, [cr_std, cd_std, prop_std_kg]]) ** 2))
+
+    def sample_vectors(self, rng: np.random.Generator, num: int) -> np.ndarray:
+        """[num, 9] perturbation vectors (one row per run, draw order = run index)."""
+        z = rng.standard_normal((num, 9))
+        return z @ self.sqrt_s_v.T + self.mean[None, :]
+
+    def apply(self, x: np.ndarray) -> DispersedState:
+        vec = self.template.to_vector() + x
+        state = self.template.with_vector(self.template.epoch(), vec)
+        return DispersedState(state, [(p, float(-x[i])) for i, p in enumerate(_PARAMS)])
+
+
+@dataclass
+class Run:
+    """`Run` (mc/results.rs:48-59): per-run result or error, never aborting the ensemble."""
+
+    index: int
+    dispersed_state: DispersedState
+    result: object  # Spacecraft | PropagationError
+
+
+@dataclass
+class Results:
+    """`Results` (mc/results.rs:62-72) in final-state-only form + SoA views for bulk consumers."""
+
+    runs: List[Run]
+    scenario: str
+    final_state_soa: np.ndarray = field(repr=False, default=None)  # [9][n]
+    details: np.ndarray = field(repr=False, default=None)
+    status: np.ndarray = field(repr=False, default=None)
+
+    def ok_runs(self) -> List[Run]:
+        return [r for r in self.runs if not isinstance(r.result, Exception)]
+
+    def total_steps(self) -> int:
+        return int(self.details["n_steps"].sum())
+
+
+class MonteCarlo:
+    """`MonteCarlo` (mc/montecarlo.rs:48-327)."""
+
+    def __init__(self, nominal_state: Spacecraft, random_variable: MvnSpacecraft, scenario: str, seed: Optional[int] = None):
+        self.nominal_state = nominal_state
+        self.random_state = random_variable
+        self.scenario = scenario
+        self.seed = seed
+
+    @classmethod
+    def new(cls, nominal_state, random_variable, scenario, seed=None) -> "MonteCarlo":
+        return cls(nominal_state, random_variable, scenario, seed)
+
+    def generate_states(self, skip: int, num_runs: int, seed: Optional[int] = None) -> List[Tuple[int, DispersedState]]:
+        """mc/montecarlo.rs:277-296: one serial stream; `skip` discards the first draws."""
+        rng = np.random.Generator(np.random.PCG64(self.seed if seed is None else seed))
+        x = self.random_state.sample_vectors(rng, skip + num_runs)[skip:]
+        return [(i, self.random_state.apply(x[i])) for i in range(num_runs)]
+
+    def run_until_epoch(self, prop: Propagator, almanac: Optional[Almanac], end_epoch_ns: int, num_runs: int) -> Results:
+        return self.resume_run_until_epoch(prop, almanac, 0, end_epoch_ns, num_runs)
+
+    def resume_run_until_epoch(self, prop: Propagator, almanac: Optional[Almanac], skip: int, end_epoch_ns: int,
+                               num_runs: int) -> Results:
+        """mc/montecarlo.rs:208-273"""
+        init_states = self.generate_states(skip, num_runs, self.seed)
+        st, cs, ep = pack_spacecraft(ds.state for _, ds in init_states)
+        eng = prop.engine(self.nominal_state.orbit.frame, almanac)
+        out, out_ep, det, status = eng.propagate_batch(st, cs, ep, end_epoch_ns)
+        runs = []
+        for (idx, ds) in init_states:
+            err = status_error(status[idx])
+            res = err if err is not None else ds.state.with_vector(int(out_ep[idx]), out[:, idx])
+            runs.append(Run(idx, ds, res))
+        return Results(runs, self.scenario, out, det, status)
+
+    def __str__(self):
+        return f"{self.scenario} - Nyx Monte Carlo - seed: {self.seed}"

@@ -1,0 +1,329 @@
+"""`Propagator` / `PropInstance` / `IntegratorOptions` — host-side mirror of
+``propagators/{propagator,instance,options}.rs`` driving the CUDA engine through the C ABI.
+
+All numerical work (RK stages, error control, step-size controller, force models) runs in
+``csrc/`` on the GPU; this module only packs/unpacks arrays and mirrors the reference's
+call surface so that user code and the parity tests read like the reference's own:
+
+    setup = Propagator.rk89(dynamics, IntegratorOptions.with_adaptive_step_s(0.1, 30.0, 1e-12, ErrorControl.RSSCartesianState))
+    prop = setup.with_(spacecraft, almanac)
+    final = prop.for_duration(1 * Unit.Day)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from dataclasses import dataclass, replace
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import abi
+from .cosmic import Spacecraft, Unit, pack_spacecraft
+from .dynamics import PackedDynamics, SpacecraftDynamics
+from .frames import Almanac, Frame
+
+
+class IntegratorMethod(enum.IntEnum):
+    """`IntegratorMethod` (rk_methods/mod.rs:65-79)."""
+
+    RungeKutta89 = abi.RK89
+    DormandPrince78 = abi.DP78
+    DormandPrince45 = abi.DP45
+    RungeKutta4 = abi.RK4
+    CashKarp45 = abi.CK45
+    Verner56 = abi.V56
+
+    @classmethod
+    def from_str(cls, s: str) -> "IntegratorMethod":
+        for m in cls:
+            if m.name.lower() == s.lower():
+                return m
+        valid = ",".join(m.name for m in cls)
+        raise PropagationError(f"unknow integration method `{s}`, must be one of {valid}")
+
+    def order(self) -> int:
+        return {0: 9, 1: 8, 2: 5, 3: 4, 4: 5, 5: 6}[int(self)]
+
+    def stages(self) -> int:
+        return {0: 16, 1: 13, 2: 7, 3: 4, 4: 6, 5: 8}[int(self)]
+
+
+class ErrorControl(enum.IntEnum):
+    """`ErrorControl` (error_ctrl.rs:30-71)."""
+
+    RSSCartesianState = abi.RSS_CARTESIAN_STATE
+    RSSCartesianStep = abi.RSS_CARTESIAN_STEP
+    RSSState = abi.RSS_STATE
+    RSSStep = abi.RSS_STEP
+    LargestError = abi.LARGEST_ERROR
+    LargestState = abi.LARGEST_STATE
+    LargestStep = abi.LARGEST_STEP
+
+
+class PropagationError(RuntimeError):
+    """`PropagationError` (propagators/mod.rs:68-92)."""
+
+
+_STATUS_MSG = {
+    abi.ERR_PROP_MATH: "PropMathError: try another integration method, or decrease step size; part of state vector is NaN",
+    abi.ERR_FUEL_EXHAUSTED: "DynamicsError::FuelExhausted: negative prop mass",
+    abi.ERR_MASSLESS: "DynamicsError::MasslessSpacecraft",
+    abi.ERR_EPHEMERIS: "DynamicsError::DynamicsAlmanacError: epoch outside ephemeris coverage",
+}
+
+
+def status_error(code: int) -> Optional[PropagationError]:
+    code = int(code) & 0xFF
+    return None if code == 0 else PropagationError(_STATUS_MSG.get(code, f"status {code}"))
+
+
+@dataclass
+class IntegratorOptions:
+    """`IntegratorOptions` (options.rs:42-186); durations are integer nanoseconds."""
+
+    init_step: int = 60 * Unit.Second
+    min_step: int = 0.001 * Unit.Second
+    max_step: int = 2700 * Unit.Second
+    tolerance: float = 1e-12
+    attempts: int = 50
+    fixed_step: bool = False
+    error_ctrl: ErrorControl = ErrorControl.RSSCartesianStep
+
+    @classmethod
+    def default(cls) -> "IntegratorOptions":
+        return cls()
+
+    @classmethod
+    def with_adaptive_step(cls, min_step: int, max_step: int, tolerance: float, error_ctrl: ErrorControl):
+        return cls(init_step=max_step, min_step=min_step, max_step=max_step, tolerance=tolerance, attempts=50,
+                   fixed_step=False, error_ctrl=error_ctrl)  # options.rs:66-82
+
+    @classmethod
+    def with_adaptive_step_s(cls, min_step: float, max_step: float, tolerance: float, error_ctrl: ErrorControl):
+        return cls.with_adaptive_step(min_step * Unit.Second, max_step * Unit.Second, tolerance, error_ctrl)
+
+    @classmethod
+    def with_fixed_step(cls, step: int):
+        return cls(init_step=step, min_step=step, max_step=step, tolerance=0.0, fixed_step=True, attempts=0,
+                   error_ctrl=ErrorControl.RSSCartesianStep)  # options.rs:100-111
+
+    @classmethod
+    def with_fixed_step_s(cls, step: float):
+        return cls.with_fixed_step(step * Unit.Second)
+
+    @classmethod
+    def with_tolerance(cls, tolerance: float):
+        return cls(tolerance=tolerance)
+
+    @classmethod
+    def with_max_step(cls, max_step: int):
+        o = cls()
+        o.set_max_step(max_step)
+        return o
+
+    def set_max_step(self, max_step: int) -> None:
+        if self.init_step > max_step:
+            self.init_step = max_step
+        self.max_step = max_step
+
+    def set_min_step(self, min_step: int) -> None:
+        if self.init_step < min_step:
+            self.init_step = min_step
+        self.min_step = min_step
+
+    def to_c(self, method: IntegratorMethod) -> abi.IntegOpts:
+        return abi.IntegOpts(int(method), int(self.error_ctrl), int(self.init_step), int(self.min_step),
+                             int(self.max_step), float(self.tolerance), int(self.attempts), int(bool(self.fixed_step)))
+
+
+@dataclass
+class IntegrationDetails:
+    """`IntegrationDetails` (propagators/mod.rs:49-56) + step counters."""
+
+    step: int
+    error: float
+    attempts: int
+    n_steps: int = 0
+    n_rejected: int = 0
+    n_rhs: int = 0
+
+
+class Engine:
+    """Owns one `nyxb_engine` (device tables for a (dynamics, method, options, frame) tuple)."""
+
+    def __init__(self, packed: PackedDynamics, opts_c: abi.IntegOpts, mode: int, device: int):
+        self._lib = abi.load_library()
+        self._packed = packed
+        self._opts = opts_c
+        self.mode = mode
+        self.device = device
+        self._h = self._lib.nyxb_engine_create(packed.byref(), C.byref(opts_c), mode, device)
+        if not self._h:
+            raise PropagationError(f"nyxb_engine_create failed: {abi.last_error()}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.nyxb_engine_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def handle(self):
+        return self._h
+
+    def set_lanes(self, lanes: int):
+        rc = self._lib.nyxb_engine_set_lanes(self._h, lanes)
+        if rc != 0:
+            raise PropagationError(f"set_lanes({lanes}): {abi.last_error()}")
+
+    def lanes(self) -> int:
+        return self._lib.nyxb_engine_get_lanes(self._h)
+
+    def launch_count(self) -> int:
+        return self._lib.nyxb_engine_launch_count(self._h)
+
+    def last_kernel_ms(self) -> float:
+        return self._lib.nyxb_engine_last_kernel_ms(self._h)
+
+    def propagate_batch(self, state_soa, consts_soa, epoch0_ns, end_epoch_ns, step_ns=None):
+        """Host-buffer call of `nyxb_propagate_batch`. Returns (state, epoch, details, status)."""
+        state_soa = np.ascontiguousarray(state_soa, dtype=np.float64)
+        consts_soa = np.ascontiguousarray(consts_soa, dtype=np.float64)
+        epoch0_ns = np.ascontiguousarray(epoch0_ns, dtype=np.int64)
+        n = state_soa.shape[1]
+        if state_soa.shape != (9, n) or consts_soa.shape != (4, n) or epoch0_ns.shape != (n,):
+            raise ValueError("expected state[9][n], consts[4][n], epoch0[n]")
+        out_state = np.empty((9, n))
+        out_epoch = np.empty(n, dtype=np.int64)
+        details = np.zeros(n, dtype=abi.DETAILS_DTYPE)
+        status = np.zeros(n, dtype=np.int32)
+        step_ptr = None
+        if step_ns is not None:
+            if step_ns.dtype != np.int64 or step_ns.shape != (n,) or not step_ns.flags["C_CONTIGUOUS"]:
+                raise ValueError("step_ns must be a contiguous int64[n] array")
+            step_ptr = step_ns.ctypes.data
+        rc = self._lib.nyxb_propagate_batch(self._h, n, state_soa.ctypes.data, consts_soa.ctypes.data,
+                                            epoch0_ns.ctypes.data, int(end_epoch_ns), step_ptr, out_state.ctypes.data,
+                                            out_epoch.ctypes.data, details.ctypes.data, status.ctypes.data)
+        if rc != 0:
+            raise PropagationError(f"nyxb_propagate_batch rc={rc}: {abi.last_error()}")
+        return out_state, out_epoch, details, status
+
+    def propagate_batch_dev(self, n, state_ptr, consts_ptr, epoch0_ptr, end_epoch_ns, step_ptr, out_state_ptr,
+                            out_epoch_ptr, details_ptr, status_ptr, stream_ptr=None):
+        """Device-pointer call (`nyxb_propagate_batch_dev`): asynchronous on `stream_ptr`."""
+        rc = self._lib.nyxb_propagate_batch_dev(self._h, n, state_ptr, consts_ptr, epoch0_ptr, int(end_epoch_ns), step_ptr,
+                                                out_state_ptr, out_epoch_ptr, details_ptr, status_ptr, stream_ptr)
+        if rc != 0:
+            raise PropagationError(f"nyxb_propagate_batch_dev rc={rc}: {abi.last_error()}")
+
+
+@dataclass
+class Propagator:
+    """`Propagator<SpacecraftDynamics>` (propagator.rs:34-118)."""
+
+    dynamics: SpacecraftDynamics
+    method: IntegratorMethod = IntegratorMethod.RungeKutta89
+    opts: IntegratorOptions = None  # type: ignore[assignment]
+    mode: int = abi.MODE_STRICT  # NYXB_MODE_STRICT (bit parity) | NYXB_MODE_FAST
+    device: int = 0
+
+    def __post_init__(self):
+        if self.opts is None:
+            self.opts = IntegratorOptions.default()
+        self._engines = {}
+
+    # constructors -----------------------------------------------------------------------------
+    @classmethod
+    def new(cls, dynamics, method: IntegratorMethod, opts: IntegratorOptions, **kw) -> "Propagator":
+        return cls(dynamics, method, opts, **kw)
+
+    @classmethod
+    def rk89(cls, dynamics, opts: IntegratorOptions, **kw) -> "Propagator":
+        return cls(dynamics, IntegratorMethod.RungeKutta89, opts, **kw)
+
+    @classmethod
+    def dp78(cls, dynamics, opts: IntegratorOptions, **kw) -> "Propagator":
+        return cls(dynamics, IntegratorMethod.DormandPrince78, opts, **kw)
+
+    @classmethod
+    def default(cls, dynamics, **kw) -> "Propagator":
+        return cls.rk89(dynamics, IntegratorOptions.default(), **kw)
+
+    @classmethod
+    def default_dp78(cls, dynamics, **kw) -> "Propagator":
+        return cls.dp78(dynamics, IntegratorOptions.default(), **kw)
+
+    def set_tolerance(self, tol: float):
+        self.opts.tolerance = tol
+        self._engines.clear()
+
+    def set_max_step(self, step: int):
+        self.opts.set_max_step(step)
+        self._engines.clear()
+
+    def set_min_step(self, step: int):
+        self.opts.set_min_step(step)
+        self._engines.clear()
+
+    # engine cache ------------------------------------------------------------------------------
+    def engine(self, frame: Frame, almanac: Optional[Almanac]) -> Engine:
+        key = (id(almanac), frame)
+        eng = self._engines.get(key)
+        if eng is None:
+            packed = self.dynamics.pack(frame, almanac)
+            eng = Engine(packed, self.opts.to_c(self.method), self.mode, self.device)
+            self._engines[key] = eng
+        return eng
+
+    # instances ---------------------------------------------------------------------------------
+    def with_(self, state: Spacecraft, almanac: Optional[Almanac] = None) -> "PropInstance":
+        """`Propagator::with` (propagator.rs:88-108)."""
+        return PropInstance(self, state, almanac)
+
+    def many_until_epoch(self, spacecraft: Sequence[Spacecraft], epoch_ns: int, almanac: Optional[Almanac] = None,
+                         ) -> List[Spacecraft]:
+        """nyx-py `Propagator.many_until_epoch(list, epoch, trajectory=False)` (py_md.rs:224-271):
+        failed runs are dropped (py_md.rs:251-254, 262-265)."""
+        spacecraft = list(spacecraft)
+        if not spacecraft:
+            return []
+        frame = spacecraft[0].orbit.frame
+        st, cs, ep = pack_spacecraft(spacecraft)
+        out, out_ep, _, status = self.engine(frame, almanac).propagate_batch(st, cs, ep, epoch_ns)
+        return [sc.with_vector(int(out_ep[i]), out[:, i]) for i, sc in enumerate(spacecraft) if (status[i] & 0xFF) == 0]
+
+
+class PropInstance:
+    """`PropInstance` (instance.rs:41-499): one spacecraft, keeps the adapted step between calls."""
+
+    def __init__(self, prop: Propagator, state: Spacecraft, almanac: Optional[Almanac]):
+        self.prop = prop
+        self.state = state
+        self.almanac = almanac
+        self.details = IntegrationDetails(step=prop.opts.init_step, error=0.0, attempts=1)
+        self._step_ns = np.array([prop.opts.init_step], dtype=np.int64)  # instance.rs:56 step_size
+
+    def latest_details(self) -> IntegrationDetails:
+        return self.details
+
+    def for_duration(self, duration_ns: int) -> Spacecraft:
+        """instance.rs:265-267"""
+        return self.until_epoch(self.state.epoch() + int(duration_ns))
+
+    def until_epoch(self, end_ns: int) -> Spacecraft:
+        """instance.rs:279-282"""
+        st, cs, ep = pack_spacecraft([self.state])
+        eng = self.prop.engine(self.state.orbit.frame, self.almanac)
+        out, out_ep, det, status = eng.propagate_batch(st, cs, ep, int(end_ns), self._step_ns)
+        err = status_error(status[0])
+        if err is not None:
+            raise err
+        d = det[0]
+        if d["n_steps"] > 0:
+            self.details = IntegrationDetails(int(d["step_ns"]), float(d["error"]), int(d["attempts"]), int(d["n_steps"]),
+                                              int(d["n_rejected"]), int(d["n_rhs"]))
+        self.state = self.state.with_vector(int(out_ep[0]), out[:, 0])
+        return self.state

