@@ -7,6 +7,9 @@
 #include <string>
 #include <vector>
 
+#include <map>
+
+#include "nyxb_coop.h"
 #include "nyxb_device.cuh"
 #include "nyxb_tableaux.h"
 
@@ -17,9 +20,6 @@ extern "C" cudaError_t nyxb_launch_thread_strict(const DevSetup*, size_t, const 
 extern "C" cudaError_t nyxb_launch_thread_fast(const DevSetup*, size_t, const double*, const double*, const long long*,
                                                long long, long long*, double*, long long*, nyxb_details*, int*, int,
                                                cudaStream_t);
-extern "C" cudaError_t nyxb_launch_coop(const DevSetup*, int lanes, size_t, const double*, const double*, const long long*,
-                                        long long, long long*, double*, long long*, nyxb_details*, int*, cudaStream_t);
-extern "C" int nyxb_coop_supported(const DevSetup*, int lanes);
 extern "C" double nyxb_fp64_probe(int device, int iters);
 
 static thread_local std::string g_err;
@@ -41,6 +41,8 @@ struct nyxb_engine {
     std::vector<void*> dev_allocs;
     long long launches = 0;
     double last_ms = 0.0;
+    std::vector<double> h_cnm, h_snm;      // host copies for building cooperative tables lazily
+    std::map<int, DevCoop> coop;           // lanes -> device tables
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ~nyxb_engine() {
         for (void* p : dev_allocs) cudaFree(p);
@@ -204,6 +206,8 @@ extern "C" nyxb_engine* nyxb_engine_create(const nyxb_dynamics* dyn, const nyxb_
                 tab[(size_t)n * (n + 1) / 2 + m] = h;
             }
         }
+        e->h_cnm.assign(g.c_nm, g.c_nm + (size_t)(N + 1) * (N + 1));
+        e->h_snm.assign(g.s_nm, g.s_nm + (size_t)(N + 1) * (N + 1));
         S.grav.tab = upload(e, tab.data(), tab.size());
         S.grav.a_diag = upload(e, adiag.data(), adiag.size());
         S.grav.offdiag = upload(e, offd.data(), offd.size());
@@ -240,15 +244,32 @@ extern "C" void nyxb_engine_destroy(nyxb_engine* eng) {
     delete eng;
 }
 
+static bool coop_supported(const nyxb_engine* e, int lanes) {
+    if (e->mode != NYXB_MODE_FAST || !e->S.has_grav) return false;
+    return lanes == 8 || lanes == 16 || lanes == 32;
+}
+
 static int pick_lanes(const nyxb_engine* e, size_t n) {
     if (e->mode == NYXB_MODE_STRICT) return 1;
     if (e->lanes > 0) return e->lanes;
     // auto: cooperative lanes only pay off when the harmonic sum dominates
-    if (!e->S.has_grav || e->S.grav.N < 8) return 1;
-    int lanes = (e->S.grav.N >= 40) ? 32 : 16;
+    if (!e->S.has_grav || e->S.grav.N < 6) return 1;
     (void)n;
-    while (lanes > 1 && !nyxb_coop_supported(&e->S, lanes)) lanes >>= 1;
-    return lanes;
+    return (e->S.grav.N >= 48) ? 32 : ((e->S.grav.N >= 30) ? 16 : 8);
+}
+
+static const DevCoop* get_coop(nyxb_engine* e, int lanes) {
+    auto it = e->coop.find(lanes);
+    if (it != e->coop.end()) return &it->second;
+    CoopHost h;
+    nyxb_coop_build_host(e->S.grav.N, e->S.grav.M, e->h_cnm.data(), e->h_snm.data(), lanes, h);
+    DevCoop d;
+    d.G = h.G; d.L = h.L; d.kmax = h.kmax;
+    d.recs = upload(e, h.recs.data(), h.recs.size());
+    d.col_start = upload(e, h.col_start.data(), h.col_start.size());
+    d.col_m = upload(e, h.col_m.data(), h.col_m.size());
+    if (!d.recs || !d.col_start || !d.col_m) return nullptr;
+    return &(e->coop[lanes] = d);
 }
 
 static int32_t launch(nyxb_engine* e, size_t n, const double* state, const double* consts, const int64_t* epoch0,
@@ -257,7 +278,9 @@ static int32_t launch(nyxb_engine* e, size_t n, const double* state, const doubl
     int lanes = pick_lanes(e, n);
     cudaError_t err;
     if (lanes > 1) {
-        err = nyxb_launch_coop(&e->S, lanes, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io,
+        const DevCoop* cp = get_coop(e, lanes);
+        if (!cp) { set_err("cooperative table upload failed"); return NYXB_RC_CUDA; }
+        err = nyxb_launch_coop(&e->S, cp, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io,
                                out_state, (long long*)out_epoch, out_details, out_status, stream);
     } else if (e->mode == NYXB_MODE_STRICT) {
         err = nyxb_launch_thread_strict(&e->S, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io,
@@ -334,8 +357,8 @@ done:
 
 extern "C" int32_t nyxb_engine_set_lanes(nyxb_engine* eng, int32_t lanes) {
     if (!eng) return NYXB_RC_BAD_ARG;
-    if (lanes != 0 && lanes != 1 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) { set_err("lanes must be 0,1,4,8,16,32"); return NYXB_RC_BAD_ARG; }
-    if (lanes > 1 && (eng->mode == NYXB_MODE_STRICT || !nyxb_coop_supported(&eng->S, lanes))) {
+    if (lanes != 0 && lanes != 1 && lanes != 8 && lanes != 16 && lanes != 32) { set_err("lanes must be 0,1,8,16,32"); return NYXB_RC_BAD_ARG; }
+    if (lanes > 1 && !coop_supported(eng, lanes)) {
         set_err("cooperative lanes unsupported for this engine (strict mode or no gravity field)");
         return NYXB_RC_UNSUPPORTED;
     }

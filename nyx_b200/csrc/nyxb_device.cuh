@@ -142,6 +142,36 @@ __device__ __forceinline__ void det_sincos(double x, double& s, double& c) {
     }
 }
 
+// ---- step-size controller power: (tol/err)^(1/n), n = order or order-1 (instance.rs:451-454, 479-482).
+// The reference calls libm `pow(x, fl(1/n))` (glibc: correctly rounded in all but a percent of cases).
+// CUDA's pow is only 2-ulp accurate, and after a *rejected* attempt the raw f64 step is used
+// unquantised (instance.rs:484-488), so a 1-ulp difference would perturb the whole trajectory.
+// We therefore correct CUDA's result to the correctly rounded value: one Newton step on
+// q^n = x evaluated in double-double, plus the first-order term for fl(1/n) != 1/n.
+struct dd_t { double hi, lo; };
+__device__ __forceinline__ dd_t dd_mul_d(dd_t a, double b) {
+    double t = __dmul_rn(a.hi, b);
+    double e = fma(a.hi, b, -t);
+    double lo = fma(a.lo, b, e);
+    double hi = __dadd_rn(t, lo);
+    dd_t r; r.hi = hi; r.lo = __dsub_rn(lo, __dsub_rn(hi, t));
+    return r;
+}
+__device__ __forceinline__ double pow_inv_int(double x, int n) {
+    // eps_n = fl(1/n) - 1/n
+    const double eps_tab[10] = {0.0, 0.0, 0.0, -1.850371707708594e-17, 0.0, 1.1102230246251566e-17,
+                                -9.25185853854297e-18, -7.93016446160826e-18, 0.0, -6.1679056923619804e-18};
+    double yinv = __ddiv_rn(1.0, (double)n);
+    double q0 = pow(x, yinv);
+    if (!(x > 0.0) || !(x < 1.0e300) || n < 2 || n > 9 || !(q0 > 0.0) || !(q0 < 1.0e300)) return q0;
+    dd_t p; p.hi = q0; p.lo = 0.0;
+    for (int i = 1; i < n; ++i) p = dd_mul_d(p, q0);
+    double r = __dadd_rn(__dsub_rn(p.hi, x), p.lo);              // q0^n - x
+    double delta = __ddiv_rn(__dmul_rn(r, q0), __dmul_rn((double)n, p.hi));
+    double corr = __dmul_rn(__dmul_rn(q0, eps_tab[n]), log(x));  // x^y = x^(1/n) (1 + eps ln x)
+    return __dadd_rn(q0, __dsub_rn(corr, delta));
+}
+
 #define NYXB_DEG2RAD 1.7453292519943295e-2
 
 // inertial -> body-fixed DCM (row-major R[9]) of the orientation model in nyxb.h
@@ -298,25 +328,19 @@ __device__ inline void grav_accel_rows(const DevGrav& g, long long t_ns, const d
 #define NYXB_AU_KM 149597870.700
 #define NYXB_C_M_S (299792.458 * 1e3)
 
-// SpacecraftDynamics::eom for one trajectory: y[9] -> dy[0..5] (dy[6..8] == 0).
-// Returns 0 or an nyxb_status error code.
-__device__ inline int eom_full(const DevSetup& S, long long epoch_ns, double delta_t_s, const double y[9],
-                               double dry_mass, double extra_mass, double srp_area, double drag_area, double dy[6]) {
-    long long t_ns = epoch_ns + dur_from_seconds(delta_t_s);
-    double cr = y[6] < 0.0 ? 0.0 : (y[6] > 2.0 ? 2.0 : y[6]);
-    double cd = y[7];
-    double mass = dry_mass + y[8] + extra_mass;
-    bool has_force = S.has_srp || S.has_drag;
-    if (has_force && !(mass > 0.0)) return NYXB_ERR_MASSLESS;
-
+// ---- SpacecraftDynamics::eom split in three ordered parts so that the per-thread kernel
+// (reference accumulation order) and the cooperative kernel (lanes share the harmonic sum)
+// reuse the same force-model code:
+//   accel_pre  : two-body + PointMasses                 orbital.rs:86-92, 213-247
+//   (gravity)  : GravityField                           gravity_field.rs:148-268
+//   accel_post : SolarPressure + Drag, each / mass      spacecraft.rs:238-243
+__device__ inline int accel_pre(const DevSetup& S, long long t_ns, const double y[9],
+                                double bpos[NYXB_MAX_BODIES][3], double acc[3]) {
     double rmag = norm3(y[0], y[1], y[2]);
     double fac = -S.mu_central / (rmag * rmag * rmag);
-    double acc[3] = { fac * y[0], fac * y[1], fac * y[2] };
-
-    double bpos[NYXB_MAX_BODIES][3];
+    acc[0] = fac * y[0]; acc[1] = fac * y[1]; acc[2] = fac * y[2];
     for (int j = 0; j < S.n_bodies; ++j)
         if (!body_position(S.bodies[j], t_ns, bpos[j])) return NYXB_ERR_EPHEMERIS;
-
     if (S.point_mass_mask) {
         double dx[3] = {0.0, 0.0, 0.0};
         for (int j = 0; j < S.n_bodies; ++j) {
@@ -333,11 +357,14 @@ __device__ inline int eom_full(const DevSetup& S, long long epoch_ns, double del
         }
         acc[0] += dx[0]; acc[1] += dx[1]; acc[2] += dx[2];
     }
-    if (S.has_grav) {
-        double ga[3];
-        grav_accel_rows(S.grav, t_ns, y, ga);
-        acc[0] += ga[0]; acc[1] += ga[1]; acc[2] += ga[2];
-    }
+    return 0;
+}
+
+__device__ inline void accel_post(const DevSetup& S, long long t_ns, const double y[9],
+                                  const double bpos[NYXB_MAX_BODIES][3], double mass, double srp_area,
+                                  double drag_area, double acc[3]) {
+    double cr = y[6] < 0.0 ? 0.0 : (y[6] > 2.0 ? 2.0 : y[6]);  // cosmic/spacecraft.rs:494
+    double cd = y[7];
     if (S.has_srp) {
         const double* sun = bpos[S.srp.sun_body];
         double rs[3] = { y[0] - sun[0], y[1] - sun[1], y[2] - sun[2] };
@@ -396,6 +423,26 @@ __device__ inline int eom_full(const DevSetup& S, long long epoch_ns, double del
         double scal = -0.5 * 1e3 * rho * cd * drag_area * norm3(vel[0], vel[1], vel[2]);
         acc[0] += (scal * vel[0]) / mass; acc[1] += (scal * vel[1]) / mass; acc[2] += (scal * vel[2]) / mass;
     }
+}
+
+// SpacecraftDynamics::eom for one trajectory on one thread: y[9] -> dy[0..5] (dy[6..8] == 0).
+// Returns 0 or an nyxb_status error code.
+__device__ inline int eom_full(const DevSetup& S, long long epoch_ns, double delta_t_s, const double y[9],
+                               double dry_mass, double extra_mass, double srp_area, double drag_area, double dy[6]) {
+    long long t_ns = epoch_ns + dur_from_seconds(delta_t_s);
+    double mass = dry_mass + y[8] + extra_mass;
+    bool has_force = S.has_srp || S.has_drag;
+    if (has_force && !(mass > 0.0)) return NYXB_ERR_MASSLESS;
+    double acc[3];
+    double bpos[NYXB_MAX_BODIES][3];
+    int rc = accel_pre(S, t_ns, y, bpos, acc);
+    if (rc) return rc;
+    if (S.has_grav) {
+        double ga[3];
+        grav_accel_rows(S.grav, t_ns, y, ga);
+        acc[0] += ga[0]; acc[1] += ga[1]; acc[2] += ga[2];
+    }
+    if (has_force) accel_post(S, t_ns, y, bpos, mass, srp_area, drag_area, acc);
     dy[0] = y[3]; dy[1] = y[4]; dy[2] = y[5];
     dy[3] = acc[0]; dy[4] = acc[1]; dy[5] = acc[2];
     return 0;

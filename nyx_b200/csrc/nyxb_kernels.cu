@@ -91,7 +91,7 @@ __device__ static int derive(const DevSetup& S, Inst& in, long long& dt_ns, doub
             if (in.det_attempts >= S.attempts) in.status |= NYXB_WARN_MAX_ATTEMPTS;
             in.det_step_ns = dur_from_seconds(h);
             if (in.det_error < S.tolerance) {
-                double proposed = 0.9 * h * pow(S.tolerance / in.det_error, S.inv_order);
+                double proposed = 0.9 * h * pow_inv_int(S.tolerance / in.det_error, S.tb.order);
                 if (fabs(proposed) > fabs(S.max_step_s)) {
                     double sg = (proposed != proposed) ? proposed : (signbit(proposed) ? -1.0 : 1.0);
                     h = S.max_step_s * sg;
@@ -107,7 +107,7 @@ __device__ static int derive(const DevSetup& S, Inst& in, long long& dt_ns, doub
         }
         in.det_attempts += 1;
         in.n_rejected += 1;
-        double proposed = 0.9 * h * pow(S.tolerance / in.det_error, S.inv_order_m1);
+        double proposed = 0.9 * h * pow_inv_int(S.tolerance / in.det_error, S.tb.order - 1);
         h = (proposed < S.min_step_s) ? S.min_step_s : proposed;
     }
 }

@@ -78,15 +78,61 @@ def test_harmonics_ensemble_strict_bitexact(oracle, degree):
 
 @pytest.mark.parametrize("degree", [2, 21])
 def test_harmonics_ensemble_fast_tolerance(oracle, degree):
-    """Fast mode: sub-mm (north-star tolerance 1e-6 km; we assert 1e-8 km over 6 h)."""
+    """Fast mode: sub-mm (north-star tolerance 1e-6 km).  FMA contraction perturbs the error estimate by
+    ~1e-4 relative, hence the adapted step sequence, hence the result at the integrator's own
+    truncation-error level (~1e-7 km after 6 h): we assert 5e-7 km."""
     mc, (st, cs, ep) = leo_ensemble(256, seed=3)
     gd = nb.GravityFieldData.from_fixture("jgm3_70x70", degree, degree, nb.IAU_EARTH_FRAME)
     dyn = nb.SpacecraftDynamics.new(nb.OrbitalDynamics.from_model(nb.GravityField.new(gd)))
     prop = nb.Propagator.default(dyn, mode=nb.MODE_FAST)
     out, det, ref, ref_det = _ensemble_vs_oracle(oracle, prop, nb.EARTH_J2000, None, st, cs, ep, 6 * 3600 * S)
     dr, dv = max_dr_dv(out, ref)
-    assert dr < 1e-8 and dv < 1e-11, (dr, dv)
-    assert (det["n_steps"] != ref_det["n_steps"]).mean() < 0.02
+    assert dr < 5e-7 and dv < 1e-9, (dr, dv)
+    assert np.abs(det["n_steps"] - ref_det["n_steps"]).max() <= 1
+
+
+@pytest.mark.parametrize("lanes,degree,order", [(8, 21, 21), (16, 21, 21), (32, 21, 21), (8, 12, 7), (16, 40, 40), (32, 70, 70)])
+def test_cooperative_kernel_vs_oracle(oracle, lanes, degree, order):
+    """Lane-cooperative kernel (G lanes per trajectory, column-split harmonic sum) against the oracle.
+    6 h of adaptive RK89: differences are bounded by the integrator's own step-sequence sensitivity
+    (~1e-7 km); the north-star bound is 1e-6 km."""
+    n = 96 if degree <= 40 else 24
+    mc, (st, cs, ep) = leo_ensemble(n, seed=11)
+    gd = nb.GravityFieldData.from_fixture("jgm3_70x70", degree, order, nb.IAU_EARTH_FRAME)
+    dyn = nb.SpacecraftDynamics.new(nb.OrbitalDynamics.from_model(nb.GravityField.new(gd)))
+    prop = nb.Propagator.default(dyn, mode=nb.MODE_FAST)
+    eng = prop.engine(nb.EARTH_J2000, None)
+    eng.set_lanes(lanes)
+    assert eng.lanes() == lanes
+    out, out_ep, det, status = eng.propagate_batch(st, cs, ep, 6 * 3600 * S)
+    ref, ref_ep, ref_det, ref_status = oracle_run(oracle, prop, nb.EARTH_J2000, None, st, cs, ep, 6 * 3600 * S)
+    assert (status == 0).all() and np.array_equal(out_ep, ref_ep)
+    dr, dv = max_dr_dv(out, ref)
+    assert dr < 5e-7 and dv < 1e-9, (dr, dv)
+    assert np.abs(det["n_steps"] - ref_det["n_steps"]).max() <= 1
+    # cooperative vs per-thread fast kernel on the same engine: same algorithm class
+    eng.set_lanes(1)
+    out1, _, det1, _ = eng.propagate_batch(st, cs, ep, 6 * 3600 * S)
+    assert max_dr_dv(out, out1)[0] < 5e-7
+
+
+def test_cooperative_kernel_fixed_step_tight(oracle):
+    """With a FIXED step the step sequence cannot diverge, so the cooperative kernel must agree with the
+    oracle to round-off (1e-9 km over 6 h), which pins the regrouped harmonic sum itself."""
+    mc, (st, cs, ep) = leo_ensemble(64, seed=12)
+    gd = nb.GravityFieldData.from_fixture("jgm3_70x70", 21, 21, nb.IAU_EARTH_FRAME)
+    almanac = nb.Almanac.synthetic(nb.EARTH_J2000, 0, 1.0)
+    orb = nb.OrbitalDynamics.new([nb.PointMasses.new([nb.MOON, nb.SUN]), nb.GravityField.new(gd)])
+    dyn = nb.SpacecraftDynamics.new(orb)
+    for lanes in (8, 16, 32):
+        prop = nb.Propagator.rk89(dyn, nb.IntegratorOptions.with_fixed_step_s(60.0), mode=nb.MODE_FAST)
+        eng = prop.engine(nb.EARTH_J2000, almanac)
+        eng.set_lanes(lanes)
+        out, out_ep, det, status = eng.propagate_batch(st, cs, ep, 6 * 3600 * S)
+        ref, ref_ep, ref_det, _ = oracle_run(oracle, prop, nb.EARTH_J2000, almanac, st, cs, ep, 6 * 3600 * S)
+        assert (status == 0).all() and np.array_equal(det["n_steps"], ref_det["n_steps"])
+        dr, dv = max_dr_dv(out, ref)
+        assert dr < 1e-9 and dv < 1e-12, (lanes, dr, dv)
 
 
 @pytest.mark.parametrize("mode", [nb.MODE_STRICT, nb.MODE_FAST])
@@ -123,7 +169,7 @@ def test_drag_and_leo_eclipse_ensemble(oracle, density):
     prop = nb.Propagator.default(dyn, mode=nb.MODE_FAST)
     out, det, ref, ref_det = _ensemble_vs_oracle(oracle, prop, nb.EARTH_J2000, almanac, st, cs, ep, 4 * 3600 * S)
     dr, dv = max_dr_dv(out, ref)
-    assert dr < 1e-7 and dv < 1e-10, (dr, dv)
+    assert dr < 5e-7 and dv < 1e-9, (dr, dv)
 
 
 @pytest.mark.parametrize("ctrl", list(nb.ErrorControl))
