@@ -62,7 +62,7 @@ void nyxb_coop_build_host(int N, int M, const double* c_nm, const double* s_nm, 
     out.L = *std::max_element(load.begin(), load.end());
     out.kmax = 1;
     for (auto& c : cols) out.kmax = std::max(out.kmax, (int)c.size());
-    out.recs.assign((size_t)out.L * G, DevCoopRec{0, 0, 0, 0, 0, 0, 0, 0});
+    out.recs.assign((size_t)(out.L + 1) * G, DevCoopRec{0, 0, 0, 0, 0, 0, 0, 0});  // +1: prefetch pad
     out.col_start.assign((size_t)G * out.kmax, out.L + 1);
     out.col_m.assign((size_t)G * out.kmax, 1);
     for (int lane = 0; lane < G; ++lane) {
@@ -87,7 +87,10 @@ void nyxb_coop_build_host(int N, int M, const double* c_nm, const double* s_nm, 
                     if (n == m) { r.bq = std::sqrt(2.0 * (double)m + 3.0); r.cq = 0.0; }  // gravity_field.rs:168-173
                     else { r.bq = bnm(n + 1, m); r.cq = cnm(n + 1, m); }                    // gravity_field.rs:175-181
                 }
-                out.recs[(size_t)e * G + lane] = r;
+                // device layout: [entry][quarter][lane] of 16-byte pieces (one coalesced 16*G-byte segment per load)
+                double* base = reinterpret_cast<double*>(out.recs.data()) + (size_t)e * G * 8;
+                const double q[8] = {r.p1, r.p2, r.p3, r.p4, r.p5, r.p6, r.bq, r.cq};
+                for (int k = 0; k < 4; ++k) { base[(k * G + lane) * 2] = q[2 * k]; base[(k * G + lane) * 2 + 1] = q[2 * k + 1]; }
             }
         }
     }
@@ -96,8 +99,20 @@ void nyxb_coop_build_host(int N, int M, const double* c_nm, const double* s_nm, 
 // ------------------------------------------------------------------------------------------------
 // device
 // ------------------------------------------------------------------------------------------------
-#define COOP_CTA 128
+#ifndef COOP_CTA
+#define COOP_CTA 64   /* 9 CTAs x 64 threads per SM: 10 000 x 8 lanes fit in ONE wave of 148 SMs */
+#endif
+#ifndef COOP_MINB
+#define COOP_MINB 9
+#endif
 #define COOP_SM_FIXED 120  // kst[16*6] + ys[6] + ycur[6] + nxt[6] + er[6]
+
+// doubles of shared memory per trajectory group, padded to 8 (mod 16) doubles: the groups of one warp then
+// start 64 B apart modulo the 128-B bank row instead of on the same banks
+__host__ __device__ inline int coop_group_stride(int N) {
+    int s = COOP_SM_FIXED + 3 * (N + 3);
+    return s + ((8 - (s & 15)) & 15);
+}
 
 __device__ __forceinline__ double shfl_d(unsigned mask, double v, int src, int width) {
     return __shfl_sync(mask, v, src, width);
@@ -113,10 +128,11 @@ struct GroupCtx {
     unsigned gmask;
     double dry_mass, extra_mass, srp_area, drag_area;
     double cr, cd, pm;  // y[6..8]: constant without guidance (spacecraft.rs:248)
+    double hz;          // h * 0.0 of the current attempt: NaN-propagating stand-in for y[6..8] + h*0 (instance.rs:394)
 };
 
 __device__ __noinline__ int coop_nongrav(const DevSetup& S, const GroupCtx& g, long long t_ns, const double y[9], double acc[3]) {
-    double mass = g.dry_mass + g.pm + g.extra_mass;
+    double mass = g.dry_mass + y[8] + g.extra_mass;
     const bool has_force = S.has_srp || S.has_drag;
     if (has_force && !(mass > 0.0)) return NYXB_ERR_MASSLESS;
     double bpos[NYXB_MAX_BODIES][3];
@@ -128,11 +144,11 @@ __device__ __noinline__ int coop_nongrav(const DevSetup& S, const GroupCtx& g, l
 
 // Cooperative SpacecraftDynamics::eom at the stage state held in g.ys; lane c < 6 receives dy[c].
 template <int G>
-__device__ __noinline__ int coop_rhs(const DevSetup& S, const DevCoop& Cp, const GroupCtx& g, long long t_ns, double& dyc) {
+__device__ __forceinline__ int coop_rhs(const DevSetup& S, const DevCoop& Cp, const GroupCtx& g, long long t_ns, double& dyc) {
     double y[9];
 #pragma unroll
     for (int e = 0; e < 6; ++e) y[e] = g.ys[e];
-    y[6] = g.cr; y[7] = g.cd; y[8] = g.pm;
+    y[6] = g.cr + g.hz; y[7] = g.cd + g.hz; y[8] = g.pm + g.hz;
     // two-body + third bodies + SRP + drag: a few hundred flops, evaluated redundantly by every lane
     // (kept out of line so that its ephemeris scratch does not inflate the register count of the sum)
     double acc[3];
@@ -206,9 +222,13 @@ __device__ __noinline__ int coop_rhs(const DevSetup& S, const DevCoop& Cp, const
     const int* cm = Cp.col_m + g.lane * Cp.kmax;
     int ci = 0;
     int next_start = __ldg(cstart);
-    const double2* rec = reinterpret_cast<const double2*>(Cp.recs) + (size_t)g.lane * 4;
+    const double2* rec = reinterpret_cast<const double2*>(Cp.recs) + g.lane;
     const int L = Cp.L;
+    double2 n0 = __ldg(rec), n1 = __ldg(rec + G), n2 = __ldg(rec + 2 * G), n3 = __ldg(rec + 3 * G);
     for (int e = 0; e < L; ++e) {
+        const double2 q0 = n0, q1 = n1, q2 = n2, q3 = n3;
+        rec += (size_t)G * 4;
+        n0 = __ldg(rec); n1 = __ldg(rec + G); n2 = __ldg(rec + 2 * G); n3 = __ldg(rec + 3 * G);  // software prefetch
         if (e == next_start) {
             int m = __ldg(cm + ci);
             rr = g.rm[m - 1]; ii = g.im[m - 1];
@@ -217,8 +237,6 @@ __device__ __noinline__ int coop_rhs(const DevSetup& S, const DevCoop& Cp, const
             ++ci;
             next_start = (ci < Cp.kmax) ? __ldg(cstart + ci) : L + 1;
         }
-        double2 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
-        rec += (size_t)G * 4;
         double t1 = fma(q0.y, ii, q0.x * rr);
         double t2 = fma(q0.y, rr, -(q0.x * ii));
         double t3 = fma(q1.y, ii, q1.x * rr);
@@ -257,7 +275,7 @@ __device__ __noinline__ int coop_rhs(const DevSetup& S, const DevCoop& Cp, const
 }
 
 template <int G>
-__global__ void __launch_bounds__(COOP_CTA)
+__global__ void __launch_bounds__(COOP_CTA, COOP_MINB)
 nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop Cp, size_t n,
             const double* __restrict__ state, const double* __restrict__ consts,
             const long long* __restrict__ epoch0, long long end_epoch, long long* __restrict__ step_io,
@@ -267,7 +285,7 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
     const int tid = threadIdx.x;
     const int lane = tid % G, grp = tid / G;
     const int pw = S.grav.N + 3;
-    double* sm = sm_all + (size_t)grp * (COOP_SM_FIXED + 3 * pw);
+    double* sm = sm_all + (size_t)grp * coop_group_stride(S.grav.N);
     GroupCtx g;
     g.kst = sm; g.ys = sm + 96; g.ycur = sm + 102; g.nxt = sm + 108; g.er = sm + 114;
     g.rm = sm + COOP_SM_FIXED; g.im = g.rm + pw; g.rp = g.im + pw;
@@ -317,28 +335,29 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
         long long dt_ns = 0;
         double nx = 0.0;
         for (;;) {
-            if (lane < 6) g.ys[lane] = yc;
-            __syncwarp(g.gmask);
             double dyc;
-            rc = coop_rhs<G>(S, Cp, g, epoch, dyc);
-            ++n_rhs;
-            if (rc) break;
-            if (lane < 6) g.kst[lane] = dyc;
-            for (int i = 0; i < stages - 1; ++i) {
+            for (int i = 0; i < stages; ++i) {
+                // stage state y + h * sum_j a_ij k_j (instance.rs:376-394); stage 0 is y itself
                 if (lane < 6) {
-                    const double* arow = &S.tb.a[i * NYXB_MAX_STAGES];
-                    double w = 0.0;
-                    for (int j = 0; j <= i; ++j) {
-                        double a_ij = arow[j];
-                        if (a_ij != 0.0) w = fma(a_ij, g.kst[j * 6 + lane], w);
+                    double ysv = yc;
+                    if (i > 0) {
+                        const double* arow = &S.tb.a[(i - 1) * NYXB_MAX_STAGES];
+                        double w = 0.0;
+                        for (int j = 0; j < i; ++j) {
+                            double a_ij = arow[j];
+                            if (a_ij != 0.0) w = fma(a_ij, g.kst[j * 6 + lane], w);
+                        }
+                        ysv = fma(h, w, yc);
                     }
-                    g.ys[lane] = fma(h, w, yc);
+                    g.ys[lane] = ysv;
                 }
                 __syncwarp(g.gmask);
-                rc = coop_rhs<G>(S, Cp, g, epoch + dur_from_seconds(S.tb.c[i] * h), dyc);
+                g.hz = (i > 0) ? h * 0.0 : 0.0;
+                const long long t_ns = (i > 0) ? epoch + dur_from_seconds(S.tb.c[i - 1] * h) : epoch;
+                rc = coop_rhs<G>(S, Cp, g, t_ns, dyc);
                 ++n_rhs;
                 if (rc) break;
-                if (lane < 6) g.kst[(i + 1) * 6 + lane] = dyc;
+                if (lane < 6) g.kst[i * 6 + lane] = dyc;
             }
             if (rc) break;
             double er = 0.0;
@@ -358,7 +377,8 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
 #pragma unroll
             for (int e = 0; e < 6; ++e) { e9[e] = g.er[e]; c9[e] = g.nxt[e]; y9[e] = g.ycur[e]; }
             e9[6] = e9[7] = e9[8] = 0.0;
-            c9[6] = y9[6] = g.cr; c9[7] = y9[7] = g.cd; c9[8] = y9[8] = g.pm;
+            y9[6] = g.cr; y9[7] = g.cd; y9[8] = g.pm;
+            c9[6] = g.cr + g.hz; c9[7] = g.cd + g.hz; c9[8] = g.pm + g.hz;
             det_error = error_estimate(S.error_ctrl, e9, c9, y9);
             if (det_error <= S.tolerance || h <= S.min_step_s || det_attempts >= S.attempts) {
                 bool bad = false;
@@ -424,7 +444,7 @@ static cudaError_t launch_g(const DevSetup* S, const DevCoop* Cp, size_t n, cons
                             const long long* epoch0, long long end_epoch, long long* step_io, double* out_state,
                             long long* out_epoch, nyxb_details* out_details, int* out_status, cudaStream_t stream) {
     const int groups = COOP_CTA / G;
-    size_t smem = (size_t)groups * (COOP_SM_FIXED + 3 * (S->grav.N + 3)) * sizeof(double);
+    size_t smem = (size_t)groups * coop_group_stride(S->grav.N) * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(nyxb_k_coop<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     unsigned grid = (unsigned)((n + groups - 1) / groups);

@@ -60,7 +60,9 @@ __device__ static int derive(const DevSetup& S, Inst& in, long long& dt_ns, doub
             double ys[9];
 #pragma unroll
             for (int e = 0; e < 6; ++e) ys[e] = in.y[e] + h * wi[e];
-            ys[6] = in.y[6]; ys[7] = in.y[7]; ys[8] = in.y[8];
+            // components 6..8 have zero derivative: y + h*0 (NaN-propagating like the reference's 90-vector algebra, instance.rs:394)
+            const double hz = h * 0.0;
+            ys[6] = in.y[6] + hz; ys[7] = in.y[7] + hz; ys[8] = in.y[8] + hz;
             rc = eom_full(S, in.epoch_ns, S.tb.c[i] * h, ys, in.dry_mass, in.extra_mass, in.srp_area, in.drag_area, k[i + 1]);
             in.n_rhs++;
             if (rc) return rc;
@@ -68,6 +70,7 @@ __device__ static int derive(const DevSetup& S, Inst& in, long long& dt_ns, doub
         double err_est[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int e = 0; e < 9; ++e) next[e] = in.y[e];
+        { const double hz = h * 0.0; next[6] += hz; next[7] += hz; next[8] += hz; }
         for (int i = 0; i < stages; ++i) {
             if (!in.fixed) {
                 double cf = h * S.tb.e[i];
