@@ -334,11 +334,15 @@ __device__ inline void grav_accel_rows(const DevGrav& g, long long t_ns, const d
 //   accel_pre  : two-body + PointMasses                 orbital.rs:86-92, 213-247
 //   (gravity)  : GravityField                           gravity_field.rs:148-268
 //   accel_post : SolarPressure + Drag, each / mass      spacecraft.rs:238-243
-__device__ inline int accel_pre(const DevSetup& S, long long t_ns, const double y[9],
-                                double bpos[NYXB_MAX_BODIES][3], double acc[3]) {
+__device__ __forceinline__ void accel_two_body(const DevSetup& S, const double y[9], double acc[3]) {
     double rmag = norm3(y[0], y[1], y[2]);
     double fac = -S.mu_central / (rmag * rmag * rmag);
     acc[0] = fac * y[0]; acc[1] = fac * y[1]; acc[2] = fac * y[2];
+}
+
+// body positions at t_ns + PointMasses::eom added to acc (orbital.rs:213-247)
+__device__ inline int accel_point_masses(const DevSetup& S, long long t_ns, const double y[9],
+                                         double bpos[NYXB_MAX_BODIES][3], double acc[3]) {
     for (int j = 0; j < S.n_bodies; ++j)
         if (!body_position(S.bodies[j], t_ns, bpos[j])) return NYXB_ERR_EPHEMERIS;
     if (S.point_mass_mask) {
@@ -358,6 +362,12 @@ __device__ inline int accel_pre(const DevSetup& S, long long t_ns, const double 
         acc[0] += dx[0]; acc[1] += dx[1]; acc[2] += dx[2];
     }
     return 0;
+}
+
+__device__ inline int accel_pre(const DevSetup& S, long long t_ns, const double y[9],
+                                double bpos[NYXB_MAX_BODIES][3], double acc[3]) {
+    accel_two_body(S, y, acc);
+    return accel_point_masses(S, t_ns, y, bpos, acc);
 }
 
 __device__ inline void accel_post(const DevSetup& S, long long t_ns, const double y[9],
