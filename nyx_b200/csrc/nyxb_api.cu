@@ -41,11 +41,20 @@ struct nyxb_engine {
     std::vector<void*> dev_allocs;
     long long launches = 0;
     double last_ms = 0.0;
+    // grow-only device staging slab of the host-pointer entry point (no cudaMalloc/cudaFree per call)
+    size_t cap = 0;
+    double* d_f64 = nullptr;
+    long long* d_i64 = nullptr;
+    nyxb_details* d_det = nullptr;
+    int* d_status = nullptr;
+    cudaStream_t stream = nullptr;
     std::vector<double> h_cnm, h_snm;      // host copies for building cooperative tables lazily
     std::map<int, DevCoop> coop;           // lanes -> device tables
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ~nyxb_engine() {
         for (void* p : dev_allocs) cudaFree(p);
+        cudaFree(d_f64); cudaFree(d_i64); cudaFree(d_det); cudaFree(d_status);
+        if (stream) cudaStreamDestroy(stream);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
     }
@@ -317,19 +326,25 @@ extern "C" int32_t nyxb_propagate_batch(nyxb_engine* eng, size_t n, const double
     }
     if (n == 0) return NYXB_RC_OK;
     CUDA_TRY(cudaSetDevice(eng->device));
-    // one device slab: [state 9n | consts 4n | out_state 9n] doubles, [epoch0 n | out_epoch n | step n] i64, details, status
-    double* d_f64 = nullptr;
-    long long* d_i64 = nullptr;
-    nyxb_details* d_det = nullptr;
-    int* d_status = nullptr;
-    cudaStream_t st = 0;
+    // device slab: [state 9n | consts 4n | out_state 9n] doubles, [epoch0 n | out_epoch n | step n] i64, details, status
     int32_t rc = NYXB_RC_OK;
     cudaError_t ce;
-#define TRY2(x) do { ce = (x); if (ce != cudaSuccess) { set_err(std::string(#x) + ": " + cudaGetErrorString(ce)); rc = NYXB_RC_CUDA; goto done; } } while (0)
-    TRY2(cudaMalloc(&d_f64, sizeof(double) * 22 * n));
-    TRY2(cudaMalloc(&d_i64, sizeof(long long) * 3 * n));
-    TRY2(cudaMalloc(&d_det, sizeof(nyxb_details) * n));
-    TRY2(cudaMalloc(&d_status, sizeof(int) * n));
+#define TRY2(x) do { ce = (x); if (ce != cudaSuccess) { set_err(std::string(#x) + ": " + cudaGetErrorString(ce)); return NYXB_RC_CUDA; } } while (0)
+    if (!eng->stream) TRY2(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+    if (n > eng->cap) {
+        cudaFree(eng->d_f64); cudaFree(eng->d_i64); cudaFree(eng->d_det); cudaFree(eng->d_status);
+        eng->d_f64 = nullptr; eng->d_i64 = nullptr; eng->d_det = nullptr; eng->d_status = nullptr; eng->cap = 0;
+        TRY2(cudaMalloc(&eng->d_f64, sizeof(double) * 22 * n));
+        TRY2(cudaMalloc(&eng->d_i64, sizeof(long long) * 3 * n));
+        TRY2(cudaMalloc(&eng->d_det, sizeof(nyxb_details) * n));
+        TRY2(cudaMalloc(&eng->d_status, sizeof(int) * n));
+        eng->cap = n;
+    }
+    double* d_f64 = eng->d_f64;
+    long long* d_i64 = eng->d_i64;
+    nyxb_details* d_det = eng->d_det;
+    int* d_status = eng->d_status;
+    cudaStream_t st = eng->stream;
     TRY2(cudaMemcpyAsync(d_f64, state_soa, sizeof(double) * 9 * n, cudaMemcpyHostToDevice, st));
     TRY2(cudaMemcpyAsync(d_f64 + 9 * n, consts_soa, sizeof(double) * 4 * n, cudaMemcpyHostToDevice, st));
     TRY2(cudaMemcpyAsync(d_i64, epoch0_ns, sizeof(long long) * n, cudaMemcpyHostToDevice, st));
@@ -337,7 +352,7 @@ extern "C" int32_t nyxb_propagate_batch(nyxb_engine* eng, size_t n, const double
     TRY2(cudaEventRecord(eng->ev0, st));
     rc = launch(eng, n, d_f64, d_f64 + 9 * n, (const int64_t*)d_i64, end_epoch_ns, step_ns ? (int64_t*)(d_i64 + 2 * n) : nullptr,
                 d_f64 + 13 * n, (int64_t*)(d_i64 + n), d_det, d_status, st);
-    if (rc != NYXB_RC_OK) goto done;
+    if (rc != NYXB_RC_OK) return rc;
     TRY2(cudaEventRecord(eng->ev1, st));
     TRY2(cudaMemcpyAsync(out_state_soa, d_f64 + 13 * n, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost, st));
     TRY2(cudaMemcpyAsync(out_epoch_ns, d_i64 + n, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
@@ -349,8 +364,6 @@ extern "C" int32_t nyxb_propagate_batch(nyxb_engine* eng, size_t n, const double
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, eng->ev0, eng->ev1) == cudaSuccess) eng->last_ms = ms;
     }
-done:
-    cudaFree(d_f64); cudaFree(d_i64); cudaFree(d_det); cudaFree(d_status);
     return rc;
 #undef TRY2
 }

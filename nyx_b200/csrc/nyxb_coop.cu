@@ -129,6 +129,16 @@ __device__ __forceinline__ double shfl_xor_d(unsigned mask, double v, int lanema
 
 // ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int lds_s32(unsigned addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -190,58 +200,49 @@ __device__ __forceinline__ int coop_rhs(const DevSetup& S, const double2* __rest
                                         const double* __restrict__ a_diag, const int* __restrict__ cs,
                                         const int* __restrict__ cm, const GroupCtx& g, const RotBase& rb,
                                         double dt_s, long long t_ns, double& dyc) {
-    double y[9];
-#pragma unroll
-    for (int e = 0; e < 6; ++e) y[e] = g.ys[e];
-    y[6] = g.cr + g.hz; y[7] = g.cd + g.hz; y[8] = g.pm + g.hz;
     const DevGrav& gv = S.grav;
-
-    // ---- inertial -> body-fixed DCM at the stage time
-    double R[9];
-    if (gv.rot.kind == 0) {
-        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
-    } else {
-        const double da = rb.ra_dot * dt_s, dd = rb.dec_dot * dt_s, dw = rb.w_dot * dt_s;
-        const double sa = fma(rb.ca, da, rb.sa), ca = fma(-rb.sa, da, rb.ca);
-        const double sd = fma(rb.cd, dd, rb.sd), cd = fma(-rb.sd, dd, rb.cd);
-        double sdl, cdl;
-        if (fabs(dw) < 0.02) {
-            const double z = dw * dw;
-            sdl = dw * fma(z, fma(z, 1.0 / 120.0, -1.0 / 6.0), 1.0);
-            cdl = fma(z, fma(z, fma(z, -1.0 / 720.0, 1.0 / 24.0), -0.5), 1.0);
+    double inv_r, rho, ub;
+    {
+        // ---- inertial -> body-fixed DCM at the stage time (angle addition from the step-epoch base)
+        double R[9];
+        if (gv.rot.kind == 0) {
+            R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
         } else {
-            det_sincos(dw, sdl, cdl);
+            const double da = rb.ra_dot * dt_s, dd = rb.dec_dot * dt_s, dw = rb.w_dot * dt_s;
+            const double sa = fma(rb.ca, da, rb.sa), ca = fma(-rb.sa, da, rb.ca);
+            const double sd = fma(rb.cd, dd, rb.sd), cd = fma(-rb.sd, dd, rb.cd);
+            double sdl, cdl;
+            if (fabs(dw) < 0.02) {
+                const double z = dw * dw;
+                sdl = dw * fma(z, fma(z, 1.0 / 120.0, -1.0 / 6.0), 1.0);
+                cdl = fma(z, fma(z, fma(z, -1.0 / 720.0, 1.0 / 24.0), -0.5), 1.0);
+            } else {
+                det_sincos(dw, sdl, cdl);
+            }
+            const double sw = fma(rb.sw, cdl, rb.cw * sdl), cw = fma(rb.cw, cdl, -(rb.sw * sdl));
+            const double b00 = -sa, b01 = ca;
+            const double b10 = -(sd * ca), b11 = -(sd * sa), b12 = cd;
+            R[0] = fma(cw, b00, sw * b10); R[1] = fma(cw, b01, sw * b11); R[2] = sw * b12;
+            R[3] = fma(cw, b10, -(sw * b00)); R[4] = fma(cw, b11, -(sw * b01)); R[5] = cw * b12;
+            R[6] = cd * ca; R[7] = cd * sa; R[8] = sd;
         }
-        const double sw = fma(rb.sw, cdl, rb.cw * sdl), cw = fma(rb.cw, cdl, -(rb.sw * sdl));
-        const double b00 = -sa, b01 = ca;
-        const double b10 = -(sd * ca), b11 = -(sd * sa), b12 = cd;
-        R[0] = fma(cw, b00, sw * b10); R[1] = fma(cw, b01, sw * b11); R[2] = sw * b12;
-        R[3] = fma(cw, b10, -(sw * b00)); R[4] = fma(cw, b11, -(sw * b01)); R[5] = cw * b12;
-        R[6] = cd * ca; R[7] = cd * sa; R[8] = sd;
-    }
-    const double rb0 = fma(R[2], y[2], fma(R[1], y[1], R[0] * y[0]));
-    const double rb1 = fma(R[5], y[2], fma(R[4], y[1], R[3] * y[0]));
-    const double rb2 = fma(R[8], y[2], fma(R[7], y[1], R[6] * y[0]));
-    const double r_ = norm3(rb0, rb1, rb2);
-    const double inv_r = 1.0 / r_;
-    const double s_ = rb0 * inv_r, t_ = rb1 * inv_r, u_ = rb2 * inv_r;
-    const double rho = gv.r_eq * inv_r;
-
-    // ---- two-body (orbital.rs:86-92) from the same 1/r; third bodies / SRP / drag out of line when present
-    double acc[3];
-    {
-        const double fac = -S.mu_central * inv_r * inv_r * inv_r;
-        acc[0] = fac * y[0]; acc[1] = fac * y[1]; acc[2] = fac * y[2];
-    }
-    if (S.n_bodies > 0 || S.has_srp || S.has_drag) {
-        int rc = coop_extra(S, g, t_ns, y, acc);
-        if (rc) return rc;
-    }
-
-    // ---- power tables (cos,sin)(k lambda) cos^k(phi) and rho^k: lane computes k = lane, lane+G, ...
-    {
+        const double y0 = g.ys[0], y1 = g.ys[1], y2 = g.ys[2];
+        const double rb0 = fma(R[2], y2, fma(R[1], y1, R[0] * y0));
+        const double rb1 = fma(R[5], y2, fma(R[4], y1, R[3] * y0));
+        const double rb2 = fma(R[8], y2, fma(R[7], y1, R[6] * y0));
+        const double r_ = norm3(rb0, rb1, rb2);
+        inv_r = 1.0 / r_;
+        rho = gv.r_eq * inv_r;
+        ub = (rb2 * inv_r) * rho;
+        // park the DCM in the group's scratch (nxt/er are idle during the stages): it is only needed again after
+        // the column walk, and keeping it in registers would push the walk's live set past the occupancy target
+        if (g.lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 9; ++q) g.nxt[q] = R[q];
+        }
+        // power-table seeds
         double zr = 1.0, zi = 0.0, pr = 1.0;
-        double bzr = s_, bzi = t_, bp = rho;
+        double bzr = rb0 * inv_r, bzi = rb1 * inv_r, bp = rho;
 #pragma unroll
         for (int bit = 1; bit < G; bit <<= 1) {
             if (g.lane & bit) {
@@ -257,7 +258,7 @@ __device__ __forceinline__ int coop_rhs(const DevSetup& S, const double2* __rest
         }
         const int top = gv.N + 1;
         for (int k = g.lane; k <= top; k += G) {
-            g.rm[k] = zr; g.im[k] = zi; g.rp[k] = pr;
+            g.rm[k] = zr; g.im[k] = zi; g.rp[k] = pr * a_diag[k];  // rho^k * A[k][k]: the seed of column k
             const double nzr = fma(zr, bzr, -(zi * bzi));
             zi = fma(zr, bzi, zi * bzr);
             zr = nzr;
@@ -267,12 +268,20 @@ __device__ __forceinline__ int coop_rhs(const DevSetup& S, const double2* __rest
     __syncwarp(g.gmask);
 
     // ---- column walk; the (A, cos, sin) seed of the NEXT column is prefetched one column ahead
-    const double ub = u_ * rho, r2 = rho * rho;
+    double r2 = rho * rho;
+    // keep the loop invariants in registers: ptxas otherwise rematerialises them (two extra DMULs per entry and
+    // ~30 integer instructions of shared-memory address arithmetic per column start)
+    asm volatile("" : "+d"(r2), "+d"(ub));
+    unsigned a_rm = smem_u32(g.rm), a_cs = smem_u32(cs);
+    asm volatile("" : "+r"(a_rm), "+r"(a_cs));
+    const unsigned pw8 = (unsigned)(gv.N + 3) * 8u;   // rm -> im -> rp stride in bytes
+    const unsigned cm_off = (unsigned)((cm - cs) * 4);
     double X = 0.0, Y = 0.0, Z = 0.0, W = 0.0, A = 0.0, Ap = 0.0, rr = 0.0, ii = 0.0;
     int ci = 0;
-    int next_start = cs[0];
-    int mn = cm[0];
-    double An0 = g.rp[mn] * a_diag[mn], rrn = g.rm[mn - 1], iin = g.im[mn - 1];
+    int next_start = lds_s32(a_cs);
+    int mn = lds_s32(a_cs + cm_off);
+    double An0 = lds_f64(a_rm + 2 * pw8 + mn * 8);
+    double rrn = lds_f64(a_rm + mn * 8 - 8), iin = lds_f64(a_rm + pw8 + mn * 8 - 8);
     const double2* rec = recs + g.lane;
     double2 n0 = rec[0], n1 = rec[G], n2 = rec[2 * G], n3 = rec[3 * G];
     for (int e = 0; e < L; ++e) {
@@ -282,9 +291,10 @@ __device__ __forceinline__ int coop_rhs(const DevSetup& S, const double2* __rest
         if (e == next_start) {
             A = An0; rr = rrn; ii = iin; Ap = 0.0;
             ++ci;
-            next_start = cs[ci];  // sentinel L+1 after the last column
-            mn = cm[ci];          // sentinel column 1
-            An0 = g.rp[mn] * a_diag[mn]; rrn = g.rm[mn - 1]; iin = g.im[mn - 1];
+            next_start = lds_s32(a_cs + ci * 4);          // sentinel L+1 after the last column
+            mn = lds_s32(a_cs + cm_off + ci * 4);         // sentinel column 1
+            An0 = lds_f64(a_rm + 2 * pw8 + mn * 8);
+            rrn = lds_f64(a_rm + mn * 8 - 8); iin = lds_f64(a_rm + pw8 + mn * 8 - 8);
         }
         const double t1 = fma(q0.y, ii, q0.x * rr);
         const double t2 = fma(q0.y, rr, -(q0.x * ii));
@@ -305,14 +315,32 @@ __device__ __forceinline__ int coop_rhs(const DevSetup& S, const double2* __rest
         Z += shfl_xor_d(g.gmask, Z, off, G);
         W += shfl_xor_d(g.gmask, W, off, G);
     }
+    // ---- reload the stage state and the DCM, assemble the acceleration
+    double y[9];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) y[e] = g.ys[e];
+    y[6] = g.cr + g.hz; y[7] = g.cd + g.hz; y[8] = g.pm + g.hz;
+    double R[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) R[q] = g.nxt[q];
+    const double s_ = fma(R[2], y[2], fma(R[1], y[1], R[0] * y[0])) * inv_r;
+    const double t_ = fma(R[5], y[2], fma(R[4], y[1], R[3] * y[0])) * inv_r;
+    const double u_ = fma(R[8], y[2], fma(R[7], y[1], R[6] * y[0])) * inv_r;
     // rr_n A[n][m] = K0 rho (rho^n A),  rr_{n-1} A[n][m] = K0 (rho^n A),  K0 = mu / (r R_eq)
     const double K0 = gv.mu * inv_r / gv.r_eq;
     const double K1 = K0 * rho;
     const double aw = -K0 * W;
     const double ab0 = fma(aw, s_, K1 * X), ab1 = fma(aw, t_, K1 * Y), ab2 = fma(aw, u_, K1 * Z);
-    acc[0] += fma(R[6], ab2, fma(R[3], ab1, R[0] * ab0));
-    acc[1] += fma(R[7], ab2, fma(R[4], ab1, R[1] * ab0));
-    acc[2] += fma(R[8], ab2, fma(R[5], ab1, R[2] * ab0));
+    // two-body (orbital.rs:86-92) from the same 1/r
+    const double fac = -S.mu_central * inv_r * inv_r * inv_r;
+    double acc[3];
+    acc[0] = fma(fac, y[0], fma(R[6], ab2, fma(R[3], ab1, R[0] * ab0)));
+    acc[1] = fma(fac, y[1], fma(R[7], ab2, fma(R[4], ab1, R[1] * ab0)));
+    acc[2] = fma(fac, y[2], fma(R[8], ab2, fma(R[5], ab1, R[2] * ab0)));
+    if (S.n_bodies > 0 || S.has_srp || S.has_drag) {
+        int rc = coop_extra(S, g, t_ns, y, acc);
+        if (rc) return rc;
+    }
     double out = y[3];
     if (g.lane == 1) out = y[4];
     else if (g.lane == 2) out = y[5];
@@ -462,6 +490,7 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
             if (rc) break;
             double er = 0.0;
             nx = yc;
+            __syncwarp(g.gmask);  // the last stage's readers of the parked DCM (nxt) are done
             if (lane < 6) {
                 for (int i = 0; i < stages; ++i) {
                     const double ki = g.kst[i * 6 + lane];
