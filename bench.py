@@ -52,7 +52,8 @@ def parse_args():
     p.add_argument("--degree", type=int, default=21)
     p.add_argument("--mode", default="fast", choices=["fast", "strict"])
     p.add_argument("--lanes", type=int, default=0)
-    p.add_argument("--cpu-sample", type=int, default=192, help="trajectories in the bounded CPU-baseline sample")
+    p.add_argument("--cpu-sample", type=int, default=0,
+                   help="trajectories in the bounded CPU-baseline sample (0: 32 per host core, ~10 s of CPU work)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     return p.parse_args()
 
@@ -137,6 +138,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     import nyx_b200 as nb
 
+    if args.cpu_sample <= 0:
+        args.cpu_sample = 32 * (os.cpu_count() or 8)
     workload = (f"C2: {args.n_traj} LEO trajectories/GPU (alt 300 km, e 0.015, i 68.5 deg; N(0, 1 km / 1 m/s) dispersions), "
                 f"two-body + JGM-3 {args.degree}x{args.degree}, adaptive RK89 (IntegratorOptions::default), {args.span_days:g}-day span")
     fps = flops_per_step(args.degree)
