@@ -2,6 +2,7 @@
 // upload, launches.  Host side of `Propagator::new` + `MonteCarlo::run_until_epoch`'s fan-out.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -289,7 +290,10 @@ static int32_t launch(nyxb_engine* e, size_t n, const double* state, const doubl
     if (lanes > 1) {
         const DevCoop* cp = get_coop(e, lanes);
         if (!cp) { set_err("cooperative table upload failed"); return NYXB_RC_CUDA; }
-        err = nyxb_launch_coop(&e->S, cp, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io,
+        // two trajectories per lane group once the ensemble is large enough to still fill the SMs with half the threads
+        int T = (n * (size_t)lanes >= 65536) ? 2 : 1;
+        if (const char* ev = getenv("NYXB_COOP_T")) { int v = atoi(ev); if (v == 1 || v == 2) T = v; }
+        err = nyxb_launch_coop(&e->S, cp, T, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io,
                                out_state, (long long*)out_epoch, out_details, out_status, stream);
     } else if (e->mode == NYXB_MODE_STRICT) {
         err = nyxb_launch_thread_strict(&e->S, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io,

@@ -29,7 +29,8 @@ struct CoopHost {
 
 void nyxb_coop_build_host(int N, int M, const double* c_nm, const double* s_nm, int G, CoopHost& out);
 
-extern "C" cudaError_t nyxb_launch_coop(const DevSetup* S, const DevCoop* Cp, size_t n, const double* state,
+// T = trajectories integrated together by one lane group (1 or 2: register blocking over the coefficient records)
+extern "C" cudaError_t nyxb_launch_coop(const DevSetup* S, const DevCoop* Cp, int T, size_t n, const double* state,
                                         const double* consts, const long long* epoch0, long long end_epoch,
                                         long long* step_io, double* out_state, long long* out_epoch,
                                         nyxb_details* out_details, int* out_status, cudaStream_t stream);

@@ -1,13 +1,13 @@
 #!/bin/bash
-# Run on the GPU box: sweep libnyxb variants (csrc/variants/*.so) over the quick C2 bench and print one line each.
+# Run on the GPU box: quick C2 bench over (lanes, trajectories-per-group) and print one line each.
 mkdir -p gpurun_out
 SPAN=${SPAN:-0.25}
-for so in nyx_b200/csrc/variants/libnyxb_*.so; do
+for T in ${TS:-1 2}; do
   for L in ${LANES:-8}; do
-    NYXB_LIBRARY=$so python bench.py --steps 2 --warmup 1 --span-days $SPAN --no-cpu-baseline --lanes $L 2> gpurun_out/sweep_err.log | tail -1 | python -c "
+    NYXB_COOP_T=$T python bench.py --steps 2 --warmup 1 --span-days $SPAN --no-cpu-baseline --lanes $L 2> gpurun_out/sweep_err.log | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
-print('$so', 'lanes', $L, 'value %.3e' % d['value'], 'e2e %.3e' % d['e2e']['value'], 'frac %.3f' % d['roofline']['frac'], 'kern_ms %.1f' % d['roofline']['kernel_ms'], d['clocks']['sm_mhz'])
+print('T', $T, 'lanes', $L, 'value %.3e' % d['value'], 'e2e %.3e' % d['e2e']['value'], 'frac %.3f' % d['roofline']['frac'], 'kern_ms %.1f' % d['roofline']['kernel_ms'], d['clocks']['sm_mhz'])
 " | tee -a gpurun_out/sweep.log
   done
 done

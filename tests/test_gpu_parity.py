@@ -118,6 +118,33 @@ def test_cooperative_kernel_vs_oracle(oracle, lanes, degree, order):
     assert max_dr_dv(out, out1)[0] < 5e-7
 
 
+@pytest.mark.parametrize("n", [1, 2, 33, 64])
+def test_cooperative_kernel_two_trajectories_per_group(oracle, monkeypatch, n):
+    """Register-blocked variant (T = 2 trajectories per lane group, NYXB_COOP_T=2): odd ensemble sizes leave a group
+    with an absent partner; trajectories of a pair end at different step counts and retry independently."""
+    monkeypatch.setenv("NYXB_COOP_T", "2")
+    mc, (st, cs, ep) = leo_ensemble(n, seed=13)
+    ep = ep + (np.arange(n, dtype=np.int64) % 5) * 600 * S  # different start epochs => different step counts
+    gd = nb.GravityFieldData.from_fixture("jgm3_70x70", 21, 21, nb.IAU_EARTH_FRAME)
+    dyn = nb.SpacecraftDynamics.new(nb.OrbitalDynamics.from_model(nb.GravityField.new(gd)))
+    end = 4 * 3600 * S
+    for opts, tol in ((nb.IntegratorOptions.default(), 5e-7), (nb.IntegratorOptions.with_fixed_step_s(45.0), 5e-9),
+                      # forced rejections: a too-large initial step with a tight tolerance
+                      (nb.IntegratorOptions(init_step=600 * nb.Unit.Second, tolerance=1e-13), 5e-7)):
+        prop = nb.Propagator.rk89(dyn, opts, mode=nb.MODE_FAST)
+        eng = prop.engine(nb.EARTH_J2000, None)
+        eng.set_lanes(8)
+        out, out_ep, det, status = eng.propagate_batch(st, cs, ep, end)
+        ref, ref_ep, ref_det, ref_status = oracle_run(oracle, prop, nb.EARTH_J2000, None, st, cs, ep, end)
+        assert np.array_equal(status, ref_status) and np.array_equal(out_ep, ref_ep)
+        assert max_dr_dv(out, ref)[0] < tol, (opts, max_dr_dv(out, ref))
+        assert np.abs(det["n_steps"] - ref_det["n_steps"]).max() <= 1
+        assert np.abs(det["n_rejected"] - ref_det["n_rejected"]).max() <= 1
+    monkeypatch.setenv("NYXB_COOP_T", "1")
+    out1, _, det1, _ = eng.propagate_batch(st, cs, ep, end)
+    assert max_dr_dv(out, out1)[0] < 5e-7
+
+
 def test_cooperative_kernel_fixed_step_tight(oracle):
     """With a FIXED step the step sequence cannot diverge, so the cooperative kernel must agree with the
     oracle to round-off (5e-9 km over 6 h), which pins the regrouped harmonic sum itself."""
