@@ -177,7 +177,7 @@ extern "C" nyxb_engine* nyxb_engine_create(const nyxb_dynamics* dyn, const nyxb_
         }
         const int N = g.degree, np2 = N + 2;
         S.has_grav = 1;
-        S.grav.N = N; S.grav.M = g.order; S.grav.mu = g.mu_km3_s2; S.grav.r_eq = g.r_eq_km;
+        S.grav.N = N; S.grav.M = g.order; S.grav.mu = g.mu_km3_s2; S.grav.r_eq = g.r_eq_km; S.grav.inv_r_eq = 1.0 / g.r_eq_km;
         S.grav.rot = pack_rot(g.rot);
         // GravityField::new gravity_field.rs:52-92 (same formulas; sqrt and / are correctly rounded)
         std::vector<double> adiag(N + 3), offd(N + 2);

@@ -35,10 +35,10 @@ __host__ __device__ inline int coop_traj_stride(int N) {
     int s = COOP_SM_FIXED + 3 * (N + 3);
     return s + ((8 - (s & 15)) & 15);
 }
-// bytes of the CTA-shared table region: records [(L+1)][4][G] double2, then a_diag[N+3], col_start/col_m [G][kmax+1]
+// bytes of the CTA-shared table region: records [(L+1)][4][G] double2, then a_diag[N+3], col_start/col_m [G][kmax+2]
 __host__ __device__ inline size_t coop_rec_bytes(int L, int G) { return (size_t)(L + 1) * G * 64; }
 __host__ __device__ inline size_t coop_meta_bytes(int N, int G, int kmax) {
-    size_t b = (size_t)(N + 3) * 8 + (size_t)2 * G * (kmax + 1) * 4;
+    size_t b = (size_t)(N + 3) * 8 + (size_t)2 * G * (kmax + 2) * 4;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -147,8 +147,7 @@ __device__ __forceinline__ void coop_rhs(const DevSetup& S, const double2* __res
         const double rb0 = fma(R[2], y2, fma(R[1], y1, R[0] * y0));
         const double rb1 = fma(R[5], y2, fma(R[4], y1, R[3] * y0));
         const double rb2 = fma(R[8], y2, fma(R[7], y1, R[6] * y0));
-        const double r_ = norm3(rb0, rb1, rb2);
-        inv_r[t] = 1.0 / r_;
+        inv_r[t] = rsqrt(fma(rb2, rb2, fma(rb1, rb1, rb0 * rb0)));  // one Newton chain instead of sqrt + division
         rho[t] = gv.r_eq * inv_r[t];
         ub[t] = (rb2 * inv_r[t]) * rho[t];
         r2[t] = rho[t] * rho[t];
@@ -194,7 +193,7 @@ __device__ __forceinline__ void coop_rhs(const DevSetup& S, const double2* __res
     const unsigned pw8 = (unsigned)(gv.N + 3) * 8u;  // rm -> im -> rp stride in bytes
     double X[T], Y[T], Z[T], W[T], A[T], Ap[T], rr[T], ii[T], An0[T], rrn[T], iin[T];
     int ci = 0;
-    int next_start = lds_s32(a_cs);
+    int next_start = lds_s32(a_cs), start_after = lds_s32(a_cs + 4);
     {
         const int mn = lds_s32(a_cs + cm_off);
 #pragma unroll
@@ -212,7 +211,8 @@ __device__ __forceinline__ void coop_rhs(const DevSetup& S, const double2* __res
         n0 = rec[0]; n1 = rec[G]; n2 = rec[2 * G]; n3 = rec[3 * G];  // software prefetch (table padded by one entry)
         if (e == next_start) {
             ++ci;
-            next_start = lds_s32(a_cs + ci * 4);                // sentinel L+1 after the last column
+            next_start = start_after;                           // sentinel L+1 after the last column
+            start_after = lds_s32(a_cs + ci * 4 + 4);           // (table has two sentinel slots)
             const int mn = lds_s32(a_cs + cm_off + ci * 4);     // sentinel column 1
 #pragma unroll
             for (int t = 0; t < T; ++t) {
@@ -257,7 +257,7 @@ __device__ __forceinline__ void coop_rhs(const DevSetup& S, const double2* __res
         const double t_ = fma(R[5], y[2], fma(R[4], y[1], R[3] * y[0])) * inv_r[t];
         const double u_ = fma(R[8], y[2], fma(R[7], y[1], R[6] * y[0])) * inv_r[t];
         // rr_n A[n][m] = K0 rho (rho^n A),  rr_{n-1} A[n][m] = K0 (rho^n A),  K0 = mu / (r R_eq)
-        const double K0 = gv.mu * inv_r[t] / gv.r_eq;
+        const double K0 = (gv.mu * gv.inv_r_eq) * inv_r[t];
         const double K1 = K0 * rho[t];
         const double aw = -K0 * W[t];
         const double ab0 = fma(aw, s_, K1 * X[t]), ab1 = fma(aw, t_, K1 * Y[t]), ab2 = fma(aw, u_, K1 * Z[t]);
@@ -297,7 +297,7 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
     unsigned char* meta = smem_raw + rec_bytes;
     double* sm_adiag = reinterpret_cast<double*>(meta);
     int* sm_cs = reinterpret_cast<int*>(meta + (size_t)(N + 3) * 8);
-    int* sm_cm = sm_cs + G * (Cp.kmax + 1);
+    int* sm_cm = sm_cs + G * (Cp.kmax + 2);
     if (SMEM_TABLE) {
         if (tid == 0) mbar_init(&tma_bar, 1);
         __syncthreads();
@@ -307,16 +307,16 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
         }
     }
     for (int k = tid; k < N + 3; k += COOP_CTA) sm_adiag[k] = __ldg(S.grav.a_diag + k);
-    for (int k = tid; k < G * (Cp.kmax + 1); k += COOP_CTA) {
-        const int l = k / (Cp.kmax + 1), q = k % (Cp.kmax + 1);
+    for (int k = tid; k < G * (Cp.kmax + 2); k += COOP_CTA) {
+        const int l = k / (Cp.kmax + 2), q = k % (Cp.kmax + 2);
         sm_cs[k] = (q < Cp.kmax) ? __ldg(Cp.col_start + l * Cp.kmax + q) : Cp.L + 1;
         sm_cm[k] = (q < Cp.kmax) ? __ldg(Cp.col_m + l * Cp.kmax + q) : 1;
     }
     if (SMEM_TABLE) mbar_wait(&tma_bar, 0);
     __syncthreads();
     const double2* recs = SMEM_TABLE ? reinterpret_cast<const double2*>(smem_raw) : reinterpret_cast<const double2*>(Cp.recs);
-    const unsigned a_cs = smem_u32(sm_cs + lane * (Cp.kmax + 1));
-    const unsigned cm_off = (unsigned)(G * (Cp.kmax + 1) * 4);
+    const unsigned a_cs = smem_u32(sm_cs + lane * (Cp.kmax + 2));
+    const unsigned cm_off = (unsigned)(G * (Cp.kmax + 2) * 4);
 
     // ---- trajectories of this group: pair index strided over the grid so that every SM gets the same share
     const size_t n_sets = (n + T - 1) / T;
@@ -420,12 +420,14 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
                     double ysv = yc[t];
                     if (i > 0) {
                         const double* arow = &S.tb.a[(i - 1) * NYXB_MAX_STAGES];
-                        double w = 0.0;
-                        for (int j = 0; j < i; ++j) {
-                            const double a_ij = arow[j];
-                            if (a_ij != 0.0) w = fma(a_ij, g[t].kst[j * 6 + lane], w);
+                        double w0 = 0.0, w1 = 0.0;  // two chains: the sum is latency-bound otherwise
+                        int j = 0;
+                        for (; j + 1 < i; j += 2) {
+                            w0 = fma(arow[j], g[t].kst[j * 6 + lane], w0);
+                            w1 = fma(arow[j + 1], g[t].kst[(j + 1) * 6 + lane], w1);
                         }
-                        ysv = fma(h[t], w, yc[t]);
+                        if (j < i) w0 = fma(arow[j], g[t].kst[j * 6 + lane], w0);
+                        ysv = fma(h[t], w0 + w1, yc[t]);
                     }
                     g[t].ys[lane] = ysv;
                 }

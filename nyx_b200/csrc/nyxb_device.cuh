@@ -43,7 +43,7 @@ struct __align__(16) DevHarm {
 
 struct DevGrav {
     int N, M;
-    double mu, r_eq;
+    double mu, r_eq, inv_r_eq;
     DevRotation rot;
     const DevHarm* tab;      // (N+2)(N+3)/2 records
     const double* a_diag;    // [N+3]   gravity_field.rs:61-66
