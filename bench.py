@@ -55,25 +55,59 @@ def parse_args():
     p.add_argument("--cpu-sample", type=int, default=0,
                    help="trajectories in the bounded CPU-baseline sample (0: 32 per host core, ~10 s of CPU work)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-strict", action="store_true", help="skip the extra bit-parity (STRICT mode) pass at N=1")
+    p.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
+                   help="c2 = BASELINE configs[1] (the metric's workload); c3/c4 = configs[2]/[3], reported for context only")
     return p.parse_args()
 
 
 def build_workload(args, n_total, nb):
-    """C2 of SURVEY.md §8(d): example-01 orbit + N(0, diag(1 km, 1 m/s)) dispersions, seed 0."""
-    frame = nb.EARTH_J2000
-    gd = nb.GravityFieldData.from_fixture("jgm3_70x70", args.degree, args.degree, nb.IAU_EARTH_FRAME)
-    dyn = nb.SpacecraftDynamics.new(nb.OrbitalDynamics.from_model(nb.GravityField.new(gd)))
-    # alt 300 km, e 0.015, i 68.5, RAAN 65.2, AoP 75, TA 0 (examples/01_orbit_prop/main.rs:52-53)
-    orbit = nb.Orbit.keplerian(6378.1363 + 300.0, 0.015, 68.5, 65.2, 75.0, 0.0, 0, frame)
-    template = nb.Spacecraft(orbit=orbit, mass=nb.Mass(1000.0, 0.0, 0.0))
-    mvn = nb.MvnSpacecraft.from_cartesian_std(template, 1.0, 1e-3)
+    """Synthetic inputs of SURVEY.md §8(d); returns (frame, dynamics, almanac, state[9][n], consts[4][n], epoch0[n])."""
     rng = np.random.Generator(np.random.PCG64(0))
+    almanac = None
+    if args.workload == "c2":
+        # C2: example-01 orbit (examples/01_orbit_prop/main.rs:52-53) + N(0, diag(1 km, 1 m/s)), JGM-3 NxN
+        frame = nb.EARTH_J2000
+        gd = nb.GravityFieldData.from_fixture("jgm3_70x70", args.degree, args.degree, nb.IAU_EARTH_FRAME)
+        dyn = nb.SpacecraftDynamics.new(nb.OrbitalDynamics.from_model(nb.GravityField.new(gd)))
+        orbit = nb.Orbit.keplerian(6378.1363 + 300.0, 0.015, 68.5, 65.2, 75.0, 0.0, 0, frame)
+        template = nb.Spacecraft(orbit=orbit, mass=nb.Mass(1000.0, 0.0, 0.0))
+        mvn = nb.MvnSpacecraft.from_cartesian_std(template, 1.0, 1e-3)
+    elif args.workload == "c3":
+        # C3: JWST-like (examples/02_jwst_covar_monte_carlo/main.rs:63-86, README.md:52): Sun+Moon point masses + SRP
+        frame = nb.EARTH_J2000
+        almanac = nb.Almanac.synthetic(frame, 0, args.span_days + 2.0)
+        srp = nb.SolarPressure.new([nb.EARTH_J2000, nb.MOON_J2000], almanac)
+        dyn = nb.SpacecraftDynamics.from_model(nb.OrbitalDynamics.point_masses([nb.MOON, nb.SUN]), srp)
+        orbit = nb.Orbit.cartesian(119901.070276, -1389299.665421, -1041369.150539, 0.045956, -0.013168, 0.034535, 0, frame)
+        template = nb.Spacecraft(orbit=orbit, mass=nb.Mass(6200.0, 0.0, 0.0), srp=nb.SRPData(21.197 * 14.162, 1.56))
+        mvn = nb.MvnSpacecraft.from_cartesian_std(template, 0.5, 1e-4)
+    else:
+        # C4: low lunar orbit, GRAIL 70x70 + Earth/Sun point masses, Moon-centred
+        from nyx_b200.frames import EARTH
+
+        frame = nb.MOON_J2000
+        almanac = nb.Almanac.synthetic(frame, 0, args.span_days + 2.0, bodies=(EARTH, nb.SUN))
+        gd = nb.GravityFieldData.from_fixture("luna_jggrx_80x80", 70, 70, nb.IAU_MOON_FRAME)
+        dyn = nb.SpacecraftDynamics.new(nb.OrbitalDynamics.new([nb.PointMasses.new([EARTH, nb.SUN]), nb.GravityField.new(gd)]))
+        orbit = nb.Orbit.keplerian(1737.4 + 100.0, 0.001, 90.0, 10.0, 0.0, 0.0, 0, frame)
+        template = nb.Spacecraft(orbit=orbit, mass=nb.Mass(1000.0, 0.0, 0.0))
+        mvn = nb.MvnSpacecraft.from_cartesian_std(template, 0.1, 1e-4)
     x = mvn.sample_vectors(rng, n_total)  # serial host stream, run index == draw order (montecarlo.rs:290-295)
     st = np.ascontiguousarray((template.to_vector()[None, :] + x).T)  # [9][n]
     cs = np.zeros((4, n_total))
     cs[0] = template.mass.dry_mass_kg
+    cs[2] = template.srp.area_m2
     ep = np.zeros(n_total, dtype=np.int64)
-    return frame, dyn, st, cs, ep
+    return frame, dyn, almanac, st, cs, ep
+
+
+WORKLOAD_TEXT = {
+    "c2": "C2: {n} LEO trajectories/GPU (alt 300 km, e 0.015, i 68.5 deg; N(0, 1 km / 1 m/s) dispersions), two-body + JGM-3 {deg}x{deg}, "
+          "adaptive RK89 (IntegratorOptions::default), {span:g}-day span",
+    "c3": "C3: {n} JWST-like trajectories/GPU, Sun+Moon point masses + SRP (Earth & Moon shadows), adaptive RK89 defaults, {span:g}-day span",
+    "c4": "C4: {n} low-lunar-orbit trajectories/GPU, GRAIL 70x70 + Earth/Sun point masses, adaptive RK89 defaults, {span:g}-day span",
+}
 
 
 class ClockSampler(threading.Thread):
@@ -116,16 +150,16 @@ def cpu_reference_leg(args, nb, sample_n, repeats=1):
     on a bounded sample of the same ensemble."""
     from oracle import pyoracle
 
-    frame, dyn, st, cs, ep = build_workload(args, sample_n, nb)
+    frame, dyn, almanac, st, cs, ep = build_workload(args, sample_n, nb)
     prop = nb.Propagator.default(dyn)
-    packed = dyn.pack(frame, None)
+    packed = dyn.pack(frame, almanac)
     end = int(args.span_days * DAY)
-    cores = pyoracle.num_threads()
+    cores = os.cpu_count() or pyoracle.num_threads()  # explicit: torchrun exports OMP_NUM_THREADS=1
     times, steps = [], 0
     out = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        out, _, det, status = pyoracle.propagate_batch(packed.c, prop.opts.to_c(prop.method), st, cs, ep, end)
+        out, _, det, status = pyoracle.propagate_batch(packed.c, prop.opts.to_c(prop.method), st, cs, ep, end, n_threads=cores)
         times.append(time.perf_counter() - t0)
         steps = int(det["n_steps"].sum())
     return {"steps": steps, "times": times, "cores": cores, "final": out, "inputs": (st, cs, ep)}
@@ -140,9 +174,9 @@ def main():
 
     if args.cpu_sample <= 0:
         args.cpu_sample = 32 * (os.cpu_count() or 8)
-    workload = (f"C2: {args.n_traj} LEO trajectories/GPU (alt 300 km, e 0.015, i 68.5 deg; N(0, 1 km / 1 m/s) dispersions), "
-                f"two-body + JGM-3 {args.degree}x{args.degree}, adaptive RK89 (IntegratorOptions::default), {args.span_days:g}-day span")
-    fps = flops_per_step(args.degree)
+    workload = WORKLOAD_TEXT[args.workload].format(n=args.n_traj, deg=args.degree, span=args.span_days)
+    # algorithmic flop per accepted step: C2 from the degree; C3 ~ 9 k (two ephemeris bodies + SRP); C4 = 70x70
+    fps = {"c2": flops_per_step(args.degree), "c3": 9.0e3, "c4": flops_per_step(70) + 16 * 200.0}[args.workload]
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -179,12 +213,12 @@ def main():
     from nyx_b200.dist import all_gather_final_states, shard_bounds
 
     n_total = args.n_traj * world  # weak scaling: per-GPU work fixed
-    frame, dyn, st, cs, ep = build_workload(args, n_total, nb)
+    frame, dyn, almanac, st, cs, ep = build_workload(args, n_total, nb)
     lo, hi = shard_bounds(n_total, world, rank)
     n = hi - lo
     mode = nb.MODE_FAST if args.mode == "fast" else nb.MODE_STRICT
     prop = nb.Propagator.default(dyn, mode=mode, device=local_rank)
-    eng = prop.engine(frame, None)
+    eng = prop.engine(frame, almanac)
     if args.lanes:
         eng.set_lanes(args.lanes)
     end = int(args.span_days * DAY)
@@ -312,6 +346,19 @@ def main():
             line["max_dr_km"] = float(dr.max())
             line["max_dv_km_s"] = float(dv.max())
             line["parity_sample"] = sample_n
+            if not args.no_strict:
+                # bit-parity pass: the STRICT kernel over the SAME full ensemble, compared bit for bit with the oracle sample
+                sprop = nb.Propagator.default(dyn, mode=nb.MODE_STRICT, device=local_rank)
+                seng = sprop.engine(frame, almanac)
+                seng.propagate_batch(h_st.numpy()[:, :256].copy(), h_cs.numpy()[:, :256].copy(), h_ep.numpy()[:256].copy(), end)  # warm-up
+                t0 = time.perf_counter()
+                s_out, _, s_det, s_status = seng.propagate_batch(h_st.numpy(), h_cs.numpy(), h_ep.numpy(), end)
+                s_t = time.perf_counter() - t0
+                same = (s_out[:, :sample_n] == leg["final"]).all(axis=0)
+                sdr = np.sqrt(((s_out[:3, :sample_n] - leg["final"][:3]) ** 2).sum(0))
+                line["strict"] = {"value": float(s_det["n_steps"].sum() / s_t), "unit": "trajectory-steps/s (host buffers, e2e)",
+                                  "bit_identical_trajectories": int(same.sum()), "of": int(sample_n), "max_dr_km": float(sdr.max()),
+                                  "note": "NYXB_MODE_STRICT per-thread kernel (no FMA, reference summation order) vs the CPU oracle"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -291,7 +291,7 @@ static int32_t launch(nyxb_engine* e, size_t n, const double* state, const doubl
         const DevCoop* cp = get_coop(e, lanes);
         if (!cp) { set_err("cooperative table upload failed"); return NYXB_RC_CUDA; }
         // two trajectories per lane group once the ensemble is large enough to still fill the SMs with half the threads
-        int T = (n * (size_t)lanes >= 65536) ? 2 : 1;
+        int T = (n * (size_t)lanes >= 1000000) ? 2 : 1;  // measured: T=1 wins at 10 000 x 8 lanes (latency-bound regime)
         if (const char* ev = getenv("NYXB_COOP_T")) { int v = atoi(ev); if (v == 1 || v == 2) T = v; }
         err = nyxb_launch_coop(&e->S, cp, T, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io,
                                out_state, (long long*)out_epoch, out_details, out_status, stream);

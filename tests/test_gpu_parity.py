@@ -182,6 +182,35 @@ def test_third_body_srp_ensemble(oracle, mode):
     assert dr < 1e-6 and dv < 1e-11, (dr, dv)  # |r| ~ 1.7e6 km: 1e-6 km is < 1e-12 relative
 
 
+@pytest.mark.parametrize("mode,lanes", [(nb.MODE_FAST, 32), (nb.MODE_FAST, 16), (nb.MODE_STRICT, 1)])
+def test_cislunar_70x70_third_body(oracle, mode, lanes):
+    """BASELINE config 4 shape: low lunar orbit, GRAIL 70x70 + Earth/Sun point masses, Moon-centred, IAU Moon rotation."""
+    from nyx_b200.frames import EARTH
+
+    moon = nb.MOON_J2000
+    almanac = nb.Almanac.synthetic(moon, 0, 2.0, bodies=(EARTH, nb.SUN))
+    gd = nb.GravityFieldData.from_fixture("luna_jggrx_80x80", 70, 70, nb.IAU_MOON_FRAME)
+    orb = nb.OrbitalDynamics.new([nb.PointMasses.new([EARTH, nb.SUN]), nb.GravityField.new(gd)])
+    dyn = nb.SpacecraftDynamics.new(orb)
+    orbit = nb.Orbit.keplerian(1737.4 + 100.0, 0.001, 90.0, 10.0, 0.0, 0.0, 0, moon)
+    template = nb.Spacecraft(orbit=orbit, mass=nb.Mass(1000.0, 0.0, 0.0))
+    mc = nb.MonteCarlo(template, nb.MvnSpacecraft.from_cartesian_std(template, 0.1, 1e-4), "llo", seed=31)
+    st, cs, ep = nb.pack_spacecraft(ds.state for _, ds in mc.generate_states(0, 12))
+    prop = nb.Propagator.default(dyn, mode=mode)
+    eng = prop.engine(moon, almanac)
+    if lanes > 1:
+        eng.set_lanes(lanes)
+    end = 4 * 3600 * S
+    out, out_ep, det, status = eng.propagate_batch(st, cs, ep, end)
+    ref, ref_ep, ref_det, ref_status = oracle_run(oracle, prop, moon, almanac, st, cs, ep, end)
+    assert (status == 0).all() and np.array_equal(status, ref_status) and np.array_equal(out_ep, ref_ep)
+    dr, dv = max_dr_dv(out, ref)
+    if mode == nb.MODE_STRICT:
+        assert (out == ref).all(axis=0).mean() >= 0.9 and dr < 1e-9, dr
+    else:
+        assert dr < 5e-7 and dv < 1e-9, (dr, dv)
+
+
 @pytest.mark.parametrize("density", ["constant", "exponential", "stdatm"])
 def test_drag_and_leo_eclipse_ensemble(oracle, density):
     """LEO with drag (3 density models, drag.rs:181-284) + SRP through Earth umbra/penumbra."""
