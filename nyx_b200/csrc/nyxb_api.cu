@@ -51,6 +51,7 @@ struct nyxb_engine {
     cudaStream_t stream = nullptr;
     std::vector<double> h_cnm, h_snm;      // host copies for building cooperative tables lazily
     std::map<int, DevCoop> coop;           // lanes -> device tables
+    std::map<int, DevCoopStrict> scoop;    // lanes -> STRICT cooperative schedules
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ~nyxb_engine() {
         for (void* p : dev_allocs) cudaFree(p);
@@ -255,17 +256,29 @@ extern "C" void nyxb_engine_destroy(nyxb_engine* eng) {
 }
 
 static bool coop_supported(const nyxb_engine* e, int lanes) {
-    if (e->mode != NYXB_MODE_FAST || !e->S.has_grav) return false;
+    if (!e->S.has_grav) return false;
     return lanes == 8 || lanes == 16 || lanes == 32;
 }
 
 static int pick_lanes(const nyxb_engine* e, size_t n) {
-    if (e->mode == NYXB_MODE_STRICT) return 1;
     if (e->lanes > 0) return e->lanes;
     // auto: cooperative lanes only pay off when the harmonic sum dominates
     if (!e->S.has_grav || e->S.grav.N < 6) return 1;
     (void)n;
     return (e->S.grav.N >= 48) ? 32 : ((e->S.grav.N >= 30) ? 16 : 8);
+}
+
+static const DevCoopStrict* get_scoop(nyxb_engine* e, int lanes) {
+    auto it = e->scoop.find(lanes);
+    if (it != e->scoop.end()) return &it->second;
+    CoopStrictHost h;
+    nyxb_coop_strict_build_host(e->S.grav.N, e->S.grav.M, lanes, h);
+    DevCoopStrict d;
+    d.G = h.G; d.kc = h.kc; d.kr = h.kr;
+    d.cols = upload(e, h.cols.data(), h.cols.size());
+    d.rows = upload(e, h.rows.data(), h.rows.size());
+    if (!d.cols || !d.rows) return nullptr;
+    return &(e->scoop[lanes] = d);
 }
 
 static const DevCoop* get_coop(nyxb_engine* e, int lanes) {
@@ -287,7 +300,12 @@ static int32_t launch(nyxb_engine* e, size_t n, const double* state, const doubl
                       nyxb_details* out_details, int32_t* out_status, cudaStream_t stream) {
     int lanes = pick_lanes(e, n);
     cudaError_t err;
-    if (lanes > 1) {
+    if (lanes > 1 && e->mode == NYXB_MODE_STRICT) {
+        const DevCoopStrict* cs = get_scoop(e, lanes);
+        if (!cs) { set_err("cooperative schedule upload failed"); return NYXB_RC_CUDA; }
+        err = nyxb_launch_coop_strict(&e->S, cs, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io,
+                                      out_state, (long long*)out_epoch, out_details, out_status, stream);
+    } else if (lanes > 1) {
         const DevCoop* cp = get_coop(e, lanes);
         if (!cp) { set_err("cooperative table upload failed"); return NYXB_RC_CUDA; }
         // two trajectories per lane group once the ensemble is large enough to still fill the SMs with half the threads
@@ -376,7 +394,7 @@ extern "C" int32_t nyxb_engine_set_lanes(nyxb_engine* eng, int32_t lanes) {
     if (!eng) return NYXB_RC_BAD_ARG;
     if (lanes != 0 && lanes != 1 && lanes != 8 && lanes != 16 && lanes != 32) { set_err("lanes must be 0,1,8,16,32"); return NYXB_RC_BAD_ARG; }
     if (lanes > 1 && !coop_supported(eng, lanes)) {
-        set_err("cooperative lanes unsupported for this engine (strict mode or no gravity field)");
+        set_err("cooperative lanes need a gravity field");
         return NYXB_RC_UNSUPPORTED;
     }
     eng->lanes = lanes;

@@ -27,6 +27,22 @@ struct CoopHost {
     std::vector<int> col_start, col_m;
 };
 
+// ---- STRICT cooperative kernel (nyxb_coop_strict.cu): column lists for phase 1, degree lists for phase 2
+struct DevCoopStrict {
+    int G, kc, kr;
+    const int* cols;  // [G][kc+1], -1 terminated, ascending m
+    const int* rows;  // [G][kr+1], -1 terminated, ascending n
+};
+struct CoopStrictHost {
+    int G = 0, kc = 0, kr = 0;
+    std::vector<int> cols, rows;
+};
+void nyxb_coop_strict_build_host(int N, int M, int G, CoopStrictHost& out);
+extern "C" cudaError_t nyxb_launch_coop_strict(const DevSetup* S, const DevCoopStrict* Cs, size_t n, const double* state,
+                                               const double* consts, const long long* epoch0, long long end_epoch,
+                                               long long* step_io, double* out_state, long long* out_epoch,
+                                               nyxb_details* out_details, int* out_status, cudaStream_t stream);
+
 void nyxb_coop_build_host(int N, int M, const double* c_nm, const double* s_nm, int G, CoopHost& out);
 
 // T = trajectories integrated together by one lane group (1 or 2: register blocking over the coefficient records)

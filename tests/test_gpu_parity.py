@@ -64,13 +64,17 @@ def test_two_body_ensemble_strict_bitexact(oracle):
     assert np.array_equal(det["n_steps"], ref_det["n_steps"])
 
 
-@pytest.mark.parametrize("degree", [2, 8, 21])
-def test_harmonics_ensemble_strict_bitexact(oracle, degree):
-    """Strict mode reproduces the oracle's harmonic sums bit for bit (deterministic sin/cos, no FMA)."""
-    mc, (st, cs, ep) = leo_ensemble(128, seed=2)
-    gd = nb.GravityFieldData.from_fixture("jgm3_70x70", degree, degree, nb.IAU_EARTH_FRAME)
+@pytest.mark.parametrize("degree,order,lanes", [(2, 2, 1), (8, 8, 1), (21, 21, 1), (8, 8, 8), (21, 21, 8), (21, 21, 16), (21, 21, 32),
+                                                (12, 7, 8), (40, 40, 16)])
+def test_harmonics_ensemble_strict_bitexact(oracle, degree, order, lanes):
+    """Strict mode reproduces the oracle's harmonic sums bit for bit (deterministic sin/cos, no FMA), both with the
+    per-thread kernel (lanes = 1) and with the lane-cooperative STRICT kernel (columns -> shared triangle -> rows)."""
+    mc, (st, cs, ep) = leo_ensemble(128 if degree <= 21 else 32, seed=2)
+    gd = nb.GravityFieldData.from_fixture("jgm3_70x70", degree, order, nb.IAU_EARTH_FRAME)
     dyn = nb.SpacecraftDynamics.new(nb.OrbitalDynamics.from_model(nb.GravityField.new(gd)))
     prop = nb.Propagator.default(dyn, mode=nb.MODE_STRICT)
+    prop.engine(nb.EARTH_J2000, None).set_lanes(lanes)
+    assert prop.engine(nb.EARTH_J2000, None).lanes() == lanes
     out, det, ref, ref_det = _ensemble_vs_oracle(oracle, prop, nb.EARTH_J2000, None, st, cs, ep, 3 * 3600 * S)
     same = (out == ref).all(axis=0)
     assert same.mean() >= 0.98, same.mean()
