@@ -358,7 +358,8 @@ def main():
                 sdr = np.sqrt(((s_out[:3, :sample_n] - leg["final"][:3]) ** 2).sum(0))
                 line["strict"] = {"value": float(s_det["n_steps"].sum() / s_t), "unit": "trajectory-steps/s (host buffers, e2e)",
                                   "bit_identical_trajectories": int(same.sum()), "of": int(sample_n), "max_dr_km": float(sdr.max()),
-                                  "note": "NYXB_MODE_STRICT per-thread kernel (no FMA, reference summation order) vs the CPU oracle"}
+                                  "lanes_per_trajectory": seng.lanes(),
+                                  "note": "NYXB_MODE_STRICT kernel (no FMA, reference operation order) over the full ensemble vs the CPU oracle sample"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
