@@ -139,9 +139,13 @@ __device__ __forceinline__ int scoop_rhs(const DevSetup& S, const DevCoopStrict&
             if (m + 1 <= N + 1) {
                 double a1 = __ldg(gv.offdiag + m) * u_ * a2;  // a[m+1][m] = sqrt(2m+3) * u * a[m][m]
                 g.A[tri(m + 1, m)] = a1;
+                // (b, c) of the next degree are fetched one iteration ahead: the recursion is a dependent chain
+                const double2* bc = reinterpret_cast<const double2*>(gv.tab);  // DevHarm = {b,c | vr01,vr11 | cbar,sbar}
+                double2 nbc = (m + 2 <= N + 1) ? __ldg(bc + 3 * tri(m + 2, m)) : make_double2(0.0, 0.0);
                 for (int n = m + 2; n <= N + 1; ++n) {
-                    const DevHarm* h = gv.tab + tri(n, m);
-                    const double an = u_ * __ldg(&h->b) * a1 - __ldg(&h->c) * a2;
+                    const double2 cur = nbc;
+                    if (n + 1 <= N + 1) nbc = __ldg(bc + 3 * tri(n + 1, m));
+                    const double an = u_ * cur.x * a1 - cur.y * a2;
                     g.A[tri(n, m)] = an;
                     a2 = a1; a1 = an;
                 }
@@ -177,8 +181,13 @@ __device__ __forceinline__ int scoop_rhs(const DevSetup& S, const DevCoopStrict&
             const double* An1 = g.A + tri(n + 1, 0);
             const int mtop = n < M ? n : M;
             double rm_prev = 0.0, im_prev = 0.0;
+            // software pipeline: coefficients of term m+1 are in flight while term m is summed
+            const double2* t2 = reinterpret_cast<const double2*>(trow);
+            double2 nvr = __ldg(t2 + 1), ncs = __ldg(t2 + 2);
             for (int m = 0; m <= mtop; ++m) {
-                const double cv = __ldg(&trow[m].cbar), sv = __ldg(&trow[m].sbar);
+                const double2 vr = nvr, csv = ncs;
+                if (m < mtop) { nvr = __ldg(t2 + 3 * (m + 1) + 1); ncs = __ldg(t2 + 3 * (m + 1) + 2); }
+                const double cv = csv.x, sv = csv.y;
                 const double rmm = g.rm[m], imm = g.im[m];
                 const double d_ = (cv * rmm + sv * imm) * sqrt2;
                 if (m != 0) {
@@ -189,8 +198,8 @@ __device__ __forceinline__ int scoop_rhs(const DevSetup& S, const DevCoopStrict&
                     sy += (double)m * anm * f_;
                 }  // m == 0: the reference adds (0*a)*0 = +-0, which leaves the sums unchanged
                 const double a_n_m1 = (m + 1 <= n) ? An[m + 1] : 0.0;  // above the diagonal the matrix is zero
-                sz += __ldg(&trow[m].vr01) * a_n_m1 * d_;
-                sw -= __ldg(&trow[m].vr11) * An1[m + 1] * d_;
+                sz += vr.x * a_n_m1 * d_;
+                sw -= vr.y * An1[m + 1] * d_;
                 rm_prev = rmm; im_prev = imm;
             }
             const double rr = rho_np1 / gv.r_eq;
