@@ -1,0 +1,102 @@
+"""Host-side logic (CPU only): gravity-file loaders, packing, Monte Carlo state generation, option builders."""
+import gzip
+
+import numpy as np
+import pytest
+
+import nyx_b200 as nb
+from nyx_b200 import abi
+from nyx_b200.gravity import _split_cof_pair
+
+
+def test_cof_pair_splitting_quirk():
+    """io/gravity.rs:236-312: C and S are glued together when S is negative."""
+    assert _split_cof_pair("2.43926074865630e-06-1.40026639758800e-06") == (2.4392607486563e-06, -1.400266397588e-06)
+    assert _split_cof_pair("-5.36243554298510e-07-4.73772370615970e-07") == (-5.3624355429851e-07, -4.7377237061597e-07)
+    assert _split_cof_pair("-4.84165374886470e-04") == (-4.8416537488647e-04, None)
+    assert _split_cof_pair("9.57170590888000e-07") == (9.57170590888e-07, None)
+
+
+def test_from_cof_and_fixture_agree_with_reference_values(tmp_path):
+    """JGM-3 values quoted in SURVEY.md a13; from_cof on a synthetic file mirrors degree/order truncation semantics."""
+    gd = nb.GravityFieldData.from_fixture("jgm3_70x70", 21, 21, nb.IAU_EARTH_FRAME)
+    assert (gd.degree, gd.order) == (21, 21)
+    assert gd.cs_nm(2, 0) == (-4.8416537488647e-4, 0.0)
+    assert gd.cs_nm(2, 2) == (2.4392607486563e-6, -1.400266397588e-6)
+    assert np.count_nonzero(gd.c_nm) == 250
+    text = ("COMMENT\nPOTFIELD 3 3 1 3.986e14 6.378e6 1.0\nRECOEF    2  0   -4.84165374886470e-04\n"
+            "RECOEF    2  1   -1.86987640000000e-10 1.19528010000000e-09\nRECOEF    2  2    2.43926074865630e-06-1.40026639758800e-06\n"
+            "RECOEF    3  0    9.57170590888000e-07\nRECOEF    3  3    7.21144939823090e-07 1.41420398473540e-06\nEND\n")
+    p = tmp_path / "t.cof.gz"
+    with gzip.open(p, "wt") as fh:
+        fh.write(text)
+    g = nb.GravityFieldData.from_cof(p, 2, 1, True, nb.IAU_EARTH_FRAME)
+    assert (g.degree, g.order) == (2, 2)      # maxima SEEN within the requested degree (io/gravity.rs:345-367)
+    assert g.cs_nm(2, 1) == (-1.8698764e-10, 1.1952801e-09) and g.cs_nm(2, 2) == (0.0, 0.0)  # order 2 > requested 1: skipped
+    j2 = nb.GravityFieldData.from_j2(-4.84e-4, nb.IAU_EARTH_FRAME)
+    assert (j2.degree, j2.order, j2.c_nm[2, 0]) == (2, 0, -4.84e-4)
+
+
+def test_from_shadr_skips_header(tmp_path):
+    p = tmp_path / "m.tab"
+    p.write_text(" 0.1738E+04, 0.49028E+04, 0.1, 3, 3, 1, 0.0, 0.0\n    1,    0, 0.0, 0.0, 0.0, 0.0\n"
+                 "    2,    0,-0.9088017496403000E-04, 0.0, 0.7D-11, 0.0\n    2,    1, 0.1729508721878000D-09, 0.1041216830058000E-08, 0, 0\n"
+                 "    3,    0, 1.0, 2.0, 0, 0\n")
+    g = nb.GravityFieldData.from_shadr(p, 2, 2, False, nb.IAU_MOON_FRAME)
+    assert g.degree == 2 and g.cs_nm(2, 0)[0] == -0.9088017496403e-04 and g.cs_nm(2, 1) == (0.1729508721878e-09, 0.1041216830058e-08)
+
+
+def test_integrator_option_builders_follow_reference():
+    d = nb.IntegratorOptions.default()
+    assert (d.init_step, d.min_step, d.max_step, d.tolerance, d.attempts, d.fixed_step) == (60 * 10**9, 10**6, 2700 * 10**9, 1e-12, 50, False)
+    a = nb.IntegratorOptions.with_adaptive_step_s(0.1, 30.0, 1e-12, nb.ErrorControl.RSSCartesianState)
+    assert a.init_step == a.max_step == 30 * 10**9 and a.min_step == 10**8            # options.rs:66-82
+    f = nb.IntegratorOptions.with_fixed_step_s(10.0)
+    assert f.fixed_step and f.tolerance == 0.0 and f.attempts == 0 and f.min_step == f.max_step == f.init_step == 10**10
+    m = nb.IntegratorOptions.with_max_step(30 * nb.Unit.Second)
+    assert m.init_step == 30 * 10**9                                                  # options.rs:127-131
+    c = a.to_c(nb.IntegratorMethod.DormandPrince78)
+    assert (c.method, c.error_ctrl, c.init_step_ns) == (abi.DP78, abi.RSS_CARTESIAN_STATE, 30 * 10**9)
+    assert nb.IntegratorMethod.from_str("rungekutta89") is nb.IntegratorMethod.RungeKutta89
+    with pytest.raises(nb.PropagationError):
+        nb.IntegratorMethod.from_str("blah")
+    assert [m.stages() for m in nb.IntegratorMethod] == [16, 13, 7, 4, 6, 8]
+
+
+def test_monte_carlo_generation_is_a_single_serial_stream():
+    """mc/montecarlo.rs:277-296: run index == draw order; `skip` discards the head of the same stream."""
+    frame = nb.EARTH_J2000
+    tmpl = nb.Spacecraft(orbit=nb.Orbit.keplerian(7000.0, 0.01, 30.0, 10.0, 20.0, 30.0, 0, frame), mass=nb.Mass(100.0, 5.0, 1.0),
+                         srp=nb.SRPData(4.0, 1.5), drag=nb.DragData(3.0, 2.1))
+    cov = np.diag([1.0, 1.0, 1.0, 1e-6, 1e-6, 1e-6, 1e-4, 0.0, 0.0])
+    cov[0, 1] = cov[1, 0] = 0.5
+    mc = nb.MonteCarlo(tmpl, nb.MvnSpacecraft.from_spacecraft_cov(tmpl, cov), "t", seed=7)
+    a = mc.generate_states(0, 50)
+    b = mc.generate_states(40, 10)
+    assert [i for i, _ in a] == list(range(50))
+    assert all(a[40 + k][1].state == b[k][1].state for k in range(10))
+    x = np.array([ds.state.to_vector() - tmpl.to_vector() for _, ds in mc.generate_states(0, 4000)])
+    assert np.abs(np.cov(x.T)[:2, :2] - cov[:2, :2]).max() < 0.08 and np.abs(x[:, 7:]).max() == 0.0
+    st, cs, ep = nb.pack_spacecraft(ds.state for _, ds in a)
+    assert st.shape == (9, 50) and cs.shape == (4, 50) and np.array_equal(cs[:, 0], [100.0, 1.0, 4.0, 3.0])
+    with pytest.raises(ValueError):
+        nb.MvnSpacecraft.from_spacecraft_cov(tmpl, -np.eye(9))
+
+
+def test_dynamics_lowering_to_the_c_abi():
+    frame = nb.EARTH_J2000
+    alm = nb.Almanac.synthetic(frame, 0, 5.0)
+    gd = nb.GravityFieldData.from_fixture("jgm3_70x70", 8, 8, nb.IAU_EARTH_FRAME)
+    dyn = nb.SpacecraftDynamics.from_models(nb.OrbitalDynamics.new([nb.PointMasses.new([nb.EARTH, nb.MOON, nb.SUN]), nb.GravityField.new(gd)]),
+                                            [nb.SolarPressure.new([nb.EARTH_J2000, nb.MOON_J2000], alm), nb.Drag.earth_exp(alm)])
+    p = dyn.pack(frame, alm).c
+    assert p.n_bodies == 2 and p.point_mass_mask == 0b11            # the central body is skipped (orbital.rs:219-222)
+    assert p.gravity.contents.degree == 8 and p.gravity.contents.rot.kind == 1 and p.gravity.contents.r_eq_km == 6378.14
+    assert p.srp.contents.n_shadow == 2 and p.srp.contents.shadow_body[0] == abi.NYXB_CENTRAL_BODY
+    assert p.drag.contents.density == abi.DENSITY_EXPONENTIAL and p.drag.contents.r0 == 700_000.0
+    with pytest.raises(nb.DynamicsError):
+        nb.SpacecraftDynamics.new(nb.OrbitalDynamics.new([object()])).pack(frame, alm)
+    with pytest.raises(nb.DynamicsError):
+        nb.SpacecraftDynamics.new(nb.OrbitalDynamics.point_masses([nb.SUN])).pack(frame, None)
+    kep = nb.Orbit.keplerian(7000.0, 0.01, 30.0, 10.0, 20.0, 30.0, 0, frame)
+    assert abs(kep.rmag_km() - 7000.0 * (1 - 0.01**2) / (1 + 0.01 * np.cos(np.radians(30.0)))) < 1e-9
