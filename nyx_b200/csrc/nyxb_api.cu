@@ -289,9 +289,10 @@ static const DevCoop* get_coop(nyxb_engine* e, int lanes) {
     DevCoop d;
     d.G = h.G; d.L = h.L; d.kmax = h.kmax;
     d.recs = upload(e, h.recs.data(), h.recs.size());
+    d.colseed = upload(e, h.colseed.data(), h.colseed.size());
     d.col_start = upload(e, h.col_start.data(), h.col_start.size());
     d.col_m = upload(e, h.col_m.data(), h.col_m.size());
-    if (!d.recs || !d.col_start || !d.col_m) return nullptr;
+    if (!d.recs || !d.col_start || !d.col_m || !d.colseed) return nullptr;
     return &(e->coop[lanes] = d);
 }
 

@@ -19,7 +19,9 @@
 // tolerance-parity path (tests assert < 1e-6 km, the north-star's sub-mm bound).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <numeric>
+#include <string>
 
 #include "nyxb_coop.h"
 
@@ -40,58 +42,86 @@ void nyxb_coop_build_host(int N, int M, const double* c_nm, const double* s_nm, 
         double v = std::sqrt(((2.0 * nf + 1.0) * (nf + mf + 2.0) * (nf + mf + 1.0)) / (2.0 * nf + 3.0));
         return m == 0 ? v / sqrt2 : v;
     };
-    auto bnm = [&](int n, int m) {
-        double nf = n, mf = m;
-        return std::sqrt(((2.0 * nf + 1.0) * (2.0 * nf - 1.0)) / ((nf + mf) * (nf - mf)));
-    };
-    auto cnm = [&](int n, int m) {
-        double nf = n, mf = m;
-        return std::sqrt(((2.0 * nf + 1.0) * (nf + mf - 1.0) * (nf - mf - 1.0)) / ((nf - mf) * (nf + mf) * (2.0 * nf - 3.0)));
-    };
     const int mcols = std::min(M + 1, N + 1);  // columns m = 1..mcols
-    // LPT assignment
+    // column -> lane schedule.  Default: longest-processing-time greedy (every lane walks the same number of entries,
+    // column boundaries differ per lane).  NYXB_COOP_SCHED=rounds: G columns per round, all lanes start their k-th column
+    // at the same entry (uniform boundaries, shorter columns padded with null records).
     std::vector<int> order(mcols);
     std::iota(order.begin(), order.end(), 1);  // already sorted by decreasing length (N + 2 - m)
     std::vector<int> load(G, 0);
     std::vector<std::vector<int>> cols(G);
-    for (int m : order) {
-        int best = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-        cols[best].push_back(m);
-        load[best] += N + 2 - m;
+    std::vector<std::vector<int>> starts(G);
+    const char* sched = getenv("NYXB_COOP_SCHED");
+    const bool rounds = sched && std::string(sched) == "rounds";
+    if (rounds) {
+        int base = 0;
+        for (size_t i = 0; i < order.size(); i += G) {
+            int len = N + 2 - order[i];  // longest of the round
+            for (int j = 0; j < G && i + j < order.size(); ++j) { cols[j].push_back(order[i + j]); starts[j].push_back(base); }
+            base += len;
+        }
+        for (int j = 0; j < G; ++j) load[j] = base;
+    } else {
+        for (int m : order) {
+            int best = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+            cols[best].push_back(m);
+            starts[best].push_back(load[best]);
+            load[best] += N + 2 - m;
+        }
     }
     out.G = G;
     out.L = *std::max_element(load.begin(), load.end());
     out.kmax = 1;
-    for (auto& c : cols) out.kmax = std::max(out.kmax, (int)c.size());
-    out.recs.assign((size_t)(out.L + 1) * G, DevCoopRec{0, 0, 0, 0, 0, 0, 0, 0});  // +1: prefetch pad
+    for (auto& cl : cols) out.kmax = std::max(out.kmax, (int)cl.size());
+    out.recs.assign((size_t)(out.L + 1) * G * 5, 0.0);  // +1: prefetch pad
     out.col_start.assign((size_t)G * out.kmax, out.L + 1);
     out.col_m.assign((size_t)G * out.kmax, 1);
+    out.colseed.assign((size_t)(N + 2) * 4, 0.0);
+
+    // scale[n][m] = A_ref[n][m] / Q[n][m]  (long double; both sides are multiples of d^m P_n / du^m):
+    //   A_ref[m][m] = a_diag[m] (gravity_field.rs:61-66),  Q[m][m] = (2m-1)!!,
+    //   ratio step  gamma_n = gamma_{n-1} * sqrt((2n+1)(n-m) / ((2n-1)(n+m))),  then divide by (n-m)!
+    auto scale = [&](int n, int m) -> long double {
+        long double adiag = 1.0L, dfact = 1.0L;
+        for (int k = 1; k <= m; ++k) { adiag *= sqrtl(1.0L + 1.0L / (2.0L * k)); dfact *= (2.0L * k - 1.0L); }
+        long double g = adiag / dfact;
+        for (int k = m + 1; k <= n; ++k) g *= sqrtl(((2.0L * k + 1.0L) * (k - m)) / ((2.0L * k - 1.0L) * (k + m)));
+        for (int k = 2; k <= n - m; ++k) g /= (long double)k;
+        return g;
+    };
+    for (int m = 1; m <= mcols; ++m) {
+        long double dfact = 1.0L;
+        for (int k = 1; k <= m; ++k) dfact *= (2.0L * k - 1.0L);
+        double* s = &out.colseed[(size_t)m * 4];
+        s[0] = (double)dfact;
+        if (m >= 2) {  // W term of the first entry (n = m): degree n-1 = m-1 >= 1
+            long double f = (long double)sqrt2 * vr11(m - 1, m - 1) * scale(m, m);
+            s[1] = (double)(f * C(m - 1, m - 1));
+            s[2] = (double)(f * Sx(m - 1, m - 1));
+        }
+        s[3] = 2.0 * m + 1.0;
+    }
     for (int lane = 0; lane < G; ++lane) {
-        int e = 0;
         for (size_t k = 0; k < cols[lane].size(); ++k) {
             int m = cols[lane][k];
+            int e = starts[lane][k];
             out.col_start[(size_t)lane * out.kmax + k] = e;
             out.col_m[(size_t)lane * out.kmax + k] = m;
             for (int n = m; n <= N + 1; ++n, ++e) {
-                DevCoopRec r{0, 0, 0, 0, 0, 0, 0, 0};
+                const long double sc = scale(n, m);
+                double p1 = 0, p2 = 0, p3 = 0, p4 = 0, kappa = 1.0;
                 if (n <= N) {
-                    r.p1 = sqrt2 * (double)m * C(n, m);
-                    r.p2 = sqrt2 * (double)m * Sx(n, m);
-                    r.p3 = sqrt2 * vr01(n, m - 1) * C(n, m - 1);
-                    r.p4 = sqrt2 * vr01(n, m - 1) * Sx(n, m - 1);
+                    p1 = (double)(sc * sqrt2 * (double)m * C(n, m));
+                    p2 = (double)(sc * sqrt2 * (double)m * Sx(n, m));
+                    p3 = (double)(sc * sqrt2 * vr01(n, m - 1) * C(n, m - 1));
+                    p4 = (double)(sc * sqrt2 * vr01(n, m - 1) * Sx(n, m - 1));
                 }
-                if (n >= 2) {
-                    r.p5 = sqrt2 * vr11(n - 1, m - 1) * C(n - 1, m - 1);
-                    r.p6 = sqrt2 * vr11(n - 1, m - 1) * Sx(n - 1, m - 1);
-                }
-                if (n <= N) {
-                    if (n == m) { r.bq = std::sqrt(2.0 * (double)m + 3.0); r.cq = 0.0; }  // gravity_field.rs:168-173
-                    else { r.bq = bnm(n + 1, m); r.cq = cnm(n + 1, m); }                    // gravity_field.rs:175-181
-                }
-                // device layout: [entry][quarter][lane] of 16-byte pieces (one coalesced 16*G-byte segment per load)
-                double* base = reinterpret_cast<double*>(out.recs.data()) + (size_t)e * G * 8;
-                const double q[8] = {r.p1, r.p2, r.p3, r.p4, r.p5, r.p6, r.bq, r.cq};
-                for (int k = 0; k < 4; ++k) { base[(k * G + lane) * 2] = q[2 * k]; base[(k * G + lane) * 2 + 1] = q[2 * k + 1]; }
+                if (n > m) kappa = (double)(((long double)vr11(n - 1, m - 1) * sc) / ((long double)vr01(n - 1, m - 1) * scale(n - 1, m)));
+                // device layout: [entry][piece][lane]: pieces 0,1 are 16 B per lane, piece 2 is 8 B per lane
+                double* base = out.recs.data() + (size_t)e * G * 5;
+                base[lane * 2] = p1; base[lane * 2 + 1] = p2;
+                base[2 * G + lane * 2] = p3; base[2 * G + lane * 2 + 1] = p4;
+                base[4 * G + lane] = kappa;
             }
         }
     }

@@ -5,26 +5,29 @@
 
 #include "nyxb_device.cuh"
 
-// One record per entry (n, m) of the derived-Legendre triangle, m >= 1, m <= n <= N+1,
-// laid out [entry e][lane] in the order each lane walks its columns.
-struct __align__(16) DevCoopRec {
-    double p1, p2;  // sqrt2 * m * (Cbar, Sbar)[n][m]                       -> X, Y sums
-    double p3, p4;  // sqrt2 * vr01[n][m-1] * (Cbar, Sbar)[n][m-1]          -> Z sum
-    double p5, p6;  // sqrt2 * vr11[n-1][m-1] * (Cbar, Sbar)[n-1][m-1]      -> W sum
-    double bq, cq;  // recursion factors producing A[n+1][m] from A[n][m], A[n-1][m]
-};
+// Compact per-entry record of the FAST cooperative kernel, 40 bytes per lane and entry (n, m), m >= 1, m <= n <= N+1,
+// laid out [entry e][piece][lane] in the order each lane walks its columns:
+//   piece 0 (16 B): p1, p2 = sqrt2 * m * (Cbar, Sbar)[n][m] * scale[n][m]                    -> X, Y sums
+//   piece 1 (16 B): p3, p4 = sqrt2 * vr01[n][m-1] * (Cbar, Sbar)[n][m-1] * scale[n][m]       -> Z sum
+//   piece 2 ( 8 B): kappa  = vr11[n-1][m-1] scale[n][m] / (vr01[n-1][m-1] scale[n-1][m])     -> W term = kappa * (Z term of the entry above)
+// scale[n][m] = A_ref[n][m] / Q[n][m] converts the integer-coefficient recursion
+//   Q[n] = (2n-1) u Q[n-1] - (n+m-1)(n-m-1) Q[n-2],  Q[m] = (2m-1)!!
+// (whose coefficients are generated in registers, no loads) to the reference's normalised A[n][m].
+#define NYXB_COOP_REC_BYTES 40
 
 struct DevCoop {
     int G, L, kmax;
-    const DevCoopRec* recs;  // [L][G]
+    const double* recs;      // (L+1) * G * 5 doubles
     const int* col_start;    // [G][kmax] entry index at which the k-th column of the lane starts (L+1: none)
     const int* col_m;        // [G][kmax] order m of that column
+    const double* colseed;   // [N+2][4]: (2m-1)!!, pd1, pd2 (W term of the column's first entry), 2m+1
 };
 
 struct CoopHost {
     int G = 0, L = 0, kmax = 0;
-    std::vector<DevCoopRec> recs;
+    std::vector<double> recs;
     std::vector<int> col_start, col_m;
+    std::vector<double> colseed;
 };
 
 // ---- STRICT cooperative kernel (nyxb_coop_strict.cu): column lists for phase 1, degree lists for phase 2

@@ -9,9 +9,11 @@
 //         Z += rr_n   vr01[n][m-1] A[n][m] D(n,m-1)   W -= rr_{n-1} vr11[n-1][m-1] A[n][m] D(n-1,m-1)
 //     (E, F, D share the per-column constant (cos,sin)((m-1) lambda)): no A matrix in memory, no cross-lane
 //     traffic inside the sum, one butterfly reduction at the end.
-//   * The 64-byte coefficient record of an entry is fetched ONCE (LDS.128 x4 from the TMA-staged table) and
-//     applied to T trajectories: with T = 1 the shared-memory return path (128 B/clk/SM) caps the FP64 pipe
-//     at ~56 % (64 B per 18 DFMA-class lane-instructions); T = 2 halves the bytes per flop.
+//   * The shared-memory return path (128 B/clk/SM) is the scarce resource of this loop, so the per-entry record is
+//     compressed to 40 bytes: the column recursion runs on the un-normalised Q[n][m] = (n-m)! d^m P_n/du^m whose
+//     coefficients (2n+1), (n+m)(n-m) are generated in registers, the normalisation is folded into the stored
+//     coefficients, and the W term reuses the Z term of the entry above (one ratio instead of two coefficients).
+//     The record is fetched ONCE (2 x LDS.128 + LDS.64 from the TMA-staged table) and applied to T trajectories.
 //   * RK stage vectors live in shared memory ([stage][6] per trajectory), lane c < 6 owns state component c;
 //     the error norm and the step-size controller are evaluated redundantly by every lane of the group.
 //   * Trajectory t of a group advances by ONE step attempt per outer iteration; a rejected attempt simply
@@ -35,10 +37,10 @@ __host__ __device__ inline int coop_traj_stride(int N) {
     int s = COOP_SM_FIXED + 3 * (N + 3);
     return s + ((8 - (s & 15)) & 15);
 }
-// bytes of the CTA-shared table region: records [(L+1)][4][G] double2, then a_diag[N+3], col_start/col_m [G][kmax+2]
-__host__ __device__ inline size_t coop_rec_bytes(int L, int G) { return (size_t)(L + 1) * G * 64; }
+// bytes of the CTA-shared table region: records [(L+1)][5 doubles][G], then colseed[N+2][4], col_start/col_m [G][kmax+2]
+__host__ __device__ inline size_t coop_rec_bytes(int L, int G) { return (size_t)(L + 1) * G * NYXB_COOP_REC_BYTES; }
 __host__ __device__ inline size_t coop_meta_bytes(int N, int G, int kmax) {
-    size_t b = (size_t)(N + 3) * 8 + (size_t)2 * G * (kmax + 2) * 4;
+    size_t b = (size_t)(N + 2) * 32 + (size_t)2 * G * (kmax + 2) * 4;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -108,8 +110,8 @@ static __device__ __noinline__ int coop_extra(const DevSetup& S, const TrajCtx& 
 
 // Cooperative SpacecraftDynamics::eom for the T stage states held in g[t].ys; lane c < 6 receives dy[c] of each.
 template <int G, int T>
-__device__ __forceinline__ void coop_rhs(const DevSetup& S, const double2* __restrict__ recs, int L,
-                                         const double* __restrict__ a_diag, unsigned a_cs, unsigned cm_off,
+__device__ __forceinline__ void coop_rhs(const DevSetup& S, const double* __restrict__ recs, int L,
+                                         const double* __restrict__ colseed, unsigned a_cs, unsigned cm_off,
                                          TrajCtx (&g)[T], const RotBase (&rbase)[T], const double (&dt_s)[T],
                                          const long long (&t_ns)[T], int lane, unsigned gmask, unsigned traj_stride_bytes,
                                          double (&dyc)[T], int (&rc)[T]) {
@@ -175,7 +177,7 @@ __device__ __forceinline__ void coop_rhs(const DevSetup& S, const double2* __res
         }
         const int top = gv.N + 1;
         for (int k = lane; k <= top; k += G) {
-            g[t].rm[k] = zr; g[t].im[k] = zi; g[t].rp[k] = pr * a_diag[k];  // rho^k * A[k][k]: the seed of column k
+            g[t].rm[k] = zr; g[t].im[k] = zi; g[t].rp[k] = pr * colseed[4 * k];  // rho^k (2k-1)!!: the seed Q[k][k] of column k
             const double nzr = fma(zr, bzr, -(zi * bzi));
             zi = fma(zr, bzi, zi * bzr);
             zr = nzr;
@@ -184,57 +186,70 @@ __device__ __forceinline__ void coop_rhs(const DevSetup& S, const double2* __res
     }
     __syncwarp(gmask);
 
-    // ---- column walk; the (A, cos, sin) seed of the NEXT column is prefetched one column ahead.
-    // Loop invariants are pinned with empty asm: ptxas otherwise rematerialises them inside the loop.
-    unsigned a_rm = smem_u32(g[0].rm);
-    asm volatile("" : "+r"(a_rm), "+r"(a_cs));
+    // ---- column walk.  Per entry: one 40-byte record (2 x LDS.128 + LDS.64), 17 FP64 instructions per trajectory;
+    // the recursion coefficients (2n+1) and (n+m)(n-m) are generated in registers.  The seed of the NEXT column
+    // (Q, cos, sin, W seed) is prefetched one column ahead.  Loop invariants are pinned with empty asm: ptxas
+    // otherwise rematerialises them inside the loop.
+    unsigned a_rm = smem_u32(g[0].rm), a_seed = smem_u32(colseed);
+    asm volatile("" : "+r"(a_rm), "+r"(a_cs), "+r"(a_seed));
 #pragma unroll
     for (int t = 0; t < T; ++t) asm volatile("" : "+d"(r2[t]), "+d"(ub[t]));
     const unsigned pw8 = (unsigned)(gv.N + 3) * 8u;  // rm -> im -> rp stride in bytes
-    double X[T], Y[T], Z[T], W[T], A[T], Ap[T], rr[T], ii[T], An0[T], rrn[T], iin[T];
+    double X[T], Y[T], Z[T], W[T], Q1[T], Q2[T], rr[T], ii[T], t3p[T], Qn0[T], rrn[T], iin[T];
+    double al = 0.0, be = 0.0, aln, pd1n, pd2n;
     int ci = 0;
     int next_start = lds_s32(a_cs), start_after = lds_s32(a_cs + 4);
     {
         const int mn = lds_s32(a_cs + cm_off);
+        pd1n = lds_f64(a_seed + mn * 32 + 8); pd2n = lds_f64(a_seed + mn * 32 + 16); aln = lds_f64(a_seed + mn * 32 + 24);
 #pragma unroll
         for (int t = 0; t < T; ++t) {
             const unsigned base = a_rm + t * traj_stride_bytes + mn * 8;
-            X[t] = Y[t] = Z[t] = W[t] = A[t] = Ap[t] = rr[t] = ii[t] = 0.0;
-            An0[t] = lds_f64(base + 2 * pw8); rrn[t] = lds_f64(base - 8); iin[t] = lds_f64(base + pw8 - 8);
+            X[t] = Y[t] = Z[t] = W[t] = Q1[t] = Q2[t] = rr[t] = ii[t] = t3p[t] = 0.0;
+            Qn0[t] = lds_f64(base + 2 * pw8); rrn[t] = lds_f64(base - 8); iin[t] = lds_f64(base + pw8 - 8);
         }
     }
-    const double2* rec = recs + lane;
-    double2 n0 = rec[0], n1 = rec[G], n2 = rec[2 * G], n3 = rec[3 * G];
+    const double2* rec = reinterpret_cast<const double2*>(recs) + lane;  // pieces 0/1: 16 B per lane
+    const double* rek = recs + 4 * G + lane;                              // piece 2: 8 B per lane
+    double2 n0 = rec[0], n1 = rec[G];
+    double nk = rek[0];
     for (int e = 0; e < L; ++e) {
-        const double2 q0 = n0, q1 = n1, q2 = n2, q3 = n3;
-        rec += G * 4;
-        n0 = rec[0]; n1 = rec[G]; n2 = rec[2 * G]; n3 = rec[3 * G];  // software prefetch (table padded by one entry)
+        const double2 q0 = n0, q1 = n1;
+        const double kq = nk;
+        rec += (G * 5) / 2; rek += G * 5;
+        n0 = rec[0]; n1 = rec[G]; nk = rek[0];  // software prefetch (table padded by one entry)
         if (e == next_start) {
             ++ci;
             next_start = start_after;                           // sentinel L+1 after the last column
             start_after = lds_s32(a_cs + ci * 4 + 4);           // (table has two sentinel slots)
             const int mn = lds_s32(a_cs + cm_off + ci * 4);     // sentinel column 1
+            al = aln; be = 0.0;
 #pragma unroll
             for (int t = 0; t < T; ++t) {
-                A[t] = An0[t]; rr[t] = rrn[t]; ii[t] = iin[t]; Ap[t] = 0.0;
+                Q1[t] = Qn0[t]; rr[t] = rrn[t]; ii[t] = iin[t]; Q2[t] = 0.0;
+                t3p[t] = fma(pd2n, ii[t], pd1n * rr[t]);        // W term of the column's first entry (kappa = 1 there)
                 const unsigned base = a_rm + t * traj_stride_bytes + mn * 8;
-                An0[t] = lds_f64(base + 2 * pw8); rrn[t] = lds_f64(base - 8); iin[t] = lds_f64(base + pw8 - 8);
+                Qn0[t] = lds_f64(base + 2 * pw8); rrn[t] = lds_f64(base - 8); iin[t] = lds_f64(base + pw8 - 8);
             }
+            pd1n = lds_f64(a_seed + mn * 32 + 8); pd2n = lds_f64(a_seed + mn * 32 + 16); aln = lds_f64(a_seed + mn * 32 + 24);
         }
 #pragma unroll
         for (int t = 0; t < T; ++t) {
             const double t1 = fma(q0.y, ii[t], q0.x * rr[t]);
             const double t2 = fma(q0.y, rr[t], -(q0.x * ii[t]));
             const double t3 = fma(q1.y, ii[t], q1.x * rr[t]);
-            const double t4 = fma(q2.y, ii[t], q2.x * rr[t]);
-            X[t] = fma(A[t], t1, X[t]);
-            Y[t] = fma(A[t], t2, Y[t]);
-            Z[t] = fma(A[t], t3, Z[t]);
-            W[t] = fma(A[t], t4, W[t]);
-            const double An = fma(ub[t] * q3.x, A[t], -((r2[t] * q3.y) * Ap[t]));
-            Ap[t] = A[t];
-            A[t] = An;
+            const double t4 = kq * t3p[t];
+            X[t] = fma(Q1[t], t1, X[t]);
+            Y[t] = fma(Q1[t], t2, Y[t]);
+            Z[t] = fma(Q1[t], t3, Z[t]);
+            W[t] = fma(Q1[t], t4, W[t]);
+            const double Qn = fma(al * ub[t], Q1[t], -((be * r2[t]) * Q2[t]));  // Q[n+1] = (2n+1) u Q[n] - (n+m)(n-m) Q[n-1]
+            Q2[t] = Q1[t];
+            Q1[t] = Qn;
+            t3p[t] = t3;
         }
+        be += al;   // (n+1)^2 - m^2 = n^2 - m^2 + (2n+1)
+        al += 2.0;
     }
 #pragma unroll
     for (int t = 0; t < T; ++t) {
@@ -280,7 +295,10 @@ __device__ __forceinline__ void coop_rhs(const DevSetup& S, const double2* __res
 }
 
 template <int G, int T, bool SMEM_TABLE>
-__global__ void __launch_bounds__(COOP_CTA, (T == 1 ? 5 : 3))
+#ifndef COOP_MINB1
+#define COOP_MINB1 5
+#endif
+__global__ void __launch_bounds__(COOP_CTA, (T == 1 ? COOP_MINB1 : 3))
 nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop Cp, size_t n,
             const double* __restrict__ state, const double* __restrict__ consts,
             const long long* __restrict__ epoch0, long long end_epoch, long long* __restrict__ step_io,
@@ -295,8 +313,8 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
     // ---- CTA-shared tables: records via one TMA bulk copy (SMEM_TABLE), small metadata via plain loads
     const size_t rec_bytes = SMEM_TABLE ? coop_rec_bytes(Cp.L, G) : 0;
     unsigned char* meta = smem_raw + rec_bytes;
-    double* sm_adiag = reinterpret_cast<double*>(meta);
-    int* sm_cs = reinterpret_cast<int*>(meta + (size_t)(N + 3) * 8);
+    double* sm_seed = reinterpret_cast<double*>(meta);
+    int* sm_cs = reinterpret_cast<int*>(meta + (size_t)(N + 2) * 32);
     int* sm_cm = sm_cs + G * (Cp.kmax + 2);
     if (SMEM_TABLE) {
         if (tid == 0) mbar_init(&tma_bar, 1);
@@ -306,7 +324,7 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
             tma_bulk_g2s(smem_raw, Cp.recs, (unsigned)rec_bytes, &tma_bar);
         }
     }
-    for (int k = tid; k < N + 3; k += COOP_CTA) sm_adiag[k] = __ldg(S.grav.a_diag + k);
+    for (int k = tid; k < (N + 2) * 4; k += COOP_CTA) sm_seed[k] = __ldg(Cp.colseed + k);
     for (int k = tid; k < G * (Cp.kmax + 2); k += COOP_CTA) {
         const int l = k / (Cp.kmax + 2), q = k % (Cp.kmax + 2);
         sm_cs[k] = (q < Cp.kmax) ? __ldg(Cp.col_start + l * Cp.kmax + q) : Cp.L + 1;
@@ -314,7 +332,7 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
     }
     if (SMEM_TABLE) mbar_wait(&tma_bar, 0);
     __syncthreads();
-    const double2* recs = SMEM_TABLE ? reinterpret_cast<const double2*>(smem_raw) : reinterpret_cast<const double2*>(Cp.recs);
+    const double* recs = SMEM_TABLE ? reinterpret_cast<const double*>(smem_raw) : Cp.recs;
     const unsigned a_cs = smem_u32(sm_cs + lane * (Cp.kmax + 2));
     const unsigned cm_off = (unsigned)(G * (Cp.kmax + 2) * 4);
 
@@ -437,7 +455,7 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
                 t_ns[t] = epoch[t] + off_ns;
             }
             __syncwarp(gmask);
-            coop_rhs<G, T>(S, recs, Cp.L, sm_adiag, a_cs, cm_off, g, rbase, dt_s, t_ns, lane, gmask,
+            coop_rhs<G, T>(S, recs, Cp.L, sm_seed, a_cs, cm_off, g, rbase, dt_s, t_ns, lane, gmask,
                            (unsigned)(tstride * 8), dyc, rcs);
 #pragma unroll
             for (int t = 0; t < T; ++t) {
