@@ -93,6 +93,8 @@ static DevRotation pack_rot(const nyxb_rotation& r) {
     d.ra0 = r.ra0_deg; d.ra1 = r.ra1_deg_cy; d.dec0 = r.dec0_deg; d.dec1 = r.dec1_deg_cy; d.w0 = r.w0_deg; d.w1 = r.w1_deg_day;
     volatile double w = r.w1_deg_day * 1.7453292519943295e-2;
     d.wdot = (r.kind == 0) ? 0.0 : w / 86400.0;
+    d.ra_dot = r.ra1_deg_cy * 1.7453292519943295e-2 / (36525.0 * 86400.0);
+    d.dec_dot = r.dec1_deg_cy * 1.7453292519943295e-2 / (36525.0 * 86400.0);
     return d;
 }
 

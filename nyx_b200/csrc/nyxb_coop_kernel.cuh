@@ -116,8 +116,7 @@ __device__ __forceinline__ void coop_rhs(const DevSetup& S, const double* __rest
                                          const long long (&t_ns)[T], int lane, unsigned gmask, unsigned traj_stride_bytes,
                                          double (&dyc)[T], int (&rc)[T]) {
     const DevGrav& gv = S.grav;
-    const double ra_dot = gv.rot.ra1 * NYXB_DEG2RAD / (36525.0 * 86400.0);
-    const double dec_dot = gv.rot.dec1 * NYXB_DEG2RAD / (36525.0 * 86400.0);
+    const double ra_dot = gv.rot.ra_dot, dec_dot = gv.rot.dec_dot;  // rad/s, precomputed on the host
     double inv_r[T], rho[T], ub[T], r2[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) {
@@ -284,13 +283,11 @@ __device__ __forceinline__ void coop_rhs(const DevSetup& S, const double* __rest
         acc[2] = fma(fac, y[2], fma(R[8], ab2, fma(R[5], ab1, R[2] * ab0)));
         rc[t] = 0;
         if (S.n_bodies > 0 || S.has_srp || S.has_drag) rc[t] = coop_extra(S, g[t], t_ns[t], y, acc);
-        double out = y[3];
-        if (lane == 1) out = y[4];
-        else if (lane == 2) out = y[5];
-        else if (lane == 3) out = acc[0];
-        else if (lane == 4) out = acc[1];
-        else if (lane == 5) out = acc[2];
-        dyc[t] = out;
+        // lane c < 3 keeps the velocity component c, lanes 3..5 the acceleration components (selects, no jump table)
+        const int c3 = lane >= 3 ? lane - 3 : lane;
+        const double vsel = c3 == 0 ? y[3] : (c3 == 1 ? y[4] : y[5]);
+        const double asel = c3 == 0 ? acc[0] : (c3 == 1 ? acc[1] : acc[2]);
+        dyc[t] = lane >= 3 ? asel : vsel;
     }
 }
 
@@ -337,8 +334,10 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
     const unsigned cm_off = (unsigned)(G * (Cp.kmax + 2) * 4);
 
     // ---- trajectories of this group: pair index strided over the grid so that every SM gets the same share
+    // whole warps are strided over the grid (every SM gets the same number of FULL warps, surplus warps exit)
     const size_t n_sets = (n + T - 1) / T;
-    const size_t set = (size_t)blockIdx.x + (size_t)gridDim.x * grp;
+    const int gpw = 32 / G;
+    const size_t set = ((size_t)blockIdx.x + (size_t)gridDim.x * (tid >> 5)) * gpw + (tid & 31) / G;
     if (set >= n_sets) return;  // uniform per group; no block-wide barrier below this point
     const int tstride = coop_traj_stride(N);
     double* sm = reinterpret_cast<double*>(meta + coop_meta_bytes(N, G, Cp.kmax)) + (size_t)grp * T * tstride;
@@ -350,7 +349,8 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
     size_t traj[T];
     bool valid[T], done[T], retry[T], last[T], backprop[T];
     double yc[T], h[T], nx[T], det_error[T];
-    long long epoch[T], step_ns[T], prev_step[T], det_step[T], n_steps[T], n_rej[T], n_rhs[T];
+    long long epoch[T], step_ns[T], prev_step[T], det_step[T];
+    int n_steps[T], n_rej[T], n_rhs[T];
     int fixed[T], prev_fixed[T], status[T], rc[T], det_attempts[T];
     RotBase rbase[T];
     const int cidx = lane < 6 ? lane : 0;
@@ -584,11 +584,7 @@ static cudaError_t launch_gt(const DevSetup* S, const DevCoop* Cp, size_t n, siz
     // one resident wave spread evenly over the SMs when the ensemble fits; otherwise plain tiling
     size_t grid = (n_sets + groups - 1) / groups;
     const size_t wave = (size_t)sms * occ;
-    if (grid <= wave) {
-        size_t per_sm = (grid + sms - 1) / sms;
-        grid = per_sm * sms;
-        if (grid * groups < n_sets) grid = (n_sets + groups - 1) / groups;
-    }
+    if (grid <= wave) grid = ((grid + sms - 1) / sms) * sms;  // one resident wave, same CTA count on every SM
     nyxb_k_coop<G, T, TAB><<<(unsigned)grid, COOP_CTA, smem, stream>>>(*S, *Cp, n, state, consts, epoch0, end_epoch, step_io,
                                                                        out_state, out_epoch, out_details, out_status);
     return cudaGetLastError();

@@ -24,6 +24,7 @@ struct DevRotation {
     int kind;
     double ra0, ra1, dec0, dec1, w0, w1;  // degrees
     double wdot;                           // rad/s
+    double ra_dot, dec_dot;                // rad/s (FAST cooperative kernel: first-order pole update)
 };
 
 struct DevBody {
