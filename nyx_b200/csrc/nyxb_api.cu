@@ -312,7 +312,7 @@ static int32_t launch(nyxb_engine* e, size_t n, const double* state, const doubl
         const DevCoop* cp = get_coop(e, lanes);
         if (!cp) { set_err("cooperative table upload failed"); return NYXB_RC_CUDA; }
         // two trajectories per lane group once the ensemble is large enough to still fill the SMs with half the threads
-        int T = (n * (size_t)lanes >= 1000000) ? 2 : 1;  // measured: T=1 wins at 10 000 x 8 lanes (latency-bound regime)
+        int T = 1;  // measured on B200: T = 1 beats T = 2 at both 10 000 and 100 000 trajectories (7.2e7 vs 5.7e7, 8.8e7 vs 7.6e7 steps/s)
         if (const char* ev = getenv("NYXB_COOP_T")) { int v = atoi(ev); if (v == 1 || v == 2) T = v; }
         err = nyxb_launch_coop(&e->S, cp, T, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io,
                                out_state, (long long*)out_epoch, out_details, out_status, stream);
