@@ -232,6 +232,37 @@ int32_t nyxb_propagate_batch_dev(nyxb_engine* eng, size_t n,
                                  nyxb_details* out_details, int32_t* out_status,
                                  void* cuda_stream);
 
+/* ---- Trajectory recording (next row (f)-1 of SURVEY.md §8): what `for_duration_with_traj` / `until_epoch_with_traj`
+ * (propagators/instance.rs:297-340) collect through the mpsc channel (instance.rs:186-193, 255-259): the start state and
+ * the state after every accepted step, final partial step included.  Record s of trajectory i lives at
+ *   epoch_ns[s*n + i],  state[(c*capacity + s)*n + i]  (c = x,y,z,vx,vy,vz)
+ * i.e. step-major SoA: trajectories that advance together write coalesced 56-byte-per-step streams.
+ * count[i] = min(n_steps + 1, capacity); records beyond `capacity` are dropped (the final state is still returned). */
+typedef struct {
+    int64_t capacity;
+    int64_t* epoch_ns;   /* [capacity][n] */
+    double* state;       /* [6][capacity][n] */
+    int64_t* count;      /* [n] */
+} nyxb_traj_sink;
+
+/* nyxb_propagate_batch + recording into `sink` (HOST arrays; NULL sink == nyxb_propagate_batch). */
+int32_t nyxb_propagate_batch_traj(nyxb_engine* eng, size_t n,
+                                  const double* state_soa, const double* consts_soa,
+                                  const int64_t* epoch0_ns, int64_t end_epoch_ns,
+                                  int64_t* step_ns,
+                                  double* out_state_soa, int64_t* out_epoch_ns,
+                                  nyxb_details* out_details, int32_t* out_status,
+                                  const nyxb_traj_sink* sink);
+
+/* Device-pointer variant: the sink's arrays are DEVICE pointers (the struct itself is read on the host). */
+int32_t nyxb_propagate_batch_traj_dev(nyxb_engine* eng, size_t n,
+                                      const double* state_soa, const double* consts_soa,
+                                      const int64_t* epoch0_ns, int64_t end_epoch_ns,
+                                      int64_t* step_ns,
+                                      double* out_state_soa, int64_t* out_epoch_ns,
+                                      nyxb_details* out_details, int32_t* out_status,
+                                      const nyxb_traj_sink* sink, void* cuda_stream);
+
 /* Tuning / introspection. */
 int32_t nyxb_engine_set_lanes(nyxb_engine* eng, int32_t lanes_per_trajectory); /* 0 = auto */
 int32_t nyxb_engine_get_lanes(const nyxb_engine* eng);

@@ -129,6 +129,15 @@ class Details(C.Structure):
     ]
 
 
+class TrajSink(C.Structure):
+    _fields_ = [
+        ("capacity", C.c_int64),
+        ("epoch_ns", C.c_void_p),
+        ("state", C.c_void_p),
+        ("count", C.c_void_p),
+    ]
+
+
 DETAILS_DTYPE = np.dtype(
     [
         ("step_ns", "<i8"),
@@ -179,6 +188,10 @@ def _declare(lib):
     lib.nyxb_propagate_batch.argtypes = batch_args
     lib.nyxb_propagate_batch_dev.restype = C.c_int32
     lib.nyxb_propagate_batch_dev.argtypes = batch_args + [vp]
+    lib.nyxb_propagate_batch_traj.restype = C.c_int32
+    lib.nyxb_propagate_batch_traj.argtypes = batch_args + [C.POINTER(TrajSink)]
+    lib.nyxb_propagate_batch_traj_dev.restype = C.c_int32
+    lib.nyxb_propagate_batch_traj_dev.argtypes = batch_args + [C.POINTER(TrajSink), vp]
     lib.nyxb_engine_set_lanes.restype = C.c_int32
     lib.nyxb_engine_set_lanes.argtypes = [vp, C.c_int32]
     lib.nyxb_engine_get_lanes.restype = C.c_int32
@@ -201,6 +214,8 @@ EXPORTED_SYMBOLS = [
     "nyxb_engine_destroy",
     "nyxb_propagate_batch",
     "nyxb_propagate_batch_dev",
+    "nyxb_propagate_batch_traj",
+    "nyxb_propagate_batch_traj_dev",
     "nyxb_engine_set_lanes",
     "nyxb_engine_get_lanes",
     "nyxb_engine_launch_count",

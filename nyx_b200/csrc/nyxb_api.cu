@@ -17,10 +17,10 @@
 // kernels (nyxb_kernels.cu built twice, nyxb_coop.cu)
 extern "C" cudaError_t nyxb_launch_thread_strict(const DevSetup*, size_t, const double*, const double*, const long long*,
                                                  long long, long long*, double*, long long*, nyxb_details*, int*, int,
-                                                 cudaStream_t);
+                                                 const DevSink*, cudaStream_t);
 extern "C" cudaError_t nyxb_launch_thread_fast(const DevSetup*, size_t, const double*, const double*, const long long*,
                                                long long, long long*, double*, long long*, nyxb_details*, int*, int,
-                                               cudaStream_t);
+                                               const DevSink*, cudaStream_t);
 extern "C" double nyxb_fp64_probe(int device, int iters);
 
 static thread_local std::string g_err;
@@ -49,13 +49,16 @@ struct nyxb_engine {
     nyxb_details* d_det = nullptr;
     int* d_status = nullptr;
     cudaStream_t stream = nullptr;
+    // grow-only device buffers of the trajectory sink (host-pointer entry point)
+    size_t sink_bytes = 0;
+    unsigned char* d_sink = nullptr;
     std::vector<double> h_cnm, h_snm;      // host copies for building cooperative tables lazily
     std::map<int, DevCoop> coop;           // lanes -> device tables
     std::map<int, DevCoopStrict> scoop;    // lanes -> STRICT cooperative schedules
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ~nyxb_engine() {
         for (void* p : dev_allocs) cudaFree(p);
-        cudaFree(d_f64); cudaFree(d_i64); cudaFree(d_det); cudaFree(d_status);
+        cudaFree(d_f64); cudaFree(d_i64); cudaFree(d_det); cudaFree(d_status); cudaFree(d_sink);
         if (stream) cudaStreamDestroy(stream);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -300,14 +303,14 @@ static const DevCoop* get_coop(nyxb_engine* e, int lanes) {
 
 static int32_t launch(nyxb_engine* e, size_t n, const double* state, const double* consts, const int64_t* epoch0,
                       int64_t end_epoch, int64_t* step_io, double* out_state, int64_t* out_epoch,
-                      nyxb_details* out_details, int32_t* out_status, cudaStream_t stream) {
+                      nyxb_details* out_details, int32_t* out_status, const DevSink& sink, cudaStream_t stream) {
     int lanes = pick_lanes(e, n);
     cudaError_t err;
     if (lanes > 1 && e->mode == NYXB_MODE_STRICT) {
         const DevCoopStrict* cs = get_scoop(e, lanes);
         if (!cs) { set_err("cooperative schedule upload failed"); return NYXB_RC_CUDA; }
         err = nyxb_launch_coop_strict(&e->S, cs, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io,
-                                      out_state, (long long*)out_epoch, out_details, out_status, stream);
+                                      out_state, (long long*)out_epoch, out_details, out_status, &sink, stream);
     } else if (lanes > 1) {
         const DevCoop* cp = get_coop(e, lanes);
         if (!cp) { set_err("cooperative table upload failed"); return NYXB_RC_CUDA; }
@@ -315,36 +318,52 @@ static int32_t launch(nyxb_engine* e, size_t n, const double* state, const doubl
         int T = 1;  // measured on B200: T = 1 beats T = 2 at both 10 000 and 100 000 trajectories (7.2e7 vs 5.7e7, 8.8e7 vs 7.6e7 steps/s)
         if (const char* ev = getenv("NYXB_COOP_T")) { int v = atoi(ev); if (v == 1 || v == 2) T = v; }
         err = nyxb_launch_coop(&e->S, cp, T, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io,
-                               out_state, (long long*)out_epoch, out_details, out_status, stream);
+                               out_state, (long long*)out_epoch, out_details, out_status, &sink, stream);
     } else if (e->mode == NYXB_MODE_STRICT) {
         err = nyxb_launch_thread_strict(&e->S, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io,
-                                        out_state, (long long*)out_epoch, out_details, out_status, 64, stream);
+                                        out_state, (long long*)out_epoch, out_details, out_status, 64, &sink, stream);
     } else {
         err = nyxb_launch_thread_fast(&e->S, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io,
-                                      out_state, (long long*)out_epoch, out_details, out_status, 64, stream);
+                                      out_state, (long long*)out_epoch, out_details, out_status, 64, &sink, stream);
     }
     if (err != cudaSuccess) { set_err(std::string("kernel launch: ") + cudaGetErrorString(err)); return NYXB_RC_CUDA; }
     e->launches += 1;
     return NYXB_RC_OK;
 }
 
-extern "C" int32_t nyxb_propagate_batch_dev(nyxb_engine* eng, size_t n, const double* state_soa, const double* consts_soa,
-                                            const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
-                                            double* out_state_soa, int64_t* out_epoch_ns, nyxb_details* out_details,
-                                            int32_t* out_status, void* cuda_stream) {
+static DevSink make_sink(const nyxb_traj_sink* sink) {
+    DevSink d{0, nullptr, nullptr, nullptr};
+    if (sink && sink->capacity > 0 && sink->epoch_ns && sink->state && sink->count) {
+        d.cap = sink->capacity; d.epoch = (long long*)sink->epoch_ns; d.state = sink->state; d.count = (long long*)sink->count;
+    }
+    return d;
+}
+
+extern "C" int32_t nyxb_propagate_batch_traj_dev(nyxb_engine* eng, size_t n, const double* state_soa, const double* consts_soa,
+                                                 const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
+                                                 double* out_state_soa, int64_t* out_epoch_ns, nyxb_details* out_details,
+                                                 int32_t* out_status, const nyxb_traj_sink* sink, void* cuda_stream) {
     if (!eng || !state_soa || !consts_soa || !epoch0_ns || !out_state_soa || !out_epoch_ns || !out_status) {
         set_err("null argument");
         return NYXB_RC_BAD_ARG;
     }
     CUDA_TRY(cudaSetDevice(eng->device));
     return launch(eng, n, state_soa, consts_soa, epoch0_ns, end_epoch_ns, step_ns, out_state_soa, out_epoch_ns, out_details,
-                  out_status, (cudaStream_t)cuda_stream);
+                  out_status, make_sink(sink), (cudaStream_t)cuda_stream);
 }
 
-extern "C" int32_t nyxb_propagate_batch(nyxb_engine* eng, size_t n, const double* state_soa, const double* consts_soa,
-                                        const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
-                                        double* out_state_soa, int64_t* out_epoch_ns, nyxb_details* out_details,
-                                        int32_t* out_status) {
+extern "C" int32_t nyxb_propagate_batch_dev(nyxb_engine* eng, size_t n, const double* state_soa, const double* consts_soa,
+                                            const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
+                                            double* out_state_soa, int64_t* out_epoch_ns, nyxb_details* out_details,
+                                            int32_t* out_status, void* cuda_stream) {
+    return nyxb_propagate_batch_traj_dev(eng, n, state_soa, consts_soa, epoch0_ns, end_epoch_ns, step_ns, out_state_soa,
+                                         out_epoch_ns, out_details, out_status, nullptr, cuda_stream);
+}
+
+extern "C" int32_t nyxb_propagate_batch_traj(nyxb_engine* eng, size_t n, const double* state_soa, const double* consts_soa,
+                                             const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
+                                             double* out_state_soa, int64_t* out_epoch_ns, nyxb_details* out_details,
+                                             int32_t* out_status, const nyxb_traj_sink* sink) {
     if (!eng || !state_soa || !consts_soa || !epoch0_ns || !out_state_soa || !out_epoch_ns || !out_status) {
         set_err("null argument");
         return NYXB_RC_BAD_ARG;
@@ -374,9 +393,25 @@ extern "C" int32_t nyxb_propagate_batch(nyxb_engine* eng, size_t n, const double
     TRY2(cudaMemcpyAsync(d_f64 + 9 * n, consts_soa, sizeof(double) * 4 * n, cudaMemcpyHostToDevice, st));
     TRY2(cudaMemcpyAsync(d_i64, epoch0_ns, sizeof(long long) * n, cudaMemcpyHostToDevice, st));
     if (step_ns) TRY2(cudaMemcpyAsync(d_i64 + 2 * n, step_ns, sizeof(long long) * n, cudaMemcpyHostToDevice, st));
+    // trajectory sink on the device: [epoch cap*n i64 | state 6*cap*n f64 | count n i64]
+    DevSink dsink{0, nullptr, nullptr, nullptr};
+    const bool rec = sink && sink->capacity > 0 && sink->epoch_ns && sink->state && sink->count;
+    if (rec) {
+        const size_t cap = (size_t)sink->capacity;
+        const size_t need = (cap * n * 7 + n) * 8;
+        if (need > eng->sink_bytes) {
+            cudaFree(eng->d_sink); eng->d_sink = nullptr; eng->sink_bytes = 0;
+            TRY2(cudaMalloc(&eng->d_sink, need));
+            eng->sink_bytes = need;
+        }
+        dsink.cap = sink->capacity;
+        dsink.epoch = (long long*)eng->d_sink;
+        dsink.state = (double*)(eng->d_sink + cap * n * 8);
+        dsink.count = (long long*)(eng->d_sink + cap * n * 56);
+    }
     TRY2(cudaEventRecord(eng->ev0, st));
     rc = launch(eng, n, d_f64, d_f64 + 9 * n, (const int64_t*)d_i64, end_epoch_ns, step_ns ? (int64_t*)(d_i64 + 2 * n) : nullptr,
-                d_f64 + 13 * n, (int64_t*)(d_i64 + n), d_det, d_status, st);
+                d_f64 + 13 * n, (int64_t*)(d_i64 + n), d_det, d_status, dsink, st);
     if (rc != NYXB_RC_OK) return rc;
     TRY2(cudaEventRecord(eng->ev1, st));
     TRY2(cudaMemcpyAsync(out_state_soa, d_f64 + 13 * n, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost, st));
@@ -384,6 +419,12 @@ extern "C" int32_t nyxb_propagate_batch(nyxb_engine* eng, size_t n, const double
     if (step_ns) TRY2(cudaMemcpyAsync(step_ns, d_i64 + 2 * n, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
     if (out_details) TRY2(cudaMemcpyAsync(out_details, d_det, sizeof(nyxb_details) * n, cudaMemcpyDeviceToHost, st));
     TRY2(cudaMemcpyAsync(out_status, d_status, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    if (rec) {
+        const size_t cap = (size_t)sink->capacity;
+        TRY2(cudaMemcpyAsync(sink->epoch_ns, dsink.epoch, cap * n * 8, cudaMemcpyDeviceToHost, st));
+        TRY2(cudaMemcpyAsync(sink->state, dsink.state, cap * n * 48, cudaMemcpyDeviceToHost, st));
+        TRY2(cudaMemcpyAsync(sink->count, dsink.count, n * 8, cudaMemcpyDeviceToHost, st));
+    }
     TRY2(cudaStreamSynchronize(st));
     {
         float ms = 0.f;
@@ -391,6 +432,14 @@ extern "C" int32_t nyxb_propagate_batch(nyxb_engine* eng, size_t n, const double
     }
     return rc;
 #undef TRY2
+}
+
+extern "C" int32_t nyxb_propagate_batch(nyxb_engine* eng, size_t n, const double* state_soa, const double* consts_soa,
+                                        const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
+                                        double* out_state_soa, int64_t* out_epoch_ns, nyxb_details* out_details,
+                                        int32_t* out_status) {
+    return nyxb_propagate_batch_traj(eng, n, state_soa, consts_soa, epoch0_ns, end_epoch_ns, step_ns, out_state_soa, out_epoch_ns,
+                                     out_details, out_status, nullptr);
 }
 
 extern "C" int32_t nyxb_engine_set_lanes(nyxb_engine* eng, int32_t lanes) {

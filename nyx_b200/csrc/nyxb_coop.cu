@@ -132,7 +132,7 @@ void nyxb_coop_build_host(int N, int M, const double* c_nm, const double* s_nm, 
 // ------------------------------------------------------------------------------------------------
 #define NYXB_COOP_DECL(G) \
     cudaError_t nyxb_launch_coop_g##G(const DevSetup*, const DevCoop*, int, size_t, const double*, const double*, const long long*, \
-                                      long long, long long*, double*, long long*, nyxb_details*, int*, cudaStream_t);
+                                      long long, long long*, double*, long long*, nyxb_details*, int*, const DevSink*, cudaStream_t);
 NYXB_COOP_DECL(8)
 NYXB_COOP_DECL(16)
 NYXB_COOP_DECL(32)
@@ -140,13 +140,13 @@ NYXB_COOP_DECL(32)
 extern "C" cudaError_t nyxb_launch_coop(const DevSetup* S, const DevCoop* Cp, int T, size_t n, const double* state,
                                         const double* consts, const long long* epoch0, long long end_epoch,
                                         long long* step_io, double* out_state, long long* out_epoch,
-                                        nyxb_details* out_details, int* out_status, cudaStream_t stream) {
+                                        nyxb_details* out_details, int* out_status, const DevSink* sink, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     if (T != 1 && T != 2) return cudaErrorInvalidValue;
     switch (Cp->G) {
-    case 8: return nyxb_launch_coop_g8(S, Cp, T, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, stream);
-    case 16: return nyxb_launch_coop_g16(S, Cp, T, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, stream);
-    case 32: return nyxb_launch_coop_g32(S, Cp, T, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, stream);
+    case 8: return nyxb_launch_coop_g8(S, Cp, T, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, sink, stream);
+    case 16: return nyxb_launch_coop_g16(S, Cp, T, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, sink, stream);
+    case 32: return nyxb_launch_coop_g32(S, Cp, T, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, sink, stream);
     default: return cudaErrorInvalidValue;
     }
 }

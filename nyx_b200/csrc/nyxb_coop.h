@@ -44,7 +44,7 @@ void nyxb_coop_strict_build_host(int N, int M, int G, CoopStrictHost& out);
 extern "C" cudaError_t nyxb_launch_coop_strict(const DevSetup* S, const DevCoopStrict* Cs, size_t n, const double* state,
                                                const double* consts, const long long* epoch0, long long end_epoch,
                                                long long* step_io, double* out_state, long long* out_epoch,
-                                               nyxb_details* out_details, int* out_status, cudaStream_t stream);
+                                               nyxb_details* out_details, int* out_status, const DevSink* sink, cudaStream_t stream);
 
 void nyxb_coop_build_host(int N, int M, const double* c_nm, const double* s_nm, int G, CoopHost& out);
 
@@ -52,4 +52,4 @@ void nyxb_coop_build_host(int N, int M, const double* c_nm, const double* s_nm, 
 extern "C" cudaError_t nyxb_launch_coop(const DevSetup* S, const DevCoop* Cp, int T, size_t n, const double* state,
                                         const double* consts, const long long* epoch0, long long end_epoch,
                                         long long* step_io, double* out_state, long long* out_epoch,
-                                        nyxb_details* out_details, int* out_status, cudaStream_t stream);
+                                        nyxb_details* out_details, int* out_status, const DevSink* sink, cudaStream_t stream);

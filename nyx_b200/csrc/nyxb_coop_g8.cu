@@ -3,7 +3,8 @@
 
 cudaError_t nyxb_launch_coop_g8(const DevSetup* S, const DevCoop* Cp, int T, size_t n, const double* state, const double* consts,
                                  const long long* epoch0, long long end_epoch, long long* step_io, double* out_state,
-                                 long long* out_epoch, nyxb_details* out_details, int* out_status, cudaStream_t stream) {
+                                 long long* out_epoch, nyxb_details* out_details, int* out_status, const DevSink* sink,
+                                 cudaStream_t stream) {
     return nyxb_launch_coop_g<8>(S, Cp, T, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details,
-                                  out_status, stream);
+                                  out_status, sink, stream);
 }

@@ -300,7 +300,7 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
             const double* __restrict__ state, const double* __restrict__ consts,
             const long long* __restrict__ epoch0, long long end_epoch, long long* __restrict__ step_io,
             double* __restrict__ out_state, long long* __restrict__ out_epoch,
-            nyxb_details* __restrict__ out_details, int* __restrict__ out_status) {
+            nyxb_details* __restrict__ out_details, int* __restrict__ out_status, const DevSink sink) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long tma_bar;
     const int tid = threadIdx.x;
@@ -376,6 +376,10 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
         retry[t] = false; last[t] = false; h[t] = 0.0; nx[t] = 0.0; prev_step[t] = step_ns[t]; prev_fixed[t] = fixed[t];
         rbase[t].sa = 0; rbase[t].ca = 1; rbase[t].sd = 1; rbase[t].cd = 0; rbase[t].sw = 0; rbase[t].cw = 1;
         if (lane < 6) g[t].ycur[lane] = yc[t];
+        if (valid[t] && sink.cap > 0) {  // start state (instance.rs:307, 321)
+            if (lane < 6) sink.state[((size_t)lane * sink.cap) * n + traj[t]] = yc[t];
+            if (lane == 6) sink.epoch[traj[t]] = epoch[t];
+        }
         // instance.rs:96-115
         const long long duration = end_epoch - epoch[t];
         backprop[t] = duration < 0;
@@ -533,6 +537,11 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
             yc[t] = nx[t];  // committed below, after every lane has finished reading ycur/nxt
             g[t].cr = g[t].cr < 0.0 ? 0.0 : (g[t].cr > 2.0 ? 2.0 : g[t].cr);  // cosmic/spacecraft.rs:494
             n_steps[t] += 1;
+            if (n_steps[t] < sink.cap) {  // the channel send of instance.rs:186-193 / 255-259 (56 B per accepted step)
+                const size_t s = (size_t)n_steps[t];
+                if (lane < 6) sink.state[((size_t)lane * sink.cap + s) * n + traj[t]] = nx[t];
+                if (lane == 6) sink.epoch[s * n + traj[t]] = epoch[t];
+            }
             if (g[t].pm < 0.0) { rc[t] = NYXB_ERR_FUEL_EXHAUSTED; done[t] = true; }
             if (last[t]) {
                 step_ns[t] = prev_step[t];
@@ -556,6 +565,7 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
             out_epoch[traj[t]] = epoch[t];
             if (step_io) step_io[traj[t]] = step_ns[t];
             out_status[traj[t]] = (status[t] & NYXB_WARN_MAX_ATTEMPTS) | rc[t];
+            if (sink.cap > 0) sink.count[traj[t]] = (n_steps[t] + 1 < sink.cap) ? n_steps[t] + 1 : sink.cap;
         }
         if (lane == 7 && out_details) {
             nyxb_details d;
@@ -570,7 +580,7 @@ template <int G, int T, bool TAB>
 static cudaError_t launch_gt(const DevSetup* S, const DevCoop* Cp, size_t n, size_t smem, const double* state,
                              const double* consts, const long long* epoch0, long long end_epoch, long long* step_io,
                              double* out_state, long long* out_epoch, nyxb_details* out_details, int* out_status,
-                             cudaStream_t stream) {
+                             const DevSink* sink, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(nyxb_k_coop<G, T, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 0, occ = 0;
@@ -586,14 +596,15 @@ static cudaError_t launch_gt(const DevSetup* S, const DevCoop* Cp, size_t n, siz
     const size_t wave = (size_t)sms * occ;
     if (grid <= wave) grid = ((grid + sms - 1) / sms) * sms;  // one resident wave, same CTA count on every SM
     nyxb_k_coop<G, T, TAB><<<(unsigned)grid, COOP_CTA, smem, stream>>>(*S, *Cp, n, state, consts, epoch0, end_epoch, step_io,
-                                                                       out_state, out_epoch, out_details, out_status);
+                                                                       out_state, out_epoch, out_details, out_status, *sink);
     return cudaGetLastError();
 }
 
 template <int G>
 cudaError_t nyxb_launch_coop_g(const DevSetup* S, const DevCoop* Cp, int T, size_t n, const double* state, const double* consts,
                                const long long* epoch0, long long end_epoch, long long* step_io, double* out_state,
-                               long long* out_epoch, nyxb_details* out_details, int* out_status, cudaStream_t stream) {
+                               long long* out_epoch, nyxb_details* out_details, int* out_status, const DevSink* sink,
+                               cudaStream_t stream) {
     const size_t groups = COOP_CTA / G;
     const size_t grp_bytes = groups * (size_t)T * coop_traj_stride(S->grav.N) * sizeof(double) + coop_meta_bytes(S->grav.N, G, Cp->kmax);
     const size_t with_table = grp_bytes + coop_rec_bytes(Cp->L, G);
@@ -601,7 +612,7 @@ cudaError_t nyxb_launch_coop_g(const DevSetup* S, const DevCoop* Cp, int T, size
     const bool tab = with_table * 2 <= 227 * 1024;
     const size_t smem = tab ? with_table : grp_bytes;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-#define NYXB_COOP_GO(TT, TAB) launch_gt<G, TT, TAB>(S, Cp, n, smem, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, stream)
+#define NYXB_COOP_GO(TT, TAB) launch_gt<G, TT, TAB>(S, Cp, n, smem, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, sink, stream)
     if (T == 2) return tab ? NYXB_COOP_GO(2, true) : NYXB_COOP_GO(2, false);
     return tab ? NYXB_COOP_GO(1, true) : NYXB_COOP_GO(1, false);
 #undef NYXB_COOP_GO

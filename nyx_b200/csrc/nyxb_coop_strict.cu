@@ -235,7 +235,7 @@ nyxb_k_coop_strict(const __grid_constant__ DevSetup S, const __grid_constant__ D
                    const double* __restrict__ state, const double* __restrict__ consts,
                    const long long* __restrict__ epoch0, long long end_epoch, long long* __restrict__ step_io,
                    double* __restrict__ out_state, long long* __restrict__ out_epoch,
-                   nyxb_details* __restrict__ out_details, int* __restrict__ out_status) {
+                   nyxb_details* __restrict__ out_details, int* __restrict__ out_status, const DevSink sink) {
     extern __shared__ __align__(16) double ssm[];
     const int tid = threadIdx.x;
     const int lane = tid % G, grp = tid / G;
@@ -264,6 +264,10 @@ nyxb_k_coop_strict(const __grid_constant__ DevSetup S, const __grid_constant__ D
     // the whole triangle starts at zero: entries never written (column 0, columns beyond M+1) read as the reference's zeros
     for (int k = lane; k < (N + 2) * (N + 3) / 2; k += G) g.A[k] = 0.0;
     if (lane < 6) g.ycur[lane] = yc;
+    if (sink.cap > 0) {  // start state (instance.rs:307, 321)
+        if (lane < 6) sink.state[((size_t)lane * sink.cap) * n + traj] = yc;
+        if (lane == 6) sink.epoch[traj] = epoch;
+    }
     __syncwarp(gmask);
 
     const int stages = S.tb.stages;
@@ -367,6 +371,10 @@ nyxb_k_coop_strict(const __grid_constant__ DevSetup S, const __grid_constant__ D
         if (lane < 6) { yc = nx; g.ycur[lane] = nx; }
         g.cr = g.cr < 0.0 ? 0.0 : (g.cr > 2.0 ? 2.0 : g.cr);
         n_steps += 1;
+        if (n_steps < sink.cap) {  // the channel send of instance.rs:186-193 / 255-259
+            if (lane < 6) sink.state[((size_t)lane * sink.cap + (size_t)n_steps) * n + traj] = nx;
+            if (lane == 6) sink.epoch[(size_t)n_steps * n + traj] = epoch;
+        }
         if (g.pm < 0.0) { rc = NYXB_ERR_FUEL_EXHAUSTED; break; }
         if (last) {
             step_ns = prev_step;
@@ -382,6 +390,7 @@ nyxb_k_coop_strict(const __grid_constant__ DevSetup S, const __grid_constant__ D
         out_epoch[traj] = epoch;
         if (step_io) step_io[traj] = step_ns;
         out_status[traj] = (status & NYXB_WARN_MAX_ATTEMPTS) | rc;
+        if (sink.cap > 0) sink.count[traj] = (n_steps + 1 < sink.cap) ? n_steps + 1 : sink.cap;
     }
     if (lane == 7 && out_details) {
         nyxb_details d;
@@ -394,7 +403,8 @@ nyxb_k_coop_strict(const __grid_constant__ DevSetup S, const __grid_constant__ D
 template <int G>
 static cudaError_t launch_strict_g(const DevSetup* S, const DevCoopStrict* Cs, size_t n, const double* state, const double* consts,
                                    const long long* epoch0, long long end_epoch, long long* step_io, double* out_state,
-                                   long long* out_epoch, nyxb_details* out_details, int* out_status, cudaStream_t stream) {
+                                   long long* out_epoch, nyxb_details* out_details, int* out_status, const DevSink* sink,
+                                   cudaStream_t stream) {
     const size_t groups = SCOOP_CTA / G;
     const size_t smem = groups * (size_t)scoop_traj_stride(S->grav.N) * sizeof(double);
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
@@ -412,19 +422,20 @@ static cudaError_t launch_strict_g(const DevSetup* S, const DevCoopStrict* Cs, s
         if (grid * groups < n) grid = (n + groups - 1) / groups;
     }
     nyxb_k_coop_strict<G><<<(unsigned)grid, SCOOP_CTA, smem, stream>>>(*S, *Cs, n, state, consts, epoch0, end_epoch, step_io,
-                                                                       out_state, out_epoch, out_details, out_status);
+                                                                       out_state, out_epoch, out_details, out_status, *sink);
     return cudaGetLastError();
 }
 
 extern "C" cudaError_t nyxb_launch_coop_strict(const DevSetup* S, const DevCoopStrict* Cs, size_t n, const double* state,
                                                const double* consts, const long long* epoch0, long long end_epoch,
                                                long long* step_io, double* out_state, long long* out_epoch,
-                                               nyxb_details* out_details, int* out_status, cudaStream_t stream) {
+                                               nyxb_details* out_details, int* out_status, const DevSink* sink,
+                                               cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     switch (Cs->G) {
-    case 8: return launch_strict_g<8>(S, Cs, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, stream);
-    case 16: return launch_strict_g<16>(S, Cs, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, stream);
-    case 32: return launch_strict_g<32>(S, Cs, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, stream);
+    case 8: return launch_strict_g<8>(S, Cs, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, sink, stream);
+    case 16: return launch_strict_g<16>(S, Cs, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, sink, stream);
+    case 32: return launch_strict_g<32>(S, Cs, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, sink, stream);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -89,6 +89,14 @@ struct DevSetup {
     DevDrag drag;
 };
 
+// trajectory recording sink (device pointers; cap == 0: recording off)
+struct DevSink {
+    long long cap;
+    long long* epoch;  // [cap][n]
+    double* state;     // [6][cap][n]
+    long long* count;  // [n]
+};
+
 #define NYXB_NS_PER_S 1000000000LL
 #define NYXB_NS_PER_CENTURY 3155760000000000000LL
 

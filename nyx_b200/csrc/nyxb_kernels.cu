@@ -34,6 +34,9 @@ struct Inst {
     int det_attempts;
     long long n_steps, n_rejected, n_rhs;
     double dry_mass, extra_mass, srp_area, drag_area;
+    // trajectory recording (instance.rs:186-193, 255-259)
+    DevSink sink;
+    size_t idx, n;
 };
 
 // instance.rs:358-493
@@ -115,6 +118,14 @@ __device__ static int derive(const DevSetup& S, Inst& in, long long& dt_ns, doub
     }
 }
 
+// one record of the trajectory sink: epoch + position/velocity of trajectory `idx` at slot s (step-major SoA)
+__device__ __forceinline__ void record_state(const Inst& in, long long s) {
+    if (s >= in.sink.cap) return;
+    in.sink.epoch[(size_t)s * in.n + in.idx] = in.epoch_ns;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) in.sink.state[((size_t)c * in.sink.cap + s) * in.n + in.idx] = in.y[c];
+}
+
 // instance.rs:343-352 + spacecraft.rs:158-189
 __device__ static int single_step(const DevSetup& S, Inst& in) {
     long long dt;
@@ -126,6 +137,7 @@ __device__ static int single_step(const DevSetup& S, Inst& in) {
     for (int e = 0; e < 9; ++e) in.y[e] = next[e];
     in.y[6] = in.y[6] < 0.0 ? 0.0 : (in.y[6] > 2.0 ? 2.0 : in.y[6]);  // cosmic/spacecraft.rs:494
     in.n_steps += 1;
+    record_state(in, in.n_steps);  // the channel send of instance.rs:186-193 / 255-259
     return (in.y[8] < 0.0) ? NYXB_ERR_FUEL_EXHAUSTED : 0;
 }
 
@@ -162,7 +174,7 @@ NYXB_KTHREAD(const __grid_constant__ DevSetup S, size_t n,
              const long long* __restrict__ epoch0, long long end_epoch,
              long long* __restrict__ step_io,
              double* __restrict__ out_state, long long* __restrict__ out_epoch,
-             nyxb_details* __restrict__ out_details, int* __restrict__ out_status) {
+             nyxb_details* __restrict__ out_details, int* __restrict__ out_status, const DevSink sink) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Inst in;
@@ -175,7 +187,10 @@ NYXB_KTHREAD(const __grid_constant__ DevSetup S, size_t n,
     in.status = 0;
     in.det_step_ns = S.init_step_ns; in.det_error = 0.0; in.det_attempts = 1;
     in.n_steps = 0; in.n_rejected = 0; in.n_rhs = 0;
+    in.sink = sink; in.idx = i; in.n = n;
+    record_state(in, 0);  // start state (instance.rs:307, 321)
     int rc = propagate(S, in, end_epoch - in.epoch_ns);
+    if (sink.cap > 0) sink.count[i] = (in.n_steps + 1 < sink.cap) ? in.n_steps + 1 : sink.cap;
 #pragma unroll
     for (int e = 0; e < 9; ++e) out_state[(size_t)e * n + i] = in.y[e];
     out_epoch[i] = in.epoch_ns;
@@ -192,10 +207,10 @@ NYXB_KTHREAD(const __grid_constant__ DevSetup S, size_t n,
 extern "C" cudaError_t NYXB_LAUNCH_THREAD(const DevSetup* S, size_t n, const double* state, const double* consts,
                                           const long long* epoch0, long long end_epoch, long long* step_io,
                                           double* out_state, long long* out_epoch, nyxb_details* out_details,
-                                          int* out_status, int block, cudaStream_t stream) {
+                                          int* out_status, int block, const DevSink* sink, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     unsigned grid = (unsigned)((n + block - 1) / block);
     NYXB_KTHREAD<<<grid, block, 0, stream>>>(*S, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch,
-                                             out_details, out_status);
+                                             out_details, out_status, *sink);
     return cudaGetLastError();
 }

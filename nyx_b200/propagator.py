@@ -187,8 +187,10 @@ class Engine:
     def last_kernel_ms(self) -> float:
         return self._lib.nyxb_engine_last_kernel_ms(self._h)
 
-    def propagate_batch(self, state_soa, consts_soa, epoch0_ns, end_epoch_ns, step_ns=None):
-        """Host-buffer call of `nyxb_propagate_batch`. Returns (state, epoch, details, status)."""
+    def propagate_batch(self, state_soa, consts_soa, epoch0_ns, end_epoch_ns, step_ns=None, traj_capacity: int = 0):
+        """Host-buffer call of `nyxb_propagate_batch[_traj]`. Returns (state, epoch, details, status) and, when
+        `traj_capacity` > 0, a fifth element (epochs[cap][n], states[6][cap][n], count[n]): the start state and the
+        state after every accepted step (instance.rs:297-326)."""
         state_soa = np.ascontiguousarray(state_soa, dtype=np.float64)
         consts_soa = np.ascontiguousarray(consts_soa, dtype=np.float64)
         epoch0_ns = np.ascontiguousarray(epoch0_ns, dtype=np.int64)
@@ -204,11 +206,20 @@ class Engine:
             if step_ns.dtype != np.int64 or step_ns.shape != (n,) or not step_ns.flags["C_CONTIGUOUS"]:
                 raise ValueError("step_ns must be a contiguous int64[n] array")
             step_ptr = step_ns.ctypes.data
-        rc = self._lib.nyxb_propagate_batch(self._h, n, state_soa.ctypes.data, consts_soa.ctypes.data,
-                                            epoch0_ns.ctypes.data, int(end_epoch_ns), step_ptr, out_state.ctypes.data,
-                                            out_epoch.ctypes.data, details.ctypes.data, status.ctypes.data)
+        sink = None
+        if traj_capacity:
+            t_ep = np.zeros((traj_capacity, n), dtype=np.int64)
+            t_st = np.zeros((6, traj_capacity, n), dtype=np.float64)
+            t_cnt = np.zeros(n, dtype=np.int64)
+            sink = abi.TrajSink(int(traj_capacity), t_ep.ctypes.data, t_st.ctypes.data, t_cnt.ctypes.data)
+        rc = self._lib.nyxb_propagate_batch_traj(self._h, n, state_soa.ctypes.data, consts_soa.ctypes.data,
+                                                 epoch0_ns.ctypes.data, int(end_epoch_ns), step_ptr, out_state.ctypes.data,
+                                                 out_epoch.ctypes.data, details.ctypes.data, status.ctypes.data,
+                                                 C.byref(sink) if sink is not None else None)
         if rc != 0:
             raise PropagationError(f"nyxb_propagate_batch rc={rc}: {abi.last_error()}")
+        if traj_capacity:
+            return out_state, out_epoch, details, status, (t_ep, t_st, t_cnt)
         return out_state, out_epoch, details, status
 
     def propagate_batch_dev(self, n, state_ptr, consts_ptr, epoch0_ptr, end_epoch_ns, step_ptr, out_state_ptr,
@@ -312,6 +323,45 @@ class PropInstance:
     def for_duration(self, duration_ns: int) -> Spacecraft:
         """instance.rs:265-267"""
         return self.until_epoch(self.state.epoch() + int(duration_ns))
+
+    def for_duration_with_traj(self, duration_ns: int, capacity: Optional[int] = None):
+        """instance.rs:297-326: returns (end state, Traj of the start state + every accepted step)."""
+        return self.until_epoch_with_traj(self.state.epoch() + int(duration_ns), capacity)
+
+    def until_epoch_with_traj(self, end_ns: int, capacity: Optional[int] = None):
+        """instance.rs:330-340.  `capacity` bounds the records kept (default: enough for min-step-free propagation at
+        1/4 of the current step; the call is repeated with a larger buffer if it overflowed)."""
+        from .trajectory import Traj
+
+        start = self.state
+        span = abs(int(end_ns) - start.epoch())
+        cap = capacity or max(64, 4 * span // max(abs(int(self._step_ns[0])), 1) + 64)
+        while True:
+            step_before = self._step_ns.copy()
+            final, tr, overflow = self._run(end_ns, cap, start)
+            if not overflow or capacity:
+                break
+            self.state, self._step_ns = start, step_before  # retry with a larger sink
+            cap *= 4
+        return final, tr
+
+    def _run(self, end_ns, cap, start):
+        from .trajectory import Traj
+
+        st, cs, ep = pack_spacecraft([self.state])
+        eng = self.prop.engine(self.state.orbit.frame, self.almanac)
+        out, out_ep, det, status, (t_ep, t_st, t_cnt) = eng.propagate_batch(st, cs, ep, int(end_ns), self._step_ns, traj_capacity=cap)
+        err = status_error(status[0])
+        if err is not None:
+            raise err
+        d = det[0]
+        if d["n_steps"] > 0:
+            self.details = IntegrationDetails(int(d["step_ns"]), float(d["error"]), int(d["attempts"]), int(d["n_steps"]),
+                                              int(d["n_rejected"]), int(d["n_rhs"]))
+        self.state = self.state.with_vector(int(out_ep[0]), out[:, 0])
+        k = int(t_cnt[0])
+        tr = Traj(start, t_ep[:k, 0].copy(), np.ascontiguousarray(t_st[:, :k, 0].T)).finalize()
+        return self.state, tr, int(d["n_steps"]) + 1 > cap
 
     def until_epoch(self, end_ns: int) -> Spacecraft:
         """instance.rs:279-282"""

@@ -1,0 +1,102 @@
+"""`Traj` — recorded trajectory of one spacecraft with Hermite interpolation.
+
+Mirrors ``md/trajectory/traj.rs:54-162`` for what the propagation path produces:
+``finalize`` (dedup equal epochs, sort by epoch, traj.rs:75-80), ``at`` (exact hit or a 13-sample window
+centred like the reference's, traj.rs:83-126) and the `Interpolatable for Spacecraft` rule
+(interpolatable.rs:53-108): position/velocity by Hermite interpolation of (r, v) pairs.
+
+anise's `hermite_eval` is not in the reference tree; the interpolation here is the textbook Hermite
+divided-difference form (the algorithm NAIF's HRMINT / SPK type 13 uses) — parity unpinned at the anise boundary.
+Host-side utility (numpy): the reference interpolates on the host as well; it is not on the hot path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from .cosmic import Spacecraft
+
+INTERPOLATION_SAMPLES = 13  # interpolatable.rs:22
+
+
+class TrajError(RuntimeError):
+    """`TrajError::NoInterpolationData` (md/trajectory/mod.rs)."""
+
+
+def hermite_eval(xs: np.ndarray, ys: np.ndarray, ydots: np.ndarray, x: float):
+    """Hermite interpolation through (xs, ys) with derivatives ydots; returns (y(x), y'(x))."""
+    n = len(xs)
+    z = np.repeat(np.asarray(xs, dtype=np.float64), 2)
+    q = np.zeros((2 * n, 2 * n))
+    q[0::2, 0] = ys
+    q[1::2, 0] = ys
+    q[1::2, 1] = ydots
+    q[2::2, 1] = (q[2::2, 0] - q[1:-1:2, 0]) / (z[2::2] - z[1:-1:2])
+    for j in range(2, 2 * n):
+        q[j:, j] = (q[j:, j - 1] - q[j - 1:-1, j - 1]) / (z[j:] - z[:-j])
+    coef = np.diag(q)
+    # Horner on the Newton form, value and derivative together
+    val, der = coef[-1], 0.0
+    for k in range(2 * n - 2, -1, -1):
+        der = der * (x - z[k]) + val
+        val = val * (x - z[k]) + coef[k]
+    return float(val), float(der)
+
+
+@dataclass
+class Traj:
+    """Recorded states of one spacecraft: epochs [k] (int64 ns) and states [k, 6] (km, km/s)."""
+
+    template: Spacecraft
+    epochs_ns: np.ndarray
+    states: np.ndarray
+    name: Optional[str] = None
+
+    def finalize(self) -> "Traj":
+        """traj.rs:75-80: remove duplicate epochs, sort by epoch (a back-propagation is stored ascending)."""
+        keep = np.ones(len(self.epochs_ns), dtype=bool)
+        keep[1:] = self.epochs_ns[1:] != self.epochs_ns[:-1]
+        ep, st = self.epochs_ns[keep], self.states[keep]
+        order = np.argsort(ep, kind="stable")
+        self.epochs_ns, self.states = ep[order], st[order]
+        return self
+
+    def __len__(self) -> int:
+        return len(self.epochs_ns)
+
+    def _sc(self, epoch_ns: int, rv) -> Spacecraft:
+        vec = self.template.to_vector()
+        vec[:6] = rv
+        return self.template.with_vector(int(epoch_ns), vec)
+
+    def first(self) -> Spacecraft:
+        return self._sc(self.epochs_ns[0], self.states[0])
+
+    def last(self) -> Spacecraft:
+        return self._sc(self.epochs_ns[-1], self.states[-1])
+
+    def at(self, epoch_ns: int) -> Spacecraft:
+        """traj.rs:83-126."""
+        n = len(self)
+        if n == 0 or self.epochs_ns[0] > epoch_ns or self.epochs_ns[-1] < epoch_ns:
+            raise TrajError(f"no interpolation data at {epoch_ns}")
+        idx = int(np.searchsorted(self.epochs_ns, epoch_ns, side="left"))
+        if idx < n and self.epochs_ns[idx] == epoch_ns:
+            return self._sc(epoch_ns, self.states[idx])  # "Oh wow, we actually had this exact state!"
+        if idx == 0 or idx >= n:
+            raise TrajError(f"no interpolation data at {epoch_ns}")
+        num_left = INTERPOLATION_SAMPLES // 2
+        first_idx = max(idx - num_left, 0)
+        last_idx = min(n, first_idx + INTERPOLATION_SAMPLES)
+        if last_idx == n:
+            first_idx = max(last_idx - 2 * num_left, 0)
+        t0 = int(self.epochs_ns[first_idx])
+        ts = (self.epochs_ns[first_idx:last_idx] - t0).astype(np.float64) * 1e-9
+        win = self.states[first_idx:last_idx]
+        x = (int(epoch_ns) - t0) * 1e-9
+        rv = np.empty(6)
+        for c in range(3):
+            rv[c], rv[3 + c] = hermite_eval(ts, win[:, c], win[:, 3 + c], x)
+        return self._sc(epoch_ns, rv)

@@ -639,7 +639,16 @@ typedef struct {
     int fixed;          /* instance.rs:57 */
     nyxb_details det;
     int status;
+    /* trajectory recording: the channel of for_duration_with_traj (instance.rs:297-326) */
+    const nyxb_traj_sink* sink;
+    size_t idx, n;
 } inst_t;
+
+static void record_state(const inst_t* in, int64_t s) {
+    if (!in->sink || s >= in->sink->capacity) return;
+    in->sink->epoch_ns[(size_t)s * in->n + in->idx] = in->epoch_ns;
+    for (int c = 0; c < 6; ++c) in->sink->state[((size_t)c * in->sink->capacity + s) * in->n + in->idx] = in->y[c];
+}
 
 #define MAX_STAGES 16
 
@@ -729,6 +738,7 @@ static int single_step(inst_t* in, eom_ctx* cx, const nyxb_integ_opts* o, const 
     /* State::set clamps Cr (cosmic/spacecraft.rs:494) */
     in->y[6] = in->y[6] < 0.0 ? 0.0 : (in->y[6] > 2.0 ? 2.0 : in->y[6]);
     in->det.n_steps += 1;
+    record_state(in, in->det.n_steps);                           /* instance.rs:186-193, 255-259 */
     return finally_check(in);
 }
 
@@ -761,11 +771,11 @@ static int propagate(inst_t* in, eom_ctx* cx, const nyxb_integ_opts* o, const ta
 /* Batch driver == MonteCarlo::resume_run_until_epoch's par_iter              */
 /* (mc/montecarlo.rs:233-253): independent runs, OpenMP dynamic schedule.     */
 /* ------------------------------------------------------------------------- */
-int nyx_oracle_propagate_batch(const nyxb_dynamics* dyn, const nyxb_integ_opts* opts, size_t n,
-                               const double* state_soa, const double* consts_soa,
-                               const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
-                               double* out_state_soa, int64_t* out_epoch_ns,
-                               nyxb_details* out_details, int32_t* out_status, int n_threads) {
+int nyx_oracle_propagate_batch_traj(const nyxb_dynamics* dyn, const nyxb_integ_opts* opts, size_t n,
+                                    const double* state_soa, const double* consts_soa,
+                                    const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
+                                    double* out_state_soa, int64_t* out_epoch_ns,
+                                    nyxb_details* out_details, int32_t* out_status, const nyxb_traj_sink* sink, int n_threads) {
     tableau_t tb;
     if (tableau_for(opts->method, &tb)) return -1;
     if (dyn->n_bodies > NYXB_MAX_BODIES) return -1;
@@ -789,6 +799,8 @@ int nyx_oracle_propagate_batch(const nyxb_dynamics* dyn, const nyxb_integ_opts* 
             in.step_ns = step_ns ? step_ns[i] : opts->init_step_ns;
             in.fixed = opts->fixed_step;
             in.det.step_ns = opts->init_step_ns; in.det.error = 0.0; in.det.attempts = 1;
+            in.sink = (sink && sink->capacity > 0) ? sink : NULL; in.idx = i; in.n = n;
+            record_state(&in, 0);                                /* start state: instance.rs:307, 321 */
             eom_ctx cx;
             cx.dyn = dyn; cx.grav = grav; cx.grav_scratch = scratch; cx.n_rhs = 0;
             cx.dry_mass = consts_soa[0 * n + i]; cx.extra_mass = consts_soa[1 * n + i];
@@ -801,11 +813,21 @@ int nyx_oracle_propagate_batch(const nyxb_dynamics* dyn, const nyxb_integ_opts* 
             if (step_ns) step_ns[i] = in.step_ns;
             if (out_details) out_details[i] = in.det;
             out_status[i] = in.status;
+            if (in.sink) in.sink->count[i] = (in.det.n_steps + 1 < in.sink->capacity) ? in.det.n_steps + 1 : in.sink->capacity;
         }
         free(scratch);
     }
     nyx_oracle_grav_free(grav);
     return 0;
+}
+
+int nyx_oracle_propagate_batch(const nyxb_dynamics* dyn, const nyxb_integ_opts* opts, size_t n,
+                               const double* state_soa, const double* consts_soa,
+                               const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
+                               double* out_state_soa, int64_t* out_epoch_ns,
+                               nyxb_details* out_details, int32_t* out_status, int n_threads) {
+    return nyx_oracle_propagate_batch_traj(dyn, opts, n, state_soa, consts_soa, epoch0_ns, end_epoch_ns, step_ns, out_state_soa,
+                                           out_epoch_ns, out_details, out_status, NULL, n_threads);
 }
 
 /* Direct RHS access for unit tests (one evaluation of SpacecraftDynamics::eom). */

@@ -1,0 +1,125 @@
+"""Trajectory recording + interpolation: `for_duration_with_traj` / `Traj::at`."""
+import numpy as np
+import pytest
+
+import nyx_b200 as nb
+from nyx_b200.trajectory import Traj, hermite_eval
+from tests.util import S, leo_ensemble, leo_state, max_dr_dv, oracle_run
+
+
+def _dyn(degree=8):
+    gd = nb.GravityFieldData.from_fixture("jgm3_70x70", degree, degree, nb.IAU_EARTH_FRAME)
+    return nb.SpacecraftDynamics.new(nb.OrbitalDynamics.from_model(nb.GravityField.new(gd)))
+
+
+def _oracle_traj(oracle, prop, frame, st, cs, ep, end, cap):
+    packed = prop.dynamics.pack(frame, None)
+    return oracle.propagate_batch(packed.c, prop.opts.to_c(prop.method), st, cs, ep, end, traj_capacity=cap)
+
+
+def test_hermite_eval_reproduces_polynomials_and_derivatives():
+    xs = np.array([0.0, 0.7, 1.1, 2.0, 3.5])
+    f = lambda x: 3 * x**5 - x**3 + 2 * x - 1
+    df = lambda x: 15 * x**4 - 3 * x**2 + 2
+    y, yd = hermite_eval(xs, f(xs), df(xs), 1.7)  # degree 9 interpolant of a quintic: exact
+    assert abs(y - f(1.7)) < 1e-11 and abs(yd - df(1.7)) < 1e-10
+
+
+def test_oracle_recording_matches_channel_semantics(oracle):
+    """instance.rs:297-326: start state + every accepted step incl. the final partial one; overflow drops the tail."""
+    frame = nb.EARTH_J2000
+    mc, (st, cs, ep) = leo_ensemble(5, seed=41)
+    prop = nb.Propagator.default(_dyn())
+    end = 2 * 3600 * S
+    out, out_ep, det, status, (t_ep, t_st, t_cnt) = _oracle_traj(oracle, prop, frame, st, cs, ep, end, 256)
+    assert np.array_equal(t_cnt, det["n_steps"] + 1)
+    for i in range(5):
+        k = t_cnt[i]
+        assert t_ep[0, i] == 0 and np.array_equal(t_st[:, 0, i], st[:6, i])          # start state
+        assert t_ep[k - 1, i] == end and np.array_equal(t_st[:, k - 1, i], out[:6, i])  # final state
+        assert (np.diff(t_ep[:k, i]) > 0).all()
+    small = _oracle_traj(oracle, prop, frame, st, cs, ep, end, 10)
+    assert (small[4][2] == 10).all() and np.array_equal(small[4][0], t_ep[:10]) and np.array_equal(small[0], out)
+
+
+def test_traj_at_exact_hit_window_and_accuracy(oracle):
+    """Traj::at (traj.rs:83-126): exact epochs return the stored state; in between, the 13-sample Hermite window
+    reproduces an independent fine propagation to well below a millimetre."""
+    frame = nb.EARTH_J2000
+    sc = leo_state(frame)
+    st, cs, ep = nb.pack_spacecraft([sc])
+    prop = nb.Propagator.default(_dyn())
+    end = 3 * 3600 * S
+    out, _, det, _, (t_ep, t_st, t_cnt) = _oracle_traj(oracle, prop, frame, st, cs, ep, end, 512)
+    k = int(t_cnt[0])
+    tr = Traj(sc, t_ep[:k, 0].copy(), np.ascontiguousarray(t_st[:, :k, 0].T)).finalize()
+    assert len(tr) == k and tr.first().epoch() == 0 and tr.last().epoch() == end
+    mid = tr.at(int(tr.epochs_ns[7]))
+    assert np.array_equal(mid.orbit.to_cartesian_pos_vel(), tr.states[7])
+    for probe in (12_345_678_901, 5_000 * S + 17, end - 3):
+        direct, *_ = oracle_run(oracle, prop, frame, None, st, cs, ep, probe)
+        got = tr.at(probe).orbit.to_cartesian_pos_vel()
+        assert np.linalg.norm(got[:3] - direct[:3, 0]) < 2e-7 and np.linalg.norm(got[3:] - direct[3:6, 0]) < 1e-9
+    with pytest.raises(nb.TrajError):
+        tr.at(end + 1)
+    with pytest.raises(nb.TrajError):
+        tr.at(-1)
+
+
+def test_traj_finalize_sorts_back_propagation(oracle):
+    frame = nb.EARTH_J2000
+    sc = leo_state(frame, epoch_ns=3600 * S)
+    st, cs, ep = nb.pack_spacecraft([sc])
+    prop = nb.Propagator.default(nb.SpacecraftDynamics.new(nb.OrbitalDynamics.two_body()))
+    out, out_ep, det, _, (t_ep, t_st, t_cnt) = _oracle_traj(oracle, prop, frame.with_mu_km3_s2(nb.GMAT_EARTH_GM), st, cs, ep, 0, 256)
+    k = int(t_cnt[0])
+    assert out_ep[0] == 0 and (np.diff(t_ep[:k, 0]) < 0).all()  # recorded in propagation order (descending epochs)
+    tr = Traj(sc, t_ep[:k, 0].copy(), np.ascontiguousarray(t_st[:, :k, 0].T)).finalize()
+    assert (np.diff(tr.epochs_ns) > 0).all() and tr.first().epoch() == 0 and tr.last().epoch() == 3600 * S
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,lanes", [(nb.MODE_STRICT, 1), (nb.MODE_STRICT, 8), (nb.MODE_FAST, 1), (nb.MODE_FAST, 8), (nb.MODE_FAST, 16)])
+def test_gpu_recording_matches_oracle(oracle, mode, lanes):
+    """Every kernel writes the same step-major SoA stream the oracle records: bit-identical in STRICT mode."""
+    frame = nb.EARTH_J2000
+    mc, (st, cs, ep) = leo_ensemble(40, seed=42)
+    ep = ep + (np.arange(40, dtype=np.int64) % 3) * 900 * S
+    prop = nb.Propagator.default(_dyn(21), mode=mode)
+    eng = prop.engine(frame, None)
+    eng.set_lanes(lanes)
+    end = 2 * 3600 * S
+    out, out_ep, det, status, (g_ep, g_st, g_cnt) = eng.propagate_batch(st, cs, ep, end, traj_capacity=128)
+    ref, ref_ep, ref_det, ref_status, (o_ep, o_st, o_cnt) = _oracle_traj(oracle, prop, frame, st, cs, ep, end, 128)
+    assert (status == 0).all() and np.array_equal(g_cnt, det["n_steps"] + 1)
+    if mode == nb.MODE_STRICT:
+        assert np.array_equal(g_cnt, o_cnt) and np.array_equal(g_ep, o_ep) and np.array_equal(g_st, o_st)
+    else:
+        assert np.abs(g_cnt - o_cnt).max() <= 1
+        for i in range(40):
+            k = int(min(g_cnt[i], o_cnt[i])) - 1
+            assert np.abs(g_ep[:k, i] - o_ep[:k, i]).max() < 50_000_000  # adapted steps agree to < 50 ms
+            assert np.array_equal(g_st[:, 0, i], st[:6, i])
+        assert max_dr_dv(out, ref)[0] < 5e-7
+    # capacity overflow keeps the head of the stream and still returns the right final state
+    o2, _, d2, _, (e2, s2, c2) = eng.propagate_batch(st, cs, ep, end, traj_capacity=7)
+    assert (c2 == 7).all() and np.array_equal(e2, g_ep[:7]) and np.array_equal(o2, out)
+
+
+@pytest.mark.gpu
+def test_prop_instance_with_traj_api(oracle):
+    """`PropInstance::for_duration_with_traj` (instance.rs:297-326) + `Traj::at` through the public API."""
+    frame = nb.EARTH_J2000
+    sc = leo_state(frame)
+    prop = nb.Propagator.default(_dyn(21), mode=nb.MODE_STRICT)
+    inst = prop.with_(sc)
+    final, tr = inst.for_duration_with_traj(6 * 3600 * S)
+    assert final.epoch() == 6 * 3600 * S and tr.last().epoch() == final.epoch() and tr.first().epoch() == 0
+    assert len(tr) == inst.latest_details().n_steps + 1
+    assert np.array_equal(tr.last().orbit.to_cartesian_pos_vel(), final.orbit.to_cartesian_pos_vel())
+    st, cs, ep = nb.pack_spacecraft([sc])
+    direct, *_ = oracle_run(oracle, prop, frame, None, st, cs, ep, 10_000 * S)
+    assert np.linalg.norm(tr.at(10_000 * S).orbit.radius_km - direct[:3, 0]) < 2e-7
+    # explicit small capacity: truncated recording, same final state
+    f2, tr2 = prop.with_(sc).for_duration_with_traj(6 * 3600 * S, capacity=16)
+    assert len(tr2) == 16 and np.array_equal(f2.orbit.to_cartesian_pos_vel(), final.orbit.to_cartesian_pos_vel())
