@@ -56,6 +56,8 @@ def parse_args():
                    help="trajectories in the bounded CPU-baseline sample (0: 32 per host core, ~10 s of CPU work)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-strict", action="store_true", help="skip the extra bit-parity (STRICT mode) pass at N=1")
+    p.add_argument("--record", type=int, default=0, metavar="CAP",
+                   help="also time one pass with trajectory recording (CAP records per trajectory, device-resident sink)")
     p.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
                    help="c2 = BASELINE configs[1] (the metric's workload); c3/c4 = configs[2]/[3], reported for context only")
     return p.parse_args()
@@ -334,6 +336,29 @@ def main():
                              "frac": hbm_achieved / hbm_peak, "of": "measured" if peaks else "fallback",
                              "note": f"{BYTES_PER_TRAJ} algorithmic bytes per trajectory, independent of step count"},
         }
+        if world == 1 and args.record > 0:
+            # trajectory recording: 56 B per accepted step streamed to HBM, step-major SoA
+            cap = args.record
+            t_ep = torch.empty((cap, n), dtype=torch.int64, device=dev)
+            t_st = torch.empty((6, cap, n), dtype=torch.float64, device=dev)
+            t_cnt = torch.empty(n, dtype=torch.int64, device=dev)
+            sink = nb.abi.TrajSink(cap, t_ep.data_ptr(), t_st.data_ptr(), t_cnt.data_ptr())
+            import ctypes as C
+
+            def rec_pass():
+                rc = eng._lib.nyxb_propagate_batch_traj_dev(eng.handle, n, d_st.data_ptr(), d_cs.data_ptr(), d_ep.data_ptr(), end, None,
+                                                            d_out.data_ptr(), d_oep.data_ptr(), d_det.data_ptr(), d_status.data_ptr(),
+                                                            C.byref(sink), torch.cuda.current_stream(dev).cuda_stream)
+                assert rc == 0
+            rec_pass()
+            torch.cuda.synchronize(dev)
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record(); rec_pass(); r1.record(); torch.cuda.synchronize(dev)
+            rec_ms = r0.elapsed_time(r1)
+            recs = int(t_cnt.sum().item())
+            line["recording"] = {"value": local_steps / (rec_ms * 1e-3), "unit": "trajectory-steps/s", "ms": rec_ms, "records": recs,
+                                 "bytes_written": recs * 56, "write_gbs": recs * 56 / (rec_ms * 1e-3) / 1e9,
+                                 "note": "same pass with the start state + every accepted step recorded (instance.rs:297-326)"}
         if world == 1 and not args.no_cpu_baseline:
             leg = cpu_reference_leg(args, nb, min(args.cpu_sample, n))
             sample_n = min(args.cpu_sample, n)
