@@ -97,14 +97,16 @@ struct RotBase { double sa, ca, sd, cd, sw, cw; };
 
 // third bodies + SRP + drag: a few hundred flops, evaluated redundantly by every lane, kept out of line so that
 // the ephemeris scratch does not inflate the register count of the harmonic sum
-static __device__ __noinline__ int coop_extra(const DevSetup& S, const TrajCtx& g, long long t_ns, const double y[9], double acc[3]) {
-    double mass = g.dry_mass + y[8] + g.extra_mass;
+// (scalars, not the TrajCtx, are passed: taking the struct's address would force it into local memory)
+static __device__ __noinline__ int coop_extra(const DevSetup& S, double dry_mass, double extra_mass, double srp_area, double drag_area,
+                                              long long t_ns, const double y[9], double acc[3]) {
+    double mass = dry_mass + y[8] + extra_mass;
     const bool has_force = S.has_srp || S.has_drag;
     if (has_force && !(mass > 0.0)) return NYXB_ERR_MASSLESS;
     double bpos[NYXB_MAX_BODIES][3];
     int rc = accel_point_masses(S, t_ns, y, bpos, acc);
     if (rc) return rc;
-    if (has_force) accel_post(S, t_ns, y, bpos, mass, g.srp_area, g.drag_area, acc);
+    if (has_force) accel_post(S, t_ns, y, bpos, mass, srp_area, drag_area, acc);
     return 0;
 }
 
@@ -282,7 +284,15 @@ __device__ __forceinline__ void coop_rhs(const DevSetup& S, const double* __rest
         acc[1] = fma(fac, y[1], fma(R[7], ab2, fma(R[4], ab1, R[1] * ab0)));
         acc[2] = fma(fac, y[2], fma(R[8], ab2, fma(R[5], ab1, R[2] * ab0)));
         rc[t] = 0;
-        if (S.n_bodies > 0 || S.has_srp || S.has_drag) rc[t] = coop_extra(S, g[t], t_ns[t], y, acc);
+        if (S.n_bodies > 0 || S.has_srp || S.has_drag) {
+            // cold path: private copies, so that y/acc of the common path are never address-taken (they stay in registers)
+            double yy[9], aa[3];
+#pragma unroll
+            for (int e = 0; e < 9; ++e) yy[e] = y[e];
+            aa[0] = acc[0]; aa[1] = acc[1]; aa[2] = acc[2];
+            rc[t] = coop_extra(S, g[t].dry_mass, g[t].extra_mass, g[t].srp_area, g[t].drag_area, t_ns[t], yy, aa);
+            acc[0] = aa[0]; acc[1] = aa[1]; acc[2] = aa[2];
+        }
         // lane c < 3 keeps the velocity component c, lanes 3..5 the acceleration components (selects, no jump table)
         const int c3 = lane >= 3 ? lane - 3 : lane;
         const double vsel = c3 == 0 ? y[3] : (c3 == 1 ? y[4] : y[5]);
