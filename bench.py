@@ -314,6 +314,13 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None  # dram__bytes_read + dram__bytes_write of one launch of this workload, from the committed ncu capture
+        try:
+            tj = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
+            if args.workload == "c2" and args.n_traj == 10_000 and args.span_days == 3.0 and args.degree == 21:
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
         hbm_achieved = n * BYTES_PER_TRAJ / (kern_ms * 1e-3) / 1e9
         line = {
             "metric": "trajectory-steps/sec (ensemble)", "value": value, "unit": "trajectory-steps/s",
@@ -328,7 +335,8 @@ def main():
             "gpu_launches": all_launches,
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None, "traffic": None,
+                         "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
+                         "algorithmic_bytes": n * BYTES_PER_TRAJ,
                          "note": "FP64-pipe bound (no tensor-core or HBM-bound work on this path); peak = live DFMA probe "
                                  f"(nyxb_measure_fp64_tflops); algorithmic {fps:.0f} flop per accepted step",
                          "kernel_ms": kern_ms},
