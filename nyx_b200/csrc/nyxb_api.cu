@@ -65,7 +65,7 @@ struct nyxb_engine {
     }
 };
 
-static bool tableau_for(int method, int& order, int& stages, const double*& a, const double*& b) {
+static bool tableau_for(int method, int& order, int& stages, const NyxbCoef*& a, const NyxbCoef*& b) {
     switch (method) {  // rk_methods/mod.rs:81-133
     case NYXB_RK89: order = 9; stages = 16; a = NYXB_RK89_A; b = NYXB_RK89_B; return true;
     case NYXB_DP78: order = 8; stages = 13; a = NYXB_DP78_A; b = NYXB_DP78_B; return true;
@@ -131,7 +131,7 @@ extern "C" nyxb_engine* nyxb_engine_create(const nyxb_dynamics* dyn, const nyxb_
 
     // ---- tableau (dense rows, c accumulated left to right as instance.rs:379-386 does)
     int order, stages;
-    const double *a, *b;
+    const NyxbCoef *a, *b;
     if (!tableau_for(opts->method, order, stages, a, b)) { set_err("unknown integration method"); delete e; return nullptr; }
     S.tb.stages = stages;
     S.tb.order = order;
@@ -139,15 +139,15 @@ extern "C" nyxb_engine* nyxb_engine_create(const nyxb_dynamics* dyn, const nyxb_
     for (int i = 0; i < stages - 1; ++i) {
         volatile double ci = 0.0;
         for (int j = 0; j <= i; ++j) {
-            double aij = a[idx++];
+            double aij = nyxb_tableau_value(a[idx++]);
             ci = ci + aij;
             S.tb.a[i * NYXB_MAX_STAGES + j] = aij;
         }
         S.tb.c[i] = ci;
     }
     for (int i = 0; i < stages; ++i) {
-        S.tb.b[i] = b[i];
-        volatile double d = b[i] - b[i + stages];
+        S.tb.b[i] = nyxb_tableau_value(b[i]);
+        volatile double d = S.tb.b[i] - nyxb_tableau_value(b[i + stages]);
         S.tb.e[i] = d;
     }
     S.error_ctrl = opts->error_ctrl;
