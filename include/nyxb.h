@@ -174,6 +174,7 @@ enum nyxb_status {
     NYXB_ERR_FUEL_EXHAUSTED = 2, /* DynamicsError::FuelExhausted           spacecraft.rs:163-168 */
     NYXB_ERR_MASSLESS = 3,       /* DynamicsError::MasslessSpacecraft      spacecraft.rs:201-203 */
     NYXB_ERR_EPHEMERIS = 4,      /* almanac error: epoch outside ephemeris coverage */
+    NYXB_ERR_EVENT_NOT_FOUND = 5,/* PropagationError::NthEventError: end epoch reached first (event.rs:177-182) */
     NYXB_WARN_MAX_ATTEMPTS = 0x100 /* OR-ed flag: instance.rs:440-445 (warn only) */
 };
 
@@ -244,6 +245,35 @@ typedef struct {
     double* state;       /* [6][capacity][n] */
     int64_t* count;      /* [n] */
 } nyxb_traj_sink;
+
+/* ---- Event-terminated propagation (next row (f)-3): the stop condition of `PropInstance::until_nth_event`
+ * (propagators/event.rs:88-211, used by MonteCarlo::run_until_nth_event mc/montecarlo.rs:93-183).  After every accepted
+ * NON-final step the event scalar minus `value` is evaluated; a sign change (y_prev * y_next < 0, event.rs:141-144) counts
+ * one crossing; the run stops at the end of the step that brings the count to `trigger` (the state is returned and
+ * recorded).  The root search inside that last step (Brent on the Hermite-interpolated trajectory, event.rs:186-196)
+ * stays on the host.  Closed set of scalars (the reference's anise `ScalarExpr` is open-ended and not in the tree). */
+enum nyxb_event_kind {
+    NYXB_EVENT_NONE = 0,
+    NYXB_EVENT_RMAG = 1,   /* |r| km            */
+    NYXB_EVENT_RDOTV = 2,  /* r . v  km^2/s  (zero at the apsides) */
+    NYXB_EVENT_X = 3, NYXB_EVENT_Y = 4, NYXB_EVENT_Z = 5,   /* Cartesian components, km (Z = 0: node crossing) */
+    NYXB_EVENT_VMAG = 6    /* |v| km/s          */
+};
+typedef struct {
+    int32_t kind;       /* enum nyxb_event_kind */
+    int32_t trigger;    /* 1-based number of crossings to stop at */
+    double value;       /* desired value: the monitored function is scalar - value */
+    int32_t* crossings; /* [n] out: crossings seen; status NYXB_ERR_EVENT_NOT_FOUND when < trigger at the end epoch */
+} nyxb_event;
+
+/* nyxb_propagate_batch_traj + stop condition (HOST arrays; event == NULL: plain until-epoch propagation). */
+int32_t nyxb_propagate_batch_event(nyxb_engine* eng, size_t n,
+                                   const double* state_soa, const double* consts_soa,
+                                   const int64_t* epoch0_ns, int64_t end_epoch_ns,
+                                   int64_t* step_ns,
+                                   double* out_state_soa, int64_t* out_epoch_ns,
+                                   nyxb_details* out_details, int32_t* out_status,
+                                   const nyxb_traj_sink* sink, const nyxb_event* event);
 
 /* nyxb_propagate_batch + recording into `sink` (HOST arrays; NULL sink == nyxb_propagate_batch). */
 int32_t nyxb_propagate_batch_traj(nyxb_engine* eng, size_t n,

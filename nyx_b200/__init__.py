@@ -15,6 +15,7 @@ from .frames import (EARTH, EARTH_J2000, GMAT_EARTH_GM, GMAT_MOON_GM, GMAT_SUN_G
 from .gravity import GravityFieldData
 from .monte_carlo import DispersedState, MonteCarlo, MvnSpacecraft, Results, Run
 from .trajectory import Traj, TrajError, hermite_eval
+from .event import Event, brent, locate_event
 from .propagator import (Engine, ErrorControl, IntegrationDetails, IntegratorMethod, IntegratorOptions, PropagationError,
                          PropInstance, Propagator)
 

@@ -19,10 +19,12 @@ RK89, DP78, DP45, RK4, CK45, V56 = range(6)
 # enum nyxb_error_ctrl — propagators/error_ctrl.rs:30-71
 (RSS_CARTESIAN_STATE, RSS_CARTESIAN_STEP, RSS_STATE, RSS_STEP, LARGEST_ERROR, LARGEST_STATE, LARGEST_STEP) = range(7)
 # enum nyxb_status
-OK, ERR_PROP_MATH, ERR_FUEL_EXHAUSTED, ERR_MASSLESS, ERR_EPHEMERIS = range(5)
+OK, ERR_PROP_MATH, ERR_FUEL_EXHAUSTED, ERR_MASSLESS, ERR_EPHEMERIS, ERR_EVENT_NOT_FOUND = range(6)
 WARN_MAX_ATTEMPTS = 0x100
 # enum nyxb_mode
 MODE_STRICT, MODE_FAST = 0, 1
+# enum nyxb_event_kind
+EVENT_NONE, EVENT_RMAG, EVENT_RDOTV, EVENT_X, EVENT_Y, EVENT_Z, EVENT_VMAG = range(7)
 # enum nyxb_density
 DENSITY_CONSTANT, DENSITY_EXPONENTIAL, DENSITY_STDATM = range(3)
 
@@ -138,6 +140,15 @@ class TrajSink(C.Structure):
     ]
 
 
+class EventC(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("trigger", C.c_int32),
+        ("value", C.c_double),
+        ("crossings", C.c_void_p),
+    ]
+
+
 DETAILS_DTYPE = np.dtype(
     [
         ("step_ns", "<i8"),
@@ -192,6 +203,8 @@ def _declare(lib):
     lib.nyxb_propagate_batch_traj.argtypes = batch_args + [C.POINTER(TrajSink)]
     lib.nyxb_propagate_batch_traj_dev.restype = C.c_int32
     lib.nyxb_propagate_batch_traj_dev.argtypes = batch_args + [C.POINTER(TrajSink), vp]
+    lib.nyxb_propagate_batch_event.restype = C.c_int32
+    lib.nyxb_propagate_batch_event.argtypes = batch_args + [C.POINTER(TrajSink), C.POINTER(EventC)]
     lib.nyxb_engine_set_lanes.restype = C.c_int32
     lib.nyxb_engine_set_lanes.argtypes = [vp, C.c_int32]
     lib.nyxb_engine_get_lanes.restype = C.c_int32
@@ -216,6 +229,7 @@ EXPORTED_SYMBOLS = [
     "nyxb_propagate_batch_dev",
     "nyxb_propagate_batch_traj",
     "nyxb_propagate_batch_traj_dev",
+    "nyxb_propagate_batch_event",
     "nyxb_engine_set_lanes",
     "nyxb_engine_get_lanes",
     "nyxb_engine_launch_count",

@@ -332,7 +332,7 @@ static int32_t launch(nyxb_engine* e, size_t n, const double* state, const doubl
 }
 
 static DevSink make_sink(const nyxb_traj_sink* sink) {
-    DevSink d{0, nullptr, nullptr, nullptr};
+    DevSink d{};
     if (sink && sink->capacity > 0 && sink->epoch_ns && sink->state && sink->count) {
         d.cap = sink->capacity; d.epoch = (long long*)sink->epoch_ns; d.state = sink->state; d.count = (long long*)sink->count;
     }
@@ -360,10 +360,16 @@ extern "C" int32_t nyxb_propagate_batch_dev(nyxb_engine* eng, size_t n, const do
                                          out_epoch_ns, out_details, out_status, nullptr, cuda_stream);
 }
 
-extern "C" int32_t nyxb_propagate_batch_traj(nyxb_engine* eng, size_t n, const double* state_soa, const double* consts_soa,
-                                             const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
-                                             double* out_state_soa, int64_t* out_epoch_ns, nyxb_details* out_details,
-                                             int32_t* out_status, const nyxb_traj_sink* sink) {
+extern "C" int32_t nyxb_propagate_batch_event(nyxb_engine* eng, size_t n, const double* state_soa, const double* consts_soa,
+                                              const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
+                                              double* out_state_soa, int64_t* out_epoch_ns, nyxb_details* out_details,
+                                              int32_t* out_status, const nyxb_traj_sink* sink, const nyxb_event* event) {
+    if (event && event->kind != NYXB_EVENT_NONE &&
+        (event->kind < NYXB_EVENT_RMAG || event->kind > NYXB_EVENT_VMAG || event->trigger < 1 || !event->crossings)) {
+        set_err("bad event descriptor");
+        return NYXB_RC_BAD_ARG;
+    }
+    const bool has_ev = event && event->kind != NYXB_EVENT_NONE;
     if (!eng || !state_soa || !consts_soa || !epoch0_ns || !out_state_soa || !out_epoch_ns || !out_status) {
         set_err("null argument");
         return NYXB_RC_BAD_ARG;
@@ -381,7 +387,7 @@ extern "C" int32_t nyxb_propagate_batch_traj(nyxb_engine* eng, size_t n, const d
         TRY2(cudaMalloc(&eng->d_f64, sizeof(double) * 22 * n));
         TRY2(cudaMalloc(&eng->d_i64, sizeof(long long) * 3 * n));
         TRY2(cudaMalloc(&eng->d_det, sizeof(nyxb_details) * n));
-        TRY2(cudaMalloc(&eng->d_status, sizeof(int) * n));
+        TRY2(cudaMalloc(&eng->d_status, sizeof(int) * 2 * n));  // status | event crossings
         eng->cap = n;
     }
     double* d_f64 = eng->d_f64;
@@ -394,7 +400,8 @@ extern "C" int32_t nyxb_propagate_batch_traj(nyxb_engine* eng, size_t n, const d
     TRY2(cudaMemcpyAsync(d_i64, epoch0_ns, sizeof(long long) * n, cudaMemcpyHostToDevice, st));
     if (step_ns) TRY2(cudaMemcpyAsync(d_i64 + 2 * n, step_ns, sizeof(long long) * n, cudaMemcpyHostToDevice, st));
     // trajectory sink on the device: [epoch cap*n i64 | state 6*cap*n f64 | count n i64]
-    DevSink dsink{0, nullptr, nullptr, nullptr};
+    DevSink dsink{};
+    if (has_ev) { dsink.ev_kind = event->kind; dsink.ev_trigger = event->trigger; dsink.ev_value = event->value; dsink.ev_crossings = d_status + n; }
     const bool rec = sink && sink->capacity > 0 && sink->epoch_ns && sink->state && sink->count;
     if (rec) {
         const size_t cap = (size_t)sink->capacity;
@@ -419,6 +426,7 @@ extern "C" int32_t nyxb_propagate_batch_traj(nyxb_engine* eng, size_t n, const d
     if (step_ns) TRY2(cudaMemcpyAsync(step_ns, d_i64 + 2 * n, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
     if (out_details) TRY2(cudaMemcpyAsync(out_details, d_det, sizeof(nyxb_details) * n, cudaMemcpyDeviceToHost, st));
     TRY2(cudaMemcpyAsync(out_status, d_status, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    if (has_ev) TRY2(cudaMemcpyAsync(event->crossings, d_status + n, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
     if (rec) {
         const size_t cap = (size_t)sink->capacity;
         TRY2(cudaMemcpyAsync(sink->epoch_ns, dsink.epoch, cap * n * 8, cudaMemcpyDeviceToHost, st));
@@ -432,6 +440,14 @@ extern "C" int32_t nyxb_propagate_batch_traj(nyxb_engine* eng, size_t n, const d
     }
     return rc;
 #undef TRY2
+}
+
+extern "C" int32_t nyxb_propagate_batch_traj(nyxb_engine* eng, size_t n, const double* state_soa, const double* consts_soa,
+                                             const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
+                                             double* out_state_soa, int64_t* out_epoch_ns, nyxb_details* out_details,
+                                             int32_t* out_status, const nyxb_traj_sink* sink) {
+    return nyxb_propagate_batch_event(eng, n, state_soa, consts_soa, epoch0_ns, end_epoch_ns, step_ns, out_state_soa, out_epoch_ns,
+                                      out_details, out_status, sink, nullptr);
 }
 
 extern "C" int32_t nyxb_propagate_batch(nyxb_engine* eng, size_t n, const double* state_soa, const double* consts_soa,

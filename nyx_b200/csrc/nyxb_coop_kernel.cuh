@@ -29,7 +29,7 @@
 #ifndef COOP_CTA
 #define COOP_CTA 128
 #endif
-#define COOP_SM_FIXED 120  // kst[16*6] + ys[6] + ycur[6] + nxt[6] + er[6]
+#define COOP_SM_FIXED 122  // kst[16*6] + ys[6] + ycur[6] + nxt[6] + er[6] + event {previous value, crossings}
 
 // doubles of shared memory per trajectory, padded to 8 (mod 16) doubles so that consecutive trajectories
 // start 64 B apart modulo the 128-B bank row instead of on the same banks
@@ -85,6 +85,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 // per-trajectory view of the group's shared memory + constants of motion
 struct TrajCtx {
     double* kst; double* ys; double* ycur; double* nxt; double* er;
+    double* ev;  // [0] previous event value, [1] crossings so far (kept out of registers: cold path)
     double* rm; double* im; double* rp;
     double dry_mass, extra_mass, srp_area, drag_area;
     double cr, cd, pm;  // y[6..8]: constant without guidance (spacecraft.rs:248)
@@ -367,7 +368,7 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
 #pragma unroll
     for (int t = 0; t < T; ++t) {
         double* s = sm + (size_t)t * tstride;
-        g[t].kst = s; g[t].ys = s + 96; g[t].ycur = s + 102; g[t].nxt = s + 108; g[t].er = s + 114;
+        g[t].kst = s; g[t].ys = s + 96; g[t].ycur = s + 102; g[t].nxt = s + 108; g[t].er = s + 114; g[t].ev = s + 120;
         g[t].rm = s + COOP_SM_FIXED; g[t].im = g[t].rm + pw; g[t].rp = g[t].im + pw;
         g[t].hz = 0.0;
         valid[t] = (set * T + t) < n;
@@ -386,6 +387,11 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
         retry[t] = false; last[t] = false; h[t] = 0.0; nx[t] = 0.0; prev_step[t] = step_ns[t]; prev_fixed[t] = fixed[t];
         rbase[t].sa = 0; rbase[t].ca = 1; rbase[t].sd = 1; rbase[t].cd = 0; rbase[t].sw = 0; rbase[t].cw = 1;
         if (lane < 6) g[t].ycur[lane] = yc[t];
+        if (sink.ev_kind && lane == 0) {
+            g[t].ev[0] = event_eval(sink.ev_kind, sink.ev_value, state[traj[t]], state[n + traj[t]], state[2 * n + traj[t]],
+                                    state[3 * n + traj[t]], state[4 * n + traj[t]], state[5 * n + traj[t]]);
+            g[t].ev[1] = 0.0;
+        }
         if (valid[t] && sink.cap > 0) {  // start state (instance.rs:307, 321)
             if (lane < 6) sink.state[((size_t)lane * sink.cap) * n + traj[t]] = yc[t];
             if (lane == 6) sink.epoch[traj[t]] = epoch[t];
@@ -553,6 +559,13 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
                 if (lane == 6) sink.epoch[s * n + traj[t]] = epoch[t];
             }
             if (g[t].pm < 0.0) { rc[t] = NYXB_ERR_FUEL_EXHAUSTED; done[t] = true; }
+            if (sink.ev_kind && !last[t]) {  // stop condition on non-final steps (instance.rs:243-252, event.rs:120-150); nxt = new state
+                const double yn = event_eval(sink.ev_kind, sink.ev_value, g[t].nxt[0], g[t].nxt[1], g[t].nxt[2], g[t].nxt[3], g[t].nxt[4], g[t].nxt[5]);
+                const double cnt = g[t].ev[1] + ((g[t].ev[0] * yn < 0.0) ? 1.0 : 0.0);
+                __syncwarp(gmask);
+                if (lane == 0) { g[t].ev[0] = yn; g[t].ev[1] = cnt; }
+                if (cnt >= (double)sink.ev_trigger) done[t] = true;
+            }
             if (last[t]) {
                 step_ns[t] = prev_step[t];
                 fixed[t] = prev_fixed[t];
@@ -574,6 +587,11 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
             out_state[6 * n + traj[t]] = g[t].cr; out_state[7 * n + traj[t]] = g[t].cd; out_state[8 * n + traj[t]] = g[t].pm;
             out_epoch[traj[t]] = epoch[t];
             if (step_io) step_io[traj[t]] = step_ns[t];
+            if (sink.ev_kind) {
+                const int cnt = (int)g[t].ev[1];
+                sink.ev_crossings[traj[t]] = cnt;
+                if (rc[t] == 0 && cnt < sink.ev_trigger) rc[t] = NYXB_ERR_EVENT_NOT_FOUND;  // event.rs:177-182
+            }
             out_status[traj[t]] = (status[t] & NYXB_WARN_MAX_ATTEMPTS) | rc[t];
             if (sink.cap > 0) sink.count[traj[t]] = (n_steps[t] + 1 < sink.cap) ? n_steps[t] + 1 : sink.cap;
         }

@@ -264,6 +264,9 @@ nyxb_k_coop_strict(const __grid_constant__ DevSetup S, const __grid_constant__ D
     // the whole triangle starts at zero: entries never written (column 0, columns beyond M+1) read as the reference's zeros
     for (int k = lane; k < (N + 2) * (N + 3) / 2; k += G) g.A[k] = 0.0;
     if (lane < 6) g.ycur[lane] = yc;
+    int ev_count = 0;
+    double ev_prev = sink.ev_kind ? event_eval(sink.ev_kind, sink.ev_value, state[traj], state[n + traj], state[2 * n + traj],
+                                               state[3 * n + traj], state[4 * n + traj], state[5 * n + traj]) : 0.0;
     if (sink.cap > 0) {  // start state (instance.rs:307, 321)
         if (lane < 6) sink.state[((size_t)lane * sink.cap) * n + traj] = yc;
         if (lane == 6) sink.epoch[traj] = epoch;
@@ -376,6 +379,12 @@ nyxb_k_coop_strict(const __grid_constant__ DevSetup S, const __grid_constant__ D
             if (lane == 6) sink.epoch[(size_t)n_steps * n + traj] = epoch;
         }
         if (g.pm < 0.0) { rc = NYXB_ERR_FUEL_EXHAUSTED; break; }
+        if (sink.ev_kind && !last) {  // stop condition on non-final steps (instance.rs:243-252, event.rs:120-150)
+            const double yn = event_eval(sink.ev_kind, sink.ev_value, g.nxt[0], g.nxt[1], g.nxt[2], g.nxt[3], g.nxt[4], g.nxt[5]);
+            if (ev_prev * yn < 0.0) ev_count += 1;
+            ev_prev = yn;
+            if (ev_count >= sink.ev_trigger) break;
+        }
         if (last) {
             step_ns = prev_step;
             fixed = prev_fixed;
@@ -389,6 +398,10 @@ nyxb_k_coop_strict(const __grid_constant__ DevSetup S, const __grid_constant__ D
         out_state[6 * n + traj] = g.cr; out_state[7 * n + traj] = g.cd; out_state[8 * n + traj] = g.pm;
         out_epoch[traj] = epoch;
         if (step_io) step_io[traj] = step_ns;
+        if (sink.ev_kind) {
+            sink.ev_crossings[traj] = ev_count;
+            if (rc == 0 && ev_count < sink.ev_trigger) rc = NYXB_ERR_EVENT_NOT_FOUND;  // event.rs:177-182
+        }
         out_status[traj] = (status & NYXB_WARN_MAX_ATTEMPTS) | rc;
         if (sink.cap > 0) sink.count[traj] = (n_steps + 1 < sink.cap) ? n_steps + 1 : sink.cap;
     }

@@ -95,7 +95,25 @@ struct DevSink {
     long long* epoch;  // [cap][n]
     double* state;     // [6][cap][n]
     long long* count;  // [n]
+    // stop condition of until_nth_event (event.rs:88-211); ev_kind == 0: none
+    int ev_kind, ev_trigger;
+    double ev_value;
+    int* ev_crossings;  // [n]
 };
+
+// event scalar minus the desired value (closed set, see nyxb_event_kind)
+__device__ __forceinline__ double event_eval(int kind, double value, double x, double y, double z, double vx, double vy, double vz) {
+    double s;
+    switch (kind) {
+    case NYXB_EVENT_RMAG: s = sqrt((x * x + y * y) + z * z); break;
+    case NYXB_EVENT_RDOTV: s = (x * vx + y * vy) + z * vz; break;
+    case NYXB_EVENT_X: s = x; break;
+    case NYXB_EVENT_Y: s = y; break;
+    case NYXB_EVENT_Z: s = z; break;
+    default: s = sqrt((vx * vx + vy * vy) + vz * vz); break;
+    }
+    return s - value;
+}
 
 #define NYXB_NS_PER_S 1000000000LL
 #define NYXB_NS_PER_CENTURY 3155760000000000000LL

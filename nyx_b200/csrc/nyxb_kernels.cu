@@ -37,6 +37,8 @@ struct Inst {
     // trajectory recording (instance.rs:186-193, 255-259)
     DevSink sink;
     size_t idx, n;
+    double ev_prev;
+    int ev_count;
 };
 
 // instance.rs:358-493
@@ -165,6 +167,12 @@ __device__ static int propagate(const DevSetup& S, Inst& in, long long duration_
         }
         int rc = single_step(S, in);
         if (rc) return rc;
+        if (in.sink.ev_kind) {  // stop condition, evaluated on non-final steps only (instance.rs:243-252, event.rs:120-150)
+            const double yn = event_eval(in.sink.ev_kind, in.sink.ev_value, in.y[0], in.y[1], in.y[2], in.y[3], in.y[4], in.y[5]);
+            if (in.ev_prev * yn < 0.0) in.ev_count += 1;
+            in.ev_prev = yn;
+            if (in.ev_count >= in.sink.ev_trigger) return 0;
+        }
     }
 }
 
@@ -189,7 +197,13 @@ NYXB_KTHREAD(const __grid_constant__ DevSetup S, size_t n,
     in.n_steps = 0; in.n_rejected = 0; in.n_rhs = 0;
     in.sink = sink; in.idx = i; in.n = n;
     record_state(in, 0);  // start state (instance.rs:307, 321)
+    in.ev_count = 0;
+    in.ev_prev = sink.ev_kind ? event_eval(sink.ev_kind, sink.ev_value, in.y[0], in.y[1], in.y[2], in.y[3], in.y[4], in.y[5]) : 0.0;
     int rc = propagate(S, in, end_epoch - in.epoch_ns);
+    if (sink.ev_kind) {
+        sink.ev_crossings[i] = in.ev_count;
+        if (rc == 0 && in.ev_count < sink.ev_trigger) rc = NYXB_ERR_EVENT_NOT_FOUND;  // event.rs:177-182
+    }
     if (sink.cap > 0) sink.count[i] = (in.n_steps + 1 < sink.cap) ? in.n_steps + 1 : sink.cap;
 #pragma unroll
     for (int e = 0; e < 9; ++e) out_state[(size_t)e * n + i] = in.y[e];

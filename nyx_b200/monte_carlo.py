@@ -136,5 +136,42 @@ class MonteCarlo:
             runs.append(Run(idx, ds, res))
         return Results(runs, self.scenario, out, det, status)
 
+    def run_until_nth_event(self, prop: Propagator, almanac: Optional[Almanac], max_duration_ns: int, event, trigger: int,
+                            num_runs: int, traj_capacity: int = 2048) -> Results:
+        return self.resume_run_until_nth_event(prop, almanac, 0, max_duration_ns, event, trigger, num_runs, traj_capacity)
+
+    def resume_run_until_nth_event(self, prop: Propagator, almanac: Optional[Almanac], skip: int, max_duration_ns: int, event,
+                                   trigger: int, num_runs: int, traj_capacity: int = 2048) -> Results:
+        """mc/montecarlo.rs:115-183: every run stops at the end of the step in which `event` crossed zero for the
+        `trigger`-th time (ONE device launch with the stop condition + recording), then the event epoch is located per
+        run on its recorded trajectory (event.rs:186-211).  A run's result is (state at the event, Traj) or the error."""
+        from .event import locate_event
+        from .trajectory import Traj
+
+        init_states = self.generate_states(skip, num_runs, self.seed)
+        st, cs, ep = pack_spacecraft(ds.state for _, ds in init_states)
+        eng = prop.engine(self.nominal_state.orbit.frame, almanac)
+        end_ns = self.nominal_state.epoch() + int(max_duration_ns)
+        cap = int(traj_capacity)
+        while True:
+            out, out_ep, det, status, (t_ep, t_st, t_cnt), crossings = eng.propagate_batch(
+                st, cs, ep, end_ns, traj_capacity=cap, event=(event.kind, event.value, trigger))
+            if int(det["n_steps"].max()) + 1 <= cap:
+                break
+            cap *= 4  # a run overflowed its sink: its bracket would be lost
+        runs = []
+        for (idx, ds) in init_states:
+            code = int(status[idx]) & 0xFF
+            if code == abi.ERR_EVENT_NOT_FOUND:
+                res = PropagationError(f"NthEventError: nth={trigger}, found={int(crossings[idx])}")
+            elif code:
+                res = status_error(status[idx])
+            else:
+                k = int(t_cnt[idx])
+                tr = Traj(ds.state, t_ep[:k, idx].copy(), np.ascontiguousarray(t_st[:, :k, idx].T)).finalize()
+                res = (locate_event(tr, event), tr)
+            runs.append(Run(idx, ds, res))
+        return Results(runs, self.scenario, out, det, status)
+
     def __str__(self):
         return f"{self.scenario} - Nyx Monte Carlo - seed: {self.seed}"

@@ -70,6 +70,7 @@ _STATUS_MSG = {
     abi.ERR_FUEL_EXHAUSTED: "DynamicsError::FuelExhausted: negative prop mass",
     abi.ERR_MASSLESS: "DynamicsError::MasslessSpacecraft",
     abi.ERR_EPHEMERIS: "DynamicsError::DynamicsAlmanacError: epoch outside ephemeris coverage",
+    abi.ERR_EVENT_NOT_FOUND: "PropagationError::NthEventError: end of the search window reached before the n-th event",
 }
 
 
@@ -187,10 +188,12 @@ class Engine:
     def last_kernel_ms(self) -> float:
         return self._lib.nyxb_engine_last_kernel_ms(self._h)
 
-    def propagate_batch(self, state_soa, consts_soa, epoch0_ns, end_epoch_ns, step_ns=None, traj_capacity: int = 0):
+    def propagate_batch(self, state_soa, consts_soa, epoch0_ns, end_epoch_ns, step_ns=None, traj_capacity: int = 0,
+                        event=None):
         """Host-buffer call of `nyxb_propagate_batch[_traj]`. Returns (state, epoch, details, status) and, when
         `traj_capacity` > 0, a fifth element (epochs[cap][n], states[6][cap][n], count[n]): the start state and the
-        state after every accepted step (instance.rs:297-326)."""
+        state after every accepted step (instance.rs:297-326).  `event=(kind, value, trigger)` adds the stop condition of
+        `until_nth_event` (`nyxb_propagate_batch_event`, event.rs:88-211) and appends crossings[n] to the result."""
         state_soa = np.ascontiguousarray(state_soa, dtype=np.float64)
         consts_soa = np.ascontiguousarray(consts_soa, dtype=np.float64)
         epoch0_ns = np.ascontiguousarray(epoch0_ns, dtype=np.int64)
@@ -212,15 +215,23 @@ class Engine:
             t_st = np.zeros((6, traj_capacity, n), dtype=np.float64)
             t_cnt = np.zeros(n, dtype=np.int64)
             sink = abi.TrajSink(int(traj_capacity), t_ep.ctypes.data, t_st.ctypes.data, t_cnt.ctypes.data)
-        rc = self._lib.nyxb_propagate_batch_traj(self._h, n, state_soa.ctypes.data, consts_soa.ctypes.data,
-                                                 epoch0_ns.ctypes.data, int(end_epoch_ns), step_ptr, out_state.ctypes.data,
-                                                 out_epoch.ctypes.data, details.ctypes.data, status.ctypes.data,
-                                                 C.byref(sink) if sink is not None else None)
+        ev = None
+        if event is not None:
+            crossings = np.zeros(n, dtype=np.int32)
+            ev = abi.EventC(int(event[0]), int(event[2]), float(event[1]), crossings.ctypes.data)
+        rc = self._lib.nyxb_propagate_batch_event(self._h, n, state_soa.ctypes.data, consts_soa.ctypes.data,
+                                                  epoch0_ns.ctypes.data, int(end_epoch_ns), step_ptr, out_state.ctypes.data,
+                                                  out_epoch.ctypes.data, details.ctypes.data, status.ctypes.data,
+                                                  C.byref(sink) if sink is not None else None,
+                                                  C.byref(ev) if ev is not None else None)
         if rc != 0:
             raise PropagationError(f"nyxb_propagate_batch rc={rc}: {abi.last_error()}")
+        ret = (out_state, out_epoch, details, status)
         if traj_capacity:
-            return out_state, out_epoch, details, status, (t_ep, t_st, t_cnt)
-        return out_state, out_epoch, details, status
+            ret = ret + ((t_ep, t_st, t_cnt),)
+        if ev is not None:
+            ret = ret + (crossings,)
+        return ret
 
     def propagate_batch_dev(self, n, state_ptr, consts_ptr, epoch0_ptr, end_epoch_ns, step_ptr, out_state_ptr,
                             out_epoch_ptr, details_ptr, status_ptr, stream_ptr=None):
@@ -362,6 +373,41 @@ class PropInstance:
         k = int(t_cnt[0])
         tr = Traj(start, t_ep[:k, 0].copy(), np.ascontiguousarray(t_st[:, :k, 0].T)).finalize()
         return self.state, tr, int(d["n_steps"]) + 1 > cap
+
+    def until_nth_event(self, max_duration_ns: int, event, trigger: int = 1, capacity: Optional[int] = None):
+        """event.rs:88-211: propagate until `event` crossed zero `trigger` times (or raise NthEventError after
+        `max_duration_ns`); returns (state interpolated at the event epoch, Traj up to the end of the bracketing step).
+        The stop condition runs on the device, the Brent search on the recorded trajectory here (event.rs:186-196)."""
+        from .event import locate_event
+        from .trajectory import Traj
+
+        start = self.state
+        end_ns = start.epoch() + int(max_duration_ns)
+        cap = capacity or max(64, 4 * abs(int(max_duration_ns)) // max(abs(int(self._step_ns[0])), 1) + 64)
+        while True:
+            step_before = self._step_ns.copy()
+            st, cs, ep = pack_spacecraft([start])
+            eng = self.prop.engine(start.orbit.frame, self.almanac)
+            out, out_ep, det, status, (t_ep, t_st, t_cnt), crossings = eng.propagate_batch(
+                st, cs, ep, end_ns, self._step_ns, traj_capacity=cap, event=(event.kind, event.value, trigger))
+            if int(det[0]["n_steps"]) + 1 <= cap or capacity:
+                break
+            self._step_ns = step_before
+            cap *= 4
+        d = det[0]
+        if d["n_steps"] > 0:
+            self.details = IntegrationDetails(int(d["step_ns"]), float(d["error"]), int(d["attempts"]), int(d["n_steps"]),
+                                              int(d["n_rejected"]), int(d["n_rhs"]))
+        self.state = start.with_vector(int(out_ep[0]), out[:, 0])
+        code = int(status[0]) & 0xFF
+        if code == abi.ERR_EVENT_NOT_FOUND:
+            raise PropagationError(f"NthEventError: nth={trigger}, found={int(crossings[0])}")
+        err = status_error(status[0])
+        if err is not None:
+            raise err
+        k = int(t_cnt[0])
+        tr = Traj(start, t_ep[:k, 0].copy(), np.ascontiguousarray(t_st[:, :k, 0].T)).finalize()
+        return locate_event(tr, event), tr
 
     def until_epoch(self, end_ns: int) -> Spacecraft:
         """instance.rs:279-282"""

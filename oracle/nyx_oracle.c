@@ -642,7 +642,26 @@ typedef struct {
     /* trajectory recording: the channel of for_duration_with_traj (instance.rs:297-326) */
     const nyxb_traj_sink* sink;
     size_t idx, n;
+    /* stop condition of until_nth_event (event.rs:88-211) */
+    const nyxb_event* ev;
+    double ev_prev;
+    int ev_count;
 } inst_t;
+
+/* Event scalar minus the desired value for the closed set of include/nyxb.h (anise's Event::eval with
+ * Condition::Equals(value) is `scalar - value`; anise is not in the tree). */
+static double event_eval(const nyxb_event* ev, const double* y) {
+    double s;
+    switch (ev->kind) {
+    case NYXB_EVENT_RMAG: s = sqrt((y[0] * y[0] + y[1] * y[1]) + y[2] * y[2]); break;
+    case NYXB_EVENT_RDOTV: s = (y[0] * y[3] + y[1] * y[4]) + y[2] * y[5]; break;
+    case NYXB_EVENT_X: s = y[0]; break;
+    case NYXB_EVENT_Y: s = y[1]; break;
+    case NYXB_EVENT_Z: s = y[2]; break;
+    default: s = sqrt((y[3] * y[3] + y[4] * y[4]) + y[5] * y[5]); break;
+    }
+    return s - ev->value;
+}
 
 static void record_state(const inst_t* in, int64_t s) {
     if (!in->sink || s >= in->sink->capacity) return;
@@ -742,7 +761,7 @@ static int single_step(inst_t* in, eom_ctx* cx, const nyxb_integ_opts* o, const 
     return finally_check(in);
 }
 
-/* instance.rs:87-262 propagate() with no channel / no stop condition */
+/* instance.rs:87-262 propagate(); the channel is record_state() inside single_step, the stop condition is in->ev */
 static int propagate(inst_t* in, eom_ctx* cx, const nyxb_integ_opts* o, const tableau_t* tb, int64_t duration_ns) {
     if (duration_ns == 0) return 0;                              /* :96-98 */
     int64_t stop = in->epoch_ns + duration_ns;
@@ -764,6 +783,12 @@ static int propagate(inst_t* in, eom_ctx* cx, const nyxb_integ_opts* o, const ta
         }
         rc = single_step(in, cx, o, tb);                         /* :241 */
         if (rc) return rc;
+        if (in->ev) {                                            /* :243-252 stop condition == event.rs:120-150 closure */
+            double y_next = event_eval(in->ev, in->y);
+            if (in->ev_prev * y_next < 0.0) in->ev_count += 1;   /* event.rs:141-144 (non-angle scalars) */
+            in->ev_prev = y_next;
+            if (in->ev_count >= in->ev->trigger) return 0;
+        }
     }
 }
 
@@ -771,12 +796,14 @@ static int propagate(inst_t* in, eom_ctx* cx, const nyxb_integ_opts* o, const ta
 /* Batch driver == MonteCarlo::resume_run_until_epoch's par_iter              */
 /* (mc/montecarlo.rs:233-253): independent runs, OpenMP dynamic schedule.     */
 /* ------------------------------------------------------------------------- */
-int nyx_oracle_propagate_batch_traj(const nyxb_dynamics* dyn, const nyxb_integ_opts* opts, size_t n,
-                                    const double* state_soa, const double* consts_soa,
-                                    const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
-                                    double* out_state_soa, int64_t* out_epoch_ns,
-                                    nyxb_details* out_details, int32_t* out_status, const nyxb_traj_sink* sink, int n_threads) {
+int nyx_oracle_propagate_batch_event(const nyxb_dynamics* dyn, const nyxb_integ_opts* opts, size_t n,
+                                     const double* state_soa, const double* consts_soa,
+                                     const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
+                                     double* out_state_soa, int64_t* out_epoch_ns,
+                                     nyxb_details* out_details, int32_t* out_status, const nyxb_traj_sink* sink,
+                                     const nyxb_event* event, int n_threads) {
     tableau_t tb;
+    if (event && event->kind == NYXB_EVENT_NONE) event = NULL;
     if (tableau_for(opts->method, &tb)) return -1;
     if (dyn->n_bodies > NYXB_MAX_BODIES) return -1;
     nyx_oracle_grav* grav = dyn->gravity ? nyx_oracle_grav_new(dyn->gravity) : NULL;
@@ -801,11 +828,17 @@ int nyx_oracle_propagate_batch_traj(const nyxb_dynamics* dyn, const nyxb_integ_o
             in.det.step_ns = opts->init_step_ns; in.det.error = 0.0; in.det.attempts = 1;
             in.sink = (sink && sink->capacity > 0) ? sink : NULL; in.idx = i; in.n = n;
             record_state(&in, 0);                                /* start state: instance.rs:307, 321 */
+            in.ev = event; in.ev_count = 0;
+            if (event) in.ev_prev = event_eval(event, in.y);     /* event.rs:111-113 */
             eom_ctx cx;
             cx.dyn = dyn; cx.grav = grav; cx.grav_scratch = scratch; cx.n_rhs = 0;
             cx.dry_mass = consts_soa[0 * n + i]; cx.extra_mass = consts_soa[1 * n + i];
             cx.srp_area = consts_soa[2 * n + i]; cx.drag_area = consts_soa[3 * n + i];
             int rc = propagate(&in, &cx, opts, &tb, end_epoch_ns - in.epoch_ns); /* instance.rs:279-282 */
+            if (event) {
+                event->crossings[i] = in.ev_count;
+                if (rc == 0 && in.ev_count < event->trigger) rc = NYXB_ERR_EVENT_NOT_FOUND; /* event.rs:177-182 */
+            }
             in.status = (in.status & NYXB_WARN_MAX_ATTEMPTS) | rc;
             in.det.n_rhs = cx.n_rhs;
             for (int e = 0; e < 9; ++e) out_state_soa[(size_t)e * n + i] = in.y[e];
@@ -819,6 +852,15 @@ int nyx_oracle_propagate_batch_traj(const nyxb_dynamics* dyn, const nyxb_integ_o
     }
     nyx_oracle_grav_free(grav);
     return 0;
+}
+
+int nyx_oracle_propagate_batch_traj(const nyxb_dynamics* dyn, const nyxb_integ_opts* opts, size_t n,
+                                    const double* state_soa, const double* consts_soa,
+                                    const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
+                                    double* out_state_soa, int64_t* out_epoch_ns,
+                                    nyxb_details* out_details, int32_t* out_status, const nyxb_traj_sink* sink, int n_threads) {
+    return nyx_oracle_propagate_batch_event(dyn, opts, n, state_soa, consts_soa, epoch0_ns, end_epoch_ns, step_ns, out_state_soa,
+                                            out_epoch_ns, out_details, out_status, sink, NULL, n_threads);
 }
 
 int nyx_oracle_propagate_batch(const nyxb_dynamics* dyn, const nyxb_integ_opts* opts, size_t n,

@@ -27,6 +27,12 @@ int nyx_oracle_propagate_batch(const nyxb_dynamics* dyn, const nyxb_integ_opts* 
                                const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
                                double* out_state_soa, int64_t* out_epoch_ns,
                                nyxb_details* out_details, int32_t* out_status, int n_threads);
+int nyx_oracle_propagate_batch_event(const nyxb_dynamics* dyn, const nyxb_integ_opts* opts, size_t n,
+                                     const double* state_soa, const double* consts_soa,
+                                     const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
+                                     double* out_state_soa, int64_t* out_epoch_ns,
+                                     nyxb_details* out_details, int32_t* out_status, const nyxb_traj_sink* sink,
+                                     const nyxb_event* event, int n_threads);
 int nyx_oracle_propagate_batch_traj(const nyxb_dynamics* dyn, const nyxb_integ_opts* opts, size_t n,
                                     const double* state_soa, const double* consts_soa,
                                     const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,

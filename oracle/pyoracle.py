@@ -37,6 +37,10 @@ def lib():
         L.nyx_oracle_propagate_batch_traj.argtypes = [
             C.POINTER(abi.DynamicsC), C.POINTER(abi.IntegOpts), C.c_size_t, vp, vp, vp, C.c_int64, vp, vp, vp, vp, vp,
             C.POINTER(abi.TrajSink), C.c_int]
+        L.nyx_oracle_propagate_batch_event.restype = C.c_int
+        L.nyx_oracle_propagate_batch_event.argtypes = [
+            C.POINTER(abi.DynamicsC), C.POINTER(abi.IntegOpts), C.c_size_t, vp, vp, vp, C.c_int64, vp, vp, vp, vp, vp,
+            C.POINTER(abi.TrajSink), C.POINTER(abi.EventC), C.c_int]
         L.nyx_oracle_dur_to_seconds.restype = C.c_double
         L.nyx_oracle_dur_to_seconds.argtypes = [C.c_int64]
         L.nyx_oracle_dur_from_seconds.restype = C.c_int64
@@ -60,9 +64,11 @@ def lib():
     return _LIB
 
 
-def propagate_batch(dyn_c, opts_c, state_soa, consts_soa, epoch0_ns, end_epoch_ns, step_ns=None, n_threads=0, traj_capacity=0):
+def propagate_batch(dyn_c, opts_c, state_soa, consts_soa, epoch0_ns, end_epoch_ns, step_ns=None, n_threads=0, traj_capacity=0,
+                    event=None):
     """Same contract as nyxb_propagate_batch[_traj] (include/nyxb.h) but on the CPU oracle.
-    With traj_capacity > 0 returns a fifth element (epochs[cap][n], states[6][cap][n], count[n])."""
+    With traj_capacity > 0 returns a fifth element (epochs[cap][n], states[6][cap][n], count[n]); with
+    event=(kind, value, trigger) the stop condition of until_nth_event applies and crossings[n] is appended."""
     L = lib()
     state_soa = np.ascontiguousarray(state_soa, dtype=np.float64)
     consts_soa = np.ascontiguousarray(consts_soa, dtype=np.float64)
@@ -83,15 +89,22 @@ def propagate_batch(dyn_c, opts_c, state_soa, consts_soa, epoch0_ns, end_epoch_n
         t_st = np.zeros((6, traj_capacity, n), dtype=np.float64)
         t_cnt = np.zeros(n, dtype=np.int64)
         sink = abi.TrajSink(int(traj_capacity), t_ep.ctypes.data, t_st.ctypes.data, t_cnt.ctypes.data)
-    rc = L.nyx_oracle_propagate_batch_traj(
+    ev = None
+    if event is not None:
+        crossings = np.zeros(n, dtype=np.int32)
+        ev = abi.EventC(int(event[0]), int(event[2]), float(event[1]), crossings.ctypes.data)
+    rc = L.nyx_oracle_propagate_batch_event(
         C.byref(dyn_c), C.byref(opts_c), n, state_soa.ctypes.data, consts_soa.ctypes.data, epoch0_ns.ctypes.data,
         int(end_epoch_ns), step_ptr, out_state.ctypes.data, out_epoch.ctypes.data, details.ctypes.data,
-        status.ctypes.data, C.byref(sink) if sink is not None else None, int(n_threads))
+        status.ctypes.data, C.byref(sink) if sink is not None else None, C.byref(ev) if ev is not None else None, int(n_threads))
     if rc != 0:
         raise RuntimeError(f"oracle rejected the configuration (rc={rc})")
+    ret = (out_state, out_epoch, details, status)
     if traj_capacity:
-        return out_state, out_epoch, details, status, (t_ep, t_st, t_cnt)
-    return out_state, out_epoch, details, status
+        ret = ret + ((t_ep, t_st, t_cnt),)
+    if ev is not None:
+        ret = ret + (crossings,)
+    return ret
 
 
 def num_threads() -> int:
