@@ -303,6 +303,13 @@ double nyxb_engine_last_kernel_ms(const nyxb_engine* eng); /* CUDA-event time of
  * on `device`; the FP64 roof that bench.py reports against. */
 double nyxb_measure_fp64_tflops(int32_t device, int32_t iters);
 
+/* Host-only inspection of the cooperative kernel's coefficient table (no device needed): the column -> lane
+ * schedule and the packed records for `lanes` in {8,16,32}.  Two-call pattern: with recs == NULL only the sizes are
+ * returned.  Layouts: recs [(L+2)/2 pairs][5 pieces][lanes][2], col_start / col_m [lanes][kmax], colseed [N+2][4]
+ * (see nyx_b200/csrc/nyxb_coop.h).  Used by the CPU tests to check the table algebra against a direct evaluation. */
+int32_t nyxb_coop_table_dump(const nyxb_gravity_field* field, int32_t lanes, int32_t* out_L, int32_t* out_kmax,
+                             double* recs, int32_t* col_start, int32_t* col_m, double* colseed);
+
 int32_t nyxb_abi_version(void);
 const char* nyxb_last_error(void);
 

@@ -215,6 +215,8 @@ def _declare(lib):
     lib.nyxb_engine_last_kernel_ms.argtypes = [vp]
     lib.nyxb_measure_fp64_tflops.restype = C.c_double
     lib.nyxb_measure_fp64_tflops.argtypes = [C.c_int32, C.c_int32]
+    lib.nyxb_coop_table_dump.restype = C.c_int32
+    lib.nyxb_coop_table_dump.argtypes = [C.POINTER(GravityFieldC), C.c_int32, c_int32_p, c_int32_p, vp, vp, vp, vp]
     lib.nyxb_abi_version.restype = C.c_int32
     lib.nyxb_abi_version.argtypes = []
     lib.nyxb_last_error.restype = C.c_char_p
@@ -235,6 +237,7 @@ EXPORTED_SYMBOLS = [
     "nyxb_engine_launch_count",
     "nyxb_engine_last_kernel_ms",
     "nyxb_measure_fp64_tflops",
+    "nyxb_coop_table_dump",
     "nyxb_abi_version",
     "nyxb_last_error",
 ]

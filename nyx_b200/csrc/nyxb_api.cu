@@ -472,5 +472,21 @@ extern "C" int32_t nyxb_engine_get_lanes(const nyxb_engine* eng) { return eng ? 
 extern "C" int64_t nyxb_engine_launch_count(const nyxb_engine* eng) { return eng ? eng->launches : 0; }
 extern "C" double nyxb_engine_last_kernel_ms(const nyxb_engine* eng) { return eng ? eng->last_ms : 0.0; }
 extern "C" double nyxb_measure_fp64_tflops(int32_t device, int32_t iters) { return nyxb_fp64_probe(device, iters); }
+extern "C" int32_t nyxb_coop_table_dump(const nyxb_gravity_field* f, int32_t lanes, int32_t* out_L, int32_t* out_kmax,
+                                        double* recs, int32_t* col_start, int32_t* col_m, double* colseed) {
+    if (!f || !f->c_nm || !f->s_nm || f->degree < 2 || (lanes != 8 && lanes != 16 && lanes != 32) || !out_L || !out_kmax) {
+        set_err("bad argument");
+        return NYXB_RC_BAD_ARG;
+    }
+    CoopHost h;
+    nyxb_coop_build_host(f->degree, f->order, f->c_nm, f->s_nm, lanes, h);
+    *out_L = h.L; *out_kmax = h.kmax;
+    if (recs) std::copy(h.recs.begin(), h.recs.end(), recs);
+    if (col_start) std::copy(h.col_start.begin(), h.col_start.end(), col_start);
+    if (col_m) std::copy(h.col_m.begin(), h.col_m.end(), col_m);
+    if (colseed) std::copy(h.colseed.begin(), h.colseed.end(), colseed);
+    return NYXB_RC_OK;
+}
+
 extern "C" int32_t nyxb_abi_version(void) { return NYXB_ABI_VERSION; }
 extern "C" const char* nyxb_last_error(void) { return g_err.c_str(); }

@@ -43,6 +43,10 @@ void nyxb_coop_build_host(int N, int M, const double* c_nm, const double* s_nm, 
         return m == 0 ? v / sqrt2 : v;
     };
     const int mcols = std::min(M + 1, N + 1);  // columns m = 1..mcols
+    // entries of column m: n = m..N (the W term of degree n+1 is carried by entry n, so n = N+1 needs no entry of its own);
+    // column N+1 keeps one null entry (only its seed W term is non-zero).  Lengths are padded to EVEN: the kernel walks
+    // two entries per iteration and tests for a column switch once per pair.
+    auto col_len = [&](int m) { int l = std::max(N + 1 - m, 1); return l + (l & 1); };
     // column -> lane schedule.  Default: longest-processing-time greedy (every lane walks the same number of entries,
     // column boundaries differ per lane).  NYXB_COOP_SCHED=rounds: G columns per round, all lanes start their k-th column
     // at the same entry (uniform boundaries, shorter columns padded with null records).
@@ -56,7 +60,7 @@ void nyxb_coop_build_host(int N, int M, const double* c_nm, const double* s_nm, 
     if (rounds) {
         int base = 0;
         for (size_t i = 0; i < order.size(); i += G) {
-            int len = N + 2 - order[i];  // longest of the round
+            int len = col_len(order[i]);  // longest of the round
             for (int j = 0; j < G && i + j < order.size(); ++j) { cols[j].push_back(order[i + j]); starts[j].push_back(base); }
             base += len;
         }
@@ -66,14 +70,14 @@ void nyxb_coop_build_host(int N, int M, const double* c_nm, const double* s_nm, 
             int best = (int)(std::min_element(load.begin(), load.end()) - load.begin());
             cols[best].push_back(m);
             starts[best].push_back(load[best]);
-            load[best] += N + 2 - m;
+            load[best] += col_len(m);
         }
     }
     out.G = G;
     out.L = *std::max_element(load.begin(), load.end());
     out.kmax = 1;
     for (auto& cl : cols) out.kmax = std::max(out.kmax, (int)cl.size());
-    out.recs.assign((size_t)(out.L + 1) * G * 5, 0.0);  // +1: prefetch pad
+    out.recs.assign((size_t)(out.L + 2) * G * 5, 0.0);  // +2: one null pair behind the last one
     out.col_start.assign((size_t)G * out.kmax, out.L + 1);
     out.col_m.assign((size_t)G * out.kmax, 1);
     out.colseed.assign((size_t)(N + 2) * 4, 0.0);
@@ -107,21 +111,25 @@ void nyxb_coop_build_host(int N, int M, const double* c_nm, const double* s_nm, 
             int e = starts[lane][k];
             out.col_start[(size_t)lane * out.kmax + k] = e;
             out.col_m[(size_t)lane * out.kmax + k] = m;
-            for (int n = m; n <= N + 1; ++n, ++e) {
+            auto kappa = [&](int n) -> double {  // W term of degree n = kappa * (Z term of degree n-1), n > m
+                return (double)(((long double)vr11(n - 1, m - 1) * scale(n, m)) / ((long double)vr01(n - 1, m - 1) * scale(n - 1, m)));
+            };
+            for (int n = m; n <= std::max(N, m); ++n, ++e) {
                 const long double sc = scale(n, m);
-                double p1 = 0, p2 = 0, p3 = 0, p4 = 0, kappa = 1.0;
+                double p1 = 0, p2 = 0, p3 = 0, p4 = 0, kn = 0.0;
                 if (n <= N) {
                     p1 = (double)(sc * sqrt2 * (double)m * C(n, m));
                     p2 = (double)(sc * sqrt2 * (double)m * Sx(n, m));
                     p3 = (double)(sc * sqrt2 * vr01(n, m - 1) * C(n, m - 1));
                     p4 = (double)(sc * sqrt2 * vr01(n, m - 1) * Sx(n, m - 1));
+                    kn = kappa(n + 1);  // applied to Q[n+1] p3/p4 of THIS entry
                 }
-                if (n > m) kappa = (double)(((long double)vr11(n - 1, m - 1) * sc) / ((long double)vr01(n - 1, m - 1) * scale(n - 1, m)));
-                // device layout: [entry][piece][lane]: pieces 0,1 are 16 B per lane, piece 2 is 8 B per lane
-                double* base = out.recs.data() + (size_t)e * G * 5;
-                base[lane * 2] = p1; base[lane * 2 + 1] = p2;
-                base[2 * G + lane * 2] = p3; base[2 * G + lane * 2 + 1] = p4;
-                base[4 * G + lane] = kappa;
+                // device layout: [pair][piece][lane], 16-byte pieces: (p1,p2)a (p3,p4)a (p1,p2)b (p3,p4)b (kappa a, kappa b)
+                double* base = out.recs.data() + (size_t)(e / 2) * G * 10;
+                const int h = e & 1;
+                base[(2 * h) * 2 * G + lane * 2] = p1; base[(2 * h) * 2 * G + lane * 2 + 1] = p2;
+                base[(2 * h + 1) * 2 * G + lane * 2] = p3; base[(2 * h + 1) * 2 * G + lane * 2 + 1] = p4;
+                base[8 * G + lane * 2 + h] = kn;
             }
         }
     }

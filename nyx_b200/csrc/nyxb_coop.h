@@ -5,11 +5,15 @@
 
 #include "nyxb_device.cuh"
 
-// Compact per-entry record of the FAST cooperative kernel, 40 bytes per lane and entry (n, m), m >= 1, m <= n <= N+1,
-// laid out [entry e][piece][lane] in the order each lane walks its columns:
-//   piece 0 (16 B): p1, p2 = sqrt2 * m * (Cbar, Sbar)[n][m] * scale[n][m]                    -> X, Y sums
-//   piece 1 (16 B): p3, p4 = sqrt2 * vr01[n][m-1] * (Cbar, Sbar)[n][m-1] * scale[n][m]       -> Z sum
-//   piece 2 ( 8 B): kappa  = vr11[n-1][m-1] scale[n][m] / (vr01[n-1][m-1] scale[n-1][m])     -> W term = kappa * (Z term of the entry above)
+// Compact records of the FAST cooperative kernel, 40 bytes per lane and entry (n, m), 1 <= m <= N+1, m <= n <= N,
+// stored as PAIRS of consecutive entries (a, b) of a column, [pair][piece][lane] in the order each lane walks its columns
+// (columns are padded to an even number of entries with null records):
+//   pieces 0 / 2 (16 B): p1, p2 = sqrt2 * m * (Cbar, Sbar)[n][m] * scale[n][m]                 -> X, Y sums
+//   pieces 1 / 3 (16 B): p3, p4 = sqrt2 * vr01[n][m-1] * (Cbar, Sbar)[n][m-1] * scale[n][m]    -> Z sum
+//   piece  4     (16 B): kappa(a), kappa(b); kappa(n) = vr11[n][m-1] scale[n+1][m] / (vr01[n][m-1] scale[n][m])
+//                        -> W sum: the term of degree n+1 is kappa(n) * Q[n+1] * (p3, p4)(n)
+// The four sums are accumulated per column WITHOUT the column's (cos, sin)((m-1) lambda) factor and folded into the
+// totals at the column switch (8 FMAs per column instead of 6 per entry).
 // scale[n][m] = A_ref[n][m] / Q[n][m] converts the integer-coefficient recursion
 //   Q[n] = (2n-1) u Q[n-1] - (n+m-1)(n-m-1) Q[n-2],  Q[m] = (2m-1)!!
 // (whose coefficients are generated in registers, no loads) to the reference's normalised A[n][m].
@@ -17,7 +21,7 @@
 
 struct DevCoop {
     int G, L, kmax;
-    const double* recs;      // (L+1) * G * 5 doubles
+    const double* recs;      // (L+2) * G * 5 doubles (L even)
     const int* col_start;    // [G][kmax] entry index at which the k-th column of the lane starts (L+1: none)
     const int* col_m;        // [G][kmax] order m of that column
     const double* colseed;   // [N+2][4]: (2m-1)!!, pd1, pd2 (W term of the column's first entry), 2m+1

@@ -37,8 +37,8 @@ __host__ __device__ inline int coop_traj_stride(int N) {
     int s = COOP_SM_FIXED + 3 * (N + 3);
     return s + ((8 - (s & 15)) & 15);
 }
-// bytes of the CTA-shared table region: records [(L+1)][5 doubles][G], then colseed[N+2][4], col_start/col_m [G][kmax+2]
-__host__ __device__ inline size_t coop_rec_bytes(int L, int G) { return (size_t)(L + 1) * G * NYXB_COOP_REC_BYTES; }
+// bytes of the CTA-shared table region: records [(L+2)/2 pairs][5 x 16 B][G], then colseed[N+2][4], col_start/col_m [G][kmax+2]
+__host__ __device__ inline size_t coop_rec_bytes(int L, int G) { return (size_t)(L + 2) * G * NYXB_COOP_REC_BYTES; }
 __host__ __device__ inline size_t coop_meta_bytes(int N, int G, int kmax) {
     size_t b = (size_t)(N + 2) * 32 + (size_t)2 * G * (kmax + 2) * 4;
     return (b + 15) & ~(size_t)15;
@@ -188,16 +188,19 @@ __device__ __forceinline__ void coop_rhs(const DevSetup& S, const double* __rest
     }
     __syncwarp(gmask);
 
-    // ---- column walk.  Per entry: one 40-byte record (2 x LDS.128 + LDS.64), 17 FP64 instructions per trajectory;
-    // the recursion coefficients (2n+1) and (n+m)(n-m) are generated in registers.  The seed of the NEXT column
-    // (Q, cos, sin, W seed) is prefetched one column ahead.  Loop invariants are pinned with empty asm: ptxas
-    // otherwise rematerialises them inside the loop.
+    // ---- column walk, two entries per iteration.  Per pair: one 80-byte record (5 x LDS.128) and 26 FP64 instructions per
+    // trajectory; the recursion coefficients (2n+1) and (n+m)(n-m) are generated in registers.  The per-column sums
+    // S1..S6 carry no (cos, sin)((m-1) lambda) factor: it is applied once, when the lane switches to its next column
+    // (columns have an even number of entries, so the switch is tested once per pair).  The seed of the NEXT column
+    // (Q, cos, sin, W seed) is prefetched one column ahead.  Loop invariants are pinned with empty asm: ptxas otherwise
+    // rematerialises them inside the loop.
     unsigned a_rm = smem_u32(g[0].rm), a_seed = smem_u32(colseed);
     asm volatile("" : "+r"(a_rm), "+r"(a_cs), "+r"(a_seed));
 #pragma unroll
     for (int t = 0; t < T; ++t) asm volatile("" : "+d"(r2[t]), "+d"(ub[t]));
     const unsigned pw8 = (unsigned)(gv.N + 3) * 8u;  // rm -> im -> rp stride in bytes
-    double X[T], Y[T], Z[T], W[T], Q1[T], Q2[T], rr[T], ii[T], t3p[T], Qn0[T], rrn[T], iin[T];
+    double X[T], Y[T], Z[T], W[T], Q1[T], Q2[T], rr[T], ii[T], Qn0[T], rrn[T], iin[T];
+    double S1[T], S2[T], S3[T], S4[T], S5[T], S6[T];
     double al = 0.0, be = 0.0, aln, pd1n, pd2n;
     int ci = 0;
     int next_start = lds_s32(a_cs), start_after = lds_s32(a_cs + 4);
@@ -207,19 +210,14 @@ __device__ __forceinline__ void coop_rhs(const DevSetup& S, const double* __rest
 #pragma unroll
         for (int t = 0; t < T; ++t) {
             const unsigned base = a_rm + t * traj_stride_bytes + mn * 8;
-            X[t] = Y[t] = Z[t] = W[t] = Q1[t] = Q2[t] = rr[t] = ii[t] = t3p[t] = 0.0;
+            X[t] = Y[t] = Z[t] = W[t] = Q1[t] = Q2[t] = rr[t] = ii[t] = 0.0;
+            S1[t] = S2[t] = S3[t] = S4[t] = S5[t] = S6[t] = 0.0;
             Qn0[t] = lds_f64(base + 2 * pw8); rrn[t] = lds_f64(base - 8); iin[t] = lds_f64(base + pw8 - 8);
         }
     }
-    const double2* rec = reinterpret_cast<const double2*>(recs) + lane;  // pieces 0/1: 16 B per lane
-    const double* rek = recs + 4 * G + lane;                              // piece 2: 8 B per lane
-    double2 n0 = rec[0], n1 = rec[G];
-    double nk = rek[0];
-    for (int e = 0; e < L; ++e) {
-        const double2 q0 = n0, q1 = n1;
-        const double kq = nk;
-        rec += (G * 5) / 2; rek += G * 5;
-        n0 = rec[0]; n1 = rec[G]; nk = rek[0];  // software prefetch (table padded by one entry)
+    const double2* rec = reinterpret_cast<const double2*>(recs) + lane;  // five 16-byte pieces per pair and lane
+#pragma unroll 1
+    for (int e = 0; e < L; e += 2) {
         if (e == next_start) {
             ++ci;
             next_start = start_after;                           // sentinel L+1 after the last column
@@ -228,30 +226,54 @@ __device__ __forceinline__ void coop_rhs(const DevSetup& S, const double* __rest
             al = aln; be = 0.0;
 #pragma unroll
             for (int t = 0; t < T; ++t) {
+                // close the previous column: apply its (cos, sin)((m-1) lambda)
+                X[t] = fma(rr[t], S1[t], fma(ii[t], S2[t], X[t]));
+                Y[t] = fma(rr[t], S2[t], fma(-ii[t], S1[t], Y[t]));
+                Z[t] = fma(rr[t], S3[t], fma(ii[t], S4[t], Z[t]));
+                W[t] = fma(rr[t], S5[t], fma(ii[t], S6[t], W[t]));
                 Q1[t] = Qn0[t]; rr[t] = rrn[t]; ii[t] = iin[t]; Q2[t] = 0.0;
-                t3p[t] = fma(pd2n, ii[t], pd1n * rr[t]);        // W term of the column's first entry (kappa = 1 there)
+                S1[t] = S2[t] = S3[t] = S4[t] = 0.0;
+                S5[t] = Q1[t] * pd1n; S6[t] = Q1[t] * pd2n;     // W term of the column's first degree (seed record, kappa = 1)
                 const unsigned base = a_rm + t * traj_stride_bytes + mn * 8;
                 Qn0[t] = lds_f64(base + 2 * pw8); rrn[t] = lds_f64(base - 8); iin[t] = lds_f64(base + pw8 - 8);
             }
             pd1n = lds_f64(a_seed + mn * 32 + 8); pd2n = lds_f64(a_seed + mn * 32 + 16); aln = lds_f64(a_seed + mn * 32 + 24);
         }
+        const double2 a0 = rec[0], a1 = rec[G], b0 = rec[2 * G], b1 = rec[3 * G], kk = rec[4 * G];
+        rec += 5 * G;
+        const double be1 = be + al, al1 = al + 2.0;  // (n+1)^2 - m^2 = n^2 - m^2 + (2n+1)
 #pragma unroll
         for (int t = 0; t < T; ++t) {
-            const double t1 = fma(q0.y, ii[t], q0.x * rr[t]);
-            const double t2 = fma(q0.y, rr[t], -(q0.x * ii[t]));
-            const double t3 = fma(q1.y, ii[t], q1.x * rr[t]);
-            const double t4 = kq * t3p[t];
-            X[t] = fma(Q1[t], t1, X[t]);
-            Y[t] = fma(Q1[t], t2, Y[t]);
-            Z[t] = fma(Q1[t], t3, Z[t]);
-            W[t] = fma(Q1[t], t4, W[t]);
-            const double Qn = fma(al * ub[t], Q1[t], -((be * r2[t]) * Q2[t]));  // Q[n+1] = (2n+1) u Q[n] - (n+m)(n-m) Q[n-1]
-            Q2[t] = Q1[t];
-            Q1[t] = Qn;
-            t3p[t] = t3;
+            // entry a (degree n): Q1 = Q[n], Q2 = Q[n-1]
+            S1[t] = fma(Q1[t], a0.x, S1[t]);
+            S2[t] = fma(Q1[t], a0.y, S2[t]);
+            S3[t] = fma(Q1[t], a1.x, S3[t]);
+            S4[t] = fma(Q1[t], a1.y, S4[t]);
+            const double Qa = fma(al * ub[t], Q1[t], -((be * r2[t]) * Q2[t]));  // Q[n+1] = (2n+1) u Q[n] - (n+m)(n-m) Q[n-1]
+            const double wa = kk.x * Qa;
+            S5[t] = fma(wa, a1.x, S5[t]);
+            S6[t] = fma(wa, a1.y, S6[t]);
+            // entry b (degree n+1)
+            S1[t] = fma(Qa, b0.x, S1[t]);
+            S2[t] = fma(Qa, b0.y, S2[t]);
+            S3[t] = fma(Qa, b1.x, S3[t]);
+            S4[t] = fma(Qa, b1.y, S4[t]);
+            const double Qb = fma(al1 * ub[t], Qa, -((be1 * r2[t]) * Q1[t]));
+            const double wb = kk.y * Qb;
+            S5[t] = fma(wb, b1.x, S5[t]);
+            S6[t] = fma(wb, b1.y, S6[t]);
+            Q2[t] = Qa;
+            Q1[t] = Qb;
         }
-        be += al;   // (n+1)^2 - m^2 = n^2 - m^2 + (2n+1)
-        al += 2.0;
+        be = be1 + al1;
+        al = al1 + 2.0;
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {  // close the last column
+        X[t] = fma(rr[t], S1[t], fma(ii[t], S2[t], X[t]));
+        Y[t] = fma(rr[t], S2[t], fma(-ii[t], S1[t], Y[t]));
+        Z[t] = fma(rr[t], S3[t], fma(ii[t], S4[t], Z[t]));
+        W[t] = fma(rr[t], S5[t], fma(ii[t], S6[t], W[t]));
     }
 #pragma unroll
     for (int t = 0; t < T; ++t) {
