@@ -47,8 +47,8 @@ void nyxb_coop_build_host(int N, int M, const double* c_nm, const double* s_nm, 
     // column N+1 keeps one null entry (only its seed W term is non-zero).  Lengths are padded to EVEN: the kernel walks
     // two entries per iteration and tests for a column switch once per pair.
     auto col_len = [&](int m) { int l = std::max(N + 1 - m, 1); return l + (l & 1); };
-    // column -> lane schedule.  Default: longest-processing-time greedy (every lane walks the same number of entries,
-    // column boundaries differ per lane).  NYXB_COOP_SCHED=rounds: G columns per round, all lanes start their k-th column
+    // column -> lane schedule.  Default: first-fit-decreasing bin packing (every lane walks at most L entries, column
+    // boundaries differ per lane).  NYXB_COOP_SCHED=rounds: G columns per round, all lanes start their k-th column
     // at the same entry (uniform boundaries, shorter columns padded with null records).
     std::vector<int> order(mcols);
     std::iota(order.begin(), order.end(), 1);  // already sorted by decreasing length (N + 2 - m)
@@ -66,11 +66,25 @@ void nyxb_coop_build_host(int N, int M, const double* c_nm, const double* s_nm, 
         }
         for (int j = 0; j < G; ++j) load[j] = base;
     } else {
-        for (int m : order) {
-            int best = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-            cols[best].push_back(m);
-            starts[best].push_back(load[best]);
-            load[best] += col_len(m);
+        // first-fit decreasing into G bins of capacity cap, smallest feasible even cap (LPT alone leaves 34 where 32 fits for 21x21)
+        int total = 0;
+        for (int m : order) total += col_len(m);
+        int cap = std::max((total + G - 1) / G, col_len(order[0]));
+        cap += cap & 1;
+        for (;; cap += 2) {
+            std::fill(load.begin(), load.end(), 0);
+            for (auto& cl : cols) cl.clear();
+            for (auto& st : starts) st.clear();
+            bool ok = true;
+            for (int m : order) {
+                int b = 0;
+                while (b < G && load[b] + col_len(m) > cap) ++b;
+                if (b == G) { ok = false; break; }
+                cols[b].push_back(m);
+                starts[b].push_back(load[b]);
+                load[b] += col_len(m);
+            }
+            if (ok) break;
         }
     }
     out.G = G;

@@ -116,8 +116,9 @@ template <int G, int T>
 __device__ __forceinline__ void coop_rhs(const DevSetup& S, const double* __restrict__ recs, int L,
                                          const double* __restrict__ colseed, unsigned a_cs, unsigned cm_off,
                                          TrajCtx (&g)[T], const RotBase (&rbase)[T], const double (&dt_s)[T],
-                                         const long long (&t_ns)[T], int lane, unsigned gmask, unsigned traj_stride_bytes,
+                                         const long long (&t_ns)[T], int lane, unsigned traj_stride_bytes,
                                          double (&dyc)[T], int (&rc)[T]) {
+    constexpr unsigned FULL = 0xffffffffu;  // the caller keeps the warp converged (see nyxb_k_coop)
     const DevGrav& gv = S.grav;
     const double ra_dot = gv.rot.ra_dot, dec_dot = gv.rot.dec_dot;  // rad/s, precomputed on the host
     double inv_r[T], rho[T], ub[T], r2[T];
@@ -186,88 +187,94 @@ __device__ __forceinline__ void coop_rhs(const DevSetup& S, const double* __rest
             pr *= bp;
         }
     }
-    __syncwarp(gmask);
+    __syncwarp(FULL);
 
     // ---- column walk, two entries per iteration.  Per pair: one 80-byte record (5 x LDS.128) and 26 FP64 instructions per
     // trajectory; the recursion coefficients (2n+1) and (n+m)(n-m) are generated in registers.  The per-column sums
     // S1..S6 carry no (cos, sin)((m-1) lambda) factor: it is applied once, when the lane switches to its next column
-    // (columns have an even number of entries, so the switch is tested once per pair).  The seed of the NEXT column
-    // (Q, cos, sin, W seed) is prefetched one column ahead.  Loop invariants are pinned with empty asm: ptxas otherwise
-    // rematerialises them inside the loop.
+    // (columns have an even number of entries, so the switch is tested once per pair).  Loop invariants are pinned with
+    // empty asm: ptxas otherwise rematerialises them inside the loop.
     unsigned a_rm = smem_u32(g[0].rm), a_seed = smem_u32(colseed);
     asm volatile("" : "+r"(a_rm), "+r"(a_cs), "+r"(a_seed));
 #pragma unroll
     for (int t = 0; t < T; ++t) asm volatile("" : "+d"(r2[t]), "+d"(ub[t]));
     const unsigned pw8 = (unsigned)(gv.N + 3) * 8u;  // rm -> im -> rp stride in bytes
-    double X[T], Y[T], Z[T], W[T], Q1[T], Q2[T], rr[T], ii[T], Qn0[T], rrn[T], iin[T];
+    double X[T], Y[T], Z[T], W[T], Q1[T], Q2[T], rr[T], ii[T];
     double S1[T], S2[T], S3[T], S4[T], S5[T], S6[T];
-    double al = 0.0, be = 0.0, aln, pd1n, pd2n;
+    double al = 0.0, be = 0.0;
     int ci = 0;
-    int next_start = lds_s32(a_cs), start_after = lds_s32(a_cs + 4);
-    {
-        const int mn = lds_s32(a_cs + cm_off);
-        pd1n = lds_f64(a_seed + mn * 32 + 8); pd2n = lds_f64(a_seed + mn * 32 + 16); aln = lds_f64(a_seed + mn * 32 + 24);
+    int next_start = lds_s32(a_cs);
+    unsigned a_col = a_rm + lds_s32(a_cs + cm_off) * 8;  // &rm[m] of the lane's next column (trajectory 0)
 #pragma unroll
-        for (int t = 0; t < T; ++t) {
-            const unsigned base = a_rm + t * traj_stride_bytes + mn * 8;
-            X[t] = Y[t] = Z[t] = W[t] = Q1[t] = Q2[t] = rr[t] = ii[t] = 0.0;
-            S1[t] = S2[t] = S3[t] = S4[t] = S5[t] = S6[t] = 0.0;
-            Qn0[t] = lds_f64(base + 2 * pw8); rrn[t] = lds_f64(base - 8); iin[t] = lds_f64(base + pw8 - 8);
-        }
+    for (int t = 0; t < T; ++t) {
+        X[t] = Y[t] = Z[t] = W[t] = Q1[t] = Q2[t] = rr[t] = ii[t] = 0.0;
+        S1[t] = S2[t] = S3[t] = S4[t] = S5[t] = S6[t] = 0.0;
     }
     const double2* rec = reinterpret_cast<const double2*>(recs) + lane;  // five 16-byte pieces per pair and lane
-#pragma unroll 1
-    for (int e = 0; e < L; e += 2) {
-        if (e == next_start) {
-            ++ci;
-            next_start = start_after;                           // sentinel L+1 after the last column
-            start_after = lds_s32(a_cs + ci * 4 + 4);           // (table has two sentinel slots)
-            const int mn = lds_s32(a_cs + cm_off + ci * 4);     // sentinel column 1
-            al = aln; be = 0.0;
-#pragma unroll
-            for (int t = 0; t < T; ++t) {
-                // close the previous column: apply its (cos, sin)((m-1) lambda)
-                X[t] = fma(rr[t], S1[t], fma(ii[t], S2[t], X[t]));
-                Y[t] = fma(rr[t], S2[t], fma(-ii[t], S1[t], Y[t]));
-                Z[t] = fma(rr[t], S3[t], fma(ii[t], S4[t], Z[t]));
-                W[t] = fma(rr[t], S5[t], fma(ii[t], S6[t], W[t]));
-                Q1[t] = Qn0[t]; rr[t] = rrn[t]; ii[t] = iin[t]; Q2[t] = 0.0;
-                S1[t] = S2[t] = S3[t] = S4[t] = 0.0;
-                S5[t] = Q1[t] * pd1n; S6[t] = Q1[t] * pd2n;     // W term of the column's first degree (seed record, kappa = 1)
-                const unsigned base = a_rm + t * traj_stride_bytes + mn * 8;
-                Qn0[t] = lds_f64(base + 2 * pw8); rrn[t] = lds_f64(base - 8); iin[t] = lds_f64(base + pw8 - 8);
-            }
-            pd1n = lds_f64(a_seed + mn * 32 + 8); pd2n = lds_f64(a_seed + mn * 32 + 16); aln = lds_f64(a_seed + mn * 32 + 24);
-        }
-        const double2 a0 = rec[0], a1 = rec[G], b0 = rec[2 * G], b1 = rec[3 * G], kk = rec[4 * G];
-        rec += 5 * G;
-        const double be1 = be + al, al1 = al + 2.0;  // (n+1)^2 - m^2 = n^2 - m^2 + (2n+1)
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-            // entry a (degree n): Q1 = Q[n], Q2 = Q[n-1]
-            S1[t] = fma(Q1[t], a0.x, S1[t]);
-            S2[t] = fma(Q1[t], a0.y, S2[t]);
-            S3[t] = fma(Q1[t], a1.x, S3[t]);
-            S4[t] = fma(Q1[t], a1.y, S4[t]);
-            const double Qa = fma(al * ub[t], Q1[t], -((be * r2[t]) * Q2[t]));  // Q[n+1] = (2n+1) u Q[n] - (n+m)(n-m) Q[n-1]
-            const double wa = kk.x * Qa;
-            S5[t] = fma(wa, a1.x, S5[t]);
-            S6[t] = fma(wa, a1.y, S6[t]);
-            // entry b (degree n+1)
-            S1[t] = fma(Qa, b0.x, S1[t]);
-            S2[t] = fma(Qa, b0.y, S2[t]);
-            S3[t] = fma(Qa, b1.x, S3[t]);
-            S4[t] = fma(Qa, b1.y, S4[t]);
-            const double Qb = fma(al1 * ub[t], Qa, -((be1 * r2[t]) * Q1[t]));
-            const double wb = kk.y * Qb;
-            S5[t] = fma(wb, b1.x, S5[t]);
-            S6[t] = fma(wb, b1.y, S6[t]);
-            Q2[t] = Qa;
-            Q1[t] = Qb;
-        }
-        be = be1 + al1;
-        al = al1 + 2.0;
+    // Software pipeline over two register sets (A, B): the records of the NEXT pair are requested before the current
+    // pair is consumed, so no LDS latency is exposed; the macro is instantiated twice to avoid register-rotation moves.
+#define COOP_WALK_PAIR(a0, a1, b0, b1, kk, na0, na1, nb0, nb1, nkk)                                                     \
+    {                                                                                                                   \
+        if (e == next_start) {                                                                                          \
+            /* column switch (about three per lane and RHS): seeds are loaded here, not prefetched */                   \
+            ++ci;                                                                                                       \
+            const unsigned a_sd = a_seed + ((a_col - a_rm) >> 3) * 32;                                                  \
+            const double pd1 = lds_f64(a_sd + 8), pd2 = lds_f64(a_sd + 16);                                             \
+            al = lds_f64(a_sd + 24); be = 0.0;                                                                          \
+            _Pragma("unroll") for (int t = 0; t < T; ++t) {                                                             \
+                const unsigned base = a_col + t * traj_stride_bytes;                                                    \
+                const double q = lds_f64(base + 2 * pw8), rn = lds_f64(base - 8), in_ = lds_f64(base + pw8 - 8);        \
+                /* close the previous column: apply its (cos, sin)((m-1) lambda) */                                     \
+                X[t] = fma(rr[t], S1[t], fma(ii[t], S2[t], X[t]));                                                      \
+                Y[t] = fma(rr[t], S2[t], fma(-ii[t], S1[t], Y[t]));                                                     \
+                Z[t] = fma(rr[t], S3[t], fma(ii[t], S4[t], Z[t]));                                                      \
+                W[t] = fma(rr[t], S5[t], fma(ii[t], S6[t], W[t]));                                                      \
+                Q1[t] = q; rr[t] = rn; ii[t] = in_; Q2[t] = 0.0;                                                        \
+                S1[t] = S2[t] = S3[t] = S4[t] = 0.0;                                                                    \
+                S5[t] = q * pd1; S6[t] = q * pd2; /* W term of the column's first degree (seed record, kappa = 1) */    \
+            }                                                                                                           \
+            next_start = lds_s32(a_cs + ci * 4);                /* sentinel L+1 after the last column */                \
+            a_col = a_rm + lds_s32(a_cs + cm_off + ci * 4) * 8; /* sentinel column 1 */                                 \
+        }                                                                                                               \
+        rec += 5 * G;                                                                                                   \
+        na0 = rec[0]; na1 = rec[G]; nb0 = rec[2 * G]; nb1 = rec[3 * G]; nkk = rec[4 * G]; /* table ends with a null pair */ \
+        const double be1 = be + al, al1 = al + 2.0; /* (n+1)^2 - m^2 = n^2 - m^2 + (2n+1) */                             \
+        _Pragma("unroll") for (int t = 0; t < T; ++t) {                                                                 \
+            /* entry a (degree n): Q1 = Q[n], Q2 = Q[n-1] */                                                            \
+            S1[t] = fma(Q1[t], a0.x, S1[t]);                                                                            \
+            S2[t] = fma(Q1[t], a0.y, S2[t]);                                                                            \
+            S3[t] = fma(Q1[t], a1.x, S3[t]);                                                                            \
+            S4[t] = fma(Q1[t], a1.y, S4[t]);                                                                            \
+            const double Qa = fma(al * ub[t], Q1[t], -((be * r2[t]) * Q2[t])); /* Q[n+1] = (2n+1) u Q[n] - (n+m)(n-m) Q[n-1] */ \
+            const double wa = kk.x * Qa;                                                                                \
+            S5[t] = fma(wa, a1.x, S5[t]);                                                                               \
+            S6[t] = fma(wa, a1.y, S6[t]);                                                                               \
+            /* entry b (degree n+1) */                                                                                  \
+            S1[t] = fma(Qa, b0.x, S1[t]);                                                                               \
+            S2[t] = fma(Qa, b0.y, S2[t]);                                                                               \
+            S3[t] = fma(Qa, b1.x, S3[t]);                                                                               \
+            S4[t] = fma(Qa, b1.y, S4[t]);                                                                               \
+            const double Qb = fma(al1 * ub[t], Qa, -((be1 * r2[t]) * Q1[t]));                                           \
+            const double wb = kk.y * Qb;                                                                                \
+            S5[t] = fma(wb, b1.x, S5[t]);                                                                               \
+            S6[t] = fma(wb, b1.y, S6[t]);                                                                               \
+            Q2[t] = Qa;                                                                                                 \
+            Q1[t] = Qb;                                                                                                 \
+        }                                                                                                               \
+        be = be1 + al1;                                                                                                 \
+        al = al1 + 2.0;                                                                                                 \
+        e += 2;                                                                                                         \
     }
+    double2 A0 = rec[0], A1 = rec[G], A2 = rec[2 * G], A3 = rec[3 * G], A4 = rec[4 * G];
+    double2 B0, B1, B2, B3, B4;
+    int e = 0;
+#pragma unroll 1
+    while (e < L) {
+        COOP_WALK_PAIR(A0, A1, A2, A3, A4, B0, B1, B2, B3, B4)
+        if (e >= L) break;
+        COOP_WALK_PAIR(B0, B1, B2, B3, B4, A0, A1, A2, A3, A4)
+    }
+#undef COOP_WALK_PAIR
 #pragma unroll
     for (int t = 0; t < T; ++t) {  // close the last column
         X[t] = fma(rr[t], S1[t], fma(ii[t], S2[t], X[t]));
@@ -279,10 +286,10 @@ __device__ __forceinline__ void coop_rhs(const DevSetup& S, const double* __rest
     for (int t = 0; t < T; ++t) {
 #pragma unroll
         for (int off = G / 2; off >= 1; off >>= 1) {
-            X[t] += shfl_xor_d(gmask, X[t], off, G);
-            Y[t] += shfl_xor_d(gmask, Y[t], off, G);
-            Z[t] += shfl_xor_d(gmask, Z[t], off, G);
-            W[t] += shfl_xor_d(gmask, W[t], off, G);
+            X[t] += shfl_xor_d(FULL, X[t], off, G);
+            Y[t] += shfl_xor_d(FULL, Y[t], off, G);
+            Z[t] += shfl_xor_d(FULL, Z[t], off, G);
+            W[t] += shfl_xor_d(FULL, W[t], off, G);
         }
         // ---- reload the stage state and the DCM, assemble the acceleration
         double y[9];
@@ -370,13 +377,20 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
     // whole warps are strided over the grid (every SM gets the same number of FULL warps, surplus warps exit)
     const size_t n_sets = (n + T - 1) / T;
     const int gpw = 32 / G;
-    const size_t set = ((size_t)blockIdx.x + (size_t)gridDim.x * (tid >> 5)) * gpw + (tid & 31) / G;
-    if (set >= n_sets) return;  // uniform per group; no block-wide barrier below this point
+    const size_t set0 = ((size_t)blockIdx.x + (size_t)gridDim.x * (tid >> 5)) * gpw;  // first set of this WARP
+    if (set0 >= n_sets) return;  // uniform per warp; no block-wide barrier below this point
+    // The control flow below is WARP-uniform: every group of the warp runs the same sequence of attempts until all of them
+    // are done (a finished or absent group keeps executing on its own scratch without committing anything), so all
+    // synchronisation uses the full mask -- sub-warp masks cost a MATCH/REDUX/VOTE sequence per shuffle group.
+    const size_t set_raw = set0 + (tid & 31) / G;
+    const bool group_valid = set_raw < n_sets;
+    const size_t set = group_valid ? set_raw : 0;  // an absent group shadows set 0 and is never committed
     const int tstride = coop_traj_stride(N);
     double* sm = reinterpret_cast<double*>(meta + coop_meta_bytes(N, G, Cp.kmax)) + (size_t)grp * T * tstride;
     const int pw = N + 3;
     const unsigned lw = tid & 31;
-    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lw - lane));
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lw - lane));  // cold, group-divergent paths only
+    constexpr unsigned FULL = 0xffffffffu;
 
     TrajCtx g[T];
     size_t traj[T];
@@ -393,7 +407,7 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
         g[t].kst = s; g[t].ys = s + 96; g[t].ycur = s + 102; g[t].nxt = s + 108; g[t].er = s + 114; g[t].ev = s + 120;
         g[t].rm = s + COOP_SM_FIXED; g[t].im = g[t].rm + pw; g[t].rp = g[t].im + pw;
         g[t].hz = 0.0;
-        valid[t] = (set * T + t) < n;
+        valid[t] = group_valid && (set * T + t) < n;
         traj[t] = valid[t] ? set * T + t : set * T;  // an absent partner shadows trajectory 0 and is never committed
         // every lane of the group reads the same addresses (broadcast within the request)
         yc[t] = state[(size_t)cidx * n + traj[t]];
@@ -425,7 +439,7 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
         if (!done[t] && g[t].pm < 0.0) { rc[t] = NYXB_ERR_FUEL_EXHAUSTED; done[t] = true; }
         if (!done[t] && duration < 0) step_ns[t] = -step_ns[t];
     }
-    __syncwarp(gmask);
+    __syncwarp(FULL);
     const int stages = S.tb.stages;
     const long long stop = end_epoch;
 
@@ -448,12 +462,11 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
             det_attempts[t] = 1;
             h[t] = dur_to_seconds(step_ns[t]);
         }
-        if (all_done) break;
+        if (__all_sync(FULL, all_done)) break;
         // ---- orientation angles at the step epochs: lanes 0..2 evaluate one sin/cos pair each
         if (S.grav.rot.kind != 0) {
 #pragma unroll
             for (int t = 0; t < T; ++t) {
-                if (retry[t]) continue;  // same epoch as the rejected attempt
                 const double t_s = dur_to_seconds(epoch[t]);
                 const double d = t_s / 86400.0;
                 const double Tc = d / 36525.0;
@@ -463,9 +476,9 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
                 else ang = fmod(S.grav.rot.w0 + S.grav.rot.w1 * d, 360.0) * NYXB_DEG2RAD;
                 double sv, cv;
                 det_sincos(ang, sv, cv);
-                rbase[t].sa = shfl_d(gmask, sv, 0, G); rbase[t].ca = shfl_d(gmask, cv, 0, G);
-                rbase[t].sd = shfl_d(gmask, sv, 1, G); rbase[t].cd = shfl_d(gmask, cv, 1, G);
-                rbase[t].sw = shfl_d(gmask, sv, 2, G); rbase[t].cw = shfl_d(gmask, cv, 2, G);
+                rbase[t].sa = shfl_d(FULL, sv, 0, G); rbase[t].ca = shfl_d(FULL, cv, 0, G);
+                rbase[t].sd = shfl_d(FULL, sv, 1, G); rbase[t].cd = shfl_d(FULL, cv, 1, G);
+                rbase[t].sw = shfl_d(FULL, sv, 2, G); rbase[t].cw = shfl_d(FULL, cv, 2, G);
             }
         }
         // ---- derive(): one attempt for every trajectory of the group (instance.rs:358-493)
@@ -496,8 +509,8 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
                 dt_s[t] = (double)off_ns * 1e-9;
                 t_ns[t] = epoch[t] + off_ns;
             }
-            __syncwarp(gmask);
-            coop_rhs<G, T>(S, recs, Cp.L, sm_seed, a_cs, cm_off, g, rbase, dt_s, t_ns, lane, gmask,
+            __syncwarp(FULL);
+            coop_rhs<G, T>(S, recs, Cp.L, sm_seed, a_cs, cm_off, g, rbase, dt_s, t_ns, lane,
                            (unsigned)(tstride * 8), dyc, rcs);
 #pragma unroll
             for (int t = 0; t < T; ++t) {
@@ -507,7 +520,7 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
                 if (lane < 6) g[t].kst[i * 6 + lane] = dyc[t];
             }
         }
-        __syncwarp(gmask);  // the last stage's readers of the parked DCM (nxt) are done
+        __syncwarp(FULL);  // the last stage's readers of the parked DCM (nxt) are done
 #pragma unroll
         for (int t = 0; t < T; ++t) {
             double er = 0.0;
@@ -522,7 +535,7 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
                 g[t].er[lane] = er;
             }
         }
-        __syncwarp(gmask);
+        __syncwarp(FULL);
 #pragma unroll
         for (int t = 0; t < T; ++t) {
             if (done[t]) continue;
@@ -595,12 +608,12 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
                 done[t] = true;
             }
         }
-        __syncwarp(gmask);  // all lanes are done reading ycur/nxt/er
+        __syncwarp(FULL);  // all lanes are done reading ycur/nxt/er
 #pragma unroll
         for (int t = 0; t < T; ++t)
             if (lane < 6) g[t].ycur[lane] = yc[t];
     }
-    __syncwarp(gmask);
+    __syncwarp(FULL);
 #pragma unroll
     for (int t = 0; t < T; ++t) {
         if (!valid[t]) continue;
