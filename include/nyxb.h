@@ -123,6 +123,8 @@ typedef struct {
     int32_t sun_body;       /* index of the light source in bodies[] */
     int32_t n_shadow;
     int32_t shadow_body[4];
+    int32_t estimate;       /* SolarPressure.estimate (solarpressure.rs:47-48, 131-133): Cr column of the STM A-matrix */
+    int32_t _pad;
 } nyxb_srp;
 
 /* ---- Drag — dynamics/drag.rs:36-42,123-130,181-284 ---- */
@@ -292,6 +294,105 @@ int32_t nyxb_propagate_batch_traj_dev(nyxb_engine* eng, size_t n,
                                       double* out_state_soa, int64_t* out_epoch_ns,
                                       nyxb_details* out_details, int32_t* out_status,
                                       const nyxb_traj_sink* sink, void* cuda_stream);
+
+/* ---- State-transition-matrix propagation (next row (f)-2 of SURVEY.md §8): `Spacecraft::with_stm()` + propagate.
+ * The integrated vector is the reference's 90-vector [x,y,z,vx,vy,vz,Cr,Cd,prop_mass, STM 9x9 column-major]
+ * (cosmic/spacecraft.rs:449-473).  Stage derivative of the STM block AS CODED in the reference:
+ * `ctx.stm * grad` with `ctx` = the state at the START of the step (dynamics/spacecraft.rs:203-227,
+ * propagators/instance.rs:363-364), grad = the 9x9 A-matrix of `dual_eom` (spacecraft.rs:312-363;
+ * orbital.rs:116-172, 249-307; gravity_field.rs:273-431; solarpressure.rs:167-233; Cr column when the SRP model
+ * estimates it; Drag has no partials: `PartialsUndefined`, drag.rs:109-118, 286-295 -> NYXB_RC_UNSUPPORTED).
+ * Only the Cartesian error controls (which look at r and v alone, error_ctrl.rs:89-122) and fixed steps are accepted.
+ *  stm_in_soa / out_stm_soa  [81][n], entry (row r, col c) of trajectory i at [(c*9 + r)*n + i];
+ *  stm_in_soa == NULL: identity (State::with_stm, cosmic/spacecraft.rs:433-440). */
+int32_t nyxb_propagate_batch_stm(nyxb_engine* eng, size_t n,
+                                 const double* state_soa, const double* consts_soa,
+                                 const int64_t* epoch0_ns, int64_t end_epoch_ns,
+                                 int64_t* step_ns, const double* stm_in_soa,
+                                 double* out_state_soa, int64_t* out_epoch_ns, double* out_stm_soa,
+                                 nyxb_details* out_details, int32_t* out_status);
+
+/* ---- Sequential Kalman orbit determination over an ensemble (next row (f)-2; BASELINE configs[4]):
+ * n independent `KalmanODProcess::process_arc` runs (od/process/mod.rs:128-497) — propagate the nominal state + STM
+ * to each measurement, `KalmanFilter::time_update` / `measurement_update` (od/kalman/filtering.rs:59-316), state
+ * replacement (EKF) and STM reset — in ONE kernel launch, one filter per trajectory. */
+enum nyxb_msr_type { NYXB_MSR_RANGE = 0, NYXB_MSR_DOPPLER = 1 };  /* od/msr/types.rs:31-45 (the two-way capable ones) */
+
+/* GroundStation (od/ground_station/mod.rs:47-75) reduced to what the filter needs.  The host converts latitude /
+ * longitude / height into the body-fixed position and the local zenith (anise `Orbit::try_latlongalt`); the tracker's
+ * inertial state is R^T p (+ w x r), translated by the ephemeris of `body` when the station does not sit on the
+ * integration centre (trk_device.rs:150-152 `location`).  Instantaneous measurements only
+ * (`integration_time: None`, trk_device.rs:154-200); light-time correction off. */
+typedef struct {
+    double pos_fixed_km[3];
+    double up_fixed[3];          /* unit local zenith in the body-fixed frame (elevation = asin(rho_hat . up)) */
+    double elevation_mask_deg;
+    nyxb_rotation rot;           /* orientation of the station's body-fixed frame */
+    int32_t body;                /* NYXB_CENTRAL_BODY or index into dynamics.bodies: the body the station sits on */
+    int32_t n_types;             /* 1 or 2 */
+    int32_t types[2];            /* enum nyxb_msr_type, in the device's IndexSet order */
+    int32_t _pad;
+    double noise_var[2];         /* TrackingDevice::measurement_covar per type (trk_device.rs:223-236) */
+    double bias[2];              /* TrackingDevice::measurement_bias per type (trk_device.rs:238-253) */
+    double body_radius_km;       /* radius of the body the spacecraft orbits when it can obstruct the line of sight
+                                    (trk_device.rs:162-166); <= 0: no obstruction test */
+} nyxb_ground_station;
+
+enum nyxb_kf_variant { NYXB_KF_REFERENCE_UPDATE = 0 /* EKF */, NYXB_KF_DEVIATION_TRACKING = 1 /* CKF */ }; /* od/kalman/mod.rs */
+
+typedef struct {
+    int32_t variant;             /* enum nyxb_kf_variant */
+    int32_t msr_size;            /* MsrSize::DIM: 2 = SpacecraftKalmanOD, 1 = SpacecraftKalmanScalarOD (od/mod.rs:77-91) */
+    double reject_num_sigmas;    /* SigmaRejection.num_sigmas (process/rejectcrit.rs:35-46); < 0: None */
+    int64_t max_step_ns;         /* KalmanODProcess.max_step, default 1 min (process/initializers.rs:66-75) */
+    int64_t epoch_precision_ns;  /* default 1 us */
+    /* one ProcessNoise3D (od/snc.rs:38-56), no decay / start time */
+    int32_t snc_enabled;
+    int32_t snc_frame;           /* 0: state frame, 1: LocalFrame::RIC (snc.rs:226-262) */
+    double snc_diag[3];          /* km^2/s^4 */
+    int64_t snc_disable_time_ns;
+} nyxb_od_config;
+
+/* Tracking arc shared by the ensemble (one schedule, n observation sets) and the per-measurement outputs.
+ * obs[(k*2 + t)*n + i]: observation of type t (enum nyxb_msr_type) of trajectory i at measurement k; NaN = that
+ * type is not in `msr.data` (both NaN: the measurement is not in trajectory i's arc at all). */
+typedef struct {
+    int64_t n_msr;
+    const int64_t* epoch_ns;     /* [n_msr] ascending */
+    const int32_t* tracker;      /* [n_msr] index into stations; < 0: unknown tracker (process/mod.rs:400-410) */
+    const double* obs;           /* [n_msr][2][n] */
+} nyxb_tracking_arc;
+
+enum nyxb_msr_flag {
+    NYXB_MSRF_PROCESSED = 1,     /* a measurement update ran (accepted or rejected by the sigma test) */
+    NYXB_MSRF_REJECTED = 2,      /* residual ratio above num_sigmas: time update only (filtering.rs:169-184) */
+    NYXB_MSRF_NOT_VISIBLE = 4,   /* device.measure() returned None: below the mask / obstructed (process/mod.rs:386-392) */
+    NYXB_MSRF_ABSENT = 8         /* no data for this trajectory */
+};
+
+typedef struct {
+    double* state_soa;           /* [9][n]  final nominal state (EKF: estimate) */
+    int64_t* epoch_ns;           /* [n] */
+    double* covar_soa;           /* [81][n] final covariance, (r,c) at [(c*9+r)*n + i] */
+    double* state_dev_soa;       /* [9][n]  final state deviation (CKF); NULL to skip */
+    /* per measurement k and residual window w (msr_size 2: one window holding both types; msr_size 1: one per type) */
+    double* resid_ratio;         /* [n_msr][2][n] or NULL */
+    double* prefit;              /* [n_msr][2][n] or NULL  (slot = position of the type in the device's list) */
+    double* postfit;             /* [n_msr][2][n] or NULL */
+    int32_t* msr_flags;          /* [n_msr][n]    or NULL */
+    double* est_state;           /* [n_msr][9][n] or NULL: estimated state after measurement k */
+    double* est_covar_diag;      /* [n_msr][9][n] or NULL */
+    nyxb_details* details;       /* [n] or NULL: n_steps / n_rhs over the whole arc */
+    int32_t* status;             /* [n] */
+} nyxb_od_outputs;
+
+/* state_soa/consts_soa/epoch0_ns as in nyxb_propagate_batch (initial_estimate.nominal_state);
+ * covar0_soa [81][n] initial covariance (KfEstimate.covar); HOST pointers everywhere. */
+int32_t nyxb_od_ekf_batch(nyxb_engine* eng, const nyxb_od_config* cfg,
+                          int32_t n_stations, const nyxb_ground_station* stations,
+                          const nyxb_tracking_arc* arc, size_t n,
+                          const double* state_soa, const double* consts_soa, const int64_t* epoch0_ns,
+                          const double* covar0_soa, const nyxb_od_outputs* out);
 
 /* Tuning / introspection. */
 int32_t nyxb_engine_set_lanes(nyxb_engine* eng, int32_t lanes_per_trajectory); /* 0 = auto */

@@ -121,7 +121,7 @@ struct GravityFieldData {  // io/gravity.rs:90-128
 };
 struct PointMasses { std::vector<int32_t> celestial_objects; };
 struct GravityField { GravityFieldData grav_data; };
-struct SolarPressure { double phi = 1367.0; int32_t light_source = 10; std::vector<int32_t> shadow_bodies; };
+struct SolarPressure { double phi = 1367.0; int32_t light_source = 10; std::vector<int32_t> shadow_bodies; bool estimate = true; /* solarpressure.rs:47-48, 88-92 */ };
 struct Drag { int32_t density = NYXB_DENSITY_EXPONENTIAL; double rho0 = 3.614e-13, r0 = 700000.0, ref_alt_m = 88667.0; Frame frame = IAU_EARTH(); };
 
 struct OrbitalDynamics {
@@ -170,7 +170,7 @@ inline EnginePtr make_engine(const SpacecraftDynamics& dyn, const Frame& frame, 
     }
     nyxb_srp s{};
     if (dyn.srp) {
-        s.phi_w_m2 = dyn.srp->phi; s.sun_body = body_index(dyn.srp->light_source); s.n_shadow = (int32_t)dyn.srp->shadow_bodies.size();
+        s.phi_w_m2 = dyn.srp->phi; s.sun_body = body_index(dyn.srp->light_source); s.n_shadow = (int32_t)dyn.srp->shadow_bodies.size(); s.estimate = dyn.srp->estimate ? 1 : 0;
         for (int q = 0; q < s.n_shadow && q < 4; ++q)
             s.shadow_body[q] = dyn.srp->shadow_bodies[q] == frame.ephemeris_id ? NYXB_CENTRAL_BODY : body_index(dyn.srp->shadow_bodies[q]);
         d.srp = &s;

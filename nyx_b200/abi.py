@@ -89,6 +89,8 @@ class SrpC(C.Structure):
         ("sun_body", C.c_int32),
         ("n_shadow", C.c_int32),
         ("shadow_body", C.c_int32 * 4),
+        ("estimate", C.c_int32),
+        ("_pad", C.c_int32),
     ]
 
 

@@ -274,6 +274,7 @@ class SpacecraftDynamics:
             if len(srp.shadow_model.shadow_bodies) > 4:
                 raise DynamicsError("at most 4 shadow bodies")
             sc.n_shadow = len(srp.shadow_model.shadow_bodies)
+            sc.estimate = 1 if srp.estimate else 0
             for q, fb in enumerate(srp.shadow_model.shadow_bodies):
                 sc.shadow_body[q] = (abi.NYXB_CENTRAL_BODY if fb.ephemeris_id == frame.ephemeris_id
                                      else almanac.body_index(fb.ephemeris_id))

@@ -26,6 +26,7 @@
  * contracts a*b+c into an FMA; neither may we).
  */
 #include "nyx_oracle.h"
+#include "nyx_oracle_priv.h"
 
 #include <math.h>
 #include <stdlib.h>
@@ -278,15 +279,7 @@ static inline double norm3(const double v[3]) {
 /* ------------------------------------------------------------------------- */
 /* GravityField — dynamics/gravity_field.rs                                   */
 /* ------------------------------------------------------------------------- */
-struct nyx_oracle_grav {
-    int n, m;                 /* max degree / order */
-    int dim;                  /* n + 3 */
-    double mu, r_eq;
-    nyxb_rotation rot;
-    double *a_diag;           /* gravity_field.rs:61-66: a_nm[(k,k)], k = 0..n+2 */
-    double *b_nm, *c_nm, *vr01, *vr11; /* (n+2)^2 each, row-major [n][m], gravity_field.rs:69-92 */
-    double *cbar, *sbar;      /* (n+1)^2 row-major */
-};
+/* struct nyx_oracle_grav: see nyx_oracle_priv.h (shared with nyx_oracle_od.c) */
 
 /* gravity_field.rs:52-132 (GravityField::new) */
 nyx_oracle_grav* nyx_oracle_grav_new(const nyxb_gravity_field* g) {

@@ -26,7 +26,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(abi.Rotation) == 56
     assert C.sizeof(abi.GravityFieldC) == 8 + 16 + 16 + 56
     assert C.sizeof(abi.BodyC) == 48
-    assert C.sizeof(abi.SrpC) == 32
+    assert C.sizeof(abi.SrpC) == 40
     assert C.sizeof(abi.DragC) == 40 + 56
     assert C.sizeof(abi.DynamicsC) == 64
     assert C.sizeof(abi.Details) == 48
