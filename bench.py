@@ -48,7 +48,7 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="nyxb", choices=["nyxb", "reference"])
     p.add_argument("--n-traj", type=int, default=10_000, help="trajectories per GPU")
-    p.add_argument("--span-days", type=float, default=3.0)
+    p.add_argument("--span-days", type=float, default=None, help="default: 3 days (c2-c4), 2 days (c5)")
     p.add_argument("--degree", type=int, default=21)
     p.add_argument("--mode", default="fast", choices=["fast", "strict"])
     p.add_argument("--lanes", type=int, default=0)
@@ -58,9 +58,14 @@ def parse_args():
     p.add_argument("--no-strict", action="store_true", help="skip the extra bit-parity (STRICT mode) pass at N=1")
     p.add_argument("--record", type=int, default=0, metavar="CAP",
                    help="also time one pass with trajectory recording (CAP records per trajectory, device-resident sink)")
-    p.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
-                   help="c2 = BASELINE configs[1] (the metric's workload); c3/c4 = configs[2]/[3], reported for context only")
-    return p.parse_args()
+    p.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
+                   help="c2 = BASELINE configs[1] (the metric's workload); c3/c4/c5 = configs[2]/[3]/[4], reported for context only")
+    a = p.parse_args()
+    if a.span_days is None:
+        a.span_days = 2.0 if a.workload == "c5" else 3.0
+    if a.workload == "c5" and a.n_traj == 10_000:
+        a.n_traj = 1000
+    return a
 
 
 def build_workload(args, n_total, nb):
@@ -102,6 +107,97 @@ def build_workload(args, n_total, nb):
     cs[2] = template.srp.area_m2
     ep = np.zeros(n_total, dtype=np.int64)
     return frame, dyn, almanac, st, cs, ep
+
+
+def bench_c5(args, nb, local_rank):
+    """BASELINE configs[4] (context only, N=1): LRO-like ensemble, every trajectory runs its own EKF over the same tracking
+    schedule — `nyxb_od_ekf_batch`, ONE launch for the whole arc (propagation with STM + time/measurement updates)."""
+    from nyx_b200.frames import EARTH
+
+    S_ = 10**9
+    frame = nb.MOON_J2000
+    n = args.n_traj
+    deg = args.degree if args.degree != 21 else 70
+    alm = nb.Almanac.synthetic(frame, 0, args.span_days + 2.0, bodies=(EARTH, nb.SUN))
+    gd = nb.GravityFieldData.from_fixture("luna_jggrx_80x80", deg, deg, nb.IAU_MOON_FRAME)
+    srp = nb.SolarPressure.new([nb.EARTH_J2000, nb.MOON_J2000], alm)
+    dyn = nb.SpacecraftDynamics.from_model(nb.OrbitalDynamics.new([nb.PointMasses.new([EARTH, nb.SUN]), nb.GravityField.new(gd)]), srp)
+    mode = nb.MODE_FAST if args.mode == "fast" else nb.MODE_STRICT
+    prop = nb.Propagator.default_dp78(dyn, mode=mode, device=local_rank)   # examples/04_lro_od/main.rs:163
+    orbit = nb.Orbit.keplerian(1737.4 + 100.0, 0.002, 88.0, 20.0, 10.0, 0.0, 0, frame)
+    truth0 = nb.Spacecraft(orbit=orbit, mass=nb.Mass(1018.0, 900.0, 0.0), srp=nb.SRPData(3.9 * 2.7, 0.96))
+    rn, dn = nb.StochasticNoise(5e-3), nb.StochasticNoise(5e-6)
+    devices = {"Madrid": nb.GroundStation.dss65_madrid(5.0, rn, dn), "Canberra": nb.GroundStation.dss34_canberra(5.0, rn, dn),
+               "Goldstone": nb.GroundStation.dss13_goldstone(5.0, rn, dn)}
+    names = list(devices)
+    n_msr = int(args.span_days * 86400 // 60)
+    epochs = (np.arange(1, n_msr + 1) * 60 * S_).astype(np.int64)
+    schedule = [names[(k // 240) % 3] for k in range(n_msr)]   # 4-hour passes
+    # truth trajectory (one spacecraft, fixed 60 s steps, recorded) through the product's own recording path
+    tprop = nb.Propagator.new(dyn, nb.IntegratorMethod.RungeKutta89, nb.IntegratorOptions.with_fixed_step_s(60.0), mode=nb.MODE_FAST, device=local_rank)
+    st1, cs1, ep1 = nb.pack_spacecraft([truth0])
+    _, _, _, tstat, (t_ep, t_st, t_cnt) = tprop.engine(frame, alm).propagate_batch(st1, cs1, ep1, int(epochs[-1]), traj_capacity=n_msr + 2)
+    assert tstat[0] == 0 and np.array_equal(t_ep[1: n_msr + 1, 0], epochs)
+    truth = np.repeat(t_st[:, 1: n_msr + 1, 0].T[:, :, None], n, axis=2)
+    rng = np.random.default_rng(0)
+    arc = nb.simulate_tracking(epochs, truth, devices, schedule, frame, alm, rng)
+    ests = []
+    for i in range(n):   # examples/04_lro_od/main.rs:268-282: 0.5 km / 5 m/s RIC sigmas; smaller velocity dispersion here
+        v = truth0.to_vector()
+        v[:6] += np.concatenate([rng.normal(0, 0.3, 3), rng.normal(0, 3e-4, 3)])
+        ests.append(nb.KfEstimate.from_diag(truth0.with_vector(0, v), [0.25, 0.25, 0.25, 2.5e-7, 2.5e-7, 2.5e-7, 0.04, 0.0, 0.0]))
+    odp = nb.SpacecraftKalmanOD(prop, nb.KalmanVariant.ReferenceUpdate, nb.SigmaRejection(3.0), devices, alm)
+    odp.with_process_noise(nb.ProcessNoise3D.from_velocity_km_s([1e-10, 1e-10, 1e-10], 1 * nb.Unit.Hour, 10 * nb.Unit.Minute, None))
+    eng = prop.engine(frame, alm)
+    # warm-up: a short arc
+    warm = nb.TrackingDataArc(arc.epoch_ns[:4], arc.tracker[:4], arc.obs[:4, :, :min(n, 64)])
+    odp.process_arcs(ests[:min(n, 64)], warm)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = eng.launch_count()
+    t0 = time.perf_counter()
+    sol = odp.process_arcs(ests, arc)
+    wall = time.perf_counter() - t0
+    kern_ms = eng.last_kernel_ms()
+    clocks = sampler.stop()
+    steps = int(sol.details["n_steps"].sum())
+    ok = int((sol.status == 0).sum())
+    acc = int(sol.accepted().sum())
+    err = np.linalg.norm(sol.final_state_soa[:3] - truth[-1, :3, :], axis=0)
+    last_vis = np.where(~np.isnan(arc.obs[:, 0, 0]))[0]
+    line = {"metric": "trajectory-steps/sec (ensemble)", "value": steps / (kern_ms * 1e-3), "unit": "trajectory-steps/s", "n_gpus": 1,
+            "steps": 1, "warmup": 1, "ms_per_step": kern_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C5: {n} LRO-like filters (Moon-centred, GRAIL {deg}x{deg} + Earth/Sun point masses + SRP with Cr estimated), "
+                                   f"EKF over {n_msr} range+Doppler measurement epochs at 60 s from 3 DSN stations, {args.span_days:g}-day span, DP78",
+                       "ok_trajectories": ok, "measurement_updates_accepted": acc, "mode": args.mode, "kernel": "nyxb_k_od (1 thread = 1 filter)",
+                       "median_final_position_error_km": float(np.median(err)) if last_vis.size and last_vis[-1] == n_msr - 1 else None},
+            "e2e": {"value": steps / wall, "unit": "trajectory-steps/s", "h2d_bytes_per_step": int(arc.obs.nbytes + n * (13 + 81) * 8),
+                    "d2h_bytes_per_step": int(n * (9 + 81 + 9) * 8 + 3 * arc.obs.nbytes + n_msr * n * 4), "ms_per_step": wall * 1e3},
+            "gpu_launches": eng.launch_count() - launches0, "clocks": clocks,
+            "measurement_updates_per_s": acc / (kern_ms * 1e-3)}
+    if not args.no_cpu_baseline:
+        # numpy + C oracle filter (tests' checker) on ONE filter over the first measurements: a bounded sample
+        from oracle import pyoracle_od
+
+        m_s = min(n_msr, 90)
+        names_c, st_c = odp.stations_c(frame)
+        tracker = np.array([names_c.index(t) for t in arc.tracker[:m_s]], dtype=np.int32)
+        e0 = ests[0]
+        msc = e0.nominal_state.mass
+        cs0 = np.array([msc.dry_mass_kg, msc.extra_mass_kg, e0.nominal_state.srp.area_m2, 0.0])
+        packed = dyn.pack(frame, alm)
+        t0 = time.perf_counter()
+        ref = pyoracle_od.process_arc(packed.c, prop.opts.to_c(prop.method), odp.config_c(), st_c, arc.epoch_ns[:m_s], tracker,
+                                      np.ascontiguousarray(arc.obs[:m_s, :, 0]), e0.nominal_state.to_vector(), cs0, 0, e0.covar)
+        ct = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": ref["n_steps"] / ct, "unit": "trajectory-steps/s", "cores": 1, "kind": "port",
+                                "sample": f"filter 0 over the first {m_s} measurement epochs ({ref['n_steps']} steps, {ct:.1f} s), numpy + C oracle"}
+        k_last = int(np.where(~np.isnan(ref["est_state"][:, 0]))[0][-1])
+        sub = odp.process_arcs(ests[:1], nb.TrackingDataArc(arc.epoch_ns[:m_s], arc.tracker[:m_s], arc.obs[:m_s, :, :1]), record_estimates=True)
+        line["max_dr_km"] = float(np.abs(sub.est_state[k_last, :3, 0] - ref["est_state"][k_last, :3]).max())
+    print(json.dumps(line))
+    return 0
 
 
 WORKLOAD_TEXT = {
@@ -176,6 +272,10 @@ def main():
 
     if args.cpu_sample <= 0:
         args.cpu_sample = 32 * (os.cpu_count() or 8)
+    if args.workload == "c5":
+        if rank != 0 or args.impl == "reference":
+            return 0
+        return bench_c5(args, nb, local_rank)
     workload = WORKLOAD_TEXT[args.workload].format(n=args.n_traj, deg=args.degree, span=args.span_days)
     # algorithmic flop per accepted step: C2 from the degree; C3 ~ 9 k (two ephemeris bodies + SRP); C4 = 70x70
     fps = {"c2": flops_per_step(args.degree), "c3": 9.0e3, "c4": flops_per_step(70) + 16 * 200.0}[args.workload]

@@ -16,6 +16,9 @@ from .gravity import GravityFieldData
 from .monte_carlo import DispersedState, MonteCarlo, MvnSpacecraft, Results, Run
 from .trajectory import Traj, TrajError, hermite_eval
 from .event import Event, brent, locate_event
+from .od import (GroundStation, KalmanODProcess, KalmanVariant, KfEstimate, LocalFrame, MeasurementType, ODError, ODSolution,
+                 ProcessNoise3D, SigmaRejection, SpacecraftKalmanOD, SpacecraftKalmanScalarOD, SpacecraftUncertainty,
+                 StochasticNoise, TrackingDataArc, simulate_tracking, station_state)
 from .propagator import (Engine, ErrorControl, IntegrationDetails, IntegratorMethod, IntegratorOptions, PropagationError,
                          PropInstance, Propagator)
 

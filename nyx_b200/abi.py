@@ -151,6 +151,68 @@ class EventC(C.Structure):
     ]
 
 
+# ---- orbit determination: mirrors of nyxb_ground_station / nyxb_od_config / nyxb_tracking_arc / nyxb_od_outputs
+MSR_RANGE, MSR_DOPPLER = 0, 1
+KF_REFERENCE_UPDATE, KF_DEVIATION_TRACKING = 0, 1
+MSRF_PROCESSED, MSRF_REJECTED, MSRF_NOT_VISIBLE, MSRF_ABSENT = 1, 2, 4, 8
+
+
+class GroundStationC(C.Structure):
+    _fields_ = [
+        ("pos_fixed_km", C.c_double * 3),
+        ("up_fixed", C.c_double * 3),
+        ("elevation_mask_deg", C.c_double),
+        ("rot", Rotation),
+        ("body", C.c_int32),
+        ("n_types", C.c_int32),
+        ("types", C.c_int32 * 2),
+        ("_pad", C.c_int32),
+        ("noise_var", C.c_double * 2),
+        ("bias", C.c_double * 2),
+        ("body_radius_km", C.c_double),
+    ]
+
+
+class OdConfigC(C.Structure):
+    _fields_ = [
+        ("variant", C.c_int32),
+        ("msr_size", C.c_int32),
+        ("reject_num_sigmas", C.c_double),
+        ("max_step_ns", C.c_int64),
+        ("epoch_precision_ns", C.c_int64),
+        ("snc_enabled", C.c_int32),
+        ("snc_frame", C.c_int32),
+        ("snc_diag", C.c_double * 3),
+        ("snc_disable_time_ns", C.c_int64),
+    ]
+
+
+class TrackingArcC(C.Structure):
+    _fields_ = [
+        ("n_msr", C.c_int64),
+        ("epoch_ns", C.c_void_p),
+        ("tracker", C.c_void_p),
+        ("obs", C.c_void_p),
+    ]
+
+
+class OdOutputsC(C.Structure):
+    _fields_ = [
+        ("state_soa", C.c_void_p),
+        ("epoch_ns", C.c_void_p),
+        ("covar_soa", C.c_void_p),
+        ("state_dev_soa", C.c_void_p),
+        ("resid_ratio", C.c_void_p),
+        ("prefit", C.c_void_p),
+        ("postfit", C.c_void_p),
+        ("msr_flags", C.c_void_p),
+        ("est_state", C.c_void_p),
+        ("est_covar_diag", C.c_void_p),
+        ("details", C.c_void_p),
+        ("status", C.c_void_p),
+    ]
+
+
 DETAILS_DTYPE = np.dtype(
     [
         ("step_ns", "<i8"),
@@ -207,6 +269,11 @@ def _declare(lib):
     lib.nyxb_propagate_batch_traj_dev.argtypes = batch_args + [C.POINTER(TrajSink), vp]
     lib.nyxb_propagate_batch_event.restype = C.c_int32
     lib.nyxb_propagate_batch_event.argtypes = batch_args + [C.POINTER(TrajSink), C.POINTER(EventC)]
+    lib.nyxb_propagate_batch_stm.restype = C.c_int32
+    lib.nyxb_propagate_batch_stm.argtypes = [vp, C.c_size_t, vp, vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp]
+    lib.nyxb_od_ekf_batch.restype = C.c_int32
+    lib.nyxb_od_ekf_batch.argtypes = [vp, C.POINTER(OdConfigC), C.c_int32, C.POINTER(GroundStationC), C.POINTER(TrackingArcC),
+                                      C.c_size_t, vp, vp, vp, vp, C.POINTER(OdOutputsC)]
     lib.nyxb_engine_set_lanes.restype = C.c_int32
     lib.nyxb_engine_set_lanes.argtypes = [vp, C.c_int32]
     lib.nyxb_engine_get_lanes.restype = C.c_int32
@@ -234,6 +301,8 @@ EXPORTED_SYMBOLS = [
     "nyxb_propagate_batch_traj",
     "nyxb_propagate_batch_traj_dev",
     "nyxb_propagate_batch_event",
+    "nyxb_propagate_batch_stm",
+    "nyxb_od_ekf_batch",
     "nyxb_engine_set_lanes",
     "nyxb_engine_get_lanes",
     "nyxb_engine_launch_count",

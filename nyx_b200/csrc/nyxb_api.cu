@@ -12,6 +12,7 @@
 
 #include "nyxb_coop.h"
 #include "nyxb_device.cuh"
+#include "nyxb_od.cuh"
 #include "nyxb_tableaux.h"
 
 // kernels (nyxb_kernels.cu built twice, nyxb_coop.cu)
@@ -235,7 +236,7 @@ extern "C" nyxb_engine* nyxb_engine_create(const nyxb_dynamics* dyn, const nyxb_
             set_err("bad SRP descriptor"); delete e; return nullptr;
         }
         S.has_srp = 1;
-        S.srp.phi = s.phi_w_m2; S.srp.sun_body = s.sun_body; S.srp.n_shadow = s.n_shadow;
+        S.srp.phi = s.phi_w_m2; S.srp.sun_body = s.sun_body; S.srp.n_shadow = s.n_shadow; S.srp.estimate = s.estimate;
         for (int q = 0; q < 4; ++q) {
             S.srp.shadow_body[q] = s.shadow_body[q];
             if (q < s.n_shadow && s.shadow_body[q] != NYXB_CENTRAL_BODY && (s.shadow_body[q] < 0 || s.shadow_body[q] >= dyn->n_bodies)) {
@@ -456,6 +457,190 @@ extern "C" int32_t nyxb_propagate_batch(nyxb_engine* eng, size_t n, const double
                                         int32_t* out_status) {
     return nyxb_propagate_batch_traj(eng, n, state_soa, consts_soa, epoch0_ns, end_epoch_ns, step_ns, out_state_soa, out_epoch_ns,
                                      out_details, out_status, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// (f)-2: STM propagation and the batched sequential filter (kernels in nyxb_od.cu).  Host-pointer entry points with
+// per-call device buffers (these calls run for seconds; allocation cost is irrelevant).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+struct DevBufs {
+    std::vector<void*> p;
+    ~DevBufs() { for (void* q : p) cudaFree(q); }
+    template <typename T> T* alloc(size_t count) {
+        T* d = nullptr;
+        if (cudaMalloc(&d, sizeof(T) * (count ? count : 1)) != cudaSuccess) return nullptr;
+        p.push_back(d);
+        return d;
+    }
+    template <typename T> T* put(const T* host, size_t count, cudaStream_t st) {
+        T* d = alloc<T>(count);
+        if (d && count && cudaMemcpyAsync(d, host, sizeof(T) * count, cudaMemcpyHostToDevice, st) != cudaSuccess) return nullptr;
+        return d;
+    }
+};
+bool stm_supported(const nyxb_engine* e) {
+    if (e->S.has_drag) { set_err("PartialsUndefined: the drag model has no partials (drag.rs:109-118, 286-295)"); return false; }
+    if (!e->S.fixed_step && e->S.error_ctrl != NYXB_RSS_CARTESIAN_STATE && e->S.error_ctrl != NYXB_RSS_CARTESIAN_STEP) {
+        set_err("STM propagation accepts the Cartesian error controls or a fixed step");
+        return false;
+    }
+    return true;
+}
+}  // namespace
+
+extern "C" int32_t nyxb_propagate_batch_stm(nyxb_engine* eng, size_t n, const double* state_soa, const double* consts_soa,
+                                            const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
+                                            const double* stm_in_soa, double* out_state_soa, int64_t* out_epoch_ns,
+                                            double* out_stm_soa, nyxb_details* out_details, int32_t* out_status) {
+    if (!eng || !state_soa || !consts_soa || !epoch0_ns || !out_state_soa || !out_epoch_ns || !out_stm_soa || !out_status) {
+        set_err("null argument");
+        return NYXB_RC_BAD_ARG;
+    }
+    if (!stm_supported(eng)) return NYXB_RC_UNSUPPORTED;
+    if (n == 0) return NYXB_RC_OK;
+    CUDA_TRY(cudaSetDevice(eng->device));
+    if (!eng->stream) CUDA_TRY(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+    cudaStream_t st = eng->stream;
+    DevBufs B;
+    double* d_state = B.put(state_soa, 9 * n, st);
+    double* d_consts = B.put(consts_soa, 4 * n, st);
+    long long* d_ep = B.put((const long long*)epoch0_ns, n, st);
+    long long* d_step = step_ns ? B.put((const long long*)step_ns, n, st) : nullptr;
+    double* d_stm_in = stm_in_soa ? B.put(stm_in_soa, 81 * n, st) : nullptr;
+    double* d_out = B.alloc<double>(9 * n);
+    double* d_stm = B.alloc<double>(81 * n);
+    long long* d_oep = B.alloc<long long>(n);
+    nyxb_details* d_det = B.alloc<nyxb_details>(n);
+    int* d_status = B.alloc<int>(n);
+    if (!d_state || !d_consts || !d_ep || (step_ns && !d_step) || (stm_in_soa && !d_stm_in) || !d_out || !d_stm || !d_oep || !d_det || !d_status) {
+        set_err("device allocation / upload failed");
+        return NYXB_RC_CUDA;
+    }
+    CUDA_TRY(cudaEventRecord(eng->ev0, st));
+    cudaError_t err = (eng->mode == NYXB_MODE_STRICT)
+        ? nyxb_launch_stm_strict(&eng->S, n, d_state, d_consts, d_ep, end_epoch_ns, d_step, d_stm_in, d_out, d_oep, d_stm, d_det, d_status, st)
+        : nyxb_launch_stm_fast(&eng->S, n, d_state, d_consts, d_ep, end_epoch_ns, d_step, d_stm_in, d_out, d_oep, d_stm, d_det, d_status, st);
+    if (err != cudaSuccess) { set_err(std::string("kernel launch: ") + cudaGetErrorString(err)); return NYXB_RC_CUDA; }
+    eng->launches += 1;
+    CUDA_TRY(cudaEventRecord(eng->ev1, st));
+    CUDA_TRY(cudaMemcpyAsync(out_state_soa, d_out, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_stm_soa, d_stm, sizeof(double) * 81 * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_epoch_ns, d_oep, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+    if (step_ns) CUDA_TRY(cudaMemcpyAsync(step_ns, d_step, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+    if (out_details) CUDA_TRY(cudaMemcpyAsync(out_details, d_det, sizeof(nyxb_details) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_status, d_status, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, eng->ev0, eng->ev1) == cudaSuccess) eng->last_ms = ms;
+    return NYXB_RC_OK;
+}
+
+extern "C" int32_t nyxb_od_ekf_batch(nyxb_engine* eng, const nyxb_od_config* cfg, int32_t n_stations,
+                                     const nyxb_ground_station* stations, const nyxb_tracking_arc* arc, size_t n,
+                                     const double* state_soa, const double* consts_soa, const int64_t* epoch0_ns,
+                                     const double* covar0_soa, const nyxb_od_outputs* out) {
+    if (!eng || !cfg || !arc || !state_soa || !consts_soa || !epoch0_ns || !covar0_soa || !out || !out->state_soa || !out->epoch_ns ||
+        !out->covar_soa || !out->status || (n_stations > 0 && !stations) || n_stations < 0) {
+        set_err("null argument");
+        return NYXB_RC_BAD_ARG;
+    }
+    if (!stm_supported(eng)) return NYXB_RC_UNSUPPORTED;
+    if (cfg->msr_size != 1 && cfg->msr_size != 2) { set_err("msr_size must be 1 or 2"); return NYXB_RC_BAD_ARG; }
+    if (cfg->variant != NYXB_KF_REFERENCE_UPDATE && cfg->variant != NYXB_KF_DEVIATION_TRACKING) { set_err("bad filter variant"); return NYXB_RC_BAD_ARG; }
+    if (cfg->max_step_ns <= 0) { set_err("StepSize: max_step must be positive (process/mod.rs:147-150)"); return NYXB_RC_BAD_ARG; }
+    if (arc->n_msr < 2) { set_err("TooFewMeasurements: need 2 (process/mod.rs:139-145)"); return NYXB_RC_BAD_ARG; }
+    if (!arc->epoch_ns || !arc->tracker || !arc->obs) { set_err("null tracking arc arrays"); return NYXB_RC_BAD_ARG; }
+    for (int32_t s = 0; s < n_stations; ++s) {
+        const nyxb_ground_station& g = stations[s];
+        if (g.n_types < 1 || g.n_types > 2 || (g.body != NYXB_CENTRAL_BODY && (g.body < 0 || g.body >= eng->S.n_bodies))) {
+            set_err("bad ground station descriptor");
+            return NYXB_RC_BAD_ARG;
+        }
+        for (int q = 0; q < g.n_types; ++q)
+            if (g.types[q] != NYXB_MSR_RANGE && g.types[q] != NYXB_MSR_DOPPLER) { set_err("unsupported measurement type"); return NYXB_RC_UNSUPPORTED; }
+        if (g.n_types % cfg->msr_size != 0) { set_err("filter misconfigured: measurement types per device must be a multiple of msr_size"); return NYXB_RC_UNSUPPORTED; }
+    }
+    if (n == 0) return NYXB_RC_OK;
+    CUDA_TRY(cudaSetDevice(eng->device));
+    if (!eng->stream) CUDA_TRY(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+    cudaStream_t st = eng->stream;
+    const size_t m = (size_t)arc->n_msr;
+    DevBufs B;
+    std::vector<DevStation> hs((size_t)n_stations);
+    for (int32_t s = 0; s < n_stations; ++s) {
+        const nyxb_ground_station& g = stations[s];
+        DevStation& d = hs[s];
+        for (int q = 0; q < 3; ++q) { d.pos[q] = g.pos_fixed_km[q]; d.up[q] = g.up_fixed[q]; }
+        d.mask_deg = g.elevation_mask_deg; d.rot = pack_rot(g.rot); d.body = g.body; d.n_types = g.n_types;
+        for (int q = 0; q < 2; ++q) { d.types[q] = g.types[q]; d.noise_var[q] = g.noise_var[q]; d.bias[q] = g.bias[q]; }
+        d.body_radius = g.body_radius_km;
+    }
+    DevOd od{};
+    od.variant = cfg->variant; od.msr_size = cfg->msr_size; od.reject = cfg->reject_num_sigmas;
+    od.max_step_ns = cfg->max_step_ns; od.eps_ns = cfg->epoch_precision_ns;
+    od.snc_enabled = cfg->snc_enabled; od.snc_frame = cfg->snc_frame;
+    for (int q = 0; q < 3; ++q) od.snc_diag[q] = cfg->snc_diag[q];
+    od.snc_disable_ns = cfg->snc_disable_time_ns;
+    od.n_stations = n_stations;
+    od.stations = B.put(hs.data(), hs.size(), st);
+    od.n_msr = arc->n_msr;
+    od.msr_epoch = B.put((const long long*)arc->epoch_ns, m, st);
+    od.msr_tracker = B.put((const int*)arc->tracker, m, st);
+    od.obs = B.put(arc->obs, m * 2 * n, st);
+    od.covar0 = B.put(covar0_soa, 81 * n, st);
+    double* d_state = B.put(state_soa, 9 * n, st);
+    double* d_consts = B.put(consts_soa, 4 * n, st);
+    long long* d_ep = B.put((const long long*)epoch0_ns, n, st);
+    double* d_out = B.alloc<double>(9 * n);
+    long long* d_oep = B.alloc<long long>(n);
+    nyxb_details* d_det = B.alloc<nyxb_details>(n);
+    int* d_status = B.alloc<int>(n);
+    od.covar = B.alloc<double>(81 * n);
+    od.state_dev = out->state_dev_soa ? B.alloc<double>(9 * n) : nullptr;
+    od.ratio = out->resid_ratio ? B.alloc<double>(m * 2 * n) : nullptr;
+    od.prefit = out->prefit ? B.alloc<double>(m * 2 * n) : nullptr;
+    od.postfit = out->postfit ? B.alloc<double>(m * 2 * n) : nullptr;
+    od.flags = out->msr_flags ? B.alloc<int>(m * n) : nullptr;
+    od.est_state = out->est_state ? B.alloc<double>(m * 9 * n) : nullptr;
+    od.est_cov = out->est_covar_diag ? B.alloc<double>(m * 9 * n) : nullptr;
+    if (!od.stations || !od.msr_epoch || !od.msr_tracker || !od.obs || !od.covar0 || !d_state || !d_consts || !d_ep || !d_out || !d_oep ||
+        !d_det || !d_status || !od.covar || (out->state_dev_soa && !od.state_dev) || (out->resid_ratio && !od.ratio) ||
+        (out->prefit && !od.prefit) || (out->postfit && !od.postfit) || (out->msr_flags && !od.flags) ||
+        (out->est_state && !od.est_state) || (out->est_covar_diag && !od.est_cov)) {
+        set_err("device allocation / upload failed");
+        return NYXB_RC_CUDA;
+    }
+    // per-measurement records default to NaN (0xFF bytes) / 0 flags where nothing is written
+    if (od.ratio) CUDA_TRY(cudaMemsetAsync(od.ratio, 0xFF, sizeof(double) * m * 2 * n, st));
+    if (od.prefit) CUDA_TRY(cudaMemsetAsync(od.prefit, 0xFF, sizeof(double) * m * 2 * n, st));
+    if (od.postfit) CUDA_TRY(cudaMemsetAsync(od.postfit, 0xFF, sizeof(double) * m * 2 * n, st));
+    if (od.flags) CUDA_TRY(cudaMemsetAsync(od.flags, 0, sizeof(int) * m * n, st));
+    if (od.est_state) CUDA_TRY(cudaMemsetAsync(od.est_state, 0xFF, sizeof(double) * m * 9 * n, st));
+    if (od.est_cov) CUDA_TRY(cudaMemsetAsync(od.est_cov, 0xFF, sizeof(double) * m * 9 * n, st));
+    CUDA_TRY(cudaEventRecord(eng->ev0, st));
+    cudaError_t err = (eng->mode == NYXB_MODE_STRICT)
+        ? nyxb_launch_od_strict(&eng->S, &od, n, d_state, d_consts, d_ep, d_out, d_oep, d_det, d_status, st)
+        : nyxb_launch_od_fast(&eng->S, &od, n, d_state, d_consts, d_ep, d_out, d_oep, d_det, d_status, st);
+    if (err != cudaSuccess) { set_err(std::string("kernel launch: ") + cudaGetErrorString(err)); return NYXB_RC_CUDA; }
+    eng->launches += 1;
+    CUDA_TRY(cudaEventRecord(eng->ev1, st));
+    CUDA_TRY(cudaMemcpyAsync(out->state_soa, d_out, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out->epoch_ns, d_oep, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out->covar_soa, od.covar, sizeof(double) * 81 * n, cudaMemcpyDeviceToHost, st));
+    if (od.state_dev) CUDA_TRY(cudaMemcpyAsync(out->state_dev_soa, od.state_dev, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost, st));
+    if (od.ratio) CUDA_TRY(cudaMemcpyAsync(out->resid_ratio, od.ratio, sizeof(double) * m * 2 * n, cudaMemcpyDeviceToHost, st));
+    if (od.prefit) CUDA_TRY(cudaMemcpyAsync(out->prefit, od.prefit, sizeof(double) * m * 2 * n, cudaMemcpyDeviceToHost, st));
+    if (od.postfit) CUDA_TRY(cudaMemcpyAsync(out->postfit, od.postfit, sizeof(double) * m * 2 * n, cudaMemcpyDeviceToHost, st));
+    if (od.flags) CUDA_TRY(cudaMemcpyAsync(out->msr_flags, od.flags, sizeof(int) * m * n, cudaMemcpyDeviceToHost, st));
+    if (od.est_state) CUDA_TRY(cudaMemcpyAsync(out->est_state, od.est_state, sizeof(double) * m * 9 * n, cudaMemcpyDeviceToHost, st));
+    if (od.est_cov) CUDA_TRY(cudaMemcpyAsync(out->est_covar_diag, od.est_cov, sizeof(double) * m * 9 * n, cudaMemcpyDeviceToHost, st));
+    if (out->details) CUDA_TRY(cudaMemcpyAsync(out->details, d_det, sizeof(nyxb_details) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out->status, d_status, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, eng->ev0, eng->ev1) == cudaSuccess) eng->last_ms = ms;
+    return NYXB_RC_OK;
 }
 
 extern "C" int32_t nyxb_engine_set_lanes(nyxb_engine* eng, int32_t lanes) {

@@ -55,6 +55,7 @@ struct DevSrp {
     double phi;
     int sun_body, n_shadow;
     int shadow_body[4];
+    int estimate;  // Cr column of the STM A-matrix (solarpressure.rs:131-133)
 };
 
 struct DevDrag {

@@ -1,0 +1,798 @@
+// nyxb_od.cu — state-transition-matrix propagation and the sequential Kalman filter, one CUDA thread per trajectory
+// (BASELINE configs[4]).  The whole arc of a filter — propagation of the nominal state and the STM
+// between measurements, time updates, measurement updates, state replacement — runs inside ONE kernel launch; state,
+// STM, covariance and stage data stay in registers / L1-resident local memory, HBM sees the inputs once and the
+// per-measurement residual records as coalesced [m][..][n] stores.
+//
+// Built twice like nyxb_kernels.cu: -DNYXB_STRICT=1 -fmad=false (same operation order as oracle/nyx_oracle_od.c for
+// the dynamics) and -DNYXB_STRICT=0 -fmad=true.
+//
+// Reference behaviour (paths relative to /root/reference/nyx-core/src):
+//   SpacecraftDynamics::eom `Some(stm)` branch / dual_eom      dynamics/spacecraft.rs:203-227, 312-363
+//   OrbitalDynamics::dual_eom, PointMasses::gradient           dynamics/orbital.rs:116-172, 249-307
+//   GravityField::gradient                                     dynamics/gravity_field.rs:273-431
+//   SolarPressure::gradient                                    dynamics/solarpressure.rs:167-233
+//   PropInstance::{propagate, single_step, derive}             propagators/instance.rs:87-262, 343-493
+//   KalmanODProcess::process_arc                               od/process/mod.rs:128-497
+//   KalmanFilter::{time_update, measurement_update}            od/kalman/filtering.rs:59-316
+//   ProcessNoise::propagate                                    od/snc.rs:175-286
+//   GroundStation::measure_instantaneous, ScalarSensitivity    od/ground_station/trk_device.rs:154-200, od/msr/sensitivity.rs:118-239
+// The reference gets the partials from forward-mode dual numbers (hyperdual 1.5.0); so does this file, with a 3-partial
+// dual type (only d/d(position) is ever read).
+#include "nyxb_od.cuh"
+
+#ifndef NYXB_STRICT
+#error "NYXB_STRICT must be defined to 0 or 1"
+#endif
+#if NYXB_STRICT
+#define NYXB_KSTM nyxb_k_stm_strict
+#define NYXB_KOD nyxb_k_od_strict
+#define NYXB_LAUNCH_STM nyxb_launch_stm_strict
+#define NYXB_LAUNCH_OD nyxb_launch_od_strict
+#else
+#define NYXB_KSTM nyxb_k_stm_fast
+#define NYXB_KOD nyxb_k_od_fast
+#define NYXB_LAUNCH_STM nyxb_launch_stm_fast
+#define NYXB_LAUNCH_OD nyxb_launch_od_fast
+#endif
+
+// ------------------------------------------------------------------------- dual numbers (value + d/dx, d/dy, d/dz)
+struct D3 { double v, x, y, z; };
+__device__ __forceinline__ D3 dc(double v) { return D3{v, 0.0, 0.0, 0.0}; }
+__device__ __forceinline__ D3 dvar(double v, int i) { return D3{v, i == 0 ? 1.0 : 0.0, i == 1 ? 1.0 : 0.0, i == 2 ? 1.0 : 0.0}; }
+__device__ __forceinline__ D3 operator+(D3 a, D3 b) { return D3{a.v + b.v, a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ D3 operator-(D3 a, D3 b) { return D3{a.v - b.v, a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ D3 operator*(D3 a, D3 b) {
+    return D3{a.v * b.v, b.v * a.x + a.v * b.x, b.v * a.y + a.v * b.y, b.v * a.z + a.v * b.z};
+}
+__device__ __forceinline__ D3 operator/(D3 a, D3 b) {
+    double den = b.v * b.v;
+    return D3{a.v / b.v, (b.v * a.x - a.v * b.x) / den, (b.v * a.y - a.v * b.y) / den, (b.v * a.z - a.v * b.z) / den};
+}
+__device__ __forceinline__ D3 dscale(D3 a, double c) { return D3{a.v * c, a.x * c, a.y * c, a.z * c}; }
+__device__ __forceinline__ D3 ddivs(D3 a, double c) { return D3{a.v / c, a.x / c, a.y / c, a.z / c}; }
+__device__ __forceinline__ D3 dsq(D3 a) { double p = 2.0 * a.v; return D3{a.v * a.v, p * a.x, p * a.y, p * a.z}; }
+__device__ __forceinline__ D3 dcube(D3 a) { double p = 3.0 * (a.v * a.v); return D3{(a.v * a.v) * a.v, p * a.x, p * a.y, p * a.z}; }
+__device__ __forceinline__ D3 dsqrt(D3 a) {
+    double r = sqrt(a.v), dd = 1.0 / (2.0 * r);
+    return D3{r, a.x * dd, a.y * dd, a.z * dd};
+}
+__device__ __forceinline__ D3 dnorm(D3 a, D3 b, D3 c) { return dsqrt(((dc(0.0) + dsq(a)) + dsq(b)) + dsq(c)); }
+__device__ __forceinline__ double dpart(const D3& a, int j) { return j == 0 ? a.x : (j == 1 ? a.y : a.z); }
+
+// ------------------------------------------------------------------------- GravityField::gradient (gravity_field.rs:273-431)
+// rolling rows of the derived-Legendre triangle in dual numbers: P = row n, Q = row n-1 -> row n+1
+__device__ static void grav_gradient(const DevGrav& g, long long t_ns, const double r_in[3], double acc[3], double G[9]) {
+    const int N = g.N, M = g.M;
+    double R[9];
+    rotation_dcm(g.rot, t_ns, R);
+    double rb[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) rb[i] = (R[3 * i] * r_in[0] + R[3 * i + 1] * r_in[1]) + R[3 * i + 2] * r_in[2];
+    D3 rx = dvar(rb[0], 0), ry = dvar(rb[1], 1), rz = dvar(rb[2], 2);
+    D3 r_ = dnorm(rx, ry, rz);
+    D3 s_ = rx / r_, t_ = ry / r_, u_ = rz / r_;
+    D3 rowA[NYXB_MAX_DEGREE + 3], rowB[NYXB_MAX_DEGREE + 3];
+    D3 r_m[NYXB_MAX_DEGREE + 1], i_m[NYXB_MAX_DEGREE + 1];
+    D3* P = rowA;
+    D3* Q = rowB;
+    for (int m = 0; m <= N + 2; ++m) { rowA[m] = dc(0.0); rowB[m] = dc(0.0); }
+    Q[0] = dc(1.0);
+    P[0] = dscale(u_, sqrt(3.0));
+    P[1] = dc(__ldg(g.a_diag + 1));
+    const int mm = N < M ? N : M;
+    r_m[0] = dc(1.0); i_m[0] = dc(0.0);
+    for (int m = 1; m <= mm; ++m) {
+        r_m[m] = s_ * r_m[m - 1] - t_ * i_m[m - 1];
+        i_m[m] = s_ * i_m[m - 1] + t_ * r_m[m - 1];
+    }
+    D3 eq_radius = dc(g.r_eq);
+    D3 rho = eq_radius / r_;
+    D3 rho_np1 = (dc(g.mu) / r_) * rho;
+    D3 a0 = dc(0.0), a1 = dc(0.0), a2 = dc(0.0), a3 = dc(0.0);
+    const D3 sqrt2 = dc(sqrt(2.0));
+    for (int n = 1; n <= N; ++n) {
+        {   // row n+1 into Q (holds row n-1): gravity_field.rs:305-317
+            const int np1 = n + 1;
+            const DevHarm* trow = g.tab + tri(np1, 0);
+            int mrec = np1 - 2;
+            if (mrec > M + 1) mrec = M + 1;
+            for (int m = 0; m <= mrec; ++m) {
+                double bb = __ldg(&trow[m].b), cc = __ldg(&trow[m].c);
+                Q[m] = (u_ * dc(bb)) * P[m] - dc(cc) * Q[m];
+            }
+            for (int m = mrec + 1; m <= np1 - 2; ++m) Q[m] = dc(0.0);
+            Q[n] = (dc(__ldg(g.offdiag + n)) * u_) * dc(__ldg(g.a_diag + n));
+            Q[np1] = dc(__ldg(g.a_diag + np1));
+        }
+        D3 sum0 = dc(0.0), sum1 = dc(0.0), sum2 = dc(0.0), sum3 = dc(0.0);
+        rho_np1 = rho_np1 * rho;
+        const DevHarm* trow = g.tab + tri(n, 0);
+        int mtop = n < M ? n : M;
+        for (int m = 0; m <= mtop; ++m) {
+            D3 cv = dc(__ldg(&trow[m].cbar)), sv = dc(__ldg(&trow[m].sbar));
+            D3 d_ = (cv * r_m[m] + sv * i_m[m]) * sqrt2;
+            D3 e_ = dc(0.0), f_ = dc(0.0);
+            if (m != 0) {
+                e_ = (cv * r_m[m - 1] + sv * i_m[m - 1]) * sqrt2;
+                f_ = (sv * r_m[m - 1] - cv * i_m[m - 1]) * sqrt2;
+            }
+            D3 mf = dc((double)m);
+            sum0 = sum0 + (mf * P[m]) * e_;
+            sum1 = sum1 + (mf * P[m]) * f_;
+            sum2 = sum2 + (dc(__ldg(&trow[m].vr01)) * P[m + 1]) * d_;
+            sum3 = sum3 + (dc(__ldg(&trow[m].vr11)) * Q[m + 1]) * d_;
+        }
+        D3 rr = rho_np1 / eq_radius;
+        a0 = a0 + rr * sum0;
+        a1 = a1 + rr * sum1;
+        a2 = a2 + rr * sum2;
+        a3 = a3 - rr * sum3;
+        D3* tmp = P; P = Q; Q = tmp;
+    }
+    D3 al[3] = { a0 + a3 * s_, a1 + a3 * t_, a2 + a3 * u_ };
+#pragma unroll
+    for (int i = 0; i < 3; ++i) acc[i] = (R[i] * al[0].v + R[3 + i] * al[1].v) + R[6 + i] * al[2].v;
+    double tmp9[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            tmp9[3 * i + j] = (R[i] * dpart(al[0], j) + R[3 + i] * dpart(al[1], j)) + R[6 + i] * dpart(al[2], j);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            G[3 * i + j] = (tmp9[3 * i] * R[j] + tmp9[3 * i + 1] * R[3 + j]) + tmp9[3 * i + 2] * R[6 + j];
+}
+
+// ------------------------------------------------------------------------- dual_eom (spacecraft.rs:312-363)
+// y[9] with Cr already clamped; outputs: acc[3], G[9] = d(acc)/d(r) row-major, gcr[3] = d(acc)/d(Cr)
+__device__ static int dual_eom_dev(const DevSetup& S, long long t_ns, const double y[9], double total_mass, double srp_area,
+                                   double acc[3], double G[9], double gcr[3]) {
+    // OrbitalDynamics::dual_eom, orbital.rs:116-172
+    D3 rad[3] = { dvar(y[0], 0), dvar(y[1], 1), dvar(y[2], 2) };
+    D3 rmag = dnorm(rad[0], rad[1], rad[2]);
+    D3 fac = dc(-S.mu_central) / dcube(rmag);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        D3 ba = rad[i] * fac;
+        acc[i] = ba.v;
+        G[3 * i] = ba.x; G[3 * i + 1] = ba.y; G[3 * i + 2] = ba.z;
+        gcr[i] = 0.0;
+    }
+    double bpos[NYXB_MAX_BODIES][3];
+    for (int j = 0; j < S.n_bodies; ++j)
+        if (!body_position(S.bodies[j], t_ns, bpos[j])) return NYXB_ERR_EPHEMERIS;
+    if (S.point_mass_mask) {  // PointMasses::gradient, orbital.rs:249-307 (r_ij carries identity partials, as coded)
+        double fx[3] = {0.0, 0.0, 0.0}, gp[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int j = 0; j < S.n_bodies; ++j) {
+            if (!((S.point_mass_mask >> j) & 1u)) continue;
+            D3 gm_d = dc(-S.bodies[j].mu);
+            D3 rij[3] = { dvar(bpos[j][0], 0), dvar(bpos[j][1], 1), dvar(bpos[j][2], 2) };
+            D3 rij3 = dcube(dnorm(rij[0], rij[1], rij[2]));
+            D3 rj[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { rj[i] = rad[i] - rij[i]; }
+            rj[0].x = 1.0; rj[1].y = 1.0; rj[2].z = 1.0;
+            D3 rj3 = dcube(dnorm(rj[0], rj[1], rj[2]));
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                D3 t = (rj[i] / rj3 + rij[i] / rij3) * gm_d;
+                fx[i] += t.v;
+                gp[3 * i] += t.x; gp[3 * i + 1] += t.y; gp[3 * i + 2] += t.z;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) acc[i] += fx[i];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) G[q] += gp[q];
+    }
+    if (S.has_grav) {
+        double ga[3], gg[9];
+        grav_gradient(S.grav, t_ns, y, ga, gg);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) acc[i] += ga[i];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) G[q] += gg[q];
+    }
+    if (S.has_srp) {  // SolarPressure::gradient, solarpressure.rs:167-233
+        const double cr = y[6];
+        const double* sun = bpos[S.srp.sun_body];
+        double rs[3] = { y[0] - sun[0], y[1] - sun[1], y[2] - sun[2] };
+        D3 rsd[3] = { dvar(rs[0], 0), dvar(rs[1], 1), dvar(rs[2], 2) };
+        D3 n_d = dnorm(rsd[0], rsd[1], rsd[2]);
+        double occult = 0.0;
+        double r_ls[3] = { -rs[0], -rs[1], -rs[2] };
+        for (int q = 0; q < S.srp.n_shadow; ++q) {
+            int bi = S.srp.shadow_body[q];
+            double r_eb[3], radb;
+            if (bi == NYXB_CENTRAL_BODY) { r_eb[0] = y[0]; r_eb[1] = y[1]; r_eb[2] = y[2]; radb = S.central_radius; }
+            else { r_eb[0] = y[0] - bpos[bi][0]; r_eb[1] = y[1] - bpos[bi][1]; r_eb[2] = y[2] - bpos[bi][2]; radb = S.bodies[bi].radius; }
+            double p = occultation(r_eb, r_ls, S.bodies[S.srp.sun_body].radius, radb);
+            if (p > occult) occult = p;
+        }
+        double k = fabs(occult - 1.0);
+        D3 r_sun_au = ddivs(n_d, NYXB_AU_KM);
+        D3 inv = dc(1.0) / r_sun_au;
+        D3 flux = dc(k * S.srp.phi / NYXB_C_M_S) * dsq(inv);
+        D3 scal = dc(1e-3 * cr * srp_area);
+        double n_sun = norm3(rs[0], rs[1], rs[2]);
+        double r_au = n_sun / NYXB_AU_KM, inv_s = 1.0 / r_au;
+        double flux_s = (k * S.srp.phi / NYXB_C_M_S) * (inv_s * inv_s);
+        double scal_s = 1e-3 * cr * srp_area * flux_s;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            D3 f = (scal * flux) * (rsd[i] / n_d);
+            acc[i] += f.v / total_mass;
+            G[3 * i] += f.x / total_mass; G[3 * i + 1] += f.y / total_mass; G[3 * i + 2] += f.z / total_mass;
+            if (S.srp.estimate) gcr[i] += ((scal_s * (rs[i] / n_sun)) / cr) / total_mass;
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------- PropInstance over state + STM
+struct InstS {
+    double y[9];
+    double phi[81];  // column-major like the reference's vector tail: (r, c) at c*9 + r
+    long long epoch_ns, step_ns;
+    int fixed, status;
+    long long det_step_ns;
+    double det_error;
+    int det_attempts;
+    long long n_steps, n_rejected, n_rhs;
+    double dry_mass, extra_mass, srp_area;
+};
+
+__device__ __forceinline__ void phi_identity(double* phi) {
+    for (int e = 0; e < 81; ++e) phi[e] = 0.0;
+    for (int c = 0; c < 9; ++c) phi[c * 9 + c] = 1.0;
+}
+
+// one RHS evaluation: k[6] = (v, a), A-parts G[9], gcr[3]
+__device__ static int eom_stm(const DevSetup& S, InstS& in, double delta_t_s, const double ys[9], double k[6], double G[9], double gcr[3]) {
+    long long t_ns = in.epoch_ns + dur_from_seconds(delta_t_s);
+    double yy[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) yy[e] = ys[e];
+    yy[6] = yy[6] < 0.0 ? 0.0 : (yy[6] > 2.0 ? 2.0 : yy[6]);
+    double mass = in.dry_mass + yy[8] + in.extra_mass;
+    if (S.has_srp && !(mass > 0.0)) return NYXB_ERR_MASSLESS;
+    double acc[3];
+    int rc = dual_eom_dev(S, t_ns, yy, mass, in.srp_area, acc, G, gcr);
+    in.n_rhs++;
+    if (rc) return rc;
+    k[0] = yy[3]; k[1] = yy[4]; k[2] = yy[5];
+    k[3] = acc[0]; k[4] = acc[1]; k[5] = acc[2];
+    return 0;
+}
+
+// instance.rs:358-493 on the 90-vector; stage STM derivative = ctx.stm * A_i (spacecraft.rs:213) with ctx = step start
+__device__ static int derive_stm(const DevSetup& S, InstS& in, long long& dt_ns, double next[9], double next_phi[81]) {
+    double k[NYXB_MAX_STAGES][6];
+    double Ai[NYXB_MAX_STAGES][12];
+    const int stages = S.tb.stages;
+    in.det_attempts = 1;
+    double h = dur_to_seconds(in.step_ns);
+    for (;;) {
+        int rc = eom_stm(S, in, 0.0, in.y, k[0], Ai[0], Ai[0] + 9);
+        if (rc) return rc;
+        for (int i = 0; i < stages - 1; ++i) {
+            double wi[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            const double* arow = &S.tb.a[i * NYXB_MAX_STAGES];
+            for (int j = 0; j <= i; ++j) {
+                double a_ij = arow[j];
+#if !NYXB_STRICT
+                if (a_ij == 0.0) continue;
+#endif
+#pragma unroll
+                for (int e = 0; e < 6; ++e) wi[e] += a_ij * k[j][e];
+            }
+            double ys[9];
+#pragma unroll
+            for (int e = 0; e < 6; ++e) ys[e] = in.y[e] + h * wi[e];
+            const double hz = h * 0.0;
+            ys[6] = in.y[6] + hz; ys[7] = in.y[7] + hz; ys[8] = in.y[8] + hz;
+            rc = eom_stm(S, in, S.tb.c[i] * h, ys, k[i + 1], Ai[i + 1], Ai[i + 1] + 9);
+            if (rc) return rc;
+        }
+        double err_est[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int e = 0; e < 9; ++e) next[e] = in.y[e];
+        { const double hz = h * 0.0; next[6] += hz; next[7] += hz; next[8] += hz; }
+        for (int e = 0; e < 81; ++e) next_phi[e] = in.phi[e];
+        for (int i = 0; i < stages; ++i) {
+            if (!in.fixed) {
+                double cf = h * S.tb.e[i];
+#pragma unroll
+                for (int e = 0; e < 6; ++e) err_est[e] += cf * k[i][e];
+            }
+            double cb = h * S.tb.b[i];
+#pragma unroll
+            for (int e = 0; e < 6; ++e) next[e] += cb * k[i][e];
+            // (phi * A_i)(r, c): c < 3: sum_q phi(r, 3+q) G(q, c); 3 <= c < 6: phi(r, c-3); c == 6: sum_q phi(r, 3+q) gcr(q)
+            const double* Gi = Ai[i];
+            for (int r = 0; r < 9; ++r) {
+                double p3 = in.phi[27 + r], p4 = in.phi[36 + r], p5 = in.phi[45 + r];
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    next_phi[c * 9 + r] += cb * ((p3 * Gi[c] + p4 * Gi[3 + c]) + p5 * Gi[6 + c]);
+#pragma unroll
+                for (int c = 3; c < 6; ++c) next_phi[c * 9 + r] += cb * in.phi[(c - 3) * 9 + r];
+                next_phi[54 + r] += cb * ((p3 * Gi[9] + p4 * Gi[10]) + p5 * Gi[11]);
+            }
+        }
+        if (in.fixed) {
+            in.det_step_ns = in.step_ns;
+            dt_ns = in.step_ns;
+            return 0;
+        }
+        in.det_error = error_estimate(S.error_ctrl, err_est, next, in.y);
+        if (in.det_error <= S.tolerance || h <= S.min_step_s || in.det_attempts >= S.attempts) {
+            for (int e = 0; e < 9; ++e)
+                if (next[e] != next[e]) return NYXB_ERR_PROP_MATH;
+            for (int e = 0; e < 81; ++e)
+                if (next_phi[e] != next_phi[e]) return NYXB_ERR_PROP_MATH;
+            if (in.det_attempts >= S.attempts) in.status |= NYXB_WARN_MAX_ATTEMPTS;
+            in.det_step_ns = dur_from_seconds(h);
+            if (in.det_error < S.tolerance) {
+                double proposed = 0.9 * h * pow_inv_int(S.tolerance / in.det_error, S.tb.order);
+                if (fabs(proposed) > fabs(S.max_step_s)) {
+                    double sg = (proposed != proposed) ? proposed : (signbit(proposed) ? -1.0 : 1.0);
+                    h = S.max_step_s * sg;
+                } else {
+                    h = proposed;
+                }
+            }
+            in.step_ns = dur_from_seconds(h);
+            long long ab = in.step_ns < 0 ? -in.step_ns : in.step_ns;
+            if (ab < S.min_step_ns) in.step_ns = (in.step_ns < 0) ? -S.min_step_ns : S.min_step_ns;
+            dt_ns = in.det_step_ns;
+            return 0;
+        }
+        in.det_attempts += 1;
+        in.n_rejected += 1;
+        double proposed = 0.9 * h * pow_inv_int(S.tolerance / in.det_error, S.tb.order - 1);
+        h = (proposed < S.min_step_s) ? S.min_step_s : proposed;
+    }
+}
+
+__device__ static int single_step_stm(const DevSetup& S, InstS& in) {
+    long long dt;
+    double next[9], next_phi[81];
+    int rc = derive_stm(S, in, dt, next, next_phi);
+    if (rc) return rc;
+    in.epoch_ns += dt;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) in.y[e] = next[e];
+    for (int e = 0; e < 81; ++e) in.phi[e] = next_phi[e];
+    in.y[6] = in.y[6] < 0.0 ? 0.0 : (in.y[6] > 2.0 ? 2.0 : in.y[6]);
+    in.n_steps += 1;
+    return (in.y[8] < 0.0) ? NYXB_ERR_FUEL_EXHAUSTED : 0;
+}
+
+__device__ static int propagate_stm(const DevSetup& S, InstS& in, long long duration_ns) {
+    if (duration_ns == 0) return 0;
+    long long stop = in.epoch_ns + duration_ns;
+    if (in.y[8] < 0.0) return NYXB_ERR_FUEL_EXHAUSTED;
+    bool backprop = duration_ns < 0;
+    if (backprop) in.step_ns = -in.step_ns;
+    for (;;) {
+        long long epoch = in.epoch_ns;
+        if ((!backprop && epoch + in.step_ns > stop) || (backprop && epoch + in.step_ns <= stop)) {
+            if (stop == epoch) return 0;
+            long long prev_step = in.step_ns;
+            int prev_fixed = in.fixed;
+            in.step_ns = stop - epoch;
+            in.fixed = 1;
+            int rc = single_step_stm(S, in);
+            if (rc) return rc;
+            in.step_ns = prev_step;
+            in.fixed = prev_fixed;
+            if (backprop) in.step_ns = -in.step_ns;
+            return 0;
+        }
+        int rc = single_step_stm(S, in);
+        if (rc) return rc;
+    }
+}
+
+__device__ __forceinline__ void inst_load(const DevSetup& S, InstS& in, size_t i, size_t n, const double* state, const double* consts,
+                                          const long long* epoch0, const long long* step_io) {
+#pragma unroll
+    for (int e = 0; e < 9; ++e) in.y[e] = state[(size_t)e * n + i];
+    in.dry_mass = consts[i]; in.extra_mass = consts[n + i]; in.srp_area = consts[2 * n + i];
+    in.epoch_ns = epoch0[i];
+    in.step_ns = step_io ? step_io[i] : S.init_step_ns;
+    in.fixed = S.fixed_step;
+    in.status = 0;
+    in.det_step_ns = S.init_step_ns; in.det_error = 0.0; in.det_attempts = 1;
+    in.n_steps = 0; in.n_rejected = 0; in.n_rhs = 0;
+}
+
+__device__ __forceinline__ void inst_store(const InstS& in, int rc, size_t i, size_t n, double* out_state, long long* out_epoch,
+                                           nyxb_details* out_details, int* out_status) {
+#pragma unroll
+    for (int e = 0; e < 9; ++e) out_state[(size_t)e * n + i] = in.y[e];
+    out_epoch[i] = in.epoch_ns;
+    if (out_details) {
+        nyxb_details d;
+        d.step_ns = in.det_step_ns; d.error = in.det_error; d.attempts = in.det_attempts; d._pad = 0;
+        d.n_steps = in.n_steps; d.n_rejected = in.n_rejected; d.n_rhs = in.n_rhs;
+        out_details[i] = d;
+    }
+    out_status[i] = (in.status & NYXB_WARN_MAX_ATTEMPTS) | rc;
+}
+
+__global__ void __launch_bounds__(64)
+NYXB_KSTM(const __grid_constant__ DevSetup S, size_t n, const double* __restrict__ state, const double* __restrict__ consts,
+          const long long* __restrict__ epoch0, long long end_epoch, long long* __restrict__ step_io,
+          const double* __restrict__ stm_in, double* __restrict__ out_state, long long* __restrict__ out_epoch,
+          double* __restrict__ out_stm, nyxb_details* __restrict__ out_details, int* __restrict__ out_status) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    InstS in;
+    inst_load(S, in, i, n, state, consts, epoch0, step_io);
+    if (stm_in) { for (int e = 0; e < 81; ++e) in.phi[e] = stm_in[(size_t)e * n + i]; }
+    else phi_identity(in.phi);
+    int rc = propagate_stm(S, in, end_epoch - in.epoch_ns);
+    for (int e = 0; e < 81; ++e) out_stm[(size_t)e * n + i] = in.phi[e];
+    if (step_io) step_io[i] = in.step_ns;
+    inst_store(in, rc, i, n, out_state, out_epoch, out_details, out_status);
+}
+
+// ------------------------------------------------------------------------- tracking geometry
+// d/dt of the Chebyshev ephemeris: sum_k c_k k U_{k-1}(tau) * 2 / interval
+__device__ static bool body_velocity(const DevBody& b, long long t_ns, double vel[3]) {
+    long long dt = t_ns - b.t0_ns;
+    if (dt < 0) return false;
+    long long idx = dt / b.interval_ns;
+    if (idx >= b.n_intervals) return false;
+    long long off = dt - idx * b.interval_ns;
+    double tau = 2.0 * ((double)off / (double)b.interval_ns) - 1.0;
+    double tau2 = 2.0 * tau;
+    int nc = b.n_coeffs;
+    const double* c = b.coeffs + (size_t)idx * 3 * (size_t)nc;
+    double scale = 2.0 / ((double)b.interval_ns * 1e-9);
+    for (int ax = 0; ax < 3; ++ax) {
+        const double* ca = c + ax * nc;
+        double b1 = 0.0, b2 = 0.0;
+        for (int j = nc - 2; j >= 0; --j) {
+            double bj = ((double)(j + 1) * __ldg(ca + j + 1) + tau2 * b1) - b2;
+            b2 = b1; b1 = bj;
+        }
+        vel[ax] = b1 * scale;
+    }
+    return true;
+}
+
+// trk_device.rs:150-152 `location`: antenna position / velocity in the integration frame and the inertial zenith
+__device__ static bool station_state(const DevSetup& S, const DevStation& st, long long t_ns, double r[3], double v[3], double up[3]) {
+    double R[9];
+    rotation_dcm(st.rot, t_ns, R);
+    const double wdot = st.rot.kind ? st.rot.wdot : 0.0;
+    double vf[3] = { -(wdot * st.pos[1]), wdot * st.pos[0], 0.0 };
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        r[i] = (R[i] * st.pos[0] + R[3 + i] * st.pos[1]) + R[6 + i] * st.pos[2];
+        v[i] = (R[i] * vf[0] + R[3 + i] * vf[1]) + R[6 + i] * vf[2];
+        up[i] = (R[i] * st.up[0] + R[3 + i] * st.up[1]) + R[6 + i] * st.up[2];
+    }
+    if (st.body != NYXB_CENTRAL_BODY) {
+        double bp[3], bv[3];
+        if (!body_position(S.bodies[st.body], t_ns, bp) || !body_velocity(S.bodies[st.body], t_ns, bv)) return false;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { r[i] += bp[i]; v[i] += bv[i]; }
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------- 9x9 helpers (row-major)
+__device__ static void mat9_mul(const double* A, const double* B, double* Cm) {  // C = A B
+    for (int r = 0; r < 9; ++r)
+        for (int c = 0; c < 9; ++c) {
+            double s = 0.0;
+            for (int k = 0; k < 9; ++k) s += A[r * 9 + k] * B[k * 9 + c];
+            Cm[r * 9 + c] = s;
+        }
+}
+__device__ static void mat9_mul_bt(const double* A, const double* B, double* Cm) {  // C = A B^T
+    for (int r = 0; r < 9; ++r)
+        for (int c = 0; c < 9; ++c) {
+            double s = 0.0;
+            for (int k = 0; k < 9; ++k) s += A[r * 9 + k] * B[c * 9 + k];
+            Cm[r * 9 + c] = s;
+        }
+}
+
+struct Filt {
+    double P[81];      // covariance, row-major
+    double xdev[9];    // state deviation (CKF)
+    long long prev_epoch;
+};
+
+// ProcessNoise::propagate (snc.rs:211-286) added onto Pbar
+__device__ static void add_snc(const DevOd& od, const InstS& in, const Filt& f, double* Pbar) {
+    if (!od.snc_enabled) return;
+    long long delta = in.epoch_ns - f.prev_epoch;
+    if (delta > od.snc_disable_ns) return;
+    double s[3] = { od.snc_diag[0], od.snc_diag[1], od.snc_diag[2] };
+    if (od.snc_frame == 1) {  // RIC: rotate, keep the diagonal (snc.rs:226-247)
+        const double* y = in.y;
+        double rn = norm3(y[0], y[1], y[2]);
+        double rh[3] = { y[0] / rn, y[1] / rn, y[2] / rn };
+        double hx = y[1] * y[5] - y[2] * y[4], hy = y[2] * y[3] - y[0] * y[5], hz = y[0] * y[4] - y[1] * y[3];
+        double hn = norm3(hx, hy, hz);
+        double ch[3] = { hx / hn, hy / hn, hz / hn };
+        double ih[3] = { ch[1] * rh[2] - ch[2] * rh[1], ch[2] * rh[0] - ch[0] * rh[2], ch[0] * rh[1] - ch[1] * rh[0] };
+        double d[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) d[i] = ((rh[i] * s[0]) * rh[i] + (ih[i] * s[1]) * ih[i]) + (ch[i] * s[2]) * ch[i];
+        s[0] = d[0]; s[1] = d[1]; s[2] = d[2];
+    }
+    double dt = dur_to_seconds(delta);
+    double g1 = (dt * dt) / 2.0, g2 = dt;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        Pbar[i * 9 + i] += (g1 * s[i]) * g1;
+        Pbar[i * 9 + 3 + i] += (g1 * s[i]) * g2;
+        Pbar[(3 + i) * 9 + i] += (g2 * s[i]) * g1;
+        Pbar[(3 + i) * 9 + 3 + i] += (g2 * s[i]) * g2;
+    }
+}
+
+// covar_bar = stm * P * stm^T (+ SNC); filtering.rs:61-78 / 132-150
+__device__ static void covar_bar(const DevOd& od, const InstS& in, const Filt& f, double* Pbar) {
+    double Phi[81], T[81];
+    for (int r = 0; r < 9; ++r)
+        for (int c = 0; c < 9; ++c) Phi[r * 9 + c] = in.phi[c * 9 + r];
+    mat9_mul(Phi, f.P, T);
+    mat9_mul_bt(T, Phi, Pbar);
+    add_snc(od, in, f, Pbar);
+}
+
+// KalmanFilter::time_update, filtering.rs:59-102
+__device__ static void time_update(const DevOd& od, const InstS& in, Filt& f) {
+    double Pbar[81];
+    covar_bar(od, in, f, Pbar);
+    if (od.variant == NYXB_KF_DEVIATION_TRACKING) {
+        double nx[9];
+        for (int r = 0; r < 9; ++r) {
+            double s = 0.0;
+            for (int k = 0; k < 9; ++k) s += in.phi[k * 9 + r] * f.xdev[k];
+            nx[r] = s;
+        }
+        for (int r = 0; r < 9; ++r) f.xdev[r] = nx[r];
+    } else {
+        for (int r = 0; r < 9; ++r) f.xdev[r] = 0.0;
+    }
+    for (int e = 0; e < 81; ++e) f.P[e] = Pbar[e];
+    f.prev_epoch = in.epoch_ns;
+}
+
+__global__ void __launch_bounds__(64)
+NYXB_KOD(const __grid_constant__ DevSetup S, const __grid_constant__ DevOd od, size_t n, const double* __restrict__ state,
+         const double* __restrict__ consts, const long long* __restrict__ epoch0, double* __restrict__ out_state,
+         long long* __restrict__ out_epoch, nyxb_details* __restrict__ out_details, int* __restrict__ out_status) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    InstS in;
+    inst_load(S, in, i, n, state, consts, epoch0, nullptr);
+    phi_identity(in.phi);                                    // prop.with(nominal.with_stm()) process/mod.rs:167
+    if (!in.fixed) in.step_ns = od.max_step_ns;              // :170-172
+    Filt f;
+    for (int r = 0; r < 9; ++r)
+        for (int c = 0; c < 9; ++c) f.P[r * 9 + c] = od.covar0[(size_t)(c * 9 + r) * n + i];
+    for (int r = 0; r < 9; ++r) f.xdev[r] = 0.0;
+    f.prev_epoch = in.epoch_ns;
+    long long epoch = in.epoch_ns;
+    int rc = 0;
+    const bool ekf = od.variant == NYXB_KF_REFERENCE_UPDATE;
+    const int M = od.msr_size;
+    for (long long k = 0; k < od.n_msr && rc == 0; ++k) {
+        const long long t_k = od.msr_epoch[k];
+        const double o[2] = { od.obs[((size_t)k * 2 + 0) * n + i], od.obs[((size_t)k * 2 + 1) * n + i] };
+        int flags = 0;
+        if (o[0] != o[0] && o[1] != o[1]) {
+            if (od.flags) od.flags[(size_t)k * n + i] = NYXB_MSRF_ABSENT;
+            continue;
+        }
+        for (;;) {
+            long long delta_t = t_k - epoch;
+            long long next_step = delta_t;                                      // :218
+            if (in.step_ns < next_step) next_step = in.step_ns;
+            if (od.max_step_ns < next_step) next_step = od.max_step_ns;
+            rc = propagate_stm(S, in, next_step);                               // :232-234
+            if (rc) break;
+            epoch = in.epoch_ns;
+            long long gap = in.epoch_ns - t_k;
+            if (gap < 0) gap = -gap;
+            if (gap < od.eps_ns) {                                              // :250
+                in.epoch_ns = t_k;                                              // :254
+                const int trk = od.msr_tracker[k];
+                if (trk < 0 || trk >= od.n_stations) break;                     // unknown tracker :400-410
+                const DevStation& gs = od.stations[trk];
+                const int windows = gs.n_types / M;
+                for (int wno = 0; wno <= windows; ++wno) {                      // :270-398
+                    int cur[2], ncur = 0;
+                    for (int q = wno * M; q < (wno + 1) * M && q < gs.n_types; ++q) cur[ncur++] = gs.types[q];
+                    if (ncur == 0) break;
+                    bool avail[2] = { false, false }, any = false;
+                    for (int q = 0; q < ncur; ++q) { avail[q] = (o[cur[q]] == o[cur[q]]); any = any || avail[q]; }
+                    if (!any) continue;
+                    double real_obs[2] = { 0.0, 0.0 };
+                    for (int q = 0; q < ncur; ++q) if (avail[q]) real_obs[q] = o[cur[q]];
+                    // geometry: transmitter state, range, range rate, elevation, obstruction
+                    double r_tx[3], v_tx[3], up[3];
+                    if (!station_state(S, gs, t_k, r_tx, v_tx, up)) { rc = NYXB_ERR_EPHEMERIS; break; }
+                    const double dr[3] = { in.y[0] - r_tx[0], in.y[1] - r_tx[1], in.y[2] - r_tx[2] };
+                    const double dv[3] = { in.y[3] - v_tx[0], in.y[4] - v_tx[1], in.y[5] - v_tx[2] };
+                    const double rng = sqrt((dr[0] * dr[0] + dr[1] * dr[1]) + dr[2] * dr[2]);
+                    const double rr = ((dr[0] * dv[0] + dr[1] * dv[1]) + dr[2] * dv[2]) / rng;
+                    const double elev = asin(((dr[0] * up[0] + dr[1] * up[1]) + dr[2] * up[2]) / rng) * (180.0 / 3.14159265358979323846);
+                    bool visible = !(elev - gs.mask_deg < 0.0);
+                    if (visible && gs.body != NYXB_CENTRAL_BODY && gs.body_radius > 0.0) {   // Vallado SIGHT (anise line_of_sight_obstructed)
+                        double r1sq = (in.y[0] * in.y[0] + in.y[1] * in.y[1]) + in.y[2] * in.y[2];
+                        double r2sq = (r_tx[0] * r_tx[0] + r_tx[1] * r_tx[1]) + r_tx[2] * r_tx[2];
+                        double r12 = (in.y[0] * r_tx[0] + in.y[1] * r_tx[1]) + in.y[2] * r_tx[2];
+                        double tau = (r1sq - r12) / (r1sq + r2sq - 2.0 * r12);
+                        if (tau >= 0.0 && tau <= 1.0 && (1.0 - tau) * r1sq + r12 * tau <= gs.body_radius * gs.body_radius) visible = false;
+                    }
+                    if (!visible) { flags |= NYXB_MSRF_NOT_VISIBLE; continue; }  // :386-392
+                    // h_tilde (sensitivity.rs:88-239): identity rows unless the type is in msr.data
+                    double H[2][9];
+                    for (int q = 0; q < 2; ++q)
+                        for (int c = 0; c < 9; ++c) H[q][c] = (q == c) ? 1.0 : 0.0;
+                    double Rk[2] = { 0.0, 0.0 }, comp[2] = { 0.0, 0.0 };
+                    for (int q = 0; q < ncur; ++q) {
+                        int slot = wno * M + q;  // position of the type in the device's list
+                        Rk[q] = gs.noise_var[slot];
+                        comp[q] = ((cur[q] == NYXB_MSR_RANGE) ? rng : rr) - gs.bias[slot];
+                        if (!avail[q]) continue;
+                        if (cur[q] == NYXB_MSR_DOPPLER) {
+                            double rho = rng, rho_dot = o[NYXB_MSR_DOPPLER], rho2 = rho * rho;
+                            H[q][0] = dv[0] / rho - rho_dot * dr[0] / rho2;
+                            H[q][1] = dv[1] / rho - rho_dot * dr[1] / rho2;
+                            H[q][2] = dv[2] / rho - rho_dot * dr[2] / rho2;
+                            H[q][3] = dr[0] / rho; H[q][4] = dr[1] / rho; H[q][5] = dr[2] / rho;
+                            H[q][6] = 0.0; H[q][7] = 0.0; H[q][8] = 0.0;
+                        } else {
+                            double rho = o[NYXB_MSR_RANGE];
+                            H[q][0] = dr[0] / rho; H[q][1] = dr[1] / rho; H[q][2] = dr[2] / rho;
+                            for (int c = 3; c < 9; ++c) H[q][c] = 0.0;
+                        }
+                    }
+                    // ---- measurement_update (filtering.rs:107-316)
+                    double Pbar[81];
+                    covar_bar(od, in, f, Pbar);
+                    double PHt[9][2], Sk[2][2] = { {0.0, 0.0}, {0.0, 0.0} }, pre[2] = { 0.0, 0.0 };
+                    for (int r = 0; r < 9; ++r)
+                        for (int q = 0; q < M; ++q) {
+                            double s = 0.0;
+                            for (int c = 0; c < 9; ++c) s += Pbar[r * 9 + c] * H[q][c];
+                            PHt[r][q] = s;
+                        }
+                    for (int a = 0; a < M; ++a)
+                        for (int b = 0; b < M; ++b) {
+                            double s = 0.0;
+                            for (int c = 0; c < 9; ++c) s += H[a][c] * PHt[c][b];
+                            Sk[a][b] = s + ((a == b) ? Rk[a] : 0.0);
+                        }
+                    for (int q = 0; q < M; ++q) pre[q] = real_obs[q] - comp[q];
+                    // Cholesky of S (fallback: of R), whitened residual, ratio
+                    double L00, L10 = 0.0, L11 = 1.0;
+                    bool chol_ok = Sk[0][0] > 0.0;
+                    if (chol_ok) {
+                        L00 = sqrt(Sk[0][0]);
+                        if (M == 2) {
+                            L10 = Sk[1][0] / L00;
+                            double d = Sk[1][1] - L10 * L10;
+                            if (d > 0.0) L11 = sqrt(d); else chol_ok = false;
+                        }
+                    }
+                    double W00 = L00, W10 = L10, W11 = L11;
+                    if (!chol_ok) {
+                        if (!(Rk[0] > 0.0) || (M == 2 && !(Rk[1] > 0.0))) { rc = NYXB_ERR_PROP_MATH; break; }  // SingularNoiseRk
+                        W00 = sqrt(Rk[0]); W10 = 0.0; W11 = (M == 2) ? sqrt(Rk[1]) : 1.0;
+                    }
+                    double w0 = pre[0] / W00, w1 = (M == 2) ? (pre[1] - W10 * w0) / W11 : 0.0;
+                    double ratio = sqrt(((M == 2) ? (w0 * w0 + w1 * w1) : (w0 * w0)) / (double)M);
+                    const int rslot = (M == 1) ? wno : 0;
+                    if (od.ratio) od.ratio[((size_t)k * 2 + rslot) * n + i] = ratio;
+                    if (od.prefit) for (int q = 0; q < ncur; ++q) od.prefit[((size_t)k * 2 + wno * M + q) * n + i] = pre[q];
+                    flags |= NYXB_MSRF_PROCESSED;
+                    if (od.reject >= 0.0 && ratio > od.reject) {                // :169-184
+                        time_update(od, in, f);
+                        flags |= NYXB_MSRF_REJECTED;
+                    } else {
+                        // gain K = PHt S^-1 (Cholesky solve; plain inverse when S is not positive definite)
+                        double Si[2][2];
+                        if (M == 1) { Si[0][0] = 1.0 / Sk[0][0]; Si[0][1] = Si[1][0] = 0.0; Si[1][1] = 0.0; }
+                        else {
+                            double det = Sk[0][0] * Sk[1][1] - Sk[0][1] * Sk[1][0];
+                            if (det == 0.0 || det != det) { rc = NYXB_ERR_PROP_MATH; break; }       // SingularKalmanGain
+                            Si[0][0] = Sk[1][1] / det; Si[0][1] = -Sk[0][1] / det; Si[1][0] = -Sk[1][0] / det; Si[1][1] = Sk[0][0] / det;
+                        }
+                        double K[9][2];
+                        for (int r = 0; r < 9; ++r)
+                            for (int q = 0; q < M; ++q) {
+                                double s = 0.0;
+                                for (int b = 0; b < M; ++b) s += PHt[r][b] * Si[b][q];
+                                K[r][q] = s;
+                            }
+                        double xhat[9], post[2] = { 0.0, 0.0 };
+                        if (ekf) {
+                            for (int r = 0; r < 9; ++r) { double s = 0.0; for (int q = 0; q < M; ++q) s += K[r][q] * pre[q]; xhat[r] = s; }
+                            for (int q = 0; q < M; ++q) { double s = 0.0; for (int c = 0; c < 9; ++c) s += H[q][c] * xhat[c]; post[q] = pre[q] - s; }
+                        } else {
+                            double xbar[9];
+                            for (int r = 0; r < 9; ++r) { double s = 0.0; for (int c = 0; c < 9; ++c) s += in.phi[c * 9 + r] * f.xdev[c]; xbar[r] = s; }
+                            for (int q = 0; q < M; ++q) { double s = 0.0; for (int c = 0; c < 9; ++c) s += H[q][c] * xbar[c]; post[q] = pre[q] - s; }
+                            for (int r = 0; r < 9; ++r) { double s = 0.0; for (int q = 0; q < M; ++q) s += K[r][q] * post[q]; xhat[r] = xbar[r] + s; }
+                        }
+                        // Joseph update: (I - K H) Pbar (I - K H)^T + K R K^T, then symmetrise (filtering.rs:290-300)
+                        double F[81], T[81], Cv[81];
+                        for (int r = 0; r < 9; ++r)
+                            for (int c = 0; c < 9; ++c) {
+                                double s = 0.0;
+                                for (int q = 0; q < M; ++q) s += K[r][q] * H[q][c];
+                                F[r * 9 + c] = ((r == c) ? 1.0 : 0.0) - s;
+                            }
+                        mat9_mul(F, Pbar, T);
+                        mat9_mul_bt(T, F, Cv);
+                        for (int r = 0; r < 9; ++r)
+                            for (int c = 0; c < 9; ++c) {
+                                double s = 0.0;
+                                for (int q = 0; q < M; ++q) s += (K[r][q] * Rk[q]) * K[c][q];
+                                Cv[r * 9 + c] += s;
+                            }
+                        for (int r = 0; r < 9; ++r)
+                            for (int c = 0; c < 9; ++c) f.P[r * 9 + c] = 0.5 * (Cv[r * 9 + c] + Cv[c * 9 + r]);
+                        for (int r = 0; r < 9; ++r) f.xdev[r] = xhat[r];
+                        f.prev_epoch = in.epoch_ns;
+                        if (od.postfit) for (int q = 0; q < ncur; ++q) od.postfit[((size_t)k * 2 + wno * M + q) * n + i] = post[q];
+                        if (ekf) {                                               // :364-369 `Spacecraft + OVector<9>`
+                            for (int r = 0; r < 9; ++r) in.y[r] = in.y[r] + xhat[r];
+                            in.y[6] = in.y[6] < 0.0 ? 0.0 : (in.y[6] > 2.0 ? 2.0 : in.y[6]);
+                        }
+                    }
+                    phi_identity(in.phi);                                        // reset_stm :371
+                }
+                if (od.est_state) for (int r = 0; r < 9; ++r) od.est_state[((size_t)k * 9 + r) * n + i] = in.y[r];
+                if (od.est_cov) for (int r = 0; r < 9; ++r) od.est_cov[((size_t)k * 9 + r) * n + i] = f.P[r * 9 + r];
+                break;
+            } else {
+                time_update(od, in, f);                                          // :417-421
+                phi_identity(in.phi);
+            }
+        }
+        if (od.flags) od.flags[(size_t)k * n + i] = flags;
+    }
+    for (int r = 0; r < 9; ++r)
+        for (int c = 0; c < 9; ++c) od.covar[(size_t)(c * 9 + r) * n + i] = f.P[r * 9 + c];
+    if (od.state_dev) for (int r = 0; r < 9; ++r) od.state_dev[(size_t)r * n + i] = f.xdev[r];
+    inst_store(in, rc, i, n, out_state, out_epoch, out_details, out_status);
+}
+
+extern "C" cudaError_t NYXB_LAUNCH_STM(const DevSetup* S, size_t n, const double* state, const double* consts, const long long* epoch0,
+                                       long long end_epoch, long long* step_io, const double* stm_in, double* out_state,
+                                       long long* out_epoch, double* out_stm, nyxb_details* out_details, int* out_status,
+                                       cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const int block = 32;
+    unsigned grid = (unsigned)((n + block - 1) / block);
+    NYXB_KSTM<<<grid, block, 0, stream>>>(*S, n, state, consts, epoch0, end_epoch, step_io, stm_in, out_state, out_epoch, out_stm,
+                                          out_details, out_status);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t NYXB_LAUNCH_OD(const DevSetup* S, const DevOd* od, size_t n, const double* state, const double* consts,
+                                      const long long* epoch0, double* out_state, long long* out_epoch, nyxb_details* out_details,
+                                      int* out_status, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const int block = 32;  // few, long-running threads: spread them over as many SMs as possible
+    unsigned grid = (unsigned)((n + block - 1) / block);
+    NYXB_KOD<<<grid, block, 0, stream>>>(*S, *od, n, state, consts, epoch0, out_state, out_epoch, out_details, out_status);
+    return cudaGetLastError();
+}

@@ -56,6 +56,7 @@ class Frame:
     mu: Optional[float] = None  # km^3/s^2
     radius_km: Optional[float] = None  # mean equatorial radius
     rotation: Optional[Rotation] = None  # None: inertial (J2000 axes)
+    polar_radius_km: Optional[float] = None  # ellipsoid shape for geodetic coordinates (None: sphere)
 
     def mu_km3_s2(self) -> float:
         if self.mu is None:
@@ -82,7 +83,7 @@ SUN_J2000 = Frame("Sun J2000", SUN, 132712440041.27942, 696000.0)
 EARTH_J2000 = Frame("Earth J2000", EARTH, 398600.435436096, 6378.14)
 MOON_J2000 = Frame("Moon J2000", MOON, 4902.800066163796, 1737.4)
 JUPITER_BARYCENTER_J2000 = Frame("Jupiter Barycenter J2000", JUPITER_BARYCENTER, 126712764.09999998, 71492.0)
-IAU_EARTH_FRAME = Frame("IAU Earth", EARTH, 398600.435436096, 6378.14, IAU_EARTH_ROTATION)
+IAU_EARTH_FRAME = Frame("IAU Earth", EARTH, 398600.435436096, 6378.14, IAU_EARTH_ROTATION, 6356.75)  # pck00008 radii
 IAU_MOON_FRAME = Frame("IAU Moon", MOON, 4902.800066163796, 1737.4, IAU_MOON_ROTATION)
 
 _FRAMES = {f.ephemeris_id: f for f in (SUN_J2000, EARTH_J2000, MOON_J2000, JUPITER_BARYCENTER_J2000)}

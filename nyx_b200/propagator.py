@@ -233,6 +233,70 @@ class Engine:
             ret = ret + (crossings,)
         return ret
 
+    def propagate_batch_stm(self, state_soa, consts_soa, epoch0_ns, end_epoch_ns, stm_in=None, step_ns=None):
+        """`nyxb_propagate_batch_stm`: `Spacecraft::with_stm()` + propagate (spacecraft.rs:203-227, 312-363).
+        Returns (state[9][n], epoch[n], stm[81][n] column-major per trajectory, details, status)."""
+        state_soa = np.ascontiguousarray(state_soa, dtype=np.float64)
+        consts_soa = np.ascontiguousarray(consts_soa, dtype=np.float64)
+        epoch0_ns = np.ascontiguousarray(epoch0_ns, dtype=np.int64)
+        n = state_soa.shape[1]
+        if state_soa.shape != (9, n) or consts_soa.shape != (4, n) or epoch0_ns.shape != (n,):
+            raise ValueError("expected state[9][n], consts[4][n], epoch0[n]")
+        if stm_in is not None:
+            stm_in = np.ascontiguousarray(stm_in, dtype=np.float64)
+            if stm_in.shape != (81, n):
+                raise ValueError("expected stm_in[81][n]")
+        out_state = np.empty((9, n))
+        out_epoch = np.empty(n, dtype=np.int64)
+        out_stm = np.empty((81, n))
+        details = np.zeros(n, dtype=abi.DETAILS_DTYPE)
+        status = np.zeros(n, dtype=np.int32)
+        rc = self._lib.nyxb_propagate_batch_stm(
+            self._h, n, state_soa.ctypes.data, consts_soa.ctypes.data, epoch0_ns.ctypes.data, int(end_epoch_ns),
+            step_ns.ctypes.data if step_ns is not None else None, stm_in.ctypes.data if stm_in is not None else None,
+            out_state.ctypes.data, out_epoch.ctypes.data, out_stm.ctypes.data, details.ctypes.data, status.ctypes.data)
+        if rc != 0:
+            raise PropagationError(f"nyxb_propagate_batch_stm rc={rc}: {abi.last_error()}")
+        return out_state, out_epoch, out_stm, details, status
+
+    def od_ekf_batch(self, cfg_c, n_stations, stations_c, msr_epoch_ns, msr_tracker, obs, state_soa, consts_soa, epoch0_ns,
+                     covar0_soa, record_estimates: bool = False):
+        """`nyxb_od_ekf_batch`: n sequential Kalman filters over one tracking schedule in ONE launch (od/process/mod.rs:128-497)."""
+        from .od import ODSolution
+
+        state_soa = np.ascontiguousarray(state_soa, dtype=np.float64)
+        consts_soa = np.ascontiguousarray(consts_soa, dtype=np.float64)
+        epoch0_ns = np.ascontiguousarray(epoch0_ns, dtype=np.int64)
+        covar0_soa = np.ascontiguousarray(covar0_soa, dtype=np.float64)
+        msr_epoch_ns = np.ascontiguousarray(msr_epoch_ns, dtype=np.int64)
+        msr_tracker = np.ascontiguousarray(msr_tracker, dtype=np.int32)
+        obs = np.ascontiguousarray(obs, dtype=np.float64)
+        n = state_soa.shape[1]
+        m = msr_epoch_ns.shape[0]
+        if state_soa.shape != (9, n) or consts_soa.shape != (4, n) or epoch0_ns.shape != (n,) or covar0_soa.shape != (81, n):
+            raise ValueError("expected state[9][n], consts[4][n], epoch0[n], covar0[81][n]")
+        if obs.shape != (m, 2, n) or msr_tracker.shape != (m,):
+            raise ValueError("expected obs[m][2][n], tracker[m]")
+        arc = abi.TrackingArcC(m, msr_epoch_ns.ctypes.data, msr_tracker.ctypes.data, obs.ctypes.data)
+        out_state = np.empty((9, n)); out_epoch = np.empty(n, dtype=np.int64); out_cov = np.empty((81, n)); out_dev = np.empty((9, n))
+        ratio = np.full((m, 2, n), np.nan); prefit = np.full((m, 2, n), np.nan); postfit = np.full((m, 2, n), np.nan)
+        flags = np.zeros((m, n), dtype=np.int32)
+        est_state = np.full((m, 9, n), np.nan) if record_estimates else None
+        est_cov = np.full((m, 9, n), np.nan) if record_estimates else None
+        details = np.zeros(n, dtype=abi.DETAILS_DTYPE)
+        status = np.zeros(n, dtype=np.int32)
+        out = abi.OdOutputsC(out_state.ctypes.data, out_epoch.ctypes.data, out_cov.ctypes.data, out_dev.ctypes.data,
+                             ratio.ctypes.data, prefit.ctypes.data, postfit.ctypes.data, flags.ctypes.data,
+                             est_state.ctypes.data if record_estimates else None, est_cov.ctypes.data if record_estimates else None,
+                             details.ctypes.data, status.ctypes.data)
+        rc = self._lib.nyxb_od_ekf_batch(self._h, C.byref(cfg_c), int(n_stations), stations_c, C.byref(arc), n,
+                                         state_soa.ctypes.data, consts_soa.ctypes.data, epoch0_ns.ctypes.data,
+                                         covar0_soa.ctypes.data, C.byref(out))
+        if rc != 0:
+            raise PropagationError(f"nyxb_od_ekf_batch rc={rc}: {abi.last_error()}")
+        covar = np.ascontiguousarray(out_cov.T.reshape(n, 9, 9).transpose(0, 2, 1))  # (c*9+r) -> [i][r][c]
+        return ODSolution(out_state, out_epoch, covar, out_dev, ratio, prefit, postfit, flags, est_state, est_cov, details, status)
+
     def propagate_batch_dev(self, n, state_ptr, consts_ptr, epoch0_ptr, end_epoch_ns, step_ptr, out_state_ptr,
                             out_epoch_ptr, details_ptr, status_ptr, stream_ptr=None):
         """Device-pointer call (`nyxb_propagate_batch_dev`): asynchronous on `stream_ptr`."""

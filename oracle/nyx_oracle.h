@@ -38,6 +38,21 @@ int nyx_oracle_propagate_batch_traj(const nyxb_dynamics* dyn, const nyxb_integ_o
                                     const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
                                     double* out_state_soa, int64_t* out_epoch_ns,
                                     nyxb_details* out_details, int32_t* out_status, const nyxb_traj_sink* sink, int n_threads);
+/* ---- STM path (nyx_oracle_od.c): dual-number gradient, 90-vector propagation, PropInstance handle ---- */
+typedef struct nyx_oracle_inst nyx_oracle_inst;
+nyx_oracle_inst* nyx_oracle_inst_new(const nyxb_dynamics* dyn, const nyxb_integ_opts* opts, const double y9[9],
+                                     const double consts[4], int64_t epoch_ns);
+void nyx_oracle_inst_free(nyx_oracle_inst* in);
+int nyx_oracle_inst_for_duration(nyx_oracle_inst* in, int64_t duration_ns);
+void nyx_oracle_inst_get(const nyx_oracle_inst* in, double y[90], int64_t* epoch_ns, int64_t* step_ns, int* fixed, nyxb_details* det);
+void nyx_oracle_inst_set(nyx_oracle_inst* in, const double y[90], int64_t epoch_ns);
+void nyx_oracle_inst_set_step(nyx_oracle_inst* in, int64_t step_ns, int fixed);
+int nyx_oracle_dual_eom(const nyxb_dynamics* dyn, int64_t t_ns, const double y[9], const double consts[4], double dx[9], double grad[81]);
+int nyx_oracle_propagate_batch_stm(const nyxb_dynamics* dyn, const nyxb_integ_opts* opts, size_t n,
+                                   const double* state_soa, const double* consts_soa,
+                                   const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
+                                   const double* stm_in_soa, double* out_state_soa, int64_t* out_epoch_ns,
+                                   double* out_stm_soa, nyxb_details* out_details, int32_t* out_status, int n_threads);
 int nyx_oracle_num_threads(void);
 #ifdef __cplusplus
 }

@@ -18,8 +18,8 @@ _LIB = None
 
 def build(force: bool = False) -> Path:
     so = _DIR / "libnyx_oracle.so"
-    src = _DIR / "nyx_oracle.c"
-    if force or not so.exists() or so.stat().st_mtime < src.stat().st_mtime:
+    srcs = [_DIR / "nyx_oracle.c", _DIR / "nyx_oracle_od.c", _DIR / "nyx_oracle.h", _DIR / "nyx_oracle_priv.h"]
+    if force or not so.exists() or so.stat().st_mtime < max(f.stat().st_mtime for f in srcs):
         subprocess.run(["make", "-C", str(_DIR), "-B" if force else "-s"], check=True, capture_output=True)
     return so
 
@@ -60,6 +60,24 @@ def lib():
         L.nyx_oracle_tableau.restype = C.c_int
         L.nyx_oracle_tableau.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(abi.c_double_p), C.POINTER(abi.c_double_p)]
         L.nyx_oracle_num_threads.restype = C.c_int
+        # STM path (nyx_oracle_od.c)
+        L.nyx_oracle_dual_eom.restype = C.c_int
+        L.nyx_oracle_dual_eom.argtypes = [C.POINTER(abi.DynamicsC), C.c_int64, abi.c_double_p, abi.c_double_p, abi.c_double_p, abi.c_double_p]
+        L.nyx_oracle_propagate_batch_stm.restype = C.c_int
+        L.nyx_oracle_propagate_batch_stm.argtypes = [
+            C.POINTER(abi.DynamicsC), C.POINTER(abi.IntegOpts), C.c_size_t, vp, vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, C.c_int]
+        L.nyx_oracle_inst_new.restype = vp
+        L.nyx_oracle_inst_new.argtypes = [C.POINTER(abi.DynamicsC), C.POINTER(abi.IntegOpts), abi.c_double_p, abi.c_double_p, C.c_int64]
+        L.nyx_oracle_inst_free.restype = None
+        L.nyx_oracle_inst_free.argtypes = [vp]
+        L.nyx_oracle_inst_for_duration.restype = C.c_int
+        L.nyx_oracle_inst_for_duration.argtypes = [vp, C.c_int64]
+        L.nyx_oracle_inst_get.restype = None
+        L.nyx_oracle_inst_get.argtypes = [vp, abi.c_double_p, abi.c_int64_p, abi.c_int64_p, C.POINTER(C.c_int), vp]
+        L.nyx_oracle_inst_set.restype = None
+        L.nyx_oracle_inst_set.argtypes = [vp, abi.c_double_p, C.c_int64]
+        L.nyx_oracle_inst_set_step.restype = None
+        L.nyx_oracle_inst_set_step.argtypes = [vp, C.c_int64, C.c_int]
         _LIB = L
     return _LIB
 
@@ -109,3 +127,74 @@ def propagate_batch(dyn_c, opts_c, state_soa, consts_soa, epoch0_ns, end_epoch_n
 
 def num_threads() -> int:
     return lib().nyx_oracle_num_threads()
+
+
+# --------------------------------------------------------------------------- STM path
+def dual_eom(dyn_c, t_ns, y9, consts4):
+    """One evaluation of SpacecraftDynamics::dual_eom (spacecraft.rs:312-363): returns (dx[9], A[9][9])."""
+    L = lib()
+    y9 = np.ascontiguousarray(y9, dtype=np.float64)
+    consts4 = np.ascontiguousarray(consts4, dtype=np.float64)
+    dx = np.zeros(9)
+    grad = np.zeros(81)
+    rc = L.nyx_oracle_dual_eom(C.byref(dyn_c), int(t_ns), abi.as_double_p(y9), abi.as_double_p(consts4), abi.as_double_p(dx), abi.as_double_p(grad))
+    if rc != 0:
+        raise RuntimeError(f"oracle dual_eom rc={rc}")
+    return dx, grad.reshape(9, 9)
+
+
+def propagate_batch_stm(dyn_c, opts_c, state_soa, consts_soa, epoch0_ns, end_epoch_ns, stm_in=None, step_ns=None, n_threads=0):
+    """Same contract as nyxb_propagate_batch_stm: returns (state[9][n], epoch[n], stm[81][n], details, status)."""
+    L = lib()
+    state_soa = np.ascontiguousarray(state_soa, dtype=np.float64)
+    consts_soa = np.ascontiguousarray(consts_soa, dtype=np.float64)
+    epoch0_ns = np.ascontiguousarray(epoch0_ns, dtype=np.int64)
+    n = state_soa.shape[1]
+    out_state = np.empty((9, n)); out_epoch = np.empty(n, dtype=np.int64); out_stm = np.empty((81, n))
+    details = np.zeros(n, dtype=abi.DETAILS_DTYPE); status = np.zeros(n, dtype=np.int32)
+    if stm_in is not None:
+        stm_in = np.ascontiguousarray(stm_in, dtype=np.float64)
+        assert stm_in.shape == (81, n)
+    rc = L.nyx_oracle_propagate_batch_stm(
+        C.byref(dyn_c), C.byref(opts_c), n, state_soa.ctypes.data, consts_soa.ctypes.data, epoch0_ns.ctypes.data, int(end_epoch_ns),
+        step_ns.ctypes.data if step_ns is not None else None, stm_in.ctypes.data if stm_in is not None else None,
+        out_state.ctypes.data, out_epoch.ctypes.data, out_stm.ctypes.data, details.ctypes.data, status.ctypes.data, int(n_threads))
+    if rc != 0:
+        raise RuntimeError(f"oracle rejected the STM configuration (rc={rc})")
+    return out_state, out_epoch, out_stm, details, status
+
+
+class Inst:
+    """PropInstance over the 90-vector (state + STM) for the numpy Kalman-filter restatement (pyoracle_od.py)."""
+
+    def __init__(self, dyn_c, opts_c, y9, consts4, epoch_ns):
+        self._L = lib()
+        self._keep = (dyn_c, opts_c)
+        y9 = np.ascontiguousarray(y9, dtype=np.float64)
+        consts4 = np.ascontiguousarray(consts4, dtype=np.float64)
+        self._h = self._L.nyx_oracle_inst_new(C.byref(dyn_c), C.byref(opts_c), abi.as_double_p(y9), abi.as_double_p(consts4), int(epoch_ns))
+        if not self._h:
+            raise RuntimeError("oracle rejected the STM configuration")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.nyx_oracle_inst_free(self._h)
+            self._h = None
+
+    def for_duration(self, duration_ns) -> int:
+        return self._L.nyx_oracle_inst_for_duration(self._h, int(duration_ns))
+
+    def get(self):
+        y = np.zeros(90)
+        ep, st = C.c_int64(), C.c_int64()
+        fx = C.c_int()
+        det = np.zeros(1, dtype=abi.DETAILS_DTYPE)
+        self._L.nyx_oracle_inst_get(self._h, abi.as_double_p(y), C.byref(ep), C.byref(st), C.byref(fx), det.ctypes.data)
+        return y, ep.value, st.value, fx.value, det[0]
+
+    def set(self, y90, epoch_ns):
+        y90 = np.ascontiguousarray(y90, dtype=np.float64)
+        self._L.nyx_oracle_inst_set(self._h, abi.as_double_p(y90), int(epoch_ns))
+
+    def set_step(self, step_ns, fixed):
+        self._L.nyx_oracle_inst_set_step(self._h, int(step_ns), int(bool(fixed)))
