@@ -170,12 +170,24 @@ def bench_c5(args, nb, local_rank):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"C5: {n} LRO-like filters (Moon-centred, GRAIL {deg}x{deg} + Earth/Sun point masses + SRP with Cr estimated), "
                                    f"EKF over {n_msr} range+Doppler measurement epochs at 60 s from 3 DSN stations, {args.span_days:g}-day span, DP78",
-                       "ok_trajectories": ok, "measurement_updates_accepted": acc, "mode": args.mode, "kernel": "nyxb_k_od (1 thread = 1 filter)",
+                       "ok_trajectories": ok, "measurement_updates_accepted": acc, "mode": args.mode,
+                       "kernel": "nyxb_k_od_coop (1 warp = 1 filter, harmonic gradient split by columns over the lanes)"
+                                 if (mode == nb.MODE_FAST and deg >= 8) else "nyxb_k_od (1 thread = 1 filter)",
                        "median_final_position_error_km": float(np.median(err)) if last_vis.size and last_vis[-1] == n_msr - 1 else None},
             "e2e": {"value": steps / wall, "unit": "trajectory-steps/s", "h2d_bytes_per_step": int(arc.obs.nbytes + n * (13 + 81) * 8),
                     "d2h_bytes_per_step": int(n * (9 + 81 + 9) * 8 + 3 * arc.obs.nbytes + n_msr * n * 4), "ms_per_step": wall * 1e3},
             "gpu_launches": eng.launch_count() - launches0, "clocks": clocks,
             "measurement_updates_per_s": acc / (kern_ms * 1e-3)}
+    # FP64 roofline of the filter kernel: algorithmic work of the dual-number harmonic gradient (gravity_field.rs:273-431 with 3
+    # partials): ~150 flop per (n, m) entry (two column recursions, three products with rr_n, six accumulations; FMA = 2), entries =
+    # N + N(N+1)/2, 13 DP78 stages per step; everything else (point masses, SRP, 9x9 filter algebra) is < 3 % and not counted.
+    entries = deg + deg * (deg + 1) // 2
+    fps5 = 13 * 150.0 * entries
+    fp64_peak = eng._lib.nyxb_measure_fp64_tflops(local_rank, 4096)
+    ach = steps * fps5 / (kern_ms * 1e-3) / 1e12
+    line["roofline"] = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak if fp64_peak > 0 else None,
+                        "traffic": None, "kernel_ms": kern_ms,
+                        "note": f"algorithmic {fps5:.3g} flop per accepted step (dual-number {deg}x{deg} gradient x 13 stages); peak = live DFMA probe"}
     if not args.no_cpu_baseline:
         # numpy + C oracle filter (tests' checker) on ONE filter over the first measurements: a bounded sample
         from oracle import pyoracle_od

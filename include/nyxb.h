@@ -394,6 +394,20 @@ int32_t nyxb_od_ekf_batch(nyxb_engine* eng, const nyxb_od_config* cfg,
                           const double* state_soa, const double* consts_soa, const int64_t* epoch0_ns,
                           const double* covar0_soa, const nyxb_od_outputs* out);
 
+/* ---- On-device Monte Carlo dispersions (next row (f)-4): `MvnSpacecraft::sample` (mc/multivariate.rs:298-331) for the
+ * runs [first_index, first_index + n): state_i = template + (sqrt_s_v * z_i + mean), z_i ~ N(0, I_9) drawn from a
+ * counter-based stream keyed by (seed, run index) — Philox4x32-10 + Box-Muller, see nyx_b200/csrc/nyxb_mvn.cu — so that a
+ * run's draw does not depend on how the ensemble is sharded (the reference's serial Pcg64Mcg + ziggurat stream,
+ * mc/montecarlo.rs:277-296, is not reproduced: DESIGN.md §3).
+ *  template_state[9], mean[9] (NULL = 0), sqrt_s_v[81] row-major (V * sqrt(S) of the covariance's SVD, multivariate.rs:237-247)
+ *  out_state_soa [9][n], out_dispersion_soa [9][n] or NULL (the x_i themselves).  `_dev`: device pointers, stream-ordered. */
+int32_t nyxb_mvn_sample(int32_t device, uint64_t seed, uint64_t first_index, size_t n,
+                        const double* template_state, const double* mean, const double* sqrt_s_v,
+                        double* out_state_soa, double* out_dispersion_soa);
+int32_t nyxb_mvn_sample_dev(int32_t device, uint64_t seed, uint64_t first_index, size_t n,
+                            const double* template_state, const double* mean, const double* sqrt_s_v,
+                            double* out_state_soa, double* out_dispersion_soa, void* cuda_stream);
+
 /* Tuning / introspection. */
 int32_t nyxb_engine_set_lanes(nyxb_engine* eng, int32_t lanes_per_trajectory); /* 0 = auto */
 int32_t nyxb_engine_get_lanes(const nyxb_engine* eng);

@@ -274,6 +274,10 @@ def _declare(lib):
     lib.nyxb_od_ekf_batch.restype = C.c_int32
     lib.nyxb_od_ekf_batch.argtypes = [vp, C.POINTER(OdConfigC), C.c_int32, C.POINTER(GroundStationC), C.POINTER(TrackingArcC),
                                       C.c_size_t, vp, vp, vp, vp, C.POINTER(OdOutputsC)]
+    lib.nyxb_mvn_sample.restype = C.c_int32
+    lib.nyxb_mvn_sample.argtypes = [C.c_int32, C.c_uint64, C.c_uint64, C.c_size_t, vp, vp, vp, vp, vp]
+    lib.nyxb_mvn_sample_dev.restype = C.c_int32
+    lib.nyxb_mvn_sample_dev.argtypes = [C.c_int32, C.c_uint64, C.c_uint64, C.c_size_t, vp, vp, vp, vp, vp, vp]
     lib.nyxb_engine_set_lanes.restype = C.c_int32
     lib.nyxb_engine_set_lanes.argtypes = [vp, C.c_int32]
     lib.nyxb_engine_get_lanes.restype = C.c_int32
@@ -303,6 +307,8 @@ EXPORTED_SYMBOLS = [
     "nyxb_propagate_batch_event",
     "nyxb_propagate_batch_stm",
     "nyxb_od_ekf_batch",
+    "nyxb_mvn_sample",
+    "nyxb_mvn_sample_dev",
     "nyxb_engine_set_lanes",
     "nyxb_engine_get_lanes",
     "nyxb_engine_launch_count",

@@ -23,6 +23,11 @@ extern "C" cudaError_t nyxb_launch_thread_fast(const DevSetup*, size_t, const do
                                                long long, long long*, double*, long long*, nyxb_details*, int*, int,
                                                const DevSink*, cudaStream_t);
 extern "C" double nyxb_fp64_probe(int device, int iters);
+extern "C" cudaError_t nyxb_launch_od_coop(const DevSetup*, const DevOd*, const int*, size_t, const double*, const double*, const long long*,
+                                           double*, long long*, nyxb_details*, int*, cudaStream_t);
+extern "C" int nyxb_od_coop_kmax(void);
+extern "C" cudaError_t nyxb_launch_mvn(unsigned long long, unsigned long long, size_t, const double*, const double*, const double*,
+                                       double*, double*, cudaStream_t);
 
 static thread_local std::string g_err;
 static void set_err(const std::string& s) { g_err = s; }
@@ -618,10 +623,34 @@ extern "C" int32_t nyxb_od_ekf_batch(nyxb_engine* eng, const nyxb_od_config* cfg
     if (od.flags) CUDA_TRY(cudaMemsetAsync(od.flags, 0, sizeof(int) * m * n, st));
     if (od.est_state) CUDA_TRY(cudaMemsetAsync(od.est_state, 0xFF, sizeof(double) * m * 9 * n, st));
     if (od.est_cov) CUDA_TRY(cudaMemsetAsync(od.est_cov, 0xFF, sizeof(double) * m * 9 * n, st));
+    // FAST mode with a gravity field: one WARP per filter, the harmonic gradient split by columns over the lanes
+    // (nyxb_od_coop.cu); columns -> lanes by longest-processing-time.  NYXB_OD_COOP=0 forces the per-thread kernel.
+    const int* d_cols = nullptr;
+    bool coop = eng->mode == NYXB_MODE_FAST && eng->S.has_grav && eng->S.grav.N >= 8;
+    if (const char* ev = getenv("NYXB_OD_COOP")) coop = coop && atoi(ev) != 0;
+    if (coop) {
+        const int N = eng->S.grav.N, mtop = eng->S.grav.M < N ? eng->S.grav.M : N, kmax = nyxb_od_coop_kmax();
+        std::vector<int> cols(32 * (size_t)kmax, -1), cnt(32, 0);
+        std::vector<long long> load(32, 0);
+        for (int m = 0; m <= mtop && coop; ++m) {   // columns in decreasing length order: m = 0, 1 (same length), 2, ...
+            int best = 0;
+            for (int l = 1; l < 32; ++l)
+                if (load[l] < load[best] || (load[l] == load[best] && cnt[l] < cnt[best])) best = l;
+            if (cnt[best] >= kmax) { coop = false; break; }
+            cols[(size_t)best * kmax + cnt[best]++] = m;
+            load[best] += N - (m > 0 ? m : 1) + 1 + 6;   // entries + per-column overhead
+        }
+        if (coop) {
+            d_cols = B.put(cols.data(), cols.size(), st);
+            if (!d_cols) { set_err("device allocation / upload failed"); return NYXB_RC_CUDA; }
+        }
+    }
     CUDA_TRY(cudaEventRecord(eng->ev0, st));
-    cudaError_t err = (eng->mode == NYXB_MODE_STRICT)
-        ? nyxb_launch_od_strict(&eng->S, &od, n, d_state, d_consts, d_ep, d_out, d_oep, d_det, d_status, st)
-        : nyxb_launch_od_fast(&eng->S, &od, n, d_state, d_consts, d_ep, d_out, d_oep, d_det, d_status, st);
+    cudaError_t err = coop
+        ? nyxb_launch_od_coop(&eng->S, &od, d_cols, n, d_state, d_consts, d_ep, d_out, d_oep, d_det, d_status, st)
+        : (eng->mode == NYXB_MODE_STRICT)
+            ? nyxb_launch_od_strict(&eng->S, &od, n, d_state, d_consts, d_ep, d_out, d_oep, d_det, d_status, st)
+            : nyxb_launch_od_fast(&eng->S, &od, n, d_state, d_consts, d_ep, d_out, d_oep, d_det, d_status, st);
     if (err != cudaSuccess) { set_err(std::string("kernel launch: ") + cudaGetErrorString(err)); return NYXB_RC_CUDA; }
     eng->launches += 1;
     CUDA_TRY(cudaEventRecord(eng->ev1, st));
@@ -640,6 +669,39 @@ extern "C" int32_t nyxb_od_ekf_batch(nyxb_engine* eng, const nyxb_od_config* cfg
     CUDA_TRY(cudaStreamSynchronize(st));
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, eng->ev0, eng->ev1) == cudaSuccess) eng->last_ms = ms;
+    return NYXB_RC_OK;
+}
+
+extern "C" int32_t nyxb_mvn_sample_dev(int32_t device, uint64_t seed, uint64_t first_index, size_t n, const double* template_state,
+                                       const double* mean, const double* sqrt_s_v, double* out_state_soa, double* out_dispersion_soa,
+                                       void* cuda_stream) {
+    if (!template_state || !sqrt_s_v || !out_state_soa) { set_err("null argument"); return NYXB_RC_BAD_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_err("no CUDA device available: nyxb has no CPU fallback"); return NYXB_RC_NO_DEVICE; }
+    if (device < 0 || device >= ndev) { set_err("bad device ordinal"); return NYXB_RC_BAD_ARG; }
+    CUDA_TRY(cudaSetDevice(device));
+    cudaError_t err = nyxb_launch_mvn(seed, first_index, n, template_state, mean, sqrt_s_v, out_state_soa, out_dispersion_soa,
+                                      (cudaStream_t)cuda_stream);
+    if (err != cudaSuccess) { set_err(std::string("kernel launch: ") + cudaGetErrorString(err)); return NYXB_RC_CUDA; }
+    return NYXB_RC_OK;
+}
+
+extern "C" int32_t nyxb_mvn_sample(int32_t device, uint64_t seed, uint64_t first_index, size_t n, const double* template_state,
+                                   const double* mean, const double* sqrt_s_v, double* out_state_soa, double* out_dispersion_soa) {
+    if (!template_state || !sqrt_s_v || !out_state_soa) { set_err("null argument"); return NYXB_RC_BAD_ARG; }
+    if (n == 0) return NYXB_RC_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_err("no CUDA device available: nyxb has no CPU fallback"); return NYXB_RC_NO_DEVICE; }
+    if (device < 0 || device >= ndev) { set_err("bad device ordinal"); return NYXB_RC_BAD_ARG; }
+    CUDA_TRY(cudaSetDevice(device));
+    DevBufs B;
+    double* d_out = B.alloc<double>(9 * n);
+    double* d_disp = out_dispersion_soa ? B.alloc<double>(9 * n) : nullptr;
+    if (!d_out || (out_dispersion_soa && !d_disp)) { set_err("device allocation failed"); return NYXB_RC_CUDA; }
+    int32_t rc = nyxb_mvn_sample_dev(device, seed, first_index, n, template_state, mean, sqrt_s_v, d_out, d_disp, nullptr);
+    if (rc != NYXB_RC_OK) return rc;
+    CUDA_TRY(cudaMemcpy(out_state_soa, d_out, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost));
+    if (d_disp) CUDA_TRY(cudaMemcpy(out_dispersion_soa, d_disp, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost));
     return NYXB_RC_OK;
 }
 

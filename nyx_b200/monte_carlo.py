@@ -68,6 +68,21 @@ class MvnSpacecraft:
         z = rng.standard_normal((num, 9))
         return z @ self.sqrt_s_v.T + self.mean[None, :]
 
+    def sample_on_device(self, seed: int, num: int, first_index: int = 0, device: int = 0):
+        """`nyxb_mvn_sample`: the dispersed states of runs [first_index, first_index + num) drawn on the
+        GPU from the counter-based stream keyed by (seed, run index).  Returns (state[9][n], dispersion[9][n])."""
+        lib = abi.load_library()
+        t = np.ascontiguousarray(self.template.to_vector(), dtype=np.float64)
+        mean = np.ascontiguousarray(self.mean, dtype=np.float64)
+        L = np.ascontiguousarray(self.sqrt_s_v, dtype=np.float64).reshape(81)
+        out = np.empty((9, num))
+        disp = np.empty((9, num))
+        rc = lib.nyxb_mvn_sample(int(device), int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_index), num, t.ctypes.data, mean.ctypes.data,
+                                 L.ctypes.data, out.ctypes.data, disp.ctypes.data)
+        if rc != 0:
+            raise PropagationError(f"nyxb_mvn_sample rc={rc}: {abi.last_error()}")
+        return out, disp
+
     def apply(self, x: np.ndarray) -> DispersedState:
         vec = self.template.to_vector() + x
         state = self.template.with_vector(self.template.epoch(), vec)
@@ -119,8 +134,33 @@ class MonteCarlo:
         x = self.random_state.sample_vectors(rng, skip + num_runs)[skip:]
         return [(i, self.random_state.apply(x[i])) for i in range(num_runs)]
 
-    def run_until_epoch(self, prop: Propagator, almanac: Optional[Almanac], end_epoch_ns: int, num_runs: int) -> Results:
+    def generate_states_on_device(self, skip: int, num_runs: int, seed: Optional[int] = None, device: int = 0):
+        """Device counterpart of `generate_states`: run i gets the draw keyed by (seed, skip + i)."""
+        sd = self.seed if seed is None else seed
+        st, disp = self.random_state.sample_on_device(0 if sd is None else sd, num_runs, first_index=skip, device=device)
+        return st, disp
+
+    def run_until_epoch(self, prop: Propagator, almanac: Optional[Almanac], end_epoch_ns: int, num_runs: int,
+                        device_dispersions: bool = False) -> Results:
+        if device_dispersions:
+            return self._run_device_dispersions(prop, almanac, 0, end_epoch_ns, num_runs)
         return self.resume_run_until_epoch(prop, almanac, 0, end_epoch_ns, num_runs)
+
+    def _run_device_dispersions(self, prop, almanac, skip, end_epoch_ns, num_runs) -> Results:
+        """mc/montecarlo.rs:208-273 with the dispersions drawn on the GPU."""
+        tmpl = self.random_state.template
+        st, disp = self.generate_states_on_device(skip, num_runs, self.seed, prop.device)
+        cs = np.empty((4, num_runs))
+        cs[0], cs[1], cs[2], cs[3] = tmpl.mass.dry_mass_kg, tmpl.mass.extra_mass_kg, tmpl.srp.area_m2, tmpl.drag.area_m2
+        ep = np.full(num_runs, tmpl.epoch(), dtype=np.int64)
+        eng = prop.engine(self.nominal_state.orbit.frame, almanac)
+        out, out_ep, det, status = eng.propagate_batch(st, cs, ep, end_epoch_ns)
+        runs = []
+        for idx in range(num_runs):
+            ds = DispersedState(tmpl.with_vector(tmpl.epoch(), st[:, idx]), [(p, float(-disp[q, idx])) for q, p in enumerate(_PARAMS)])
+            err = status_error(status[idx])
+            runs.append(Run(idx, ds, err if err is not None else ds.state.with_vector(int(out_ep[idx]), out[:, idx])))
+        return Results(runs, self.scenario, out, det, status)
 
     def resume_run_until_epoch(self, prop: Propagator, almanac: Optional[Almanac], skip: int, end_epoch_ns: int,
                                num_runs: int) -> Results:

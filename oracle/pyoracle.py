@@ -18,7 +18,7 @@ _LIB = None
 
 def build(force: bool = False) -> Path:
     so = _DIR / "libnyx_oracle.so"
-    srcs = [_DIR / "nyx_oracle.c", _DIR / "nyx_oracle_od.c", _DIR / "nyx_oracle.h", _DIR / "nyx_oracle_priv.h"]
+    srcs = [_DIR / "nyx_oracle.c", _DIR / "nyx_oracle_od.c", _DIR / "nyx_oracle_mvn.c", _DIR / "nyx_oracle.h", _DIR / "nyx_oracle_priv.h"]
     if force or not so.exists() or so.stat().st_mtime < max(f.stat().st_mtime for f in srcs):
         subprocess.run(["make", "-C", str(_DIR), "-B" if force else "-s"], check=True, capture_output=True)
     return so
@@ -78,6 +78,10 @@ def lib():
         L.nyx_oracle_inst_set.argtypes = [vp, abi.c_double_p, C.c_int64]
         L.nyx_oracle_inst_set_step.restype = None
         L.nyx_oracle_inst_set_step.argtypes = [vp, C.c_int64, C.c_int]
+        L.nyx_oracle_philox4x32_10.restype = None
+        L.nyx_oracle_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.nyx_oracle_mvn_sample.restype = C.c_int
+        L.nyx_oracle_mvn_sample.argtypes = [C.c_uint64, C.c_uint64, C.c_size_t, abi.c_double_p, abi.c_double_p, abi.c_double_p, vp, vp]
         _LIB = L
     return _LIB
 
@@ -198,3 +202,14 @@ class Inst:
 
     def set_step(self, step_ns, fixed):
         self._L.nyx_oracle_inst_set_step(self._h, int(step_ns), int(bool(fixed)))
+
+
+def mvn_sample(seed, first_index, n, template9, mean9, sqrt_s_v):
+    """Same contract as nyxb_mvn_sample: returns (state[9][n], dispersion[9][n])."""
+    L = lib()
+    t = np.ascontiguousarray(template9, dtype=np.float64); m = np.ascontiguousarray(mean9, dtype=np.float64)
+    sq = np.ascontiguousarray(np.asarray(sqrt_s_v, dtype=np.float64).reshape(81))
+    out = np.empty((9, n)); disp = np.empty((9, n))
+    rc = L.nyx_oracle_mvn_sample(int(seed), int(first_index), n, abi.as_double_p(t), abi.as_double_p(m), abi.as_double_p(sq), out.ctypes.data, disp.ctypes.data)
+    assert rc == 0
+    return out, disp
