@@ -8,6 +8,9 @@
 //   PropInstance::{for_duration,until_epoch,latest_details}   propagators/instance.rs:265-282, 495-498
 //   SpacecraftDynamics / OrbitalDynamics / PointMasses / GravityField / SolarPressure / Drag   dynamics/*.rs
 //   MonteCarlo::{generate_states,run_until_epoch,resume_run_until_epoch}   mc/montecarlo.rs:188-296
+//   Propagator::propagate_batch_stm (Spacecraft::with_stm + propagate)       dynamics/spacecraft.rs:203-227, 312-363
+//   GroundStation / StochasticNoise / ProcessNoise3D / SigmaRejection / KfEstimate / TrackingDataArc / KalmanODProcess
+//                                                         od/ground_station, od/snc.rs, od/process/{mod,initializers,rejectcrit}.rs
 //
 // No arithmetic of the hot path lives here: every propagate call is one nyxb_propagate_batch on the GPU.
 #pragma once
@@ -80,12 +83,14 @@ struct Frame {
     double mu_km3_s2 = 398600.435436096;
     double mean_equatorial_radius_km = 6378.14;
     nyxb_rotation rotation{};  // kind 0: inertial axes
+    double polar_radius_km = 0.0;  // > 0: ellipsoid for geodetic coordinates (ground stations); 0: sphere
     Frame with_mu_km3_s2(double mu) const { Frame f = *this; f.mu_km3_s2 = mu; return f; }
 };
 inline Frame EARTH_J2000() { return {}; }
 inline Frame IAU_EARTH() {
     Frame f;
     f.rotation = nyxb_rotation{1, 0, 0.0, -0.641, 90.0, -0.557, 190.147, 360.9856235};  // pck00008
+    f.polar_radius_km = 6356.75;
     return f;
 }
 
@@ -237,6 +242,23 @@ class Propagator {
         if (rc != NYXB_RC_OK) throw std::runtime_error(std::string("nyxb_propagate_batch: ") + nyxb_last_error());
         return r;
     }
+    // Spacecraft::with_stm() + until_epoch for a batch: final states and the 9x9 STMs (column-major per trajectory, [81][n])
+    struct StmResult { std::vector<double> state, stm; std::vector<int64_t> epoch; std::vector<nyxb_details> details; std::vector<int32_t> status;
+                       double phi(size_t n, size_t i, int r, int c) const { return stm[(size_t)(c * 9 + r) * n + i]; } };
+    StmResult propagate_batch_stm(const std::vector<Spacecraft>& v, int64_t end_epoch_ns, const Almanac* almanac = nullptr,
+                                  const std::vector<double>* stm_in = nullptr) const {
+        StmResult r;
+        const size_t n = v.size();
+        r.state.resize(9 * n); r.stm.resize(81 * n); r.epoch.resize(n); r.details.resize(n); r.status.resize(n);
+        if (n == 0) return r;
+        auto eng = detail::make_engine(dynamics, v[0].frame, almanac, method, opts, mode, device);
+        detail::Soa soa(v);
+        int32_t rc = nyxb_propagate_batch_stm(eng.get(), n, soa.state.data(), soa.consts.data(), soa.epoch.data(), end_epoch_ns, nullptr,
+                                              stm_in ? stm_in->data() : nullptr, r.state.data(), r.epoch.data(), r.stm.data(),
+                                              r.details.data(), r.status.data());
+        if (rc != NYXB_RC_OK) throw std::runtime_error(std::string("nyxb_propagate_batch_stm: ") + nyxb_last_error());
+        return r;
+    }
     // nyx-py Propagator.many_until_epoch (py_md.rs:224-271): failed runs are dropped
     std::vector<Spacecraft> many_until_epoch(const std::vector<Spacecraft>& v, int64_t end_epoch_ns, const Almanac* almanac = nullptr) const {
         auto r = propagate_batch(v, end_epoch_ns, almanac);
@@ -296,6 +318,20 @@ class MonteCarlo {
         }
         return out;
     }
+    // the same dispersions drawn on the GPU (nyxb_mvn_sample: counter-based stream keyed by (seed, run index), shard-invariant)
+    std::vector<Spacecraft> generate_states_on_device(size_t skip, size_t num_runs, int32_t device = 0) const {
+        const Spacecraft& t = nominal_state;
+        const double tmpl[9] = {t.x_km, t.y_km, t.z_km, t.vx_km_s, t.vy_km_s, t.vz_km_s, t.coeff_reflectivity, t.coeff_drag, t.prop_mass_kg};
+        double L[81] = {0};
+        for (int i = 0; i < 9; ++i) L[i * 9 + i] = std_dev[i];
+        std::vector<double> st(9 * num_runs);
+        if (nyxb_mvn_sample(device, seed, skip, num_runs, tmpl, nullptr, L, st.data(), nullptr) != NYXB_RC_OK)
+            throw std::runtime_error(std::string("nyxb_mvn_sample: ") + nyxb_last_error());
+        std::vector<int64_t> ep(num_runs, t.epoch_ns);
+        std::vector<Spacecraft> out;
+        for (size_t i = 0; i < num_runs; ++i) out.push_back(detail::unpack(t, st, ep, num_runs, i));
+        return out;
+    }
     Results run_until_epoch(const Propagator& prop, const Almanac* almanac, int64_t end_epoch_ns, size_t num_runs) const {
         return resume_run_until_epoch(prop, almanac, 0, end_epoch_ns, num_runs);
     }
@@ -309,6 +345,122 @@ class MonteCarlo {
             else res.runs.push_back(Run{i, init[i], detail::unpack(init[i], r.state, r.epoch, num_runs, i)});
         }
         return res;
+    }
+};
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Orbit determination: n sequential Kalman filters over one tracking schedule in ONE launch.
+// ---------------------------------------------------------------------------------------------------------------------
+enum class MeasurementType : int32_t { Range = NYXB_MSR_RANGE, Doppler = NYXB_MSR_DOPPLER };          // od/msr/types.rs:31-45
+enum class KalmanVariant : int32_t { ReferenceUpdate = NYXB_KF_REFERENCE_UPDATE, DeviationTracking = NYXB_KF_DEVIATION_TRACKING };
+struct StochasticNoise { double sigma = 0.0, bias_constant = 0.0; double covariance() const { return sigma * sigma; } };
+struct SigmaRejection { double num_sigmas = 3.0; };                                                        // process/rejectcrit.rs:35-46
+
+// GroundStation (od/ground_station/mod.rs:47-75; builtin.rs:25-117), instantaneous Range + Doppler
+struct GroundStation {
+    std::string name;
+    double latitude_deg = 0, longitude_deg = 0, height_km = 0, elevation_mask_deg = 0;
+    Frame frame = IAU_EARTH();
+    std::vector<MeasurementType> measurement_types{MeasurementType::Range, MeasurementType::Doppler};
+    StochasticNoise range_noise_km{2e-3, 0.0}, doppler_noise_km_s{3e-6, 0.0};
+    static GroundStation dss65_madrid(double mask, StochasticNoise r, StochasticNoise d) { return {"Madrid", 40.427222, 4.250556, 0.834939, mask, IAU_EARTH(), {MeasurementType::Range, MeasurementType::Doppler}, r, d}; }
+    static GroundStation dss34_canberra(double mask, StochasticNoise r, StochasticNoise d) { return {"Canberra", -35.398333, 148.981944, 0.691750, mask, IAU_EARTH(), {MeasurementType::Range, MeasurementType::Doppler}, r, d}; }
+    static GroundStation dss13_goldstone(double mask, StochasticNoise r, StochasticNoise d) { return {"Goldstone", 35.247164, 243.205, 1.07114904, mask, IAU_EARTH(), {MeasurementType::Range, MeasurementType::Doppler}, r, d}; }
+    // geodetic -> body-fixed position and local zenith on the frame's ellipsoid (anise Orbit::try_latlongalt)
+    void body_fixed(double pos[3], double up[3]) const {
+        const double a = frame.mean_equatorial_radius_km, b = frame.polar_radius_km > 0 ? frame.polar_radius_km : a;
+        const double e2 = 1.0 - (b * b) / (a * a), d2r = 3.14159265358979323846 / 180.0;
+        const double sl = std::sin(latitude_deg * d2r), cl = std::cos(latitude_deg * d2r), so = std::sin(longitude_deg * d2r), co = std::cos(longitude_deg * d2r);
+        const double nu = a / std::sqrt(1.0 - e2 * sl * sl);
+        pos[0] = (nu + height_km) * cl * co; pos[1] = (nu + height_km) * cl * so; pos[2] = (nu * (1.0 - e2) + height_km) * sl;
+        up[0] = cl * co; up[1] = cl * so; up[2] = sl;
+    }
+    nyxb_ground_station to_c(const Frame& integration_frame, int32_t body_index, double central_radius_km) const {
+        nyxb_ground_station g{};
+        body_fixed(g.pos_fixed_km, g.up_fixed);
+        g.elevation_mask_deg = elevation_mask_deg; g.rot = frame.rotation;
+        const bool same = frame.ephemeris_id == integration_frame.ephemeris_id;
+        g.body = same ? NYXB_CENTRAL_BODY : body_index;
+        g.body_radius_km = same ? -1.0 : central_radius_km;
+        g.n_types = (int32_t)measurement_types.size();
+        for (int q = 0; q < g.n_types && q < 2; ++q) {
+            g.types[q] = (int32_t)measurement_types[q];
+            const StochasticNoise& nz = measurement_types[q] == MeasurementType::Range ? range_noise_km : doppler_noise_km_s;
+            g.noise_var[q] = nz.covariance(); g.bias[q] = nz.bias_constant;
+        }
+        return g;
+    }
+};
+
+struct ProcessNoise3D {   // od/snc.rs:38-56, 118-134, 288-311
+    double diag[3] = {0, 0, 0}; int64_t disable_time = 0; bool ric = false;
+    static ProcessNoise3D from_diagonal(const double (&v)[3], int64_t disable, bool ric_frame = false) { ProcessNoise3D p; for (int i = 0; i < 3; ++i) p.diag[i] = v[i]; p.disable_time = disable; p.ric = ric_frame; return p; }
+    static ProcessNoise3D from_velocity_km_s(const double (&v)[3], int64_t noise_duration, int64_t disable, bool ric_frame = false) {
+        ProcessNoise3D p; for (int i = 0; i < 3; ++i) p.diag[i] = v[i] / ((double)noise_duration * 1e-9); p.disable_time = disable; p.ric = ric_frame; return p;
+    }
+};
+
+struct KfEstimate {   // od/estimate/kfestimate.rs: nominal state + 9x9 covariance (row-major here)
+    Spacecraft nominal_state; double covar[81] = {0};
+    static KfEstimate from_diag(const Spacecraft& s, const double (&d)[9]) { KfEstimate e; e.nominal_state = s; for (int i = 0; i < 9; ++i) e.covar[i * 9 + i] = d[i]; return e; }
+};
+
+// one tracking schedule, n observation sets: obs[(k*2 + type)*n + i], NaN = type not in the measurement's data
+struct TrackingDataArc { std::vector<int64_t> epoch_ns; std::vector<std::string> tracker; std::vector<double> obs; size_t n = 0; };
+
+struct ODSolution {
+    size_t n = 0, m = 0;
+    std::vector<double> state, covar, state_dev, resid_ratio, prefit, postfit;   // [9][n], [81][n] (c*9+r), [9][n], [m][2][n] x3
+    std::vector<int64_t> epoch; std::vector<int32_t> msr_flags, status; std::vector<nyxb_details> details;
+    Spacecraft final_state(const Spacecraft& tmpl, size_t i) const { return detail::unpack(tmpl, state, epoch, n, i); }
+};
+
+// KalmanODProcess (od/process/{initializers.rs:60-113, mod.rs:128-497}); msr_size 2 = SpacecraftKalmanOD, 1 = SpacecraftKalmanScalarOD
+class KalmanODProcess {
+  public:
+    Propagator prop; KalmanVariant variant; std::optional<SigmaRejection> sigma_reject; std::vector<GroundStation> devices;
+    const Almanac* almanac = nullptr; std::optional<ProcessNoise3D> process_noise;
+    int64_t max_step = 60 * NS_PER_S, epoch_precision = 1000; int32_t msr_size = 2;
+    KalmanODProcess(Propagator p, KalmanVariant v, std::optional<SigmaRejection> rej, std::vector<GroundStation> dev, const Almanac* alm = nullptr, int32_t msr = 2)
+        : prop(std::move(p)), variant(v), sigma_reject(rej), devices(std::move(dev)), almanac(alm), msr_size(msr) {}
+    KalmanODProcess& with_process_noise(ProcessNoise3D snc) { process_noise = snc; return *this; }
+
+    ODSolution process_arcs(const std::vector<KfEstimate>& initial, const TrackingDataArc& arc) const {
+        const size_t n = initial.size(), m = arc.epoch_ns.size();
+        if (arc.n != n || arc.obs.size() != m * 2 * n || arc.tracker.size() != m) throw std::runtime_error("arc shape does not match the filters");
+        std::vector<Spacecraft> noms; for (auto& e : initial) noms.push_back(e.nominal_state);
+        const Frame& frame = noms.at(0).frame;
+        auto eng = detail::make_engine(prop.dynamics, frame, almanac, prop.method, prop.opts, prop.mode, prop.device);
+        detail::Soa soa(noms);
+        std::vector<double> cov0(81 * n);
+        for (size_t i = 0; i < n; ++i) for (int r = 0; r < 9; ++r) for (int c = 0; c < 9; ++c) cov0[(size_t)(c * 9 + r) * n + i] = initial[i].covar[r * 9 + c];
+        std::vector<nyxb_ground_station> st;
+        for (auto& d : devices) {
+            int32_t bi = NYXB_CENTRAL_BODY;
+            if (d.frame.ephemeris_id != frame.ephemeris_id) {
+                if (!almanac) throw std::runtime_error("an almanac with the station's body is needed");
+                bi = -2;
+                for (size_t j = 0; j < almanac->bodies.size(); ++j) if (almanac->bodies[j].ephemeris_id == d.frame.ephemeris_id) bi = (int32_t)j;
+                if (bi == -2) throw std::runtime_error("no ephemeris loaded for the station's body");
+            }
+            st.push_back(d.to_c(frame, bi, frame.mean_equatorial_radius_km));
+        }
+        std::vector<int32_t> trk(m);
+        for (size_t k = 0; k < m; ++k) { trk[k] = -1; for (size_t j = 0; j < devices.size(); ++j) if (devices[j].name == arc.tracker[k]) trk[k] = (int32_t)j; }
+        nyxb_od_config cfg{};
+        cfg.variant = (int32_t)variant; cfg.msr_size = msr_size; cfg.reject_num_sigmas = sigma_reject ? sigma_reject->num_sigmas : -1.0;
+        cfg.max_step_ns = max_step; cfg.epoch_precision_ns = epoch_precision;
+        if (process_noise) { cfg.snc_enabled = 1; cfg.snc_frame = process_noise->ric ? 1 : 0; for (int i = 0; i < 3; ++i) cfg.snc_diag[i] = process_noise->diag[i]; cfg.snc_disable_time_ns = process_noise->disable_time; }
+        nyxb_tracking_arc carc{(int64_t)m, arc.epoch_ns.data(), trk.data(), arc.obs.data()};
+        ODSolution s; s.n = n; s.m = m;
+        s.state.resize(9 * n); s.epoch.resize(n); s.covar.resize(81 * n); s.state_dev.resize(9 * n); s.resid_ratio.resize(m * 2 * n); s.prefit.resize(m * 2 * n);
+        s.postfit.resize(m * 2 * n); s.msr_flags.resize(m * n); s.details.resize(n); s.status.resize(n);
+        nyxb_od_outputs out{s.state.data(), s.epoch.data(), s.covar.data(), s.state_dev.data(), s.resid_ratio.data(), s.prefit.data(), s.postfit.data(),
+                            s.msr_flags.data(), nullptr, nullptr, s.details.data(), s.status.data()};
+        if (nyxb_od_ekf_batch(eng.get(), &cfg, (int32_t)st.size(), st.data(), &carc, n, soa.state.data(), soa.consts.data(), soa.epoch.data(), cov0.data(), &out) != NYXB_RC_OK)
+            throw std::runtime_error(std::string("nyxb_od_ekf_batch: ") + nyxb_last_error());
+        return s;
     }
 };
 

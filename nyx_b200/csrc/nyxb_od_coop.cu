@@ -36,6 +36,13 @@ __device__ __forceinline__ double wsum(double v) {
 __device__ __forceinline__ D3 wsum(D3 a) { return D3{wsum(a.v), wsum(a.x), wsum(a.y), wsum(a.z)}; }
 __device__ __forceinline__ D3 dfma(D3 acc, D3 t, double c) { return D3{fma(t.v, c, acc.v), fma(t.x, c, acc.x), fma(t.y, c, acc.y), fma(t.z, c, acc.z)}; }
 
+__device__ __forceinline__ D3 dsel(bool c, D3 a, D3 b) { return c ? a : b; }
+// complex dual product (ar + i ai)(br + i bi)
+__device__ __forceinline__ void cmul(const D3& ar, const D3& ai, const D3& br, const D3& bi, D3& rr, D3& ri) {
+    rr = ar * br - ai * bi;
+    ri = ar * bi + ai * br;
+}
+
 // GravityField::gradient split by columns over the lanes of a warp.  pw: per-warp D3 tables RM/IM/RP of N+2 entries each.
 __device__ static void grav_gradient_coop(const DevGrav& g, const int* __restrict__ mycols, long long t_ns, const double r_in[3],
                                           D3* __restrict__ pw, int lane, double acc[3], double Gm[9]) {
@@ -52,16 +59,28 @@ __device__ static void grav_gradient_coop(const DevGrav& g, const int* __restric
     const D3 r_ = dnorm(rx, ry, rz);
     const D3 s_ = rx / r_, t_ = ry / r_, u_ = rz / r_;
     const D3 rho = dc(g.r_eq) / r_;
-    {   // powers (s + i t)^j and (mu / r) rho^(j+1), j = 0..N: every lane runs the recurrence, lane j % 32 keeps entry j
-        D3 rm = dc(1.0), im = dc(0.0), rp = (dc(g.mu) / r_) * rho;
+    {   // powers z^j = (s + i t)^j and (mu / r) rho^(j+1), j = 0..N, in log depth: lane l forms z^l from the binary digits of l
+        // (the squarings z, z^2, .., z^16 are uniform), then z^(l+32), z^(l+64), .. by the uniform factor z^32.
+        D3 zr = s_, zi = t_, pr = dc(1.0), pi = dc(0.0), qr = rho, qp = dc(1.0);
+#pragma unroll 1
+        for (int b = 0; b < 5; ++b) {
+            D3 nr, ni;
+            cmul(pr, pi, zr, zi, nr, ni);
+            const bool on = (lane >> b) & 1;
+            pr = dsel(on, nr, pr); pi = dsel(on, ni, pi);
+            qp = dsel(on, qp * qr, qp);
+            cmul(zr, zi, zr, zi, nr, ni);
+            zr = nr; zi = ni;
+            qr = qr * qr;
+        }
+        const D3 c0 = (dc(g.mu) / r_) * rho;   // (mu / r) rho^(0+1)
         __syncwarp();
-        if (lane == 0) { RM[0] = rm; IM[0] = im; RP[0] = rp; }
-        for (int j = 1; j <= N; ++j) {
-            D3 nr = s_ * rm - t_ * im;
-            D3 ni = s_ * im + t_ * rm;
-            rm = nr; im = ni;
-            rp = rp * rho;
-            if ((j & 31) == lane) { RM[j] = rm; IM[j] = im; RP[j] = rp; }
+        for (int j = lane; j <= N; j += 32) {
+            RM[j] = pr; IM[j] = pi; RP[j] = c0 * qp;
+            D3 nr, ni;
+            cmul(pr, pi, zr, zi, nr, ni);
+            pr = nr; pi = ni;
+            qp = qp * qr;
         }
         __syncwarp();
     }

@@ -49,3 +49,32 @@ def all_gather_final_states(local, n_total: int, group=None):
         lo, hi = shard_bounds(n_total, world, r)
         out[:, lo:hi] = recv[r, :, : hi - lo]
     return out
+
+
+def shard_tracking_arc(arc, world_size: int, rank: int):
+    """The observation sets of this rank's filters: one tracking schedule, obs[m][2][lo:hi] (od/process/mod.rs:128-497 runs are
+    independent, so an ensemble of filters shards exactly like an ensemble of propagations)."""
+    from .od import TrackingDataArc
+
+    lo, hi = shard_bounds(arc.n, world_size, rank)
+    return TrackingDataArc(arc.epoch_ns, list(arc.tracker), np.ascontiguousarray(arc.obs[:, :, lo:hi]))
+
+
+def sharded_process_arcs(odp, initial_estimates, arc, group=None, device=None):
+    """n filters split over the ranks by contiguous index; every rank runs `process_arcs` on its shard (ONE launch), then
+    ONE all-gather of [9 state + 81 covariance] per filter gives every rank the full, index-ordered set of final estimates.
+    Returns (local ODSolution, final_state[9][n], covar[n][9][9])."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n = len(initial_estimates)
+    lo, hi = shard_bounds(n, world, rank)
+    sol = odp.process_arcs(initial_estimates[lo:hi], shard_tracking_arc(arc, world, rank))
+    local = np.concatenate([sol.final_state_soa, sol.covar.reshape(hi - lo, 81).T], axis=0)  # [90][n_local]
+    t = torch.from_numpy(np.ascontiguousarray(local))
+    if device is not None:
+        t = t.to(device)
+    full = all_gather_final_states(t, n, group).cpu().numpy()
+    return sol, full[:9], np.ascontiguousarray(full[9:].T).reshape(n, 9, 9)

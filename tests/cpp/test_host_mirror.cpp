@@ -67,6 +67,78 @@ int main() {
         try { Propagator::default_(dynamics).with(bad).for_duration(60 * NS_PER_S); } catch (const PropagationError& e) { threw = e.status == NYXB_ERR_FUEL_EXHAUSTED; }
         CHECK(threw);
     }
+    {   // STM (tests/propagation/stm.rs:33-118 shape): RK4 fixed 10 s, ten steps, two-body; chaining through stm_in reproduces the run
+        auto setup = Propagator::new_(dynamics, IntegratorMethod::RungeKutta4, IntegratorOptions::with_fixed_step_s(10.0));
+        auto r = setup.propagate_batch_stm({init}, 100 * NS_PER_S);
+        CHECK(r.status[0] == 0 && r.details[0].n_steps == 10);
+        CHECK(std::fabs(r.phi(1, 0, 0, 3) - 100.0) < 0.2 && std::fabs(r.phi(1, 0, 0, 0) - 1.0) < 0.02);   // dr/dv ~ t, dr/dr ~ 1
+        CHECK(r.phi(1, 0, 6, 6) == 1.0 && r.phi(1, 0, 3, 6) == 0.0);
+        auto h1 = setup.propagate_batch_stm({init}, 50 * NS_PER_S);
+        Spacecraft mid = init; mid.x_km = h1.state[0]; mid.y_km = h1.state[1]; mid.z_km = h1.state[2]; mid.vx_km_s = h1.state[3]; mid.vy_km_s = h1.state[4];
+        mid.vz_km_s = h1.state[5]; mid.epoch_ns = h1.epoch[0];
+        auto h2 = setup.propagate_batch_stm({mid}, 100 * NS_PER_S, nullptr, &h1.stm);
+        CHECK(std::memcmp(h2.stm.data(), r.stm.data(), 81 * sizeof(double)) == 0);
+    }
+    {   // device dispersions: shard-invariant, right spread
+        Spacecraft nominal = init; nominal.frame = EARTH_J2000(); nominal.dry_mass_kg = 100.0;
+        const double sd[9] = {1.0, 1.0, 1.0, 1e-3, 1e-3, 1e-3, 0, 0, 0};
+        MonteCarlo mc(nominal, sd, "cpp-mvn", 5);
+        auto all = mc.generate_states_on_device(0, 2000), tail = mc.generate_states_on_device(1500, 500);
+        CHECK(all[1500].x_km == tail[0].x_km && all[1999].vz_km_s == tail[499].vz_km_s);
+        double m = 0, v = 0;
+        for (auto& sc : all) m += sc.x_km - nominal.x_km;
+        m /= 2000;
+        for (auto& sc : all) v += (sc.x_km - nominal.x_km - m) * (sc.x_km - nominal.x_km - m);
+        CHECK(std::fabs(m) < 0.1 && std::fabs(std::sqrt(v / 2000) - 1.0) < 0.1);
+    }
+    {   // sequential filter (tests/orbit_determination/two_body.rs shape): EKF on synthetic range + Doppler from three DSN stations
+        const Frame eme = EARTH_J2000();
+        Spacecraft truth = Spacecraft::cartesian(-2436.45, -2436.45, 6891.037, 5.088611, -5.088611, 0.0, 0, eme);
+        truth.dry_mass_kg = 500.0;
+        const int m = 30;
+        std::vector<GroundStation> dev{GroundStation::dss65_madrid(-90.0, {1e-2, 0}, {1e-5, 0}), GroundStation::dss34_canberra(-90.0, {1e-2, 0}, {1e-5, 0}),
+                                       GroundStation::dss13_goldstone(-90.0, {1e-2, 0}, {1e-5, 0})};
+        // truth states every 60 s (one trajectory, restartable PropInstance), noise-free observations computed with the same geometry
+        auto tset = Propagator::rk89(dynamics, IntegratorOptions::with_fixed_step_s(10.0));
+        auto tprop = tset.with(truth);
+        TrackingDataArc arc; arc.n = 2; arc.obs.assign((size_t)m * 2 * 2, 0.0);
+        Spacecraft last = truth;
+        for (int k = 0; k < m; ++k) {
+            last = tprop.for_duration(60 * NS_PER_S);
+            const GroundStation& gs = dev[(k / 10) % 3];
+            double p[3], up[3]; gs.body_fixed(p, up);
+            // IAU Earth with ra0 = 0, dec0 = 90 deg: inertial -> fixed = R3(W) R1(0) R3(90 deg) = R3(W + 90 deg), W = 190.147 + 360.9856235 d
+            // (the secular pole drift is < 1e-5 rad over this arc: ignored in this synthetic data)
+            const double d = (double)last.epoch_ns * 1e-9 / 86400.0, w = std::fmod(190.147 + 90.0 + 360.9856235 * d, 360.0) * 3.14159265358979323846 / 180.0;
+            const double wd = 360.9856235 * 3.14159265358979323846 / 180.0 / 86400.0;
+            const double rtx[3] = {std::cos(w) * p[0] - std::sin(w) * p[1], std::sin(w) * p[0] + std::cos(w) * p[1], p[2]};
+            const double vtx[3] = {-wd * rtx[1], wd * rtx[0], 0.0};
+            const double dr[3] = {last.x_km - rtx[0], last.y_km - rtx[1], last.z_km - rtx[2]}, dv[3] = {last.vx_km_s - vtx[0], last.vy_km_s - vtx[1], last.vz_km_s - vtx[2]};
+            const double rng = std::sqrt(dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2]);
+            arc.epoch_ns.push_back(last.epoch_ns); arc.tracker.push_back(gs.name);
+            for (size_t i = 0; i < 2; ++i) {
+                arc.obs[((size_t)k * 2 + 0) * 2 + i] = rng;
+                arc.obs[((size_t)k * 2 + 1) * 2 + i] = (dr[0] * dv[0] + dr[1] * dv[1] + dr[2] * dv[2]) / rng;
+            }
+        }
+        Spacecraft e0 = truth, e1 = truth;
+        e0.x_km += 0.5; e0.vy_km_s += 4e-4; e1.z_km -= 0.6; e1.vx_km_s -= 3e-4;
+        const double p0[9] = {1, 1, 1, 1e-6, 1e-6, 1e-6, 0, 0, 0};
+        KalmanODProcess odp(Propagator::default_(dynamics), KalmanVariant::ReferenceUpdate, std::nullopt, dev);
+        const double q[3] = {1e-12, 1e-12, 1e-12};
+        odp.with_process_noise(ProcessNoise3D::from_diagonal(q, 600 * NS_PER_S, true));
+        auto sol = odp.process_arcs({KfEstimate::from_diag(e0, p0), KfEstimate::from_diag(e1, p0)}, arc);
+        for (size_t i = 0; i < 2; ++i) {
+            CHECK(sol.status[i] == 0 && sol.epoch[i] == last.epoch_ns);
+            Spacecraft f = sol.final_state(truth, i);
+            const double err = std::sqrt((f.x_km - last.x_km) * (f.x_km - last.x_km) + (f.y_km - last.y_km) * (f.y_km - last.y_km) + (f.z_km - last.z_km) * (f.z_km - last.z_km));
+            CHECK(err < 0.1);   // from 0.5 / 0.6 km
+            CHECK(sol.covar[(size_t)(0 * 9 + 0) * 2 + i] < 0.05);
+        }
+        int processed = 0;
+        for (int k = 0; k < m; ++k) processed += (sol.msr_flags[(size_t)k * 2] & NYXB_MSRF_PROCESSED) ? 1 : 0;
+        CHECK(processed == m);
+    }
     std::printf(failures ? "FAILED (%d)\n" : "OK\n", failures);
     return failures ? 1 : 0;
 }

@@ -220,3 +220,62 @@ def test_warp_cooperative_filter_matches_oracle_and_per_thread_kernel(oracle, or
     assert np.abs(sol.final_state_soa[:3] - ref.final_state_soa[:3]).max() < 1e-7
     assert np.abs(sol.covar - ref.covar).max() <= 1e-7 * np.abs(ref.covar).max()
     assert np.allclose(sol.resid_ratio, ref.resid_ratio, rtol=1e-6, atol=1e-9, equal_nan=True)
+
+
+def test_filter_edge_cases_match_oracle(oracle, oracle_od):
+    """process_arc corner cases (od/process/mod.rs:211-426): two measurements at the same epoch (zero-length propagation,
+    identity STM), an unknown tracker (skipped, no time update), a pass below the elevation mask (device.measure -> None:
+    no update and NO STM reset), a measurement with only one of the device's two types in its data (identity H row, zero
+    observation, as coded), and measurement epochs farther apart than the filter's max_step (time updates in between)."""
+    sc = leo_od_scenario(oracle, n=3, n_msr=24, seed=13, cadence_s=150, reject=None, elevation_mask_deg=-90.0)
+    arc = sc["arc"]
+    ep = arc.epoch_ns.copy()
+    ep[5] = ep[4]                      # same epoch, other station
+    trk = list(arc.tracker)
+    trk[5] = "Canberra" if trk[4] != "Canberra" else "Madrid"
+    trk[7] = "Atlantis"                # not in the devices
+    obs = arc.obs.copy()
+    obs[9, 1, :] = np.nan              # Doppler missing from measurement 9
+    # recompute the observations of the moved measurement 5 for its new station / epoch
+    moved = nb.simulate_tracking(ep[5:6], sc["truth"][4:5], sc["devices"], [trk[5]], sc["frame"], None, None)
+    obs[5] = moved.obs[0]
+    sc["arc"] = nb.TrackingDataArc(ep, trk, obs)
+    # one station with a high mask: some of its passes are reported by the simulator-free arc but invisible to the filter
+    sc["devices"]["Goldstone"].elevation_mask_deg = 89.0
+    sc["odp"].devices = sc["devices"]
+    sc["prop"].mode = nb.MODE_STRICT
+    sol = sc["odp"].process_arcs(sc["ests"], sc["arc"], record_estimates=True)
+    _compare_filters(sol, sc, oracle_od, 1e-6, 1e-9, 3)
+    fl = sol.msr_flags[:, 0]
+    assert fl[7] == 0                                      # unknown tracker: nothing happened
+    gold = [k for k, t in enumerate(trk) if t == "Goldstone"]
+    assert gold and all(fl[k] == abi.MSRF_NOT_VISIBLE for k in gold)
+    assert fl[5] & abi.MSRF_PROCESSED and fl[9] & abi.MSRF_PROCESSED
+    assert sol.details["n_steps"][0] >= 3 * 22            # 150 s between epochs, 60 s max_step: 3 steps per interval
+
+
+def test_od_argument_validation():
+    frame = nb.EARTH_J2000
+    dyn = nb.SpacecraftDynamics.new(nb.OrbitalDynamics.two_body())
+    prop = nb.Propagator.default(dyn)
+    sc0 = nb.Spacecraft.from_orbit(nb.Orbit.keplerian(7000.0, 0.01, 51.6, 30.0, 40.0, 10.0, 0, frame))
+    est = nb.KfEstimate.from_diag(sc0, [1, 1, 1, 1e-6, 1e-6, 1e-6, 0, 0, 0])
+    gs = nb.GroundStation.dss65_madrid(0.0, nb.StochasticNoise(1e-2), nb.StochasticNoise(1e-5))
+    odp = nb.SpacecraftKalmanOD(prop, nb.KalmanVariant.ReferenceUpdate, None, {"Madrid": gs}, None)
+    one = nb.TrackingDataArc(np.array([60 * S]), ["Madrid"], np.zeros((1, 2, 1)))
+    with pytest.raises(nb.ODError, match="TooFewMeasurements"):
+        odp.process_arcs([est], one)
+    two = nb.TrackingDataArc(np.array([60 * S, 120 * S]), ["Madrid", "Madrid"], np.full((2, 2, 1), 7000.0))
+    odp.max_step = 0
+    with pytest.raises(nb.ODError, match="StepSize"):
+        odp.process_arcs([est], two)
+    odp.max_step = 60 * S
+    drag = nb.SpacecraftDynamics.from_model(nb.OrbitalDynamics.two_body(), nb.Drag(nb.AtmDensity.Constant(1e-12), nb.IAU_EARTH_FRAME))
+    odp2 = nb.SpacecraftKalmanOD(nb.Propagator.default(drag), nb.KalmanVariant.ReferenceUpdate, None, {"Madrid": gs}, None)
+    with pytest.raises(nb.PropagationError, match="PartialsUndefined"):
+        odp2.process_arcs([est], two)
+    gs2 = nb.GroundStation.dss65_madrid(0.0, nb.StochasticNoise(1e-2), nb.StochasticNoise(1e-5))
+    gs2.integration_time = 60 * S
+    odp3 = nb.SpacecraftKalmanOD(prop, nb.KalmanVariant.ReferenceUpdate, None, {"Madrid": gs2}, None)
+    with pytest.raises(nb.ODError, match="instantaneous"):
+        odp3.process_arcs([est], two)
