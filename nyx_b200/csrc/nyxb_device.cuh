@@ -230,6 +230,7 @@ __device__ __forceinline__ void rotation_dcm(const DevRotation& rot, long long t
 __device__ __forceinline__ bool body_position(const DevBody& b, long long t_ns, double pos[3]) {
     long long dt = t_ns - b.t0_ns;
     if (dt < 0) return false;
+#if NYXB_STRICT
     long long idx = dt / b.interval_ns;
     if (idx >= b.n_intervals) return false;
     long long off = dt - idx * b.interval_ns;
@@ -247,6 +248,30 @@ __device__ __forceinline__ bool body_position(const DevBody& b, long long t_ns, 
         }
         pos[ax] = (tau * b1 - b2) + __ldg(ca);
     }
+#else
+    // FAST: interval index from the reciprocal (no 64-bit division; +-1 corrected), the three axes share one Clenshaw loop
+    long long idx = (long long)((double)dt * b.inv_interval);
+    long long off = dt - idx * b.interval_ns;
+    if (off < 0) { idx -= 1; off += b.interval_ns; }
+    else if (off >= b.interval_ns) { idx += 1; off -= b.interval_ns; }
+    if (idx >= b.n_intervals) return false;
+    const double tau = fma(2.0 * (double)off, b.inv_interval, -1.0);
+    const double tau2 = 2.0 * tau;
+    const int nc = b.n_coeffs;
+    const double* cx = b.coeffs + (size_t)idx * 3 * (size_t)nc;
+    const double* cy = cx + nc;
+    const double* cz = cy + nc;
+    double x1 = 0.0, x2 = 0.0, y1 = 0.0, y2 = 0.0, z1 = 0.0, z2 = 0.0;
+    for (int k = nc - 1; k >= 1; --k) {
+        const double xk = fma(tau2, x1, __ldg(cx + k) - x2);
+        const double yk = fma(tau2, y1, __ldg(cy + k) - y2);
+        const double zk = fma(tau2, z1, __ldg(cz + k) - z2);
+        x2 = x1; x1 = xk; y2 = y1; y1 = yk; z2 = z1; z1 = zk;
+    }
+    pos[0] = fma(tau, x1, __ldg(cx) - x2);
+    pos[1] = fma(tau, y1, __ldg(cy) - y2);
+    pos[2] = fma(tau, z1, __ldg(cz) - z2);
+#endif
     return true;
 }
 
@@ -257,6 +282,18 @@ __device__ __forceinline__ double circ_seg_area(double r, double d) {
 
 __device__ inline double occultation(const double r_eb[3], const double r_ls[3], double light_radius, double body_radius) {
     double n_ls = norm3(r_ls[0], r_ls[1], r_ls[2]), n_eb = norm3(r_eb[0], r_eb[1], r_eb[2]);
+#if !NYXB_STRICT
+    {   // FAST: the common case "the two disks are far apart" (d' > r_ls' + r_fobj', result 0) decided without asin/acos:
+        // with s = sin of an apparent radius (< 1), d' > a + b  <=>  cos d' < cos a cos b - sin a sin b.  A 1e-9 guard band
+        // sends everything near the boundary to the full evaluation below, so the returned values are unchanged.
+        const double sl = light_radius / n_ls, sb = body_radius / n_eb;
+        if (sl < 1.0 && sb < 1.0) {
+            const double cd = -((r_ls[0] * r_eb[0] + r_ls[1] * r_eb[1]) + r_ls[2] * r_eb[2]) / (n_eb * n_ls);
+            const double cs = sqrt((1.0 - sl * sl) * (1.0 - sb * sb)) - sl * sb;
+            if (cd < cs - 1e-9) return 0.0;
+        }
+    }
+#endif
     double r_ls_prime = (light_radius >= n_ls) ? light_radius : asin(light_radius / n_ls);
     double r_fobj_prime = (body_radius >= n_eb) ? body_radius : asin(body_radius / n_eb);
     double dot = (r_ls[0] * r_eb[0] + r_ls[1] * r_eb[1]) + r_ls[2] * r_eb[2];
@@ -383,9 +420,16 @@ __device__ inline int accel_point_masses(const DevSetup& S, long long t_ns, cons
             double n_j = norm3(rj0, rj1, rj2);
             double r_j3 = n_j * n_j * n_j;
             double nmu = -S.bodies[j].mu;
+#if NYXB_STRICT
             dx[0] += nmu * (rj0 / r_j3 + bpos[j][0] / r_ij3);
             dx[1] += nmu * (rj1 / r_j3 + bpos[j][1] / r_ij3);
             dx[2] += nmu * (rj2 / r_j3 + bpos[j][2] / r_ij3);
+#else
+            const double i_j3 = 1.0 / r_j3, i_ij3 = 1.0 / r_ij3;   // FAST: two reciprocals instead of six divisions
+            dx[0] += nmu * fma(rj0, i_j3, bpos[j][0] * i_ij3);
+            dx[1] += nmu * fma(rj1, i_j3, bpos[j][1] * i_ij3);
+            dx[2] += nmu * fma(rj2, i_j3, bpos[j][2] * i_ij3);
+#endif
         }
         acc[0] += dx[0]; acc[1] += dx[1]; acc[2] += dx[2];
     }
@@ -407,7 +451,12 @@ __device__ inline void accel_post(const DevSetup& S, long long t_ns, const doubl
         const double* sun = bpos[S.srp.sun_body];
         double rs[3] = { y[0] - sun[0], y[1] - sun[1], y[2] - sun[2] };
         double n_sun = norm3(rs[0], rs[1], rs[2]);
+#if NYXB_STRICT
         double unit[3] = { rs[0] / n_sun, rs[1] / n_sun, rs[2] / n_sun };
+#else
+        const double i_sun = 1.0 / n_sun;
+        double unit[3] = { rs[0] * i_sun, rs[1] * i_sun, rs[2] * i_sun };
+#endif
         double occult = 0.0;
         double r_ls[3] = { -rs[0], -rs[1], -rs[2] };
         for (int q = 0; q < S.srp.n_shadow; ++q) {
@@ -423,7 +472,12 @@ __device__ inline void accel_post(const DevSetup& S, long long t_ns, const doubl
         double inv = 1.0 / r_sun_au;
         double flux_pressure = (k * S.srp.phi / NYXB_C_M_S) * (inv * inv);
         double scal = 1e-3 * cr * srp_area * flux_pressure;
+#if NYXB_STRICT
         acc[0] += (scal * unit[0]) / mass; acc[1] += (scal * unit[1]) / mass; acc[2] += (scal * unit[2]) / mass;
+#else
+        const double sm = scal / mass;
+        acc[0] = fma(sm, unit[0], acc[0]); acc[1] = fma(sm, unit[1], acc[1]); acc[2] = fma(sm, unit[2], acc[2]);
+#endif
     }
     if (S.has_drag) {
         double R[9];
@@ -465,6 +519,7 @@ __device__ inline void accel_post(const DevSetup& S, long long t_ns, const doubl
 
 // SpacecraftDynamics::eom for one trajectory on one thread: y[9] -> dy[0..5] (dy[6..8] == 0).
 // Returns 0 or an nyxb_status error code.
+template <bool GRAV = true>
 __device__ inline int eom_full(const DevSetup& S, long long epoch_ns, double delta_t_s, const double y[9],
                                double dry_mass, double extra_mass, double srp_area, double drag_area, double dy[6]) {
     long long t_ns = epoch_ns + dur_from_seconds(delta_t_s);
@@ -475,7 +530,7 @@ __device__ inline int eom_full(const DevSetup& S, long long epoch_ns, double del
     double bpos[NYXB_MAX_BODIES][3];
     int rc = accel_pre(S, t_ns, y, bpos, acc);
     if (rc) return rc;
-    if (S.has_grav) {
+    if (GRAV && S.has_grav) {
         double ga[3];
         grav_accel_rows(S.grav, t_ns, y, ga);
         acc[0] += ga[0]; acc[1] += ga[1]; acc[2] += ga[2];

@@ -42,13 +42,14 @@ struct Inst {
 };
 
 // instance.rs:358-493
+template <bool GRAV>
 __device__ static int derive(const DevSetup& S, Inst& in, long long& dt_ns, double next[9]) {
     double k[NYXB_MAX_STAGES][6];
     const int stages = S.tb.stages;
     in.det_attempts = 1;
     double h = dur_to_seconds(in.step_ns);
     for (;;) {
-        int rc = eom_full(S, in.epoch_ns, 0.0, in.y, in.dry_mass, in.extra_mass, in.srp_area, in.drag_area, k[0]);
+        int rc = eom_full<GRAV>(S, in.epoch_ns, 0.0, in.y, in.dry_mass, in.extra_mass, in.srp_area, in.drag_area, k[0]);
         in.n_rhs++;
         if (rc) return rc;
         for (int i = 0; i < stages - 1; ++i) {
@@ -68,7 +69,7 @@ __device__ static int derive(const DevSetup& S, Inst& in, long long& dt_ns, doub
             // components 6..8 have zero derivative: y + h*0 (NaN-propagating like the reference's 90-vector algebra, instance.rs:394)
             const double hz = h * 0.0;
             ys[6] = in.y[6] + hz; ys[7] = in.y[7] + hz; ys[8] = in.y[8] + hz;
-            rc = eom_full(S, in.epoch_ns, S.tb.c[i] * h, ys, in.dry_mass, in.extra_mass, in.srp_area, in.drag_area, k[i + 1]);
+            rc = eom_full<GRAV>(S, in.epoch_ns, S.tb.c[i] * h, ys, in.dry_mass, in.extra_mass, in.srp_area, in.drag_area, k[i + 1]);
             in.n_rhs++;
             if (rc) return rc;
         }
@@ -129,10 +130,11 @@ __device__ __forceinline__ void record_state(const Inst& in, long long s) {
 }
 
 // instance.rs:343-352 + spacecraft.rs:158-189
+template <bool GRAV>
 __device__ static int single_step(const DevSetup& S, Inst& in) {
     long long dt;
     double next[9];
-    int rc = derive(S, in, dt, next);
+    int rc = derive<GRAV>(S, in, dt, next);
     if (rc) return rc;
     in.epoch_ns += dt;
 #pragma unroll
@@ -144,6 +146,7 @@ __device__ static int single_step(const DevSetup& S, Inst& in) {
 }
 
 // instance.rs:87-262
+template <bool GRAV>
 __device__ static int propagate(const DevSetup& S, Inst& in, long long duration_ns) {
     if (duration_ns == 0) return 0;
     long long stop = in.epoch_ns + duration_ns;
@@ -158,14 +161,14 @@ __device__ static int propagate(const DevSetup& S, Inst& in, long long duration_
             int prev_fixed = in.fixed;
             in.step_ns = stop - epoch;
             in.fixed = 1;
-            int rc = single_step(S, in);
+            int rc = single_step<GRAV>(S, in);
             if (rc) return rc;
             in.step_ns = prev_step;
             in.fixed = prev_fixed;
             if (backprop) in.step_ns = -in.step_ns;
             return 0;
         }
-        int rc = single_step(S, in);
+        int rc = single_step<GRAV>(S, in);
         if (rc) return rc;
         if (in.sink.ev_kind) {  // stop condition, evaluated on non-final steps only (instance.rs:243-252, event.rs:120-150)
             const double yn = event_eval(in.sink.ev_kind, in.sink.ev_value, in.y[0], in.y[1], in.y[2], in.y[3], in.y[4], in.y[5]);
@@ -176,6 +179,8 @@ __device__ static int propagate(const DevSetup& S, Inst& in, long long duration_
     }
 }
 
+// GRAV = false: the instantiation for dynamics without a gravity field (no Legendre scratch: fewer registers, smaller stack)
+template <bool GRAV>
 __global__ void __launch_bounds__(128)
 NYXB_KTHREAD(const __grid_constant__ DevSetup S, size_t n,
              const double* __restrict__ state, const double* __restrict__ consts,
@@ -199,7 +204,7 @@ NYXB_KTHREAD(const __grid_constant__ DevSetup S, size_t n,
     record_state(in, 0);  // start state (instance.rs:307, 321)
     in.ev_count = 0;
     in.ev_prev = sink.ev_kind ? event_eval(sink.ev_kind, sink.ev_value, in.y[0], in.y[1], in.y[2], in.y[3], in.y[4], in.y[5]) : 0.0;
-    int rc = propagate(S, in, end_epoch - in.epoch_ns);
+    int rc = propagate<GRAV>(S, in, end_epoch - in.epoch_ns);
     if (sink.ev_kind) {
         sink.ev_crossings[i] = in.ev_count;
         if (rc == 0 && in.ev_count < sink.ev_trigger) rc = NYXB_ERR_EVENT_NOT_FOUND;  // event.rs:177-182
@@ -224,7 +229,11 @@ extern "C" cudaError_t NYXB_LAUNCH_THREAD(const DevSetup* S, size_t n, const dou
                                           int* out_status, int block, const DevSink* sink, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     unsigned grid = (unsigned)((n + block - 1) / block);
-    NYXB_KTHREAD<<<grid, block, 0, stream>>>(*S, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch,
-                                             out_details, out_status, *sink);
+    if (S->has_grav)
+        NYXB_KTHREAD<true><<<grid, block, 0, stream>>>(*S, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch,
+                                                       out_details, out_status, *sink);
+    else
+        NYXB_KTHREAD<false><<<grid, block, 0, stream>>>(*S, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch,
+                                                        out_details, out_status, *sink);
     return cudaGetLastError();
 }
