@@ -15,6 +15,7 @@ from .frames import (EARTH, EARTH_J2000, GMAT_EARTH_GM, GMAT_MOON_GM, GMAT_SUN_G
 from .gravity import GravityFieldData
 from .monte_carlo import DispersedState, MonteCarlo, MvnSpacecraft, Results, Run
 from .trajectory import Traj, TrajError, hermite_eval
+from .config import PropagatorConfig, integrator_options_from, load_ground_stations, parse_duration
 from .event import Event, brent, locate_event
 from .od import (GroundStation, KalmanODProcess, KalmanVariant, KfEstimate, LocalFrame, MeasurementType, ODError, ODSolution,
                  ProcessNoise3D, SigmaRejection, SpacecraftKalmanOD, SpacecraftKalmanScalarOD, SpacecraftUncertainty,
