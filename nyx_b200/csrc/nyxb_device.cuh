@@ -281,19 +281,21 @@ __device__ __forceinline__ double circ_seg_area(double r, double d) {
 }
 
 __device__ inline double occultation(const double r_eb[3], const double r_ls[3], double light_radius, double body_radius) {
-    double n_ls = norm3(r_ls[0], r_ls[1], r_ls[2]), n_eb = norm3(r_eb[0], r_eb[1], r_eb[2]);
 #if !NYXB_STRICT
-    {   // FAST: the common case "the two disks are far apart" (d' > r_ls' + r_fobj', result 0) decided without asin/acos:
+    {   // FAST: the common case "the two disks are far apart" (d' > r_ls' + r_fobj', result 0) decided without asin/acos/division:
         // with s = sin of an apparent radius (< 1), d' > a + b  <=>  cos d' < cos a cos b - sin a sin b.  A 1e-9 guard band
         // sends everything near the boundary to the full evaluation below, so the returned values are unchanged.
-        const double sl = light_radius / n_ls, sb = body_radius / n_eb;
+        const double i_ls = rsqrt(fma(r_ls[2], r_ls[2], fma(r_ls[1], r_ls[1], r_ls[0] * r_ls[0])));
+        const double i_eb = rsqrt(fma(r_eb[2], r_eb[2], fma(r_eb[1], r_eb[1], r_eb[0] * r_eb[0])));
+        const double sl = light_radius * i_ls, sb = body_radius * i_eb;
         if (sl < 1.0 && sb < 1.0) {
-            const double cd = -((r_ls[0] * r_eb[0] + r_ls[1] * r_eb[1]) + r_ls[2] * r_eb[2]) / (n_eb * n_ls);
+            const double cd = -((r_ls[0] * r_eb[0] + r_ls[1] * r_eb[1]) + r_ls[2] * r_eb[2]) * (i_eb * i_ls);
             const double cs = sqrt((1.0 - sl * sl) * (1.0 - sb * sb)) - sl * sb;
             if (cd < cs - 1e-9) return 0.0;
         }
     }
 #endif
+    double n_ls = norm3(r_ls[0], r_ls[1], r_ls[2]), n_eb = norm3(r_eb[0], r_eb[1], r_eb[2]);
     double r_ls_prime = (light_radius >= n_ls) ? light_radius : asin(light_radius / n_ls);
     double r_fobj_prime = (body_radius >= n_eb) ? body_radius : asin(body_radius / n_eb);
     double dot = (r_ls[0] * r_eb[0] + r_ls[1] * r_eb[1]) + r_ls[2] * r_eb[2];
@@ -400,8 +402,13 @@ __device__ inline void grav_accel_rows(const DevGrav& g, long long t_ns, const d
 //   (gravity)  : GravityField                           gravity_field.rs:148-268
 //   accel_post : SolarPressure + Drag, each / mass      spacecraft.rs:238-243
 __device__ __forceinline__ void accel_two_body(const DevSetup& S, const double y[9], double acc[3]) {
+#if NYXB_STRICT
     double rmag = norm3(y[0], y[1], y[2]);
     double fac = -S.mu_central / (rmag * rmag * rmag);
+#else
+    const double ir = rsqrt(fma(y[2], y[2], fma(y[1], y[1], y[0] * y[0])));   // FAST: one rsqrt chain instead of sqrt + division
+    double fac = -S.mu_central * (ir * ir * ir);
+#endif
     acc[0] = fac * y[0]; acc[1] = fac * y[1]; acc[2] = fac * y[2];
 }
 
@@ -414,18 +421,21 @@ __device__ inline int accel_point_masses(const DevSetup& S, long long t_ns, cons
         double dx[3] = {0.0, 0.0, 0.0};
         for (int j = 0; j < S.n_bodies; ++j) {
             if (!((S.point_mass_mask >> j) & 1u)) continue;
-            double n_ij = norm3(bpos[j][0], bpos[j][1], bpos[j][2]);
-            double r_ij3 = n_ij * n_ij * n_ij;
             double rj0 = y[0] - bpos[j][0], rj1 = y[1] - bpos[j][1], rj2 = y[2] - bpos[j][2];
-            double n_j = norm3(rj0, rj1, rj2);
-            double r_j3 = n_j * n_j * n_j;
             double nmu = -S.bodies[j].mu;
 #if NYXB_STRICT
+            double n_ij = norm3(bpos[j][0], bpos[j][1], bpos[j][2]);
+            double r_ij3 = n_ij * n_ij * n_ij;
+            double n_j = norm3(rj0, rj1, rj2);
+            double r_j3 = n_j * n_j * n_j;
             dx[0] += nmu * (rj0 / r_j3 + bpos[j][0] / r_ij3);
             dx[1] += nmu * (rj1 / r_j3 + bpos[j][1] / r_ij3);
             dx[2] += nmu * (rj2 / r_j3 + bpos[j][2] / r_ij3);
 #else
-            const double i_j3 = 1.0 / r_j3, i_ij3 = 1.0 / r_ij3;   // FAST: two reciprocals instead of six divisions
+            // FAST: |r|^-3 from two rsqrt chains instead of two sqrt + six divisions
+            const double i_ij = rsqrt(fma(bpos[j][2], bpos[j][2], fma(bpos[j][1], bpos[j][1], bpos[j][0] * bpos[j][0])));
+            const double i_j = rsqrt(fma(rj2, rj2, fma(rj1, rj1, rj0 * rj0)));
+            const double i_j3 = i_j * i_j * i_j, i_ij3 = i_ij * i_ij * i_ij;
             dx[0] += nmu * fma(rj0, i_j3, bpos[j][0] * i_ij3);
             dx[1] += nmu * fma(rj1, i_j3, bpos[j][1] * i_ij3);
             dx[2] += nmu * fma(rj2, i_j3, bpos[j][2] * i_ij3);
@@ -450,11 +460,12 @@ __device__ inline void accel_post(const DevSetup& S, long long t_ns, const doubl
     if (S.has_srp) {
         const double* sun = bpos[S.srp.sun_body];
         double rs[3] = { y[0] - sun[0], y[1] - sun[1], y[2] - sun[2] };
-        double n_sun = norm3(rs[0], rs[1], rs[2]);
 #if NYXB_STRICT
+        double n_sun = norm3(rs[0], rs[1], rs[2]);
         double unit[3] = { rs[0] / n_sun, rs[1] / n_sun, rs[2] / n_sun };
 #else
-        const double i_sun = 1.0 / n_sun;
+        const double d2_sun = fma(rs[2], rs[2], fma(rs[1], rs[1], rs[0] * rs[0]));
+        const double i_sun = rsqrt(d2_sun);
         double unit[3] = { rs[0] * i_sun, rs[1] * i_sun, rs[2] * i_sun };
 #endif
         double occult = 0.0;
@@ -468,8 +479,12 @@ __device__ inline void accel_post(const DevSetup& S, long long t_ns, const doubl
             if (p > occult) occult = p;
         }
         double k = fabs(occult - 1.0);
+#if NYXB_STRICT
         double r_sun_au = n_sun / NYXB_AU_KM;
         double inv = 1.0 / r_sun_au;
+#else
+        const double inv = NYXB_AU_KM * i_sun;
+#endif
         double flux_pressure = (k * S.srp.phi / NYXB_C_M_S) * (inv * inv);
         double scal = 1e-3 * cr * srp_area * flux_pressure;
 #if NYXB_STRICT
