@@ -29,6 +29,10 @@ extern "C" int nyxb_od_coop_kmax(void);
 extern "C" cudaError_t nyxb_launch_mvn(unsigned long long, unsigned long long, size_t, const double*, const double*, const double*,
                                        double*, double*, cudaStream_t);
 
+// layout of the PODs the host mirrors rely on (nyx_b200/abi.py, tests/test_abi.py)
+static_assert(sizeof(nyxb_integ_opts) == 48 && sizeof(nyxb_rotation) == 56 && sizeof(nyxb_srp) == 40 && sizeof(nyxb_details) == 48, "ABI layout");
+static_assert(sizeof(nyxb_ground_station) == 176 && sizeof(nyxb_od_config) == 72 && sizeof(nyxb_tracking_arc) == 32 && sizeof(nyxb_od_outputs) == 96, "ABI layout");
+
 static thread_local std::string g_err;
 static void set_err(const std::string& s) { g_err = s; }
 #define CUDA_TRY(x)                                                                                   \

@@ -44,6 +44,31 @@ def test_product_fails_loudly_without_gpu():
         prop.with_(sc).for_duration(60 * nb.Unit.Second)
 
 
+def test_new_entry_points_reject_bad_arguments_and_need_a_gpu():
+    """STM / OD / dispersion entry points: argument validation runs before any device work; without a CUDA device they
+    report NYXB_RC_NO_DEVICE instead of computing on the host."""
+    import numpy as np
+    import torch
+
+    lib = abi.load_library()
+    vp = C.c_void_p
+    assert lib.nyxb_propagate_batch_stm(None, 1, None, None, None, 0, None, None, None, None, None, None, None) == -1
+    assert b"null" in lib.nyxb_last_error()
+    assert lib.nyxb_od_ekf_batch(None, None, 0, None, None, 1, None, None, None, None, None) == -1
+    assert lib.nyxb_mvn_sample(0, 1, 0, 4, None, None, None, None, None) == -1
+    if not torch.cuda.is_available():
+        t = np.zeros(9); L = np.eye(9).reshape(81); out = np.zeros((9, 4))
+        rc = lib.nyxb_mvn_sample(0, 1, 0, 4, t.ctypes.data, None, L.ctypes.data, out.ctypes.data, None)
+        assert rc == -2 and b"no CUDA device" in lib.nyxb_last_error()   # NYXB_RC_NO_DEVICE: no CPU fallback
+
+
+def test_od_struct_layouts():
+    assert C.sizeof(abi.GroundStationC) == 176
+    assert C.sizeof(abi.OdConfigC) == 72
+    assert C.sizeof(abi.TrackingArcC) == 32
+    assert C.sizeof(abi.OdOutputsC) == 96
+
+
 def test_missing_library_is_an_error(monkeypatch, tmp_path):
     monkeypatch.setattr(abi, "_lib", None)
     monkeypatch.setenv("NYXB_LIBRARY", str(tmp_path / "nope.so"))
