@@ -1,0 +1,114 @@
+"""Size-independent properties at BASELINE.json's FULL sizes (the oracle cannot cover these in seconds): shard / permutation
+invariance (trajectories are independent, so any split of the ensemble must give bit-identical results), forward-backward round
+trips, span splitting, and bit-parity of the STRICT kernel against the oracle on a sample drawn from the full ensemble.
+Tolerances: round trip over 3 days (two adaptive passes, FAST) < 1e-4 km; split span < 1e-5 km (different step sequence after
+the restart); everything that only regroups trajectories: bit-exact."""
+import numpy as np
+import pytest
+
+import nyx_b200 as nb
+
+from .util import S
+
+pytestmark = pytest.mark.gpu
+DAY = 86400 * S
+
+
+def _c2(n, degree=21):
+    rng = np.random.Generator(np.random.PCG64(0))
+    frame = nb.EARTH_J2000
+    gd = nb.GravityFieldData.from_fixture("jgm3_70x70", degree, degree, nb.IAU_EARTH_FRAME)
+    dyn = nb.SpacecraftDynamics.new(nb.OrbitalDynamics.from_model(nb.GravityField.new(gd)))
+    orbit = nb.Orbit.keplerian(6378.1363 + 300.0, 0.015, 68.5, 65.2, 75.0, 0.0, 0, frame)
+    template = nb.Spacecraft(orbit=orbit, mass=nb.Mass(1000.0, 0.0, 0.0))
+    mvn = nb.MvnSpacecraft.from_cartesian_std(template, 1.0, 1e-3)
+    st = np.ascontiguousarray((template.to_vector()[None, :] + mvn.sample_vectors(rng, n)).T)
+    cs = np.zeros((4, n)); cs[0] = 1000.0
+    return frame, dyn, st, cs, np.zeros(n, dtype=np.int64)
+
+
+def test_c2_full_size_invariances_fast():
+    n = 10_000
+    frame, dyn, st, cs, ep = _c2(n)
+    eng = nb.Propagator.default(dyn, mode=nb.MODE_FAST).engine(frame, None)
+    out, oep, det, status = eng.propagate_batch(st, cs, ep, 3 * DAY)
+    assert (status == 0).all() and (oep == 3 * DAY).all()
+    assert 3.5e7 < det["n_steps"].sum() < 4.5e7                       # ~3.9e7 accepted steps
+    # shards: the two halves on their own reproduce the full batch bit for bit
+    a = eng.propagate_batch(st[:, :5000].copy(), cs[:, :5000].copy(), ep[:5000].copy(), 3 * DAY)[0]
+    b = eng.propagate_batch(st[:, 5000:].copy(), cs[:, 5000:].copy(), ep[5000:].copy(), 3 * DAY)[0]
+    assert np.array_equal(np.concatenate([a, b], axis=1), out)
+    # permutation of the run order permutes the results
+    perm = np.random.default_rng(1).permutation(n)
+    p = eng.propagate_batch(np.ascontiguousarray(st[:, perm]), cs[:, perm].copy(), ep[perm].copy(), 3 * DAY)[0]
+    assert np.array_equal(p, out[:, perm])
+    # forward then backward returns to the start
+    back, bep, _, bst = eng.propagate_batch(out, cs, oep, 0)
+    assert (bst == 0).all() and (bep == 0).all()
+    assert np.sqrt(((back[:3] - st[:3]) ** 2).sum(0)).max() < 1e-4
+    # split span (the adapted step is carried like a PropInstance would): same end state to the truncation level
+    step = np.full(n, 60 * S, dtype=np.int64)
+    mid, mep, _, _ = eng.propagate_batch(st, cs, ep, 3 * DAY // 2, step_ns=step)
+    fin, fep, _, _ = eng.propagate_batch(mid, cs, mep, 3 * DAY, step_ns=step)
+    assert np.sqrt(((fin[:3] - out[:3]) ** 2).sum(0)).max() < 1e-5
+
+
+def test_c2_full_size_strict_bit_parity_sample(oracle):
+    n = 10_000
+    frame, dyn, st, cs, ep = _c2(n)
+    prop = nb.Propagator.default(dyn, mode=nb.MODE_STRICT)
+    out, oep, det, status = prop.engine(frame, None).propagate_batch(st, cs, ep, 3 * DAY)
+    assert (status == 0).all()
+    idx = np.random.default_rng(2).choice(n, 256, replace=False)
+    packed = dyn.pack(frame, None)
+    ref, _, rdet, _ = oracle.propagate_batch(packed.c, prop.opts.to_c(prop.method), np.ascontiguousarray(st[:, idx]), cs[:, idx].copy(), ep[idx].copy(), 3 * DAY)
+    assert np.array_equal(out[:, idx], ref) and np.array_equal(det["n_steps"][idx], rdet["n_steps"])
+
+
+def test_c3_full_size_invariances():
+    """100 000 JWST-like trajectories, Sun + Moon point masses + SRP with Earth / Moon shadows, 30 days (BASELINE configs[2])."""
+    n = 100_000
+    frame = nb.EARTH_J2000
+    alm = nb.Almanac.synthetic(frame, 0, 32.0)
+    srp = nb.SolarPressure.new([nb.EARTH_J2000, nb.MOON_J2000], alm)
+    dyn = nb.SpacecraftDynamics.from_model(nb.OrbitalDynamics.point_masses([nb.MOON, nb.SUN]), srp)
+    orbit = nb.Orbit.cartesian(119901.070276, -1389299.665421, -1041369.150539, 0.045956, -0.013168, 0.034535, 0, frame)
+    template = nb.Spacecraft(orbit=orbit, mass=nb.Mass(6200.0, 0.0, 0.0), srp=nb.SRPData(21.197 * 14.162, 1.56))
+    mvn = nb.MvnSpacecraft.from_cartesian_std(template, 0.5, 1e-4)
+    st = np.ascontiguousarray((template.to_vector()[None, :] + mvn.sample_vectors(np.random.default_rng(0), n)).T)
+    cs = np.zeros((4, n)); cs[0] = 6200.0; cs[2] = template.srp.area_m2
+    ep = np.zeros(n, dtype=np.int64)
+    eng = nb.Propagator.default(dyn, mode=nb.MODE_FAST).engine(frame, alm)
+    out, oep, det, status = eng.propagate_batch(st, cs, ep, 30 * DAY)
+    assert (status == 0).all() and det["n_steps"].min() > 900          # steps saturate near max_step = 2700 s
+    k = 37_123
+    a = eng.propagate_batch(st[:, :k].copy(), cs[:, :k].copy(), ep[:k].copy(), 30 * DAY)[0]
+    b = eng.propagate_batch(st[:, k:].copy(), cs[:, k:].copy(), ep[k:].copy(), 30 * DAY)[0]
+    assert np.array_equal(np.concatenate([a, b], axis=1), out)
+    back, bep, _, bst = eng.propagate_batch(out, cs, oep, 0)
+    assert (bst == 0).all() and np.sqrt(((back[:3] - st[:3]) ** 2).sum(0)).max() < 1e-3   # 1.7e6 km from the Earth, 2 x 30 days
+
+
+def test_c4_size_shard_invariance_and_round_trip():
+    """2 000 low-lunar-orbit trajectories, GRAIL 70x70 + Earth/Sun point masses (BASELINE configs[3]; 1 of the 7 days)."""
+    from nyx_b200.frames import EARTH
+
+    n = 2000
+    frame = nb.MOON_J2000
+    alm = nb.Almanac.synthetic(frame, 0, 3.0, bodies=(EARTH, nb.SUN))
+    gd = nb.GravityFieldData.from_fixture("luna_jggrx_80x80", 70, 70, nb.IAU_MOON_FRAME)
+    dyn = nb.SpacecraftDynamics.new(nb.OrbitalDynamics.new([nb.PointMasses.new([EARTH, nb.SUN]), nb.GravityField.new(gd)]))
+    orbit = nb.Orbit.keplerian(1737.4 + 100.0, 0.001, 90.0, 10.0, 0.0, 0.0, 0, frame)
+    template = nb.Spacecraft(orbit=orbit, mass=nb.Mass(1000.0, 0.0, 0.0))
+    mvn = nb.MvnSpacecraft.from_cartesian_std(template, 0.1, 1e-4)
+    st = np.ascontiguousarray((template.to_vector()[None, :] + mvn.sample_vectors(np.random.default_rng(0), n)).T)
+    cs = np.zeros((4, n)); cs[0] = 1000.0
+    ep = np.zeros(n, dtype=np.int64)
+    eng = nb.Propagator.default(dyn, mode=nb.MODE_FAST).engine(frame, alm)
+    out, oep, det, status = eng.propagate_batch(st, cs, ep, DAY)
+    assert (status == 0).all() and eng.lanes() == 32
+    a = eng.propagate_batch(st[:, :777].copy(), cs[:, :777].copy(), ep[:777].copy(), DAY)[0]
+    b = eng.propagate_batch(st[:, 777:].copy(), cs[:, 777:].copy(), ep[777:].copy(), DAY)[0]
+    assert np.array_equal(np.concatenate([a, b], axis=1), out)
+    back, _, _, bst = eng.propagate_batch(out, cs, oep, 0)
+    assert (bst == 0).all() and np.sqrt(((back[:3] - st[:3]) ** 2).sum(0)).max() < 1e-5
