@@ -115,8 +115,8 @@ __device__ static void grav_gradient_coop(const DevGrav& g, const int* __restric
             const D3 t3 = dscale(rr * b1, v11);
             ZC = dfma(ZC, t3, C); ZS = dfma(ZS, t3, Sv);
             if (n < N) {
-                const DevHarm* rec1 = g.tab + tri(n + 1, m);        // row n+1, column m
-                const DevHarm* rec2 = g.tab + tri(n + 2, m + 1);    // row n+2, column m+1
+                const DevHarm* rec1 = rec + (n + 1);                // row n+1, column m:     tri(n+1, m) - tri(n, m) = n + 1
+                const DevHarm* rec2 = rec1 + (n + 3);               // row n+2, column m+1:   tri(n+2, m+1) - tri(n+1, m) = n + 3
                 D3 an, bn;
                 if (n == m) {
                     an = (dc(__ldg(g.offdiag + m)) * u_) * a;                                // A[m+1][m]
@@ -180,7 +180,9 @@ struct Ctx {
 };
 
 // one RHS: stage slot `slot` of the shared k / Ai arrays receives (v, a) and the A-matrix parts
-__device__ static int eom_coop(const Ctx& cx, InstC& in, double delta_t_s, const double ys[9], int slot) {
+// __noinline__: called from two places in derive_coop; one copy keeps the kernel's instruction footprint (and the
+// instruction-cache misses ncu shows as `no_inst` stalls) down
+__device__ __noinline__ static int eom_coop(const Ctx& cx, InstC& in, double delta_t_s, const double ys[9], int slot) {
     const DevSetup& S = *cx.S;
     long long t_ns = in.epoch_ns + dur_from_seconds(delta_t_s);
     double yy[9];

@@ -14,8 +14,13 @@ __device__ __forceinline__ D3 operator*(D3 a, D3 b) {
     return D3{a.v * b.v, b.v * a.x + a.v * b.x, b.v * a.y + a.v * b.y, b.v * a.z + a.v * b.z};
 }
 __device__ __forceinline__ D3 operator/(D3 a, D3 b) {
+#if NYXB_STRICT
     double den = b.v * b.v;
     return D3{a.v / b.v, (b.v * a.x - a.v * b.x) / den, (b.v * a.y - a.v * b.y) / den, (b.v * a.z - a.v * b.z) / den};
+#else
+    const double r = 1.0 / b.v, q = a.v * r;   // FAST: one division; d(a/b) = (da - (a/b) db) / b
+    return D3{q, (a.x - q * b.x) * r, (a.y - q * b.y) * r, (a.z - q * b.z) * r};
+#endif
 }
 __device__ __forceinline__ D3 dscale(D3 a, double c) { return D3{a.v * c, a.x * c, a.y * c, a.z * c}; }
 __device__ __forceinline__ D3 ddivs(D3 a, double c) { return D3{a.v / c, a.x / c, a.y / c, a.z / c}; }
