@@ -11,6 +11,10 @@
  *     -> PropInstance::derive              propagators/instance.rs:358-493
  *     -> SpacecraftDynamics::eom           dynamics/spacecraft.rs:191-310
  *
+ * plus the "next" rows of SURVEY.md §8(f) that sit on the same path: trajectory recording, event-terminated runs,
+ * STM propagation and the sequential Kalman filter of od/process (nyxb_propagate_batch_stm, nyxb_od_ekf_batch), and
+ * on-device dispersions (nyxb_mvn_sample).
+ *
  * A Rust shim packs `Vec<Spacecraft>` into the SoA arrays
  * below, calls nyxb_propagate_batch through `extern "C"`, and unpacks the final
  * states into `Results` / `Vec<Spacecraft>`.  Nothing here mentions torch or CUDA
@@ -30,7 +34,7 @@
 extern "C" {
 #endif
 
-#define NYXB_ABI_VERSION 1
+#define NYXB_ABI_VERSION 2 /* 2: nyxb_srp gained `estimate`; STM, filter and dispersion entry points */
 
 /* ---- IntegratorMethod — propagators/rk_methods/mod.rs:65-79 (same order) ---- */
 enum nyxb_method {

@@ -11,6 +11,7 @@ from pathlib import Path
 
 import numpy as np
 
+NYXB_ABI_VERSION = 2  # include/nyxb.h
 NYXB_MAX_BODIES = 8
 NYXB_CENTRAL_BODY = -1
 
@@ -332,6 +333,8 @@ def load_library():
             "(nyx_b200 has no CPU fallback by design)"
         )
     _lib = _declare(C.CDLL(str(path)))
+    if _lib.nyxb_abi_version() != NYXB_ABI_VERSION:
+        raise NyxbLibraryMissing(f"{path} exports ABI {_lib.nyxb_abi_version()}, this package needs {NYXB_ABI_VERSION}: rebuild (make -C nyx_b200/csrc)")
     return _lib
 
 
