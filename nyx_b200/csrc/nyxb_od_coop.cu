@@ -115,8 +115,8 @@ __device__ static void grav_gradient_coop(const DevGrav& g, const int* __restric
             const D3 t3 = dscale(rr * b1, v11);
             ZC = dfma(ZC, t3, C); ZS = dfma(ZS, t3, Sv);
             if (n < N) {
-                const DevHarm* rec1 = rec + (n + 1);                // row n+1, column m:     tri(n+1, m) - tri(n, m) = n + 1
-                const DevHarm* rec2 = rec1 + (n + 3);               // row n+2, column m+1:   tri(n+2, m+1) - tri(n+1, m) = n + 3
+                const DevHarm* rec1 = g.tab + tri(n + 1, m);        // row n+1, column m
+                const DevHarm* rec2 = g.tab + tri(n + 2, m + 1);    // row n+2, column m+1
                 D3 an, bn;
                 if (n == m) {
                     an = (dc(__ldg(g.offdiag + m)) * u_) * a;                                // A[m+1][m]
