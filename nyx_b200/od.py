@@ -200,7 +200,7 @@ class ProcessNoise3D:
 
 def dcm_ric_to_inertial(orbit: Orbit) -> np.ndarray:
     """Columns R, I, C (anise `Orbit::dcm_to_inertial(LocalFrame::RIC)`): R = r/|r|, C = h/|h|, I = C x R."""
-    r, v = orbit.radius_km(), orbit.velocity_km_s()
+    r, v = orbit.radius_km, orbit.velocity_km_s
     rh = r / np.linalg.norm(r)
     h = np.cross(r, v)
     ch = h / np.linalg.norm(h)

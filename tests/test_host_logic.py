@@ -100,3 +100,41 @@ def test_dynamics_lowering_to_the_c_abi():
         nb.SpacecraftDynamics.new(nb.OrbitalDynamics.point_masses([nb.SUN])).pack(frame, None)
     kep = nb.Orbit.keplerian(7000.0, 0.01, 30.0, 10.0, 20.0, 30.0, 0, frame)
     assert abs(kep.rmag_km() - 7000.0 * (1 - 0.01**2) / (1 + 0.01 * np.cos(np.radians(30.0)))) < 1e-9
+
+
+def test_od_host_objects():
+    """Host-side OD mirror (nyx_b200/od.py): RIC DCM, SpacecraftUncertainty::to_estimate (sc_uncertainty.rs:70-138, D^T C D as coded),
+    KfEstimate::state (Spacecraft + OVector<9> clamps Cr, cosmic/spacecraft.rs:713-728), SNC from a velocity noise (snc.rs:288-311),
+    geodetic -> body-fixed station coordinates."""
+    import numpy as np
+
+    import nyx_b200 as nb
+    from nyx_b200.od import dcm_ric_to_inertial
+
+    orbit = nb.Orbit.keplerian(7000.0, 0.01, 51.6, 30.0, 40.0, 10.0, 0, nb.EARTH_J2000)
+    D = dcm_ric_to_inertial(orbit)
+    assert np.allclose(D @ D.T, np.eye(3), atol=1e-14) and abs(np.linalg.det(D) - 1.0) < 1e-14
+    r, v = orbit.radius_km, orbit.velocity_km_s
+    assert np.allclose(D[:, 0], r / np.linalg.norm(r)) and np.allclose(D[:, 2], np.cross(r, v) / np.linalg.norm(np.cross(r, v)))
+    sc = nb.Spacecraft(orbit=orbit, srp=nb.SRPData(2.0, 1.9))
+    unc = nb.SpacecraftUncertainty(sc, nb.LocalFrame.RIC, 0.5, 0.3, 1.5, 1e-4, 6e-4, 3e-3, coeff_reflectivity=0.2)
+    est = unc.to_estimate()
+    P = est.covar
+    assert np.allclose(P, P.T) and (np.linalg.eigvalsh(P[:6, :6]) > 0).all()
+    assert abs(np.trace(P[:3, :3]) - (0.5**2 + 0.3**2 + 1.5**2)) < 1e-12 and abs(P[6, 6] - 0.04) < 1e-15 and P[7, 7] == 0.0
+    d6 = np.zeros((6, 6)); d6[:3, :3] = D; d6[3:, 3:] = D
+    assert np.allclose(P[:6, :6], d6.T @ np.diag([0.25, 0.09, 2.25, 1e-8, 3.6e-7, 9e-6]) @ d6)
+    inertial = nb.SpacecraftUncertainty(sc).to_estimate().covar
+    assert np.allclose(np.diag(inertial)[:6], [0.25, 0.25, 0.25, 2.5e-7, 2.5e-7, 2.5e-7])
+    with pytest.raises(nb.ODError):
+        nb.SpacecraftUncertainty(sc, x_km=-1.0).to_estimate()
+    est.state_deviation = np.array([1, 0, 0, 0, 0, 0, 0.5, 0.1, 2.0])
+    st = est.state()
+    assert st.srp.coeff_reflectivity == 2.0 and abs(st.orbit.radius_km[0] - (r[0] + 1.0)) < 1e-12 and st.mass.prop_mass_kg == 2.0
+    snc = nb.ProcessNoise3D.from_velocity_km_s([1e-10, 2e-10, 3e-10], 1 * nb.Unit.Hour, 10 * nb.Unit.Minute)
+    assert np.allclose(snc.diag, np.array([1e-10, 2e-10, 3e-10]) / 3600.0) and snc.disable_time == 600 * 10**9
+    gs = nb.GroundStation("pole", 90.0, 0.0, 0.0, nb.IAU_EARTH_FRAME)
+    pos, up = gs.body_fixed()
+    assert abs(pos[2] - 6356.75) < 1e-9 and abs(pos[0]) < 1e-9 and np.allclose(up, [0, 0, 1], atol=1e-15)
+    eq = nb.GroundStation("equator", 0.0, 90.0, 1.0, nb.IAU_EARTH_FRAME).body_fixed()[0]
+    assert np.allclose(eq, [0.0, 6379.14, 0.0], atol=1e-9)
