@@ -237,6 +237,33 @@ extern "C" nyxb_engine* nyxb_engine_create(const nyxb_dynamics* dyn, const nyxb_
         S.grav.tab = upload(e, tab.data(), tab.size());
         S.grav.a_diag = upload(e, adiag.data(), adiag.size());
         S.grav.offdiag = upload(e, offd.data(), offd.size());
+        {   // records of the FAST per-thread column walk (grav_accel_cols, nyxb_device.cuh), in walk order
+            const int ncols = std::min(N, g.order) + 1;
+            auto T = [&](int n, int m) -> const DevHarm& { return tab[(size_t)n * (n + 1) / 2 + m]; };
+            std::vector<double> cr;
+            cr.reserve((size_t)ncols * (N + 2) * 8);
+            const double inv_req = 1.0 / g.r_eq_km;
+            auto push = [&](int k, int j) {
+                double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (j <= N && k <= g.order) { v[0] = (double)k * sqrt2 * T(j, k).cbar * inv_req; v[1] = (double)k * sqrt2 * T(j, k).sbar * inv_req; }
+                if (j <= N) { v[2] = sqrt2 * T(j, k - 1).vr01 * T(j, k - 1).cbar * inv_req; v[3] = sqrt2 * T(j, k - 1).vr01 * T(j, k - 1).sbar * inv_req; }
+                if (j >= 2) { v[4] = sqrt2 * T(j - 1, k - 1).vr11 * T(j - 1, k - 1).cbar * inv_req; v[5] = sqrt2 * T(j - 1, k - 1).vr11 * T(j - 1, k - 1).sbar * inv_req; }
+                if (j <= N) {
+                    if (j == k) { v[6] = offd[k]; v[7] = 0.0; }
+                    else { v[6] = T(j + 1, k).b; v[7] = T(j + 1, k).c; }
+                }
+                cr.insert(cr.end(), v, v + 8);
+            };
+            for (int k = 1; k <= ncols; k += 2) {   // walk order of grav_accel_cols: columns in pairs, rows interleaved
+                const bool two = k + 1 <= ncols;
+                push(k, k);
+                for (int j = k + 1; j <= N + 1; ++j) { push(k, j); if (two) push(k + 1, j); }
+            }
+            cr.insert(cr.end(), 8, 0.0);            // null record: target of the last prefetch
+            S.grav.colrec = upload(e, cr.data(), cr.size());
+            S.grav.ncols = ncols;
+            if (!S.grav.colrec) { set_err("gravity table upload failed"); delete e; return nullptr; }
+        }
         if (!S.grav.tab || !S.grav.a_diag || !S.grav.offdiag) { set_err("gravity table upload failed"); delete e; return nullptr; }
     }
     if (dyn->srp) {
@@ -279,7 +306,10 @@ static int pick_lanes(const nyxb_engine* e, size_t n) {
     if (e->lanes > 0) return e->lanes;
     // auto: cooperative lanes only pay off when the harmonic sum dominates
     if (!e->S.has_grav || e->S.grav.N < 6) return 1;
-    (void)n;
+    // FAST, moderate degree, very large ensembles: one thread per trajectory (column walk, grav_accel_cols) has enough warps to
+    // hide its latencies and issues ~3x fewer instructions per trajectory than the cooperative kernel
+    // (measured on B200, 21x21: 100 000 trajectories 1.13e8 vs 1.07e8 steps/s; 10 000 trajectories 5.0e7 vs 9.0e7)
+    if (e->mode == NYXB_MODE_FAST && e->S.grav.N < 30 && n >= 65536) return 1;
     return (e->S.grav.N >= 48) ? 32 : ((e->S.grav.N >= 30) ? 16 : 8);
 }
 

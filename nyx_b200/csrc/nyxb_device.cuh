@@ -49,6 +49,11 @@ struct DevGrav {
     const DevHarm* tab;      // (N+2)(N+3)/2 records
     const double* a_diag;    // [N+3]   gravity_field.rs:61-66
     const double* offdiag;   // [N+2]   sqrt(2n+3), n = 0..N+1   gravity_field.rs:168-173
+    // FAST per-thread column walk (grav_accel_cols): 8 doubles per (column k, row j) in walk order — columns in pairs (k, k+1):
+    // row k of column k, then rows j = k+1..N+1 of both columns interleaved; one null record at the end:
+    // {q1..q6: the entry's coefficients of the six per-column sums (1/r_eq folded in), b, c: factors of A[j+1][k]}
+    const double* colrec;
+    int ncols;
 };
 
 struct DevSrp {
@@ -392,6 +397,91 @@ __device__ inline void grav_accel_rows(const DevGrav& g, long long t_ns, const d
     for (int i = 0; i < 3; ++i) acc[i] = (R[i] * ab0 + R[3 + i] * ab1) + R[6 + i] * ab2;
 }
 
+#if !NYXB_STRICT
+// GravityField::eom for one trajectory on one thread, FAST mode: the double sum walked by COLUMNS of the derived-Legendre
+// triangle.  Each A[j][k] is produced by its column recursion in a register and consumed once: the four sums of the
+// reference (gravity_field.rs:217-249) are regrouped per column k — sum2/sum3 re-indexed by k = m + 1 — so that all terms of
+// a column share the pair (r_{k-1}, i_{k-1}) = (cos, sin)((k-1) lambda) cos^(k-1)(phi), applied once per column:
+//   P1,P2 = sum_j rr_j     A[j][k] k sqrt2 (C,S)_{j,k}            -> a0 += r P1 + i P2,  a1 += r P2 - i P1
+//   P3,P4 = sum_j rr_j     A[j][k] sqrt2 vr01(j,k-1) (C,S)_{j,k-1}    -> a2 += r P3 + i P4
+//   P5,P6 = sum_j rr_{j-1} A[j][k] sqrt2 vr11(j-1,k-1) (C,S)_{j-1,k-1} -> a3 -= r P5 + i P6
+// No Legendre rows in local memory, no trig/power tables: the running powers advance once per column.  Every thread of a
+// warp walks the same (k, j) sequence, so the 64-byte records are warp-uniform loads.  12 FP64 instructions per entry.
+__device__ inline void grav_accel_cols(const DevGrav& g, long long t_ns, const double r_in[3], double acc[3]) {
+    const int N = g.N;
+    double R[9];
+    rotation_dcm(g.rot, t_ns, R);
+    double rb[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) rb[i] = fma(R[3 * i + 2], r_in[2], fma(R[3 * i + 1], r_in[1], R[3 * i] * r_in[0]));
+    const double ir = rsqrt(fma(rb[2], rb[2], fma(rb[1], rb[1], rb[0] * rb[0])));
+    const double s_ = rb[0] * ir, t_ = rb[1] * ir, u_ = rb[2] * ir;
+    const double rho = g.r_eq * ir;
+    const double irho = 1.0 / rho;
+    double rk = 1.0, ik = 0.0;                 // (r_{k-1}, i_{k-1})
+    double rho_k = (g.mu * ir) * rho * rho;    // (mu / r) rho^(k+1) at k = 1
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    // Columns are walked in PAIRS (k, k+1): two independent recursion chains per thread hide the FP64 latency, both use the same
+    // rr_j.  Records come in walk order and are software-pipelined one entry ahead (the table ends with a null record).
+    const double2* __restrict__ p = reinterpret_cast<const double2*>(g.colrec);
+    double2 n12 = __ldg(p), n34 = __ldg(p + 1), n56 = __ldg(p + 2), nbc = __ldg(p + 3);
+    p += 4;
+#define NYXB_COL_ENTRY(A, Ap, P1, P2, P3, P4, P5, P6)                                                            \
+    {                                                                                                            \
+        const double2 q12 = n12, q34 = n34, q56 = n56, bc = nbc;                                                 \
+        n12 = __ldg(p); n34 = __ldg(p + 1); n56 = __ldg(p + 2); nbc = __ldg(p + 3);                              \
+        p += 4;                                                                                                  \
+        const double t = rhop * A, tp = t * irho;                                                                \
+        P1 = fma(t, q12.x, P1); P2 = fma(t, q12.y, P2);                                                          \
+        P3 = fma(t, q34.x, P3); P4 = fma(t, q34.y, P4);                                                          \
+        P5 = fma(tp, q56.x, P5); P6 = fma(tp, q56.y, P6);                                                        \
+        const double An = fma(u_ * bc.x, A, -(bc.y * Ap));                                                       \
+        Ap = A; A = An;                                                                                          \
+    }
+    for (int k = 1; k <= g.ncols; k += 2) {
+        const bool two = k + 1 <= g.ncols;
+        double A = __ldg(g.a_diag + k), Ap = 0.0, B = two ? __ldg(g.a_diag + k + 1) : 0.0, Bp = 0.0;
+        double rhop = rho_k;
+        double PA1 = 0.0, PA2 = 0.0, PA3 = 0.0, PA4 = 0.0, PA5 = 0.0, PA6 = 0.0;
+        double PB1 = 0.0, PB2 = 0.0, PB3 = 0.0, PB4 = 0.0, PB5 = 0.0, PB6 = 0.0;
+        NYXB_COL_ENTRY(A, Ap, PA1, PA2, PA3, PA4, PA5, PA6)   // row j = k belongs to column k alone
+        rhop *= rho;
+        if (two) {
+            for (int j = k + 1; j <= N + 1; ++j) {
+                NYXB_COL_ENTRY(A, Ap, PA1, PA2, PA3, PA4, PA5, PA6)
+                NYXB_COL_ENTRY(B, Bp, PB1, PB2, PB3, PB4, PB5, PB6)
+                rhop *= rho;
+            }
+        } else {
+            for (int j = k + 1; j <= N + 1; ++j) {
+                NYXB_COL_ENTRY(A, Ap, PA1, PA2, PA3, PA4, PA5, PA6)
+                rhop *= rho;
+            }
+        }
+        a0 = fma(rk, PA1, fma(ik, PA2, a0));
+        a1 = fma(rk, PA2, fma(-ik, PA1, a1));
+        a2 = fma(rk, PA3, fma(ik, PA4, a2));
+        a3 -= fma(rk, PA5, ik * PA6);
+        double nr = fma(s_, rk, -(t_ * ik)), ni = fma(s_, ik, t_ * rk);
+        rk = nr; ik = ni;
+        rho_k *= rho;
+        if (two) {
+            a0 = fma(rk, PB1, fma(ik, PB2, a0));
+            a1 = fma(rk, PB2, fma(-ik, PB1, a1));
+            a2 = fma(rk, PB3, fma(ik, PB4, a2));
+            a3 -= fma(rk, PB5, ik * PB6);
+            nr = fma(s_, rk, -(t_ * ik)); ni = fma(s_, ik, t_ * rk);
+            rk = nr; ik = ni;
+            rho_k *= rho;
+        }
+    }
+#undef NYXB_COL_ENTRY
+    const double ab0 = fma(a3, s_, a0), ab1 = fma(a3, t_, a1), ab2 = fma(a3, u_, a2);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) acc[i] = fma(R[6 + i], ab2, fma(R[3 + i], ab1, R[i] * ab0));
+}
+#endif
+
 #define NYXB_AU_KM 149597870.700
 #define NYXB_C_M_S (299792.458 * 1e3)
 
@@ -547,7 +637,11 @@ __device__ inline int eom_full(const DevSetup& S, long long epoch_ns, double del
     if (rc) return rc;
     if (GRAV && S.has_grav) {
         double ga[3];
+#if NYXB_STRICT
         grav_accel_rows(S.grav, t_ns, y, ga);
+#else
+        grav_accel_cols(S.grav, t_ns, y, ga);
+#endif
         acc[0] += ga[0]; acc[1] += ga[1]; acc[2] += ga[2];
     }
     if (has_force) accel_post(S, t_ns, y, bpos, mass, srp_area, drag_area, acc);
