@@ -259,7 +259,7 @@ extern "C" nyxb_engine* nyxb_engine_create(const nyxb_dynamics* dyn, const nyxb_
                 push(k, k);
                 for (int j = k + 1; j <= N + 1; ++j) { push(k, j); if (two) push(k + 1, j); }
             }
-            cr.insert(cr.end(), 8, 0.0);            // null record: target of the last prefetch
+            cr.insert(cr.end(), 16, 0.0);           // two null records: targets of the last prefetches
             S.grav.colrec = upload(e, cr.data(), cr.size());
             S.grav.ncols = ncols;
             if (!S.grav.colrec) { set_err("gravity table upload failed"); delete e; return nullptr; }
@@ -363,8 +363,10 @@ static int32_t launch(nyxb_engine* e, size_t n, const double* state, const doubl
         err = nyxb_launch_thread_strict(&e->S, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io,
                                         out_state, (long long*)out_epoch, out_details, out_status, 64, &sink, stream);
     } else {
+        int blk = 64;
+        if (const char* ev = getenv("NYXB_K1_BLOCK")) { int v = atoi(ev); if (v == 32 || v == 64 || v == 128) blk = v; }
         err = nyxb_launch_thread_fast(&e->S, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io,
-                                      out_state, (long long*)out_epoch, out_details, out_status, 64, &sink, stream);
+                                      out_state, (long long*)out_epoch, out_details, out_status, blk, &sink, stream);
     }
     if (err != cudaSuccess) { set_err(std::string("kernel launch: ") + cudaGetErrorString(err)); return NYXB_RC_CUDA; }
     e->launches += 1;

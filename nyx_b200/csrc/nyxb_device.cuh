@@ -426,10 +426,20 @@ __device__ inline void grav_accel_cols(const DevGrav& g, long long t_ns, const d
     const double2* __restrict__ p = reinterpret_cast<const double2*>(g.colrec);
     double2 n12 = __ldg(p), n34 = __ldg(p + 1), n56 = __ldg(p + 2), nbc = __ldg(p + 3);
     p += 4;
+#ifndef NYXB_COLS_PF
+#define NYXB_COLS_PF 1   /* prefetch distance in entries (1 or 2; the table ends with two null records) */
+#endif
+#if NYXB_COLS_PF == 2
+    double2 m12 = __ldg(p), m34 = __ldg(p + 1), m56 = __ldg(p + 2), mbc = __ldg(p + 3);
+    p += 4;
+#define NYXB_COL_FETCH n12 = m12; n34 = m34; n56 = m56; nbc = mbc; m12 = __ldg(p); m34 = __ldg(p + 1); m56 = __ldg(p + 2); mbc = __ldg(p + 3);
+#else
+#define NYXB_COL_FETCH n12 = __ldg(p); n34 = __ldg(p + 1); n56 = __ldg(p + 2); nbc = __ldg(p + 3);
+#endif
 #define NYXB_COL_ENTRY(A, Ap, P1, P2, P3, P4, P5, P6)                                                            \
     {                                                                                                            \
         const double2 q12 = n12, q34 = n34, q56 = n56, bc = nbc;                                                 \
-        n12 = __ldg(p); n34 = __ldg(p + 1); n56 = __ldg(p + 2); nbc = __ldg(p + 3);                              \
+        NYXB_COL_FETCH                                                                                           \
         p += 4;                                                                                                  \
         const double t = rhop * A, tp = t * irho;                                                                \
         P1 = fma(t, q12.x, P1); P2 = fma(t, q12.y, P2);                                                          \
@@ -476,6 +486,7 @@ __device__ inline void grav_accel_cols(const DevGrav& g, long long t_ns, const d
         }
     }
 #undef NYXB_COL_ENTRY
+#undef NYXB_COL_FETCH
     const double ab0 = fma(a3, s_, a0), ab1 = fma(a3, t_, a1), ab2 = fma(a3, u_, a2);
 #pragma unroll
     for (int i = 0; i < 3; ++i) acc[i] = fma(R[6 + i], ab2, fma(R[3 + i], ab1, R[i] * ab0));
