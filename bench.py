@@ -440,7 +440,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "trajectories_total": n_total, "accepted_steps_per_pass": all_steps,
                        "rejected_attempts_per_pass": all_rej, "ok_trajectories": all_ok, "mode": args.mode,
-                       "lanes_per_trajectory": eng.lanes(), "l2": "flushed between timed iterations (256 MiB write)",
+                       "lanes_per_trajectory": (1 if (args.mode == "fast" and not args.lanes and args.workload == "c2" and args.degree < 30 and n >= 65536) else eng.lanes()),
+                       "l2": "flushed between timed iterations (256 MiB write)",
                        "parallelism": f"ensemble-sharded x{world}, one all-gather of final states"},
             "e2e": {"value": e2e_value, "unit": "trajectory-steps/s", "h2d_bytes_per_step": n * (13 * 8 + 8) * world,
                     "d2h_bytes_per_step": n * (9 * 8 + 8 + 48 + 4) * world, "ms_per_step": e2e_s * 1e3},
