@@ -373,54 +373,17 @@ NYXB_KOD(const __grid_constant__ DevSetup S, const __grid_constant__ DevOd od, s
                 const DevStation& gs = od.stations[trk];
                 const int windows = gs.n_types / M;
                 for (int wno = 0; wno <= windows; ++wno) {                      // :270-398
-                    int cur[2], ncur = 0;
-                    for (int q = wno * M; q < (wno + 1) * M && q < gs.n_types; ++q) cur[ncur++] = gs.types[q];
-                    if (ncur == 0) break;
-                    bool avail[2] = { false, false }, any = false;
-                    for (int q = 0; q < ncur; ++q) { avail[q] = (o[cur[q]] == o[cur[q]]); any = any || avail[q]; }
-                    if (!any) continue;
-                    double real_obs[2] = { 0.0, 0.0 };
-                    for (int q = 0; q < ncur; ++q) if (avail[q]) real_obs[q] = o[cur[q]];
-                    // geometry: transmitter state, range, range rate, elevation, obstruction
-                    double r_tx[3], v_tx[3], up[3];
-                    if (!station_state(S, gs, t_k, r_tx, v_tx, up)) { rc = NYXB_ERR_EPHEMERIS; break; }
-                    const double dr[3] = { in.y[0] - r_tx[0], in.y[1] - r_tx[1], in.y[2] - r_tx[2] };
-                    const double dv[3] = { in.y[3] - v_tx[0], in.y[4] - v_tx[1], in.y[5] - v_tx[2] };
-                    const double rng = sqrt((dr[0] * dr[0] + dr[1] * dr[1]) + dr[2] * dr[2]);
-                    const double rr = ((dr[0] * dv[0] + dr[1] * dv[1]) + dr[2] * dv[2]) / rng;
-                    const double elev = asin(((dr[0] * up[0] + dr[1] * up[1]) + dr[2] * up[2]) / rng) * (180.0 / 3.14159265358979323846);
-                    bool visible = !(elev - gs.mask_deg < 0.0);
-                    if (visible && gs.body != NYXB_CENTRAL_BODY && gs.body_radius > 0.0) {   // Vallado SIGHT (anise line_of_sight_obstructed)
-                        double r1sq = (in.y[0] * in.y[0] + in.y[1] * in.y[1]) + in.y[2] * in.y[2];
-                        double r2sq = (r_tx[0] * r_tx[0] + r_tx[1] * r_tx[1]) + r_tx[2] * r_tx[2];
-                        double r12 = (in.y[0] * r_tx[0] + in.y[1] * r_tx[1]) + in.y[2] * r_tx[2];
-                        double tau = (r1sq - r12) / (r1sq + r2sq - 2.0 * r12);
-                        if (tau >= 0.0 && tau <= 1.0 && (1.0 - tau) * r1sq + r12 * tau <= gs.body_radius * gs.body_radius) visible = false;
-                    }
-                    if (!visible) { flags |= NYXB_MSRF_NOT_VISIBLE; continue; }  // :386-392
-                    // h_tilde (sensitivity.rs:88-239): identity rows unless the type is in msr.data
-                    double H[2][9];
-                    for (int q = 0; q < 2; ++q)
-                        for (int c = 0; c < 9; ++c) H[q][c] = (q == c) ? 1.0 : 0.0;
-                    double Rk[2] = { 0.0, 0.0 }, comp[2] = { 0.0, 0.0 };
-                    for (int q = 0; q < ncur; ++q) {
-                        int slot = wno * M + q;  // position of the type in the device's list
-                        Rk[q] = gs.noise_var[slot];
-                        comp[q] = ((cur[q] == NYXB_MSR_RANGE) ? rng : rr) - gs.bias[slot];
-                        if (!avail[q]) continue;
-                        if (cur[q] == NYXB_MSR_DOPPLER) {
-                            double rho = rng, rho_dot = o[NYXB_MSR_DOPPLER], rho2 = rho * rho;
-                            H[q][0] = dv[0] / rho - rho_dot * dr[0] / rho2;
-                            H[q][1] = dv[1] / rho - rho_dot * dr[1] / rho2;
-                            H[q][2] = dv[2] / rho - rho_dot * dr[2] / rho2;
-                            H[q][3] = dr[0] / rho; H[q][4] = dr[1] / rho; H[q][5] = dr[2] / rho;
-                            H[q][6] = 0.0; H[q][7] = 0.0; H[q][8] = 0.0;
-                        } else {
-                            double rho = o[NYXB_MSR_RANGE];
-                            H[q][0] = dr[0] / rho; H[q][1] = dr[1] / rho; H[q][2] = dr[2] / rho;
-                            for (int c = 3; c < 9; ++c) H[q][c] = 0.0;
-                        }
-                    }
+                    OdWindow w;
+                    const int wrc = od_window_setup(S, gs, M, wno, o, t_k, in.y, w);
+                    if (wrc == OD_WIN_EMPTY) break;
+                    if (wrc == OD_WIN_UNAVAILABLE) continue;
+                    if (wrc == OD_WIN_EPHEMERIS) { rc = NYXB_ERR_EPHEMERIS; break; }
+                    if (wrc == OD_WIN_NOT_VISIBLE) { flags |= NYXB_MSRF_NOT_VISIBLE; continue; }
+                    const int ncur = w.ncur;
+                    const double (&H)[2][9] = w.H;
+                    const double* Rk = w.Rk;
+                    const double* real_obs = w.real_obs;
+                    const double* comp = w.comp;
                     // ---- measurement_update (filtering.rs:107-316)
                     double Pbar[81];
                     covar_bar(od, in, f, Pbar);
@@ -438,24 +401,8 @@ NYXB_KOD(const __grid_constant__ DevSetup S, const __grid_constant__ DevOd od, s
                             Sk[a][b] = s + ((a == b) ? Rk[a] : 0.0);
                         }
                     for (int q = 0; q < M; ++q) pre[q] = real_obs[q] - comp[q];
-                    // Cholesky of S (fallback: of R), whitened residual, ratio
-                    double L00, L10 = 0.0, L11 = 1.0;
-                    bool chol_ok = Sk[0][0] > 0.0;
-                    if (chol_ok) {
-                        L00 = sqrt(Sk[0][0]);
-                        if (M == 2) {
-                            L10 = Sk[1][0] / L00;
-                            double d = Sk[1][1] - L10 * L10;
-                            if (d > 0.0) L11 = sqrt(d); else chol_ok = false;
-                        }
-                    }
-                    double W00 = L00, W10 = L10, W11 = L11;
-                    if (!chol_ok) {
-                        if (!(Rk[0] > 0.0) || (M == 2 && !(Rk[1] > 0.0))) { rc = NYXB_ERR_PROP_MATH; break; }  // SingularNoiseRk
-                        W00 = sqrt(Rk[0]); W10 = 0.0; W11 = (M == 2) ? sqrt(Rk[1]) : 1.0;
-                    }
-                    double w0 = pre[0] / W00, w1 = (M == 2) ? (pre[1] - W10 * w0) / W11 : 0.0;
-                    double ratio = sqrt(((M == 2) ? (w0 * w0 + w1 * w1) : (w0 * w0)) / (double)M);
+                    double ratio;
+                    if (!od_ratio(M, Sk, Rk, pre, ratio)) { rc = NYXB_ERR_PROP_MATH; break; }   // SingularNoiseRk
                     const int rslot = (M == 1) ? wno : 0;
                     if (od.ratio) od.ratio[((size_t)k * 2 + rslot) * n + i] = ratio;
                     if (od.prefit) for (int q = 0; q < ncur; ++q) od.prefit[((size_t)k * 2 + wno * M + q) * n + i] = pre[q];
@@ -466,12 +413,7 @@ NYXB_KOD(const __grid_constant__ DevSetup S, const __grid_constant__ DevOd od, s
                     } else {
                         // gain K = PHt S^-1 (Cholesky solve; plain inverse when S is not positive definite)
                         double Si[2][2];
-                        if (M == 1) { Si[0][0] = 1.0 / Sk[0][0]; Si[0][1] = Si[1][0] = 0.0; Si[1][1] = 0.0; }
-                        else {
-                            double det = Sk[0][0] * Sk[1][1] - Sk[0][1] * Sk[1][0];
-                            if (det == 0.0 || det != det) { rc = NYXB_ERR_PROP_MATH; break; }       // SingularKalmanGain
-                            Si[0][0] = Sk[1][1] / det; Si[0][1] = -Sk[0][1] / det; Si[1][0] = -Sk[1][0] / det; Si[1][1] = Sk[0][0] / det;
-                        }
+                        if (!od_sinv(M, Sk, Si)) { rc = NYXB_ERR_PROP_MATH; break; }   // SingularKalmanGain
                         double K[9][2];
                         for (int r = 0; r < 9; ++r)
                             for (int q = 0; q < M; ++q) {

@@ -252,3 +252,99 @@ __device__ static bool station_state(const DevSetup& S, const DevStation& st, lo
     return true;
 }
 
+// ------------------------------------------------------------------------- one residual window of a measurement
+// What od/process/mod.rs:270-352 prepares before `measurement_update`: the window's measurement types, the real observation,
+// the tracker geometry (range, range rate, elevation mask, line-of-sight obstruction), `h_tilde` (msr/sensitivity.rs:88-239:
+// identity rows unless the type is in msr.data; the observed range / Doppler in the denominators, as coded), the measurement
+// noise and the computed observation minus the device bias.  Shared by the per-thread and the warp-cooperative filter kernels.
+struct OdWindow {
+    int ncur;
+    int cur[2];
+    bool avail[2];
+    double real_obs[2], Rk[2], comp[2];
+    double H[2][9];
+};
+enum { OD_WIN_OK = 0, OD_WIN_EMPTY = 1, OD_WIN_UNAVAILABLE = 2, OD_WIN_NOT_VISIBLE = 3, OD_WIN_EPHEMERIS = 4 };
+
+__device__ static int od_window_setup(const DevSetup& S, const DevStation& gs, int M, int wno, const double o[2], long long t_k,
+                                      const double y[9], OdWindow& w) {
+    w.ncur = 0;
+    for (int q = wno * M; q < (wno + 1) * M && q < gs.n_types; ++q) w.cur[w.ncur++] = gs.types[q];
+    if (w.ncur == 0) return OD_WIN_EMPTY;
+    bool any = false;
+    w.avail[0] = w.avail[1] = false;
+    for (int q = 0; q < w.ncur; ++q) { w.avail[q] = (o[w.cur[q]] == o[w.cur[q]]); any = any || w.avail[q]; }
+    if (!any) return OD_WIN_UNAVAILABLE;
+    w.real_obs[0] = w.real_obs[1] = 0.0;
+    for (int q = 0; q < w.ncur; ++q) if (w.avail[q]) w.real_obs[q] = o[w.cur[q]];
+    double r_tx[3], v_tx[3], up[3];
+    if (!station_state(S, gs, t_k, r_tx, v_tx, up)) return OD_WIN_EPHEMERIS;
+    const double dr[3] = { y[0] - r_tx[0], y[1] - r_tx[1], y[2] - r_tx[2] };
+    const double dv[3] = { y[3] - v_tx[0], y[4] - v_tx[1], y[5] - v_tx[2] };
+    const double rng = sqrt((dr[0] * dr[0] + dr[1] * dr[1]) + dr[2] * dr[2]);
+    const double rr = ((dr[0] * dv[0] + dr[1] * dv[1]) + dr[2] * dv[2]) / rng;
+    const double elev = asin(((dr[0] * up[0] + dr[1] * up[1]) + dr[2] * up[2]) / rng) * (180.0 / 3.14159265358979323846);
+    bool visible = !(elev - gs.mask_deg < 0.0);
+    if (visible && gs.body != NYXB_CENTRAL_BODY && gs.body_radius > 0.0) {   // Vallado SIGHT (anise line_of_sight_obstructed)
+        double r1sq = (y[0] * y[0] + y[1] * y[1]) + y[2] * y[2];
+        double r2sq = (r_tx[0] * r_tx[0] + r_tx[1] * r_tx[1]) + r_tx[2] * r_tx[2];
+        double r12 = (y[0] * r_tx[0] + y[1] * r_tx[1]) + y[2] * r_tx[2];
+        double tau = (r1sq - r12) / (r1sq + r2sq - 2.0 * r12);
+        if (tau >= 0.0 && tau <= 1.0 && (1.0 - tau) * r1sq + r12 * tau <= gs.body_radius * gs.body_radius) visible = false;
+    }
+    if (!visible) return OD_WIN_NOT_VISIBLE;   // device.measure() -> None (process/mod.rs:386-392)
+    for (int q = 0; q < 2; ++q)
+        for (int c = 0; c < 9; ++c) w.H[q][c] = (q == c) ? 1.0 : 0.0;
+    w.Rk[0] = w.Rk[1] = 0.0; w.comp[0] = w.comp[1] = 0.0;
+    for (int q = 0; q < w.ncur; ++q) {
+        const int slot = wno * M + q;  // position of the type in the device's list
+        w.Rk[q] = gs.noise_var[slot];
+        w.comp[q] = ((w.cur[q] == NYXB_MSR_RANGE) ? rng : rr) - gs.bias[slot];
+        if (!w.avail[q]) continue;
+        if (w.cur[q] == NYXB_MSR_DOPPLER) {
+            const double rho = rng, rho_dot = o[NYXB_MSR_DOPPLER], rho2 = rho * rho;
+            w.H[q][0] = dv[0] / rho - rho_dot * dr[0] / rho2;
+            w.H[q][1] = dv[1] / rho - rho_dot * dr[1] / rho2;
+            w.H[q][2] = dv[2] / rho - rho_dot * dr[2] / rho2;
+            w.H[q][3] = dr[0] / rho; w.H[q][4] = dr[1] / rho; w.H[q][5] = dr[2] / rho;
+            w.H[q][6] = 0.0; w.H[q][7] = 0.0; w.H[q][8] = 0.0;
+        } else {
+            const double rho = o[NYXB_MSR_RANGE];
+            w.H[q][0] = dr[0] / rho; w.H[q][1] = dr[1] / rho; w.H[q][2] = dr[2] / rho;
+            for (int c = 3; c < 9; ++c) w.H[q][c] = 0.0;
+        }
+    }
+    return OD_WIN_OK;
+}
+
+// Innovation statistics (filtering.rs:152-167): S = H P H^T + R (given), Cholesky of S (fallback: of R), whitened residual ratio.
+// Returns false on SingularNoiseRk.
+__device__ static bool od_ratio(int M, const double Sk[2][2], const double Rk[2], const double pre[2], double& ratio) {
+    double L00 = 1.0, L10 = 0.0, L11 = 1.0;
+    bool chol_ok = Sk[0][0] > 0.0;
+    if (chol_ok) {
+        L00 = sqrt(Sk[0][0]);
+        if (M == 2) {
+            L10 = Sk[1][0] / L00;
+            const double d = Sk[1][1] - L10 * L10;
+            if (d > 0.0) L11 = sqrt(d); else chol_ok = false;
+        }
+    }
+    double W00 = L00, W10 = L10, W11 = L11;
+    if (!chol_ok) {
+        if (!(Rk[0] > 0.0) || (M == 2 && !(Rk[1] > 0.0))) return false;
+        W00 = sqrt(Rk[0]); W10 = 0.0; W11 = (M == 2) ? sqrt(Rk[1]) : 1.0;
+    }
+    const double w0 = pre[0] / W00, w1 = (M == 2) ? (pre[1] - W10 * w0) / W11 : 0.0;
+    ratio = sqrt(((M == 2) ? (w0 * w0 + w1 * w1) : (w0 * w0)) / (double)M);
+    return true;
+}
+
+// S^-1 for M = 1, 2 (the gain K = P H^T S^-1, filtering.rs:206-231); false on SingularKalmanGain
+__device__ static bool od_sinv(int M, const double Sk[2][2], double Si[2][2]) {
+    if (M == 1) { Si[0][0] = 1.0 / Sk[0][0]; Si[0][1] = Si[1][0] = 0.0; Si[1][1] = 0.0; return true; }
+    const double det = Sk[0][0] * Sk[1][1] - Sk[0][1] * Sk[1][0];
+    if (det == 0.0 || det != det) return false;
+    Si[0][0] = Sk[1][1] / det; Si[0][1] = -Sk[0][1] / det; Si[1][0] = -Sk[1][0] / det; Si[1][1] = Sk[0][0] / det;
+    return true;
+}
