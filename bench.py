@@ -109,34 +109,38 @@ def build_workload(args, n_total, nb):
     return frame, dyn, almanac, st, cs, ep
 
 
-def bench_c5(args, nb, local_rank):
-    """BASELINE configs[4] (context only, N=1): LRO-like ensemble, every trajectory runs its own EKF over the same tracking
-    schedule — `nyxb_od_ekf_batch`, ONE launch for the whole arc (propagation with STM + time/measurement updates)."""
+def c5_scenario(args, nb, n, n_msr, device, truth_on_cpu):
+    """LRO-like orbit determination ensemble (BASELINE configs[4]): dynamics, DSN stations, tracking arc, dispersed initial estimates."""
     from nyx_b200.frames import EARTH
 
     S_ = 10**9
     frame = nb.MOON_J2000
-    n = args.n_traj
     deg = args.degree if args.degree != 21 else 70
     alm = nb.Almanac.synthetic(frame, 0, args.span_days + 2.0, bodies=(EARTH, nb.SUN))
     gd = nb.GravityFieldData.from_fixture("luna_jggrx_80x80", deg, deg, nb.IAU_MOON_FRAME)
     srp = nb.SolarPressure.new([nb.EARTH_J2000, nb.MOON_J2000], alm)
     dyn = nb.SpacecraftDynamics.from_model(nb.OrbitalDynamics.new([nb.PointMasses.new([EARTH, nb.SUN]), nb.GravityField.new(gd)]), srp)
     mode = nb.MODE_FAST if args.mode == "fast" else nb.MODE_STRICT
-    prop = nb.Propagator.default_dp78(dyn, mode=mode, device=local_rank)   # examples/04_lro_od/main.rs:163
+    prop = nb.Propagator.default_dp78(dyn, mode=mode, device=device)   # examples/04_lro_od/main.rs:163
     orbit = nb.Orbit.keplerian(1737.4 + 100.0, 0.002, 88.0, 20.0, 10.0, 0.0, 0, frame)
     truth0 = nb.Spacecraft(orbit=orbit, mass=nb.Mass(1018.0, 900.0, 0.0), srp=nb.SRPData(3.9 * 2.7, 0.96))
     rn, dn = nb.StochasticNoise(5e-3), nb.StochasticNoise(5e-6)
     devices = {"Madrid": nb.GroundStation.dss65_madrid(5.0, rn, dn), "Canberra": nb.GroundStation.dss34_canberra(5.0, rn, dn),
                "Goldstone": nb.GroundStation.dss13_goldstone(5.0, rn, dn)}
     names = list(devices)
-    n_msr = int(args.span_days * 86400 // 60)
     epochs = (np.arange(1, n_msr + 1) * 60 * S_).astype(np.int64)
     schedule = [names[(k // 240) % 3] for k in range(n_msr)]   # 4-hour passes
-    # truth trajectory (one spacecraft, fixed 60 s steps, recorded) through the product's own recording path
-    tprop = nb.Propagator.new(dyn, nb.IntegratorMethod.RungeKutta89, nb.IntegratorOptions.with_fixed_step_s(60.0), mode=nb.MODE_FAST, device=local_rank)
+    # truth trajectory: one spacecraft, fixed 60 s steps, recorded (the product's recording path, or the CPU oracle in the reference arm)
+    topts = nb.IntegratorOptions.with_fixed_step_s(60.0)
     st1, cs1, ep1 = nb.pack_spacecraft([truth0])
-    _, _, _, tstat, (t_ep, t_st, t_cnt) = tprop.engine(frame, alm).propagate_batch(st1, cs1, ep1, int(epochs[-1]), traj_capacity=n_msr + 2)
+    if truth_on_cpu:
+        from oracle import pyoracle
+
+        _, _, _, tstat, (t_ep, t_st, t_cnt) = pyoracle.propagate_batch(dyn.pack(frame, alm).c, topts.to_c(nb.IntegratorMethod.RungeKutta89), st1, cs1, ep1,
+                                                                       int(epochs[-1]), traj_capacity=n_msr + 2)
+    else:
+        tprop = nb.Propagator.new(dyn, nb.IntegratorMethod.RungeKutta89, topts, mode=nb.MODE_FAST, device=device)
+        _, _, _, tstat, (t_ep, t_st, t_cnt) = tprop.engine(frame, alm).propagate_batch(st1, cs1, ep1, int(epochs[-1]), traj_capacity=n_msr + 2)
     assert tstat[0] == 0 and np.array_equal(t_ep[1: n_msr + 1, 0], epochs)
     truth = np.repeat(t_st[:, 1: n_msr + 1, 0].T[:, :, None], n, axis=2)
     rng = np.random.default_rng(0)
@@ -148,6 +152,68 @@ def bench_c5(args, nb, local_rank):
         ests.append(nb.KfEstimate.from_diag(truth0.with_vector(0, v), [0.25, 0.25, 0.25, 2.5e-7, 2.5e-7, 2.5e-7, 0.04, 0.0, 0.0]))
     odp = nb.SpacecraftKalmanOD(prop, nb.KalmanVariant.ReferenceUpdate, nb.SigmaRejection(3.0), devices, alm)
     odp.with_process_noise(nb.ProcessNoise3D.from_velocity_km_s([1e-10, 1e-10, 1e-10], 1 * nb.Unit.Hour, 10 * nb.Unit.Minute, None))
+    return dict(frame=frame, alm=alm, dyn=dyn, prop=prop, devices=devices, arc=arc, ests=ests, odp=odp, truth=truth, deg=deg, mode=mode)
+
+
+def _c5_ref_worker(job):
+    """One filter of the reference arm: numpy + C oracle (od/process/mod.rs restated), run in a worker process."""
+    import nyx_b200 as nb
+    from oracle import pyoracle_od
+
+    args, i, m_s = job
+    sc = _C5_SC
+    odp, arc, est = sc["odp"], sc["arc"], sc["ests"][i]
+    names_c, st_c = odp.stations_c(sc["frame"])
+    tracker = np.array([names_c.index(t) for t in arc.tracker[:m_s]], dtype=np.int32)
+    msc = est.nominal_state.mass
+    cs0 = np.array([msc.dry_mass_kg, msc.extra_mass_kg, est.nominal_state.srp.area_m2, 0.0])
+    ref = pyoracle_od.process_arc(sc["dyn"].pack(sc["frame"], sc["alm"]).c, sc["prop"].opts.to_c(sc["prop"].method), odp.config_c(), st_c,
+                                  arc.epoch_ns[:m_s], tracker, np.ascontiguousarray(arc.obs[:m_s, :, i]), est.nominal_state.to_vector(), cs0, 0, est.covar)
+    return ref["n_steps"]
+
+
+_C5_SC = None
+
+
+def bench_c5_reference(args, nb):
+    """`--impl reference --workload c5`: the CPU restatement of the filter on all host cores (one filter per process), each step a
+    bounded sample: `cores` filters over the first 60 measurement epochs."""
+    import multiprocessing as mp
+
+    global _C5_SC
+    cores = os.cpu_count() or 8
+    m_s = 60
+    args_small = argparse.Namespace(**vars(args))
+    args_small.span_days = max(m_s * 60 / 86400.0 + 0.01, 0.05)
+    _C5_SC = c5_scenario(args_small, nb, cores, m_s, 0, truth_on_cpu=True)
+    ctx = mp.get_context("fork")
+    times, steps = [], 0
+    with ctx.Pool(cores) as pool:
+        for it in range(max(0, min(args.warmup, 1)) + args.steps):
+            t0 = time.perf_counter()
+            res = pool.map(_c5_ref_worker, [(None, i, m_s) for i in range(cores)])
+            if it >= max(0, min(args.warmup, 1)):
+                times.append(time.perf_counter() - t0)
+                steps = int(sum(res))
+    value = steps * len(times) / sum(times)
+    line = {"impl": "reference", "metric": "trajectory-steps/sec (ensemble)", "value": value, "unit": "trajectory-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C5 sample: {cores} LRO-like EKFs (GRAIL {_C5_SC['deg']}x{_C5_SC['deg']} + Earth/Sun + SRP), first {m_s} measurement epochs"},
+            "cpu_baseline": {"value": value, "unit": "trajectory-steps/s", "cores": cores, "kind": "port",
+                             "sample": f"{cores} filters x {m_s} measurement epochs per step, one process per filter (numpy + C oracle)"},
+            "e2e": {"value": value, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def bench_c5(args, nb, local_rank):
+    """BASELINE configs[4] (context only, N=1): LRO-like ensemble, every trajectory runs its own EKF over the same tracking
+    schedule — `nyxb_od_ekf_batch`, ONE launch for the whole arc (propagation with STM + time/measurement updates)."""
+    n = args.n_traj
+    n_msr = int(args.span_days * 86400 // 60)
+    sc = c5_scenario(args, nb, n, n_msr, local_rank, truth_on_cpu=False)
+    frame, alm, dyn, prop, devices, arc, ests, odp, truth, deg, mode = (sc[k] for k in ("frame", "alm", "dyn", "prop", "devices", "arc", "ests", "odp", "truth", "deg", "mode"))
     eng = prop.engine(frame, alm)
     # warm-up: a short arc
     warm = nb.TrackingDataArc(arc.epoch_ns[:4], arc.tracker[:4], arc.obs[:4, :, :min(n, 64)])
@@ -285,9 +351,9 @@ def main():
     if args.cpu_sample <= 0:
         args.cpu_sample = 32 * (os.cpu_count() or 8)
     if args.workload == "c5":
-        if rank != 0 or args.impl == "reference":
+        if rank != 0:
             return 0
-        return bench_c5(args, nb, local_rank)
+        return bench_c5_reference(args, nb) if args.impl == "reference" else bench_c5(args, nb, local_rank)
     workload = WORKLOAD_TEXT[args.workload].format(n=args.n_traj, deg=args.degree, span=args.span_days)
     # algorithmic flop per accepted step: C2 from the degree; C3 ~ 9 k (two ephemeris bodies + SRP); C4 = 70x70
     fps = {"c2": flops_per_step(args.degree), "c3": 9.0e3, "c4": flops_per_step(70) + 16 * 200.0}[args.workload]
