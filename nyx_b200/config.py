@@ -17,7 +17,7 @@ from pathlib import Path
 from typing import Dict, Optional, Union
 
 from .dynamics import AtmDensity, Drag, DynamicsError, GravityField, OrbitalDynamics, PointMasses, SolarPressure, SpacecraftDynamics
-from .frames import EARTH, IAU_EARTH_FRAME, IAU_MOON_FRAME, MOON, Almanac, Frame
+from .frames import EARTH, IAU_EARTH_FRAME, IAU_MOON_FRAME, MOON, Almanac
 from .gravity import GravityFieldData
 from .od import GroundStation, MeasurementType, StochasticNoise
 from .propagator import ErrorControl, IntegratorMethod, IntegratorOptions, Propagator

@@ -8,7 +8,7 @@ exchanged with a single `all_gather` (NCCL over NVLink on GPUs; gloo in the CPU 
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Tuple
 
 import numpy as np
 

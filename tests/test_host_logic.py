@@ -138,3 +138,20 @@ def test_od_host_objects():
     assert abs(pos[2] - 6356.75) < 1e-9 and abs(pos[0]) < 1e-9 and np.allclose(up, [0, 0, 1], atol=1e-15)
     eq = nb.GroundStation("equator", 0.0, 90.0, 1.0, nb.IAU_EARTH_FRAME).body_fixed()[0]
     assert np.allclose(eq, [0.0, 6379.14, 0.0], atol=1e-9)
+
+
+def test_bench_reference_arm_for_c5_runs_on_cpu():
+    """`bench.py --workload c5 --impl reference` is the CPU restatement of the filter (no GPU, none of the product's kernels):
+    it must print one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--workload", "c5", "--impl", "reference", "--degree", "8", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["cores"] >= 1
