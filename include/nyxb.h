@@ -299,6 +299,28 @@ int32_t nyxb_propagate_batch_traj_dev(nyxb_engine* eng, size_t n,
                                       nyxb_details* out_details, int32_t* out_status,
                                       const nyxb_traj_sink* sink, void* cuda_stream);
 
+/* ---- Batched resampling of recorded trajectories on a common epoch grid (row (f)-1): what `Traj::every` /
+ * `every_between` (md/trajectory/traj.rs:148-162, traj_it.rs:32-63) yield through `Traj::at` (traj.rs:83-126: exact hit,
+ * else a window of 13 records around the query — 12 at the right edge, as coded — Hermite-interpolated in (r, v),
+ * md/trajectory/interpolatable.rs:53-108) and what `Results::every_value_of[_between]` (mc/results.rs:88-160) iterate over,
+ * for all n trajectories and all m query epochs in ONE launch.
+ *  sink            the recording as filled by nyxb_propagate_batch_traj / _event (capacity, epoch_ns, state, count);
+ *                  NULL (host variant only): the recording of this engine's last host-pointer propagation, still
+ *                  resident in device memory (no upload);
+ *  query_epoch_ns  [m];
+ *  out_state       [6][m][n]  x,y,z,vx,vy,vz of trajectory i at query j at [(c*m + j)*n + i]; NaN where no data;
+ *  out_status      [m][n]     NYXB_TRAJ_OK, or NYXB_TRAJ_NO_DATA when the query lies outside the trajectory's recorded
+ *                             span (TrajError::NoInterpolationData) — a per-entry status, the batch never aborts.
+ * Seconds are counted from the first record of the window (the reference passes absolute ET seconds to anise's
+ * hermite_eval, which is not in the tree: parity unpinned at that boundary). */
+enum nyxb_traj_status { NYXB_TRAJ_OK = 0, NYXB_TRAJ_NO_DATA = 1 };
+int32_t nyxb_traj_resample(nyxb_engine* eng, size_t n, const nyxb_traj_sink* sink,
+                           size_t m, const int64_t* query_epoch_ns, double* out_state, int32_t* out_status);
+/* Device-pointer variant: the sink's arrays, the queries and the outputs are DEVICE pointers; stream-ordered. */
+int32_t nyxb_traj_resample_dev(nyxb_engine* eng, size_t n, const nyxb_traj_sink* sink,
+                               size_t m, const int64_t* query_epoch_ns, double* out_state, int32_t* out_status,
+                               void* cuda_stream);
+
 /* ---- State-transition-matrix propagation (next row (f)-2 of SURVEY.md §8): `Spacecraft::with_stm()` + propagate.
  * The integrated vector is the reference's 90-vector [x,y,z,vx,vy,vz,Cr,Cd,prop_mass, STM 9x9 column-major]
  * (cosmic/spacecraft.rs:449-473).  Stage derivative of the STM block AS CODED in the reference:

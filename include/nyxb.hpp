@@ -259,6 +259,43 @@ class Propagator {
         if (rc != NYXB_RC_OK) throw std::runtime_error(std::string("nyxb_propagate_batch_stm: ") + nyxb_last_error());
         return r;
     }
+    // until_epoch_with_traj for a batch (instance.rs:297-340): final states + every accepted step of every trajectory in the
+    // step-major SoA sink; `every(queries)` = Traj::at (md/trajectory/traj.rs:83-126) for all trajectories and query epochs in
+    // one launch on the recording still resident on the device (nyxb_traj_resample).
+    struct Resampled {
+        size_t m = 0, n = 0; std::vector<double> state; std::vector<int32_t> status;   // [6][m][n], [m][n]
+        double at(int c, size_t j, size_t i) const { return state[((size_t)c * m + j) * n + i]; }
+        bool ok(size_t j, size_t i) const { return status[j * n + i] == NYXB_TRAJ_OK; }
+    };
+    struct TrajBatch : BatchResult {
+        int64_t capacity = 0; size_t n = 0;
+        std::vector<int64_t> t_epoch, t_count; std::vector<double> t_state;   // [cap][n], [n], [6][cap][n]
+        std::shared_ptr<nyxb_engine> engine;
+        int64_t epoch_at(size_t s, size_t i) const { return t_epoch[s * n + i]; }
+        double state_at(int c, size_t s, size_t i) const { return t_state[((size_t)c * capacity + s) * n + i]; }
+        Resampled every(const std::vector<int64_t>& query_epoch_ns) const {
+            Resampled r; r.m = query_epoch_ns.size(); r.n = n;
+            r.state.resize(6 * r.m * n); r.status.resize(r.m * n);
+            int32_t rc = nyxb_traj_resample(engine.get(), n, nullptr, r.m, query_epoch_ns.data(), r.state.data(), r.status.data());
+            if (rc != NYXB_RC_OK) throw std::runtime_error(std::string("nyxb_traj_resample: ") + nyxb_last_error());
+            return r;
+        }
+    };
+    TrajBatch propagate_batch_traj(const std::vector<Spacecraft>& v, int64_t end_epoch_ns, int64_t capacity, const Almanac* almanac = nullptr) const {
+        TrajBatch r;
+        const size_t n = v.size();
+        r.n = n; r.capacity = capacity;
+        r.state.resize(9 * n); r.epoch.resize(n); r.details.resize(n); r.status.resize(n);
+        r.t_epoch.assign((size_t)capacity * n, 0); r.t_state.assign((size_t)6 * capacity * n, 0.0); r.t_count.assign(n, 0);
+        if (n == 0) return r;
+        r.engine = std::shared_ptr<nyxb_engine>(detail::make_engine(dynamics, v[0].frame, almanac, method, opts, mode, device).release(), nyxb_engine_destroy);
+        detail::Soa soa(v);
+        nyxb_traj_sink sink{capacity, r.t_epoch.data(), r.t_state.data(), r.t_count.data()};
+        int32_t rc = nyxb_propagate_batch_traj(r.engine.get(), n, soa.state.data(), soa.consts.data(), soa.epoch.data(), end_epoch_ns, nullptr,
+                                               r.state.data(), r.epoch.data(), r.details.data(), r.status.data(), &sink);
+        if (rc != NYXB_RC_OK) throw std::runtime_error(std::string("nyxb_propagate_batch_traj: ") + nyxb_last_error());
+        return r;
+    }
     // nyx-py Propagator.many_until_epoch (py_md.rs:224-271): failed runs are dropped
     std::vector<Spacecraft> many_until_epoch(const std::vector<Spacecraft>& v, int64_t end_epoch_ns, const Almanac* almanac = nullptr) const {
         auto r = propagate_batch(v, end_epoch_ns, almanac);

@@ -6,14 +6,15 @@ There is NO CPU fallback: every propagate call goes through ``libnyxb.so`` on a 
 """
 from . import abi
 from .abi import MODE_FAST, MODE_STRICT, NyxbLibraryMissing
-from .cosmic import DragData, Mass, Orbit, Spacecraft, SRPData, Unit, duration_to_seconds, pack_spacecraft
+from .cosmic import DragData, Mass, Orbit, Spacecraft, SRPData, Unit, duration_to_seconds, epochs_to_utc_iso, pack_spacecraft
 from .dynamics import (AtmDensity, Drag, DynamicsError, GravityField, OrbitalDynamics, PointMasses, ShadowModel,
                        SolarPressure, SpacecraftDynamics)
 from .frames import (EARTH, EARTH_J2000, GMAT_EARTH_GM, GMAT_MOON_GM, GMAT_SUN_GM, IAU_EARTH_FRAME, IAU_MOON_FRAME,
                      JUPITER_BARYCENTER, JUPITER_BARYCENTER_J2000, MOON, MOON_J2000, SUN, SUN_J2000, Almanac, Frame,
                      Rotation)
 from .gravity import GravityFieldData
-from .monte_carlo import DispersedState, MonteCarlo, MvnSpacecraft, Results, Run
+from .monte_carlo import DispersedState, MonteCarlo, MonteCarloError, MvnSpacecraft, Results, Run
+from .param import EXPORT_PARAMS, StateError, StateParameter
 from .trajectory import Traj, TrajError, hermite_eval
 from .config import PropagatorConfig, integrator_options_from, load_ground_stations, parse_duration
 from .event import Event, brent, locate_event

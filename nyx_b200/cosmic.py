@@ -48,6 +48,30 @@ def duration_to_seconds(total_ns: int) -> float:
     return float(cent) * 3_155_760_000.0 + float(sec) + float(sub) * 1e-9
 
 
+# TAI - UTC (s) from the given UTC date on (IERS Bulletin C; public data, what hifitime's leap-second table holds)
+_LEAP_SECONDS = (("1972-01-01", 10), ("1972-07-01", 11), ("1973-01-01", 12), ("1974-01-01", 13), ("1975-01-01", 14),
+                 ("1976-01-01", 15), ("1977-01-01", 16), ("1978-01-01", 17), ("1979-01-01", 18), ("1980-01-01", 19),
+                 ("1981-07-01", 20), ("1982-07-01", 21), ("1983-07-01", 22), ("1985-07-01", 23), ("1988-01-01", 24),
+                 ("1990-01-01", 25), ("1991-01-01", 26), ("1992-07-01", 27), ("1993-07-01", 28), ("1994-07-01", 29),
+                 ("1996-01-01", 30), ("1997-07-01", 31), ("1999-01-01", 32), ("2006-01-01", 33), ("2009-01-01", 34),
+                 ("2012-07-01", 35), ("2015-07-01", 36), ("2017-01-01", 37))
+_TT_MINUS_TAI_NS = 32_184_000_000
+
+
+def epochs_to_utc_iso(epoch_ns) -> np.ndarray:
+    """ISO-8601 UTC strings of epochs given in integer ns past J2000 (2000-01-01T12:00:00 TDB), for the "Epoch (UTC)" column of
+    the parquet exports (mc/results.rs:355-360: `epoch.to_time_scale(UTC).to_isoformat()`).  TDB is taken equal to TT (the
+    periodic difference stays below 1.7 ms); inside a leap second the UTC label repeats the following second."""
+    ep = np.asarray(epoch_ns, dtype=np.int64)
+    j2000 = np.datetime64("2000-01-01T12:00:00", "ns")
+    starts = np.array([(np.datetime64(d + "T00:00:00", "ns") - j2000).astype(np.int64) + dat * NS_PER_S + _TT_MINUS_TAI_NS
+                       for d, dat in _LEAP_SECONDS], dtype=np.int64)   # TT instants at which each TAI-UTC value starts to apply
+    dat = np.array([d for _, d in _LEAP_SECONDS], dtype=np.int64)
+    k = np.clip(np.searchsorted(starts, ep, side="right") - 1, 0, None)
+    utc = ep - _TT_MINUS_TAI_NS - dat[k] * NS_PER_S
+    return np.datetime_as_string(j2000 + utc.astype("timedelta64[ns]"), unit="ns")
+
+
 # --------------------------------------------------------------------------- state
 @dataclass(frozen=True)
 class Orbit:

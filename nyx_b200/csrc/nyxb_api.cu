@@ -26,6 +26,8 @@ extern "C" double nyxb_fp64_probe(int device, int iters);
 extern "C" cudaError_t nyxb_launch_od_coop(const DevSetup*, const DevOd*, const int*, size_t, const double*, const double*, const long long*,
                                            double*, long long*, nyxb_details*, int*, cudaStream_t);
 extern "C" int nyxb_od_coop_kmax(void);
+extern "C" cudaError_t nyxb_launch_traj_resample(long long, const long long*, const double*, const long long*, size_t, size_t,
+                                                 const long long*, double*, int*, cudaStream_t);
 extern "C" cudaError_t nyxb_launch_mvn(unsigned long long, unsigned long long, size_t, const double*, const double*, const double*,
                                        double*, double*, cudaStream_t);
 
@@ -62,6 +64,8 @@ struct nyxb_engine {
     // grow-only device buffers of the trajectory sink (host-pointer entry point)
     size_t sink_bytes = 0;
     unsigned char* d_sink = nullptr;
+    size_t rec_n = 0;        // the recording resident in d_sink: trajectories and capacity (nyxb_traj_resample with sink == NULL)
+    long long rec_cap = 0;
     std::vector<double> h_cnm, h_snm;      // host copies for building cooperative tables lazily
     std::map<int, DevCoop> coop;           // lanes -> device tables
     std::map<int, DevCoopStrict> scoop;    // lanes -> STRICT cooperative schedules
@@ -457,6 +461,7 @@ extern "C" int32_t nyxb_propagate_batch_event(nyxb_engine* eng, size_t n, const 
         dsink.epoch = (long long*)eng->d_sink;
         dsink.state = (double*)(eng->d_sink + cap * n * 8);
         dsink.count = (long long*)(eng->d_sink + cap * n * 56);
+        eng->rec_n = n; eng->rec_cap = sink->capacity;
     }
     TRY2(cudaEventRecord(eng->ev0, st));
     rc = launch(eng, n, d_f64, d_f64 + 9 * n, (const int64_t*)d_i64, end_epoch_ns, step_ns ? (int64_t*)(d_i64 + 2 * n) : nullptr,
@@ -738,6 +743,67 @@ extern "C" int32_t nyxb_mvn_sample(int32_t device, uint64_t seed, uint64_t first
     if (rc != NYXB_RC_OK) return rc;
     CUDA_TRY(cudaMemcpy(out_state_soa, d_out, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost));
     if (d_disp) CUDA_TRY(cudaMemcpy(out_dispersion_soa, d_disp, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost));
+    return NYXB_RC_OK;
+}
+
+// ---- batched Hermite resampling of recorded trajectories (nyxb_traj.cu)
+extern "C" int32_t nyxb_traj_resample_dev(nyxb_engine* eng, size_t n, const nyxb_traj_sink* sink, size_t m, const int64_t* query_epoch_ns,
+                                          double* out_state, int32_t* out_status, void* cuda_stream) {
+    if (!eng || !sink || !query_epoch_ns || !out_state || !out_status) { set_err("null argument"); return NYXB_RC_BAD_ARG; }
+    if (sink->capacity <= 0 || !sink->epoch_ns || !sink->state || !sink->count) { set_err("empty trajectory sink"); return NYXB_RC_BAD_ARG; }
+    CUDA_TRY(cudaSetDevice(eng->device));
+    cudaError_t err = nyxb_launch_traj_resample(sink->capacity, (const long long*)sink->epoch_ns, sink->state, (const long long*)sink->count,
+                                                n, m, (const long long*)query_epoch_ns, out_state, out_status, (cudaStream_t)cuda_stream);
+    if (err != cudaSuccess) { set_err(std::string("kernel launch: ") + cudaGetErrorString(err)); return NYXB_RC_CUDA; }
+    if (n && m) eng->launches += 1;
+    return NYXB_RC_OK;
+}
+
+extern "C" int32_t nyxb_traj_resample(nyxb_engine* eng, size_t n, const nyxb_traj_sink* sink, size_t m, const int64_t* query_epoch_ns,
+                                      double* out_state, int32_t* out_status) {
+    if (!eng || !query_epoch_ns || !out_state || !out_status) { set_err("null argument"); return NYXB_RC_BAD_ARG; }
+    if (sink && (sink->capacity <= 0 || !sink->epoch_ns || !sink->state || !sink->count)) { set_err("empty trajectory sink"); return NYXB_RC_BAD_ARG; }
+    if (!sink && (eng->rec_cap <= 0 || eng->rec_n != n || !eng->d_sink)) {
+        set_err("no resident recording of this many trajectories: pass the sink of nyxb_propagate_batch_traj");
+        return NYXB_RC_BAD_ARG;
+    }
+    if (n == 0 || m == 0) return NYXB_RC_OK;
+    CUDA_TRY(cudaSetDevice(eng->device));
+    if (!eng->stream) CUDA_TRY(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+    cudaStream_t st = eng->stream;
+    if (sink) {   // upload into the engine's sink slab: [epoch cap*n i64 | state 6*cap*n f64 | count n i64]
+        const size_t cap = (size_t)sink->capacity;
+        const size_t need = (cap * n * 7 + n) * 8;
+        if (need > eng->sink_bytes) {
+            cudaFree(eng->d_sink); eng->d_sink = nullptr; eng->sink_bytes = 0; eng->rec_n = 0; eng->rec_cap = 0;
+            CUDA_TRY(cudaMalloc(&eng->d_sink, need));
+            eng->sink_bytes = need;
+        }
+        CUDA_TRY(cudaMemcpyAsync(eng->d_sink, sink->epoch_ns, cap * n * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(eng->d_sink + cap * n * 8, sink->state, cap * n * 48, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(eng->d_sink + cap * n * 56, sink->count, n * 8, cudaMemcpyHostToDevice, st));
+        eng->rec_n = n; eng->rec_cap = sink->capacity;
+    }
+    const size_t cap = (size_t)eng->rec_cap;
+    nyxb_traj_sink dsink;
+    dsink.capacity = eng->rec_cap;
+    dsink.epoch_ns = (int64_t*)eng->d_sink;
+    dsink.state = (double*)(eng->d_sink + cap * n * 8);
+    dsink.count = (int64_t*)(eng->d_sink + cap * n * 56);
+    DevBufs B;
+    long long* d_q = B.put((const long long*)query_epoch_ns, m, st);
+    double* d_out = B.alloc<double>(6 * m * n);
+    int* d_status = B.alloc<int>(m * n);
+    if (!d_q || !d_out || !d_status) { set_err("device allocation / upload failed"); return NYXB_RC_CUDA; }
+    CUDA_TRY(cudaEventRecord(eng->ev0, st));
+    int32_t rc = nyxb_traj_resample_dev(eng, n, &dsink, m, (const int64_t*)d_q, d_out, d_status, st);
+    if (rc != NYXB_RC_OK) return rc;
+    CUDA_TRY(cudaEventRecord(eng->ev1, st));
+    CUDA_TRY(cudaMemcpyAsync(out_state, d_out, sizeof(double) * 6 * m * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_status, d_status, sizeof(int) * m * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, eng->ev0, eng->ev1) == cudaSuccess) eng->last_ms = ms;
     return NYXB_RC_OK;
 }
 

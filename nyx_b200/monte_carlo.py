@@ -98,21 +98,207 @@ class Run:
     result: object  # Spacecraft | PropagationError
 
 
+class MonteCarloError(RuntimeError):
+    """`MonteCarloError` (mc/mod.rs): `StateError` / `NoSuccessfulRuns`."""
+
+
+_RESAMPLE_CHUNK_BYTES = 256 << 20  # bound on the [6][m][n] block one resampling launch returns
+
+
 @dataclass
 class Results:
-    """`Results` (mc/results.rs:62-72) in final-state-only form + SoA views for bulk consumers."""
+    """`Results<Spacecraft, PropResult<Spacecraft>>` (mc/results.rs:62-81) in structure-of-arrays form.
+
+    `runs[i].result` is the final `Spacecraft` (or the run's error).  When the ensemble was run with `traj_capacity > 0`
+    the per-step states the reference keeps in each run's `Traj` (results.rs:74-81) live in `recording` — the step-major SoA
+    sink (epochs[cap][n], states[6][cap][n], count[n]) the kernels appended to — and the report accessors
+    (results.rs:88-240) resample it with ONE `nyxb_traj_resample` launch per report instead of one `Traj::at` per value."""
 
     runs: List[Run]
     scenario: str
     final_state_soa: np.ndarray = field(repr=False, default=None)  # [9][n]
     details: np.ndarray = field(repr=False, default=None)
     status: np.ndarray = field(repr=False, default=None)
+    recording: Optional[Tuple[np.ndarray, np.ndarray, np.ndarray]] = field(repr=False, default=None)
+    engine: object = field(repr=False, default=None)
 
     def ok_runs(self) -> List[Run]:
         return [r for r in self.runs if not isinstance(r.result, Exception)]
 
     def total_steps(self) -> int:
         return int(self.details["n_steps"].sum())
+
+    # ---- per-run views --------------------------------------------------------------------------------------------
+    def _mu(self) -> float:
+        return self.runs[0].dispersed_state.state.orbit.frame.mu_km3_s2()
+
+    def _ok_mask(self) -> np.ndarray:
+        return np.array([not isinstance(r.result, Exception) for r in self.runs], dtype=bool)
+
+    def _run_consts(self, idx):
+        """(Cr, Cd, prop mass) of the runs `idx`: constants of motion on this path (spacecraft.rs:229-236), dispersed per run."""
+        st = [self.runs[i].dispersed_state.state for i in idx]
+        return (np.array([x.srp.coeff_reflectivity for x in st]), np.array([x.drag.coeff_drag for x in st]),
+                np.array([x.mass.prop_mass_kg for x in st]))
+
+    def _require_recording(self):
+        if self.recording is None or self.engine is None:
+            raise MonteCarloError("no recorded trajectories: run the Monte Carlo with traj_capacity > 0")
+        return self.recording
+
+    def _spans(self):
+        """first / last recorded epoch of every run (Traj::first / last after finalize's sort, traj.rs:75-80, 128-137)."""
+        t_ep, _, t_cnt = self._require_recording()
+        n = t_ep.shape[1]
+        k = np.clip(np.minimum(t_cnt, t_ep.shape[0]) - 1, 0, None)
+        a, b = t_ep[0, :], t_ep[k, np.arange(n)]
+        return np.minimum(a, b), np.maximum(a, b)
+
+    def _resampled(self, step_ns: int, start_ns: Optional[int], end_ns: Optional[int]):
+        """`Traj::every_between` (traj.rs:153-162) for all successful runs: {run index: (epochs[k], rv[6][k])}.
+        TimeSeries::inclusive(max(start, first), min(end, last), step); the device evaluates a common grid per distinct
+        series start (a Monte Carlo's runs all start at the template epoch: one group, one launch per chunk)."""
+        step_ns = int(step_ns)
+        if step_ns <= 0:
+            raise ValueError("step must be positive")
+        t_ep, t_st, t_cnt = self._require_recording()
+        first, last = self._spans()
+        s = first if start_ns is None else np.maximum(first, int(start_ns))
+        e = last if end_ns is None else np.minimum(last, int(end_ns))
+        ok = self._ok_mask() & (t_cnt > 0)
+        out = {}
+        for s0 in np.unique(s[ok]):
+            cols = np.nonzero(ok & (s == s0))[0]
+            k = np.where(e[cols] >= s0, (e[cols] - s0) // step_ns + 1, 0)
+            m = int(k.max()) if len(cols) else 0
+            if m == 0:
+                for c in cols:
+                    out[int(c)] = (np.empty(0, dtype=np.int64), np.empty((6, 0)))
+                continue
+            grid = int(s0) + step_ns * np.arange(m, dtype=np.int64)
+            whole = len(cols) == t_ep.shape[1]
+            rec = self.recording if whole else (np.ascontiguousarray(t_ep[:, cols]), np.ascontiguousarray(t_st[:, :, cols]),
+                                                np.ascontiguousarray(t_cnt[cols]))
+            nc = len(cols)
+            chunk = max(1, _RESAMPLE_CHUNK_BYTES // (48 * nc))
+            rv = np.empty((6, m, nc))
+            st = np.empty((m, nc), dtype=np.int32)
+            for j0 in range(0, m, chunk):   # the recording is uploaded once, later chunks reuse the resident copy
+                o, q = self.engine.resample(grid[j0:j0 + chunk], rec if j0 == 0 else None, n=nc)
+                rv[:, j0:j0 + chunk], st[j0:j0 + chunk] = o, q
+            for q, c in enumerate(cols):
+                kq = int(k[q])
+                bad = np.nonzero(st[:kq, q])[0]   # the iterator ends at the first epoch without data (traj_it.rs:41-59)
+                if len(bad):
+                    kq = int(bad[0])
+                out[int(c)] = (grid[:kq], rv[:, :kq, q])
+        return out
+
+    def _report(self, param, per_run, value_if_run_failed):
+        """Shared shape of the report accessors (results.rs:98-123): run-major flat list; a failed run contributes
+        `value_if_run_failed` once (or nothing); a parameter a state cannot provide contributes it once per state."""
+        from .param import StateError, evaluate
+        report: List[float] = []
+        mu = self._mu()
+        for run in self.runs:
+            if isinstance(run.result, Exception) or run.index not in per_run:
+                if value_if_run_failed is not None:
+                    report.append(float(value_if_run_failed))
+                continue
+            rv = per_run[run.index]
+            cr, cd, pm = self._run_consts([run.index])
+            try:
+                vals = evaluate(param, rv, mu, run.dispersed_state.state, cr=cr[0], cd=cd[0], prop_mass_kg=pm[0])
+                report.extend(np.atleast_1d(vals).tolist())
+            except StateError:
+                if value_if_run_failed is not None:
+                    report.extend([float(value_if_run_failed)] * (rv.shape[1] if rv.ndim == 2 else 1))
+        return report
+
+    # ---- mc/results.rs:88-240 -------------------------------------------------------------------------------------
+    def every_value_of_between(self, param, step_ns: int, start_ns: int, end_ns: int, value_if_run_failed: Optional[float] = None):
+        """results.rs:90-124: `param` of every run every `step` between `start` and `end` (clamped to each run's span)."""
+        per_run = {i: rv for i, (_, rv) in self._resampled(step_ns, start_ns, end_ns).items()}
+        return self._report(param, per_run, value_if_run_failed)
+
+    def every_value_of(self, param, step_ns: int, value_if_run_failed: Optional[float] = None):
+        """results.rs:128-160: from the start to the end of each trajectory."""
+        per_run = {i: rv for i, (_, rv) in self._resampled(step_ns, None, None).items()}
+        return self._report(param, per_run, value_if_run_failed)
+
+    def first_values_of(self, param, value_if_run_failed: Optional[float] = None):
+        """results.rs:164-191: `traj.first()` of every run — the dispersed initial state."""
+        per_run = {r.index: r.dispersed_state.state.orbit.to_cartesian_pos_vel().reshape(6, 1) for r in self.ok_runs()}
+        return self._report(param, per_run, value_if_run_failed)
+
+    def last_values_of(self, param, value_if_run_failed: Optional[float] = None):
+        """results.rs:195-222: `traj.last()` of every run — the final state."""
+        per_run = {r.index: self.final_state_soa[:6, r.index].reshape(6, 1) for r in self.ok_runs()}
+        return self._report(param, per_run, value_if_run_failed)
+
+    def dispersion_values_of(self, param) -> List[float]:
+        """results.rs:225-240: the dispersion actually applied to `param` in every run."""
+        name = param.name if hasattr(param, "name") else str(param)
+        report = []
+        for run in self.runs:
+            for dparam, val in run.dispersed_state.actual_dispersions:
+                if dparam == name:
+                    report.append(val)
+                    break
+            else:
+                raise MonteCarloError(f"StateError: {name} unavailable in the dispersions")
+        return report
+
+    def to_parquet(self, path, fields=None, start_ns: Optional[int] = None, end_ns: Optional[int] = None,
+                   step_ns: Optional[int] = None, metadata: Optional[dict] = None):
+        """results.rs:242-427: one row per state of every successful run — all recorded states, or, when any of
+        start/end/step is given, the states interpolated every `step` (default 1 min, results.rs:285-296).
+        Columns: "Epoch (UTC)", "Monte Carlo Run Index", then the requested fields (default `Spacecraft::export_params`);
+        a field no state can provide is dropped (results.rs:326-343)."""
+        import pyarrow as pa
+        import pyarrow.parquet as pq
+
+        from .cosmic import epochs_to_utc_iso
+        from .param import EXPORT_PARAMS, StateError, evaluate
+
+        t_ep, t_st, t_cnt = self._require_recording()
+        ok = self._ok_mask()
+        if not ok.any():
+            raise MonteCarloError(f"NoSuccessfulRuns: export of {len(self.runs)} runs")
+        if start_ns is not None or end_ns is not None or step_ns is not None:
+            first_ok = int(np.nonzero(ok)[0][0])
+            first, last = self._spans()
+            per_run = self._resampled(60 * 10**9 if step_ns is None else step_ns,
+                                      int(first[first_ok]) if start_ns is None else start_ns,
+                                      int(last[first_ok]) if end_ns is None else end_ns)
+        else:
+            per_run = {}
+            for i in np.nonzero(ok)[0]:
+                k = int(min(t_cnt[i], t_ep.shape[0]))
+                order = np.argsort(t_ep[:k, i], kind="stable")
+                per_run[int(i)] = (t_ep[:k, i][order], t_st[:, :k, i][:, order])
+        idx = sorted(per_run)
+        epochs = np.concatenate([per_run[i][0] for i in idx]) if idx else np.empty(0, dtype=np.int64)
+        rv = np.concatenate([per_run[i][1] for i in idx], axis=1) if idx else np.empty((6, 0))
+        counts = [len(per_run[i][0]) for i in idx]
+        run_index = np.repeat(np.array(idx, dtype=np.int32), counts)
+        cr, cd, pm = (np.repeat(a, counts) for a in self._run_consts(idx))
+        frame = self.runs[0].dispersed_state.state.orbit.frame
+        cols = [pa.array(epochs_to_utc_iso(epochs), type=pa.string()), pa.array(run_index, type=pa.int32())]
+        schema = [pa.field("Epoch (UTC)", pa.string(), nullable=False), pa.field("Monte Carlo Run Index", pa.int32(), nullable=False)]
+        tmpl = self.runs[idx[0]].dispersed_state.state
+        for f in (EXPORT_PARAMS if fields is None else fields):
+            try:
+                vals = evaluate(f, rv, frame.mu_km3_s2(), tmpl, cr=cr, cd=cd, prop_mass_kg=pm)
+            except StateError:
+                continue
+            cols.append(pa.array(vals, type=pa.float64()))
+            schema.append(pa.field(str(f), pa.float64(), nullable=False, metadata={"unit": f.unit, "Frame": frame.name}))
+        meta = {"Purpose": "Monte Carlo Trajectory data"}
+        meta.update(metadata or {})
+        table = pa.Table.from_arrays(cols, schema=pa.schema(schema, metadata=meta))
+        pq.write_table(table, str(path))
+        return path
 
 
 class MonteCarlo:
@@ -141,12 +327,26 @@ class MonteCarlo:
         return st, disp
 
     def run_until_epoch(self, prop: Propagator, almanac: Optional[Almanac], end_epoch_ns: int, num_runs: int,
-                        device_dispersions: bool = False) -> Results:
+                        device_dispersions: bool = False, traj_capacity: int = 0) -> Results:
+        """mc/montecarlo.rs:188-203.  `traj_capacity` > 0 also records every accepted step of every run (what the reference
+        always keeps in `PropResult.traj`, results.rs:74-81) for the report accessors of `Results`."""
         if device_dispersions:
-            return self._run_device_dispersions(prop, almanac, 0, end_epoch_ns, num_runs)
-        return self.resume_run_until_epoch(prop, almanac, 0, end_epoch_ns, num_runs)
+            return self._run_device_dispersions(prop, almanac, 0, end_epoch_ns, num_runs, traj_capacity)
+        return self.resume_run_until_epoch(prop, almanac, 0, end_epoch_ns, num_runs, traj_capacity)
 
-    def _run_device_dispersions(self, prop, almanac, skip, end_epoch_ns, num_runs) -> Results:
+    @staticmethod
+    def _propagate(eng, st, cs, ep, end_epoch_ns, traj_capacity):
+        """One launch; with recording, the sink grows until no run overflows it (a truncated `Traj` would end early)."""
+        cap = int(traj_capacity)
+        if cap <= 0:
+            return eng.propagate_batch(st, cs, ep, end_epoch_ns) + (None,)
+        while True:
+            out, out_ep, det, status, rec = eng.propagate_batch(st, cs, ep, end_epoch_ns, traj_capacity=cap)
+            if int(det["n_steps"].max()) + 1 <= cap:
+                return out, out_ep, det, status, rec
+            cap = int(det["n_steps"].max()) + 1
+
+    def _run_device_dispersions(self, prop, almanac, skip, end_epoch_ns, num_runs, traj_capacity=0) -> Results:
         """mc/montecarlo.rs:208-273 with the dispersions drawn on the GPU."""
         tmpl = self.random_state.template
         st, disp = self.generate_states_on_device(skip, num_runs, self.seed, prop.device)
@@ -154,27 +354,27 @@ class MonteCarlo:
         cs[0], cs[1], cs[2], cs[3] = tmpl.mass.dry_mass_kg, tmpl.mass.extra_mass_kg, tmpl.srp.area_m2, tmpl.drag.area_m2
         ep = np.full(num_runs, tmpl.epoch(), dtype=np.int64)
         eng = prop.engine(self.nominal_state.orbit.frame, almanac)
-        out, out_ep, det, status = eng.propagate_batch(st, cs, ep, end_epoch_ns)
+        out, out_ep, det, status, rec = self._propagate(eng, st, cs, ep, end_epoch_ns, traj_capacity)
         runs = []
         for idx in range(num_runs):
             ds = DispersedState(tmpl.with_vector(tmpl.epoch(), st[:, idx]), [(p, float(-disp[q, idx])) for q, p in enumerate(_PARAMS)])
             err = status_error(status[idx])
             runs.append(Run(idx, ds, err if err is not None else ds.state.with_vector(int(out_ep[idx]), out[:, idx])))
-        return Results(runs, self.scenario, out, det, status)
+        return Results(runs, self.scenario, out, det, status, rec, eng)
 
     def resume_run_until_epoch(self, prop: Propagator, almanac: Optional[Almanac], skip: int, end_epoch_ns: int,
-                               num_runs: int) -> Results:
+                               num_runs: int, traj_capacity: int = 0) -> Results:
         """mc/montecarlo.rs:208-273"""
         init_states = self.generate_states(skip, num_runs, self.seed)
         st, cs, ep = pack_spacecraft(ds.state for _, ds in init_states)
         eng = prop.engine(self.nominal_state.orbit.frame, almanac)
-        out, out_ep, det, status = eng.propagate_batch(st, cs, ep, end_epoch_ns)
+        out, out_ep, det, status, rec = self._propagate(eng, st, cs, ep, end_epoch_ns, traj_capacity)
         runs = []
         for (idx, ds) in init_states:
             err = status_error(status[idx])
             res = err if err is not None else ds.state.with_vector(int(out_ep[idx]), out[:, idx])
             runs.append(Run(idx, ds, res))
-        return Results(runs, self.scenario, out, det, status)
+        return Results(runs, self.scenario, out, det, status, rec, eng)
 
     def run_until_nth_event(self, prop: Propagator, almanac: Optional[Almanac], max_duration_ns: int, event, trigger: int,
                             num_runs: int, traj_capacity: int = 2048) -> Results:
@@ -211,7 +411,7 @@ class MonteCarlo:
                 tr = Traj(ds.state, t_ep[:k, idx].copy(), np.ascontiguousarray(t_st[:, :k, idx].T)).finalize()
                 res = (locate_event(tr, event), tr)
             runs.append(Run(idx, ds, res))
-        return Results(runs, self.scenario, out, det, status)
+        return Results(runs, self.scenario, out, det, status, (t_ep, t_st, t_cnt), eng)
 
     def __str__(self):
         return f"{self.scenario} - Nyx Monte Carlo - seed: {self.seed}"

@@ -233,6 +233,32 @@ class Engine:
             ret = ret + (crossings,)
         return ret
 
+    def resample(self, query_epochs_ns, recording=None, n: Optional[int] = None):
+        """`nyxb_traj_resample`: `Traj::at` (traj.rs:83-126) for every trajectory of a recording at every query epoch, one launch.
+        `recording` = the (epochs[cap][n], states[6][cap][n], count[n]) tuple `propagate_batch(traj_capacity=...)` returned, or
+        None to reuse the recording of this engine's last propagation still resident on the device (pass its `n`).
+        Returns (states[6][m][n], status[m][n]); status 1 = no interpolation data at that epoch (values NaN)."""
+        q = np.ascontiguousarray(query_epochs_ns, dtype=np.int64)
+        if q.ndim != 1:
+            raise ValueError("query epochs must be a 1-D int64 array")
+        sink = None
+        if recording is not None:
+            t_ep, t_st, t_cnt = (np.ascontiguousarray(a) for a in recording)
+            cap, n = t_ep.shape
+            if t_ep.dtype != np.int64 or t_st.shape != (6, cap, n) or t_st.dtype != np.float64 or t_cnt.shape != (n,) or t_cnt.dtype != np.int64:
+                raise ValueError("expected epochs int64[cap][n], states float64[6][cap][n], count int64[n]")
+            sink = abi.TrajSink(int(cap), t_ep.ctypes.data, t_st.ctypes.data, t_cnt.ctypes.data)
+        elif n is None:
+            raise ValueError("pass the number of trajectories of the resident recording")
+        m = len(q)
+        out = np.empty((6, m, n))
+        status = np.empty((m, n), dtype=np.int32)
+        rc = self._lib.nyxb_traj_resample(self._h, n, C.byref(sink) if sink is not None else None, m, q.ctypes.data,
+                                          out.ctypes.data, status.ctypes.data)
+        if rc != 0:
+            raise PropagationError(f"nyxb_traj_resample rc={rc}: {abi.last_error()}")
+        return out, status
+
     def propagate_batch_stm(self, state_soa, consts_soa, epoch0_ns, end_epoch_ns, stm_in=None, step_ns=None):
         """`nyxb_propagate_batch_stm`: `Spacecraft::with_stm()` + propagate (spacecraft.rs:203-227, 312-363).
         Returns (state[9][n], epoch[n], stm[81][n] column-major per trajectory, details, status)."""

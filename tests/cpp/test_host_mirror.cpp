@@ -79,6 +79,21 @@ int main() {
         auto h2 = setup.propagate_batch_stm({mid}, 100 * NS_PER_S, nullptr, &h1.stm);
         CHECK(std::memcmp(h2.stm.data(), r.stm.data(), 81 * sizeof(double)) == 0);
     }
+    {   // trajectory recording + batched resampling (Traj::at, traj.rs:83-126): exact hits return the stored records bit for bit,
+        // epochs in between are interpolated, epochs outside the recorded span are flagged per entry
+        auto setup = Propagator::rk89(dynamics, IntegratorOptions::with_fixed_step_s(10.0));
+        Spacecraft other = init; other.x_km += 1.0;
+        auto tb = setup.propagate_batch_traj({init, other}, 300 * NS_PER_S, 64);
+        CHECK(tb.t_count[0] == 31 && tb.t_count[1] == 31 && tb.epoch_at(30, 1) == 300 * NS_PER_S);
+        CHECK(tb.state_at(0, 0, 1) == other.x_km && tb.state_at(0, 30, 0) == tb.state[0]);
+        auto rs = tb.every({-1, 0, 120 * NS_PER_S, 125 * NS_PER_S, 300 * NS_PER_S, 300 * NS_PER_S + 1});
+        CHECK(!rs.ok(0, 0) && !rs.ok(5, 1) && rs.ok(1, 0) && rs.ok(4, 1) && std::isnan(rs.at(0, 0, 0)));
+        CHECK(rs.at(0, 2, 0) == tb.state_at(0, 12, 0) && rs.at(4, 2, 1) == tb.state_at(4, 12, 1) && rs.at(2, 4, 1) == tb.state[2 * 2 + 1]);
+        const double mid = 0.5 * (tb.state_at(0, 12, 0) + tb.state_at(0, 13, 0));   // the chord misses the arc by ~ a h^2 / 8 ~ 1e-4 km
+        CHECK(std::fabs(rs.at(0, 3, 0) - mid) < 1e-3 && rs.at(0, 3, 0) != mid);
+        auto fine = setup.with(init).for_duration(125 * NS_PER_S);   // 12 steps of 10 s + a final 5 s step
+        CHECK(std::fabs(rs.at(0, 3, 0) - fine.x_km) < 1e-7 && std::fabs(rs.at(5, 3, 0) - fine.vz_km_s) < 1e-10);
+    }
     {   // device dispersions: shard-invariant, right spread
         Spacecraft nominal = init; nominal.frame = EARTH_J2000(); nominal.dry_mass_kg = 100.0;
         const double sd[9] = {1.0, 1.0, 1.0, 1e-3, 1e-3, 1e-3, 0, 0, 0};

@@ -4,7 +4,8 @@ import pytest
 
 import nyx_b200 as nb
 from nyx_b200.trajectory import Traj, hermite_eval
-from tests.util import S, leo_ensemble, leo_state, max_dr_dv, oracle_run
+from tests.util import (S, hermite_shim, leo_ensemble, leo_state, max_dr_dv, oracle_run, resample_queries,
+                        resample_reference)
 
 
 def _dyn(degree=8):
@@ -123,3 +124,33 @@ def test_prop_instance_with_traj_api(oracle):
     # explicit small capacity: truncated recording, same final state
     f2, tr2 = prop.with_(sc).for_duration_with_traj(6 * 3600 * S, capacity=16)
     assert len(tr2) == 16 and np.array_equal(f2.orbit.to_cartesian_pos_vel(), final.orbit.to_cartesian_pos_vel())
+
+
+# ---- batched resampling (nyxb_traj_resample): the kernel's per-(query, trajectory) function on the CPU
+def test_resample_core_matches_traj_at(oracle, tmp_path):
+    """The function the CUDA kernel runs per (query, trajectory), compiled for the host: bit-identical to Traj.at on ragged
+    recordings (different step counts per trajectory, capacity overflow, empty), forward and backward."""
+    frame = nb.EARTH_J2000
+    mc, (st, cs, ep) = leo_ensemble(7, seed=77)
+    prop = nb.Propagator.default(_dyn())
+    run = hermite_shim(tmp_path)
+    sc = leo_state(frame)
+    for end, cap in ((3 * 3600 * S, 256), (3 * 3600 * S, 40), (-2 * 3600 * S, 256)):
+        ep_b = ep.copy()
+        _, _, det, status, (t_ep, t_st, t_cnt) = _oracle_traj(oracle, prop, frame, st, cs, ep_b, end, cap)
+        assert (status == 0).all()
+        t_cnt = t_cnt.copy()
+        t_cnt -= 5 * np.arange(7)   # ragged: every trajectory keeps a different prefix of its records
+        t_cnt[6] = 0                # a run that recorded nothing
+        t_cnt[5] = 9                # fewer records than one interpolation window
+        lo, hi = min(0, end), max(0, end)
+        queries = resample_queries(t_ep if end > 0 else t_ep[::-1], t_cnt, hi) if end > 0 else \
+            np.concatenate([np.array([lo - 1, lo, lo + 1, -1, 0, 1, int(t_ep[2, 1])], dtype=np.int64),
+                            np.arange(lo, 0, 450 * S, dtype=np.int64) + 987_654_321])
+        want, want_status = resample_reference(sc, t_ep, t_st, t_cnt, queries)
+        got, got_status = run(t_ep, t_st, t_cnt, queries)
+        assert np.array_equal(got_status, want_status)
+        assert (want_status == 0).any() and (want_status == 1).any()
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        ok = want_status == 0
+        assert np.array_equal(got[:, ok], want[:, ok])   # same operations in the same order, no FMA: bit-identical

@@ -44,3 +44,56 @@ def oracle_run(oracle, prop: nb.Propagator, frame, almanac, st, cs, ep, end_ns, 
 def max_dr_dv(a, b):
     d = a - b
     return float(np.sqrt((d[:3] ** 2).sum(0)).max()), float(np.sqrt((d[3:6] ** 2).sum(0)).max())
+
+
+# ---- batched resampling (nyxb_traj_resample)
+def resample_reference(sc, t_ep, t_st, t_cnt, queries):
+    """Traj.at per trajectory and query -> (states[6][m][n], status[m][n]); NaN + 1 where TrajError."""
+    from nyx_b200.trajectory import Traj, TrajError
+    n, m = t_ep.shape[1], len(queries)
+    out = np.full((6, m, n), np.nan)
+    status = np.ones((m, n), dtype=np.int32)
+    for i in range(n):
+        k = int(t_cnt[i])
+        tr = Traj(sc, t_ep[:k, i].copy(), np.ascontiguousarray(t_st[:, :k, i].T)).finalize()
+        for j, q in enumerate(queries):
+            try:
+                out[:, j, i] = tr.at(int(q)).orbit.to_cartesian_pos_vel()
+                status[j, i] = 0
+            except TrajError:
+                pass
+    return out, status
+
+
+def hermite_shim(tmp_path):
+    """The resampling kernel's per-(query, trajectory) function (nyx_b200/csrc/nyxb_hermite.h) compiled for the host:
+    run(t_ep, t_st, t_cnt, queries) -> (states[6][m][n], status[m][n])."""
+    import ctypes
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    so = tmp_path / "hermite_core_shim.so"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC",
+                    str(root / "tests" / "cpp" / "hermite_core_shim.cpp"), "-o", str(so)], check=True, capture_output=True)
+    lib = ctypes.CDLL(str(so))
+    lib.shim_traj_resample.restype = None
+    lib.shim_traj_resample.argtypes = [ctypes.c_longlong] + [ctypes.c_void_p] * 3 + [ctypes.c_size_t] * 2 + [ctypes.c_void_p] * 3
+    def run(t_ep, t_st, t_cnt, queries):
+        cap, n = t_ep.shape
+        q = np.ascontiguousarray(queries, dtype=np.int64)
+        out = np.empty((6, len(q), n))
+        status = np.empty((len(q), n), dtype=np.int32)
+        t_ep, t_st, t_cnt = (np.ascontiguousarray(a) for a in (t_ep, t_st, t_cnt))
+        lib.shim_traj_resample(cap, t_ep.ctypes.data, t_st.ctypes.data, t_cnt.ctypes.data, n, len(q), q.ctypes.data,
+                               out.ctypes.data, status.ctypes.data)
+        return out, status
+    return run
+
+
+def resample_queries(t_ep, t_cnt, end):
+    """exact hits, both window edges, out-of-span epochs, a regular grid"""
+    k0 = int(t_cnt[0])
+    return np.concatenate([
+        np.array([-5, 0, 1, int(t_ep[1, 0]) - 1, int(t_ep[3, 0]), int(t_ep[k0 - 2, 0]) + 1, end - 1, end, end + 1], dtype=np.int64),
+        np.arange(0, end, 600 * S, dtype=np.int64) + 123_456_789,
+    ])
