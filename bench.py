@@ -546,6 +546,30 @@ def main():
             line["recording"] = {"value": local_steps / (rec_ms * 1e-3), "unit": "trajectory-steps/s", "ms": rec_ms, "records": recs,
                                  "bytes_written": recs * 56, "write_gbs": recs * 56 / (rec_ms * 1e-3) / 1e9,
                                  "note": "same pass with the start state + every accepted step recorded (instance.rs:297-326)"}
+            # batched resampling of that recording on a 5-minute grid (Traj::every, traj.rs:148-162): one launch, device buffers
+            grid = torch.arange(0, end + 1, 300 * 10**9, dtype=torch.int64, device=dev)
+            m = int(grid.numel())
+            r_out = torch.empty((6, m, n), dtype=torch.float64, device=dev)
+            r_status = torch.empty((m, n), dtype=torch.int32, device=dev)
+
+            def resample_pass():
+                rc = eng._lib.nyxb_traj_resample_dev(eng.handle, n, C.byref(sink), m, grid.data_ptr(), r_out.data_ptr(), r_status.data_ptr(),
+                                                     torch.cuda.current_stream(dev).cuda_stream)
+                assert rc == 0
+            resample_pass()
+            torch.cuda.synchronize(dev)
+            flush.fill_(1)
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record(); resample_pass(); r1.record(); torch.cuda.synchronize(dev)
+            rs_ms = r0.elapsed_time(r1)
+            n_ok = int((r_status == 0).sum().item())
+            rs_bytes = recs * 56 + m * n * 52   # every record read once (neighbouring queries share windows through L2) + the outputs
+            line["resample"] = {"value": m * n / (rs_ms * 1e-3), "unit": "interpolated states/s", "ms": rs_ms, "queries": m, "ok": n_ok,
+                                "algorithmic_bytes": rs_bytes, "gbs": rs_bytes / (rs_ms * 1e-3) / 1e9,
+                                "hbm_frac": rs_bytes / (rs_ms * 1e-3) / 1e9 / hbm_peak,
+                                "note": "nyxb_k_traj_resample: Traj::at (13-record Hermite window) for every trajectory at every grid epoch; "
+                                        "975 FP64 divisions per interpolated state (divided differences, no FMA: bit-identical to the host "
+                                        "restatement) make it division-bound, not HBM-bound"}
         if world == 1 and not args.no_cpu_baseline:
             leg = cpu_reference_leg(args, nb, min(args.cpu_sample, n))
             sample_n = min(args.cpu_sample, n)
