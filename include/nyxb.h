@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define NYXB_ABI_VERSION 2 /* 2: nyxb_srp gained `estimate`; STM, filter and dispersion entry points */
+#define NYXB_ABI_VERSION 3 /* 2: nyxb_srp gained `estimate`; STM, filter and dispersion entry points.  3: nyxb_traj_resample[_dev] */
 
 /* ---- IntegratorMethod — propagators/rk_methods/mod.rs:65-79 (same order) ---- */
 enum nyxb_method {
@@ -312,7 +312,7 @@ int32_t nyxb_propagate_batch_traj_dev(nyxb_engine* eng, size_t n,
  *  out_status      [m][n]     NYXB_TRAJ_OK, or NYXB_TRAJ_NO_DATA when the query lies outside the trajectory's recorded
  *                             span (TrajError::NoInterpolationData) — a per-entry status, the batch never aborts.
  * Seconds are counted from the first record of the window (the reference passes absolute ET seconds to anise's
- * hermite_eval, which is not in the tree: parity unpinned at that boundary, DESIGN.md §6). */
+ * hermite_eval, which is not in the tree: parity unpinned at that boundary, DESIGN.md §9). */
 enum nyxb_traj_status { NYXB_TRAJ_OK = 0, NYXB_TRAJ_NO_DATA = 1 };
 int32_t nyxb_traj_resample(nyxb_engine* eng, size_t n, const nyxb_traj_sink* sink,
                            size_t m, const int64_t* query_epoch_ns, double* out_state, int32_t* out_status);

@@ -11,7 +11,7 @@ from pathlib import Path
 
 import numpy as np
 
-NYXB_ABI_VERSION = 2  # include/nyxb.h
+NYXB_ABI_VERSION = 3  # include/nyxb.h
 NYXB_MAX_BODIES = 8
 NYXB_CENTRAL_BODY = -1
 
