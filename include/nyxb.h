@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define NYXB_ABI_VERSION 3 /* 2: nyxb_srp gained `estimate`; STM, filter and dispersion entry points.  3: nyxb_traj_resample[_dev] */
+#define NYXB_ABI_VERSION 3 /* 2: nyxb_srp gained `estimate`; STM, filter and dispersion entry points.  3: nyxb_traj_resample[_dev], nyxb_event_locate[_dev] */
 
 /* ---- IntegratorMethod — propagators/rk_methods/mod.rs:65-79 (same order) ---- */
 enum nyxb_method {
@@ -320,6 +320,26 @@ int32_t nyxb_traj_resample(nyxb_engine* eng, size_t n, const nyxb_traj_sink* sin
 int32_t nyxb_traj_resample_dev(nyxb_engine* eng, size_t n, const nyxb_traj_sink* sink,
                                size_t m, const int64_t* query_epoch_ns, double* out_state, int32_t* out_status,
                                void* cuda_stream);
+
+/* ---- Event location on the recorded trajectories (row (f)-3): the search `until_nth_event` runs after the propagation
+ * stopped (propagators/event.rs:166-211: Brent's method on `event(traj.at(epoch))` between the last state on the channel and
+ * the returned state), for all n runs in ONE launch.  The bracket is the last recorded step of each trajectory; the search
+ * stops when the bracket is narrower than `epoch_precision_ns`; the state at the event epoch is the Hermite-interpolated one
+ * (nyxb_traj_resample's arithmetic).
+ *  sink               as for nyxb_traj_resample (NULL: the resident recording of the last host-pointer propagation);
+ *  kind, value        the monitored scalar (enum nyxb_event_kind) and its desired value;
+ *  run_status         [n] or NULL: out_status of the propagation — runs with an error code are skipped;
+ *  out_event_epoch_ns [n], out_event_state [6][n] (NaN where not located),
+ *  out_status         [n]: NYXB_TRAJ_OK; NYXB_TRAJ_NO_DATA (skipped run, fewer than two records);
+ *                     NYXB_EVENT_NOT_BRACKETED (the scalar has the same sign at both ends of the last step). */
+enum { NYXB_EVENT_NOT_BRACKETED = 2 };
+int32_t nyxb_event_locate(nyxb_engine* eng, size_t n, const nyxb_traj_sink* sink, int32_t kind, double value,
+                          int64_t epoch_precision_ns, const int32_t* run_status,
+                          int64_t* out_event_epoch_ns, double* out_event_state, int32_t* out_status);
+/* Device-pointer variant (sink arrays, run_status and outputs are DEVICE pointers; stream-ordered). */
+int32_t nyxb_event_locate_dev(nyxb_engine* eng, size_t n, const nyxb_traj_sink* sink, int32_t kind, double value,
+                              int64_t epoch_precision_ns, const int32_t* run_status,
+                              int64_t* out_event_epoch_ns, double* out_event_state, int32_t* out_status, void* cuda_stream);
 
 /* ---- State-transition-matrix propagation (next row (f)-2 of SURVEY.md §8): `Spacecraft::with_stm()` + propagate.
  * The integrated vector is the reference's 90-vector [x,y,z,vx,vy,vz,Cr,Cd,prop_mass, STM 9x9 column-major]

@@ -272,6 +272,10 @@ def _declare(lib):
     lib.nyxb_traj_resample.argtypes = [vp, C.c_size_t, C.POINTER(TrajSink), C.c_size_t, vp, vp, vp]
     lib.nyxb_traj_resample_dev.restype = C.c_int32
     lib.nyxb_traj_resample_dev.argtypes = [vp, C.c_size_t, C.POINTER(TrajSink), C.c_size_t, vp, vp, vp, vp]
+    lib.nyxb_event_locate.restype = C.c_int32
+    lib.nyxb_event_locate.argtypes = [vp, C.c_size_t, C.POINTER(TrajSink), C.c_int32, C.c_double, C.c_int64, vp, vp, vp, vp]
+    lib.nyxb_event_locate_dev.restype = C.c_int32
+    lib.nyxb_event_locate_dev.argtypes = [vp, C.c_size_t, C.POINTER(TrajSink), C.c_int32, C.c_double, C.c_int64, vp, vp, vp, vp, vp]
     lib.nyxb_propagate_batch_event.restype = C.c_int32
     lib.nyxb_propagate_batch_event.argtypes = batch_args + [C.POINTER(TrajSink), C.POINTER(EventC)]
     lib.nyxb_propagate_batch_stm.restype = C.c_int32
@@ -311,6 +315,8 @@ EXPORTED_SYMBOLS = [
     "nyxb_propagate_batch_traj_dev",
     "nyxb_traj_resample",
     "nyxb_traj_resample_dev",
+    "nyxb_event_locate",
+    "nyxb_event_locate_dev",
     "nyxb_propagate_batch_event",
     "nyxb_propagate_batch_stm",
     "nyxb_od_ekf_batch",

@@ -28,6 +28,8 @@ extern "C" cudaError_t nyxb_launch_od_coop(const DevSetup*, const DevOd*, const 
 extern "C" int nyxb_od_coop_kmax(void);
 extern "C" cudaError_t nyxb_launch_traj_resample(long long, const long long*, const double*, const long long*, size_t, size_t,
                                                  const long long*, double*, int*, cudaStream_t);
+extern "C" cudaError_t nyxb_launch_event_locate(long long, const long long*, const double*, const long long*, size_t, int, double, long long,
+                                                const int*, long long*, double*, int*, cudaStream_t);
 extern "C" cudaError_t nyxb_launch_mvn(unsigned long long, unsigned long long, size_t, const double*, const double*, const double*,
                                        double*, double*, cudaStream_t);
 
@@ -759,19 +761,14 @@ extern "C" int32_t nyxb_traj_resample_dev(nyxb_engine* eng, size_t n, const nyxb
     return NYXB_RC_OK;
 }
 
-extern "C" int32_t nyxb_traj_resample(nyxb_engine* eng, size_t n, const nyxb_traj_sink* sink, size_t m, const int64_t* query_epoch_ns,
-                                      double* out_state, int32_t* out_status) {
-    if (!eng || !query_epoch_ns || !out_state || !out_status) { set_err("null argument"); return NYXB_RC_BAD_ARG; }
+// upload `sink` into the engine's slab (or check the resident recording when sink == NULL) and describe it with device pointers
+static int32_t resident_sink(nyxb_engine* eng, size_t n, const nyxb_traj_sink* sink, cudaStream_t st, nyxb_traj_sink* dsink) {
     if (sink && (sink->capacity <= 0 || !sink->epoch_ns || !sink->state || !sink->count)) { set_err("empty trajectory sink"); return NYXB_RC_BAD_ARG; }
     if (!sink && (eng->rec_cap <= 0 || eng->rec_n != n || !eng->d_sink)) {
         set_err("no resident recording of this many trajectories: pass the sink of nyxb_propagate_batch_traj");
         return NYXB_RC_BAD_ARG;
     }
-    if (n == 0 || m == 0) return NYXB_RC_OK;
-    CUDA_TRY(cudaSetDevice(eng->device));
-    if (!eng->stream) CUDA_TRY(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
-    cudaStream_t st = eng->stream;
-    if (sink) {   // upload into the engine's sink slab: [epoch cap*n i64 | state 6*cap*n f64 | count n i64]
+    if (sink) {   // [epoch cap*n i64 | state 6*cap*n f64 | count n i64]
         const size_t cap = (size_t)sink->capacity;
         const size_t need = (cap * n * 7 + n) * 8;
         if (need > eng->sink_bytes) {
@@ -785,22 +782,88 @@ extern "C" int32_t nyxb_traj_resample(nyxb_engine* eng, size_t n, const nyxb_tra
         eng->rec_n = n; eng->rec_cap = sink->capacity;
     }
     const size_t cap = (size_t)eng->rec_cap;
+    dsink->capacity = eng->rec_cap;
+    dsink->epoch_ns = (int64_t*)eng->d_sink;
+    dsink->state = (double*)(eng->d_sink + cap * n * 8);
+    dsink->count = (int64_t*)(eng->d_sink + cap * n * 56);
+    return NYXB_RC_OK;
+}
+
+extern "C" int32_t nyxb_traj_resample(nyxb_engine* eng, size_t n, const nyxb_traj_sink* sink, size_t m, const int64_t* query_epoch_ns,
+                                      double* out_state, int32_t* out_status) {
+    if (!eng || !query_epoch_ns || !out_state || !out_status) { set_err("null argument"); return NYXB_RC_BAD_ARG; }
+    if (sink && (sink->capacity <= 0 || !sink->epoch_ns || !sink->state || !sink->count)) { set_err("empty trajectory sink"); return NYXB_RC_BAD_ARG; }
+    if (!sink && (eng->rec_cap <= 0 || eng->rec_n != n || !eng->d_sink)) {
+        set_err("no resident recording of this many trajectories: pass the sink of nyxb_propagate_batch_traj");
+        return NYXB_RC_BAD_ARG;
+    }
+    if (n == 0 || m == 0) return NYXB_RC_OK;
+    CUDA_TRY(cudaSetDevice(eng->device));
+    if (!eng->stream) CUDA_TRY(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+    cudaStream_t st = eng->stream;
     nyxb_traj_sink dsink;
-    dsink.capacity = eng->rec_cap;
-    dsink.epoch_ns = (int64_t*)eng->d_sink;
-    dsink.state = (double*)(eng->d_sink + cap * n * 8);
-    dsink.count = (int64_t*)(eng->d_sink + cap * n * 56);
+    int32_t rc = resident_sink(eng, n, sink, st, &dsink);
+    if (rc != NYXB_RC_OK) return rc;
     DevBufs B;
     long long* d_q = B.put((const long long*)query_epoch_ns, m, st);
     double* d_out = B.alloc<double>(6 * m * n);
     int* d_status = B.alloc<int>(m * n);
     if (!d_q || !d_out || !d_status) { set_err("device allocation / upload failed"); return NYXB_RC_CUDA; }
     CUDA_TRY(cudaEventRecord(eng->ev0, st));
-    int32_t rc = nyxb_traj_resample_dev(eng, n, &dsink, m, (const int64_t*)d_q, d_out, d_status, st);
+    rc = nyxb_traj_resample_dev(eng, n, &dsink, m, (const int64_t*)d_q, d_out, d_status, st);
     if (rc != NYXB_RC_OK) return rc;
     CUDA_TRY(cudaEventRecord(eng->ev1, st));
     CUDA_TRY(cudaMemcpyAsync(out_state, d_out, sizeof(double) * 6 * m * n, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(out_status, d_status, sizeof(int) * m * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, eng->ev0, eng->ev1) == cudaSuccess) eng->last_ms = ms;
+    return NYXB_RC_OK;
+}
+
+// ---- event location on recorded trajectories (nyxb_traj.cu)
+static bool event_kind_ok(int32_t kind) { return kind >= NYXB_EVENT_RMAG && kind <= NYXB_EVENT_VMAG; }
+
+extern "C" int32_t nyxb_event_locate_dev(nyxb_engine* eng, size_t n, const nyxb_traj_sink* sink, int32_t kind, double value,
+                                         int64_t epoch_precision_ns, const int32_t* run_status, int64_t* out_event_epoch_ns,
+                                         double* out_event_state, int32_t* out_status, void* cuda_stream) {
+    if (!eng || !sink || !out_event_epoch_ns || !out_event_state || !out_status) { set_err("null argument"); return NYXB_RC_BAD_ARG; }
+    if (sink->capacity <= 0 || !sink->epoch_ns || !sink->state || !sink->count) { set_err("empty trajectory sink"); return NYXB_RC_BAD_ARG; }
+    if (!event_kind_ok(kind) || epoch_precision_ns < 0) { set_err("bad event descriptor"); return NYXB_RC_BAD_ARG; }
+    CUDA_TRY(cudaSetDevice(eng->device));
+    cudaError_t err = nyxb_launch_event_locate(sink->capacity, (const long long*)sink->epoch_ns, sink->state, (const long long*)sink->count, n,
+                                               kind, value, epoch_precision_ns, run_status, (long long*)out_event_epoch_ns, out_event_state,
+                                               out_status, (cudaStream_t)cuda_stream);
+    if (err != cudaSuccess) { set_err(std::string("kernel launch: ") + cudaGetErrorString(err)); return NYXB_RC_CUDA; }
+    if (n) eng->launches += 1;
+    return NYXB_RC_OK;
+}
+
+extern "C" int32_t nyxb_event_locate(nyxb_engine* eng, size_t n, const nyxb_traj_sink* sink, int32_t kind, double value,
+                                     int64_t epoch_precision_ns, const int32_t* run_status, int64_t* out_event_epoch_ns,
+                                     double* out_event_state, int32_t* out_status) {
+    if (!eng || !out_event_epoch_ns || !out_event_state || !out_status) { set_err("null argument"); return NYXB_RC_BAD_ARG; }
+    if (!event_kind_ok(kind) || epoch_precision_ns < 0) { set_err("bad event descriptor"); return NYXB_RC_BAD_ARG; }
+    if (n == 0) return NYXB_RC_OK;
+    CUDA_TRY(cudaSetDevice(eng->device));
+    if (!eng->stream) CUDA_TRY(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+    cudaStream_t st = eng->stream;
+    nyxb_traj_sink dsink;
+    int32_t rc = resident_sink(eng, n, sink, st, &dsink);
+    if (rc != NYXB_RC_OK) return rc;
+    DevBufs B;
+    int* d_run = run_status ? B.put((const int*)run_status, n, st) : nullptr;
+    long long* d_ep = B.alloc<long long>(n);
+    double* d_out = B.alloc<double>(6 * n);
+    int* d_status = B.alloc<int>(n);
+    if ((run_status && !d_run) || !d_ep || !d_out || !d_status) { set_err("device allocation / upload failed"); return NYXB_RC_CUDA; }
+    CUDA_TRY(cudaEventRecord(eng->ev0, st));
+    rc = nyxb_event_locate_dev(eng, n, &dsink, kind, value, epoch_precision_ns, d_run, (int64_t*)d_ep, d_out, d_status, st);
+    if (rc != NYXB_RC_OK) return rc;
+    CUDA_TRY(cudaEventRecord(eng->ev1, st));
+    CUDA_TRY(cudaMemcpyAsync(out_event_epoch_ns, d_ep, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_event_state, d_out, sizeof(double) * 6 * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_status, d_status, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, eng->ev0, eng->ev1) == cudaSuccess) eng->last_ms = ms;

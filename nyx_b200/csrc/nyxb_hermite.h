@@ -7,6 +7,7 @@
 // through value/derivative pairs — the algorithm of NAIF HRMINT / SPK type 13 — evaluated with sub, div, mul, add only, in the
 // operation order of nyx_b200/trajectory.py::hermite_eval (bit-identical when built without FMA contraction).
 #pragma once
+#include <math.h>
 #include <stddef.h>
 
 #if defined(__CUDACC__)
@@ -105,4 +106,81 @@ NYXB_HD int nyxb_traj_at(const NyxbTrajView& tv, size_t n, size_t i, long long q
 #undef NYXB_EP
 #undef NYXB_REC
     return 0;
+}
+
+// ---- Event location inside the bracketing step (propagators/event.rs:166-211): the propagation kernels stop at the end of the
+// step in which the event scalar crossed zero for the trigger-th time; the root is searched on the Hermite-interpolated
+// recording between the last two records with Brent's method (Brent 1973, ch. 4; the reference calls anise's `brent_solver`,
+// not in the tree: restated from the published algorithm, parity unpinned).  Operation order of nyx_b200/event.py.
+
+// event scalar minus the desired value: the closed set of include/nyxb.h (enum nyxb_event_kind), reference operation order
+NYXB_HD double nyxb_event_scalar(int kind, double value, const double rv[6]) {
+    double s;
+    switch (kind) {
+    case 1: s = sqrt((rv[0] * rv[0] + rv[1] * rv[1]) + rv[2] * rv[2]); break;        // NYXB_EVENT_RMAG
+    case 2: s = (rv[0] * rv[3] + rv[1] * rv[4]) + rv[2] * rv[5]; break;              // NYXB_EVENT_RDOTV
+    case 3: s = rv[0]; break;                                                        // NYXB_EVENT_X
+    case 4: s = rv[1]; break;                                                        // NYXB_EVENT_Y
+    case 5: s = rv[2]; break;                                                        // NYXB_EVENT_Z
+    default: s = sqrt((rv[3] * rv[3] + rv[4] * rv[4]) + rv[5] * rv[5]); break;       // NYXB_EVENT_VMAG
+    }
+    return s - value;
+}
+
+// f(dt) of the search: the event scalar on the interpolated state dt seconds after t0 (rounded to integer ns, half to even)
+NYXB_HD int nyxb_event_f(const NyxbTrajView& tv, size_t n, size_t i, int kind, double value, long long t0, double dt_s, double* f) {
+    double rv[6];
+    if (nyxb_traj_at(tv, n, i, t0 + llrint(dt_s * 1e9), rv)) return 1;
+    *f = nyxb_event_scalar(kind, value, rv);
+    return 0;
+}
+
+// returns 0 and (event epoch, interpolated state), 1 = no bracket in the recording (fewer than two records / no data),
+// 2 = the last step does not bracket a root (same sign at both ends)
+NYXB_HD int nyxb_event_locate_one(const NyxbTrajView& tv, size_t n, size_t i, int kind, double value, long long precision_ns,
+                                  long long* ev_epoch, double rv[6]) {
+    long long cnt = tv.count[i];
+    if (cnt > tv.cap) cnt = tv.cap;
+    if (cnt < 2) return 1;
+    // the last step taken, in recording order (forward: the two largest epochs; backward: the two smallest)
+    const long long e1 = tv.epoch[(size_t)(cnt - 2) * n + i], e2 = tv.epoch[(size_t)(cnt - 1) * n + i];
+    const long long t0 = e1 < e2 ? e1 : e2, t1 = e1 < e2 ? e2 : e1;
+    const double xtol = (double)precision_ns * 1e-9;
+    double a = 0.0, b = (double)(t1 - t0) * 1e-9, fa, fb;
+    if (nyxb_event_f(tv, n, i, kind, value, t0, a, &fa) || nyxb_event_f(tv, n, i, kind, value, t0, b, &fb)) return 1;
+    double root = b;
+    if (fa == 0.0) root = a;
+    else if (fb == 0.0) root = b;
+    else if (fa * fb > 0.0) return 2;
+    else {
+        double c = a, fc = fa, d = b - a, e = b - a;
+        for (int it = 0; it < 100; ++it) {
+            if (fb * fc > 0.0) { c = a; fc = fa; d = b - a; e = d; }
+            if (fabs(fc) < fabs(fb)) { a = b; b = c; c = a; fa = fb; fb = fc; fc = fa; }
+            const double tol = 2.0 * 2.220446049250313e-16 * fabs(b) + 0.5 * xtol;
+            const double m = 0.5 * (c - b);
+            if (fabs(m) <= tol || fb == 0.0) break;
+            if (fabs(e) >= tol && fabs(fa) > fabs(fb)) {
+                const double s = fb / fa;
+                double p, q;
+                if (a == c) { p = 2.0 * m * s; q = 1.0 - s; }
+                else {
+                    const double qq = fa / fc, r = fb / fc;
+                    p = s * (2.0 * m * qq * (qq - r) - (b - a) * (r - 1.0));
+                    q = (qq - 1.0) * (r - 1.0) * (s - 1.0);
+                }
+                if (p > 0.0) q = -q;
+                p = fabs(p);
+                const double lim1 = 3.0 * m * q - fabs(tol * q), lim2 = fabs(e * q);
+                if (2.0 * p < (lim1 < lim2 ? lim1 : lim2)) { e = d; d = p / q; }
+                else { d = m; e = m; }
+            } else { d = m; e = m; }
+            a = b; fa = fb;
+            b = (fabs(d) > tol) ? b + d : b + copysign(tol, m);
+            if (nyxb_event_f(tv, n, i, kind, value, t0, b, &fb)) return 1;
+        }
+        root = b;
+    }
+    *ev_epoch = t0 + llrint(root * 1e9);
+    return nyxb_traj_at(tv, n, i, *ev_epoch, rv);
 }

@@ -38,3 +38,38 @@ extern "C" cudaError_t nyxb_launch_traj_resample(long long cap, const long long*
     nyxb_k_traj_resample<<<grid, 128, 0, stream>>>(tv, n, m, query, out_state, out_status);
     return cudaGetLastError();
 }
+
+// ---- event location: one thread per trajectory searches the last recorded step (nyxb_hermite.h: nyxb_event_locate_one)
+__global__ void __launch_bounds__(128)
+nyxb_k_event_locate(const NyxbTrajView tv, size_t n, int kind, double value, long long precision_ns, const int* __restrict__ run_status,
+                    long long* __restrict__ out_epoch, double* __restrict__ out_state, int* __restrict__ out_status) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    double rv[6] = {nan, nan, nan, nan, nan, nan};
+    long long ev = 0;
+    int status = NYXB_TRAJ_NO_DATA;
+    if (!run_status || (run_status[i] & 0xff) == 0) {   // failed runs have no event to locate
+        status = nyxb_event_locate_one(tv, n, i, kind, value, precision_ns, &ev, rv);
+        if (status) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) rv[c] = nan;
+            ev = 0;
+        }
+    }
+    out_epoch[i] = ev;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) out_state[(size_t)c * n + i] = rv[c];
+    out_status[i] = status;
+}
+
+extern "C" cudaError_t nyxb_launch_event_locate(long long cap, const long long* epoch, const double* state, const long long* count,
+                                                size_t n, int kind, double value, long long precision_ns, const int* run_status,
+                                                long long* out_epoch, double* out_state, int* out_status, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    NyxbTrajView tv;
+    tv.cap = cap; tv.epoch = epoch; tv.state = state; tv.count = count;
+    nyxb_k_event_locate<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(tv, n, kind, value, precision_ns, run_status, out_epoch, out_state,
+                                                                          out_status);
+    return cudaGetLastError();
+}

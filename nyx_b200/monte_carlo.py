@@ -383,9 +383,9 @@ class MonteCarlo:
     def resume_run_until_nth_event(self, prop: Propagator, almanac: Optional[Almanac], skip: int, max_duration_ns: int, event,
                                    trigger: int, num_runs: int, traj_capacity: int = 2048) -> Results:
         """mc/montecarlo.rs:115-183: every run stops at the end of the step in which `event` crossed zero for the
-        `trigger`-th time (ONE device launch with the stop condition + recording), then the event epoch is located per
-        run on its recorded trajectory (event.rs:186-211).  A run's result is (state at the event, Traj) or the error."""
-        from .event import locate_event
+        `trigger`-th time (ONE device launch with the stop condition + recording), then the event epoch of every run is
+        located on the recording still on the device (ONE launch of `nyxb_event_locate`, event.rs:186-211).
+        A run's result is (state at the event, Traj) or the error."""
         from .trajectory import Traj
 
         init_states = self.generate_states(skip, num_runs, self.seed)
@@ -399,6 +399,7 @@ class MonteCarlo:
             if int(det["n_steps"].max()) + 1 <= cap:
                 break
             cap *= 4  # a run overflowed its sink: its bracket would be lost
+        ev_ep, ev_st, ev_status = eng.locate_events(event.kind, event.value, event.epoch_precision_ns, n=num_runs, run_status=status)
         runs = []
         for (idx, ds) in init_states:
             code = int(status[idx]) & 0xFF
@@ -409,7 +410,10 @@ class MonteCarlo:
             else:
                 k = int(t_cnt[idx])
                 tr = Traj(ds.state, t_ep[:k, idx].copy(), np.ascontiguousarray(t_st[:, :k, idx].T)).finalize()
-                res = (locate_event(tr, event), tr)
+                if ev_status[idx] == 0:
+                    res = (tr._sc(int(ev_ep[idx]), ev_st[:, idx]), tr)
+                else:
+                    res = PropagationError(f"event search failed in the bracketing step (status {int(ev_status[idx])})")
             runs.append(Run(idx, ds, res))
         return Results(runs, self.scenario, out, det, status, (t_ep, t_st, t_cnt), eng)
 

@@ -259,6 +259,35 @@ class Engine:
             raise PropagationError(f"nyxb_traj_resample rc={rc}: {abi.last_error()}")
         return out, status
 
+    def locate_events(self, kind: int, value: float, epoch_precision_ns: int, recording=None, n: Optional[int] = None, run_status=None):
+        """`nyxb_event_locate`: the Brent search of `until_nth_event` (event.rs:186-211) inside the last recorded step of every
+        trajectory, one launch.  `recording` / `n` as for `resample`; `run_status` = the propagation's status array (failed runs
+        are skipped).  Returns (event_epoch_ns[n], event_state[6][n], status[n]): status 0 located, 1 no bracket / skipped,
+        2 the last step does not bracket a root."""
+        sink = None
+        if recording is not None:
+            t_ep, t_st, t_cnt = (np.ascontiguousarray(a) for a in recording)
+            cap, n = t_ep.shape
+            if t_ep.dtype != np.int64 or t_st.shape != (6, cap, n) or t_st.dtype != np.float64 or t_cnt.shape != (n,) or t_cnt.dtype != np.int64:
+                raise ValueError("expected epochs int64[cap][n], states float64[6][cap][n], count int64[n]")
+            sink = abi.TrajSink(int(cap), t_ep.ctypes.data, t_st.ctypes.data, t_cnt.ctypes.data)
+        elif n is None:
+            raise ValueError("pass the number of trajectories of the resident recording")
+        rs_ptr = None
+        if run_status is not None:
+            run_status = np.ascontiguousarray(run_status, dtype=np.int32)
+            if run_status.shape != (n,):
+                raise ValueError("run_status must be int32[n]")
+            rs_ptr = run_status.ctypes.data
+        ev_epoch = np.zeros(n, dtype=np.int64)
+        ev_state = np.empty((6, n))
+        status = np.empty(n, dtype=np.int32)
+        rc = self._lib.nyxb_event_locate(self._h, n, C.byref(sink) if sink is not None else None, int(kind), float(value),
+                                         int(epoch_precision_ns), rs_ptr, ev_epoch.ctypes.data, ev_state.ctypes.data, status.ctypes.data)
+        if rc != 0:
+            raise PropagationError(f"nyxb_event_locate rc={rc}: {abi.last_error()}")
+        return ev_epoch, ev_state, status
+
     def propagate_batch_stm(self, state_soa, consts_soa, epoch0_ns, end_epoch_ns, stm_in=None, step_ns=None):
         """`nyxb_propagate_batch_stm`: `Spacecraft::with_stm()` + propagate (spacecraft.rs:203-227, 312-363).
         Returns (state[9][n], epoch[n], stm[81][n] column-major per trajectory, details, status)."""
@@ -467,8 +496,8 @@ class PropInstance:
     def until_nth_event(self, max_duration_ns: int, event, trigger: int = 1, capacity: Optional[int] = None):
         """event.rs:88-211: propagate until `event` crossed zero `trigger` times (or raise NthEventError after
         `max_duration_ns`); returns (state interpolated at the event epoch, Traj up to the end of the bracketing step).
-        The stop condition runs on the device, the Brent search on the recorded trajectory here (event.rs:186-196)."""
-        from .event import locate_event
+        The stop condition runs inside the propagation kernel; the Brent search (event.rs:186-196) runs on the recording it
+        left on the device (`nyxb_event_locate`; `nyx_b200.event.locate_event` is the host restatement the tests check it with)."""
         from .trajectory import Traj
 
         start = self.state
@@ -497,7 +526,10 @@ class PropInstance:
             raise err
         k = int(t_cnt[0])
         tr = Traj(start, t_ep[:k, 0].copy(), np.ascontiguousarray(t_st[:, :k, 0].T)).finalize()
-        return locate_event(tr, event), tr
+        ev_ep, ev_st, ev_status = eng.locate_events(event.kind, event.value, event.epoch_precision_ns, n=1)  # resident recording
+        if ev_status[0] != 0:
+            raise PropagationError(f"event search failed in the bracketing step (status {int(ev_status[0])})")
+        return tr._sc(int(ev_ep[0]), ev_st[:, 0]), tr
 
     def until_epoch(self, end_ns: int) -> Spacecraft:
         """instance.rs:279-282"""

@@ -81,6 +81,86 @@ def test_locate_event_on_oracle_trajectory(oracle):
         assert abs(ev.eval(found)) < tol
 
 
+def _host_locate(sc, t_ep, t_st, t_cnt, ev, run_status=None):
+    """locate_event per run -> (epoch[n], state[6][n], status[n]) with the device entry point's status convention"""
+    n = t_ep.shape[1]
+    ev_ep, ev_st, status = np.zeros(n, dtype=np.int64), np.full((6, n), np.nan), np.ones(n, dtype=np.int32)
+    for i in range(n):
+        k = int(t_cnt[i])
+        if k < 2 or (run_status is not None and run_status[i] & 0xFF):
+            continue
+        tr = Traj(sc, t_ep[:k, i].copy(), np.ascontiguousarray(t_st[:, :k, i].T)).finalize()
+        try:
+            found = locate_event(tr, ev)
+        except ValueError:
+            status[i] = 2
+            continue
+        ev_ep[i], ev_st[:, i], status[i] = found.epoch(), found.orbit.to_cartesian_pos_vel(), 0
+    return ev_ep, ev_st, status
+
+
+def test_event_locate_core_matches_host_brent(oracle, tmp_path):
+    """The function the event-location kernel runs per trajectory (nyxb_hermite.h), compiled for the host: same Brent
+    iterates, same interpolation, hence the same event epoch (integer ns) and bit-identical state as `locate_event`."""
+    from tests.util import hermite_shim
+    frame = nb.EARTH_J2000
+    n = 12
+    mc, (st, cs, ep) = leo_ensemble(n, seed=29)
+    sc = mc.nominal_state
+    prop = nb.Propagator.default(_dyn())
+    locate = hermite_shim(tmp_path).locate
+    for ev in (Event.node(), Event.apsis(), Event.radius(6679.5), Event.component("x", 100.0), Event.speed(7.75),
+               Event.node(epoch_precision_ns=50)):
+        out, out_ep, det, status, (t_ep, t_st, t_cnt), crossings = _oracle_event(oracle, prop, frame, st, cs, ep, 5 * 3600 * S, 256, ev, 2)
+        status = status.copy()
+        t_cnt = t_cnt.copy()
+        status[3] = abi.ERR_PROP_MATH      # a failed run is skipped
+        t_cnt[5] = 1                       # a run without a bracket
+        t_cnt[7] -= 1                      # its last remaining step does not contain the crossing
+        want = _host_locate(sc, t_ep, t_st, t_cnt, ev, status)
+        got = locate(t_ep, t_st, t_cnt, ev.kind, ev.value, ev.epoch_precision_ns, status)
+        assert np.array_equal(got[2], want[2]) and got[2][3] == 1 and got[2][5] == 1
+        ok = want[2] == 0
+        assert ok.sum() >= n - 4 and np.array_equal(got[0], want[0]) and np.array_equal(got[1][:, ok], want[1][:, ok])
+        assert np.isnan(got[1][:, ~ok]).all()
+        if (status & 0xFF == 0)[7]:
+            assert got[2][7] == 2
+
+
+@pytest.mark.gpu
+def test_gpu_event_locate_matches_host_brent(oracle):
+    """nyxb_event_locate through the C ABI: bit-identical to the host restatement on the engine's own recording (resident and
+    re-uploaded), failed runs skipped, argument checks."""
+    frame = nb.EARTH_J2000
+    n = 40
+    mc, (st, cs, ep) = leo_ensemble(n, seed=31)
+    sc = mc.nominal_state
+    eng = nb.Propagator.default(_dyn(21), mode=nb.MODE_FAST).engine(frame, None)
+    for ev in (Event.node(), Event.apsis(), Event.radius(6679.5)):
+        out, out_ep, det, status, (t_ep, t_st, t_cnt), crossings = eng.propagate_batch(
+            st, cs, ep, 5 * 3600 * S, traj_capacity=256, event=(ev.kind, ev.value, 2))
+        want = _host_locate(sc, t_ep, t_st, t_cnt, ev, status)
+        got = eng.locate_events(ev.kind, ev.value, ev.epoch_precision_ns, n=n, run_status=status)
+        assert (want[2] == 0).sum() >= n // 2
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w, equal_nan=True)
+        status2 = status.copy()
+        status2[1] = abi.ERR_PROP_MATH
+        t_cnt2 = t_cnt.copy()
+        t_cnt2[2] -= 1
+        got2 = eng.locate_events(ev.kind, ev.value, ev.epoch_precision_ns, (t_ep, t_st, t_cnt2), run_status=status2)
+        want2 = _host_locate(sc, t_ep, t_st, t_cnt2, ev, status2)
+        for g, w in zip(got2, want2):
+            assert np.array_equal(g, w, equal_nan=True)
+        assert got2[2][1] == 1
+    with pytest.raises(nb.PropagationError):
+        eng.locate_events(99, 0.0, 1000, n=n)
+    with pytest.raises(nb.PropagationError):
+        eng.locate_events(ev.kind, 0.0, 1000, n=n + 1)
+    with pytest.raises(ValueError):
+        eng.locate_events(ev.kind, 0.0, 1000)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode,lanes", [(nb.MODE_STRICT, 1), (nb.MODE_STRICT, 8), (nb.MODE_FAST, 1), (nb.MODE_FAST, 8), (nb.MODE_FAST, 32)])
 @pytest.mark.parametrize("kind", ["apsis", "node", "radius"])

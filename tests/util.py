@@ -76,6 +76,9 @@ def hermite_shim(tmp_path):
     subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC",
                     str(root / "tests" / "cpp" / "hermite_core_shim.cpp"), "-o", str(so)], check=True, capture_output=True)
     lib = ctypes.CDLL(str(so))
+    lib.shim_event_locate.restype = None
+    lib.shim_event_locate.argtypes = ([ctypes.c_longlong] + [ctypes.c_void_p] * 3 + [ctypes.c_size_t, ctypes.c_int, ctypes.c_double,
+                                      ctypes.c_longlong] + [ctypes.c_void_p] * 4)
     lib.shim_traj_resample.restype = None
     lib.shim_traj_resample.argtypes = [ctypes.c_longlong] + [ctypes.c_void_p] * 3 + [ctypes.c_size_t] * 2 + [ctypes.c_void_p] * 3
     def run(t_ep, t_st, t_cnt, queries):
@@ -87,6 +90,19 @@ def hermite_shim(tmp_path):
         lib.shim_traj_resample(cap, t_ep.ctypes.data, t_st.ctypes.data, t_cnt.ctypes.data, n, len(q), q.ctypes.data,
                                out.ctypes.data, status.ctypes.data)
         return out, status
+
+    def locate(t_ep, t_st, t_cnt, kind, value, precision_ns, run_status=None):
+        cap, n = t_ep.shape
+        t_ep, t_st, t_cnt = (np.ascontiguousarray(a) for a in (t_ep, t_st, t_cnt))
+        rs = None if run_status is None else np.ascontiguousarray(run_status, dtype=np.int32)
+        ev_ep = np.zeros(n, dtype=np.int64)
+        ev_st = np.empty((6, n))
+        status = np.empty(n, dtype=np.int32)
+        lib.shim_event_locate(cap, t_ep.ctypes.data, t_st.ctypes.data, t_cnt.ctypes.data, n, int(kind), float(value), int(precision_ns),
+                              None if rs is None else rs.ctypes.data, ev_ep.ctypes.data, ev_st.ctypes.data, status.ctypes.data)
+        return ev_ep, ev_st, status
+
+    run.locate = locate
     return run
 
 
