@@ -16,6 +16,7 @@ from .gravity import GravityFieldData
 from .monte_carlo import DispersedState, MonteCarlo, MonteCarloError, MvnSpacecraft, Results, Run
 from .param import EXPORT_PARAMS, StateError, StateParameter
 from .trajectory import Traj, TrajError, hermite_eval
+from . import dhall
 from .config import PropagatorConfig, integrator_options_from, load_ground_stations, parse_duration
 from .event import Event, brent, locate_event
 from .od import (GroundStation, KalmanODProcess, KalmanVariant, KfEstimate, LocalFrame, MeasurementType, ODError, ODSolution,

@@ -7,7 +7,9 @@
   stochastic_noises{range_km, doppler_km_s}{white_noise{sigma}, bias{constant}}, measurement_types, light_time_correction);
 * durations are hifitime strings ("1 min", "60 s", "2 h 30 min") or integer nanoseconds.
 
-Dicts (already parsed YAML / JSON) and file paths are both accepted; YAML needs PyYAML.  Nothing here touches the device.
+Dicts (already parsed YAML / JSON) and file paths are both accepted: `.dhall` files — the format the reference ships its
+configurations in (data/02_config/prop_config.dhall, full_seq.dhall) — go through the data-subset reader `nyx_b200.dhall`,
+anything else through PyYAML.  Nothing here touches the device.
 """
 from __future__ import annotations
 
@@ -46,6 +48,10 @@ def parse_duration(v) -> int:
 def _load(src: Union[str, Path, dict]) -> dict:
     if isinstance(src, dict):
         return src
+    if str(src).endswith(".dhall"):
+        from . import dhall
+
+        return dhall.load(src)
     import yaml
 
     return yaml.safe_load(Path(src).read_text())
@@ -85,7 +91,20 @@ class PropagatorConfig:
     def load(cls, src: Union[str, Path, dict]) -> "PropagatorConfig":
         d = _load(src)
         m = d.get("method", "RungeKutta89")
-        return cls(d.get("dynamics", {}) or {}, IntegratorMethod[m] if isinstance(m, str) else IntegratorMethod(m), integrator_options_from(d.get("options")))
+        dyn = d.get("dynamics")
+        if dyn is None:   # data/02_config/prop_config.dhall keeps the `Dynamics` fields beside `method` and `options`
+            dyn = {k: d[k] for k in ("accel_models", "force_models") if k in d}
+        return cls(dyn or {}, IntegratorMethod[m] if isinstance(m, str) else IntegratorMethod(m), integrator_options_from(d.get("options")))
+
+    @classmethod
+    def load_named(cls, src: Union[str, Path, dict]) -> Dict[str, "PropagatorConfig"]:
+        """The `propagators` map of a sequence file (data/02_config/full_seq.dhall; serde_dhall writes maps as lists of
+        `{ _1 = name, _2 = config }`), or a plain mapping name -> config."""
+        from .dhall import pairs_to_dict
+
+        d = _load(src)
+        props = pairs_to_dict(d.get("propagators", d) if isinstance(d, dict) else d)
+        return {str(name): cls.load(cfg) for name, cfg in props.items()}
 
     def build_dynamics(self, almanac: Optional[Almanac]) -> SpacecraftDynamics:
         """`Dynamics::build` (config.rs:104-134): two-body + [PointMasses] + [GravityField]; [SolarPressure], [Drag]."""
@@ -96,6 +115,8 @@ class PropagatorConfig:
             accel.append(PointMasses.new([int(b) for b in am["point_masses"]["celestial_objects"]]))
         if am.get("gravity_field"):
             g = am["gravity_field"]
+            if "_1" in g:   # serde tuple (GravityFieldConfig, Frame uid) as the reference's Dhall files hold it
+                g = dict(g["_1"], frame=g.get("_2") or {})
             fr = g.get("frame", {})
             frame = _BODY_FIXED.get(int(fr.get("ephemeris_id", EARTH)), IAU_EARTH_FRAME) if isinstance(fr, dict) else fr
             path = str(g["filepath"])
