@@ -280,8 +280,19 @@ class Propagator {
             if (rc != NYXB_RC_OK) throw std::runtime_error(std::string("nyxb_traj_resample: ") + nyxb_last_error());
             return r;
         }
+        // the Brent search of until_nth_event (event.rs:186-211) inside every trajectory's last recorded step, one launch
+        struct Located { std::vector<int64_t> epoch; std::vector<double> state; std::vector<int32_t> status; };   // [n], [6][n], [n]
+        Located locate(int32_t event_kind, double value, int64_t epoch_precision_ns = 1000000) const {
+            Located r; r.epoch.resize(n); r.state.resize(6 * n); r.status.resize(n);
+            int32_t rc = nyxb_event_locate(engine.get(), n, nullptr, event_kind, value, epoch_precision_ns, status.data(), r.epoch.data(),
+                                           r.state.data(), r.status.data());
+            if (rc != NYXB_RC_OK) throw std::runtime_error(std::string("nyxb_event_locate: ") + nyxb_last_error());
+            return r;
+        }
     };
-    TrajBatch propagate_batch_traj(const std::vector<Spacecraft>& v, int64_t end_epoch_ns, int64_t capacity, const Almanac* almanac = nullptr) const {
+    // `event` != nullptr: stop every run at the end of the step in which the event scalar crossed zero for the trigger-th time
+    TrajBatch propagate_batch_traj(const std::vector<Spacecraft>& v, int64_t end_epoch_ns, int64_t capacity, const Almanac* almanac = nullptr,
+                                   nyxb_event* event = nullptr) const {
         TrajBatch r;
         const size_t n = v.size();
         r.n = n; r.capacity = capacity;
@@ -291,9 +302,9 @@ class Propagator {
         r.engine = std::shared_ptr<nyxb_engine>(detail::make_engine(dynamics, v[0].frame, almanac, method, opts, mode, device).release(), nyxb_engine_destroy);
         detail::Soa soa(v);
         nyxb_traj_sink sink{capacity, r.t_epoch.data(), r.t_state.data(), r.t_count.data()};
-        int32_t rc = nyxb_propagate_batch_traj(r.engine.get(), n, soa.state.data(), soa.consts.data(), soa.epoch.data(), end_epoch_ns, nullptr,
-                                               r.state.data(), r.epoch.data(), r.details.data(), r.status.data(), &sink);
-        if (rc != NYXB_RC_OK) throw std::runtime_error(std::string("nyxb_propagate_batch_traj: ") + nyxb_last_error());
+        int32_t rc = nyxb_propagate_batch_event(r.engine.get(), n, soa.state.data(), soa.consts.data(), soa.epoch.data(), end_epoch_ns, nullptr,
+                                                r.state.data(), r.epoch.data(), r.details.data(), r.status.data(), &sink, event);
+        if (rc != NYXB_RC_OK) throw std::runtime_error(std::string("nyxb_propagate_batch_event: ") + nyxb_last_error());
         return r;
     }
     // nyx-py Propagator.many_until_epoch (py_md.rs:224-271): failed runs are dropped

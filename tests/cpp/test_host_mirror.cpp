@@ -94,6 +94,25 @@ int main() {
         auto fine = setup.with(init).for_duration(125 * NS_PER_S);   // 12 steps of 10 s + a final 5 s step
         CHECK(std::fabs(rs.at(0, 3, 0) - fine.x_km) < 1e-7 && std::fabs(rs.at(5, 3, 0) - fine.vz_km_s) < 1e-10);
     }
+    {   // until_nth_event for a batch (event.rs:88-211): stop at the second node crossing, then locate z = 0 inside the last step
+        auto setup = Propagator::default_(dynamics);
+        Spacecraft other = init; other.vz_km_s += 1e-3;
+        std::vector<int32_t> crossings(2, 0);
+        nyxb_event ev{NYXB_EVENT_Z, 2, 0.0, crossings.data()};
+        auto tb = setup.propagate_batch_traj({init, other}, days(1), 512, nullptr, &ev);
+        CHECK(tb.status[0] == 0 && tb.status[1] == 0 && crossings[0] == 2 && crossings[1] == 2 && tb.epoch[0] < days(1));
+        auto loc = tb.locate(NYXB_EVENT_Z, 0.0);
+        for (size_t i = 0; i < 2; ++i) {
+            const int64_t k = tb.t_count[i];
+            CHECK(loc.status[i] == NYXB_TRAJ_OK && loc.epoch[i] >= tb.epoch_at(k - 2, i) && loc.epoch[i] <= tb.epoch_at(k - 1, i));
+            CHECK(std::fabs(loc.state[2 * 2 + i]) < 5e-3);                                   // z at the event, km: within precision x |vz|
+            CHECK(tb.state_at(2, k - 2, i) * tb.state_at(2, k - 1, i) < 0.0);                // the last step brackets the crossing
+        }
+        std::vector<int32_t> none(2, 0);
+        nyxb_event far{NYXB_EVENT_RMAG, 1, 50000.0, none.data()};
+        auto miss = setup.propagate_batch_traj({init, other}, 600 * NS_PER_S, 64, nullptr, &far);
+        CHECK((miss.status[0] & 0xff) == NYXB_ERR_EVENT_NOT_FOUND && miss.locate(NYXB_EVENT_RMAG, 50000.0).status[0] == NYXB_TRAJ_NO_DATA);
+    }
     {   // device dispersions: shard-invariant, right spread
         Spacecraft nominal = init; nominal.frame = EARTH_J2000(); nominal.dry_mass_kg = 100.0;
         const double sd[9] = {1.0, 1.0, 1.0, 1e-3, 1e-3, 1e-3, 0, 0, 0};
