@@ -89,8 +89,8 @@ int main() {
         auto rs = tb.every({-1, 0, 120 * NS_PER_S, 125 * NS_PER_S, 300 * NS_PER_S, 300 * NS_PER_S + 1});
         CHECK(!rs.ok(0, 0) && !rs.ok(5, 1) && rs.ok(1, 0) && rs.ok(4, 1) && std::isnan(rs.at(0, 0, 0)));
         CHECK(rs.at(0, 2, 0) == tb.state_at(0, 12, 0) && rs.at(4, 2, 1) == tb.state_at(4, 12, 1) && rs.at(2, 4, 1) == tb.state[2 * 2 + 1]);
-        const double mid = 0.5 * (tb.state_at(0, 12, 0) + tb.state_at(0, 13, 0));   // the chord misses the arc by ~ a h^2 / 8 ~ 1e-4 km
-        CHECK(std::fabs(rs.at(0, 3, 0) - mid) < 1e-3 && rs.at(0, 3, 0) != mid);
+        const double mid = 0.5 * (tb.state_at(0, 12, 0) + tb.state_at(0, 13, 0));   // the chord misses the arc by ~ a h^2 / 8 <~ 0.1 km
+        CHECK(std::fabs(rs.at(0, 3, 0) - mid) < 0.2 && rs.at(0, 3, 0) != mid);
         auto fine = setup.with(init).for_duration(125 * NS_PER_S);   // 12 steps of 10 s + a final 5 s step
         CHECK(std::fabs(rs.at(0, 3, 0) - fine.x_km) < 1e-7 && std::fabs(rs.at(5, 3, 0) - fine.vz_km_s) < 1e-10);
     }
