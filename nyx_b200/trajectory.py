@@ -100,3 +100,66 @@ class Traj:
         for c in range(3):
             rv[c], rv[3 + c] = hermite_eval(ts, win[:, c], win[:, 3 + c], x)
         return self._sc(epoch_ns, rv)
+
+    # ---- iteration and export (traj.rs:148-193, 226-360; traj_it.rs:32-63)
+    def every_between(self, step_ns: int, start_ns: int, end_ns: int):
+        """`Traj::every_between`: states every `step` over TimeSeries::inclusive(max(start, first), min(end, last), step);
+        the iteration ends at the first epoch without interpolation data."""
+        step_ns = int(step_ns)
+        if step_ns <= 0:
+            raise ValueError("step must be positive")
+        if len(self) == 0:
+            return
+        t = max(int(start_ns), int(self.epochs_ns[0]))
+        end = min(int(end_ns), int(self.epochs_ns[-1]))
+        while t <= end:
+            try:
+                yield self.at(t)
+            except TrajError:
+                return
+            t += step_ns
+
+    def every(self, step_ns: int):
+        """`Traj::every` (traj.rs:148-150)."""
+        if len(self) == 0:
+            return iter(())
+        return self.every_between(step_ns, int(self.epochs_ns[0]), int(self.epochs_ns[-1]))
+
+    def filter_by_epoch(self, start_ns: int, end_ns: int) -> "Traj":
+        """`Traj::filter_by_epoch` with an inclusive range (traj.rs:165-193): only the recorded states inside it."""
+        keep = (self.epochs_ns >= int(start_ns)) & (self.epochs_ns <= int(end_ns))
+        return Traj(self.template, self.epochs_ns[keep].copy(), self.states[keep].copy(), self.name)
+
+    def to_parquet(self, path, fields=None, start_ns: Optional[int] = None, end_ns: Optional[int] = None,
+                   step_ns: Optional[int] = None, metadata: Optional[dict] = None):
+        """`Traj::to_parquet` (traj.rs:226-360): "Epoch (UTC)" + the requested fields (default `Spacecraft::export_params`) of all
+        recorded states, or of the states interpolated every `step` (default 1 min) when start/end/step is given; fields no
+        state provides are dropped.  (For whole ensembles use `Results.to_parquet`, which interpolates on the device.)"""
+        import pyarrow as pa
+        import pyarrow.parquet as pq
+
+        from .cosmic import epochs_to_utc_iso
+        from .param import EXPORT_PARAMS, StateError, evaluate
+
+        if start_ns is not None or end_ns is not None or step_ns is not None:
+            sts = list(self.every_between(60 * 10**9 if step_ns is None else step_ns,
+                                          int(self.epochs_ns[0]) if start_ns is None else start_ns,
+                                          int(self.epochs_ns[-1]) if end_ns is None else end_ns))
+            epochs = np.array([s.epoch() for s in sts], dtype=np.int64)
+            rv = np.array([s.orbit.to_cartesian_pos_vel() for s in sts]).reshape(len(sts), 6).T
+        else:
+            epochs, rv = self.epochs_ns, self.states.T
+        frame = self.template.orbit.frame
+        cols = [pa.array(epochs_to_utc_iso(epochs), type=pa.string())]
+        schema = [pa.field("Epoch (UTC)", pa.string(), nullable=False)]
+        for f in (EXPORT_PARAMS if fields is None else fields):
+            try:
+                vals = evaluate(f, rv, frame.mu_km3_s2(), self.template)
+            except StateError:
+                continue
+            cols.append(pa.array(vals, type=pa.float64()))
+            schema.append(pa.field(str(f), pa.float64(), nullable=False, metadata={"unit": f.unit, "Frame": frame.name}))
+        meta = {"Purpose": "Trajectory data"}
+        meta.update(metadata or {})
+        pq.write_table(pa.Table.from_arrays(cols, schema=pa.schema(schema, metadata=meta)), str(path))
+        return path

@@ -154,3 +154,38 @@ def test_resample_core_matches_traj_at(oracle, tmp_path):
         assert np.array_equal(np.isnan(got), np.isnan(want))
         ok = want_status == 0
         assert np.array_equal(got[:, ok], want[:, ok])   # same operations in the same order, no FMA: bit-identical
+
+
+def test_traj_iteration_filter_and_parquet(oracle, tmp_path):
+    """traj.rs:148-193, 226-360: `every`, `every_between` (clamped to the span), `filter_by_epoch`, `to_parquet`."""
+    import pyarrow.parquet as pq
+    from nyx_b200.param import EXPORT_PARAMS, StateParameter as P
+    frame = nb.EARTH_J2000
+    sc = leo_state(frame)
+    st, cs, ep = nb.pack_spacecraft([sc])
+    prop = nb.Propagator.default(_dyn())
+    end = 2 * 3600 * S
+    _, _, _, _, (t_ep, t_st, t_cnt) = _oracle_traj(oracle, prop, frame, st, cs, ep, end, 256)
+    k = int(t_cnt[0])
+    tr = Traj(sc, t_ep[:k, 0].copy(), np.ascontiguousarray(t_st[:, :k, 0].T)).finalize()
+    step = 7 * 60 * S
+    every = list(tr.every(step))
+    assert [s.epoch() for s in every] == list(range(0, end + 1, step))
+    assert np.array_equal(every[3].orbit.to_cartesian_pos_vel(), tr.at(3 * step).orbit.to_cartesian_pos_vel())
+    clamped = list(tr.every_between(step, -5 * S, end + 5 * S))
+    assert [s.epoch() for s in clamped] == [s.epoch() for s in every]
+    inner = list(tr.every_between(step, 1000 * S, 5000 * S))
+    assert inner[0].epoch() == 1000 * S and inner[-1].epoch() <= 5000 * S and len(inner) == (4000 * S) // step + 1
+    assert list(tr.every_between(step, end + 1, end + 2)) == []
+    with pytest.raises(ValueError):
+        list(tr.every(0))
+    sub = tr.filter_by_epoch(int(tr.epochs_ns[5]), int(tr.epochs_ns[20]))
+    assert len(sub) == 16 and sub.first().epoch() == tr.epochs_ns[5] and np.array_equal(sub.states, tr.states[5:21])
+    raw = pq.read_table(str(tr.to_parquet(tmp_path / "traj.parquet")))
+    assert raw.num_rows == k and raw.column_names == ["Epoch (UTC)"] + [str(p) for p in EXPORT_PARAMS]
+    assert np.array_equal(np.array(raw["VZ (km/s)"].to_pylist()), tr.states[:, 5])
+    assert raw.schema.metadata[b"Purpose"] == b"Trajectory data"
+    grid = pq.read_table(str(tr.to_parquet(tmp_path / "traj_grid.parquet", fields=[P.X, P.Thrust, P.Rmag], step_ns=step, metadata={"k": "v"})))
+    assert grid.column_names == ["Epoch (UTC)", "X (km)", "Rmag (km)"] and grid.num_rows == len(every)
+    assert grid["X (km)"].to_pylist() == [s.orbit.x_km for s in every] and grid.schema.metadata[b"k"] == b"v"
+    assert grid["Epoch (UTC)"][1].as_py() == nb.epochs_to_utc_iso([step])[0]
