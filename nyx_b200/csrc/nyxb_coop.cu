@@ -20,7 +20,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <functional>
 #include <numeric>
+#include <set>
 #include <string>
 
 #include "nyxb_coop.h"
@@ -28,6 +30,61 @@
 // ------------------------------------------------------------------------------------------------
 // host: column -> lane schedule (longest-processing-time greedy) and record table
 // ------------------------------------------------------------------------------------------------
+
+// NYXB_COOP_SCHED=aligned (experimental, off by default): keep the bin packing, but reorder each lane's columns and insert idle
+// gaps (null records) so that column STARTS of different lane positions fall on the same entries.  The kernel executes its
+// column-switch block whenever ANY lane of the warp starts a column, so what costs is the number of DISTINCT start entries, not
+// the number of columns.  Lanes with the fewest columns fix the boundary set first; every other lane searches
+// the orders of its columns (multiset permutations) and, before each column, either continues where the previous one ended or
+// waits for a boundary that already exists.
+static void align_boundaries(int L, const std::function<int(int)>& col_len, std::vector<std::vector<int>>& cols,
+                             std::vector<std::vector<int>>& starts, std::vector<int>& load) {
+    const int G = (int)cols.size();
+    std::set<int> B;
+    std::vector<int> lane_order(G);
+    std::iota(lane_order.begin(), lane_order.end(), 0);
+    std::stable_sort(lane_order.begin(), lane_order.end(), [&](int a, int b) { return cols[a].size() < cols[b].size(); });
+    for (int lane : lane_order) {
+        std::vector<int> ms = cols[lane];
+        const int k = (int)ms.size();
+        if (k == 0) continue;
+        if (k > 8) { for (int s0 : starts[lane]) if (s0) B.insert(s0); continue; }
+        std::vector<int> lens(k);
+        for (int i = 0; i < k; ++i) lens[i] = col_len(ms[i]);
+        std::sort(lens.begin(), lens.end());
+        int best_cost = 1 << 30, best_end = 1 << 30;
+        std::vector<int> best_lens, best_starts, cur(k);
+        std::function<void(int, int, int)> dfs = [&](int i, int pos, int cost) {
+            if (cost > best_cost) return;
+            if (i == k) {
+                if (cost < best_cost || (cost == best_cost && pos < best_end)) { best_cost = cost; best_end = pos; best_lens = lens; best_starts = cur; }
+                return;
+            }
+            int rem = 0;
+            for (int j = i; j < k; ++j) rem += lens[j];
+            if (pos + rem > L) return;
+            cur[i] = pos;   // contiguous (or entry 0 for the first column)
+            dfs(i + 1, pos + lens[i], cost + ((pos != 0 && !B.count(pos)) ? 1 : 0));
+            for (int b : B)   // wait for an existing boundary
+                if (b > pos && b + rem <= L) { cur[i] = b; dfs(i + 1, b + lens[i], cost); }
+        };
+        do { dfs(0, 0, 0); } while (std::next_permutation(lens.begin(), lens.end()));
+        // hand the columns out per length, ascending m among equals
+        std::vector<int> pool = ms;
+        std::sort(pool.begin(), pool.end());
+        std::vector<int> new_cols(k);
+        for (int i = 0; i < k; ++i) {
+            auto it = std::find_if(pool.begin(), pool.end(), [&](int m) { return col_len(m) == best_lens[i]; });
+            new_cols[i] = *it;
+            pool.erase(it);
+        }
+        cols[lane] = new_cols;
+        starts[lane] = best_starts;
+        load[lane] = best_starts[k - 1] + best_lens[k - 1];
+        for (int s0 : best_starts) if (s0) B.insert(s0);
+    }
+}
+
 void nyxb_coop_build_host(int N, int M, const double* c_nm, const double* s_nm, int G, CoopHost& out) {
     const double sqrt2 = std::sqrt(2.0);
     auto C = [&](int n, int m) { return (n <= N && m <= M && m <= n) ? c_nm[(size_t)n * (N + 1) + m] : 0.0; };
@@ -57,6 +114,7 @@ void nyxb_coop_build_host(int N, int M, const double* c_nm, const double* s_nm, 
     std::vector<std::vector<int>> starts(G);
     const char* sched = getenv("NYXB_COOP_SCHED");
     const bool rounds = sched && std::string(sched) == "rounds";
+    const bool aligned = sched && std::string(sched) == "aligned";
     if (rounds) {
         int base = 0;
         for (size_t i = 0; i < order.size(); i += G) {
@@ -86,6 +144,7 @@ void nyxb_coop_build_host(int N, int M, const double* c_nm, const double* s_nm, 
             }
             if (ok) break;
         }
+        if (aligned) align_boundaries(cap, col_len, cols, starts, load);
     }
     out.G = G;
     out.L = *std::max_element(load.begin(), load.end());

@@ -79,7 +79,14 @@ def _walk(gf, lanes, tables, rb):
 
 @pytest.mark.parametrize("fixture,degree,order,lanes", [("jgm3_70x70", 21, 21, 8), ("jgm3_70x70", 21, 21, 16), ("jgm3_70x70", 8, 5, 8),
                                                           ("jgm3_70x70", 70, 70, 32), ("jgm3_70x70", 30, 30, 32), ("luna_jggrx_80x80", 48, 48, 16)])
-def test_cooperative_table_reproduces_oracle_gravity(oracle, fixture, degree, order, lanes):
+@pytest.mark.parametrize("sched", ["default", "aligned", "rounds"])
+def test_cooperative_table_reproduces_oracle_gravity(oracle, monkeypatch, fixture, degree, order, lanes, sched):
+    """`sched`: the default bin packing, and the two experimental column schedules selected by NYXB_COOP_SCHED (same kernel,
+    different tables: `aligned` reorders columns / inserts idle gaps so that lane positions start columns on common entries)."""
+    if sched != "default":
+        monkeypatch.setenv("NYXB_COOP_SCHED", sched)
+    else:
+        monkeypatch.delenv("NYXB_COOP_SCHED", raising=False)
     moon = fixture.startswith("luna")
     body_frame = nb.IAU_MOON_FRAME if moon else nb.IAU_EARTH_FRAME
     # identity rotation: the harmonic sum is exercised directly in the integration frame
@@ -95,6 +102,16 @@ def test_cooperative_table_reproduces_oracle_gravity(oracle, fixture, degree, or
     real = col_start <= L
     assert L % 2 == 0 and (col_start[real] % 2 == 0).all()
     assert sorted(col_m[real].tolist()) == list(range(1, min(gf.order + 1, gf.degree + 1) + 1))
+    for lane in range(lanes):   # columns of a lane do not overlap and end inside the walk
+        ends = 0
+        for k in range(kmax):
+            if col_start[lane, k] > L:
+                continue
+            m = int(col_m[lane, k])
+            ln = max(gf.degree + 1 - m, 1)
+            assert col_start[lane, k] >= ends
+            ends = int(col_start[lane, k]) + ln + (ln & 1)
+        assert ends <= L
     rng = np.random.default_rng(5)
     R = gf.r_eq_km
     for _ in range(4):
