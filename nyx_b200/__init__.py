@@ -6,7 +6,7 @@ There is NO CPU fallback: every propagate call goes through ``libnyxb.so`` on a 
 """
 from . import abi
 from .abi import MODE_FAST, MODE_STRICT, NyxbLibraryMissing
-from .cosmic import DragData, Mass, Orbit, Spacecraft, SRPData, Unit, duration_to_seconds, epochs_to_utc_iso, pack_spacecraft
+from .cosmic import DragData, Mass, Orbit, Spacecraft, SRPData, Unit, duration_to_seconds, epochs_to_utc_iso, pack_spacecraft, utc_iso_to_epochs
 from .dynamics import (AtmDensity, Drag, DynamicsError, GravityField, OrbitalDynamics, PointMasses, ShadowModel,
                        SolarPressure, SpacecraftDynamics)
 from .frames import (EARTH, EARTH_J2000, GMAT_EARTH_GM, GMAT_MOON_GM, GMAT_SUN_GM, IAU_EARTH_FRAME, IAU_MOON_FRAME,

@@ -72,6 +72,18 @@ def epochs_to_utc_iso(epoch_ns) -> np.ndarray:
     return np.datetime_as_string(j2000 + utc.astype("timedelta64[ns]"), unit="ns")
 
 
+def utc_iso_to_epochs(iso) -> np.ndarray:
+    """Inverse of `epochs_to_utc_iso` (`Epoch::from_gregorian_str` on the UTC ISO strings the parquet files hold): integer ns
+    past J2000 TDB (= TT here)."""
+    txt = [str(x).replace(" UTC", "").strip() for x in np.atleast_1d(iso)]
+    utc = (np.array(txt, dtype="datetime64[ns]") - np.datetime64("2000-01-01T12:00:00", "ns")).astype(np.int64)
+    j2000 = np.datetime64("2000-01-01T12:00:00", "ns")
+    starts_utc = np.array([(np.datetime64(d + "T00:00:00", "ns") - j2000).astype(np.int64) for d, _ in _LEAP_SECONDS], dtype=np.int64)
+    dat = np.array([d for _, d in _LEAP_SECONDS], dtype=np.int64)
+    k = np.clip(np.searchsorted(starts_utc, utc, side="right") - 1, 0, None)
+    return utc + dat[k] * NS_PER_S + _TT_MINUS_TAI_NS
+
+
 # --------------------------------------------------------------------------- state
 @dataclass(frozen=True)
 class Orbit:

@@ -174,6 +174,74 @@ class TrackingDataArc:
     def n(self) -> int:
         return self.obs.shape[2]
 
+    # ---- parquet I/O in the reference's layout (od/msr/trackingdata/io_parquet.rs:43-354): one arc per file
+    _COLUMNS = ("Range (km)", "Doppler (km/s)")   # MeasurementType::to_field names (od/msr/types.rs)
+
+    def to_parquet(self, path, index: int = 0, metadata: Optional[dict] = None):
+        """`TrackingDataArc::to_parquet` for the observation set `index`: "Epoch (UTC)", "Tracking device" and one nullable
+        Float64 column per measurement type present; measurements absent from this arc are not written."""
+        import pyarrow as pa
+        import pyarrow.parquet as pq
+
+        from .cosmic import epochs_to_utc_iso
+
+        o = self.obs[:, :, index]
+        present = ~np.isnan(o).all(axis=1)
+        if not present.any():
+            raise ODError("EmptyDataset: tracking data arc to parquet")
+        cols = [pa.array(epochs_to_utc_iso(self.epoch_ns[present]), type=pa.string()),
+                pa.array([t for t, p in zip(self.tracker, present) if p], type=pa.string())]
+        fields = [pa.field("Epoch (UTC)", pa.string(), nullable=False), pa.field("Tracking device", pa.string(), nullable=False)]
+        for c, name in enumerate(self._COLUMNS):
+            v = o[present, c]
+            if np.isnan(v).all():
+                continue   # unique_types(): a type no measurement carries has no column
+            cols.append(pa.array(v, type=pa.float64(), mask=np.isnan(v)))
+            fields.append(pa.field(name, pa.float64(), nullable=True, metadata={"unit": name[name.index("(") + 1:-1]}))
+        meta = {"Purpose": "Tracking Arc Data"}
+        meta.update(metadata or {})
+        pq.write_table(pa.Table.from_arrays(cols, schema=pa.schema(fields, metadata=meta)), str(path))
+        return path
+
+    @classmethod
+    def from_parquet(cls, path) -> "TrackingDataArc":
+        """`TrackingDataArc::from_parquet` (io_parquet.rs:43-213): needs "Epoch (UTC)", "Tracking device" and at least one of
+        the measurement columns this path knows (range, Doppler); rows are sorted by epoch."""
+        import pyarrow.parquet as pq
+
+        from .cosmic import utc_iso_to_epochs
+
+        tab = pq.read_table(str(path))
+        names = set(tab.column_names)
+        for need in ("Epoch (UTC)", "Tracking device"):
+            if need not in names:
+                raise ODError(f"MissingData: {need}")
+        if not names & set(cls._COLUMNS):
+            raise ODError("MissingData: `Range (km)` or `Doppler (km/s)`")
+        ep = utc_iso_to_epochs(tab["Epoch (UTC)"].to_pylist())
+        obs = np.full((len(ep), 2), np.nan)
+        for c, name in enumerate(cls._COLUMNS):
+            if name in names:
+                obs[:, c] = [np.nan if v is None else v for v in tab[name].to_pylist()]
+        order = np.argsort(ep, kind="stable")
+        trk = tab["Tracking device"].to_pylist()
+        return cls(ep[order], [trk[i] for i in order], obs[order][:, :, None])
+
+    @classmethod
+    def stack(cls, arcs: Sequence["TrackingDataArc"]) -> "TrackingDataArc":
+        """n single-observation-set arcs -> one arc with n observation sets over the union of their schedules (what
+        `process_arcs` takes); a (epoch, tracker) pair missing from an arc is NaN there."""
+        keys = sorted({(int(e), t) for a in arcs for e, t in zip(a.epoch_ns, a.tracker)})
+        pos = {k: i for i, k in enumerate(keys)}
+        n = sum(a.n for a in arcs)
+        obs = np.full((len(keys), 2, n), np.nan)
+        col = 0
+        for a in arcs:
+            rows = [pos[(int(e), t)] for e, t in zip(a.epoch_ns, a.tracker)]
+            obs[rows, :, col:col + a.n] = a.obs
+            col += a.n
+        return cls(np.array([k[0] for k in keys], dtype=np.int64), [k[1] for k in keys], obs)
+
 
 @dataclass(frozen=True)
 class SigmaRejection:

@@ -155,3 +155,53 @@ def test_bench_reference_arm_for_c5_runs_on_cpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["cores"] >= 1
+
+
+def test_utc_iso_round_trip_across_leap_seconds():
+    from nyx_b200.cosmic import epochs_to_utc_iso, utc_iso_to_epochs
+    S = 10**9
+    ep = np.array([0, 1, -86400 * 366 * S, 5 * 365 * 86400 * S + 123_456_789, 17 * 365 * 86400 * S, 25 * 365 * 86400 * S + 5], dtype=np.int64)
+    assert np.array_equal(utc_iso_to_epochs(epochs_to_utc_iso(ep)), ep)
+    assert utc_iso_to_epochs(["2000-01-01T11:58:55.816"])[0] == 0 and utc_iso_to_epochs("2000-01-01T11:58:55.816 UTC")[0] == 0
+    # one UTC second apart on either side of the 2006-01-01 leap second = two TAI seconds
+    a, b = utc_iso_to_epochs(["2005-12-31T23:59:59", "2006-01-01T00:00:00"])
+    assert b - a == 2 * S
+
+
+def test_tracking_arc_parquet_round_trip(tmp_path):
+    """od/msr/trackingdata/io_parquet.rs layout: one arc per file; absent measurements are not written, a type absent from a
+    measurement is null; `stack` rebuilds the batched arc `process_arcs` takes."""
+    import pyarrow.parquet as pq
+    S = 10**9
+    epochs = np.array([60, 120, 180, 240, 300], dtype=np.int64) * S + 7
+    tracker = ["Madrid", "Madrid", "Goldstone", "Goldstone", "Canberra"]
+    obs = np.full((5, 2, 3), np.nan)
+    rng = np.random.default_rng(0)
+    obs[:, 0, :] = rng.uniform(4e5, 5e5, (5, 3))
+    obs[:, 1, :] = rng.uniform(-1, 1, (5, 3))
+    obs[2, :, 1] = np.nan          # arc 1 misses measurement 2 altogether
+    obs[3, 1, 1] = np.nan          # ... and has no Doppler in measurement 3
+    obs[:, 1, 2] = np.nan          # arc 2 is range-only
+    arc = nb.TrackingDataArc(epochs, tracker, obs)
+    paths = [arc.to_parquet(tmp_path / f"arc{i}.parquet", index=i, metadata={"who": "test"}) for i in range(3)]
+    t1 = pq.read_table(str(paths[1]))
+    assert t1.column_names == ["Epoch (UTC)", "Tracking device", "Range (km)", "Doppler (km/s)"] and t1.num_rows == 4
+    assert t1["Doppler (km/s)"].null_count == 1 and t1.schema.metadata[b"Purpose"] == b"Tracking Arc Data" and t1.schema.metadata[b"who"] == b"test"
+    assert t1["Epoch (UTC)"][0].as_py() == nb.epochs_to_utc_iso(epochs[:1])[0]
+    assert pq.read_table(str(paths[2])).column_names == ["Epoch (UTC)", "Tracking device", "Range (km)"]
+    back = [nb.TrackingDataArc.from_parquet(p) for p in paths]
+    assert back[0].n == 1 and np.array_equal(back[0].epoch_ns, epochs) and back[0].tracker == tracker
+    assert np.array_equal(back[0].obs[:, :, 0], obs[:, :, 0])
+    assert len(back[1]) == 4 and np.array_equal(back[1].epoch_ns, epochs[[0, 1, 3, 4]])
+    again = nb.TrackingDataArc.stack(back)
+    assert again.n == 3 and np.array_equal(again.epoch_ns, epochs) and again.tracker == tracker
+    assert np.array_equal(again.obs, obs, equal_nan=True)
+    with pytest.raises(nb.ODError, match="EmptyDataset"):
+        nb.TrackingDataArc(epochs, tracker, np.full((5, 2, 1), np.nan)).to_parquet(tmp_path / "none.parquet")
+    import pyarrow as pa
+    pq.write_table(pa.table({"Epoch (UTC)": ["2020-01-01T00:00:00"], "Range (km)": [1.0]}), str(tmp_path / "bad.parquet"))
+    with pytest.raises(nb.ODError, match="Tracking device"):
+        nb.TrackingDataArc.from_parquet(tmp_path / "bad.parquet")
+    pq.write_table(pa.table({"Epoch (UTC)": ["2020-01-01T00:00:00"], "Tracking device": ["X"], "Azimuth (deg)": [1.0]}), str(tmp_path / "bad2.parquet"))
+    with pytest.raises(nb.ODError, match="Range"):
+        nb.TrackingDataArc.from_parquet(tmp_path / "bad2.parquet")
