@@ -348,6 +348,8 @@ class ODSolution:
     details: np.ndarray
     status: np.ndarray
     templates: Sequence[Spacecraft] = ()
+    arc: Optional["TrackingDataArc"] = None
+    devices: Optional[Dict[str, GroundStation]] = None
 
     def accepted(self) -> np.ndarray:
         return ((self.msr_flags & abi.MSRF_PROCESSED) != 0) & ((self.msr_flags & abi.MSRF_REJECTED) == 0)
@@ -358,6 +360,69 @@ class ODSolution:
     def final_estimate(self, i: int) -> KfEstimate:
         sc = self.templates[i].with_vector(int(self.final_epoch_ns[i]), self.final_state_soa[:, i])
         return KfEstimate(sc, self.covar[i].copy(), self.state_deviation[:, i].copy())
+
+    def to_parquet(self, path, index: int = 0, fields=None, metadata: Optional[dict] = None):
+        """`ODSolution::to_parquet` (od/process/solution/export.rs:60-688) for filter `index`, one row per processed measurement
+        epoch, with the columns this path records: "Epoch (UTC)", the state parameters of the estimate (default
+        `Spacecraft::export_params`), "Sigma <item> (<frame>) (<unit>)" from the covariance diagonal, prefit / postfit residuals
+        per measurement type, "Residual ratio", "Residual Rejected", "Tracker".  The full covariance, RIC sigmas, gains and
+        filter-smoother ratios of the reference's file need the off-diagonal terms per epoch, which the kernel does not write
+        back.  Needs `process_arcs(.., record_estimates=True)`."""
+        import pyarrow as pa
+        import pyarrow.parquet as pq
+
+        from .cosmic import epochs_to_utc_iso
+        from .param import EXPORT_PARAMS, StateError, evaluate
+
+        if self.est_state is None or self.est_covar_diag is None or self.arc is None:
+            raise ODError("no per-measurement estimates recorded: run process_arcs(.., record_estimates=True)")
+        rows = np.nonzero((self.msr_flags[:, index] & abi.MSRF_PROCESSED) != 0)[0]
+        if len(rows) == 0:
+            raise ODError("EmptyDataset: no measurement was processed")
+        tmpl = self.templates[index]
+        frame = tmpl.orbit.frame
+        est = self.est_state[rows, :, index].T          # [9][k]
+        cols = [pa.array(epochs_to_utc_iso(self.arc.epoch_ns[rows]), type=pa.string())]
+        schema = [pa.field("Epoch (UTC)", pa.string(), nullable=False)]
+        for f in (EXPORT_PARAMS if fields is None else fields):
+            try:
+                vals = evaluate(f, est[:6], frame.mu_km3_s2(), tmpl, cr=est[6], cd=est[7], prop_mass_kg=est[8])
+            except StateError:
+                continue
+            cols.append(pa.array(vals, type=pa.float64()))
+            schema.append(pa.field(str(f), pa.float64(), nullable=False, metadata={"unit": f.unit, "Frame": frame.name}))
+        items = ("X", "Y", "Z", "Vx", "Vy", "Vz", "Cr", "Cd", "Mass")
+        units = ("km", "km", "km", "km/s", "km/s", "km/s", "unitless", "unitless", "kg")
+        sig = np.sqrt(np.maximum(self.est_covar_diag[rows, :, index], 0.0))
+        for q, (it, un) in enumerate(zip(items, units)):
+            cols.append(pa.array(sig[:, q], type=pa.float64()))
+            schema.append(pa.field(f"Sigma {it} ({frame.name}) ({un})", pa.float64(), nullable=False))
+        # residual slots follow the order of the tracker's measurement types (include/nyxb.h: nyxb_od_outputs)
+        slot_type = np.full((len(rows), 2), -1)
+        for a, r in enumerate(rows):
+            dev = (self.devices or {}).get(self.arc.tracker[r])
+            types = list(dev.measurement_types) if dev is not None else [MeasurementType.Range, MeasurementType.Doppler]
+            slot_type[a, :len(types)] = [int(t) for t in types]
+        for label, arr in (("Prefit residual", self.prefit), ("Postfit residual", self.postfit)):
+            for mt, un in ((MeasurementType.Range, "km"), (MeasurementType.Doppler, "km/s")):
+                v = np.full(len(rows), np.nan)
+                for q in range(2):
+                    hit = slot_type[:, q] == int(mt)
+                    v[hit] = arr[rows[hit], q, index]
+                cols.append(pa.array(v, type=pa.float64(), mask=np.isnan(v)))
+                schema.append(pa.field(f"{label}: {mt.name} ({un})", pa.float64(), nullable=True))
+        ratio = self.resid_ratio[rows, 0, index]
+        ratio = np.where(np.isnan(ratio), self.resid_ratio[rows, 1, index], ratio)
+        cols.append(pa.array(ratio, type=pa.float64(), mask=np.isnan(ratio)))
+        schema.append(pa.field("Residual ratio", pa.float64(), nullable=True))
+        cols.append(pa.array((self.msr_flags[rows, index] & abi.MSRF_REJECTED) != 0, type=pa.bool_()))
+        schema.append(pa.field("Residual Rejected", pa.bool_(), nullable=True))
+        cols.append(pa.array([self.arc.tracker[r] for r in rows], type=pa.string()))
+        schema.append(pa.field("Tracker", pa.string(), nullable=True))
+        meta = {"Purpose": "Orbit determination results"}
+        meta.update(metadata or {})
+        pq.write_table(pa.Table.from_arrays(cols, schema=pa.schema(schema, metadata=meta)), str(path))
+        return path
 
 
 class KalmanODProcess:
@@ -429,6 +494,8 @@ class KalmanODProcess:
         res = eng.od_ekf_batch(self.config_c(), len(names), st_c, arc.epoch_ns, tracker, arc.obs, st, cs, ep, cov0,
                                record_estimates=record_estimates)
         res.templates = [e.nominal_state for e in initial_estimates]
+        res.arc = arc
+        res.devices = self.devices
         return res
 
     def process_arc(self, initial_estimate: KfEstimate, arc: TrackingDataArc) -> ODSolution:

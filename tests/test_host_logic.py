@@ -205,3 +205,46 @@ def test_tracking_arc_parquet_round_trip(tmp_path):
     pq.write_table(pa.table({"Epoch (UTC)": ["2020-01-01T00:00:00"], "Tracking device": ["X"], "Azimuth (deg)": [1.0]}), str(tmp_path / "bad2.parquet"))
     with pytest.raises(nb.ODError, match="Range"):
         nb.TrackingDataArc.from_parquet(tmp_path / "bad2.parquet")
+
+
+def test_od_solution_parquet_export(tmp_path):
+    """od/process/solution/export.rs columns this path records, from a hand-built solution (no device needed)."""
+    import pyarrow.parquet as pq
+    from nyx_b200.od import ODSolution
+    S = 10**9
+    m, n = 4, 2
+    frame = nb.EARTH_J2000
+    sc = nb.Spacecraft(orbit=nb.Orbit.keplerian(7000.0, 0.01, 30.0, 10.0, 20.0, 40.0, 0, frame), mass=nb.Mass(100.0, 5.0, 0.0))
+    rn, dn = nb.StochasticNoise(1e-3), nb.StochasticNoise(1e-6)
+    dop_first = nb.GroundStation("DopFirst", 0.0, 0.0, 0.0, measurement_types=[nb.MeasurementType.Doppler, nb.MeasurementType.Range],
+                                 stochastic_noises={nb.MeasurementType.Range: rn, nb.MeasurementType.Doppler: dn})
+    devices = {"Madrid": nb.GroundStation.dss65_madrid(0.0, rn, dn), "DopFirst": dop_first}
+    arc = nb.TrackingDataArc(np.arange(1, m + 1, dtype=np.int64) * 60 * S, ["Madrid", "Madrid", "DopFirst", "Madrid"], np.ones((m, 2, n)))
+    est = np.zeros((m, 9, n))
+    est[:, :, :] = sc.to_vector()[None, :, None]
+    est[:, 0, 1] += np.arange(m)
+    cov = np.tile(np.array([4.0, 4.0, 4.0, 1e-6, 1e-6, 1e-6, 0.25, 0.0, 0.0])[None, :, None], (m, 1, n))
+    prefit = np.arange(m * 2 * n, dtype=float).reshape(m, 2, n)
+    postfit = -prefit
+    ratio = np.full((m, 2, n), np.nan)
+    ratio[:, 0, :] = 1.5
+    flags = np.full((m, n), 1, dtype=np.int32)
+    flags[1, 1] = 1 | 2        # processed and rejected
+    flags[3, 1] = 4            # not visible: no row
+    sol = ODSolution(np.zeros((9, n)), np.zeros(n, dtype=np.int64), np.zeros((n, 9, 9)), np.zeros((9, n)), ratio, prefit, postfit, flags,
+                     est, cov, None, np.zeros(n, dtype=np.int32), templates=[sc, sc], arc=arc, devices=devices)
+    tab = pq.read_table(str(sol.to_parquet(tmp_path / "od.parquet", index=1, metadata={"run": "7"})))
+    assert tab.num_rows == 3 and tab.column_names[0] == "Epoch (UTC)" and "SemiMajorAxis (km)" in tab.column_names
+    assert tab["X (km)"].to_pylist() == (sc.orbit.x_km + np.arange(3)).tolist()
+    sig_cols = [c for c in tab.column_names if c.startswith("Sigma ")]
+    assert len(sig_cols) == 9 and tab[sig_cols[0]].to_pylist() == [2.0] * 3 and tab[sig_cols[6]].to_pylist() == [0.5] * 3
+    # slot order follows the tracker's type list: row 2 (DopFirst) has Doppler in slot 0
+    assert tab["Prefit residual: Range (km)"].to_pylist() == [prefit[0, 0, 1], prefit[1, 0, 1], prefit[2, 1, 1]]
+    assert tab["Prefit residual: Doppler (km/s)"].to_pylist() == [prefit[0, 1, 1], prefit[1, 1, 1], prefit[2, 0, 1]]
+    assert tab["Postfit residual: Range (km)"].to_pylist()[2] == postfit[2, 1, 1]
+    assert tab["Residual ratio"].to_pylist() == [1.5] * 3 and tab["Residual Rejected"].to_pylist() == [False, True, False]
+    assert tab["Tracker"].to_pylist() == ["Madrid", "Madrid", "DopFirst"] and tab.schema.metadata[b"run"] == b"7"
+    bare = ODSolution(np.zeros((9, n)), np.zeros(n, dtype=np.int64), np.zeros((n, 9, 9)), np.zeros((9, n)), ratio, prefit, postfit, flags,
+                      None, None, None, np.zeros(n, dtype=np.int32), templates=[sc, sc], arc=arc)
+    with pytest.raises(nb.ODError, match="record_estimates"):
+        bare.to_parquet(tmp_path / "x.parquet")
