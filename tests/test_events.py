@@ -81,6 +81,46 @@ def test_locate_event_on_oracle_trajectory(oracle):
         assert abs(ev.eval(found)) < tol
 
 
+@pytest.mark.parametrize("which", ["apo", "peri"])
+def test_reference_stop_cond_third_apsis(oracle, which):
+    """The reference's own `stop_cond_3rd_apo` / `stop_cond_3rd_peri` (tests/propagation/stopcond.rs:35-153): two-body, default
+    propagator, search over five periods; the third apoapsis (periapsis) lies between two and three periods after the start
+    and at true anomaly 180 deg within 1e-6 (0 deg within 1e-1).  Their `Event::apoapsis()` / `periapsis()` look at one apsis;
+    the closed scalar set here has r.v, which changes sign at both, so the third apoapsis is the 5th crossing (the start moves
+    outward: apo, peri, apo, peri, apo) and the third periapsis the 6th.  Consecutive apsides of the same kind are one period
+    apart within 0.5 s (0.3 s), as the reference asserts on its event report."""
+    from nyx_b200.param import StateParameter as P, evaluate
+    frame = nb.EARTH_J2000
+    orbit = nb.Orbit.cartesian(-2436.45, -2436.45, 6891.037, 5.088611, -5.088611, 0.01, 0, frame)
+    sc = nb.Spacecraft.from_orbit(orbit)
+    mu = frame.mu_km3_s2()
+    rv0 = orbit.to_cartesian_pos_vel().reshape(6, 1)
+    period_s = float(evaluate(P.Period, rv0, mu)[0])
+    period = int(period_s * 1e9)
+    st, cs, ep = nb.pack_spacecraft([sc])
+    prop = nb.Propagator.default(nb.SpacecraftDynamics.new(nb.OrbitalDynamics.two_body()))
+    ev = Event.apsis(epoch_precision_ns=1000)
+    found = {}
+    for trigger in (1, 2, 3, 4, 5, 6):
+        out, out_ep, det, status, (t_ep, t_st, t_cnt), crossings = _oracle_event(oracle, prop, frame, st, cs, ep, 5 * period, 2048, ev, trigger)
+        assert status[0] == 0 and crossings[0] == trigger
+        k = int(t_cnt[0])
+        found[trigger] = locate_event(Traj(sc, t_ep[:k, 0].copy(), np.ascontiguousarray(t_st[:, :k, 0].T)).finalize(), ev)
+    third = found[5] if which == "apo" else found[6]
+    assert 2 * period + 1 <= third.epoch() <= 3 * period + 1
+    ta = float(evaluate(P.TrueAnomaly, third.orbit.to_cartesian_pos_vel().reshape(6, 1), mu)[0])
+    if which == "apo":
+        assert abs(180.0 - ta) < 1e-6
+        same_kind = [found[1], found[3], found[5]]
+        tol = 0.5
+    else:
+        assert ta < 1e-1 or 360.0 - ta < 1e-1
+        same_kind = [found[2], found[4], found[6]]
+        tol = 0.3
+    for a, b in zip(same_kind, same_kind[1:]):
+        assert abs((b.epoch() - a.epoch()) * 1e-9 - period_s) < tol
+
+
 def _host_locate(sc, t_ep, t_st, t_cnt, ev, run_status=None):
     """locate_event per run -> (epoch[n], state[6][n], status[n]) with the device entry point's status convention"""
     n = t_ep.shape[1]
