@@ -279,3 +279,29 @@ def test_od_argument_validation():
     odp3 = nb.SpacecraftKalmanOD(prop, nb.KalmanVariant.ReferenceUpdate, None, {"Madrid": gs2}, None)
     with pytest.raises(nb.ODError, match="instantaneous"):
         odp3.process_arcs([est], two)
+
+
+@pytest.mark.parametrize("mode", [nb.MODE_STRICT, nb.MODE_FAST])
+def test_reference_two_body_gradient_through_the_stm(mode):
+    """The reference's `two_body_dual` golden gradient (tests/mission_design/orbitaldyn.rs:671-738, asserted there to 1e-16)
+    seen through the device: one RK4 step of 1 ms gives Phi = I + h (b1 A1 + .. + b4 A4), so (Phi - I) / h is the A-matrix of
+    `dual_eom` up to O(h) — 1.0e-14 on the CPU oracle with the same step (tests/test_oracle_stm.py pins the oracle's A itself)."""
+    frame = nb.EARTH_J2000.with_mu_km3_s2(398600.435436096)
+    dyn = nb.SpacecraftDynamics.new(nb.OrbitalDynamics.two_body())
+    y = np.array([-9_042.862_233_600_335, 18_536.333_069_123_244, 6_999.957_069_486_411_5,
+                  -3.288_789_003_770_57, -2.226_285_193_102_822, 1.646_738_380_722_676_5, 1.8, 2.2, 0.0])
+    expected = np.zeros((9, 9))
+    expected[0, 3] = expected[1, 4] = expected[2, 5] = 1.0
+    expected[3, 0] = -0.000_000_018_628_398_391_083_86
+    expected[4, 0] = expected[3, 1] = -0.000_000_040_897_747_124_379_53
+    expected[5, 0] = expected[3, 2] = -0.000_000_015_444_396_313_003_294
+    expected[4, 1] = 0.000_000_045_253_271_058_430_05
+    expected[5, 1] = expected[4, 2] = 0.000_000_031_658_391_636_846_51
+    expected[5, 2] = -0.000_000_026_624_872_667_346_21
+    h_ns = 10**6
+    prop = nb.Propagator.new(dyn, nb.IntegratorMethod.RungeKutta4, nb.IntegratorOptions.with_fixed_step(h_ns), mode=mode)
+    out, ep, stm, det, status = prop.engine(frame, None).propagate_batch_stm(y.reshape(9, 1), np.array([[100.0], [0.0], [0.0], [0.0]]),
+                                                                             np.zeros(1, dtype=np.int64), h_ns)
+    assert status[0] == 0 and det["n_steps"][0] == 1
+    a = (stm[:, 0].reshape(9, 9).T - np.eye(9)) / (h_ns * 1e-9)
+    assert np.abs(a - expected).max() < 5e-14

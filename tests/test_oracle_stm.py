@@ -180,3 +180,40 @@ def test_stm_rejects_drag_and_non_cartesian_controls(oracle):
     o2 = nb.IntegratorOptions.with_adaptive_step_s(0.1, 30.0, 1e-12, nb.ErrorControl.RSSState)
     with pytest.raises(RuntimeError):
         oracle.propagate_batch_stm(dyn2.pack(frame, None).c, o2.to_c(nb.IntegratorMethod.RungeKutta89), st, CS.reshape(4, 1), np.zeros(1, dtype=np.int64), 60 * S)
+
+
+def test_reference_two_body_dual_golden(oracle):
+    """The reference's own `two_body_dual` (tests/mission_design/orbitaldyn.rs:671-775): f(x) and the 9x9 gradient of the
+    two-body `dual_eom` at a GTO-like state against the values the reference asserts to a norm of 1e-16 (mu = the almanac's
+    Earth GM, 398600.435436096 — also `examples/04_lro_od/README.md:122`), then its STM consistency check: RK89 fixed 10 s
+    over 2 min, Phi(k,0) Phi(k-1,0)^-1 maps the state at k-1 onto the state at k to better than 0.1 km / 0.1 km/s."""
+    frame = nb.EARTH_J2000.with_mu_km3_s2(398600.435436096)
+    dyn = nb.SpacecraftDynamics.new(nb.OrbitalDynamics.two_body())
+    packed = dyn.pack(frame, None)
+    y = np.array([-9_042.862_233_600_335, 18_536.333_069_123_244, 6_999.957_069_486_411_5,
+                  -3.288_789_003_770_57, -2.226_285_193_102_822, 1.646_738_380_722_676_5, 1.8, 2.2, 0.0])
+    cs = np.array([100.0, 0.0, 0.0, 0.0])
+    dx, grad = oracle.dual_eom(packed.c, 0, y, cs)
+    expected_fx = np.array([-3.288_789_003_770_57, -2.226_285_193_102_822, 1.646_738_380_722_676_5,
+                            0.000_348_875_166_711_715_13, -0.000_715_134_890_110_951_6, -0.000_270_059_537_180_366_4])
+    assert np.linalg.norm(dx[:6] - expected_fx) < 1e-16
+    expected = np.zeros((9, 9))
+    expected[0, 3] = expected[1, 4] = expected[2, 5] = 1.0
+    expected[3, 0] = -0.000_000_018_628_398_391_083_86
+    expected[4, 0] = expected[3, 1] = -0.000_000_040_897_747_124_379_53
+    expected[5, 0] = expected[3, 2] = -0.000_000_015_444_396_313_003_294
+    expected[4, 1] = 0.000_000_045_253_271_058_430_05
+    expected[5, 1] = expected[4, 2] = 0.000_000_031_658_391_636_846_51
+    expected[5, 2] = -0.000_000_026_624_872_667_346_21
+    assert np.linalg.norm(grad - expected) < 1e-16
+    # STM consistency over the last step (orbitaldyn.rs:745-774)
+    prop = nb.Propagator.rk89(dyn, nb.IntegratorOptions.with_fixed_step(10 * S))
+    st, css, ep = y.reshape(9, 1), cs.reshape(4, 1), np.zeros(1, dtype=np.int64)
+    opts = prop.opts.to_c(prop.method)
+    fin, _, stm_k, _, s1 = oracle.propagate_batch_stm(packed.c, opts, st, css, ep, 120 * S)
+    prev, _, stm_km1, _, s2 = oracle.propagate_batch_stm(packed.c, opts, st, css, ep, 110 * S)
+    assert s1[0] == 0 and s2[0] == 0
+    phi_k = stm_k[:, 0].reshape(9, 9).T      # [(c*9 + r)] -> (r, c)
+    phi_km1 = stm_km1[:, 0].reshape(9, 9).T
+    err = phi_k @ np.linalg.inv(phi_km1) @ prev[:, 0] - fin[:, 0]
+    assert np.linalg.norm(err[:3]) < 1e-1 and np.linalg.norm(err[3:6]) < 1e-1
