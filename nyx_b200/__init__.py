@@ -13,7 +13,7 @@ from .frames import (EARTH, EARTH_J2000, GMAT_EARTH_GM, GMAT_MOON_GM, GMAT_SUN_G
                      JUPITER_BARYCENTER, JUPITER_BARYCENTER_J2000, MOON, MOON_J2000, SUN, SUN_J2000, Almanac, Frame,
                      Rotation)
 from .gravity import GravityFieldData
-from .monte_carlo import DispersedState, MonteCarlo, MonteCarloError, MvnSpacecraft, Results, Run
+from .monte_carlo import DispersedState, MonteCarlo, MonteCarloError, MvnSpacecraft, Results, Run, StateDispersion
 from .param import EXPORT_PARAMS, StateError, StateParameter
 from .trajectory import Traj, TrajError, hermite_eval
 from . import dhall

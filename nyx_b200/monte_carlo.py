@@ -32,6 +32,48 @@ class DispersedState:
 _PARAMS = ("X", "Y", "Z", "VX", "VY", "VZ", "Cr", "Cd", "PropMass")
 
 
+@dataclass
+class StateDispersion:
+    """`StateDispersion` (mc/dispersion.rs): a Gaussian dispersion of one state parameter."""
+
+    param: object                      # nyx_b200.param.StateParameter
+    mean: Optional[float] = None
+    std_dev: Optional[float] = None
+
+    @classmethod
+    def zero_mean(cls, param, std_dev: float) -> "StateDispersion":
+        return cls(param, 0.0, float(std_dev))
+
+
+_ANGLES = ("Inclination", "RAAN", "AoP", "TrueAnomaly", "AoL", "TrueLongitude")
+
+
+def _param_jacobian(param, rv: np.ndarray, mu: float) -> np.ndarray:
+    """d param / d (x, y, z, vx, vy, vz) at rv — the row `OrbitGrad::partial_for` supplies in the reference
+    (mc/multivariate.rs:116-145, hyperdual partials); here Richardson-extrapolated central differences of
+    `nyx_b200.param.evaluate` (relative accuracy ~1e-9, far below the Monte Carlo noise it feeds)."""
+    from .param import evaluate
+
+    def f(v):
+        return float(evaluate(param, v.reshape(6, 1), mu)[0])
+
+    def diff(a, b):
+        d = a - b
+        if param.name in _ANGLES:
+            d = (d + 180.0) % 360.0 - 180.0
+        return d
+
+    row = np.zeros(6)
+    for c in range(6):
+        h = 1e-4 * max(1.0, abs(rv[c]))
+        e = np.zeros(6)
+        e[c] = h
+        d1 = diff(f(rv + e), f(rv - e)) / (2 * h)
+        d2 = diff(f(rv + 0.5 * e), f(rv - 0.5 * e)) / h
+        row[c] = (4.0 * d2 - d1) / 3.0
+    return row
+
+
 class MvnSpacecraft:
     """Multivariate-normal spacecraft state generator (mc/multivariate.rs:61-331), Cartesian form.
 
@@ -40,7 +82,8 @@ class MvnSpacecraft:
     [r, v, Cr, Cd, prop mass] (multivariate.rs:298-331).
     """
 
-    def __init__(self, template: Spacecraft, cov: np.ndarray, mean: Optional[np.ndarray] = None):
+    def __init__(self, template: Spacecraft, cov: np.ndarray, mean: Optional[np.ndarray] = None, dispersions=None):
+        self.dispersions = list(dispersions) if dispersions else None
         cov = np.asarray(cov, dtype=np.float64)
         if cov.shape != (9, 9):
             raise ValueError("covariance must be 9x9")
@@ -55,6 +98,44 @@ class MvnSpacecraft:
     @classmethod
     def from_spacecraft_cov(cls, template: Spacecraft, cov, mean=None) -> "MvnSpacecraft":
         return cls(template, cov, mean)
+
+    @classmethod
+    def new(cls, template: Spacecraft, dispersions) -> "MvnSpacecraft":
+        """`MvnSpacecraft::new` (mc/multivariate.rs:80-211): dispersions of orbital parameters (Cartesian components or
+        elements) are rotated into the Cartesian state space through the pseudo-inverse of their Jacobian,
+        cov = J^+ diag(sigma^2) J^+T, mean = J^+ means; Cr, Cd and the prop mass are dispersed independently.
+        Deviations from the reference as coded: the non-orbital variances go to entries (6,6), (7,7), (8,8)
+        of the 9x9 (the reference writes (7,7), (8,8), (9,9) — one is out of bounds) and use `std_dev` (the reference reads
+        `mean`)."""
+        from .param import StateError, StateParameter
+
+        dispersions = list(dispersions)
+        cov = np.zeros((9, 9))
+        mean = np.zeros(9)
+        non_orbital = {StateParameter.Cr: 6, StateParameter.Cd: 7, StateParameter.PropMass: 8, StateParameter.DryMass: 8}
+        orbital = [d for d in dispersions if d.param not in non_orbital]
+        for d in orbital:
+            if d.param in (StateParameter.TotalMass, StateParameter.Isp, StateParameter.Thrust, StateParameter.GuidanceMode):
+                raise StateError(f"ReadOnly: {d.param}")
+        if orbital:
+            rv = template.orbit.to_cartesian_pos_vel()
+            mu = template.orbit.frame.mu_km3_s2()
+            jac = np.array([_param_jacobian(d.param, rv, mu) for d in orbital])
+            jac_inv = np.linalg.pinv(jac)
+            covar = np.diag([(d.std_dev or 0.0) ** 2 for d in orbital])
+            cov[:6, :6] = jac_inv @ covar @ jac_inv.T
+            mean[:6] = jac_inv @ np.array([d.mean or 0.0 for d in orbital])
+        for d in dispersions:
+            if d.param in non_orbital:
+                q = non_orbital[d.param]
+                cov[q, q] = (d.std_dev or 0.0) ** 2
+                mean[q] = d.mean or 0.0
+        return cls(template, cov, mean, dispersions)
+
+    @classmethod
+    def zero_mean(cls, template: Spacecraft, dispersions) -> "MvnSpacecraft":
+        """multivariate.rs:198-209"""
+        return cls.new(template, [StateDispersion(d.param, 0.0, d.std_dev) for d in dispersions])
 
     @classmethod
     def from_cartesian_std(cls, template: Spacecraft, pos_std_km, vel_std_km_s, cr_std=0.0, cd_std=0.0,
@@ -86,7 +167,21 @@ class MvnSpacecraft:
     def apply(self, x: np.ndarray) -> DispersedState:
         vec = self.template.to_vector() + x
         state = self.template.with_vector(self.template.epoch(), vec)
-        return DispersedState(state, [(p, float(-x[i])) for i, p in enumerate(_PARAMS)])
+        if self.dispersions is None:
+            return DispersedState(state, [(p, float(-x[i])) for i, p in enumerate(_PARAMS)])
+        # multivariate.rs:318-324: template.value(param) - state.value(param) for every requested dispersion
+        from .param import evaluate
+
+        mu = self.template.orbit.frame.mu_km3_s2()
+        actual = []
+        for d in self.dispersions:
+            a = float(evaluate(d.param, self.template.orbit.to_cartesian_pos_vel().reshape(6, 1), mu, self.template)[0])
+            b = float(evaluate(d.param, state.orbit.to_cartesian_pos_vel().reshape(6, 1), mu, state)[0])
+            delta = a - b
+            if d.param.name in _ANGLES:
+                delta = (delta + 180.0) % 360.0 - 180.0
+            actual.append((d.param.name, delta))
+        return DispersedState(state, actual)
 
 
 @dataclass
