@@ -163,3 +163,31 @@ class Traj:
         meta.update(metadata or {})
         pq.write_table(pa.Table.from_arrays(cols, schema=pa.schema(schema, metadata=meta)), str(path))
         return path
+
+    @classmethod
+    def from_parquet(cls, path, template: Spacecraft) -> "Traj":
+        """`Traj::<Spacecraft>::from_parquet` (md/trajectory/sc_traj.rs:212-440): "Epoch (UTC)" and the six Cartesian columns are
+        required; dry / prop mass columns update the template when present.  The frame is the template's: the reference reads it
+        from the Dhall-serialised field metadata, here the field metadata carries the frame's name and is checked against it."""
+        import pyarrow.parquet as pq
+
+        from .cosmic import utc_iso_to_epochs
+        from .param import StateParameter as P
+
+        tab = pq.read_table(str(path))
+        names = set(tab.column_names)
+        if "Epoch (UTC)" not in names:
+            raise TrajError("MissingData: Epoch (UTC)")
+        cart = [P.X, P.Y, P.Z, P.VX, P.VY, P.VZ]
+        for f in cart:
+            if str(f) not in names:
+                raise TrajError(f"MissingData: {f}")
+        meta = tab.schema.field(str(P.X)).metadata or {}
+        frame_name = meta.get(b"Frame")
+        if frame_name is None:
+            raise TrajError("MissingData: Frame in metadata")
+        if frame_name.decode() != template.orbit.frame.name:
+            raise TrajError(f"trajectory is in frame {frame_name.decode()}, the template in {template.orbit.frame.name}")
+        ep = utc_iso_to_epochs(tab["Epoch (UTC)"].to_pylist())
+        states = np.column_stack([np.asarray(tab[str(f)].to_pylist(), dtype=np.float64) for f in cart])
+        return cls(template, ep, states).finalize()

@@ -189,3 +189,11 @@ def test_traj_iteration_filter_and_parquet(oracle, tmp_path):
     assert grid.column_names == ["Epoch (UTC)", "X (km)", "Rmag (km)"] and grid.num_rows == len(every)
     assert grid["X (km)"].to_pylist() == [s.orbit.x_km for s in every] and grid.schema.metadata[b"k"] == b"v"
     assert grid["Epoch (UTC)"][1].as_py() == nb.epochs_to_utc_iso([step])[0]
+    # sc_traj.rs:212-440: read back
+    back = Traj.from_parquet(tmp_path / "traj.parquet", sc)
+    assert np.array_equal(back.epochs_ns, tr.epochs_ns) and np.array_equal(back.states, tr.states)
+    with pytest.raises(nb.TrajError, match="MissingData"):
+        Traj.from_parquet(tmp_path / "traj_grid.parquet", sc)          # no velocity columns
+    moon_sc = nb.Spacecraft.from_orbit(nb.Orbit.cartesian(1800.0, 0, 0, 0, 1.6, 0, 0, nb.MOON_J2000))
+    with pytest.raises(nb.TrajError, match="frame"):
+        Traj.from_parquet(tmp_path / "traj.parquet", moon_sc)
