@@ -425,16 +425,61 @@ class Propagator:
         return PropInstance(self, state, almanac)
 
     def many_until_epoch(self, spacecraft: Sequence[Spacecraft], epoch_ns: int, almanac: Optional[Almanac] = None,
-                         ) -> List[Spacecraft]:
-        """nyx-py `Propagator.many_until_epoch(list, epoch, trajectory=False)` (py_md.rs:224-271):
-        failed runs are dropped (py_md.rs:251-254, 262-265)."""
+                         trajectory: bool = False, traj_capacity: int = 1024):
+        """nyx-py `Propagator.many_until_epoch(list, epoch, trajectory)` (py_md.rs:224-271): ONE batched launch; failed runs
+        are dropped (py_md.rs:251-254, 262-265).  Returns the final states, or with `trajectory=True` a list of
+        (state, Traj) like the reference's `PropagationResult{state, trajectory}`; the recording sink grows until no run
+        overflows it.  Start epochs may differ per spacecraft."""
         spacecraft = list(spacecraft)
         if not spacecraft:
             return []
         frame = spacecraft[0].orbit.frame
         st, cs, ep = pack_spacecraft(spacecraft)
-        out, out_ep, _, status = self.engine(frame, almanac).propagate_batch(st, cs, ep, epoch_ns)
-        return [sc.with_vector(int(out_ep[i]), out[:, i]) for i, sc in enumerate(spacecraft) if (status[i] & 0xFF) == 0]
+        eng = self.engine(frame, almanac)
+        if not trajectory:
+            out, out_ep, _, status = eng.propagate_batch(st, cs, ep, epoch_ns)
+            return [sc.with_vector(int(out_ep[i]), out[:, i]) for i, sc in enumerate(spacecraft) if (status[i] & 0xFF) == 0]
+        from .trajectory import Traj
+
+        cap = max(2, int(traj_capacity))
+        while True:
+            out, out_ep, det, status, (t_ep, t_st, t_cnt) = eng.propagate_batch(st, cs, ep, epoch_ns, traj_capacity=cap)
+            if int(det["n_steps"].max()) + 1 <= cap:
+                break
+            cap = int(det["n_steps"].max()) + 1
+        res = []
+        for i, sc in enumerate(spacecraft):
+            if (status[i] & 0xFF) != 0:
+                continue
+            k = int(t_cnt[i])
+            res.append((sc.with_vector(int(out_ep[i]), out[:, i]), Traj(sc, t_ep[:k, i].copy(), np.ascontiguousarray(t_st[:, :k, i].T)).finalize()))
+        return res
+
+    def many_for_duration(self, spacecraft: Sequence[Spacecraft], duration_ns: int, almanac: Optional[Almanac] = None,
+                          trajectory: bool = False, traj_capacity: int = 1024):
+        """nyx-py `Propagator.many_for_duration` (py_md.rs:273-320): every spacecraft from its own epoch for `duration`; one
+        launch per distinct end epoch (one, when they share the start epoch)."""
+        spacecraft = list(spacecraft)
+        ends = [sc.epoch() + int(duration_ns) for sc in spacecraft]
+        out = [None] * len(spacecraft)
+        for end in sorted(set(ends)):
+            idx = [i for i, e in enumerate(ends) if e == end]
+            ok = self._many_indexed([spacecraft[i] for i in idx], end, almanac, trajectory, traj_capacity)
+            for j, r in ok:
+                out[idx[j]] = r
+        return [r for r in out if r is not None]
+
+    def _many_indexed(self, spacecraft, epoch_ns, almanac, trajectory, traj_capacity):
+        """many_until_epoch keeping the input index of the surviving runs"""
+        marked = [s for s in spacecraft]
+        res = self.many_until_epoch(marked, epoch_ns, almanac, trajectory, traj_capacity)
+        if len(res) == len(marked):
+            return list(enumerate(res))
+        # some runs failed: recover the indices through the per-run status of a plain launch
+        st, cs, ep = pack_spacecraft(marked)
+        status = self.engine(marked[0].orbit.frame, almanac).propagate_batch(st, cs, ep, epoch_ns)[3]
+        keep = [i for i in range(len(marked)) if (status[i] & 0xFF) == 0]
+        return list(zip(keep, res))
 
 
 class PropInstance:

@@ -113,3 +113,47 @@ def resample_queries(t_ep, t_cnt, end):
         np.array([-5, 0, 1, int(t_ep[1, 0]) - 1, int(t_ep[3, 0]), int(t_ep[k0 - 2, 0]) + 1, end - 1, end, end + 1], dtype=np.int64),
         np.arange(0, end, 600 * S, dtype=np.int64) + 123_456_789,
     ])
+
+
+# ---- CPU stand-in for `nyx_b200.Engine`: the same host-facing methods on the oracle, so that the host mirror above the C ABI
+# (PropInstance, Propagator.many_*, MonteCarlo, Results) can be exercised without a device.  Test infrastructure only.
+class OracleEngine:
+    def __init__(self, oracle, prop, frame, almanac, tmp_path=None):
+        self.oracle, self.packed, self.opts = oracle, prop.dynamics.pack(frame, almanac), prop.opts.to_c(prop.method)
+        self.launches = 0
+        self._resident = None
+        self._shim = hermite_shim(tmp_path) if tmp_path is not None else None
+
+    def propagate_batch(self, st, cs, ep, end_ns, step_ns=None, traj_capacity=0, event=None):
+        self.launches += 1
+        ret = self.oracle.propagate_batch(self.packed.c, self.opts, st, cs, ep, int(end_ns), step_ns, traj_capacity=traj_capacity, event=event)
+        if traj_capacity:
+            self._resident = ret[4]
+        return ret
+
+    def resample(self, q, recording=None, n=None):
+        if recording is not None:
+            self._resident = recording
+        return self._shim(*self._resident, q)
+
+    def locate_events(self, kind, value, precision_ns, recording=None, n=None, run_status=None):
+        if recording is not None:
+            self._resident = recording
+        return self._shim.locate(*self._resident, kind, value, precision_ns, run_status)
+
+    def launch_count(self):
+        return self.launches
+
+
+def use_oracle_engine(monkeypatch, oracle, prop, tmp_path=None):
+    """Route `prop.engine(frame, almanac)` to an OracleEngine (one per (frame, almanac), like the real cache)."""
+    cache = {}
+
+    def engine(frame, almanac):
+        key = (id(almanac), frame)
+        if key not in cache:
+            cache[key] = OracleEngine(oracle, prop, frame, almanac, tmp_path)
+        return cache[key]
+
+    monkeypatch.setattr(prop, "engine", engine)
+    return cache
