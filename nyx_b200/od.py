@@ -19,7 +19,6 @@ generation for tests and the benchmark, not part of the filter path.
 """
 from __future__ import annotations
 
-import ctypes as C
 import enum
 import math
 from dataclasses import dataclass, field

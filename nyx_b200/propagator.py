@@ -13,8 +13,8 @@ from __future__ import annotations
 
 import ctypes as C
 import enum
-from dataclasses import dataclass, replace
-from typing import Iterable, List, Optional, Sequence, Tuple
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
 
 import numpy as np
 

@@ -3,7 +3,6 @@ coefficient records (`nyxb_coop_build_host`, csrc/nyxb_coop.cu) are walked here 
 (csrc/nyxb_coop_kernel.cuh) walks them, and the resulting acceleration is compared with the oracle's
 `GravityField::eom` restatement (gravity_field.rs:148-268).  No device is needed: `nyxb_coop_table_dump` is host-only."""
 import ctypes as C
-import math
 
 import numpy as np
 import pytest

@@ -9,7 +9,7 @@ import nyx_b200 as nb
 from nyx_b200 import abi
 from nyx_b200.event import Event, brent, locate_event
 from nyx_b200.trajectory import Traj
-from tests.util import S, leo_ensemble, leo_state, max_dr_dv
+from tests.util import S, leo_ensemble, leo_state
 
 
 def _dyn(degree=8):
