@@ -87,3 +87,36 @@ def test_monte_carlo_reports_and_events_on_the_host_mirror(oracle, monkeypatch, 
     assert abs(ev.eval(found)) < 1e-3
     with pytest.raises(nb.PropagationError, match="NthEventError"):
         prop.with_(tmpl).until_nth_event(300 * S, Event.radius(30000.0), trigger=1)
+
+
+def test_kalman_od_process_on_the_host_mirror(oracle, monkeypatch, tmp_path):
+    """`KalmanODProcess.process_arcs` -> packing -> (stand-in for nyxb_od_ekf_batch) -> `ODSolution`, then the reference's
+    data formats either side of it: tracking arcs from parquet in, OD solution parquet out."""
+    import pyarrow.parquet as pq
+    from tests.od_util import leo_od_scenario, run_oracle_filter
+    from oracle import pyoracle_od
+    sc = leo_od_scenario(oracle, n=3, n_msr=24, seed=2)
+    odp, prop = sc["odp"], sc["prop"]
+    use_oracle_engine(monkeypatch, oracle, prop)
+    # the arcs travel through the reference's parquet layout and come back as the batched arc
+    paths = [sc["arc"].to_parquet(tmp_path / f"trk{i}.parquet", index=i) for i in range(3)]
+    arc = nb.TrackingDataArc.stack([nb.TrackingDataArc.from_parquet(p) for p in paths])
+    assert np.array_equal(arc.epoch_ns, sc["arc"].epoch_ns) and arc.tracker == list(sc["arc"].tracker)
+    assert np.array_equal(arc.obs, sc["arc"].obs, equal_nan=True)
+    sol = odp.process_arcs(sc["ests"], arc, record_estimates=True)
+    assert (sol.status == 0).all() and sol.accepted().sum() > 3 * 15
+    for i in range(3):   # the mirror's packing (column-major covariance, tracker indices, per-filter observations) is faithful
+        ref = run_oracle_filter(pyoracle_od, sc, i)
+        assert np.array_equal(sol.final_state_soa[:, i], ref["state"]) and np.array_equal(sol.covar[i], ref["covar"])
+        assert np.array_equal(sol.msr_flags[:, i], ref["msr_flags"])
+    est = sol.final_estimate(1)
+    truth_end = sc["truth"][-1, :3, 1]
+    assert np.linalg.norm(est.nominal_state.orbit.radius_km - truth_end) < np.linalg.norm(sc["ests"][1].nominal_state.orbit.radius_km - sc["truth"][0, :3, 1]) + 1.0
+    tab = pq.read_table(str(sol.to_parquet(tmp_path / "od1.parquet", index=1)))
+    processed = int(((sol.msr_flags[:, 1] & 1) != 0).sum())
+    assert tab.num_rows == processed and tab["Tracker"].to_pylist()[0] == arc.tracker[int(np.nonzero(sol.msr_flags[:, 1] & 1)[0][0])]
+    assert np.isfinite(np.array(tab["Residual ratio"].to_pylist(), dtype=float)).all()
+    sig_x = [c for c in tab.column_names if c.startswith("Sigma X (")]
+    assert len(sig_x) == 1 and all(v > 0 for v in tab[sig_x[0]].to_pylist())
+    with pytest.raises(nb.ODError, match="observation sets"):
+        odp.process_arcs(sc["ests"][:2], arc)

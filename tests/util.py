@@ -141,6 +141,31 @@ class OracleEngine:
             self._resident = recording
         return self._shim.locate(*self._resident, kind, value, precision_ns, run_status)
 
+    def od_ekf_batch(self, cfg_c, n_stations, stations_c, msr_epoch_ns, msr_tracker, obs, state_soa, consts_soa, epoch0_ns, covar0_soa,
+                     record_estimates=False):
+        """`Engine.od_ekf_batch` on the numpy / C oracle filter, one filter after the other."""
+        from nyx_b200.od import ODSolution
+        from oracle import pyoracle_od
+
+        self.launches += 1
+        n, m = state_soa.shape[1], len(msr_epoch_ns)
+        out_state = np.empty((9, n)); out_epoch = np.empty(n, dtype=np.int64); covar = np.empty((n, 9, 9)); dev = np.empty((9, n))
+        ratio = np.full((m, 2, n), np.nan); prefit = np.full((m, 2, n), np.nan); postfit = np.full((m, 2, n), np.nan)
+        flags = np.zeros((m, n), dtype=np.int32)
+        est_state = np.full((m, 9, n), np.nan) if record_estimates else None
+        est_cov = np.full((m, 9, n), np.nan) if record_estimates else None
+        details = np.zeros(n, dtype=abi.DETAILS_DTYPE); status = np.zeros(n, dtype=np.int32)
+        for i in range(n):
+            cov0 = covar0_soa[:, i].reshape(9, 9).T          # (c*9 + r) -> [r][c]
+            r = pyoracle_od.process_arc(self.packed.c, self.opts, cfg_c, stations_c, msr_epoch_ns, np.asarray(msr_tracker, dtype=np.int32),
+                                        np.ascontiguousarray(obs[:, :, i]), state_soa[:, i].copy(), consts_soa[:, i].copy(), int(epoch0_ns[i]), cov0)
+            out_state[:, i], out_epoch[i], covar[i], dev[:, i] = r["state"], r["epoch"], r["covar"], r["state_dev"]
+            ratio[:, :, i], prefit[:, :, i], postfit[:, :, i], flags[:, i] = r["resid_ratio"], r["prefit"], r["postfit"], r["msr_flags"]
+            if record_estimates:
+                est_state[:, :, i], est_cov[:, :, i] = r["est_state"], r["est_covar_diag"]
+            details["n_steps"][i], status[i] = r["n_steps"], r["status"]
+        return ODSolution(out_state, out_epoch, covar, dev, ratio, prefit, postfit, flags, est_state, est_cov, details, status)
+
     def launch_count(self):
         return self.launches
 
