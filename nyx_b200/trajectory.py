@@ -191,3 +191,90 @@ class Traj:
         ep = utc_iso_to_epochs(tab["Epoch (UTC)"].to_pylist())
         states = np.column_stack([np.asarray(tab[str(f)].to_pylist(), dtype=np.float64) for f in cart])
         return cls(template, ep, states).finalize()
+
+    # ---- CCSDS OEM (KVN) — md/trajectory/sc_traj.rs:176-210; the reference goes through anise's `Ephemeris`, which is not in the
+    # tree: read / written here from the published layout of CCSDS 502.0-B (header, META_START..META_STOP, ephemeris lines).
+    @classmethod
+    def from_oem_file(cls, path, template: Optional[Spacecraft] = None) -> "Traj":
+        """`Traj::from_oem_file`: all ephemeris lines of all segments; duplicate epochs removed (`finalize`); the trajectory is
+        named after OBJECT_ID.  Without a template a massless default spacecraft is used, in the frame the metadata names
+        (CENTER_NAME Earth / Moon with an inertial REF_FRAME)."""
+        from .cosmic import Orbit, utc_iso_to_epochs
+        from .frames import EARTH_J2000, MOON_J2000, NS_PER_S
+
+        meta, rows, in_meta, in_cov = {}, [], False, False
+        for raw in open(path, "r"):
+            line = raw.strip()
+            if not line or line.startswith("COMMENT"):
+                continue
+            if line == "META_START":
+                in_meta = True
+            elif line == "META_STOP":
+                in_meta = False
+            elif line == "COVARIANCE_START":
+                in_cov = True
+            elif line == "COVARIANCE_STOP":
+                in_cov = False
+            elif in_cov:
+                continue
+            elif "=" in line:
+                key, val = (t.strip() for t in line.split("=", 1))
+                if in_meta or key in ("CCSDS_OEM_VERS", "CREATION_DATE", "ORIGINATOR"):
+                    meta.setdefault(key, val)
+            else:
+                tok = line.split()
+                if len(tok) < 7:
+                    raise TrajError(f"malformed OEM ephemeris line: {line!r}")
+                rows.append((tok[0], [float(v) for v in tok[1:7]]))
+        if "CCSDS_OEM_VERS" not in meta or not rows:
+            raise TrajError("not a CCSDS OEM file (no version keyword or no ephemeris data)")
+        scale = meta.get("TIME_SYSTEM", "UTC").upper()
+        stamps = [r[0] for r in rows]
+        if scale == "UTC":
+            ep = utc_iso_to_epochs(stamps)
+        else:
+            offset = {"TT": 0, "TDB": 0, "TAI": 32_184_000_000, "GPS": 19 * NS_PER_S + 32_184_000_000}.get(scale)
+            if offset is None:
+                raise TrajError(f"unsupported OEM TIME_SYSTEM {scale}")
+            ep = (np.array(stamps, dtype="datetime64[ns]") - np.datetime64("2000-01-01T12:00:00", "ns")).astype(np.int64) + offset
+        if template is None:
+            center = meta.get("CENTER_NAME", "EARTH").upper()
+            if meta.get("REF_FRAME", "ICRF").upper() not in ("ICRF", "EME2000", "J2000", "GCRF"):
+                raise TrajError(f"unsupported OEM REF_FRAME {meta.get('REF_FRAME')}")
+            frame = {"EARTH": EARTH_J2000, "MOON": MOON_J2000}.get(center)
+            if frame is None:
+                raise TrajError(f"unsupported OEM CENTER_NAME {center}")
+            template = Spacecraft.from_orbit(Orbit.cartesian(*rows[0][1], int(ep[0]), frame))
+        tr = cls(template, np.asarray(ep, dtype=np.int64), np.array([r[1] for r in rows]), meta.get("OBJECT_ID"))
+        order = np.argsort(tr.epochs_ns, kind="stable")     # finalize() dedups neighbours: sort first
+        tr.epochs_ns, tr.states = tr.epochs_ns[order], tr.states[order]
+        return tr.finalize()
+
+    def to_oem_file(self, path, object_id: str, originator: Optional[str] = None, object_name: Optional[str] = None,
+                    start_ns: Optional[int] = None, end_ns: Optional[int] = None, step_ns: Optional[int] = None):
+        """`Traj::to_oem_file`: the recorded states, or (when start / end / step is given) the states interpolated every `step`
+        (default 1 min) like `to_parquet`; UTC time stamps with nanosecond digits, values with full precision."""
+        from .cosmic import epochs_to_utc_iso
+
+        if start_ns is not None or end_ns is not None or step_ns is not None:
+            sts = list(self.every_between(60 * 10**9 if step_ns is None else step_ns,
+                                          int(self.epochs_ns[0]) if start_ns is None else start_ns,
+                                          int(self.epochs_ns[-1]) if end_ns is None else end_ns))
+            epochs = np.array([s.epoch() for s in sts], dtype=np.int64)
+            rv = np.array([s.orbit.to_cartesian_pos_vel() for s in sts]).reshape(len(sts), 6)
+        else:
+            epochs, rv = self.epochs_ns, self.states
+        if len(epochs) == 0:
+            raise TrajError("no state to export")
+        iso = epochs_to_utc_iso(epochs)
+        frame = self.template.orbit.frame
+        center = {399: "EARTH", 301: "MOON", 10: "SUN"}.get(frame.ephemeris_id, str(frame.ephemeris_id))
+        with open(path, "w") as fh:
+            fh.write("CCSDS_OEM_VERS = 2.0\n")
+            fh.write(f"CREATION_DATE = {np.datetime_as_string(np.datetime64('now'), unit='s')}\n")
+            fh.write(f"ORIGINATOR = {originator or 'nyx_b200'}\n\nMETA_START\n")
+            fh.write(f"OBJECT_NAME = {object_name or object_id}\nOBJECT_ID = {object_id}\nCENTER_NAME = {center}\nREF_FRAME = ICRF\n")
+            fh.write(f"TIME_SYSTEM = UTC\nSTART_TIME = {iso[0]}\nSTOP_TIME = {iso[-1]}\nMETA_STOP\n\n")
+            for t, row in zip(iso, rv):
+                fh.write(t + " " + " ".join(repr(float(v)) for v in row) + "\n")
+        return path

@@ -197,3 +197,54 @@ def test_traj_iteration_filter_and_parquet(oracle, tmp_path):
     moon_sc = nb.Spacecraft.from_orbit(nb.Orbit.cartesian(1800.0, 0, 0, 0, 1.6, 0, 0, nb.MOON_J2000))
     with pytest.raises(nb.TrajError, match="frame"):
         Traj.from_parquet(tmp_path / "traj.parquet", moon_sc)
+
+
+OEM_DIR = "/root/reference/data/03_tests/ccsds/oem"
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir(OEM_DIR), reason="reference tree not present")
+def test_reference_oem_samples(tmp_path):
+    """The reference's own OEM tests (md/trajectory/sc_traj.rs:450-585) on its sample files: state counts after removing the
+    duplicate epochs (361 / 61 / 181), the name taken from OBJECT_ID, an export / reload round trip, and the trimmed,
+    re-interpolated export (one state fewer, first + 1 s, last - 19 s)."""
+    for name, count in (("LEO_10s", 361), ("MEO_60s", 61), ("GEO_20s", 181)):
+        tr = Traj.from_oem_file(f"{OEM_DIR}/{name}.oem")
+        assert len(tr) == count and tr.name == "0000-000A" and (np.diff(tr.epochs_ns) > 0).all()
+    geo = Traj.from_oem_file(f"{OEM_DIR}/GEO_20s.oem")
+    assert nb.epochs_to_utc_iso(geo.epochs_ns[:1])[0].startswith("2020-06-01T12:00:00")
+    out = tmp_path / "GEO_20s_rebuilt.oem"
+    geo.to_oem_file(out, "0000-000A", "Test Suite", "TEST_OBJ")
+    again = Traj.from_oem_file(out)
+    assert again.name == geo.name and np.array_equal(again.epochs_ns, geo.epochs_ns) and np.array_equal(again.states, geo.states)
+    S_ = 10**9
+    geo.to_oem_file(out, "TEST-OBJ-ID", "Test Suite", "TEST_OBJ", start_ns=int(geo.epochs_ns[0]) + S_, end_ns=int(geo.epochs_ns[-1]) - S_,
+                    step_ns=20 * S_)
+    trimmed = Traj.from_oem_file(out)
+    assert trimmed.name == "TEST-OBJ-ID" and len(trimmed) == len(geo) - 1
+    assert trimmed.epochs_ns[0] == geo.epochs_ns[0] + S_ and trimmed.epochs_ns[-1] == geo.epochs_ns[-1] - 19 * S_
+    # the interpolated states sit on the sampled orbit: compare with the neighbouring samples' chord to GEO accuracy
+    mid = trimmed.states[10, :3]
+    assert np.linalg.norm(mid - geo.states[10, :3]) < 3.2 and np.linalg.norm(mid - geo.states[11, :3]) > 50.0
+
+
+def test_oem_round_trip_and_errors(oracle, tmp_path):
+    frame = nb.EARTH_J2000
+    sc = leo_state(frame)
+    st, cs, ep = nb.pack_spacecraft([sc])
+    _, _, _, _, (t_ep, t_st, t_cnt) = _oracle_traj(oracle, nb.Propagator.default(_dyn()), frame, st, cs, ep, 1800 * S, 64)
+    k = int(t_cnt[0])
+    tr = Traj(sc, t_ep[:k, 0].copy(), np.ascontiguousarray(t_st[:, :k, 0].T)).finalize()
+    path = tr.to_oem_file(tmp_path / "leo.oem", "2024-001A", object_name="LEO")
+    back = Traj.from_oem_file(path, sc)
+    assert back.name == "2024-001A" and np.array_equal(back.epochs_ns, tr.epochs_ns) and np.array_equal(back.states, tr.states)
+    assert Traj.from_oem_file(path).template.orbit.frame.ephemeris_id == frame.ephemeris_id     # frame from CENTER_NAME
+    text = open(path).read()
+    (tmp_path / "tai.oem").write_text(text.replace("TIME_SYSTEM = UTC", "TIME_SYSTEM = TAI"))
+    tai = Traj.from_oem_file(tmp_path / "tai.oem")
+    assert tai.epochs_ns[0] - tr.epochs_ns[0] == -32 * S         # the same stamp read as TAI is 32 s earlier than read as UTC (2000)
+    (tmp_path / "bad.oem").write_text("META_START\nMETA_STOP\n")
+    with pytest.raises(nb.TrajError):
+        Traj.from_oem_file(tmp_path / "bad.oem")
+    (tmp_path / "mars.oem").write_text(text.replace("CENTER_NAME = EARTH", "CENTER_NAME = MARS"))
+    with pytest.raises(nb.TrajError, match="CENTER_NAME"):
+        Traj.from_oem_file(tmp_path / "mars.oem")
