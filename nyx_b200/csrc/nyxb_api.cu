@@ -22,6 +22,8 @@ extern "C" cudaError_t nyxb_launch_thread_strict(const DevSetup*, size_t, const 
 extern "C" cudaError_t nyxb_launch_thread_fast(const DevSetup*, size_t, const double*, const double*, const long long*,
                                                long long, long long*, double*, long long*, nyxb_details*, int*, int,
                                                const DevSink*, cudaStream_t);
+extern "C" cudaError_t nyxb_launch_thread_fastc(const DevSetup*, size_t, const double*, const double*, const long long*, long long, long long*,
+                                                double*, long long*, nyxb_details*, int*, int, const DevSink*, const double*, size_t, cudaStream_t);
 extern "C" double nyxb_fp64_probe(int device, int iters);
 extern "C" cudaError_t nyxb_launch_od_coop(const DevSetup*, const DevOd*, const int*, size_t, const double*, const double*, const long long*,
                                            double*, long long*, nyxb_details*, int*, cudaStream_t);
@@ -69,6 +71,7 @@ struct nyxb_engine {
     size_t rec_n = 0;        // the recording resident in d_sink: trajectories and capacity (nyxb_traj_resample with sink == NULL)
     long long rec_cap = 0;
     std::vector<double> h_cnm, h_snm;      // host copies for building cooperative tables lazily
+    std::vector<double> h_colrec;          // column-walk records (experimental constant-bank kernel, NYXB_K1_CONST=1)
     std::map<int, DevCoop> coop;           // lanes -> device tables
     std::map<int, DevCoopStrict> scoop;    // lanes -> STRICT cooperative schedules
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -266,6 +269,7 @@ extern "C" nyxb_engine* nyxb_engine_create(const nyxb_dynamics* dyn, const nyxb_
                 for (int j = k + 1; j <= N + 1; ++j) { push(k, j); if (two) push(k + 1, j); }
             }
             cr.insert(cr.end(), 16, 0.0);           // two null records: targets of the last prefetches
+            e->h_colrec = cr;
             S.grav.colrec = upload(e, cr.data(), cr.size());
             S.grav.ncols = ncols;
             if (!S.grav.colrec) { set_err("gravity table upload failed"); delete e; return nullptr; }
@@ -371,6 +375,12 @@ static int32_t launch(nyxb_engine* e, size_t n, const double* state, const doubl
     } else {
         int blk = 64;
         if (const char* ev = getenv("NYXB_K1_BLOCK")) { int v = atoi(ev); if (v == 32 || v == 64 || v == 128) blk = v; }
+        const char* kc = getenv("NYXB_K1_CONST");   // experimental: records through the constant bank
+        if (kc && kc[0] == '1' && e->S.has_grav && !e->h_colrec.empty() && e->h_colrec.size() <= 7680)
+            err = nyxb_launch_thread_fastc(&e->S, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io, out_state,
+                                           (long long*)out_epoch, out_details, out_status, blk, &sink, e->h_colrec.data(),
+                                           e->h_colrec.size(), stream);
+        else
         err = nyxb_launch_thread_fast(&e->S, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io,
                                       out_state, (long long*)out_epoch, out_details, out_status, blk, &sink, stream);
     }

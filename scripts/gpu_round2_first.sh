@@ -11,10 +11,14 @@ timeout 120 $B > gpurun_out/r02a_c2_default.json 2> gpurun_out/r02a_c2_default.e
 NYXB_COOP_SCHED=aligned timeout 120 $B > gpurun_out/r02a_c2_aligned.json 2> gpurun_out/r02a_c2_aligned.err
 NYXB_COOP_T=2 timeout 120 $B > gpurun_out/r02a_c2_t2.json 2> gpurun_out/r02a_c2_t2.err
 NYXB_COOP_T=2 NYXB_COOP_SCHED=aligned timeout 120 $B > gpurun_out/r02a_c2_t2_aligned.json 2> gpurun_out/r02a_c2_t2_aligned.err
+timeout 120 $B --lanes 1 --n-traj 100000 > gpurun_out/r02a_c2_100k_k1.json 2> gpurun_out/r02a_c2_100k_k1.err
+NYXB_K1_CONST=1 timeout 120 $B --lanes 1 --n-traj 100000 > gpurun_out/r02a_c2_100k_k1const.json 2> gpurun_out/r02a_c2_100k_k1const.err
+NYXB_K1_CONST=1 timeout 120 $B --lanes 1 > gpurun_out/r02a_c2_k1const.json 2> gpurun_out/r02a_c2_k1const.err
+NYXB_K1_CONST=1 timeout 100 python -m pytest tests/test_gpu_parity.py -q -p no:cacheprovider -k "thread or lanes1 or per_thread" > gpurun_out/r02a_pytest_k1const.log 2>&1; tail -2 gpurun_out/r02a_pytest_k1const.log
 NYXB_COOP_SCHED=aligned timeout 120 $B --workload c4 --n-traj 2000 --span-days 1 > gpurun_out/r02a_c4_aligned.json 2> gpurun_out/r02a_c4_aligned.err
 NYXB_COOP_SCHED=aligned timeout 200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py -q -p no:cacheprovider > gpurun_out/r02a_pytest_aligned.log 2>&1; tail -3 gpurun_out/r02a_pytest_aligned.log
 cat gpurun_out/r02a_smem_probe.txt
-for f in default aligned t2 t2_aligned; do python - "$f" <<'PY'
+for f in default aligned t2 t2_aligned 100k_k1 100k_k1const k1const; do python - "$f" <<'PY'
 import json, sys
 try:
     d = json.load(open(f"gpurun_out/r02a_c2_{sys.argv[1]}.json"))
