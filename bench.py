@@ -363,8 +363,14 @@ def main():
         if rank != 0:
             return 0
         sample_n = args.cpu_sample
-        for _ in range(max(0, min(args.warmup, 1))):
-            cpu_reference_leg(args, nb, min(sample_n, 32))
+        # calibration / warm-up leg: two trajectories per host thread; it also sizes the sample so that the K timed steps stay
+        # within ~2 minutes whatever K the caller asks for (each step is a bounded sample of the same workload)
+        cores = os.cpu_count() or 8
+        cal = cpu_reference_leg(args, nb, min(sample_n, 2 * cores))
+        rate = cal["steps"] / max(cal["times"][0], 1e-6)                       # trajectory-steps per second, all threads
+        per_traj = cal["steps"] / max(min(sample_n, 2 * cores), 1)
+        fit = int(rate * 120.0 / (max(args.steps, 1) * max(per_traj, 1.0)))
+        sample_n = max(cores, min(sample_n, (fit // cores) * cores if fit >= cores else cores))
         leg = cpu_reference_leg(args, nb, sample_n, repeats=args.steps)
         total_t = sum(leg["times"])
         value = leg["steps"] * args.steps / total_t
