@@ -335,7 +335,10 @@ template <int G, int T, bool SMEM_TABLE>
 #ifndef COOP_MINB1
 #define COOP_MINB1 5
 #endif
-__global__ void __launch_bounds__(COOP_CTA, (T == 1 ? COOP_MINB1 : 3))
+#ifndef COOP_MINB2
+#define COOP_MINB2 3   /* resident CTAs per SM the T = 2 instantiation is compiled for (register cap 65536 / (COOP_CTA * COOP_MINB2)) */
+#endif
+__global__ void __launch_bounds__(COOP_CTA, (T == 1 ? COOP_MINB1 : COOP_MINB2))
 nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop Cp, size_t n,
             const double* __restrict__ state, const double* __restrict__ consts,
             const long long* __restrict__ epoch0, long long end_epoch, long long* __restrict__ step_io,
