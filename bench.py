@@ -172,6 +172,21 @@ def _c5_ref_worker(job):
     return ref["n_steps"]
 
 
+def _c5_ref_full(i):
+    """Filter i of the scenario in _C5_SC over its WHOLE arc on the numpy + C oracle (parity tests at the BASELINE span)."""
+    from oracle import pyoracle_od
+
+    sc = _C5_SC
+    odp, arc, est = sc["odp"], sc["arc"], sc["ests"][i]
+    names_c, st_c = odp.stations_c(sc["frame"])
+    tracker = np.array([names_c.index(t) for t in arc.tracker], dtype=np.int32)
+    msc = est.nominal_state.mass
+    cs0 = np.array([msc.dry_mass_kg, msc.extra_mass_kg, est.nominal_state.srp.area_m2, 0.0])
+    ref = pyoracle_od.process_arc(sc["dyn"].pack(sc["frame"], sc["alm"]).c, sc["prop"].opts.to_c(sc["prop"].method), odp.config_c(), st_c,
+                                  arc.epoch_ns, tracker, np.ascontiguousarray(arc.obs[:, :, i]), est.nominal_state.to_vector(), cs0, 0, est.covar)
+    return {k: ref[k] for k in ("est_state", "msr_flags", "state", "n_steps", "status", "covar")}
+
+
 _C5_SC = None
 
 

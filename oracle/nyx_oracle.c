@@ -664,6 +664,12 @@ static void record_state(const inst_t* in, int64_t s) {
 
 #define MAX_STAGES 16
 
+/* Sensitivity probe (tests/test_oracle_sensitivity.py, scripts/oracle_sensitivity.py): the error norm of every adaptive attempt
+ * is multiplied by this factor.  1.0 (the default) leaves the restatement untouched; 1 + 2^-52 asks "what does ONE ulp in the
+ * reference's own error estimate do to the final state" -- the step-sequence sensitivity that bounds any tolerance-parity mode. */
+static double g_error_scale = 1.0;
+void nyx_oracle_set_error_scale(double s) { g_error_scale = s; }
+
 /* instance.rs:358-493 derive(); returns status, writes dt_ns and next[9] */
 static int derive(inst_t* in, eom_ctx* cx, const nyxb_integ_opts* o, const tableau_t* tb, int64_t* dt_ns, double next[9]) {
     double k[MAX_STAGES][9];
@@ -707,6 +713,7 @@ static int derive(inst_t* in, eom_ctx* cx, const nyxb_integ_opts* o, const table
             return 0;
         }
         in->det.error = nyx_oracle_error_estimate(o->error_ctrl, err_est, next, y); /* :422-426 */
+        if (g_error_scale != 1.0) in->det.error *= g_error_scale;   /* sensitivity probe only */
         if (in->det.error <= o->tolerance || h <= min_s || in->det.attempts >= o->attempts) { /* :428-431 */
             for (int e = 0; e < 9; ++e)
                 if (next[e] != next[e]) return NYXB_ERR_PROP_MATH;   /* :432-439 */

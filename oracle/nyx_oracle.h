@@ -54,6 +54,8 @@ int nyx_oracle_propagate_batch_stm(const nyxb_dynamics* dyn, const nyxb_integ_op
                                    const double* stm_in_soa, double* out_state_soa, int64_t* out_epoch_ns,
                                    double* out_stm_soa, nyxb_details* out_details, int32_t* out_status, int n_threads);
 int nyx_oracle_num_threads(void);
+/* sensitivity probe: multiply every adaptive error norm by `s` (1.0 = untouched restatement) */
+void nyx_oracle_set_error_scale(double s);
 #ifdef __cplusplus
 }
 #endif

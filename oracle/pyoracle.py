@@ -14,12 +14,14 @@ from nyx_b200 import abi
 
 _DIR = Path(__file__).resolve().parent
 _LIB = None
+_SPEED = None
 
 
 def build(force: bool = False) -> Path:
     so = _DIR / "libnyx_oracle.so"
     srcs = [_DIR / "nyx_oracle.c", _DIR / "nyx_oracle_od.c", _DIR / "nyx_oracle_mvn.c", _DIR / "nyx_oracle.h", _DIR / "nyx_oracle_priv.h"]
-    if force or not so.exists() or so.stat().st_mtime < max(f.stat().st_mtime for f in srcs):
+    so2 = _DIR / "libnyx_oracle_speed.so"
+    if force or not so.exists() or not so2.exists() or min(so.stat().st_mtime, so2.stat().st_mtime) < max(f.stat().st_mtime for f in srcs):
         subprocess.run(["make", "-C", str(_DIR), "-B" if force else "-s"], check=True, capture_output=True)
     return so
 
@@ -60,6 +62,8 @@ def lib():
         L.nyx_oracle_tableau.restype = C.c_int
         L.nyx_oracle_tableau.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(abi.c_double_p), C.POINTER(abi.c_double_p)]
         L.nyx_oracle_num_threads.restype = C.c_int
+        L.nyx_oracle_set_error_scale.restype = None
+        L.nyx_oracle_set_error_scale.argtypes = [C.c_double]
         # STM path (nyx_oracle_od.c)
         L.nyx_oracle_dual_eom.restype = C.c_int
         L.nyx_oracle_dual_eom.argtypes = [C.POINTER(abi.DynamicsC), C.c_int64, abi.c_double_p, abi.c_double_p, abi.c_double_p, abi.c_double_p]
@@ -86,12 +90,32 @@ def lib():
     return _LIB
 
 
+def speed_lib():
+    """The -O3 -march=x86-64-v3 -ffp-contract=fast build of the same sources (timing / sensitivity only, never the checker)."""
+    global _SPEED
+    if _SPEED is None:
+        build()
+        L = C.CDLL(str(_DIR / "libnyx_oracle_speed.so"))
+        vp = C.c_void_p
+        L.nyx_oracle_propagate_batch_event.restype = C.c_int
+        L.nyx_oracle_propagate_batch_event.argtypes = [
+            C.POINTER(abi.DynamicsC), C.POINTER(abi.IntegOpts), C.c_size_t, vp, vp, vp, C.c_int64, vp, vp, vp, vp, vp,
+            C.POINTER(abi.TrajSink), C.POINTER(abi.EventC), C.c_int]
+        _SPEED = L
+    return _SPEED
+
+
+def set_error_scale(scale: float = 1.0):
+    """Sensitivity probe of the parity build: every adaptive error norm is multiplied by `scale` (1.0 restores the restatement)."""
+    lib().nyx_oracle_set_error_scale(float(scale))
+
+
 def propagate_batch(dyn_c, opts_c, state_soa, consts_soa, epoch0_ns, end_epoch_ns, step_ns=None, n_threads=0, traj_capacity=0,
-                    event=None):
+                    event=None, speed_build=False):
     """Same contract as nyxb_propagate_batch[_traj] (include/nyxb.h) but on the CPU oracle.
     With traj_capacity > 0 returns a fifth element (epochs[cap][n], states[6][cap][n], count[n]); with
     event=(kind, value, trigger) the stop condition of until_nth_event applies and crossings[n] is appended."""
-    L = lib()
+    L = speed_lib() if speed_build else lib()
     state_soa = np.ascontiguousarray(state_soa, dtype=np.float64)
     consts_soa = np.ascontiguousarray(consts_soa, dtype=np.float64)
     epoch0_ns = np.ascontiguousarray(epoch0_ns, dtype=np.int64)
