@@ -52,6 +52,9 @@ def parse_args():
     p.add_argument("--degree", type=int, default=21)
     p.add_argument("--mode", default="fast", choices=["fast", "strict"])
     p.add_argument("--lanes", type=int, default=0)
+    p.add_argument("--kernel", default="auto", choices=["auto", "thread", "coop", "transposed"],
+                   help="kernel family (nyxb_engine_set_kernel); auto = the library's own dispatch")
+    p.add_argument("--tx-slice", type=int, default=0, help="transposed kernel: step attempts per time slice (0 = library default)")
     p.add_argument("--cpu-sample", type=int, default=0,
                    help="trajectories in the bounded CPU-baseline sample (0: 32 per host core, ~10 s of CPU work)")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -422,6 +425,10 @@ def main():
     eng = prop.engine(frame, almanac)
     if args.lanes:
         eng.set_lanes(args.lanes)
+    if args.kernel != "auto":
+        eng.set_kernel({"thread": nb.KERNEL_THREAD, "coop": nb.KERNEL_COOP, "transposed": nb.KERNEL_TRANSPOSED}[args.kernel])
+    if args.tx_slice:
+        eng.set_tx_tuning(args.tx_slice, 0)
     end = int(args.span_days * DAY)
 
     # pinned host inputs of this rank's shard (e2e leg) and HBM-resident copies (value leg)
@@ -527,7 +534,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "trajectories_total": n_total, "accepted_steps_per_pass": all_steps,
                        "rejected_attempts_per_pass": all_rej, "ok_trajectories": all_ok, "mode": args.mode,
-                       "lanes_per_trajectory": (1 if (args.mode == "fast" and not args.lanes and args.workload == "c2" and args.degree < 30 and n >= 65536) else eng.lanes()),
+                       "kernel": {nb.KERNEL_THREAD: "nyxb_k_thread (1 thread = 1 trajectory)", nb.KERNEL_COOP: f"nyxb_k_coop ({eng.lanes()} lanes = 1 trajectory)",
+                                  nb.KERNEL_TRANSPOSED: "nyxb_k_tx (1 CTA = 32 trajectories, lane = trajectory, warp = column position)"}.get(eng.last_kernel(), "?"),
                        "l2": "flushed between timed iterations (256 MiB write)",
                        "parallelism": f"ensemble-sharded x{world}, one all-gather of final states"},
             "e2e": {"value": e2e_value, "unit": "trajectory-steps/s", "h2d_bytes_per_step": n * (13 * 8 + 8) * world,

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define NYXB_ABI_VERSION 3 /* 2: nyxb_srp gained `estimate`; STM, filter and dispersion entry points.  3: nyxb_traj_resample[_dev], nyxb_event_locate[_dev] */
+#define NYXB_ABI_VERSION 4 /* 4: nyxb_engine_set_kernel / nyxb_engine_last_kernel / nyxb_engine_set_tx_tuning, nyxb_tx_table_dump.  Earlier: 2: nyxb_srp gained `estimate`; STM, filter and dispersion entry points.  3: nyxb_traj_resample[_dev], nyxb_event_locate[_dev] */
 
 /* ---- IntegratorMethod — propagators/rk_methods/mod.rs:65-79 (same order) ---- */
 enum nyxb_method {
@@ -455,6 +455,17 @@ int32_t nyxb_mvn_sample_dev(int32_t device, uint64_t seed, uint64_t first_index,
                             double* out_state_soa, double* out_dispersion_soa, void* cuda_stream);
 
 /* Tuning / introspection. */
+/* Kernel families behind nyxb_propagate_batch*.  AUTO picks by mode, degree and ensemble size:
+ *   THREAD      one thread per trajectory (no or low-degree gravity field; STRICT and FAST)
+ *   COOP        8 / 16 / 32 lanes of a warp per trajectory, harmonic sum split by columns over the lanes (STRICT and FAST)
+ *   TRANSPOSED  FAST only, degree 8..70: one CTA per set of 32 trajectories, lane = trajectory, warp = column position, persistent
+ *               CTAs with (set, time-slice) tickets — the kernel of large harmonics-dominated ensembles (>= 9 472 trajectories) */
+enum nyxb_kernel { NYXB_KERNEL_AUTO = 0, NYXB_KERNEL_THREAD = 1, NYXB_KERNEL_COOP = 2, NYXB_KERNEL_TRANSPOSED = 3 };
+int32_t nyxb_engine_set_kernel(nyxb_engine* eng, int32_t kernel);          /* enum nyxb_kernel; NYXB_RC_UNSUPPORTED if the setup cannot use it */
+int32_t nyxb_engine_last_kernel(const nyxb_engine* eng);                   /* family used by the last propagation launch */
+/* TRANSPOSED kernel: step attempts per time slice (default 64) and an upper bound on the persistent CTAs (0 = SMs x occupancy).
+ * Sets are only parked when there are more sets than CTAs. */
+int32_t nyxb_engine_set_tx_tuning(nyxb_engine* eng, int32_t slice_attempts, int32_t max_ctas);
 int32_t nyxb_engine_set_lanes(nyxb_engine* eng, int32_t lanes_per_trajectory); /* 0 = auto */
 int32_t nyxb_engine_get_lanes(const nyxb_engine* eng);
 int64_t nyxb_engine_launch_count(const nyxb_engine* eng); /* kernels launched so far */
@@ -470,6 +481,11 @@ double nyxb_measure_fp64_tflops(int32_t device, int32_t iters);
  * (see nyx_b200/csrc/nyxb_coop.h).  Used by the CPU tests to check the table algebra against a direct evaluation. */
 int32_t nyxb_coop_table_dump(const nyxb_gravity_field* field, int32_t lanes, int32_t* out_L, int32_t* out_kmax,
                              double* recs, int32_t* col_start, int32_t* col_m, double* colseed);
+
+/* Same for the transposed kernel (`positions` in {8,16}): recA [(n_rec+1)][4], recK [n_rec+2], colseed [N+2][4],
+ * sched [positions][2 + 2*kmax] = {first record, columns, (m, entries) per column} (see nyx_b200/csrc/nyxb_tx.h). */
+int32_t nyxb_tx_table_dump(const nyxb_gravity_field* field, int32_t positions, int32_t* out_n_rec, int32_t* out_kmax,
+                           double* recA, double* recK, double* colseed, int32_t* sched);
 
 int32_t nyxb_abi_version(void);
 const char* nyxb_last_error(void);

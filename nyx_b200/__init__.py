@@ -5,7 +5,7 @@ The package holds only what the hot path needs: ``csrc/`` (CUDA kernels + the C 
 There is NO CPU fallback: every propagate call goes through ``libnyxb.so`` on a CUDA device.
 """
 from . import abi
-from .abi import MODE_FAST, MODE_STRICT, NyxbLibraryMissing
+from .abi import KERNEL_AUTO, KERNEL_COOP, KERNEL_THREAD, KERNEL_TRANSPOSED, MODE_FAST, MODE_STRICT, NyxbLibraryMissing
 from .cosmic import DragData, Mass, Orbit, Spacecraft, SRPData, Unit, duration_to_seconds, epochs_to_utc_iso, pack_spacecraft, utc_iso_to_epochs
 from .dynamics import (AtmDensity, Drag, DynamicsError, GravityField, OrbitalDynamics, PointMasses, ShadowModel,
                        SolarPressure, SpacecraftDynamics)

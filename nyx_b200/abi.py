@@ -11,7 +11,8 @@ from pathlib import Path
 
 import numpy as np
 
-NYXB_ABI_VERSION = 3  # include/nyxb.h
+NYXB_ABI_VERSION = 4  # include/nyxb.h
+KERNEL_AUTO, KERNEL_THREAD, KERNEL_COOP, KERNEL_TRANSPOSED = 0, 1, 2, 3  # enum nyxb_kernel
 NYXB_MAX_BODIES = 8
 NYXB_CENTRAL_BODY = -1
 
@@ -299,6 +300,14 @@ def _declare(lib):
     lib.nyxb_measure_fp64_tflops.argtypes = [C.c_int32, C.c_int32]
     lib.nyxb_coop_table_dump.restype = C.c_int32
     lib.nyxb_coop_table_dump.argtypes = [C.POINTER(GravityFieldC), C.c_int32, c_int32_p, c_int32_p, vp, vp, vp, vp]
+    lib.nyxb_tx_table_dump.restype = C.c_int32
+    lib.nyxb_tx_table_dump.argtypes = [C.POINTER(GravityFieldC), C.c_int32, c_int32_p, c_int32_p, vp, vp, vp, vp]
+    lib.nyxb_engine_set_kernel.restype = C.c_int32
+    lib.nyxb_engine_set_kernel.argtypes = [vp, C.c_int32]
+    lib.nyxb_engine_last_kernel.restype = C.c_int32
+    lib.nyxb_engine_last_kernel.argtypes = [vp]
+    lib.nyxb_engine_set_tx_tuning.restype = C.c_int32
+    lib.nyxb_engine_set_tx_tuning.argtypes = [vp, C.c_int32, C.c_int32]
     lib.nyxb_abi_version.restype = C.c_int32
     lib.nyxb_abi_version.argtypes = []
     lib.nyxb_last_error.restype = C.c_char_p
@@ -328,6 +337,10 @@ EXPORTED_SYMBOLS = [
     "nyxb_engine_last_kernel_ms",
     "nyxb_measure_fp64_tflops",
     "nyxb_coop_table_dump",
+    "nyxb_tx_table_dump",
+    "nyxb_engine_set_kernel",
+    "nyxb_engine_last_kernel",
+    "nyxb_engine_set_tx_tuning",
     "nyxb_abi_version",
     "nyxb_last_error",
 ]

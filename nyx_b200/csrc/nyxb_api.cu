@@ -11,6 +11,7 @@
 #include <map>
 
 #include "nyxb_coop.h"
+#include "nyxb_tx.h"
 #include "nyxb_device.cuh"
 #include "nyxb_od.cuh"
 #include "nyxb_tableaux.h"
@@ -22,8 +23,6 @@ extern "C" cudaError_t nyxb_launch_thread_strict(const DevSetup*, size_t, const 
 extern "C" cudaError_t nyxb_launch_thread_fast(const DevSetup*, size_t, const double*, const double*, const long long*,
                                                long long, long long*, double*, long long*, nyxb_details*, int*, int,
                                                const DevSink*, cudaStream_t);
-extern "C" cudaError_t nyxb_launch_thread_fastc(const DevSetup*, size_t, const double*, const double*, const long long*, long long, long long*,
-                                                double*, long long*, nyxb_details*, int*, int, const DevSink*, const double*, size_t, cudaStream_t);
 extern "C" double nyxb_fp64_probe(int device, int iters);
 extern "C" cudaError_t nyxb_launch_od_coop(const DevSetup*, const DevOd*, const int*, size_t, const double*, const double*, const long long*,
                                            double*, long long*, nyxb_details*, int*, cudaStream_t);
@@ -71,13 +70,20 @@ struct nyxb_engine {
     size_t rec_n = 0;        // the recording resident in d_sink: trajectories and capacity (nyxb_traj_resample with sink == NULL)
     long long rec_cap = 0;
     std::vector<double> h_cnm, h_snm;      // host copies for building cooperative tables lazily
-    std::vector<double> h_colrec;          // column-walk records (experimental constant-bank kernel, NYXB_K1_CONST=1)
     std::map<int, DevCoop> coop;           // lanes -> device tables
     std::map<int, DevCoopStrict> scoop;    // lanes -> STRICT cooperative schedules
+    int kernel = NYXB_KERNEL_AUTO;         // nyxb_engine_set_kernel
+    int last_kernel = NYXB_KERNEL_AUTO;    // family the last launch used
+    std::map<int, DevTx> tx;               // positions -> tables of the transposed kernel
+    int tx_slice = 64;                     // step attempts per time slice of the persistent transposed kernel
+    int tx_max_ctas = 0;                   // 0: every resident slot (SMs x occupancy); tests shrink it to force time slicing
+    size_t txq_bytes = 0;                  // grow-only queue + parking workspace of the transposed kernel
+    unsigned char* d_txq = nullptr;
+    int sms = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ~nyxb_engine() {
         for (void* p : dev_allocs) cudaFree(p);
-        cudaFree(d_f64); cudaFree(d_i64); cudaFree(d_det); cudaFree(d_status); cudaFree(d_sink);
+        cudaFree(d_f64); cudaFree(d_i64); cudaFree(d_det); cudaFree(d_status); cudaFree(d_sink); cudaFree(d_txq);
         if (stream) cudaStreamDestroy(stream);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -269,7 +275,6 @@ extern "C" nyxb_engine* nyxb_engine_create(const nyxb_dynamics* dyn, const nyxb_
                 for (int j = k + 1; j <= N + 1; ++j) { push(k, j); if (two) push(k + 1, j); }
             }
             cr.insert(cr.end(), 16, 0.0);           // two null records: targets of the last prefetches
-            e->h_colrec = cr;
             S.grav.colrec = upload(e, cr.data(), cr.size());
             S.grav.ncols = ncols;
             if (!S.grav.colrec) { set_err("gravity table upload failed"); delete e; return nullptr; }
@@ -351,10 +356,90 @@ static const DevCoop* get_coop(nyxb_engine* e, int lanes) {
     return &(e->coop[lanes] = d);
 }
 
+static const DevTx* get_tx(nyxb_engine* e, int P) {
+    auto it = e->tx.find(P);
+    if (it != e->tx.end()) return &it->second;
+    TxHost h;
+    nyxb_tx_build_host(e->S.grav.N, e->S.grav.M, e->h_cnm.data(), e->h_snm.data(), P, h);
+    std::vector<unsigned char> blob(nyxb_tx_pack_blob(&h, e->S.grav.N, nullptr));
+    nyxb_tx_pack_blob(&h, e->S.grav.N, blob.data());
+    DevTx d;
+    d.P = h.P; d.n_rec = h.n_rec; d.kmax = h.kmax;
+    d.recA = reinterpret_cast<const double*>(upload(e, blob.data(), blob.size()));
+    if (!d.recA) return nullptr;
+    return &(e->tx[P] = d);
+}
+
+// positions of the transposed kernel for this field: 8 warps per set up to degree 40, 16 beyond (shared-memory footprint of the table)
+static int tx_positions(const nyxb_engine* e) { return e->S.grav.N <= 40 ? 8 : 16; }
+
+static bool tx_supported(const nyxb_engine* e) {
+    return e->mode == NYXB_MODE_FAST && e->S.has_grav && e->S.grav.N >= 8 && e->S.grav.N <= 70;
+}
+
+// Transposed kernel (nyxb_tx.cu): persistent CTAs, one set of 32 trajectories per CTA, (set, time-slice) tickets.
+static int32_t launch_tx(nyxb_engine* e, size_t n, const double* state, const double* consts, const int64_t* epoch0, int64_t end_epoch,
+                         int64_t* step_io, double* out_state, int64_t* out_epoch, nyxb_details* out_details, int32_t* out_status,
+                         const DevSink& sink, cudaStream_t stream) {
+    const DevTx* tx = get_tx(e, tx_positions(e));
+    if (!tx) { set_err("transposed-kernel table upload failed"); return NYXB_RC_CUDA; }
+    size_t smem = 0;
+    const int occ = nyxb_tx_occupancy(&e->S, tx, &smem);
+    if (occ < 1) { set_err("transposed kernel: tables do not fit in shared memory"); return NYXB_RC_UNSUPPORTED; }
+    if (!e->sms) CUDA_TRY(cudaDeviceGetAttribute(&e->sms, cudaDevAttrMultiProcessorCount, e->device));
+    const size_t n_sets = (n + 31) / 32;
+    size_t slots = (size_t)e->sms * occ;
+    if (e->tx_max_ctas > 0 && (size_t)e->tx_max_ctas < slots) slots = (size_t)e->tx_max_ctas;
+    const int grid = (int)std::min(n_sets, slots);
+    // workspace: [ticket u64 | n_finished i32 (+pad) | slices_done n_sets | finished n_sets | ws_step n i64 | ws_f64 2n | ws_flags n | details n]
+    const size_t ctl_bytes = (16 + 8 * n_sets + 15) & ~(size_t)15;
+    const size_t need = ctl_bytes + n * (8 + 16 + 8) + n * sizeof(nyxb_details);
+    if (need > e->txq_bytes) {
+        cudaFree(e->d_txq); e->d_txq = nullptr; e->txq_bytes = 0;
+        CUDA_TRY(cudaMalloc(&e->d_txq, need));
+        e->txq_bytes = need;
+    }
+    CUDA_TRY(cudaMemsetAsync(e->d_txq, 0, ctl_bytes, stream));
+    DevTxQueue q;
+    q.ticket = reinterpret_cast<unsigned long long*>(e->d_txq);
+    q.n_finished = reinterpret_cast<int*>(e->d_txq + 8);
+    q.slices_done = reinterpret_cast<int*>(e->d_txq + 16);
+    q.finished = q.slices_done + n_sets;
+    unsigned char* ws = e->d_txq + ctl_bytes;
+    q.ws_step = reinterpret_cast<long long*>(ws);
+    q.ws_f64 = reinterpret_cast<double*>(ws + 8 * n);
+    q.ws_flags = reinterpret_cast<int*>(ws + 24 * n);
+    q.details = out_details ? out_details : reinterpret_cast<nyxb_details*>(ws + 32 * n);
+    q.n_sets = (int)n_sets;
+    q.slice = (n_sets > slots) ? e->tx_slice : 0;   // every set resident: no parking
+    cudaError_t err = nyxb_launch_tx(&e->S, tx, &q, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io, out_state,
+                                     (long long*)out_epoch, out_status, &sink, grid, stream);
+    if (err != cudaSuccess) { set_err(std::string("kernel launch: ") + cudaGetErrorString(err)); return NYXB_RC_CUDA; }
+    e->launches += 1;
+    e->last_kernel = NYXB_KERNEL_TRANSPOSED;
+    return NYXB_RC_OK;
+}
+
+// kernel family for this call (nyxb_engine_set_kernel overrides the automatic choice)
+static int pick_kernel(const nyxb_engine* e, size_t n) {
+    if (e->kernel == NYXB_KERNEL_TRANSPOSED) return tx_supported(e) ? NYXB_KERNEL_TRANSPOSED : NYXB_KERNEL_COOP;
+    if (e->kernel != NYXB_KERNEL_AUTO) return e->kernel;
+    if (e->lanes > 0) return e->lanes == 1 ? NYXB_KERNEL_THREAD : NYXB_KERNEL_COOP;
+    // auto: the transposed kernel needs every resident CTA busy with a set of 32 trajectories (2 CTAs per SM: 9 472 trajectories on
+    // 148 SMs); smaller ensembles keep the lane-cooperative kernel, whose unit is one trajectory per 8 / 16 / 32 lanes
+    if (tx_supported(e) && e->S.grav.N <= 40 && n >= (size_t)9472) return NYXB_KERNEL_TRANSPOSED;
+    return NYXB_KERNEL_AUTO;
+}
+
 static int32_t launch(nyxb_engine* e, size_t n, const double* state, const double* consts, const int64_t* epoch0,
                       int64_t end_epoch, int64_t* step_io, double* out_state, int64_t* out_epoch,
                       nyxb_details* out_details, int32_t* out_status, const DevSink& sink, cudaStream_t stream) {
+    if (pick_kernel(e, n) == NYXB_KERNEL_TRANSPOSED)
+        return launch_tx(e, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, sink, stream);
     int lanes = pick_lanes(e, n);
+    if (e->kernel == NYXB_KERNEL_THREAD) lanes = 1;
+    if (e->kernel == NYXB_KERNEL_COOP && lanes == 1 && e->S.has_grav) lanes = (e->S.grav.N >= 48) ? 32 : ((e->S.grav.N >= 30) ? 16 : 8);
+    e->last_kernel = lanes > 1 ? NYXB_KERNEL_COOP : NYXB_KERNEL_THREAD;
     cudaError_t err;
     if (lanes > 1 && e->mode == NYXB_MODE_STRICT) {
         const DevCoopStrict* cs = get_scoop(e, lanes);
@@ -364,23 +449,15 @@ static int32_t launch(nyxb_engine* e, size_t n, const double* state, const doubl
     } else if (lanes > 1) {
         const DevCoop* cp = get_coop(e, lanes);
         if (!cp) { set_err("cooperative table upload failed"); return NYXB_RC_CUDA; }
-        // two trajectories per lane group once the ensemble is large enough to still fill the SMs with half the threads
-        int T = 1;  // measured on B200: T = 1 beats T = 2 at both 10 000 and 100 000 trajectories (7.2e7 vs 5.7e7, 8.8e7 vs 7.6e7 steps/s)
-        if (const char* ev = getenv("NYXB_COOP_T")) { int v = atoi(ev); if (v == 1 || v == 2) T = v; }
-        err = nyxb_launch_coop(&e->S, cp, T, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io,
+        // one trajectory per lane group: register blocking over two trajectories (T = 2) was measured slower at every ensemble
+        // size in two rounds (profiles/r02a_k2_variants.md) and is no longer dispatched
+        err = nyxb_launch_coop(&e->S, cp, 1, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io,
                                out_state, (long long*)out_epoch, out_details, out_status, &sink, stream);
     } else if (e->mode == NYXB_MODE_STRICT) {
         err = nyxb_launch_thread_strict(&e->S, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io,
                                         out_state, (long long*)out_epoch, out_details, out_status, 64, &sink, stream);
     } else {
-        int blk = 64;
-        if (const char* ev = getenv("NYXB_K1_BLOCK")) { int v = atoi(ev); if (v == 32 || v == 64 || v == 128) blk = v; }
-        const char* kc = getenv("NYXB_K1_CONST");   // experimental: records through the constant bank
-        if (kc && kc[0] == '1' && e->S.has_grav && !e->h_colrec.empty() && e->h_colrec.size() <= 7680)
-            err = nyxb_launch_thread_fastc(&e->S, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io, out_state,
-                                           (long long*)out_epoch, out_details, out_status, blk, &sink, e->h_colrec.data(),
-                                           e->h_colrec.size(), stream);
-        else
+        const int blk = 64;   // 32 / 128 threads per CTA measured no better (profiles/README.md, r01n)
         err = nyxb_launch_thread_fast(&e->S, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io,
                                       out_state, (long long*)out_epoch, out_details, out_status, blk, &sink, stream);
     }
@@ -890,6 +967,24 @@ extern "C" int32_t nyxb_engine_set_lanes(nyxb_engine* eng, int32_t lanes) {
     eng->lanes = lanes;
     return NYXB_RC_OK;
 }
+extern "C" int32_t nyxb_engine_set_kernel(nyxb_engine* eng, int32_t kernel) {
+    if (!eng) return NYXB_RC_BAD_ARG;
+    if (kernel < NYXB_KERNEL_AUTO || kernel > NYXB_KERNEL_TRANSPOSED) { set_err("unknown kernel family"); return NYXB_RC_BAD_ARG; }
+    if (kernel == NYXB_KERNEL_TRANSPOSED && !tx_supported(eng)) {
+        set_err("the transposed kernel needs FAST mode and a gravity field of degree 8..70");
+        return NYXB_RC_UNSUPPORTED;
+    }
+    if (kernel == NYXB_KERNEL_COOP && !eng->S.has_grav) { set_err("cooperative lanes need a gravity field"); return NYXB_RC_UNSUPPORTED; }
+    eng->kernel = kernel;
+    return NYXB_RC_OK;
+}
+extern "C" int32_t nyxb_engine_last_kernel(const nyxb_engine* eng) { return eng ? eng->last_kernel : 0; }
+extern "C" int32_t nyxb_engine_set_tx_tuning(nyxb_engine* eng, int32_t slice_attempts, int32_t max_ctas) {
+    if (!eng || slice_attempts < 1 || max_ctas < 0) { set_err("slice_attempts >= 1, max_ctas >= 0"); return NYXB_RC_BAD_ARG; }
+    eng->tx_slice = slice_attempts;
+    eng->tx_max_ctas = max_ctas;
+    return NYXB_RC_OK;
+}
 extern "C" int32_t nyxb_engine_get_lanes(const nyxb_engine* eng) { return eng ? pick_lanes(eng, 0) : 0; }
 extern "C" int64_t nyxb_engine_launch_count(const nyxb_engine* eng) { return eng ? eng->launches : 0; }
 extern "C" double nyxb_engine_last_kernel_ms(const nyxb_engine* eng) { return eng ? eng->last_ms : 0.0; }
@@ -907,6 +1002,22 @@ extern "C" int32_t nyxb_coop_table_dump(const nyxb_gravity_field* f, int32_t lan
     if (col_start) std::copy(h.col_start.begin(), h.col_start.end(), col_start);
     if (col_m) std::copy(h.col_m.begin(), h.col_m.end(), col_m);
     if (colseed) std::copy(h.colseed.begin(), h.colseed.end(), colseed);
+    return NYXB_RC_OK;
+}
+
+extern "C" int32_t nyxb_tx_table_dump(const nyxb_gravity_field* f, int32_t positions, int32_t* out_n_rec, int32_t* out_kmax,
+                                      double* recA, double* recK, double* colseed, int32_t* sched) {
+    if (!f || !f->c_nm || !f->s_nm || f->degree < 2 || (positions != 8 && positions != 16) || !out_n_rec || !out_kmax) {
+        set_err("bad argument");
+        return NYXB_RC_BAD_ARG;
+    }
+    TxHost h;
+    nyxb_tx_build_host(f->degree, f->order, f->c_nm, f->s_nm, positions, h);
+    *out_n_rec = h.n_rec; *out_kmax = h.kmax;
+    if (recA) std::copy(h.recA.begin(), h.recA.end(), recA);
+    if (recK) std::copy(h.recK.begin(), h.recK.end(), recK);
+    if (colseed) std::copy(h.colseed.begin(), h.colseed.end(), colseed);
+    if (sched) std::copy(h.sched.begin(), h.sched.end(), sched);
     return NYXB_RC_OK;
 }
 

@@ -31,8 +31,8 @@
 // host: column -> lane schedule (longest-processing-time greedy) and record table
 // ------------------------------------------------------------------------------------------------
 
-// NYXB_COOP_SCHED=aligned (experimental, off by default): keep the bin packing, but reorder each lane's columns and insert idle
-// gaps (null records) so that column STARTS of different lane positions fall on the same entries.  The kernel executes its
+// Aligned column schedule (measured +6 % on the 21x21 benchmark, profiles/r02a_k2_variants.md): keep the bin packing, but reorder
+// each lane's columns and insert idle gaps (null records) so that column STARTS of different lane positions fall on the same entries.  The kernel executes its
 // column-switch block whenever ANY lane of the warp starts a column, so what costs is the number of DISTINCT start entries, not
 // the number of columns.  Lanes with the fewest columns fix the boundary set first; every other lane searches
 // the orders of its columns (multiset permutations) and, before each column, either continues where the previous one ended or
@@ -104,26 +104,14 @@ void nyxb_coop_build_host(int N, int M, const double* c_nm, const double* s_nm, 
     // column N+1 keeps one null entry (only its seed W term is non-zero).  Lengths are padded to EVEN: the kernel walks
     // two entries per iteration and tests for a column switch once per pair.
     auto col_len = [&](int m) { int l = std::max(N + 1 - m, 1); return l + (l & 1); };
-    // column -> lane schedule.  Default: first-fit-decreasing bin packing (every lane walks at most L entries, column
-    // boundaries differ per lane).  NYXB_COOP_SCHED=rounds: G columns per round, all lanes start their k-th column
-    // at the same entry (uniform boundaries, shorter columns padded with null records).
+    // column -> lane schedule: first-fit-decreasing bin packing (every lane walks at most L entries), then the column starts of
+    // the lane positions are aligned (align_boundaries)
     std::vector<int> order(mcols);
     std::iota(order.begin(), order.end(), 1);  // already sorted by decreasing length (N + 2 - m)
     std::vector<int> load(G, 0);
     std::vector<std::vector<int>> cols(G);
     std::vector<std::vector<int>> starts(G);
-    const char* sched = getenv("NYXB_COOP_SCHED");
-    const bool rounds = sched && std::string(sched) == "rounds";
-    const bool aligned = sched && std::string(sched) == "aligned";
-    if (rounds) {
-        int base = 0;
-        for (size_t i = 0; i < order.size(); i += G) {
-            int len = col_len(order[i]);  // longest of the round
-            for (int j = 0; j < G && i + j < order.size(); ++j) { cols[j].push_back(order[i + j]); starts[j].push_back(base); }
-            base += len;
-        }
-        for (int j = 0; j < G; ++j) load[j] = base;
-    } else {
+    {
         // first-fit decreasing into G bins of capacity cap, smallest feasible even cap (LPT alone leaves 34 where 32 fits for 21x21)
         int total = 0;
         for (int m : order) total += col_len(m);
@@ -144,7 +132,7 @@ void nyxb_coop_build_host(int N, int M, const double* c_nm, const double* s_nm, 
             }
             if (ok) break;
         }
-        if (aligned) align_boundaries(cap, col_len, cols, starts, load);
+        align_boundaries(cap, col_len, cols, starts, load);
     }
     out.G = G;
     out.L = *std::max_element(load.begin(), load.end());
@@ -223,7 +211,7 @@ extern "C" cudaError_t nyxb_launch_coop(const DevSetup* S, const DevCoop* Cp, in
                                         long long* step_io, double* out_state, long long* out_epoch,
                                         nyxb_details* out_details, int* out_status, const DevSink* sink, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    if (T != 1 && T != 2) return cudaErrorInvalidValue;
+    if (T != 1) return cudaErrorInvalidValue;
     switch (Cp->G) {
     case 8: return nyxb_launch_coop_g8(S, Cp, T, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, sink, stream);
     case 16: return nyxb_launch_coop_g16(S, Cp, T, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, sink, stream);

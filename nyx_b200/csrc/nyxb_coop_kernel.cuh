@@ -679,7 +679,7 @@ cudaError_t nyxb_launch_coop_g(const DevSetup* S, const DevCoop* Cp, int T, size
     const size_t smem = tab ? with_table : grp_bytes;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
 #define NYXB_COOP_GO(TT, TAB) launch_gt<G, TT, TAB>(S, Cp, n, smem, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, sink, stream)
-    if (T == 2) return tab ? NYXB_COOP_GO(2, true) : NYXB_COOP_GO(2, false);
+    if (T != 1) return cudaErrorInvalidValue;   // T = 2 (register blocking over two trajectories) lost at every size and is not instantiated
     return tab ? NYXB_COOP_GO(1, true) : NYXB_COOP_GO(1, false);
 #undef NYXB_COOP_GO
 }

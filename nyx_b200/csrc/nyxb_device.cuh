@@ -397,14 +397,6 @@ __device__ inline void grav_accel_rows(const DevGrav& g, long long t_ns, const d
     for (int i = 0; i < 3; ++i) acc[i] = (R[i] * ab0 + R[3 + i] * ab1) + R[6 + i] * ab2;
 }
 
-#ifndef NYXB_CONST_TABLE
-#define NYXB_CONST_TABLE 0
-#endif
-#define NYXB_CONST_DOUBLES 7680   /* 60 KB of the 64 KB constant bank: column-walk records up to degree ~41 */
-#if NYXB_CONST_TABLE
-__constant__ double nyxb_c_colrec[NYXB_CONST_DOUBLES];
-#endif
-
 #if !NYXB_STRICT
 // GravityField::eom for one trajectory on one thread, FAST mode: the double sum walked by COLUMNS of the derived-Legendre
 // triangle.  Each A[j][k] is produced by its column recursion in a register and consumed once: the four sums of the
@@ -431,16 +423,8 @@ __device__ inline void grav_accel_cols(const DevGrav& g, long long t_ns, const d
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     // Columns are walked in PAIRS (k, k+1): two independent recursion chains per thread hide the FP64 latency, both use the same
     // rr_j.  Records come in walk order and are software-pipelined one entry ahead (the table ends with a null record).
-#if NYXB_CONST_TABLE
-    // experimental build (nyxb_kernels_fastc.o): every thread of a warp walks the same (k, j) sequence, so the records are
-    // warp-uniform — read them from the constant bank (uniform datapath) instead of spending 64 B per lane and entry of the
-    // LSU return path, which is what bounds this kernel
-    const double2* __restrict__ p = reinterpret_cast<const double2*>(nyxb_c_colrec);
-#define NYXB_REC_LD(x) (*(x))
-#else
     const double2* __restrict__ p = reinterpret_cast<const double2*>(g.colrec);
 #define NYXB_REC_LD(x) __ldg(x)
-#endif
     double2 n12 = NYXB_REC_LD(p), n34 = NYXB_REC_LD(p + 1), n56 = NYXB_REC_LD(p + 2), nbc = NYXB_REC_LD(p + 3);
     p += 4;
 #ifndef NYXB_COLS_PF

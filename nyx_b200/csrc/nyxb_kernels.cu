@@ -18,9 +18,6 @@
 #if NYXB_STRICT
 #define NYXB_KTHREAD nyxb_k_thread_strict
 #define NYXB_LAUNCH_THREAD nyxb_launch_thread_strict
-#elif NYXB_CONST_TABLE
-#define NYXB_KTHREAD nyxb_k_thread_fastc
-#define NYXB_LAUNCH_THREAD nyxb_launch_thread_fastc_impl
 #else
 #define NYXB_KTHREAD nyxb_k_thread_fast
 #define NYXB_LAUNCH_THREAD nyxb_launch_thread_fast
@@ -241,18 +238,3 @@ extern "C" cudaError_t NYXB_LAUNCH_THREAD(const DevSetup* S, size_t n, const dou
     return cudaGetLastError();
 }
 
-#if NYXB_CONST_TABLE
-// experimental: the column-walk records travel through the constant bank; they are (re)loaded in stream order before every launch
-// (16 KB for 21x21), so engines with different fields can alternate freely
-extern "C" cudaError_t nyxb_launch_thread_fastc(const DevSetup* S, size_t n, const double* state, const double* consts,
-                                                const long long* epoch0, long long end_epoch, long long* step_io,
-                                                double* out_state, long long* out_epoch, nyxb_details* out_details,
-                                                int* out_status, int block, const DevSink* sink, const double* host_colrec,
-                                                size_t colrec_doubles, cudaStream_t stream) {
-    if (!S->has_grav || colrec_doubles > NYXB_CONST_DOUBLES) return cudaErrorInvalidValue;
-    cudaError_t e = cudaMemcpyToSymbolAsync(nyxb_c_colrec, host_colrec, colrec_doubles * sizeof(double), 0, cudaMemcpyHostToDevice, stream);
-    if (e != cudaSuccess) return e;
-    return nyxb_launch_thread_fastc_impl(S, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status,
-                                         block, sink, stream);
-}
-#endif

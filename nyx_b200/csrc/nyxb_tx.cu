@@ -1,0 +1,837 @@
+// nyxb_tx.cu — TRANSPOSED cooperative propagation kernel (FAST mode): lane = trajectory, warp = column position.
+//
+//   * One CTA of P warps integrates a SET of 32 trajectories (lane l of every warp = trajectory l of the set).  The harmonic
+//     double sum (gravity_field.rs:217-249) is split by COLUMNS of the derived-Legendre triangle over the P warps; all 32 lanes of
+//     a warp walk the same entries, so the 40-byte coefficient record of an entry is ONE warp-uniform shared-memory read
+//     (2 x LDS.128 + LDS.64 with a single address: 5 clk of the shared-memory pipe per warp-entry against 10 clk for the
+//     lane-varying reads of nyxb_k_coop, profiles/r02a_smem_probe.txt), column boundaries are uniform branches, and no lane idles.
+//   * The column walk is software-pipelined by one entry: the six accumulations of entry n use Q[n], which was produced one
+//     iteration earlier, while the only dependent FP64 chain is the one DFMA that advances the recursion
+//     Q[n+1] = (2n+1) u Q[n] - (n+m)(n-m) r^2 Q[n-1] — 12 independent FP64 instructions sit between two links of the chain
+//     (the FP64 latency measured on B200 is ~14 clk, profiles/r02a_opnd_probe.txt).  13 FP64 instructions per entry.
+//   * Roles around the walk: warps 0..5 own one state component each (RK stage algebra, stage derivatives kst[stage][c][lane] in
+//     shared memory), warp 6 evaluates the body-fixed DCM of the stage epoch, warp 7 runs the error norm and the step-size
+//     controller.  Everything that lives across phases is in shared memory, so the walk's registers are its own.
+//     Two CTA barriers per right-hand side (stage state ready / partial sums ready) and two per step.
+//   * Persistent CTAs pull (set, time-slice) tickets from a global counter: with fewer resident CTAs than sets every SM stays
+//     busy to the end (10 000 trajectories = 313 sets on 296 resident CTAs would otherwise run 17 CTAs alone in a second wave).
+//     A parked set keeps its state in the output arrays plus a small workspace; a finished trajectory inside a set keeps stepping
+//     on its own scratch without committing anything, exactly as in nyxb_k_coop.
+//   * HBM: initial state in, final state out, ~200 B per trajectory and slice of parking traffic.
+//
+// Reference behaviour: instance.rs:87-262, 343-352, 358-493 (propagate / single_step / derive), spacecraft.rs:191-310 (eom),
+// gravity_field.rs:148-268.  FMA contraction and the regrouped summation make this a tolerance-parity path (same class as
+// nyxb_k_coop: < 1e-6 km over the benchmark span, tests/test_gpu_baseline_spans.py).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "nyxb_tx.h"
+
+#ifndef TX_MINB
+#define TX_MINB 2   /* resident CTAs per SM the kernel is compiled for (register cap 65536 / (256 * TX_MINB)) */
+#endif
+
+namespace {
+constexpr int NL = 32;
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---- per-trajectory controller state kept in shared memory ([field][lane])
+enum { TXF_H = 0, TXF_ERR, TXF_CR, TXF_CD, TXF_PM, TXF_DRY, TXF_EXTRA, TXF_SRPA, TXF_DRAGA, TXF_EVPREV, TXF_COUNT };
+enum { TXI_EPOCH = 0, TXI_STEP, TXI_PREV_STEP, TXI_DET_STEP, TXI_NSTEPS, TXI_NREJ, TXI_NRHS, TXI_COUNT };
+enum { TXW_FLAGS = 0, TXW_STATUS, TXW_RC, TXW_ATT, TXW_EVCNT, TXW_ACC, TXW_RCST, TXW_COUNT };
+enum { F_FIXED = 1, F_PREVFIXED = 2, F_RETRY = 4, F_LAST = 8, F_DONE = 16, F_BACK = 32, F_VALID = 64 };
+
+struct TxLayout {
+    unsigned blob, ys, rm, part, kst, nxt, er, ycur, f64, i64, i32, total;
+};
+__host__ __device__ inline TxLayout tx_layout(unsigned blob_bytes, int P) {
+    TxLayout L;
+    unsigned o = 0;
+    L.blob = o; o += (blob_bytes + 127u) & ~127u;
+    L.ys = o; o += 2 * 6 * NL * 8;      // double-buffered by stage parity
+    L.rm = o; o += 2 * 9 * NL * 8;
+    L.part = o; o += P * 4 * NL * 8;
+    L.kst = o; o += NYXB_MAX_STAGES * 6 * NL * 8;
+    L.nxt = o; o += 6 * NL * 8;
+    L.er = o; o += 6 * NL * 8;
+    L.ycur = o; o += 6 * NL * 8;
+    L.f64 = o; o += TXF_COUNT * NL * 8;
+    L.i64 = o; o += TXI_COUNT * NL * 8;
+    L.i32 = o; o += TXW_COUNT * NL * 4;
+    L.total = o;
+    return L;
+}
+
+struct TxSm {   // typed views of the dynamic shared memory
+    const double2* recA; const double* recK; const double* colseed; const int* sched;
+    double *ys, *rm, *part, *kst, *nxt, *er, *ycur, *f64;
+    long long* i64;
+    int* i32;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tx_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tx_mbar_expect(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tx_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tx_mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TX_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TX_WAIT_DONE;\n"
+        "bra TX_WAIT_LOOP;\n"
+        "TX_WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// third bodies + SRP + drag for one trajectory (cold path of the harmonics-dominated ensembles this kernel serves)
+__device__ __noinline__ int tx_extra(const DevSetup& S, double dry_mass, double extra_mass, double srp_area, double drag_area,
+                                     long long t_ns, const double y[9], double acc[3]) {
+    const double mass = dry_mass + y[8] + extra_mass;
+    const bool has_force = S.has_srp || S.has_drag;
+    if (has_force && !(mass > 0.0)) return NYXB_ERR_MASSLESS;
+    double bpos[NYXB_MAX_BODIES][3];
+    const int rc = accel_point_masses(S, t_ns, y, bpos, acc);
+    if (rc) return rc;
+    if (has_force) accel_post(S, t_ns, y, bpos, mass, srp_area, drag_area, acc);
+    return 0;
+}
+
+// ---- one column of the walk.  (a01, a23, kk) hold the NEXT record (prefetched); A / K point at it.
+__device__ __forceinline__ void tx_column(const double2*& A, const double*& K, double2& a01, double2& a23, double& kk, int len,
+                                          double q, double pd1, double pd2, double al, double ub, double r2, double rr, double ii,
+                                          double& X, double& Y, double& Z, double& W) {
+    double Q = q, Qm1 = 0.0, be = 0.0;
+    double kp = 1.0, p3p = pd1, p4p = pd2;   // "previous record" of the first entry: the column's seed W term (kappa = 1)
+    double S1 = 0.0, S2 = 0.0, S3 = 0.0, S4 = 0.0, S5 = 0.0, S6 = 0.0;
+#pragma unroll 2
+    for (int e = 0; e < len; ++e) {
+        const double2 c01 = a01, c23 = a23;
+        const double ck = kk;
+        A += 2; K += 1;
+        a01 = A[0]; a23 = A[1]; kk = K[0];   // the table ends with a null record
+        const double t1 = al * ub;
+        const double t2 = (be * r2) * Qm1;
+        const double Qn = fma(t1, Q, -t2);   // Q[n+1] = (2n+1) u Q[n] - (n+m)(n-m) r^2 Q[n-1]: the only dependent chain
+        S1 = fma(Q, c01.x, S1);
+        S2 = fma(Q, c01.y, S2);
+        S3 = fma(Q, c23.x, S3);
+        S4 = fma(Q, c23.y, S4);
+        const double wv = kp * Q;            // W term of degree n: kappa(n-1) Q[n] (p3, p4)(n-1)
+        S5 = fma(wv, p3p, S5);
+        S6 = fma(wv, p4p, S6);
+        kp = ck; p3p = c23.x; p4p = c23.y;
+        be += al; al += 2.0;                 // (n+1)^2 - m^2 = n^2 - m^2 + (2n+1)
+        Qm1 = Q; Q = Qn;
+    }
+    const double wv = kp * Q;                // W term carried by the column's last entry
+    S5 = fma(wv, p3p, S5);
+    S6 = fma(wv, p4p, S6);
+    // close the column: apply its (cos, sin)((m-1) lambda) cos^(m-1)(phi)
+    X = fma(rr, S1, fma(ii, S2, X));
+    Y = fma(rr, S2, fma(-ii, S1, Y));
+    Z = fma(rr, S3, fma(ii, S4, Z));
+    W = fma(rr, S5, fma(ii, S6, W));
+}
+
+// ---- instance.rs:149-196: choose the step of the next attempt (regular, or the final fixed step to the stop time)
+__device__ __forceinline__ void tx_pick_step(TxSm& sm, int lane, long long stop) {
+    int fl = sm.i32[TXW_FLAGS * NL + lane];
+    if (!(fl & (F_DONE | F_RETRY))) {
+        const long long epoch = sm.i64[TXI_EPOCH * NL + lane];
+        long long step_ns = sm.i64[TXI_STEP * NL + lane];
+        const bool back = fl & F_BACK;
+        fl &= ~(F_LAST | F_PREVFIXED);
+        if (fl & F_FIXED) fl |= F_PREVFIXED;
+        sm.i64[TXI_PREV_STEP * NL + lane] = step_ns;
+        if ((!back && epoch + step_ns > stop) || (back && epoch + step_ns <= stop)) {
+            if (stop == epoch) {
+                fl |= F_DONE;
+            } else {
+                step_ns = stop - epoch;
+                fl |= F_FIXED | F_LAST;
+                sm.i64[TXI_STEP * NL + lane] = step_ns;
+            }
+        }
+        if (!(fl & F_DONE)) {
+            sm.i32[TXW_ATT * NL + lane] = 1;
+            sm.f64[TXF_H * NL + lane] = dur_to_seconds(step_ns);
+        }
+        sm.i32[TXW_FLAGS * NL + lane] = fl;
+    }
+}
+
+// ---- error norm, accept / reject, next step (instance.rs:416-490), single_step bookkeeping (instance.rs:343-352), recording
+// and stop condition; executed by the controller warp for its 32 trajectories
+__device__ __noinline__ void tx_controller(const DevSetup& S, const DevSink& sink, TxSm sm, int lane, size_t n, size_t tr, int stages) {
+    int fl = sm.i32[TXW_FLAGS * NL + lane];
+    sm.i32[TXW_ACC * NL + lane] = 0;
+    if (fl & F_DONE) return;
+    const int rcst = sm.i32[TXW_RCST * NL + lane];   // failure of a right-hand side: code | (stage + 1) << 8
+    if (rcst) {
+        sm.i64[TXI_NRHS * NL + lane] += (rcst >> 8);
+        sm.i32[TXW_RC * NL + lane] = rcst & 0xff;
+        sm.i32[TXW_FLAGS * NL + lane] = fl | F_DONE;
+        return;
+    }
+    sm.i64[TXI_NRHS * NL + lane] += stages;
+    const double h = sm.f64[TXF_H * NL + lane];
+    double cr = sm.f64[TXF_CR * NL + lane];
+    const double cd = sm.f64[TXF_CD * NL + lane], pm = sm.f64[TXF_PM * NL + lane];
+    long long step_ns = sm.i64[TXI_STEP * NL + lane];
+    long long dt_ns = 0;
+    bool accept;
+    if (fl & F_FIXED) {
+        sm.i64[TXI_DET_STEP * NL + lane] = step_ns;
+        dt_ns = step_ns;
+        accept = true;
+    } else {
+        // the stage states of y[6..8] are y + h * 0 (instance.rs:394): h = NaN poisons them as in the reference
+        const double hz = h * 0.0;
+        double e9[9], c9[9], y9[9];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) { e9[e] = sm.er[e * NL + lane]; c9[e] = sm.nxt[e * NL + lane]; y9[e] = sm.ycur[e * NL + lane]; }
+        e9[6] = e9[7] = e9[8] = 0.0;
+        y9[6] = cr; y9[7] = cd; y9[8] = pm;
+        c9[6] = cr + hz; c9[7] = cd + hz; c9[8] = pm + hz;
+        const double err = error_estimate(S.error_ctrl, e9, c9, y9);
+        sm.f64[TXF_ERR * NL + lane] = err;
+        int att = sm.i32[TXW_ATT * NL + lane];
+        accept = err <= S.tolerance || h <= S.min_step_s || att >= S.attempts;
+        if (accept) {
+            bool bad = false;
+#pragma unroll
+            for (int e = 0; e < 9; ++e) bad |= (c9[e] != c9[e]);
+            if (bad) {
+                sm.i32[TXW_RC * NL + lane] = NYXB_ERR_PROP_MATH;
+                sm.i32[TXW_FLAGS * NL + lane] = fl | F_DONE;
+                return;
+            }
+            if (att >= S.attempts) sm.i32[TXW_STATUS * NL + lane] |= NYXB_WARN_MAX_ATTEMPTS;
+            const long long det_step = dur_from_seconds(h);
+            sm.i64[TXI_DET_STEP * NL + lane] = det_step;
+            double hn = h;
+            if (err < S.tolerance) {
+                const double proposed = 0.9 * h * pow_inv_int(S.tolerance / err, S.tb.order);
+                if (fabs(proposed) > fabs(S.max_step_s)) {
+                    const double sg = (proposed != proposed) ? proposed : (signbit(proposed) ? -1.0 : 1.0);
+                    hn = S.max_step_s * sg;
+                } else {
+                    hn = proposed;
+                }
+            }
+            step_ns = dur_from_seconds(hn);
+            const long long ab = step_ns < 0 ? -step_ns : step_ns;
+            if (ab < S.min_step_ns) step_ns = (step_ns < 0) ? -S.min_step_ns : S.min_step_ns;
+            dt_ns = det_step;
+        } else {
+            sm.i32[TXW_ATT * NL + lane] = att + 1;
+            sm.i64[TXI_NREJ * NL + lane] += 1;
+            const double proposed = 0.9 * h * pow_inv_int(S.tolerance / err, S.tb.order - 1);
+            sm.f64[TXF_H * NL + lane] = (proposed < S.min_step_s) ? S.min_step_s : proposed;
+            sm.i32[TXW_FLAGS * NL + lane] = fl | F_RETRY;
+            return;
+        }
+    }
+    // ---- single_step(): instance.rs:343-352
+    fl &= ~F_RETRY;
+    const long long epoch = sm.i64[TXI_EPOCH * NL + lane] + dt_ns;
+    sm.i64[TXI_EPOCH * NL + lane] = epoch;
+    sm.i32[TXW_ACC * NL + lane] = 1;
+    cr = cr < 0.0 ? 0.0 : (cr > 2.0 ? 2.0 : cr);   // cosmic/spacecraft.rs:494
+    sm.f64[TXF_CR * NL + lane] = cr;
+    const long long ns = sm.i64[TXI_NSTEPS * NL + lane] + 1;
+    sm.i64[TXI_NSTEPS * NL + lane] = ns;
+    if ((fl & F_VALID) && ns < sink.cap) sink.epoch[(size_t)ns * n + tr] = epoch;   // the state is stored by the component warps
+    if (pm < 0.0) { sm.i32[TXW_RC * NL + lane] = NYXB_ERR_FUEL_EXHAUSTED; fl |= F_DONE; }
+    if (sink.ev_kind && !(fl & F_LAST)) {   // stop condition on non-final steps (instance.rs:243-252, event.rs:120-150)
+        const double yn = event_eval(sink.ev_kind, sink.ev_value, sm.nxt[lane], sm.nxt[NL + lane], sm.nxt[2 * NL + lane],
+                                     sm.nxt[3 * NL + lane], sm.nxt[4 * NL + lane], sm.nxt[5 * NL + lane]);
+        const int cnt = sm.i32[TXW_EVCNT * NL + lane] + ((sm.f64[TXF_EVPREV * NL + lane] * yn < 0.0) ? 1 : 0);
+        sm.f64[TXF_EVPREV * NL + lane] = yn;
+        sm.i32[TXW_EVCNT * NL + lane] = cnt;
+        if (cnt >= sink.ev_trigger) fl |= F_DONE;
+    }
+    if (fl & F_LAST) {   // restore the adapted step (instance.rs:194-196)
+        step_ns = sm.i64[TXI_PREV_STEP * NL + lane];
+        fl = (fl & ~F_FIXED) | ((fl & F_PREVFIXED) ? F_FIXED : 0);
+        if (fl & F_BACK) step_ns = -step_ns;
+        fl |= F_DONE;
+    }
+    sm.i64[TXI_STEP * NL + lane] = step_ns;
+    sm.i32[TXW_FLAGS * NL + lane] = fl;
+}
+
+// ---- controller state of a set: initial (round 0, instance.rs:96-115) or from the parking area
+__device__ __noinline__ void tx_load_ctl(const DevSetup& S, const DevSink& sink, const DevTxQueue& q, TxSm sm, int lane, size_t n,
+                                         size_t tr, bool valid, int round, const double* __restrict__ state,
+                                         const double* __restrict__ consts, const long long* __restrict__ epoch0, long long end_epoch,
+                                         const long long* step_io, const double* out_state, const long long* out_epoch) {
+    sm.f64[TXF_DRY * NL + lane] = consts[tr];
+    sm.f64[TXF_EXTRA * NL + lane] = consts[n + tr];
+    sm.f64[TXF_SRPA * NL + lane] = consts[2 * n + tr];
+    sm.f64[TXF_DRAGA * NL + lane] = consts[3 * n + tr];
+    sm.i32[TXW_ACC * NL + lane] = 0;
+    sm.i32[TXW_RCST * NL + lane] = 0;
+    const long long ep0 = epoch0[tr];
+    const long long duration = end_epoch - ep0;
+    if (round == 0) {
+        const double pm = state[8 * n + tr];
+        sm.f64[TXF_CR * NL + lane] = state[6 * n + tr];
+        sm.f64[TXF_CD * NL + lane] = state[7 * n + tr];
+        sm.f64[TXF_PM * NL + lane] = pm;
+        sm.f64[TXF_H * NL + lane] = 0.0;
+        sm.f64[TXF_ERR * NL + lane] = 0.0;
+        long long step_ns = step_io ? step_io[tr] : S.init_step_ns;
+        int fl = (S.fixed_step ? F_FIXED : 0) | (valid ? F_VALID : 0) | (duration < 0 ? F_BACK : 0);
+        int rc = 0;
+        if (!valid || duration == 0) fl |= F_DONE;
+        if (!(fl & F_DONE) && pm < 0.0) { rc = NYXB_ERR_FUEL_EXHAUSTED; fl |= F_DONE; }
+        if (!(fl & F_DONE) && duration < 0) step_ns = -step_ns;
+        sm.i64[TXI_EPOCH * NL + lane] = ep0;
+        sm.i64[TXI_STEP * NL + lane] = step_ns;
+        sm.i64[TXI_PREV_STEP * NL + lane] = step_ns;
+        sm.i64[TXI_DET_STEP * NL + lane] = S.init_step_ns;
+        sm.i64[TXI_NSTEPS * NL + lane] = 0;
+        sm.i64[TXI_NREJ * NL + lane] = 0;
+        sm.i64[TXI_NRHS * NL + lane] = 0;
+        sm.i32[TXW_FLAGS * NL + lane] = fl;
+        sm.i32[TXW_STATUS * NL + lane] = 0;
+        sm.i32[TXW_RC * NL + lane] = rc;
+        sm.i32[TXW_ATT * NL + lane] = 1;
+        sm.i32[TXW_EVCNT * NL + lane] = 0;
+        sm.f64[TXF_EVPREV * NL + lane] = 0.0;
+        if (sink.ev_kind)
+            sm.f64[TXF_EVPREV * NL + lane] = event_eval(sink.ev_kind, sink.ev_value, state[tr], state[n + tr], state[2 * n + tr],
+                                                        state[3 * n + tr], state[4 * n + tr], state[5 * n + tr]);
+        if (valid && sink.cap > 0) sink.epoch[tr] = ep0;   // start state (instance.rs:307, 321)
+    } else {
+        const int pf = __ldcg(q.ws_flags + tr);
+        const nyxb_details* dp = q.details + tr;
+        sm.f64[TXF_CR * NL + lane] = __ldcg(out_state + 6 * n + tr);
+        sm.f64[TXF_CD * NL + lane] = __ldcg(out_state + 7 * n + tr);
+        sm.f64[TXF_PM * NL + lane] = __ldcg(out_state + 8 * n + tr);
+        sm.f64[TXF_H * NL + lane] = __ldcg(q.ws_f64 + tr);
+        sm.f64[TXF_EVPREV * NL + lane] = __ldcg(q.ws_f64 + n + tr);
+        sm.f64[TXF_ERR * NL + lane] = __ldcg(&dp->error);
+        sm.i64[TXI_EPOCH * NL + lane] = __ldcg(out_epoch + tr);
+        const long long step_ns = __ldcg(q.ws_step + tr);
+        sm.i64[TXI_STEP * NL + lane] = step_ns;
+        sm.i64[TXI_PREV_STEP * NL + lane] = step_ns;
+        sm.i64[TXI_DET_STEP * NL + lane] = __ldcg((const long long*)&dp->step_ns);
+        sm.i64[TXI_NSTEPS * NL + lane] = __ldcg((const long long*)&dp->n_steps);
+        sm.i64[TXI_NREJ * NL + lane] = __ldcg((const long long*)&dp->n_rejected);
+        sm.i64[TXI_NRHS * NL + lane] = __ldcg((const long long*)&dp->n_rhs);
+        sm.i32[TXW_ATT * NL + lane] = __ldcg(&dp->attempts);
+        int fl = (pf & (F_FIXED | F_RETRY | F_DONE)) | (valid ? F_VALID : 0) | (duration < 0 ? F_BACK : 0);
+        if (!valid) fl |= F_DONE;
+        sm.i32[TXW_FLAGS * NL + lane] = fl;
+        sm.i32[TXW_STATUS * NL + lane] = (pf & 8) ? NYXB_WARN_MAX_ATTEMPTS : 0;
+        sm.i32[TXW_RC * NL + lane] = (pf >> 8) & 0xff;
+        sm.i32[TXW_EVCNT * NL + lane] = sink.ev_kind ? __ldcg(sink.ev_crossings + tr) : 0;
+    }
+}
+
+// ---- park the controller state of a set (== the final outputs once the trajectory is done)
+__device__ __noinline__ void tx_park_ctl(const DevSink& sink, const DevTxQueue& q, TxSm sm, int lane, size_t n, size_t tr,
+                                         long long* step_io, double* out_state, long long* out_epoch, int* out_status) {
+    const int fl = sm.i32[TXW_FLAGS * NL + lane];
+    if (!(fl & F_VALID)) return;
+    const int rc = sm.i32[TXW_RC * NL + lane], st = sm.i32[TXW_STATUS * NL + lane];
+    out_state[6 * n + tr] = sm.f64[TXF_CR * NL + lane];
+    out_state[7 * n + tr] = sm.f64[TXF_CD * NL + lane];
+    out_state[8 * n + tr] = sm.f64[TXF_PM * NL + lane];
+    out_epoch[tr] = sm.i64[TXI_EPOCH * NL + lane];
+    const long long step_ns = sm.i64[TXI_STEP * NL + lane];
+    q.ws_step[tr] = step_ns;
+    q.ws_f64[tr] = sm.f64[TXF_H * NL + lane];
+    q.ws_f64[n + tr] = sm.f64[TXF_EVPREV * NL + lane];
+    q.ws_flags[tr] = (fl & (F_FIXED | F_RETRY | F_DONE)) | ((st & NYXB_WARN_MAX_ATTEMPTS) ? 8 : 0) | (rc << 8);
+    nyxb_details d;
+    d.step_ns = sm.i64[TXI_DET_STEP * NL + lane];
+    d.error = sm.f64[TXF_ERR * NL + lane];
+    d.attempts = sm.i32[TXW_ATT * NL + lane];
+    d._pad = 0;
+    d.n_steps = sm.i64[TXI_NSTEPS * NL + lane];
+    d.n_rejected = sm.i64[TXI_NREJ * NL + lane];
+    d.n_rhs = sm.i64[TXI_NRHS * NL + lane];
+    q.details[tr] = d;
+    int rc_out = rc;
+    if (sink.ev_kind) {
+        const int cnt = sm.i32[TXW_EVCNT * NL + lane];
+        sink.ev_crossings[tr] = cnt;
+        if (rc == 0 && cnt < sink.ev_trigger) rc_out = NYXB_ERR_EVENT_NOT_FOUND;   // event.rs:177-182 (final once the run is done)
+    }
+    out_status[tr] = (st & NYXB_WARN_MAX_ATTEMPTS) | rc_out;
+    if (step_io) step_io[tr] = step_ns;
+    if (sink.cap > 0) sink.count[tr] = (d.n_steps + 1 < sink.cap) ? d.n_steps + 1 : sink.cap;
+}
+
+template <int P>
+__global__ void __launch_bounds__(P * 32, TX_MINB)
+nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, const __grid_constant__ DevTxQueue q, size_t n,
+          const double* __restrict__ state, const double* __restrict__ consts, const long long* __restrict__ epoch0,
+          long long end_epoch, long long* step_io, double* out_state, long long* out_epoch, int* out_status, const DevSink sink,
+          unsigned blob_bytes, unsigned off_recK, unsigned off_seed, unsigned off_sched) {
+    static_assert(P >= 8 && P <= NYXB_TX_MAXP, "roles need 8 warps: six components, rotation, controller");
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long tma_bar;
+    __shared__ int s_set, s_round, s_skip, s_exit, s_all_done, s_slice_end;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    constexpr int W_ROT = 6, W_CTL = 7;
+    const TxLayout L = tx_layout(blob_bytes, P);
+    TxSm sm;
+    sm.recA = reinterpret_cast<const double2*>(smem + L.blob);
+    sm.recK = reinterpret_cast<const double*>(smem + L.blob + off_recK);
+    sm.colseed = reinterpret_cast<const double*>(smem + L.blob + off_seed);
+    sm.sched = reinterpret_cast<const int*>(smem + L.blob + off_sched);
+    sm.ys = reinterpret_cast<double*>(smem + L.ys); sm.rm = reinterpret_cast<double*>(smem + L.rm);
+    sm.part = reinterpret_cast<double*>(smem + L.part); sm.kst = reinterpret_cast<double*>(smem + L.kst);
+    sm.nxt = reinterpret_cast<double*>(smem + L.nxt); sm.er = reinterpret_cast<double*>(smem + L.er);
+    sm.ycur = reinterpret_cast<double*>(smem + L.ycur); sm.f64 = reinterpret_cast<double*>(smem + L.f64);
+    sm.i64 = reinterpret_cast<long long*>(smem + L.i64); sm.i32 = reinterpret_cast<int*>(smem + L.i32);
+
+    // ---- CTA-shared tables (records, column seeds, schedule): ONE TMA bulk copy
+    if (tid == 0) tx_mbar_init(&tma_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        tx_mbar_expect(&tma_bar, blob_bytes);
+        tx_bulk_g2s(smem + L.blob, Tx.recA, blob_bytes, &tma_bar);
+    }
+    tx_mbar_wait(&tma_bar, 0);
+    __syncthreads();
+
+    const int stages = S.tb.stages;
+    const DevGrav& gv = S.grav;
+    const bool has_extra = S.n_bodies > 0 || S.has_srp || S.has_drag;
+    // this warp's column schedule (warp-uniform)
+    const int* my = sm.sched + w * (2 + 2 * Tx.kmax);
+    const int rec_off = my[0], ncol = my[1];
+
+    for (;;) {
+        // ---------------------------------------------------------------- acquire a (set, slice) ticket
+        if (tid == 0) {
+            int fin_all = atomicAdd(q.n_finished, 0);
+            if (fin_all >= q.n_sets) {
+                s_exit = 1;
+            } else {
+                const unsigned long long t = atomicAdd(q.ticket, 1ULL);
+                const int set = (int)(t % (unsigned long long)q.n_sets), round = (int)(t / (unsigned long long)q.n_sets);
+                while (atomicAdd(q.slices_done + set, 0) < round) __nanosleep(256);   // the previous slice of this set is parked
+                __threadfence();
+                s_set = set; s_round = round; s_exit = 0;
+                s_skip = atomicAdd(q.finished + set, 0);
+            }
+        }
+        __syncthreads();
+        if (s_exit) break;
+        const int set = s_set, round = s_round;
+        if (s_skip) {
+            __syncthreads();
+            if (tid == 0) atomicExch(q.slices_done + set, round + 1);
+            continue;
+        }
+        const size_t traj_raw = (size_t)set * NL + lane;
+        const bool valid = traj_raw < n;
+        const size_t tr = valid ? traj_raw : (size_t)set * NL;   // an absent lane shadows the set's first trajectory, never committed
+
+        // ---------------------------------------------------------------- load the set
+        if (w < 6) {
+            const double yc = (round == 0) ? state[(size_t)w * n + tr] : __ldcg(out_state + (size_t)w * n + tr);
+            sm.ycur[w * NL + lane] = yc;
+            if (round == 0 && valid && sink.cap > 0) sink.state[((size_t)w * sink.cap) * n + tr] = yc;
+        } else if (w == W_CTL) {
+            tx_load_ctl(S, sink, q, sm, lane, n, tr, valid, round, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch);
+            tx_pick_step(sm, lane, end_epoch);
+            const bool done = sm.i32[TXW_FLAGS * NL + lane] & F_DONE;
+            const bool all = __all_sync(FULL, done);
+            if (lane == 0) { s_all_done = all; s_slice_end = 0; }
+        }
+        __syncthreads();
+
+        // ---------------------------------------------------------------- step attempts of this slice
+        for (int it = 0; !s_all_done; ++it) {
+            const double h = sm.f64[TXF_H * NL + lane];
+            const long long epoch = sm.i64[TXI_EPOCH * NL + lane];
+            // orientation angles at the step epoch (rotation warp, registers live across the stages of this attempt)
+            double b_sa = 0.0, b_ca = 1.0, b_sd = 1.0, b_cd = 0.0, b_sw = 0.0, b_cw = 1.0;
+            if (w == W_ROT && gv.rot.kind != 0) {
+                const double t_s = dur_to_seconds(epoch);
+                const double d = t_s / 86400.0;
+                const double Tc = d / 36525.0;
+                det_sincos((gv.rot.ra0 + gv.rot.ra1 * Tc) * NYXB_DEG2RAD, b_sa, b_ca);
+                det_sincos((gv.rot.dec0 + gv.rot.dec1 * Tc) * NYXB_DEG2RAD, b_sd, b_cd);
+                det_sincos(fmod(gv.rot.w0 + gv.rot.w1 * d, 360.0) * NYXB_DEG2RAD, b_sw, b_cw);
+            }
+            int rc_acc = 0;
+            // ---- derive(): one attempt for the 32 trajectories (instance.rs:358-493)
+            for (int i = 0; i < stages; ++i) {
+                double* ysb = sm.ys + (i & 1) * 6 * NL;
+                double* rmb = sm.rm + (i & 1) * 9 * NL;
+                if (w < 6) {
+                    // stage state y + h * sum_j a_ij k_j (instance.rs:376-394); stage 0 is y itself
+                    const double yc = sm.ycur[w * NL + lane];
+                    double ysv = yc;
+                    if (i > 0) {
+                        const double* arow = &S.tb.a[(i - 1) * NYXB_MAX_STAGES];
+                        const double* kc = sm.kst + w * NL + lane;
+                        double w0 = 0.0, w1 = 0.0;
+                        int j = 0;
+                        for (; j + 1 < i; j += 2) {
+                            w0 = fma(arow[j], kc[j * 6 * NL], w0);
+                            w1 = fma(arow[j + 1], kc[(j + 1) * 6 * NL], w1);
+                        }
+                        if (j < i) w0 = fma(arow[j], kc[j * 6 * NL], w0);
+                        ysv = fma(h, w0 + w1, yc);
+                    }
+                    ysb[w * NL + lane] = ysv;
+                } else if (w == W_ROT) {
+                    // inertial -> body-fixed DCM at the stage time: first-order update of the (slow) pole angles, exact angle
+                    // addition for the prime-meridian angle (the stage epoch is ns-truncated, cosmic/mod.rs:102)
+                    double R[9];
+                    if (gv.rot.kind == 0) {
+                        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+                    } else {
+                        const long long off_ns = (i > 0) ? dur_from_seconds(S.tb.c[i - 1] * h) : 0;
+                        const double dt_s = (double)off_ns * 1e-9;
+                        const double da = gv.rot.ra_dot * dt_s, dd = gv.rot.dec_dot * dt_s, dw = gv.rot.wdot * dt_s;
+                        const double sa = fma(b_ca, da, b_sa), ca = fma(-b_sa, da, b_ca);
+                        const double sd = fma(b_cd, dd, b_sd), cd = fma(-b_sd, dd, b_cd);
+                        double sdl, cdl;
+                        if (fabs(dw) < 0.02) {
+                            const double z = dw * dw;
+                            sdl = dw * fma(z, fma(z, 1.0 / 120.0, -1.0 / 6.0), 1.0);
+                            cdl = fma(z, fma(z, fma(z, -1.0 / 720.0, 1.0 / 24.0), -0.5), 1.0);
+                        } else {
+                            det_sincos(dw, sdl, cdl);
+                        }
+                        const double sw = fma(b_sw, cdl, b_cw * sdl), cw = fma(b_cw, cdl, -(b_sw * sdl));
+                        const double b00 = -sa, b01 = ca;
+                        const double b10 = -(sd * ca), b11 = -(sd * sa), b12 = cd;
+                        R[0] = fma(cw, b00, sw * b10); R[1] = fma(cw, b01, sw * b11); R[2] = sw * b12;
+                        R[3] = fma(cw, b10, -(sw * b00)); R[4] = fma(cw, b11, -(sw * b01)); R[5] = cw * b12;
+                        R[6] = cd * ca; R[7] = cd * sa; R[8] = sd;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) rmb[k * NL + lane] = R[k];
+                }
+                __syncthreads();   // (A) stage state and DCM of this stage are in shared memory
+
+                // ---- every warp: body-fixed position, 1/r, recursion scalars, powers of its columns, column walk
+                {
+                    const double y0 = ysb[lane], y1 = ysb[NL + lane], y2 = ysb[2 * NL + lane];
+                    const double rb0 = fma(rmb[2 * NL + lane], y2, fma(rmb[NL + lane], y1, rmb[lane] * y0));
+                    const double rb1 = fma(rmb[5 * NL + lane], y2, fma(rmb[4 * NL + lane], y1, rmb[3 * NL + lane] * y0));
+                    const double rb2 = fma(rmb[8 * NL + lane], y2, fma(rmb[7 * NL + lane], y1, rmb[6 * NL + lane] * y0));
+                    const double inv_r = rsqrt(fma(rb2, rb2, fma(rb1, rb1, rb0 * rb0)));
+                    const double rho = gv.r_eq * inv_r;
+                    const double ub = (rb2 * inv_r) * rho;
+                    const double r2 = rho * rho;
+                    // z^e = (cos, sin)(e lambda) cos^e(phi) and rho^(e+1) for the two interleaved exponent sequences of this position:
+                    // e = w + 2P j (za, pa) and e = 2P-1-w + 2P j (zb, pb); binary powering with warp-uniform bits, the squarings end at
+                    // the common ratio z^(2P), rho^(2P)
+                    double br = rb0 * inv_r, bi = rb1 * inv_r, bp = rho;
+                    double zar = 1.0, zai = 0.0, zbr = 1.0, zbi = 0.0, pa = rho, pb = rho;
+                    const int ea = w, eb = 2 * P - 1 - w;
+#pragma unroll
+                    for (int bit = 1; bit < 2 * P; bit <<= 1) {
+                        if (ea & bit) {
+                            const double nr = fma(zar, br, -(zai * bi));
+                            zai = fma(zar, bi, zai * br); zar = nr; pa *= bp;
+                        }
+                        if (eb & bit) {
+                            const double nr = fma(zbr, br, -(zbi * bi));
+                            zbi = fma(zbr, bi, zbi * br); zbr = nr; pb *= bp;
+                        }
+                        const double nb = fma(br, br, -(bi * bi));
+                        bi = 2.0 * br * bi; br = nb; bp *= bp;
+                    }
+                    double X = 0.0, Y = 0.0, Z = 0.0, W = 0.0;
+                    const double2* A = sm.recA + 2 * rec_off;
+                    const double* K = sm.recK + rec_off;
+                    double2 a01 = A[0], a23 = A[1];
+                    double kk = K[0];
+                    for (int k = 0; k < ncol; k += 2) {
+                        {   // column of the first sequence
+                            const int m = my[2 + 2 * k], len = my[3 + 2 * k];
+                            const double* sd = sm.colseed + 4 * m;
+                            tx_column(A, K, a01, a23, kk, len, pa * sd[0], sd[1], sd[2], sd[3], ub, r2, zar, zai, X, Y, Z, W);
+                            const double nr = fma(zar, br, -(zai * bi));
+                            zai = fma(zar, bi, zai * br); zar = nr; pa *= bp;
+                        }
+                        if (k + 1 < ncol) {   // column of the second sequence
+                            const int m = my[4 + 2 * k], len = my[5 + 2 * k];
+                            const double* sd = sm.colseed + 4 * m;
+                            tx_column(A, K, a01, a23, kk, len, pb * sd[0], sd[1], sd[2], sd[3], ub, r2, zbr, zbi, X, Y, Z, W);
+                            const double nr = fma(zbr, br, -(zbi * bi));
+                            zbi = fma(zbr, bi, zbi * br); zbr = nr; pb *= bp;
+                        }
+                    }
+                    double* pt = sm.part + (w * 4) * NL + lane;
+                    pt[0] = X; pt[NL] = Y; pt[2 * NL] = Z; pt[3 * NL] = W;
+                }
+                __syncthreads();   // (C) partial sums of all positions are in shared memory
+
+                if (w < 6) {
+                    double kval;
+                    if (w < 3) {
+                        kval = ysb[(3 + w) * NL + lane];   // dr/dt = v
+                    } else {
+                        // ---- reduce the partial sums, assemble the acceleration component j (spacecraft.rs:216-247)
+                        const int j = w - 3;
+                        double X = 0.0, Y = 0.0, Z = 0.0, Wt = 0.0;
+#pragma unroll
+                        for (int p = 0; p < P; ++p) {
+                            const double* pt = sm.part + (p * 4) * NL + lane;
+                            X += pt[0]; Y += pt[NL]; Z += pt[2 * NL]; Wt += pt[3 * NL];
+                        }
+                        const double y0 = ysb[lane], y1 = ysb[NL + lane], y2 = ysb[2 * NL + lane];
+                        const double rb0 = fma(rmb[2 * NL + lane], y2, fma(rmb[NL + lane], y1, rmb[lane] * y0));
+                        const double rb1 = fma(rmb[5 * NL + lane], y2, fma(rmb[4 * NL + lane], y1, rmb[3 * NL + lane] * y0));
+                        const double rb2 = fma(rmb[8 * NL + lane], y2, fma(rmb[7 * NL + lane], y1, rmb[6 * NL + lane] * y0));
+                        const double inv_r = rsqrt(fma(rb2, rb2, fma(rb1, rb1, rb0 * rb0)));
+                        const double rho = gv.r_eq * inv_r;
+                        const double s_ = rb0 * inv_r, t_ = rb1 * inv_r, u_ = rb2 * inv_r;
+                        // rr_n A[n][m] = K0 rho (rho^n A),  rr_{n-1} A[n][m] = K0 (rho^n A),  K0 = mu / (r R_eq)
+                        const double K0 = (gv.mu * gv.inv_r_eq) * inv_r;
+                        const double K1 = K0 * rho;
+                        const double aw = -K0 * Wt;
+                        const double ab0 = fma(aw, s_, K1 * X), ab1 = fma(aw, t_, K1 * Y), ab2 = fma(aw, u_, K1 * Z);
+                        const double fac = -S.mu_central * inv_r * inv_r * inv_r;   // two-body from the same 1/r (orbital.rs:86-92)
+                        const double yj = ysb[j * NL + lane];
+                        kval = fma(fac, yj, fma(rmb[(6 + j) * NL + lane], ab2, fma(rmb[(3 + j) * NL + lane], ab1, rmb[j * NL + lane] * ab0)));
+                        if (has_extra) {
+                            double yy[9], aa[3] = {0.0, 0.0, 0.0};
+                            const double hz = (i > 0) ? h * 0.0 : 0.0;
+#pragma unroll
+                            for (int e = 0; e < 6; ++e) yy[e] = ysb[e * NL + lane];
+                            yy[6] = sm.f64[TXF_CR * NL + lane] + hz; yy[7] = sm.f64[TXF_CD * NL + lane] + hz; yy[8] = sm.f64[TXF_PM * NL + lane] + hz;
+                            const long long off_ns = (i > 0) ? dur_from_seconds(S.tb.c[i - 1] * h) : 0;
+                            const int rcx = tx_extra(S, sm.f64[TXF_DRY * NL + lane], sm.f64[TXF_EXTRA * NL + lane], sm.f64[TXF_SRPA * NL + lane],
+                                                     sm.f64[TXF_DRAGA * NL + lane], epoch + off_ns, yy, aa);
+                            kval += (j == 0) ? aa[0] : (j == 1 ? aa[1] : aa[2]);
+                            if (rcx && !rc_acc) rc_acc = rcx | ((i + 1) << 8);
+                        }
+                    }
+                    sm.kst[(i * 6 + w) * NL + lane] = kval;
+                }
+            }
+            // ---- candidate state and error estimate of this attempt (instance.rs:402-414)
+            if (w < 6) {
+                const double yc = sm.ycur[w * NL + lane];
+                const bool fixed = sm.i32[TXW_FLAGS * NL + lane] & F_FIXED;
+                double nx = yc, er = 0.0;
+                for (int i = 0; i < stages; ++i) {
+                    const double ki = sm.kst[(i * 6 + w) * NL + lane];
+                    if (!fixed) er = fma(h * S.tb.e[i], ki, er);
+                    nx = fma(h * S.tb.b[i], ki, nx);
+                }
+                sm.nxt[w * NL + lane] = nx;
+                sm.er[w * NL + lane] = er;
+                if (w == 3) sm.i32[TXW_RCST * NL + lane] = rc_acc;
+            }
+            __syncthreads();   // (D)
+            if (w == W_CTL) {
+                tx_controller(S, sink, sm, lane, n, tr, stages);
+                const bool slice_end = q.slice > 0 && it + 1 >= q.slice;
+                if (!slice_end) tx_pick_step(sm, lane, end_epoch);
+                const bool done = sm.i32[TXW_FLAGS * NL + lane] & F_DONE;
+                const bool all = __all_sync(FULL, done);
+                if (lane == 0) { s_all_done = all; s_slice_end = slice_end; }
+            }
+            __syncthreads();   // (E)
+            if (w < 6 && sm.i32[TXW_ACC * NL + lane]) {
+                const double nx = sm.nxt[w * NL + lane];
+                sm.ycur[w * NL + lane] = nx;
+                const long long ns = sm.i64[TXI_NSTEPS * NL + lane];
+                // the channel send of instance.rs:186-193 / 255-259: lanes are consecutive trajectories, one 256-byte store per warp
+                if (valid && ns < sink.cap) sink.state[((size_t)w * sink.cap + (size_t)ns) * n + tr] = nx;
+            }
+            if (s_slice_end) break;
+        }
+
+        // ---------------------------------------------------------------- park the set (== final outputs when it is done)
+        if (w < 6) {
+            if (valid) out_state[(size_t)w * n + tr] = sm.ycur[w * NL + lane];
+        } else if (w == W_CTL) {
+            tx_park_ctl(sink, q, sm, lane, n, tr, step_io, out_state, out_epoch, out_status);
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            if (s_all_done) {
+                atomicExch(q.finished + set, 1);
+                atomicAdd(q.n_finished, 1);
+            }
+            __threadfence();
+            atomicExch(q.slices_done + set, round + 1);
+        }
+        // s_* are rewritten by thread 0 only after the barrier at the top of the next ticket
+        __syncthreads();
+    }
+}
+
+template <int P>
+cudaError_t tx_launch_p(const DevSetup* S, const DevTx* Tx, const DevTxQueue* q, size_t n, const double* state, const double* consts,
+                        const long long* epoch0, long long end_epoch, long long* step_io, double* out_state, long long* out_epoch,
+                        int* out_status, const DevSink* sink, int grid, size_t smem, unsigned blob_bytes, unsigned off_recK,
+                        unsigned off_seed, unsigned off_sched, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(nyxb_k_tx<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    nyxb_k_tx<P><<<grid, P * 32, smem, stream>>>(*S, *Tx, *q, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_status,
+                                                 *sink, blob_bytes, off_recK, off_seed, off_sched);
+    return cudaGetLastError();
+}
+
+// blob layout shared by the host builder, the launcher and the kernel: [recA | recK | colseed | sched]
+struct TxBlob { unsigned off_recK, off_seed, off_sched, bytes; };
+TxBlob tx_blob(int N, int P, int n_rec, int kmax) {
+    TxBlob b;
+    unsigned o = (unsigned)(n_rec + 1) * 32u;
+    b.off_recK = o; o += (((unsigned)(n_rec + 2) + 1u) & ~1u) * 8u;
+    b.off_seed = o; o += (unsigned)(N + 2) * 32u;
+    b.off_sched = o; o += (unsigned)P * (2u + 2u * (unsigned)kmax) * 4u;
+    b.bytes = (o + 15u) & ~15u;
+    return b;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// host: zigzag column -> position schedule and record table
+// ------------------------------------------------------------------------------------------------
+void nyxb_tx_build_host(int N, int M, const double* c_nm, const double* s_nm, int P, TxHost& out) {
+    const double sqrt2 = std::sqrt(2.0);
+    auto C = [&](int n, int m) { return (n <= N && m <= M && m <= n) ? c_nm[(size_t)n * (N + 1) + m] : 0.0; };
+    auto Sx = [&](int n, int m) { return (n <= N && m <= M && m <= n) ? s_nm[(size_t)n * (N + 1) + m] : 0.0; };
+    auto vr01 = [&](int n, int m) {
+        double nf = n, mf = m;
+        double v = std::sqrt((nf - mf) * (nf + mf + 1.0));
+        return m == 0 ? v / sqrt2 : v;
+    };
+    auto vr11 = [&](int n, int m) {
+        double nf = n, mf = m;
+        double v = std::sqrt(((2.0 * nf + 1.0) * (nf + mf + 2.0) * (nf + mf + 1.0)) / (2.0 * nf + 3.0));
+        return m == 0 ? v / sqrt2 : v;
+    };
+    // scale[n][m] = A_ref[n][m] / Q[n][m] (see nyxb_coop.cu: same normalisation algebra, long double)
+    auto scale = [&](int n, int m) -> long double {
+        long double adiag = 1.0L, dfact = 1.0L;
+        for (int k = 1; k <= m; ++k) { adiag *= sqrtl(1.0L + 1.0L / (2.0L * k)); dfact *= (2.0L * k - 1.0L); }
+        long double g = adiag / dfact;
+        for (int k = m + 1; k <= n; ++k) g *= sqrtl(((2.0L * k + 1.0L) * (k - m)) / ((2.0L * k - 1.0L) * (k + m)));
+        for (int k = 2; k <= n - m; ++k) g /= (long double)k;
+        return g;
+    };
+    const int mcols = std::min(M + 1, N + 1);   // columns m = 1..mcols
+    auto col_len = [&](int m) { return std::max(N + 1 - m, 1); };   // entries n = m..N; column N+1 keeps one null entry (seed W term)
+    std::vector<std::vector<int>> cols(P);
+    for (int m = 1; m <= mcols; ++m) {
+        const int r = (m - 1) % (2 * P);
+        cols[r < P ? r : 2 * P - 1 - r].push_back(m);   // ascending m per position: exponents alternate between the two sequences
+    }
+    out.P = P;
+    out.kmax = 1;
+    for (auto& cl : cols) out.kmax = std::max(out.kmax, (int)cl.size());
+    out.n_rec = 0;
+    for (int m = 1; m <= mcols; ++m) out.n_rec += col_len(m);
+    out.recA.assign((size_t)(out.n_rec + 1) * 4, 0.0);
+    out.recK.assign((size_t)(out.n_rec + 2), 0.0);
+    out.colseed.assign((size_t)(N + 2) * 4, 0.0);
+    out.sched.assign((size_t)P * (2 + 2 * out.kmax), 0);
+    for (int m = 1; m <= mcols; ++m) {
+        long double dfact = 1.0L;
+        for (int k = 1; k <= m; ++k) dfact *= (2.0L * k - 1.0L);
+        double* s = &out.colseed[(size_t)m * 4];
+        s[0] = (double)dfact;
+        if (m >= 2) {   // W term of the first entry (n = m): degree n-1 = m-1 >= 1
+            long double f = (long double)sqrt2 * vr11(m - 1, m - 1) * scale(m, m);
+            s[1] = (double)(f * C(m - 1, m - 1));
+            s[2] = (double)(f * Sx(m - 1, m - 1));
+        }
+        s[3] = 2.0 * m + 1.0;
+    }
+    int e = 0;
+    for (int w = 0; w < P; ++w) {
+        int* sc = &out.sched[(size_t)w * (2 + 2 * out.kmax)];
+        sc[0] = e;
+        sc[1] = (int)cols[w].size();
+        // the kernel alternates between the sequences e = w + 2P j and e = 2P-1-w + 2P j: the columns of a position must come in
+        // exactly that order (they do: consecutive m cover every residue; a truncated last period only drops the tail)
+        for (size_t k = 0; k < cols[w].size(); ++k) {
+            const int m = cols[w][k];
+            sc[2 + 2 * k] = m;
+            sc[3 + 2 * k] = col_len(m);
+            auto kappa = [&](int n) -> double {   // W term of degree n = kappa * (Z term of degree n-1), n > m
+                return (double)(((long double)vr11(n - 1, m - 1) * scale(n, m)) / ((long double)vr01(n - 1, m - 1) * scale(n - 1, m)));
+            };
+            for (int n = m; n <= std::max(N, m); ++n, ++e) {
+                if (n > N) continue;   // null entry of column N+1
+                const long double sc_ = scale(n, m);
+                double* a = &out.recA[(size_t)e * 4];
+                a[0] = (double)(sc_ * sqrt2 * (double)m * C(n, m));
+                a[1] = (double)(sc_ * sqrt2 * (double)m * Sx(n, m));
+                a[2] = (double)(sc_ * sqrt2 * vr01(n, m - 1) * C(n, m - 1));
+                a[3] = (double)(sc_ * sqrt2 * vr01(n, m - 1) * Sx(n, m - 1));
+                out.recK[e] = kappa(n + 1);   // applied to Q[n+1] (p3, p4) of THIS entry
+            }
+        }
+    }
+}
+
+extern "C" int nyxb_tx_occupancy(const DevSetup* S, const DevTx* Tx, size_t* smem_bytes) {
+    const TxBlob b = tx_blob(S->grav.N, Tx->P, Tx->n_rec, Tx->kmax);
+    const size_t smem = tx_layout(b.bytes, Tx->P).total;
+    if (smem_bytes) *smem_bytes = smem;
+    if (smem > 227 * 1024) return 0;
+    int occ = 0;
+    cudaError_t e = cudaErrorInvalidValue;
+    if (Tx->P == 8) {
+        if (cudaFuncSetAttribute(nyxb_k_tx<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nyxb_k_tx<8>, 8 * 32, smem);
+    } else if (Tx->P == 16) {
+        if (cudaFuncSetAttribute(nyxb_k_tx<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nyxb_k_tx<16>, 16 * 32, smem);
+    }
+    return e == cudaSuccess ? occ : 0;
+}
+
+extern "C" cudaError_t nyxb_launch_tx(const DevSetup* S, const DevTx* Tx, const DevTxQueue* q, size_t n, const double* state,
+                                      const double* consts, const long long* epoch0, long long end_epoch, long long* step_io,
+                                      double* out_state, long long* out_epoch, int* out_status, const DevSink* sink,
+                                      int grid, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const TxBlob b = tx_blob(S->grav.N, Tx->P, Tx->n_rec, Tx->kmax);
+    const size_t smem = tx_layout(b.bytes, Tx->P).total;
+    if (smem > 227 * 1024 || grid < 1) return cudaErrorInvalidConfiguration;
+#define NYXB_TX_GO(PP) tx_launch_p<PP>(S, Tx, q, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_status, sink, grid, smem, b.bytes, b.off_recK, b.off_seed, b.off_sched, stream)
+    switch (Tx->P) {
+    case 8: return NYXB_TX_GO(8);
+    case 16: return NYXB_TX_GO(16);
+    default: return cudaErrorInvalidValue;
+    }
+#undef NYXB_TX_GO
+}
+
+// host-side view of the blob (nyxb_api.cu uploads it as one allocation; the kernel copies it with one TMA bulk copy)
+size_t nyxb_tx_pack_blob(const TxHost* h, int N, unsigned char* dst) {
+    const TxBlob b = tx_blob(N, h->P, h->n_rec, h->kmax);
+    if (dst) {
+        std::memset(dst, 0, b.bytes);
+        std::memcpy(dst, h->recA.data(), h->recA.size() * 8);
+        std::memcpy(dst + b.off_recK, h->recK.data(), h->recK.size() * 8);
+        std::memcpy(dst + b.off_seed, h->colseed.data(), h->colseed.size() * 8);
+        std::memcpy(dst + b.off_sched, h->sched.data(), h->sched.size() * 4);
+    }
+    return b.bytes;
+}

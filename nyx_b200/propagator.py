@@ -182,6 +182,20 @@ class Engine:
     def lanes(self) -> int:
         return self._lib.nyxb_engine_get_lanes(self._h)
 
+    def set_kernel(self, kernel: int):
+        """Force a kernel family (abi.KERNEL_AUTO / _THREAD / _COOP / _TRANSPOSED, `nyxb_engine_set_kernel`)."""
+        rc = self._lib.nyxb_engine_set_kernel(self._h, kernel)
+        if rc != 0:
+            raise PropagationError(f"set_kernel({kernel}): {abi.last_error()}")
+
+    def last_kernel(self) -> int:
+        return self._lib.nyxb_engine_last_kernel(self._h)
+
+    def set_tx_tuning(self, slice_attempts: int = 64, max_ctas: int = 0):
+        """Transposed kernel: step attempts per time slice and a bound on the persistent CTAs (0: every resident slot)."""
+        if self._lib.nyxb_engine_set_tx_tuning(self._h, slice_attempts, max_ctas) != 0:
+            raise PropagationError(f"set_tx_tuning({slice_attempts}, {max_ctas}): {abi.last_error()}")
+
     def launch_count(self) -> int:
         return self._lib.nyxb_engine_launch_count(self._h)
 

@@ -18,7 +18,7 @@ def test_header_symbols_exported():
     assert declared == set(abi.EXPORTED_SYMBOLS), declared ^ set(abi.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.nyxb_abi_version() == 3
+    assert lib.nyxb_abi_version() == 4
 
 
 def test_struct_layouts_match_header():

@@ -78,14 +78,9 @@ def _walk(gf, lanes, tables, rb):
 
 @pytest.mark.parametrize("fixture,degree,order,lanes", [("jgm3_70x70", 21, 21, 8), ("jgm3_70x70", 21, 21, 16), ("jgm3_70x70", 8, 5, 8),
                                                           ("jgm3_70x70", 70, 70, 32), ("jgm3_70x70", 30, 30, 32), ("luna_jggrx_80x80", 48, 48, 16)])
-@pytest.mark.parametrize("sched", ["default", "aligned", "rounds"])
-def test_cooperative_table_reproduces_oracle_gravity(oracle, monkeypatch, fixture, degree, order, lanes, sched):
-    """`sched`: the default bin packing, and the two experimental column schedules selected by NYXB_COOP_SCHED (same kernel,
-    different tables: `aligned` reorders columns / inserts idle gaps so that lane positions start columns on common entries)."""
-    if sched != "default":
-        monkeypatch.setenv("NYXB_COOP_SCHED", sched)
-    else:
-        monkeypatch.delenv("NYXB_COOP_SCHED", raising=False)
+def test_cooperative_table_reproduces_oracle_gravity(oracle, fixture, degree, order, lanes):
+    """The schedule is the bin packing with aligned column starts (columns reordered / idle gaps inserted so that lane positions
+    start columns on common entries)."""
     moon = fixture.startswith("luna")
     body_frame = nb.IAU_MOON_FRAME if moon else nb.IAU_EARTH_FRAME
     # identity rotation: the harmonic sum is exercised directly in the integration frame
