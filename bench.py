@@ -112,7 +112,7 @@ def build_workload(args, n_total, nb):
     return frame, dyn, almanac, st, cs, ep
 
 
-def c5_scenario(args, nb, n, n_msr, device, truth_on_cpu):
+def c5_scenario(args, nb, n, n_msr, device, truth_on_cpu, fixed_step_s=None):
     """LRO-like orbit determination ensemble (BASELINE configs[4]): dynamics, DSN stations, tracking arc, dispersed initial estimates."""
     from nyx_b200.frames import EARTH
 
@@ -125,6 +125,8 @@ def c5_scenario(args, nb, n, n_msr, device, truth_on_cpu):
     dyn = nb.SpacecraftDynamics.from_model(nb.OrbitalDynamics.new([nb.PointMasses.new([EARTH, nb.SUN]), nb.GravityField.new(gd)]), srp)
     mode = nb.MODE_FAST if args.mode == "fast" else nb.MODE_STRICT
     prop = nb.Propagator.default_dp78(dyn, mode=mode, device=device)   # examples/04_lro_od/main.rs:163
+    if fixed_step_s is not None:   # parity tests: no controller feedback, so the arithmetic itself is compared
+        prop = nb.Propagator.dp78(dyn, nb.IntegratorOptions.with_fixed_step_s(fixed_step_s), mode=mode, device=device)
     orbit = nb.Orbit.keplerian(1737.4 + 100.0, 0.002, 88.0, 20.0, 10.0, 0.0, 0, frame)
     truth0 = nb.Spacecraft(orbit=orbit, mass=nb.Mass(1018.0, 900.0, 0.0), srp=nb.SRPData(3.9 * 2.7, 0.96))
     rn, dn = nb.StochasticNoise(5e-3), nb.StochasticNoise(5e-6)

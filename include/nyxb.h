@@ -69,6 +69,14 @@ typedef struct {
     double tolerance;
     int32_t attempts;    /* u8 in the reference */
     int32_t fixed_step;  /* bool */
+    /* IntegratorOptions.integration_frame (options.rs:60; instance.rs:117-142, 167-176, 211-220).  The engine's dynamics always
+     * describe the INTEGRATION frame.  0: the states handed to nyxb_propagate_batch* are expressed in it (integration_frame = None, or
+     * equal to the state's frame).  k + 1: the states are expressed relative to dynamics.bodies[k] (same inertial axes): they are
+     * translated into the integration frame before the loop with that body's position and velocity at each trajectory's start
+     * epoch (anise `transform_to`), and translated back at the epoch each run ends at.  Recorded trajectories and event scalars are
+     * in the integration frame, as in the reference (the channel sends `self.state` from inside the loop). */
+    int32_t state_center;
+    int32_t _pad;
 } nyxb_integ_opts;
 
 /* ---- Body-fixed frame orientation (what anise `Almanac::rotate` supplies to
@@ -99,6 +107,11 @@ typedef struct {
     const double* c_nm;
     const double* s_nm;
     nyxb_rotation rot;
+    /* The body this field belongs to: NYXB_CENTRAL_BODY (-1) = the integration-frame centre, else an index into
+     * nyxb_dynamics.bodies — the state is translated to that body before the harmonic sum and the acceleration vector is rotated
+     * back unchanged (gravity_field.rs:149-154, 258-267: "needed for multiple harmonic fields"). */
+    int32_t body;
+    int32_t _pad;
 } nyxb_gravity_field;
 
 /* ---- Ephemeris of one celestial body relative to the integration-frame centre,
@@ -118,6 +131,7 @@ typedef struct {
 
 #define NYXB_MAX_BODIES 8
 #define NYXB_CENTRAL_BODY (-1)
+#define NYXB_MAX_FIELDS 3      /* harmonic fields per dynamics (OrbitalDynamics holds a Vec of accel models, orbital.rs:44-46) */
 
 /* ---- SolarPressure + ShadowModel — dynamics/solarpressure.rs:43-49,135-165;
  * cosmic/eclipse.rs:35-83.  Body indices refer to nyxb_dynamics.bodies;
@@ -153,13 +167,16 @@ typedef struct {
     double mu_central_km3_s2;     /* osc.frame.mu_km3_s2()  orbital.rs:86-90 */
     double central_radius_km;     /* used when the centre is a shadow body */
     int32_t n_bodies;
-    int32_t _pad;
+    int32_t n_gravity;            /* entries of `gravity` (0 with gravity != NULL is read as 1: ABI <= 3 callers) */
     const nyxb_body* bodies;      /* ephemerides available to the models */
     uint32_t point_mass_mask;     /* bit j set: bodies[j] acts as PointMasses member (orbital.rs:213-247) */
-    uint32_t _pad2;
-    const nyxb_gravity_field* gravity;  /* NULL: none */
+    int32_t n_point_masses;       /* > 0: `point_mass_order` lists the members in `celestial_objects` order (orbital.rs:217), which is
+                                     the summation order STRICT mode reproduces; 0: ascending body index of the mask */
+    const nyxb_gravity_field* gravity;  /* NULL: none; else n_gravity fields in accel-model order.  gravity[0] is the field the
+                                           cooperative kernels split over lanes / warps; the others are summed per trajectory */
     const nyxb_srp* srp;                /* NULL: none */
     const nyxb_drag* drag;              /* NULL: none */
+    int32_t point_mass_order[NYXB_MAX_BODIES];
 } nyxb_dynamics;
 
 /* ---- IntegrationDetails (propagators/mod.rs:49-56) + counters for the metric ---- */
@@ -446,7 +463,9 @@ int32_t nyxb_od_ekf_batch(nyxb_engine* eng, const nyxb_od_config* cfg,
  * run's draw does not depend on how the ensemble is sharded (the reference's serial Pcg64Mcg + ziggurat stream,
  * mc/montecarlo.rs:277-296, is not reproduced: DESIGN.md §3).
  *  template_state[9], mean[9] (NULL = 0), sqrt_s_v[81] row-major (V * sqrt(S) of the covariance's SVD, multivariate.rs:237-247)
- *  out_state_soa [9][n], out_dispersion_soa [9][n] or NULL (the x_i themselves).  `_dev`: device pointers, stream-ordered. */
+ *  out_state_soa [9][n], out_dispersion_soa [9][n] or NULL (the x_i themselves).
+ * `_dev`: ONLY out_state_soa / out_dispersion_soa are device pointers (stream-ordered launch); template_state, mean and sqrt_s_v
+ * are HOST pointers in both variants — they are read on the host into the kernel's parameter block. */
 int32_t nyxb_mvn_sample(int32_t device, uint64_t seed, uint64_t first_index, size_t n,
                         const double* template_state, const double* mean, const double* sqrt_s_v,
                         double* out_state_soa, double* out_dispersion_soa);

@@ -165,13 +165,20 @@ inline EnginePtr make_engine(const SpacecraftDynamics& dyn, const Frame& frame, 
     d.n_bodies = (int32_t)bodies.size();
     d.bodies = bodies.data();
     if (dyn.orbital_dyn.point_masses_)
-        for (int32_t id : dyn.orbital_dyn.point_masses_->celestial_objects)
-            if (id != frame.ephemeris_id) d.point_mass_mask |= 1u << body_index(id);  // orbital.rs:219-222
+        for (int32_t id : dyn.orbital_dyn.point_masses_->celestial_objects) {   // summation order of orbital.rs:217
+            if (id == frame.ephemeris_id) continue;                              // orbital.rs:219-222
+            const int32_t j = body_index(id);
+            if (!((d.point_mass_mask >> j) & 1u)) d.point_mass_order[d.n_point_masses++] = j;
+            d.point_mass_mask |= 1u << j;
+        }
     nyxb_gravity_field g{};
     if (dyn.orbital_dyn.gravity_) {
         const auto& gd = dyn.orbital_dyn.gravity_->grav_data;
-        g = nyxb_gravity_field{gd.degree, gd.order, gd.frame.mu_km3_s2, gd.frame.mean_equatorial_radius_km, gd.c_nm.data(), gd.s_nm.data(), gd.frame.rotation};
+        // a field of another body than the integration centre is evaluated about that body (gravity_field.rs:149-154)
+        const int32_t gbody = gd.frame.ephemeris_id == frame.ephemeris_id ? NYXB_CENTRAL_BODY : body_index(gd.frame.ephemeris_id);
+        g = nyxb_gravity_field{gd.degree, gd.order, gd.frame.mu_km3_s2, gd.frame.mean_equatorial_radius_km, gd.c_nm.data(), gd.s_nm.data(), gd.frame.rotation, gbody, 0};
         d.gravity = &g;
+        d.n_gravity = 1;
     }
     nyxb_srp s{};
     if (dyn.srp) {

@@ -12,6 +12,7 @@ from pathlib import Path
 import numpy as np
 
 NYXB_ABI_VERSION = 4  # include/nyxb.h
+NYXB_MAX_FIELDS = 3
 KERNEL_AUTO, KERNEL_THREAD, KERNEL_COOP, KERNEL_TRANSPOSED = 0, 1, 2, 3  # enum nyxb_kernel
 NYXB_MAX_BODIES = 8
 NYXB_CENTRAL_BODY = -1
@@ -45,6 +46,8 @@ class IntegOpts(C.Structure):
         ("tolerance", C.c_double),
         ("attempts", C.c_int32),
         ("fixed_step", C.c_int32),
+        ("state_center", C.c_int32),   # integration_frame: 0 none, k + 1: the states are relative to dynamics.bodies[k]
+        ("_pad", C.c_int32),
     ]
 
 
@@ -70,6 +73,8 @@ class GravityFieldC(C.Structure):
         ("c_nm", c_double_p),
         ("s_nm", c_double_p),
         ("rot", Rotation),
+        ("body", C.c_int32),   # NYXB_CENTRAL_BODY or index into DynamicsC.bodies: the body the field belongs to
+        ("_pad", C.c_int32),
     ]
 
 
@@ -113,13 +118,14 @@ class DynamicsC(C.Structure):
         ("mu_central_km3_s2", C.c_double),
         ("central_radius_km", C.c_double),
         ("n_bodies", C.c_int32),
-        ("_pad", C.c_int32),
+        ("n_gravity", C.c_int32),
         ("bodies", C.POINTER(BodyC)),
         ("point_mass_mask", C.c_uint32),
-        ("_pad2", C.c_uint32),
-        ("gravity", C.POINTER(GravityFieldC)),
+        ("n_point_masses", C.c_int32),
+        ("gravity", C.POINTER(GravityFieldC)),   # array of n_gravity fields, accel-model order
         ("srp", C.POINTER(SrpC)),
         ("drag", C.POINTER(DragC)),
+        ("point_mass_order", C.c_int32 * 8),
     ]
 
 

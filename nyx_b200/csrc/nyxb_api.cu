@@ -24,6 +24,7 @@ extern "C" cudaError_t nyxb_launch_thread_fast(const DevSetup*, size_t, const do
                                                long long, long long*, double*, long long*, nyxb_details*, int*, int,
                                                const DevSink*, cudaStream_t);
 extern "C" double nyxb_fp64_probe(int device, int iters);
+extern "C" cudaError_t nyxb_launch_frame_shift(const DevBody*, double, size_t, double*, const long long*, int*, cudaStream_t);
 extern "C" cudaError_t nyxb_launch_od_coop(const DevSetup*, const DevOd*, const int*, size_t, const double*, const double*, const long long*,
                                            double*, long long*, nyxb_details*, int*, cudaStream_t);
 extern "C" int nyxb_od_coop_kmax(void);
@@ -35,7 +36,7 @@ extern "C" cudaError_t nyxb_launch_mvn(unsigned long long, unsigned long long, s
                                        double*, double*, cudaStream_t);
 
 // layout of the PODs the host mirrors rely on (nyx_b200/abi.py, tests/test_abi.py)
-static_assert(sizeof(nyxb_integ_opts) == 48 && sizeof(nyxb_rotation) == 56 && sizeof(nyxb_srp) == 40 && sizeof(nyxb_details) == 48, "ABI layout");
+static_assert(sizeof(nyxb_integ_opts) == 56 && sizeof(nyxb_gravity_field) == 104 && sizeof(nyxb_dynamics) == 96 && sizeof(nyxb_rotation) == 56 && sizeof(nyxb_srp) == 40 && sizeof(nyxb_details) == 48, "ABI layout");
 static_assert(sizeof(nyxb_ground_station) == 176 && sizeof(nyxb_od_config) == 72 && sizeof(nyxb_tracking_arc) == 32 && sizeof(nyxb_od_outputs) == 96, "ABI layout");
 
 static thread_local std::string g_err;
@@ -80,10 +81,12 @@ struct nyxb_engine {
     size_t txq_bytes = 0;                  // grow-only queue + parking workspace of the transposed kernel
     unsigned char* d_txq = nullptr;
     int sms = 0;
+    size_t frame_n = 0;                    // grow-only copy of the input states translated into the integration frame
+    double* d_frame = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ~nyxb_engine() {
         for (void* p : dev_allocs) cudaFree(p);
-        cudaFree(d_f64); cudaFree(d_i64); cudaFree(d_det); cudaFree(d_status); cudaFree(d_sink); cudaFree(d_txq);
+        cudaFree(d_f64); cudaFree(d_i64); cudaFree(d_det); cudaFree(d_status); cudaFree(d_sink); cudaFree(d_txq); cudaFree(d_frame);
         if (stream) cudaStreamDestroy(stream);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -133,6 +136,89 @@ static T* upload(nyxb_engine* e, const T* host, size_t count) {
     e->dev_allocs.push_back(d);
     if (count && cudaMemcpy(d, host, sizeof(T) * count, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
     return d;
+}
+
+// GravityField::new (gravity_field.rs:52-92) for one field: recursion factors, diagonal, per-thread column-walk records
+static bool build_grav(nyxb_engine* e, const nyxb_gravity_field& g, DevGrav& G, bool primary) {
+        if (g.degree < 1 || g.degree > NYXB_MAX_DEGREE || g.order < 0 || g.order > g.degree) {
+            set_err("gravity field degree/order out of range (1..96)"); return false;
+        }
+        const int N = g.degree, np2 = N + 2;
+        G.N = N; G.M = g.order; G.mu = g.mu_km3_s2; G.r_eq = g.r_eq_km; G.inv_r_eq = 1.0 / g.r_eq_km;
+        G.rot = pack_rot(g.rot);
+        // GravityField::new gravity_field.rs:52-92 (same formulas; sqrt and / are correctly rounded)
+        std::vector<double> adiag(N + 3), offd(N + 2);
+        adiag[0] = 1.0;
+        for (int n = 1; n <= np2; ++n) {
+            double nf = (double)n;
+            volatile double t = 1.0 + 1.0 / (2.0 * nf);
+            volatile double s = std::sqrt(t);
+            volatile double v = s * adiag[n - 1];
+            adiag[n] = v;
+        }
+        for (int n = 0; n <= N + 1; ++n) offd[n] = std::sqrt(2.0 * (double)n + 3.0);
+        std::vector<DevHarm> tab((size_t)(N + 2) * (N + 3) / 2);
+        const double sqrt2 = std::sqrt(2.0);
+        for (int n = 0; n <= N + 1; ++n) {
+            for (int m = 0; m <= n; ++m) {
+                double nf = (double)n, mf = (double)m;
+                DevHarm h;
+                volatile double cnum = (2.0 * nf + 1.0) * (nf + mf - 1.0) * (nf - mf - 1.0);
+                volatile double cden = (nf - mf) * (nf + mf) * (2.0 * nf - 3.0);
+                volatile double cq = cnum / cden;
+                h.c = std::sqrt(cq);
+                volatile double bnum = (2.0 * nf + 1.0) * (2.0 * nf - 1.0);
+                volatile double bden = (nf + mf) * (nf - mf);
+                volatile double bq = bnum / bden;
+                h.b = std::sqrt(bq);
+                volatile double v01 = (nf - mf) * (nf + mf + 1.0);
+                h.vr01 = std::sqrt(v01);
+                volatile double v11n = (2.0 * nf + 1.0) * (nf + mf + 2.0) * (nf + mf + 1.0);
+                volatile double v11 = v11n / (2.0 * nf + 3.0);
+                h.vr11 = std::sqrt(v11);
+                if (m == 0) { h.vr01 = h.vr01 / sqrt2; h.vr11 = h.vr11 / sqrt2; }
+                if (n <= N) { h.cbar = g.c_nm[(size_t)n * (N + 1) + m]; h.sbar = g.s_nm[(size_t)n * (N + 1) + m]; }
+                else { h.cbar = 0.0; h.sbar = 0.0; }
+                if (!(n >= m + 2)) { h.b = 0.0; h.c = 0.0; }  // never read; avoid NaN/inf noise
+                tab[(size_t)n * (n + 1) / 2 + m] = h;
+            }
+        }
+        if (primary) {
+            e->h_cnm.assign(g.c_nm, g.c_nm + (size_t)(N + 1) * (N + 1));
+            e->h_snm.assign(g.s_nm, g.s_nm + (size_t)(N + 1) * (N + 1));
+        }
+        G.tab = upload(e, tab.data(), tab.size());
+        G.a_diag = upload(e, adiag.data(), adiag.size());
+        G.offdiag = upload(e, offd.data(), offd.size());
+        {   // records of the FAST per-thread column walk (grav_accel_cols, nyxb_device.cuh), in walk order
+            const int ncols = std::min(N, g.order) + 1;
+            auto T = [&](int n, int m) -> const DevHarm& { return tab[(size_t)n * (n + 1) / 2 + m]; };
+            std::vector<double> cr;
+            cr.reserve((size_t)ncols * (N + 2) * 8);
+            const double inv_req = 1.0 / g.r_eq_km;
+            auto push = [&](int k, int j) {
+                double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (j <= N && k <= g.order) { v[0] = (double)k * sqrt2 * T(j, k).cbar * inv_req; v[1] = (double)k * sqrt2 * T(j, k).sbar * inv_req; }
+                if (j <= N) { v[2] = sqrt2 * T(j, k - 1).vr01 * T(j, k - 1).cbar * inv_req; v[3] = sqrt2 * T(j, k - 1).vr01 * T(j, k - 1).sbar * inv_req; }
+                if (j >= 2) { v[4] = sqrt2 * T(j - 1, k - 1).vr11 * T(j - 1, k - 1).cbar * inv_req; v[5] = sqrt2 * T(j - 1, k - 1).vr11 * T(j - 1, k - 1).sbar * inv_req; }
+                if (j <= N) {
+                    if (j == k) { v[6] = offd[k]; v[7] = 0.0; }
+                    else { v[6] = T(j + 1, k).b; v[7] = T(j + 1, k).c; }
+                }
+                cr.insert(cr.end(), v, v + 8);
+            };
+            for (int k = 1; k <= ncols; k += 2) {   // walk order of grav_accel_cols: columns in pairs, rows interleaved
+                const bool two = k + 1 <= ncols;
+                push(k, k);
+                for (int j = k + 1; j <= N + 1; ++j) { push(k, j); if (two) push(k + 1, j); }
+            }
+            cr.insert(cr.end(), 16, 0.0);           // two null records: targets of the last prefetches
+            G.colrec = upload(e, cr.data(), cr.size());
+            G.ncols = ncols;
+            if (!G.colrec) { set_err("gravity table upload failed"); return false; }
+        }
+        if (!G.tab || !G.a_diag || !G.offdiag) { set_err("gravity table upload failed"); return false; }
+    return true;
 }
 
 extern "C" nyxb_engine* nyxb_engine_create(const nyxb_dynamics* dyn, const nyxb_integ_opts* opts, int32_t mode,
@@ -192,6 +278,23 @@ extern "C" nyxb_engine* nyxb_engine_create(const nyxb_dynamics* dyn, const nyxb_
     S.central_radius = dyn->central_radius_km;
     S.n_bodies = dyn->n_bodies;
     S.point_mass_mask = dyn->point_mass_mask;
+    S.n_pm = 0;
+    if (dyn->n_point_masses > 0) {   // `celestial_objects` order (orbital.rs:217)
+        if (dyn->n_point_masses > dyn->n_bodies) { set_err("n_point_masses out of range"); delete e; return nullptr; }
+        for (int q = 0; q < dyn->n_point_masses; ++q) {
+            const int j = dyn->point_mass_order[q];
+            if (j < 0 || j >= dyn->n_bodies) { set_err("point_mass_order: bad body index"); delete e; return nullptr; }
+            S.pm_order[S.n_pm++] = (signed char)j;
+        }
+    } else {
+        for (int j = 0; j < dyn->n_bodies; ++j)
+            if ((dyn->point_mass_mask >> j) & 1u) S.pm_order[S.n_pm++] = (signed char)j;
+    }
+    S.state_center = -1;
+    if (opts->state_center != 0) {
+        if (opts->state_center < 0 || opts->state_center > dyn->n_bodies) { set_err("state_center: bad body index"); delete e; return nullptr; }
+        S.state_center = opts->state_center - 1;
+    }
     for (int j = 0; j < dyn->n_bodies; ++j) {
         const nyxb_body& hb = dyn->bodies[j];
         DevBody& db = S.bodies[j];
@@ -201,85 +304,21 @@ extern "C" nyxb_engine* nyxb_engine_create(const nyxb_dynamics* dyn, const nyxb_
         db.coeffs = upload(e, hb.coeffs, (size_t)hb.n_intervals * 3 * hb.n_coeffs);
         if (!db.coeffs) { set_err("ephemeris upload failed"); delete e; return nullptr; }
     }
-    if (dyn->gravity) {
-        const nyxb_gravity_field& g = *dyn->gravity;
-        if (g.degree < 1 || g.degree > NYXB_MAX_DEGREE || g.order < 0 || g.order > g.degree) {
-            set_err("gravity field degree/order out of range (1..96)"); delete e; return nullptr;
+    const int n_grav = dyn->gravity ? std::max(1, dyn->n_gravity) : 0;
+    if (n_grav > NYXB_MAX_FIELDS) { set_err("too many gravity fields"); delete e; return nullptr; }
+    S.grav_body = NYXB_CENTRAL_BODY;
+    for (int f = 0; f < n_grav; ++f) {
+        const nyxb_gravity_field& g = dyn->gravity[f];
+        if (g.body != NYXB_CENTRAL_BODY && (g.body < 0 || g.body >= dyn->n_bodies)) { set_err("gravity field: bad body index"); delete e; return nullptr; }
+        if (f == 0) {
+            if (!build_grav(e, g, S.grav, true)) { delete e; return nullptr; }
+            S.has_grav = 1;
+            S.grav_body = g.body;
+        } else {
+            if (!build_grav(e, g, S.xgrav[f - 1], false)) { delete e; return nullptr; }
+            S.xgrav_body[f - 1] = g.body;
+            S.n_xgrav = f;
         }
-        const int N = g.degree, np2 = N + 2;
-        S.has_grav = 1;
-        S.grav.N = N; S.grav.M = g.order; S.grav.mu = g.mu_km3_s2; S.grav.r_eq = g.r_eq_km; S.grav.inv_r_eq = 1.0 / g.r_eq_km;
-        S.grav.rot = pack_rot(g.rot);
-        // GravityField::new gravity_field.rs:52-92 (same formulas; sqrt and / are correctly rounded)
-        std::vector<double> adiag(N + 3), offd(N + 2);
-        adiag[0] = 1.0;
-        for (int n = 1; n <= np2; ++n) {
-            double nf = (double)n;
-            volatile double t = 1.0 + 1.0 / (2.0 * nf);
-            volatile double s = std::sqrt(t);
-            volatile double v = s * adiag[n - 1];
-            adiag[n] = v;
-        }
-        for (int n = 0; n <= N + 1; ++n) offd[n] = std::sqrt(2.0 * (double)n + 3.0);
-        std::vector<DevHarm> tab((size_t)(N + 2) * (N + 3) / 2);
-        const double sqrt2 = std::sqrt(2.0);
-        for (int n = 0; n <= N + 1; ++n) {
-            for (int m = 0; m <= n; ++m) {
-                double nf = (double)n, mf = (double)m;
-                DevHarm h;
-                volatile double cnum = (2.0 * nf + 1.0) * (nf + mf - 1.0) * (nf - mf - 1.0);
-                volatile double cden = (nf - mf) * (nf + mf) * (2.0 * nf - 3.0);
-                volatile double cq = cnum / cden;
-                h.c = std::sqrt(cq);
-                volatile double bnum = (2.0 * nf + 1.0) * (2.0 * nf - 1.0);
-                volatile double bden = (nf + mf) * (nf - mf);
-                volatile double bq = bnum / bden;
-                h.b = std::sqrt(bq);
-                volatile double v01 = (nf - mf) * (nf + mf + 1.0);
-                h.vr01 = std::sqrt(v01);
-                volatile double v11n = (2.0 * nf + 1.0) * (nf + mf + 2.0) * (nf + mf + 1.0);
-                volatile double v11 = v11n / (2.0 * nf + 3.0);
-                h.vr11 = std::sqrt(v11);
-                if (m == 0) { h.vr01 = h.vr01 / sqrt2; h.vr11 = h.vr11 / sqrt2; }
-                if (n <= N) { h.cbar = g.c_nm[(size_t)n * (N + 1) + m]; h.sbar = g.s_nm[(size_t)n * (N + 1) + m]; }
-                else { h.cbar = 0.0; h.sbar = 0.0; }
-                if (!(n >= m + 2)) { h.b = 0.0; h.c = 0.0; }  // never read; avoid NaN/inf noise
-                tab[(size_t)n * (n + 1) / 2 + m] = h;
-            }
-        }
-        e->h_cnm.assign(g.c_nm, g.c_nm + (size_t)(N + 1) * (N + 1));
-        e->h_snm.assign(g.s_nm, g.s_nm + (size_t)(N + 1) * (N + 1));
-        S.grav.tab = upload(e, tab.data(), tab.size());
-        S.grav.a_diag = upload(e, adiag.data(), adiag.size());
-        S.grav.offdiag = upload(e, offd.data(), offd.size());
-        {   // records of the FAST per-thread column walk (grav_accel_cols, nyxb_device.cuh), in walk order
-            const int ncols = std::min(N, g.order) + 1;
-            auto T = [&](int n, int m) -> const DevHarm& { return tab[(size_t)n * (n + 1) / 2 + m]; };
-            std::vector<double> cr;
-            cr.reserve((size_t)ncols * (N + 2) * 8);
-            const double inv_req = 1.0 / g.r_eq_km;
-            auto push = [&](int k, int j) {
-                double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                if (j <= N && k <= g.order) { v[0] = (double)k * sqrt2 * T(j, k).cbar * inv_req; v[1] = (double)k * sqrt2 * T(j, k).sbar * inv_req; }
-                if (j <= N) { v[2] = sqrt2 * T(j, k - 1).vr01 * T(j, k - 1).cbar * inv_req; v[3] = sqrt2 * T(j, k - 1).vr01 * T(j, k - 1).sbar * inv_req; }
-                if (j >= 2) { v[4] = sqrt2 * T(j - 1, k - 1).vr11 * T(j - 1, k - 1).cbar * inv_req; v[5] = sqrt2 * T(j - 1, k - 1).vr11 * T(j - 1, k - 1).sbar * inv_req; }
-                if (j <= N) {
-                    if (j == k) { v[6] = offd[k]; v[7] = 0.0; }
-                    else { v[6] = T(j + 1, k).b; v[7] = T(j + 1, k).c; }
-                }
-                cr.insert(cr.end(), v, v + 8);
-            };
-            for (int k = 1; k <= ncols; k += 2) {   // walk order of grav_accel_cols: columns in pairs, rows interleaved
-                const bool two = k + 1 <= ncols;
-                push(k, k);
-                for (int j = k + 1; j <= N + 1; ++j) { push(k, j); if (two) push(k + 1, j); }
-            }
-            cr.insert(cr.end(), 16, 0.0);           // two null records: targets of the last prefetches
-            S.grav.colrec = upload(e, cr.data(), cr.size());
-            S.grav.ncols = ncols;
-            if (!S.grav.colrec) { set_err("gravity table upload failed"); delete e; return nullptr; }
-        }
-        if (!S.grav.tab || !S.grav.a_diag || !S.grav.offdiag) { set_err("gravity table upload failed"); delete e; return nullptr; }
     }
     if (dyn->srp) {
         const nyxb_srp& s = *dyn->srp;
@@ -431,9 +470,34 @@ static int pick_kernel(const nyxb_engine* e, size_t n) {
     return NYXB_KERNEL_AUTO;
 }
 
+static int32_t launch_inner(nyxb_engine* e, size_t n, const double* state, const double* consts, const int64_t* epoch0,
+                            int64_t end_epoch, int64_t* step_io, double* out_state, int64_t* out_epoch,
+                            nyxb_details* out_details, int32_t* out_status, const DevSink& sink, cudaStream_t stream);
+
+// propagation launch with the integration_frame translations around it (instance.rs:117-142, 167-176, 211-220)
 static int32_t launch(nyxb_engine* e, size_t n, const double* state, const double* consts, const int64_t* epoch0,
                       int64_t end_epoch, int64_t* step_io, double* out_state, int64_t* out_epoch,
                       nyxb_details* out_details, int32_t* out_status, const DevSink& sink, cudaStream_t stream) {
+    if (e->S.state_center < 0 || n == 0)
+        return launch_inner(e, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, sink, stream);
+    if (n > e->frame_n) {
+        cudaFree(e->d_frame); e->d_frame = nullptr; e->frame_n = 0;
+        CUDA_TRY(cudaMalloc(&e->d_frame, sizeof(double) * 9 * n));
+        e->frame_n = n;
+    }
+    const DevBody* body = &e->S.bodies[e->S.state_center];
+    CUDA_TRY(cudaMemcpyAsync(e->d_frame, state, sizeof(double) * 9 * n, cudaMemcpyDeviceToDevice, stream));
+    CUDA_TRY(nyxb_launch_frame_shift(body, 1.0, n, e->d_frame, (const long long*)epoch0, nullptr, stream));
+    const int32_t rc = launch_inner(e, n, e->d_frame, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, sink, stream);
+    if (rc != NYXB_RC_OK) return rc;
+    CUDA_TRY(nyxb_launch_frame_shift(body, -1.0, n, out_state, (const long long*)out_epoch, out_status, stream));
+    e->launches += 2;
+    return NYXB_RC_OK;
+}
+
+static int32_t launch_inner(nyxb_engine* e, size_t n, const double* state, const double* consts, const int64_t* epoch0,
+                            int64_t end_epoch, int64_t* step_io, double* out_state, int64_t* out_epoch,
+                            nyxb_details* out_details, int32_t* out_status, const DevSink& sink, cudaStream_t stream) {
     if (pick_kernel(e, n) == NYXB_KERNEL_TRANSPOSED)
         return launch_tx(e, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, sink, stream);
     int lanes = pick_lanes(e, n);
@@ -538,6 +602,7 @@ extern "C" int32_t nyxb_propagate_batch_event(nyxb_engine* eng, size_t n, const 
     DevSink dsink{};
     if (has_ev) { dsink.ev_kind = event->kind; dsink.ev_trigger = event->trigger; dsink.ev_value = event->value; dsink.ev_crossings = d_status + n; }
     const bool rec = sink && sink->capacity > 0 && sink->epoch_ns && sink->state && sink->count;
+    eng->rec_n = 0; eng->rec_cap = 0;   // a propagation that does not record invalidates the resident recording (sink == NULL calls)
     if (rec) {
         const size_t cap = (size_t)sink->capacity;
         const size_t need = (cap * n * 7 + n) * 8;
@@ -615,6 +680,10 @@ struct DevBufs {
     }
 };
 bool stm_supported(const nyxb_engine* e) {
+    if (e->S.grav_body >= 0 || e->S.n_xgrav > 0 || e->S.state_center >= 0) {
+        set_err("the STM / filter kernels take one harmonic field, of the integration centre, and states in the integration frame");
+        return false;
+    }
     if (e->S.has_drag) { set_err("PartialsUndefined: the drag model has no partials (drag.rs:109-118, 286-295)"); return false; }
     if (!e->S.fixed_step && e->S.error_ctrl != NYXB_RSS_CARTESIAN_STATE && e->S.error_ctrl != NYXB_RSS_CARTESIAN_STEP) {
         set_err("STM propagation accepts the Cartesian error controls or a fixed step");

@@ -107,6 +107,7 @@ static __device__ __noinline__ int coop_extra(const DevSetup& S, double dry_mass
     double bpos[NYXB_MAX_BODIES][3];
     int rc = accel_point_masses(S, t_ns, y, bpos, acc);
     if (rc) return rc;
+    accel_extra_fields(S, t_ns, y, bpos, acc);
     if (has_force) accel_post(S, t_ns, y, bpos, mass, srp_area, drag_area, acc);
     return 0;
 }
@@ -148,7 +149,11 @@ __device__ __forceinline__ void coop_rhs(const DevSetup& S, const double* __rest
             R[3] = fma(cw, b10, -(sw * b00)); R[4] = fma(cw, b11, -(sw * b01)); R[5] = cw * b12;
             R[6] = cd * ca; R[7] = cd * sa; R[8] = sd;
         }
-        const double y0 = g[t].ys[0], y1 = g[t].ys[1], y2 = g[t].ys[2];
+        double y0 = g[t].ys[0], y1 = g[t].ys[1], y2 = g[t].ys[2];
+        if (S.grav_body >= 0) {   // field of another body: the state is translated to it first (gravity_field.rs:149-154)
+            double bp[3];
+            if (body_position(S.bodies[S.grav_body], t_ns[t], bp)) { y0 -= bp[0]; y1 -= bp[1]; y2 -= bp[2]; }   // out of coverage: reported by coop_extra
+        }
         const double rb0 = fma(R[2], y2, fma(R[1], y1, R[0] * y0));
         const double rb1 = fma(R[5], y2, fma(R[4], y1, R[3] * y0));
         const double rb2 = fma(R[8], y2, fma(R[7], y1, R[6] * y0));
@@ -299,22 +304,28 @@ __device__ __forceinline__ void coop_rhs(const DevSetup& S, const double* __rest
         double R[9];
 #pragma unroll
         for (int q = 0; q < 9; ++q) R[q] = g[t].nxt[q];
-        const double s_ = fma(R[2], y[2], fma(R[1], y[1], R[0] * y[0])) * inv_r[t];
-        const double t_ = fma(R[5], y[2], fma(R[4], y[1], R[3] * y[0])) * inv_r[t];
-        const double u_ = fma(R[8], y[2], fma(R[7], y[1], R[6] * y[0])) * inv_r[t];
+        double q0 = y[0], q1 = y[1], q2 = y[2];   // position relative to the field's body
+        if (S.grav_body >= 0) {
+            double bp[3];
+            if (body_position(S.bodies[S.grav_body], t_ns[t], bp)) { q0 -= bp[0]; q1 -= bp[1]; q2 -= bp[2]; }
+        }
+        const double s_ = fma(R[2], q2, fma(R[1], q1, R[0] * q0)) * inv_r[t];
+        const double t_ = fma(R[5], q2, fma(R[4], q1, R[3] * q0)) * inv_r[t];
+        const double u_ = fma(R[8], q2, fma(R[7], q1, R[6] * q0)) * inv_r[t];
         // rr_n A[n][m] = K0 rho (rho^n A),  rr_{n-1} A[n][m] = K0 (rho^n A),  K0 = mu / (r R_eq)
         const double K0 = (gv.mu * gv.inv_r_eq) * inv_r[t];
         const double K1 = K0 * rho[t];
         const double aw = -K0 * W[t];
         const double ab0 = fma(aw, s_, K1 * X[t]), ab1 = fma(aw, t_, K1 * Y[t]), ab2 = fma(aw, u_, K1 * Z[t]);
-        // two-body (orbital.rs:86-92) from the same 1/r
-        const double fac = -S.mu_central * inv_r[t] * inv_r[t] * inv_r[t];
+        // two-body (orbital.rs:86-92): from the same 1/r when the field belongs to the centre
+        const double ir_c = (S.grav_body >= 0) ? rsqrt(fma(y[2], y[2], fma(y[1], y[1], y[0] * y[0]))) : inv_r[t];
+        const double fac = -S.mu_central * ir_c * ir_c * ir_c;
         double acc[3];
         acc[0] = fma(fac, y[0], fma(R[6], ab2, fma(R[3], ab1, R[0] * ab0)));
         acc[1] = fma(fac, y[1], fma(R[7], ab2, fma(R[4], ab1, R[1] * ab0)));
         acc[2] = fma(fac, y[2], fma(R[8], ab2, fma(R[5], ab1, R[2] * ab0)));
         rc[t] = 0;
-        if (S.n_bodies > 0 || S.has_srp || S.has_drag) {
+        if (S.n_bodies > 0 || S.has_srp || S.has_drag || S.n_xgrav > 0) {
             // cold path: private copies, so that y/acc of the common path are never address-taken (they stay in registers)
             double yy[9], aa[3];
 #pragma unroll
@@ -522,8 +533,10 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
                 if (rcs[t]) { rc[t] = rcs[t]; done[t] = true; continue; }
                 if (lane < 6) g[t].kst[i * 6 + lane] = dyc[t];
             }
+            // every lane read the stage state (ys) and the parked DCM (nxt) at the end of coop_rhs: order those reads before the
+            // next stage's writes (compute-sanitizer racecheck, profiles/r02b_racecheck_coop.log: write-after-read on ys)
+            __syncwarp(FULL);
         }
-        __syncwarp(FULL);  // the last stage's readers of the parked DCM (nxt) are done
 #pragma unroll
         for (int t = 0; t < T; ++t) {
             double er = 0.0;

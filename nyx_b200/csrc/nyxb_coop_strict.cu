@@ -75,6 +75,9 @@ struct SCtx {
 static __device__ __noinline__ int scoop_pre(const DevSetup& S, long long t_ns, const double y[9], double bpos[NYXB_MAX_BODIES][3], double acc[3]) {
     return accel_pre(S, t_ns, y, bpos, acc);
 }
+static __device__ __noinline__ void scoop_xfields(const DevSetup& S, long long t_ns, const double y[9], const double bpos[NYXB_MAX_BODIES][3], double acc[3]) {
+    accel_extra_fields(S, t_ns, y, bpos, acc);
+}
 static __device__ __noinline__ void scoop_post(const DevSetup& S, const SCtx& g, long long t_ns, const double y[9],
                                                const double bpos[NYXB_MAX_BODIES][3], double mass, double acc[3]) {
     accel_post(S, t_ns, y, bpos, mass, g.srp_area, g.drag_area, acc);
@@ -122,9 +125,10 @@ __device__ __forceinline__ int scoop_rhs(const DevSetup& S, const DevCoopStrict&
         R[3] = cw * b10 - sw * b00; R[4] = cw * b11 - sw * b01; R[5] = cw * b12 - sw * b02;
         R[6] = b20; R[7] = b21; R[8] = b22;
     }
-    double rb[3];
+    double rb[3], rel[3];
+    grav_rel(S.grav_body, y, bpos, rel);   // field of another body: the state is translated to it first (gravity_field.rs:149-154)
 #pragma unroll
-    for (int i = 0; i < 3; ++i) rb[i] = (R[3 * i] * y[0] + R[3 * i + 1] * y[1]) + R[3 * i + 2] * y[2];
+    for (int i = 0; i < 3; ++i) rb[i] = (R[3 * i] * rel[0] + R[3 * i + 1] * rel[1]) + R[3 * i + 2] * rel[2];
     const double r_ = norm3(rb[0], rb[1], rb[2]);
     const double s_ = rb[0] / r_, t_ = rb[1] / r_, u_ = rb[2] / r_;
 
@@ -218,6 +222,7 @@ __device__ __forceinline__ int scoop_rhs(const DevSetup& S, const DevCoopStrict&
     const double ab0 = a4x + a4w * s_, ab1 = a4y + a4w * t_, ab2 = a4z + a4w * u_;
 #pragma unroll
     for (int i = 0; i < 3; ++i) acc[i] += (R[i] * ab0 + R[3 + i] * ab1) + R[6 + i] * ab2;
+    if (S.n_xgrav > 0) scoop_xfields(S, t_ns, y, bpos, acc);
     if (has_force) scoop_post(S, g, t_ns, y, bpos, mass, acc);
     double out = y[3];
     if (lane == 1) out = y[4];

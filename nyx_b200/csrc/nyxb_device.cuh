@@ -88,9 +88,16 @@ struct DevSetup {
     double mu_central, central_radius;
     int n_bodies;
     unsigned point_mass_mask;
+    int n_pm;                         // PointMasses members in summation order (orbital.rs:217)
+    signed char pm_order[NYXB_MAX_BODIES];
     DevBody bodies[NYXB_MAX_BODIES];
     int has_grav, has_srp, has_drag;
+    int grav_body;                    // body the primary field belongs to (NYXB_CENTRAL_BODY or an index into bodies)
+    int n_xgrav;                      // further harmonic fields, evaluated per trajectory after the primary one
+    int xgrav_body[NYXB_MAX_FIELDS - 1];
+    int state_center;                 // integration_frame: -1 none, else the body the caller's states are relative to
     DevGrav grav;
+    DevGrav xgrav[NYXB_MAX_FIELDS - 1];
     DevSrp srp;
     DevDrag drag;
 };
@@ -277,6 +284,31 @@ __device__ __forceinline__ bool body_position(const DevBody& b, long long t_ns, 
     pos[1] = fma(tau, y1, __ldg(cy) - y2);
     pos[2] = fma(tau, z1, __ldg(cz) - z2);
 #endif
+    return true;
+}
+
+// d/dt of the Chebyshev ephemeris (sum_k c_k T_k'(tau) * 2 / interval), reference operation order in every build: used where
+// anise differentiates an SPK segment — frame translations (integration_frame, instance.rs:117-142) and tracking geometry
+__device__ static bool body_velocity(const DevBody& b, long long t_ns, double vel[3]) {
+    long long dt = t_ns - b.t0_ns;
+    if (dt < 0) return false;
+    long long idx = dt / b.interval_ns;
+    if (idx >= b.n_intervals) return false;
+    long long off = dt - idx * b.interval_ns;
+    double tau = __dsub_rn(__dmul_rn(2.0, __ddiv_rn((double)off, (double)b.interval_ns)), 1.0);
+    double tau2 = __dmul_rn(2.0, tau);
+    int nc = b.n_coeffs;
+    const double* c = b.coeffs + (size_t)idx * 3 * (size_t)nc;
+    double scale = __ddiv_rn(2.0, __dmul_rn((double)b.interval_ns, 1e-9));
+    for (int ax = 0; ax < 3; ++ax) {
+        const double* ca = c + ax * nc;
+        double b1 = 0.0, b2 = 0.0;
+        for (int j = nc - 2; j >= 0; --j) {
+            double bj = __dsub_rn(__dadd_rn(__dmul_rn((double)(j + 1), __ldg(ca + j + 1)), __dmul_rn(tau2, b1)), b2);
+            b2 = b1; b1 = bj;
+        }
+        vel[ax] = __dmul_rn(b1, scale);
+    }
     return true;
 }
 
@@ -520,10 +552,10 @@ __device__ inline int accel_point_masses(const DevSetup& S, long long t_ns, cons
                                          double bpos[NYXB_MAX_BODIES][3], double acc[3]) {
     for (int j = 0; j < S.n_bodies; ++j)
         if (!body_position(S.bodies[j], t_ns, bpos[j])) return NYXB_ERR_EPHEMERIS;
-    if (S.point_mass_mask) {
+    if (S.n_pm) {
         double dx[3] = {0.0, 0.0, 0.0};
-        for (int j = 0; j < S.n_bodies; ++j) {
-            if (!((S.point_mass_mask >> j) & 1u)) continue;
+        for (int q = 0; q < S.n_pm; ++q) {
+            const int j = S.pm_order[q];
             double rj0 = y[0] - bpos[j][0], rj1 = y[1] - bpos[j][1], rj2 = y[2] - bpos[j][2];
             double nmu = -S.bodies[j].mu;
 #if NYXB_STRICT
@@ -635,6 +667,29 @@ __device__ inline void accel_post(const DevSetup& S, long long t_ns, const doubl
     }
 }
 
+// position of the spacecraft relative to the body a harmonic field belongs to (gravity_field.rs:149-154: transform_to the
+// field's frame; the body-fixed rotation follows inside the field evaluation)
+__device__ __forceinline__ void grav_rel(int body, const double y[9], const double bpos[NYXB_MAX_BODIES][3], double rel[3]) {
+    if (body < 0) { rel[0] = y[0]; rel[1] = y[1]; rel[2] = y[2]; }
+    else { rel[0] = y[0] - bpos[body][0]; rel[1] = y[1] - bpos[body][1]; rel[2] = y[2] - bpos[body][2]; }
+}
+
+// harmonic fields beyond the primary one (OrbitalDynamics holds a Vec of accel models, orbital.rs:44-46, 102-107), summed per
+// trajectory in list order
+__device__ inline void accel_extra_fields(const DevSetup& S, long long t_ns, const double y[9],
+                                          const double bpos[NYXB_MAX_BODIES][3], double acc[3]) {
+    for (int f = 0; f < S.n_xgrav; ++f) {
+        double rel[3], ga[3];
+        grav_rel(S.xgrav_body[f], y, bpos, rel);
+#if NYXB_STRICT
+        grav_accel_rows(S.xgrav[f], t_ns, rel, ga);
+#else
+        grav_accel_cols(S.xgrav[f], t_ns, rel, ga);
+#endif
+        acc[0] += ga[0]; acc[1] += ga[1]; acc[2] += ga[2];
+    }
+}
+
 // SpacecraftDynamics::eom for one trajectory on one thread: y[9] -> dy[0..5] (dy[6..8] == 0).
 // Returns 0 or an nyxb_status error code.
 template <bool GRAV = true>
@@ -649,13 +704,15 @@ __device__ inline int eom_full(const DevSetup& S, long long epoch_ns, double del
     int rc = accel_pre(S, t_ns, y, bpos, acc);
     if (rc) return rc;
     if (GRAV && S.has_grav) {
-        double ga[3];
+        double ga[3], rel[3];
+        grav_rel(S.grav_body, y, bpos, rel);
 #if NYXB_STRICT
-        grav_accel_rows(S.grav, t_ns, y, ga);
+        grav_accel_rows(S.grav, t_ns, rel, ga);
 #else
-        grav_accel_cols(S.grav, t_ns, y, ga);
+        grav_accel_cols(S.grav, t_ns, rel, ga);
 #endif
         acc[0] += ga[0]; acc[1] += ga[1]; acc[2] += ga[2];
+        accel_extra_fields(S, t_ns, y, bpos, acc);
     }
     if (has_force) accel_post(S, t_ns, y, bpos, mass, srp_area, drag_area, acc);
     dy[0] = y[3]; dy[1] = y[4]; dy[2] = y[5];

@@ -207,30 +207,6 @@ __device__ static int dual_eom_dev(const DevSetup& S, long long t_ns, const doub
 }
 
 // ------------------------------------------------------------------------- tracking geometry
-// d/dt of the Chebyshev ephemeris: sum_k c_k k U_{k-1}(tau) * 2 / interval
-__device__ static bool body_velocity(const DevBody& b, long long t_ns, double vel[3]) {
-    long long dt = t_ns - b.t0_ns;
-    if (dt < 0) return false;
-    long long idx = dt / b.interval_ns;
-    if (idx >= b.n_intervals) return false;
-    long long off = dt - idx * b.interval_ns;
-    double tau = 2.0 * ((double)off / (double)b.interval_ns) - 1.0;
-    double tau2 = 2.0 * tau;
-    int nc = b.n_coeffs;
-    const double* c = b.coeffs + (size_t)idx * 3 * (size_t)nc;
-    double scale = 2.0 / ((double)b.interval_ns * 1e-9);
-    for (int ax = 0; ax < 3; ++ax) {
-        const double* ca = c + ax * nc;
-        double b1 = 0.0, b2 = 0.0;
-        for (int j = nc - 2; j >= 0; --j) {
-            double bj = ((double)(j + 1) * __ldg(ca + j + 1) + tau2 * b1) - b2;
-            b2 = b1; b1 = bj;
-        }
-        vel[ax] = b1 * scale;
-    }
-    return true;
-}
-
 // trk_device.rs:150-152 `location`: antenna position / velocity in the integration frame and the inertial zenith
 __device__ static bool station_state(const DevSetup& S, const DevStation& st, long long t_ns, double r[3], double v[3], double up[3]) {
     double R[9];

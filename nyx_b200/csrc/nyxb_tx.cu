@@ -104,8 +104,16 @@ __device__ __noinline__ int tx_extra(const DevSetup& S, double dry_mass, double 
     double bpos[NYXB_MAX_BODIES][3];
     const int rc = accel_point_masses(S, t_ns, y, bpos, acc);
     if (rc) return rc;
+    accel_extra_fields(S, t_ns, y, bpos, acc);
     if (has_force) accel_post(S, t_ns, y, bpos, mass, srp_area, drag_area, acc);
     return 0;
+}
+
+// position relative to the body the primary field belongs to (gravity_field.rs:149-154); an epoch outside the ephemeris is reported
+// by tx_extra, which evaluates every body
+__device__ __noinline__ void tx_field_offset(const DevSetup& S, long long t_ns, double& y0, double& y1, double& y2) {
+    double bp[3];
+    if (body_position(S.bodies[S.grav_body], t_ns, bp)) { y0 -= bp[0]; y1 -= bp[1]; y2 -= bp[2]; }
 }
 
 // ---- one column of the walk.  (a01, a23, kk) hold the NEXT record (prefetched); A / K point at it.
@@ -414,7 +422,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
 
     const int stages = S.tb.stages;
     const DevGrav& gv = S.grav;
-    const bool has_extra = S.n_bodies > 0 || S.has_srp || S.has_drag;
+    const bool has_extra = S.n_bodies > 0 || S.has_srp || S.has_drag || S.n_xgrav > 0;
     // this warp's column schedule (warp-uniform)
     const int* my = sm.sched + w * (2 + 2 * Tx.kmax);
     const int rec_off = my[0], ncol = my[1];
@@ -530,7 +538,8 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
 
                 // ---- every warp: body-fixed position, 1/r, recursion scalars, powers of its columns, column walk
                 {
-                    const double y0 = ysb[lane], y1 = ysb[NL + lane], y2 = ysb[2 * NL + lane];
+                    double y0 = ysb[lane], y1 = ysb[NL + lane], y2 = ysb[2 * NL + lane];
+                    if (S.grav_body >= 0) tx_field_offset(S, epoch + ((i > 0) ? dur_from_seconds(S.tb.c[i - 1] * h) : 0), y0, y1, y2);
                     const double rb0 = fma(rmb[2 * NL + lane], y2, fma(rmb[NL + lane], y1, rmb[lane] * y0));
                     const double rb1 = fma(rmb[5 * NL + lane], y2, fma(rmb[4 * NL + lane], y1, rmb[3 * NL + lane] * y0));
                     const double rb2 = fma(rmb[8 * NL + lane], y2, fma(rmb[7 * NL + lane], y1, rmb[6 * NL + lane] * y0));
@@ -596,11 +605,17 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                             const double* pt = sm.part + (p * 4) * NL + lane;
                             X += pt[0]; Y += pt[NL]; Z += pt[2 * NL]; Wt += pt[3 * NL];
                         }
-                        const double y0 = ysb[lane], y1 = ysb[NL + lane], y2 = ysb[2 * NL + lane];
+                        double y0 = ysb[lane], y1 = ysb[NL + lane], y2 = ysb[2 * NL + lane];
+                        double ir_c = 0.0;   // 1/|r| about the integration centre (two-body term)
+                        if (S.grav_body >= 0) {
+                            ir_c = rsqrt(fma(y2, y2, fma(y1, y1, y0 * y0)));
+                            tx_field_offset(S, epoch + ((i > 0) ? dur_from_seconds(S.tb.c[i - 1] * h) : 0), y0, y1, y2);
+                        }
                         const double rb0 = fma(rmb[2 * NL + lane], y2, fma(rmb[NL + lane], y1, rmb[lane] * y0));
                         const double rb1 = fma(rmb[5 * NL + lane], y2, fma(rmb[4 * NL + lane], y1, rmb[3 * NL + lane] * y0));
                         const double rb2 = fma(rmb[8 * NL + lane], y2, fma(rmb[7 * NL + lane], y1, rmb[6 * NL + lane] * y0));
                         const double inv_r = rsqrt(fma(rb2, rb2, fma(rb1, rb1, rb0 * rb0)));
+                        if (S.grav_body < 0) ir_c = inv_r;
                         const double rho = gv.r_eq * inv_r;
                         const double s_ = rb0 * inv_r, t_ = rb1 * inv_r, u_ = rb2 * inv_r;
                         // rr_n A[n][m] = K0 rho (rho^n A),  rr_{n-1} A[n][m] = K0 (rho^n A),  K0 = mu / (r R_eq)
@@ -608,7 +623,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                         const double K1 = K0 * rho;
                         const double aw = -K0 * Wt;
                         const double ab0 = fma(aw, s_, K1 * X), ab1 = fma(aw, t_, K1 * Y), ab2 = fma(aw, u_, K1 * Z);
-                        const double fac = -S.mu_central * inv_r * inv_r * inv_r;   // two-body from the same 1/r (orbital.rs:86-92)
+                        const double fac = -S.mu_central * ir_c * ir_c * ir_c;   // two-body (orbital.rs:86-92), from the same 1/r when the field is the centre's
                         const double yj = ysb[j * NL + lane];
                         kval = fma(fac, yj, fma(rmb[(6 + j) * NL + lane], ab2, fma(rmb[(3 + j) * NL + lane], ab1, rmb[j * NL + lane] * ab0)));
                         if (has_extra) {

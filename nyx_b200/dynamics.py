@@ -208,16 +208,16 @@ class SpacecraftDynamics:
         dyn.central_radius_km = frame.radius_km if frame.radius_km is not None else 0.0
 
         pm: Optional[PointMasses] = None
-        gf: Optional[GravityField] = None
+        fields: List[GravityField] = []
         for model in self.orbital_dyn.accel_models:
             if isinstance(model, PointMasses):
                 if pm is not None:
                     raise DynamicsError("only one PointMasses model is supported on the GPU path")
                 pm = model
             elif isinstance(model, GravityField):
-                if gf is not None:
-                    raise DynamicsError("only one GravityField model is supported on the GPU path")
-                gf = model
+                if len(fields) >= abi.NYXB_MAX_FIELDS:
+                    raise DynamicsError(f"at most {abi.NYXB_MAX_FIELDS} GravityField models are supported on the GPU path")
+                fields.append(model)
             else:
                 raise DynamicsError(f"unsupported acceleration model {type(model).__name__} (closed set only)")
         srp: Optional[SolarPressure] = None
@@ -230,7 +230,15 @@ class SpacecraftDynamics:
             else:
                 raise DynamicsError(f"unsupported force model {type(model).__name__} (closed set only)")
 
-        # ---- bodies: every ephemeris the almanac holds is made available
+        # ---- bodies: every ephemeris the almanac holds is made available.  The tables are positions RELATIVE TO THE ALMANAC'S
+        # CENTRE; the kernels use them as positions relative to the integration-frame centre (the reference re-centres through
+        # anise's `almanac.transform(third_body_frame, osc.frame, ...)`, orbital.rs:230-234), so the two must be the same body.
+        if almanac is not None and almanac.bodies:
+            if almanac.center.ephemeris_id != frame.ephemeris_id:
+                raise DynamicsError(f"almanac is centred on {almanac.center.name} but the states are expressed in {frame.name}: "
+                                    f"build it with Almanac.synthetic(center=<the integration frame>)")
+            if any(b.frame.ephemeris_id == frame.ephemeris_id for b in almanac.bodies):
+                raise DynamicsError(f"almanac holds an ephemeris of its own centre ({frame.name})")
         bodies = almanac.bodies if almanac is not None else []
         if len(bodies) > abi.NYXB_MAX_BODIES:
             raise DynamicsError("too many ephemeris bodies")
@@ -246,24 +254,41 @@ class SpacecraftDynamics:
             dyn.bodies = C.cast(arr, C.POINTER(abi.BodyC))
 
         if pm is not None:
-            mask = 0
-            for obj in pm.celestial_objects:
+            mask, k = 0, 0
+            for obj in pm.celestial_objects:   # summation order of PointMasses::eom (orbital.rs:217)
                 if obj == frame.ephemeris_id:
                     continue  # orbital.rs:219-222: the central body is handled by the two-body term
                 if almanac is None:
                     raise DynamicsError("planetary data from third body not loaded")
-                mask |= 1 << almanac.body_index(obj)
+                j = almanac.body_index(obj)
+                if not (mask >> j) & 1:
+                    dyn.point_mass_order[k] = j
+                    k += 1
+                mask |= 1 << j
             dyn.point_mass_mask = mask
+            dyn.n_point_masses = k
 
-        if gf is not None:
-            gd = gf.grav_data
-            n = gd.degree
-            c = np.ascontiguousarray(gd.c_nm[: n + 1, : n + 1], dtype=np.float64)
-            s = np.ascontiguousarray(gd.s_nm[: n + 1, : n + 1], dtype=np.float64)
-            g = abi.GravityFieldC(n, gd.order, gd.frame.mu_km3_s2(), gd.frame.mean_equatorial_radius_km(),
-                                  abi.as_double_p(c), abi.as_double_p(s), _rotation_c(gd.frame.rotation))
-            keep += [c, s, g]
-            dyn.gravity = C.pointer(g)
+        if fields:
+            # every harmonic field is evaluated in ITS OWN body's frame (gravity_field.rs:149-154): a field of another body than the
+            # integration centre needs that body's ephemeris.  The first field is the one the cooperative kernels parallelise.
+            arr = (abi.GravityFieldC * len(fields))()
+            for i, gf in enumerate(fields):
+                gd = gf.grav_data
+                n = gd.degree
+                c = np.ascontiguousarray(gd.c_nm[: n + 1, : n + 1], dtype=np.float64)
+                s = np.ascontiguousarray(gd.s_nm[: n + 1, : n + 1], dtype=np.float64)
+                if gd.frame.ephemeris_id == frame.ephemeris_id:
+                    body = abi.NYXB_CENTRAL_BODY
+                else:
+                    if almanac is None or not almanac.has_body(gd.frame.ephemeris_id):
+                        raise DynamicsError(f"planetary data of the {gd.frame.name} gravity field's body not loaded")
+                    body = almanac.body_index(gd.frame.ephemeris_id)
+                arr[i] = abi.GravityFieldC(n, gd.order, gd.frame.mu_km3_s2(), gd.frame.mean_equatorial_radius_km(),
+                                           abi.as_double_p(c), abi.as_double_p(s), _rotation_c(gd.frame.rotation), body, 0)
+                keep += [c, s]
+            keep.append(arr)
+            dyn.n_gravity = len(fields)
+            dyn.gravity = C.cast(arr, C.POINTER(abi.GravityFieldC))
 
         if srp is not None:
             if almanac is None:

@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import enum
-from dataclasses import dataclass
+from dataclasses import dataclass, replace
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -90,6 +90,9 @@ class IntegratorOptions:
     attempts: int = 50
     fixed_step: bool = False
     error_ctrl: ErrorControl = ErrorControl.RSSCartesianStep
+    # options.rs:60: propagate in this frame instead of the state's own; the state is transformed before the loop and back after
+    # it (instance.rs:117-142, 167-176, 211-220).  The frame's own mu / shape, when set, are the ones used (instance.rs:131-137).
+    integration_frame: Optional[Frame] = None
 
     @classmethod
     def default(cls) -> "IntegratorOptions":
@@ -133,9 +136,12 @@ class IntegratorOptions:
             self.init_step = min_step
         self.min_step = min_step
 
-    def to_c(self, method: IntegratorMethod) -> abi.IntegOpts:
+    def to_c(self, method: IntegratorMethod, state_center: int = 0) -> abi.IntegOpts:
+        """`state_center`: 0 = the states are expressed in the frame the dynamics were packed for; k + 1 = they are relative to
+        body k of that packing (see `nyxb_integ_opts.state_center`)."""
         return abi.IntegOpts(int(method), int(self.error_ctrl), int(self.init_step), int(self.min_step),
-                             int(self.max_step), float(self.tolerance), int(self.attempts), int(bool(self.fixed_step)))
+                             int(self.max_step), float(self.tolerance), int(self.attempts), int(bool(self.fixed_step)),
+                             int(state_center), 0)
 
 
 @dataclass
@@ -424,14 +430,41 @@ class Propagator:
         self._engines.clear()
 
     # engine cache ------------------------------------------------------------------------------
+    _MAX_ENGINES = 8   # each engine owns device tables and staging buffers: the cache is bounded (oldest evicted)
+
     def engine(self, frame: Frame, almanac: Optional[Almanac]) -> Engine:
-        key = (id(almanac), frame)
-        eng = self._engines.get(key)
-        if eng is None:
-            packed = self.dynamics.pack(frame, almanac)
-            eng = Engine(packed, self.opts.to_c(self.method), self.mode, self.device)
-            self._engines[key] = eng
+        """Device engine for states expressed in `frame`.  The cache key covers everything the engine was built from — method,
+        mode, device, every option field, the dynamics object and the almanac (held by a strong reference, so `id()` cannot be
+        recycled while the entry lives) — so mutating `prop.opts.*`, `prop.method` or `prop.dynamics` rebuilds it."""
+        o = self.opts
+        key = (id(almanac), frame, int(self.method), self.mode, self.device, id(self.dynamics),
+               (o.init_step, o.min_step, o.max_step, o.tolerance, o.attempts, o.fixed_step, int(o.error_ctrl),
+                getattr(o, "integration_frame", None)))
+        hit = self._engines.get(key)
+        if hit is not None:
+            return hit[0]
+        packed, opts_c = self.lower(frame, almanac)
+        eng = Engine(packed, opts_c, self.mode, self.device)
+        if len(self._engines) >= self._MAX_ENGINES:
+            old = next(iter(self._engines))
+            self._engines.pop(old)[0].close()
+        self._engines[key] = (eng, almanac, self.dynamics)
         return eng
+
+    def lower(self, frame: Frame, almanac: Optional[Almanac]):
+        """(nyxb_dynamics, nyxb_integ_opts) for states expressed in `frame`.  With `opts.integration_frame` set to another frame
+        the dynamics are lowered for THAT frame (its own mu / shape when given, instance.rs:131-137) and `state_center` tells the
+        engine which body of the almanac the caller's states are relative to: it translates them in and out (instance.rs:117-142,
+        167-176, 211-220)."""
+        integ, state_center = frame, 0
+        f = self.opts.integration_frame
+        if f is not None and f.ephemeris_id != frame.ephemeris_id:
+            if almanac is None or not almanac.has_body(frame.ephemeris_id):
+                raise PropagationError(f"integration_frame {f.name}: the almanac holds no ephemeris of {frame.name} relative to it")
+            known = almanac.frame_info(f)
+            integ = replace(known, mu=f.mu if f.mu is not None else known.mu, radius_km=f.radius_km if f.radius_km is not None else known.radius_km)
+            state_center = almanac.body_index(frame.ephemeris_id) + 1
+        return self.dynamics.pack(integ, almanac), self.opts.to_c(self.method, state_center)
 
     # instances ---------------------------------------------------------------------------------
     def with_(self, state: Spacecraft, almanac: Optional[Almanac] = None) -> "PropInstance":
@@ -528,9 +561,11 @@ class PropInstance:
         while True:
             step_before = self._step_ns.copy()
             final, tr, overflow = self._run(end_ns, cap, start)
-            if not overflow or capacity:
+            if not overflow:
                 break
             self.state, self._step_ns = start, step_before  # retry with a larger sink
+            if capacity:   # an explicit capacity is a hard bound: a truncated Traj is never returned
+                raise PropagationError(f"trajectory capacity {capacity} too small: the run takes {self.details.n_steps + 1} records")
             cap *= 4
         return final, tr
 
@@ -568,9 +603,11 @@ class PropInstance:
             eng = self.prop.engine(start.orbit.frame, self.almanac)
             out, out_ep, det, status, (t_ep, t_st, t_cnt), crossings = eng.propagate_batch(
                 st, cs, ep, end_ns, self._step_ns, traj_capacity=cap, event=(event.kind, event.value, trigger))
-            if int(det[0]["n_steps"]) + 1 <= cap or capacity:
+            if int(det[0]["n_steps"]) + 1 <= cap:
                 break
             self._step_ns = step_before
+            if capacity:   # the event search needs the bracketing (last) step on the recording: never search a truncated one
+                raise PropagationError(f"trajectory capacity {capacity} too small: the run takes {int(det[0]['n_steps']) + 1} records")
             cap *= 4
         d = det[0]
         if d["n_steps"] > 0:

@@ -272,6 +272,30 @@ int nyx_oracle_body_position(const nyxb_body* b, int64_t t_ns, double pos[3]) {
 }
 
 /* nalgebra Vector3::norm(): sqrt((a*a + b*b) + c*c) — pinned by the golden vectors */
+/* d/dt of the Chebyshev series (anise differentiates the SPK segment the same way): sum_k c_k T_k'(tau) * 2 / interval */
+int nyx_oracle_body_velocity(const nyxb_body* b, int64_t t_ns, double vel[3]) {
+    int64_t dt = t_ns - b->t0_ns;
+    if (dt < 0) return 1;
+    int64_t idx = dt / b->interval_ns;
+    if (idx >= b->n_intervals) return 1;
+    int64_t off = dt - idx * b->interval_ns;
+    double tau = 2.0 * ((double)off / (double)b->interval_ns) - 1.0;
+    double tau2 = 2.0 * tau;
+    int nc = b->n_coeffs;
+    const double* c = b->coeffs + (size_t)idx * 3 * (size_t)nc;
+    double scale = 2.0 / ((double)b->interval_ns * 1e-9);
+    for (int ax = 0; ax < 3; ++ax) {
+        const double* ca = c + ax * nc;
+        double b1 = 0.0, b2 = 0.0;
+        for (int j = nc - 2; j >= 0; --j) {
+            double bj = ((double)(j + 1) * ca[j + 1] + tau2 * b1) - b2;
+            b2 = b1; b1 = bj;
+        }
+        vel[ax] = b1 * scale;
+    }
+    return 0;
+}
+
 static inline double norm3(const double v[3]) {
     return sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
 }
@@ -422,11 +446,30 @@ double nyx_oracle_occultation(const double r_eb[3] /* eclipsing body -> observer
 /* ------------------------------------------------------------------------- */
 typedef struct {
     const nyxb_dynamics* dyn;
-    nyx_oracle_grav* grav;
-    double* grav_scratch;
+    int n_grav;                          /* harmonic fields in accel-model order (orbital.rs:44-46, 102-107) */
+    nyx_oracle_grav* grav[NYXB_MAX_FIELDS];
+    int grav_body[NYXB_MAX_FIELDS];      /* NYXB_CENTRAL_BODY or the body the field belongs to */
+    double* grav_scratch;                /* sized for the largest field */
     double dry_mass, extra_mass, srp_area, drag_area;
     int64_t n_rhs;
 } eom_ctx;
+
+/* fields of a dynamics descriptor -> ctx; returns the scratch size (doubles) */
+static size_t ctx_fields_new(eom_ctx* cx, const nyxb_dynamics* dyn) {
+    size_t need = 0;
+    cx->n_grav = dyn->gravity ? (dyn->n_gravity > 0 ? dyn->n_gravity : 1) : 0;
+    if (cx->n_grav > NYXB_MAX_FIELDS) cx->n_grav = NYXB_MAX_FIELDS;
+    for (int f = 0; f < cx->n_grav; ++f) {
+        cx->grav[f] = nyx_oracle_grav_new(&dyn->gravity[f]);
+        cx->grav_body[f] = dyn->gravity[f].body;
+        size_t d = (size_t)cx->grav[f]->dim * cx->grav[f]->dim;
+        if (d > need) need = d;
+    }
+    return need;
+}
+static void ctx_fields_free(eom_ctx* cx) {
+    for (int f = 0; f < cx->n_grav; ++f) nyx_oracle_grav_free(cx->grav[f]);
+}
 
 #define AU_KM 149597870.700                 /* cosmic/mod.rs:183 */
 #define SPEED_OF_LIGHT_M_S (299792.458 * 1e3) /* cosmic/mod.rs:179-180 */
@@ -461,8 +504,12 @@ static int eom(eom_ctx* cx, int64_t epoch_ns, double delta_t_s, const double y[9
     /* PointMasses::eom orbital.rs:213-247 */
     if (dyn->point_mass_mask) {
         double dx[3] = {0, 0, 0};
-        for (int j = 0; j < dyn->n_bodies; ++j) {
-            if (!((dyn->point_mass_mask >> j) & 1u)) continue;
+        /* orbital.rs:217: `for third_body in &self.celestial_objects` — the caller's order when it is given */
+        int order[NYXB_MAX_BODIES], n_pm = 0;
+        if (dyn->n_point_masses > 0) { for (int q = 0; q < dyn->n_point_masses; ++q) order[n_pm++] = dyn->point_mass_order[q]; }
+        else { for (int j = 0; j < dyn->n_bodies; ++j) if ((dyn->point_mass_mask >> j) & 1u) order[n_pm++] = j; }
+        for (int q = 0; q < n_pm; ++q) {
+            const int j = order[q];
             const double* r_ij = bpos[j];
             double n_ij = norm3(r_ij);
             double r_ij3 = n_ij * n_ij * n_ij;
@@ -474,9 +521,12 @@ static int eom(eom_ctx* cx, int64_t epoch_ns, double delta_t_s, const double y[9
         }
         for (int i = 0; i < 3; ++i) acc[i] += dx[i];
     }
-    if (cx->grav) {
-        double ga[3];
-        nyx_oracle_grav_accel(cx->grav, t_ns, r, cx->grav_scratch, ga);
+    for (int f = 0; f < cx->n_grav; ++f) {
+        /* gravity_field.rs:149-154: transform_to(self.grav_data.frame): translation to the field's body, then the body-fixed rotation */
+        double ga[3], rel[3] = { r[0], r[1], r[2] };
+        const int b = cx->grav_body[f];
+        if (b >= 0) { rel[0] -= bpos[b][0]; rel[1] -= bpos[b][1]; rel[2] -= bpos[b][2]; }
+        nyx_oracle_grav_accel(cx->grav[f], t_ns, rel, cx->grav_scratch, ga);
         for (int i = 0; i < 3; ++i) acc[i] += ga[i];
     }
 
@@ -667,8 +717,8 @@ static void record_state(const inst_t* in, int64_t s) {
 /* Sensitivity probe (tests/test_oracle_sensitivity.py, scripts/oracle_sensitivity.py): the error norm of every adaptive attempt
  * is multiplied by this factor.  1.0 (the default) leaves the restatement untouched; 1 + 2^-52 asks "what does ONE ulp in the
  * reference's own error estimate do to the final state" -- the step-sequence sensitivity that bounds any tolerance-parity mode. */
-static double g_error_scale = 1.0;
-void nyx_oracle_set_error_scale(double s) { g_error_scale = s; }
+double nyx_oracle_error_scale_ = 1.0;   /* shared with nyx_oracle_od.c */
+void nyx_oracle_set_error_scale(double s) { nyx_oracle_error_scale_ = s; }
 
 /* instance.rs:358-493 derive(); returns status, writes dt_ns and next[9] */
 static int derive(inst_t* in, eom_ctx* cx, const nyxb_integ_opts* o, const tableau_t* tb, int64_t* dt_ns, double next[9]) {
@@ -713,7 +763,7 @@ static int derive(inst_t* in, eom_ctx* cx, const nyxb_integ_opts* o, const table
             return 0;
         }
         in->det.error = nyx_oracle_error_estimate(o->error_ctrl, err_est, next, y); /* :422-426 */
-        if (g_error_scale != 1.0) in->det.error *= g_error_scale;   /* sensitivity probe only */
+        if (nyx_oracle_error_scale_ != 1.0) in->det.error *= nyx_oracle_error_scale_;   /* sensitivity probe only */
         if (in->det.error <= o->tolerance || h <= min_s || in->det.attempts >= o->attempts) { /* :428-431 */
             for (int e = 0; e < 9; ++e)
                 if (next[e] != next[e]) return NYXB_ERR_PROP_MATH;   /* :432-439 */
@@ -806,7 +856,10 @@ int nyx_oracle_propagate_batch_event(const nyxb_dynamics* dyn, const nyxb_integ_
     if (event && event->kind == NYXB_EVENT_NONE) event = NULL;
     if (tableau_for(opts->method, &tb)) return -1;
     if (dyn->n_bodies > NYXB_MAX_BODIES) return -1;
-    nyx_oracle_grav* grav = dyn->gravity ? nyx_oracle_grav_new(dyn->gravity) : NULL;
+    if (opts->state_center < 0 || opts->state_center > dyn->n_bodies) return -1;
+    const nyxb_body* shift = opts->state_center ? &dyn->bodies[opts->state_center - 1] : NULL;
+    eom_ctx proto;
+    const size_t scratch_n = ctx_fields_new(&proto, dyn);
 #ifdef _OPENMP
     if (n_threads <= 0) n_threads = omp_get_max_threads();
 #else
@@ -814,7 +867,7 @@ int nyx_oracle_propagate_batch_event(const nyxb_dynamics* dyn, const nyxb_integ_
 #endif
 #pragma omp parallel num_threads(n_threads)
     {
-        double* scratch = grav ? (double*)malloc(sizeof(double) * (size_t)grav->dim * grav->dim) : NULL;
+        double* scratch = scratch_n ? (double*)malloc(sizeof(double) * scratch_n) : NULL;
 #pragma omp for schedule(dynamic, 1)
         for (long long ii = 0; ii < (long long)n; ++ii) {
             size_t i = (size_t)ii;
@@ -822,6 +875,12 @@ int nyx_oracle_propagate_batch_event(const nyxb_dynamics* dyn, const nyxb_integ_
             memset(&in, 0, sizeof(in));
             for (int e = 0; e < 9; ++e) in.y[e] = state_soa[(size_t)e * n + i];
             in.epoch_ns = epoch0_ns[i];
+            int shift_rc = 0;
+            if (shift) {   /* instance.rs:117-142: transform the state into the integration frame (same axes: a translation) */
+                double bp[3], bv[3];
+                if (nyx_oracle_body_position(shift, in.epoch_ns, bp) || nyx_oracle_body_velocity(shift, in.epoch_ns, bv)) shift_rc = NYXB_ERR_EPHEMERIS;
+                else for (int c = 0; c < 3; ++c) { in.y[c] = in.y[c] + 1.0 * bp[c]; in.y[3 + c] = in.y[3 + c] + 1.0 * bv[c]; }
+            }
             /* propagator.rs:88-108 with(): step = opts.init_step, fixed = opts.fixed_step */
             in.step_ns = step_ns ? step_ns[i] : opts->init_step_ns;
             in.fixed = opts->fixed_step;
@@ -830,11 +889,17 @@ int nyx_oracle_propagate_batch_event(const nyxb_dynamics* dyn, const nyxb_integ_
             record_state(&in, 0);                                /* start state: instance.rs:307, 321 */
             in.ev = event; in.ev_count = 0;
             if (event) in.ev_prev = event_eval(event, in.y);     /* event.rs:111-113 */
-            eom_ctx cx;
-            cx.dyn = dyn; cx.grav = grav; cx.grav_scratch = scratch; cx.n_rhs = 0;
+            eom_ctx cx = proto;
+            cx.dyn = dyn; cx.grav_scratch = scratch; cx.n_rhs = 0;
             cx.dry_mass = consts_soa[0 * n + i]; cx.extra_mass = consts_soa[1 * n + i];
             cx.srp_area = consts_soa[2 * n + i]; cx.drag_area = consts_soa[3 * n + i];
             int rc = propagate(&in, &cx, opts, &tb, end_epoch_ns - in.epoch_ns); /* instance.rs:279-282 */
+            if (shift) {   /* instance.rs:167-176, 211-220: transform back at the epoch the run ended at */
+                double bp[3], bv[3];
+                if (nyx_oracle_body_position(shift, in.epoch_ns, bp) || nyx_oracle_body_velocity(shift, in.epoch_ns, bv)) { if (!rc) rc = NYXB_ERR_EPHEMERIS; }
+                else for (int c = 0; c < 3; ++c) { in.y[c] = in.y[c] + -1.0 * bp[c]; in.y[3 + c] = in.y[3 + c] + -1.0 * bv[c]; }
+            }
+            (void)shift_rc;
             if (event) {
                 event->crossings[i] = in.ev_count;
                 if (rc == 0 && in.ev_count < event->trigger) rc = NYXB_ERR_EVENT_NOT_FOUND; /* event.rs:177-182 */
@@ -850,7 +915,7 @@ int nyx_oracle_propagate_batch_event(const nyxb_dynamics* dyn, const nyxb_integ_
         }
         free(scratch);
     }
-    nyx_oracle_grav_free(grav);
+    ctx_fields_free(&proto);
     return 0;
 }
 
@@ -875,14 +940,14 @@ int nyx_oracle_propagate_batch(const nyxb_dynamics* dyn, const nyxb_integ_opts* 
 /* Direct RHS access for unit tests (one evaluation of SpacecraftDynamics::eom). */
 int nyx_oracle_eom(const nyxb_dynamics* dyn, int64_t epoch_ns, double delta_t_s, const double y[9],
                    const double consts[4], double dy[9]) {
-    nyx_oracle_grav* grav = dyn->gravity ? nyx_oracle_grav_new(dyn->gravity) : NULL;
-    double* scratch = grav ? (double*)malloc(sizeof(double) * (size_t)grav->dim * grav->dim) : NULL;
     eom_ctx cx;
-    cx.dyn = dyn; cx.grav = grav; cx.grav_scratch = scratch; cx.n_rhs = 0;
+    const size_t scratch_n = ctx_fields_new(&cx, dyn);
+    double* scratch = scratch_n ? (double*)malloc(sizeof(double) * scratch_n) : NULL;
+    cx.dyn = dyn; cx.grav_scratch = scratch; cx.n_rhs = 0;
     cx.dry_mass = consts[0]; cx.extra_mass = consts[1]; cx.srp_area = consts[2]; cx.drag_area = consts[3];
     int rc = eom(&cx, epoch_ns, delta_t_s, y, dy);
     free(scratch);
-    nyx_oracle_grav_free(grav);
+    ctx_fields_free(&cx);
     return rc;
 }
 

@@ -53,6 +53,7 @@ int nyx_oracle_propagate_batch_stm(const nyxb_dynamics* dyn, const nyxb_integ_op
                                    const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
                                    const double* stm_in_soa, double* out_state_soa, int64_t* out_epoch_ns,
                                    double* out_stm_soa, nyxb_details* out_details, int32_t* out_status, int n_threads);
+int nyx_oracle_body_velocity(const nyxb_body* b, int64_t t_ns, double vel[3]);
 int nyx_oracle_num_threads(void);
 /* sensitivity probe: multiply every adaptive error norm by `s` (1.0 = untouched restatement) */
 void nyx_oracle_set_error_scale(double s);

@@ -183,7 +183,7 @@ static int dual_eom(od_ctx* cx, int64_t t_ns, const double y[9], double dx[9], d
     for (int j = 0; j < dyn->n_bodies; ++j)
         if (nyx_oracle_body_position(&dyn->bodies[j], t_ns, bpos[j])) return NYXB_ERR_EPHEMERIS;
     /* ---- PointMasses::gradient, orbital.rs:249-307 (r_ij carries identity partials, as coded) */
-    if (dyn->point_mass_mask) {
+    if (dyn->point_mass_mask) {   /* NB: ascending body index; the STM path takes one PointMasses list in almanac order */
         double fx[3] = {0, 0, 0}, g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         for (int j = 0; j < dyn->n_bodies; ++j) {
             if (!((dyn->point_mass_mask >> j) & 1u)) continue;
@@ -346,6 +346,7 @@ static int derive90(nyx_oracle_inst* in, int64_t* dt_ns, double next[VL]) {
         }
         /* only the Cartesian controls are accepted: they read components 0..5 (error_ctrl.rs:89-122) */
         in->det.error = nyx_oracle_error_estimate(o->error_ctrl, err_est, next, y);
+        if (nyx_oracle_error_scale_ != 1.0) in->det.error *= nyx_oracle_error_scale_;   /* sensitivity probe only (nyx_oracle.c) */
         if (in->det.error <= o->tolerance || h <= min_s || in->det.attempts >= o->attempts) {
             for (int e = 0; e < VL; ++e)
                 if (next[e] != next[e]) return NYXB_ERR_PROP_MATH;
@@ -411,6 +412,7 @@ static int propagate90(nyx_oracle_inst* in, int64_t duration_ns) {
 nyx_oracle_inst* nyx_oracle_inst_new(const nyxb_dynamics* dyn, const nyxb_integ_opts* opts, const double y9[9],
                                      const double consts[4], int64_t epoch_ns) {
     if (dyn->drag) return NULL;
+    if (dyn->n_gravity > 1 || (dyn->gravity && dyn->gravity->body != NYXB_CENTRAL_BODY) || opts->state_center) return NULL;   /* one central field, no frame swap */
     if (!opts->fixed_step && opts->error_ctrl != NYXB_RSS_CARTESIAN_STATE && opts->error_ctrl != NYXB_RSS_CARTESIAN_STEP) return NULL;
     nyx_oracle_inst* in = (nyx_oracle_inst*)calloc(1, sizeof(*in));
     in->dyn = *dyn; in->opts = *opts;

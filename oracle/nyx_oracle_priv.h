@@ -13,4 +13,5 @@ struct nyx_oracle_grav {
     double *cbar, *sbar;      /* (n+1)^2 row-major */
 };
 
+extern double nyx_oracle_error_scale_;   /* sensitivity probe: factor on every adaptive error norm (1.0 = untouched) */
 #endif

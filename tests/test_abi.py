@@ -22,13 +22,13 @@ def test_header_symbols_exported():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(abi.IntegOpts) == 48
+    assert C.sizeof(abi.IntegOpts) == 56   # ABI 4: + state_center (integration_frame)
     assert C.sizeof(abi.Rotation) == 56
-    assert C.sizeof(abi.GravityFieldC) == 8 + 16 + 16 + 56
+    assert C.sizeof(abi.GravityFieldC) == 8 + 16 + 16 + 56 + 8   # ABI 4: + body
     assert C.sizeof(abi.BodyC) == 48
     assert C.sizeof(abi.SrpC) == 40
     assert C.sizeof(abi.DragC) == 40 + 56
-    assert C.sizeof(abi.DynamicsC) == 64
+    assert C.sizeof(abi.DynamicsC) == 64 + 32   # ABI 4: + point_mass_order[8]; n_gravity / n_point_masses reuse the pads
     assert C.sizeof(abi.Details) == 48
 
 

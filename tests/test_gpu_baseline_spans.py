@@ -71,28 +71,44 @@ def test_c4_fast_7_days_vs_oracle(oracle):
     assert dv.max() < 1e-9
 
 
-def test_c5_fast_full_arc_vs_oracle_filter(oracle):
-    """BASELINE configs[4]: 8 LRO-like EKFs over the full 2-day arc (2 880 range + Doppler epochs, GRAIL 70x70 + Earth / Sun +
-    SRP with Cr estimated) against the numpy + C oracle filter, one process per filter."""
+def _c5_fast_vs_oracle(n, n_msr, fixed_step_s):
     import multiprocessing as mp
 
     import bench
 
-    n, n_msr = 8, 2880
-    args = argparse.Namespace(workload="c5", degree=21, span_days=2.0, mode="fast")
-    sc = bench.c5_scenario(args, nb, n, n_msr, 0, truth_on_cpu=True)
+    args = argparse.Namespace(workload="c5", degree=21, span_days=n_msr * 60 / 86400.0, mode="fast")
+    sc = bench.c5_scenario(args, nb, n, n_msr, 0, truth_on_cpu=True, fixed_step_s=fixed_step_s)
     sol = sc["odp"].process_arcs(sc["ests"], sc["arc"], record_estimates=True)
     assert (sol.status == 0).all()
     bench._C5_SC = sc
     with mp.get_context("fork").Pool(n) as pool:
         refs = pool.map(bench._c5_ref_full, list(range(n)))
-    worst_r = worst_v = 0.0
+    worst_r = worst_v = worst_final = 0.0
     for i, ref in enumerate(refs):
         assert np.array_equal(sol.msr_flags[:, i], ref["msr_flags"]), i
         d = np.abs(sol.est_state[:, :6, i] - ref["est_state"][:, :6])
         worst_r = max(worst_r, float(np.nanmax(d[:, :3])))
         worst_v = max(worst_v, float(np.nanmax(d[:, 3:6])))
         fr = float(np.abs(sol.final_state_soa[:3, i] - ref["state"][:3]).max())
+        worst_final = max(worst_final, fr)
         print(f"\n[c5 filter {i}] final |dr| {fr:.3g} km, worst over the arc {float(np.nanmax(d[:, :3])):.3g} km, steps {sol.details['n_steps'][i]} / {ref['n_steps']}")
-    print(f"\n[c5] worst estimate difference over {n} filters x {n_msr} epochs: {worst_r:.3g} km, {worst_v:.3g} km/s")
+    print(f"\n[c5 {'fixed ' + str(fixed_step_s) + ' s' if fixed_step_s else 'adaptive'}] worst estimate difference over {n} filters x {n_msr} epochs: "
+          f"{worst_r:.3g} km, {worst_v:.3g} km/s; final {worst_final:.3g} km")
+    return worst_r, worst_v, worst_final
+
+
+def test_c5_fast_full_arc_fixed_step_vs_oracle_filter(oracle):
+    """BASELINE configs[4] geometry with FIXED 20 s DP78 steps between the measurements (the reference's own OD validation runs
+    fixed steps, tests/orbit_determination/two_body.rs:72-203): identical step sequences, so this pins the arithmetic of the FAST
+    filter kernel — dual-number harmonic gradient, STM, time / measurement updates — over the full 2 880-epoch arc."""
+    worst_r, worst_v, worst_final = _c5_fast_vs_oracle(8, 2880, 20.0)
     assert worst_r < BOUND_KM and worst_v < 1e-9, (worst_r, worst_v)
+
+
+def test_c5_fast_full_arc_adaptive_vs_oracle_filter(oracle):
+    """BASELINE configs[4] as benchmarked (adaptive DP78).  The reference integrates the STM to first order in the step
+    (spacecraft.rs:203-214), so the gain depends on the step sequence; the CPU oracle filter against ITSELF with one ulp on the
+    error norm differs by up to 1.5e-3 km over this arc and 5.9e-5 km at its end (profiles/r02_oracle_sensitivity_c5.json).  FAST is
+    held to twice that; identical accept / reject decisions for every measurement."""
+    worst_r, worst_v, worst_final = _c5_fast_vs_oracle(8, 2880, None)
+    assert worst_r < 3e-3 and worst_final < 1.2e-4, (worst_r, worst_final)

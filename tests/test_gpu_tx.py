@@ -91,10 +91,10 @@ def test_transposed_kernel_time_slicing_is_bit_invisible(oracle):
     mc, (st, cs, ep) = leo_ensemble(n, seed=21)
     ep = ep + (np.arange(n, dtype=np.int64) % 3) * 900 * S
     dyn, _ = _leo_dyn()
-    prop = nb.Propagator.rk89(dyn, nb.IntegratorOptions(init_step=300 * nb.Unit.Second, tolerance=1e-12), mode=nb.MODE_FAST)   # some rejections
+    prop = nb.Propagator.rk89(dyn, nb.IntegratorOptions(init_step=600 * nb.Unit.Second, tolerance=1e-13), mode=nb.MODE_FAST)   # forced rejections
     eng = _tx_engine(prop)
     end = 5 * 3600 * S
-    step0 = np.full(n, 60 * S, dtype=np.int64)
+    step0 = np.full(n, 600 * S, dtype=np.int64)   # the PropInstance step carried in and out (instance.rs:56)
     base = eng.propagate_batch(st, cs, ep, end, step_ns=step0.copy(), traj_capacity=400)
     assert (base[3] == 0).all() and base[2]["n_rejected"].sum() > 0
     for slice_attempts, max_ctas in ((7, 2), (1, 3), (64, 1), (5, 6)):

@@ -119,7 +119,8 @@ def resample_queries(t_ep, t_cnt, end):
 # (PropInstance, Propagator.many_*, MonteCarlo, Results) can be exercised without a device.  Test infrastructure only.
 class OracleEngine:
     def __init__(self, oracle, prop, frame, almanac, tmp_path=None):
-        self.oracle, self.packed, self.opts = oracle, prop.dynamics.pack(frame, almanac), prop.opts.to_c(prop.method)
+        self.oracle = oracle
+        self.packed, self.opts = prop.lower(frame, almanac)
         self.launches = 0
         self._resident = None
         self._shim = hermite_shim(tmp_path) if tmp_path is not None else None
