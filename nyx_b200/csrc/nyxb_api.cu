@@ -427,9 +427,12 @@ static int32_t launch_tx(nyxb_engine* e, size_t n, const double* state, const do
     if (occ < 1) { set_err("transposed kernel: tables do not fit in shared memory"); return NYXB_RC_UNSUPPORTED; }
     if (!e->sms) CUDA_TRY(cudaDeviceGetAttribute(&e->sms, cudaDevAttrMultiProcessorCount, e->device));
     const size_t n_sets = (n + 31) / 32;
-    size_t slots = (size_t)e->sms * occ;
-    if (e->tx_max_ctas > 0 && (size_t)e->tx_max_ctas < slots) slots = (size_t)e->tx_max_ctas;
-    const int grid = (int)std::min(n_sets, slots);
+    // one persistent CTA per SM, `occ` set contexts each; tx_max_ctas (tests) shrinks the grid to force time slicing
+    size_t ctas = (size_t)e->sms;
+    if (e->tx_max_ctas > 0 && (size_t)e->tx_max_ctas < ctas) ctas = (size_t)e->tx_max_ctas;
+    ctas = std::min(ctas, (n_sets + occ - 1) / occ);
+    const size_t slots = ctas * occ;
+    const int grid = (int)ctas;
     // workspace: [ticket u64 | n_finished i32 (+pad) | slices_done n_sets | finished n_sets | ws_step n i64 | ws_f64 2n | ws_flags n | details n]
     const size_t ctl_bytes = (16 + 8 * n_sets + 15) & ~(size_t)15;
     const size_t need = ctl_bytes + n * (8 + 16 + 8) + n * sizeof(nyxb_details);

@@ -1,22 +1,25 @@
-// nyxb_tx.cu — TRANSPOSED cooperative propagation kernel (FAST mode): lane = trajectory, warp = column position.
+// nyxb_tx.cu — TRANSPOSED, warp-specialised propagation kernel (FAST mode): lane = trajectory, walker warp = column position,
+// helper warps = everything else, two sets of trajectories in flight per CTA.
 //
-//   * One CTA of P warps integrates a SET of 32 trajectories (lane l of every warp = trajectory l of the set).  The harmonic
-//     double sum (gravity_field.rs:217-249) is split by COLUMNS of the derived-Legendre triangle over the P warps; all 32 lanes of
-//     a warp walk the same entries, so the 40-byte coefficient record of an entry is ONE warp-uniform shared-memory read
-//     (2 x LDS.128 + LDS.64 with a single address: 5 clk of the shared-memory pipe per warp-entry against 10 clk for the
-//     lane-varying reads of nyxb_k_coop, profiles/r02a_smem_probe.txt), column boundaries are uniform branches, and no lane idles.
+//   * A SET is 32 trajectories (lane l of every warp = trajectory l of the set).  The harmonic double sum (gravity_field.rs:217-249)
+//     is split by COLUMNS of the derived-Legendre triangle over P WALKER warps; all 32 lanes of a walker walk the same entries, so
+//     the 40-byte coefficient record of an entry is ONE warp-uniform shared-memory read (2 x LDS.128 + LDS.64 with a single address:
+//     5 clk of the shared-memory pipe per warp-entry against 10 clk for the lane-varying reads of nyxb_k_coop,
+//     profiles/r02a_smem_probe.txt), column boundaries are uniform branches, and no lane idles.
 //   * The column walk is software-pipelined by one entry: the six accumulations of entry n use Q[n], which was produced one
 //     iteration earlier, while the only dependent FP64 chain is the one DFMA that advances the recursion
-//     Q[n+1] = (2n+1) u Q[n] - (n+m)(n-m) r^2 Q[n-1] — 12 independent FP64 instructions sit between two links of the chain
-//     (the FP64 latency measured on B200 is ~14 clk, profiles/r02a_opnd_probe.txt).  13 FP64 instructions per entry.
-//   * Roles around the walk: warps 0..5 own one state component each (RK stage algebra, stage derivatives kst[stage][c][lane] in
-//     shared memory), warp 6 evaluates the body-fixed DCM of the stage epoch, warp 7 runs the error norm and the step-size
-//     controller.  Everything that lives across phases is in shared memory, so the walk's registers are its own.
-//     Two CTA barriers per right-hand side (stage state ready / partial sums ready) and two per step.
-//   * Persistent CTAs pull (set, time-slice) tickets from a global counter: with fewer resident CTAs than sets every SM stays
-//     busy to the end (10 000 trajectories = 313 sets on 296 resident CTAs would otherwise run 17 CTAs alone in a second wave).
-//     A parked set keeps its state in the output arrays plus a small workspace; a finished trajectory inside a set keeps stepping
-//     on its own scratch without committing anything, exactly as in nyxb_k_coop.
+//     Q[n+1] = (2n+1) u Q[n] - (n+m)(n-m) r^2 Q[n-1] (FP64 latency on B200 ~14 clk, profiles/r02a_opnd_probe.txt).
+//     13 FP64 instructions per entry.
+//   * Everything that is serial per right-hand side — reduction of the partial sums, acceleration assembly, RK stage algebra,
+//     body-fixed DCM, 1/r, the (cos, sin)(m lambda) cos^m(phi) and rho^m tables, and per step the error norm, the step-size controller,
+//     recording and the stop condition — runs on three HELPER warps per set (helper j owns state components j and j+3), concurrently
+//     with the walkers, which meanwhile walk the OTHER set of the CTA: two sets alternate through the walkers (named barriers
+//     READY[set] / DONE[set]), so the FP64 pipe sees the walk of one set while the latency-bound chain of the other is hidden.
+//     The first version of this kernel ran these phases on the walker warps themselves, between CTA-wide barriers: ncu showed 45 % of
+//     the warp-time in barrier stalls and the FP64 pipe 48 % busy (profiles/r02c_tx_ncu_summary.txt).
+//   * Persistent CTAs, one per SM; every set context pulls (set, time-slice) tickets from a global counter: with fewer contexts than
+//     sets every SM stays busy to the end (10 000 trajectories = 313 sets on 296 contexts).  A parked set keeps its state in the
+//     output arrays plus a small workspace; a finished trajectory inside a set keeps stepping on its own scratch without committing.
 //   * HBM: initial state in, final state out, ~200 B per trajectory and slice of parking traffic.
 //
 // Reference behaviour: instance.rs:87-262, 343-352, 358-493 (propagate / single_step / derive), spacecraft.rs:191-310 (eom),
@@ -43,16 +46,23 @@ enum { TXI_EPOCH = 0, TXI_STEP, TXI_PREV_STEP, TXI_DET_STEP, TXI_NSTEPS, TXI_NRE
 enum { TXW_FLAGS = 0, TXW_STATUS, TXW_RC, TXW_ATT, TXW_EVCNT, TXW_ACC, TXW_RCST, TXW_COUNT };
 enum { F_FIXED = 1, F_PREVFIXED = 2, F_RETRY = 4, F_LAST = 8, F_DONE = 16, F_BACK = 32, F_VALID = 64 };
 
+// dynamic shared memory: [table blob | NCTX set contexts]; one context:
+//   walker inputs  ub, r2 [32]; rm, im, rp [N+2][32]   (written by the helpers before READY, read by the walkers)
+//   part [P][4][32]                                     (written by the walkers before DONE, read by the helpers)
+//   helper-private: ys [6][32], kst [16][6][32], nxt / er / ycur [6][32], controller fields
 struct TxLayout {
-    unsigned blob, ys, rm, part, kst, nxt, er, ycur, f64, i64, i32, total;
+    unsigned blob, ctx0, ctx_stride;                       // bytes
+    unsigned wk, part, ys, kst, nxt, er, ycur, f64, i64, i32;   // offsets inside a context
+    unsigned total;
 };
-__host__ __device__ inline TxLayout tx_layout(unsigned blob_bytes, int P) {
+__host__ __device__ inline TxLayout tx_layout(unsigned blob_bytes, int P, int N, int nctx) {
     TxLayout L;
+    L.blob = 0;
+    L.ctx0 = (blob_bytes + 127u) & ~127u;
     unsigned o = 0;
-    L.blob = o; o += (blob_bytes + 127u) & ~127u;
-    L.ys = o; o += 2 * 6 * NL * 8;      // double-buffered by stage parity
-    L.rm = o; o += 2 * 9 * NL * 8;
-    L.part = o; o += P * 4 * NL * 8;
+    L.wk = o; o += (2u + 3u * (unsigned)(N + 2)) * NL * 8;
+    L.part = o; o += (unsigned)P * 4 * NL * 8;
+    L.ys = o; o += 6 * NL * 8;
     L.kst = o; o += NYXB_MAX_STAGES * 6 * NL * 8;
     L.nxt = o; o += 6 * NL * 8;
     L.er = o; o += 6 * NL * 8;
@@ -60,16 +70,32 @@ __host__ __device__ inline TxLayout tx_layout(unsigned blob_bytes, int P) {
     L.f64 = o; o += TXF_COUNT * NL * 8;
     L.i64 = o; o += TXI_COUNT * NL * 8;
     L.i32 = o; o += TXW_COUNT * NL * 4;
-    L.total = o;
+    L.ctx_stride = (o + 127u) & ~127u;
+    L.total = L.ctx0 + (unsigned)nctx * L.ctx_stride;
     return L;
 }
 
-struct TxSm {   // typed views of the dynamic shared memory
-    const double2* recA; const double* recK; const double* colseed; const int* sched;
-    double *ys, *rm, *part, *kst, *nxt, *er, *ycur, *f64;
+struct TxSm {   // typed views of one set context
+    double *ub, *r2, *rm, *im, *rp;    // walker inputs
+    double *part, *ys, *kst, *nxt, *er, *ycur, *f64;
     long long* i64;
     int* i32;
 };
+__device__ __forceinline__ TxSm tx_views(unsigned char* smem, const TxLayout& L, int ctx, int N) {
+    unsigned char* b = smem + L.ctx0 + (unsigned)ctx * L.ctx_stride;
+    TxSm sm;
+    sm.ub = reinterpret_cast<double*>(b + L.wk); sm.r2 = sm.ub + NL; sm.rm = sm.r2 + NL; sm.im = sm.rm + (N + 2) * NL; sm.rp = sm.im + (N + 2) * NL;
+    sm.part = reinterpret_cast<double*>(b + L.part); sm.ys = reinterpret_cast<double*>(b + L.ys);
+    sm.kst = reinterpret_cast<double*>(b + L.kst); sm.nxt = reinterpret_cast<double*>(b + L.nxt);
+    sm.er = reinterpret_cast<double*>(b + L.er); sm.ycur = reinterpret_cast<double*>(b + L.ycur);
+    sm.f64 = reinterpret_cast<double*>(b + L.f64); sm.i64 = reinterpret_cast<long long*>(b + L.i64);
+    sm.i32 = reinterpret_cast<int*>(b + L.i32);
+    return sm;
+}
+
+// named barriers (id 0 is __syncthreads): helpers of a context among themselves, helpers -> walkers, walkers -> helpers
+__device__ __forceinline__ void nb_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void nb_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tx_mbar_init(unsigned long long* bar, unsigned count) {
@@ -154,7 +180,7 @@ __device__ __forceinline__ void tx_column(const double2*& A, const double*& K, d
 }
 
 // ---- instance.rs:149-196: choose the step of the next attempt (regular, or the final fixed step to the stop time)
-__device__ __forceinline__ void tx_pick_step(TxSm& sm, int lane, long long stop) {
+__device__ __forceinline__ void tx_pick_step(const TxSm& sm, int lane, long long stop) {
     int fl = sm.i32[TXW_FLAGS * NL + lane];
     if (!(fl & (F_DONE | F_RETRY))) {
         const long long epoch = sm.i64[TXI_EPOCH * NL + lane];
@@ -386,68 +412,105 @@ __device__ __noinline__ void tx_park_ctl(const DevSink& sink, const DevTxQueue& 
     if (sink.cap > 0) sink.count[tr] = (d.n_steps + 1 < sink.cap) ? d.n_steps + 1 : sink.cap;
 }
 
-template <int P>
-__global__ void __launch_bounds__(P * 32, TX_MINB)
+template <int P, int NCTX>
+__global__ void __launch_bounds__((P + 3 * NCTX) * 32, 1)
 nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, const __grid_constant__ DevTxQueue q, size_t n,
           const double* __restrict__ state, const double* __restrict__ consts, const long long* __restrict__ epoch0,
           long long end_epoch, long long* step_io, double* out_state, long long* out_epoch, int* out_status, const DevSink sink,
           unsigned blob_bytes, unsigned off_recK, unsigned off_seed, unsigned off_sched) {
-    static_assert(P >= 8 && P <= NYXB_TX_MAXP, "roles need 8 warps: six components, rotation, controller");
+    static_assert(P <= NYXB_TX_MAXP && NCTX >= 1 && NCTX <= 2, "walker positions / set contexts");
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long tma_bar;
-    __shared__ int s_set, s_round, s_skip, s_exit, s_all_done, s_slice_end;
+    __shared__ int s_set[NCTX], s_round[NCTX], s_skip[NCTX], s_exit[NCTX], s_all_done[NCTX], s_slice_end[NCTX];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    constexpr int W_ROT = 6, W_CTL = 7;
-    const TxLayout L = tx_layout(blob_bytes, P);
-    TxSm sm;
-    sm.recA = reinterpret_cast<const double2*>(smem + L.blob);
-    sm.recK = reinterpret_cast<const double*>(smem + L.blob + off_recK);
-    sm.colseed = reinterpret_cast<const double*>(smem + L.blob + off_seed);
-    sm.sched = reinterpret_cast<const int*>(smem + L.blob + off_sched);
-    sm.ys = reinterpret_cast<double*>(smem + L.ys); sm.rm = reinterpret_cast<double*>(smem + L.rm);
-    sm.part = reinterpret_cast<double*>(smem + L.part); sm.kst = reinterpret_cast<double*>(smem + L.kst);
-    sm.nxt = reinterpret_cast<double*>(smem + L.nxt); sm.er = reinterpret_cast<double*>(smem + L.er);
-    sm.ycur = reinterpret_cast<double*>(smem + L.ycur); sm.f64 = reinterpret_cast<double*>(smem + L.f64);
-    sm.i64 = reinterpret_cast<long long*>(smem + L.i64); sm.i32 = reinterpret_cast<int*>(smem + L.i32);
+    constexpr int NT_RW = (P + 3) * 32;   // threads on a READY / DONE barrier: the walkers + the three helpers of the context
+    constexpr int BAR_HB = 1, BAR_READY = 1 + NCTX, BAR_DONE = 1 + 2 * NCTX;
+    const int N = S.grav.N;
+    const TxLayout L = tx_layout(blob_bytes, P, N, NCTX);
+    const double2* recA = reinterpret_cast<const double2*>(smem + L.blob);
+    const double* recK = reinterpret_cast<const double*>(smem + L.blob + off_recK);
+    const double* colseed = reinterpret_cast<const double*>(smem + L.blob + off_seed);
+    const int* sched = reinterpret_cast<const int*>(smem + L.blob + off_sched);
 
     // ---- CTA-shared tables (records, column seeds, schedule): ONE TMA bulk copy
-    if (tid == 0) tx_mbar_init(&tma_bar, 1);
+    if (tid == 0) {
+        tx_mbar_init(&tma_bar, 1);
+#pragma unroll
+        for (int c = 0; c < NCTX; ++c) s_exit[c] = 0;
+    }
     __syncthreads();
     if (tid == 0) {
         tx_mbar_expect(&tma_bar, blob_bytes);
         tx_bulk_g2s(smem + L.blob, Tx.recA, blob_bytes, &tma_bar);
     }
     tx_mbar_wait(&tma_bar, 0);
-    __syncthreads();
+    __syncthreads();   // the last CTA-wide barrier: from here on walkers and helpers meet on named barriers only
 
+    if (w < P) {
+        // =============================================================================================== WALKER
+        const int* my = sched + w * (2 + 2 * Tx.kmax);
+        const int rec_off = my[0], ncol = my[1];
+        unsigned active = (1u << NCTX) - 1u;
+        while (active) {
+#pragma unroll
+            for (int c = 0; c < NCTX; ++c) {
+                if (!((active >> c) & 1u)) continue;
+                nb_sync(BAR_READY + c, NT_RW);   // the helpers published this stage's inputs of set context c
+                if (*(volatile int*)&s_exit[c]) { active &= ~(1u << c); continue; }
+                const TxSm sm = tx_views(smem, L, c, N);
+                const double ub = sm.ub[lane], r2 = sm.r2[lane];
+                double X = 0.0, Y = 0.0, Z = 0.0, W = 0.0;
+                const double2* A = recA + 2 * rec_off;
+                const double* K = recK + rec_off;
+                double2 a01 = A[0], a23 = A[1];
+                double kk = K[0];
+                for (int k = 0; k < ncol; ++k) {
+                    const int m = my[2 + 2 * k], len = my[3 + 2 * k];
+                    const double* sd = colseed + 4 * m;
+                    // seed Q[m][m] rho^m, W term of the first entry, 2m+1; (cos, sin)((m-1) lambda) cos^(m-1)(phi) closes the column
+                    tx_column(A, K, a01, a23, kk, len, sm.rp[m * NL + lane], sd[1], sd[2], sd[3], ub, r2, sm.rm[(m - 1) * NL + lane],
+                              sm.im[(m - 1) * NL + lane], X, Y, Z, W);
+                }
+                double* pt = sm.part + (w * 4) * NL + lane;
+                pt[0] = X; pt[NL] = Y; pt[2 * NL] = Z; pt[3 * NL] = W;
+                nb_arrive(BAR_DONE + c, NT_RW);   // partial sums of this position are in shared memory
+            }
+        }
+        return;
+    }
+
+    // =================================================================================================== HELPER
+    const int c = (w - P) / 3, j = (w - P) % 3;   // set context, helper index: owns state components j (position) and j + 3 (velocity)
+    const TxSm sm = tx_views(smem, L, c, N);
     const int stages = S.tb.stages;
     const DevGrav& gv = S.grav;
     const bool has_extra = S.n_bodies > 0 || S.has_srp || S.has_drag || S.n_xgrav > 0;
-    // this warp's column schedule (warp-uniform)
-    const int* my = sm.sched + w * (2 + 2 * Tx.kmax);
-    const int rec_off = my[0], ncol = my[1];
+    const bool lead = (j == 0);   // helper 0 also runs the controller and the ticket queue of its context
 
     for (;;) {
         // ---------------------------------------------------------------- acquire a (set, slice) ticket
-        if (tid == 0) {
-            int fin_all = atomicAdd(q.n_finished, 0);
+        if (lead && lane == 0) {
+            const int fin_all = atomicAdd(q.n_finished, 0);
             if (fin_all >= q.n_sets) {
-                s_exit = 1;
+                s_exit[c] = 1;
             } else {
                 const unsigned long long t = atomicAdd(q.ticket, 1ULL);
                 const int set = (int)(t % (unsigned long long)q.n_sets), round = (int)(t / (unsigned long long)q.n_sets);
                 while (atomicAdd(q.slices_done + set, 0) < round) __nanosleep(256);   // the previous slice of this set is parked
                 __threadfence();
-                s_set = set; s_round = round; s_exit = 0;
-                s_skip = atomicAdd(q.finished + set, 0);
+                s_set[c] = set; s_round[c] = round;
+                s_skip[c] = atomicAdd(q.finished + set, 0);
             }
         }
-        __syncthreads();
-        if (s_exit) break;
-        const int set = s_set, round = s_round;
-        if (s_skip) {
-            __syncthreads();
-            if (tid == 0) atomicExch(q.slices_done + set, round + 1);
+        nb_sync(BAR_HB + c, 96);
+        if (s_exit[c]) {
+            nb_arrive(BAR_READY + c, NT_RW);   // releases the walkers, which read s_exit and drop this context
+            return;
+        }
+        const int set = s_set[c], round = s_round[c];
+        if (s_skip[c]) {
+            nb_sync(BAR_HB + c, 96);
+            if (lead && lane == 0) atomicExch(q.slices_done + set, round + 1);
             continue;
         }
         const size_t traj_raw = (size_t)set * NL + lane;
@@ -455,26 +518,29 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
         const size_t tr = valid ? traj_raw : (size_t)set * NL;   // an absent lane shadows the set's first trajectory, never committed
 
         // ---------------------------------------------------------------- load the set
-        if (w < 6) {
-            const double yc = (round == 0) ? state[(size_t)w * n + tr] : __ldcg(out_state + (size_t)w * n + tr);
-            sm.ycur[w * NL + lane] = yc;
-            if (round == 0 && valid && sink.cap > 0) sink.state[((size_t)w * sink.cap) * n + tr] = yc;
-        } else if (w == W_CTL) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int cc = j + 3 * half;
+            const double yc = (round == 0) ? state[(size_t)cc * n + tr] : __ldcg(out_state + (size_t)cc * n + tr);
+            sm.ycur[cc * NL + lane] = yc;
+            if (round == 0 && valid && sink.cap > 0) sink.state[((size_t)cc * sink.cap) * n + tr] = yc;
+        }
+        if (lead) {
             tx_load_ctl(S, sink, q, sm, lane, n, tr, valid, round, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch);
             tx_pick_step(sm, lane, end_epoch);
             const bool done = sm.i32[TXW_FLAGS * NL + lane] & F_DONE;
             const bool all = __all_sync(FULL, done);
-            if (lane == 0) { s_all_done = all; s_slice_end = 0; }
+            if (lane == 0) { s_all_done[c] = all; s_slice_end[c] = 0; }
         }
-        __syncthreads();
+        nb_sync(BAR_HB + c, 96);
 
         // ---------------------------------------------------------------- step attempts of this slice
-        for (int it = 0; !s_all_done; ++it) {
+        for (int it = 0; !s_all_done[c]; ++it) {
             const double h = sm.f64[TXF_H * NL + lane];
             const long long epoch = sm.i64[TXI_EPOCH * NL + lane];
-            // orientation angles at the step epoch (rotation warp, registers live across the stages of this attempt)
+            // orientation angles at the step epoch (every helper keeps its own copy: no exchange)
             double b_sa = 0.0, b_ca = 1.0, b_sd = 1.0, b_cd = 0.0, b_sw = 0.0, b_cw = 1.0;
-            if (w == W_ROT && gv.rot.kind != 0) {
+            if (gv.rot.kind != 0) {
                 const double t_s = dur_to_seconds(epoch);
                 const double d = t_s / 86400.0;
                 const double Tc = d / 36525.0;
@@ -485,227 +551,194 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
             int rc_acc = 0;
             // ---- derive(): one attempt for the 32 trajectories (instance.rs:358-493)
             for (int i = 0; i < stages; ++i) {
-                double* ysb = sm.ys + (i & 1) * 6 * NL;
-                double* rmb = sm.rm + (i & 1) * 9 * NL;
-                if (w < 6) {
-                    // stage state y + h * sum_j a_ij k_j (instance.rs:376-394); stage 0 is y itself
-                    const double yc = sm.ycur[w * NL + lane];
-                    double ysv = yc;
+                // stage state y + h * sum_j a_ij k_j (instance.rs:376-394) of components j and j + 3; stage 0 is y itself
+                double ysv[2];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int cc = j + 3 * half;
+                    const double yc = sm.ycur[cc * NL + lane];
+                    double v = yc;
                     if (i > 0) {
                         const double* arow = &S.tb.a[(i - 1) * NYXB_MAX_STAGES];
-                        const double* kc = sm.kst + w * NL + lane;
-                        double w0 = 0.0, w1 = 0.0;
-                        int j = 0;
-                        for (; j + 1 < i; j += 2) {
-                            w0 = fma(arow[j], kc[j * 6 * NL], w0);
-                            w1 = fma(arow[j + 1], kc[(j + 1) * 6 * NL], w1);
+                        const double* kc = sm.kst + cc * NL + lane;
+                        double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;   // four chains: the sum is latency-bound otherwise
+                        int jj = 0;
+                        for (; jj + 3 < i; jj += 4) {
+                            w0 = fma(arow[jj], kc[jj * 6 * NL], w0);
+                            w1 = fma(arow[jj + 1], kc[(jj + 1) * 6 * NL], w1);
+                            w2 = fma(arow[jj + 2], kc[(jj + 2) * 6 * NL], w2);
+                            w3 = fma(arow[jj + 3], kc[(jj + 3) * 6 * NL], w3);
                         }
-                        if (j < i) w0 = fma(arow[j], kc[j * 6 * NL], w0);
-                        ysv = fma(h, w0 + w1, yc);
+                        for (; jj < i; ++jj) w0 = fma(arow[jj], kc[jj * 6 * NL], w0);
+                        v = fma(h, (w0 + w1) + (w2 + w3), yc);
                     }
-                    ysb[w * NL + lane] = ysv;
-                } else if (w == W_ROT) {
-                    // inertial -> body-fixed DCM at the stage time: first-order update of the (slow) pole angles, exact angle
-                    // addition for the prime-meridian angle (the stage epoch is ns-truncated, cosmic/mod.rs:102)
-                    double R[9];
-                    if (gv.rot.kind == 0) {
-                        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
-                    } else {
-                        const long long off_ns = (i > 0) ? dur_from_seconds(S.tb.c[i - 1] * h) : 0;
-                        const double dt_s = (double)off_ns * 1e-9;
-                        const double da = gv.rot.ra_dot * dt_s, dd = gv.rot.dec_dot * dt_s, dw = gv.rot.wdot * dt_s;
-                        const double sa = fma(b_ca, da, b_sa), ca = fma(-b_sa, da, b_ca);
-                        const double sd = fma(b_cd, dd, b_sd), cd = fma(-b_sd, dd, b_cd);
-                        double sdl, cdl;
-                        if (fabs(dw) < 0.02) {
-                            const double z = dw * dw;
-                            sdl = dw * fma(z, fma(z, 1.0 / 120.0, -1.0 / 6.0), 1.0);
-                            cdl = fma(z, fma(z, fma(z, -1.0 / 720.0, 1.0 / 24.0), -0.5), 1.0);
-                        } else {
-                            det_sincos(dw, sdl, cdl);
-                        }
-                        const double sw = fma(b_sw, cdl, b_cw * sdl), cw = fma(b_cw, cdl, -(b_sw * sdl));
-                        const double b00 = -sa, b01 = ca;
-                        const double b10 = -(sd * ca), b11 = -(sd * sa), b12 = cd;
-                        R[0] = fma(cw, b00, sw * b10); R[1] = fma(cw, b01, sw * b11); R[2] = sw * b12;
-                        R[3] = fma(cw, b10, -(sw * b00)); R[4] = fma(cw, b11, -(sw * b01)); R[5] = cw * b12;
-                        R[6] = cd * ca; R[7] = cd * sa; R[8] = sd;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) rmb[k * NL + lane] = R[k];
+                    ysv[half] = v;
+                    sm.ys[cc * NL + lane] = v;
                 }
-                __syncthreads();   // (A) stage state and DCM of this stage are in shared memory
+                // inertial -> body-fixed DCM at the stage time: first-order update of the (slow) pole angles, exact angle addition
+                // for the prime-meridian angle (the stage epoch is ns-truncated, cosmic/mod.rs:102)
+                const long long off_ns = (i > 0) ? dur_from_seconds(S.tb.c[i - 1] * h) : 0;
+                double R[9];
+                if (gv.rot.kind == 0) {
+                    R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+                } else {
+                    const double dt_s = (double)off_ns * 1e-9;
+                    const double da = gv.rot.ra_dot * dt_s, dd = gv.rot.dec_dot * dt_s, dw = gv.rot.wdot * dt_s;
+                    const double sa = fma(b_ca, da, b_sa), ca = fma(-b_sa, da, b_ca);
+                    const double sd = fma(b_cd, dd, b_sd), cd = fma(-b_sd, dd, b_cd);
+                    double sdl, cdl;
+                    if (fabs(dw) < 0.02) {
+                        const double z = dw * dw;
+                        sdl = dw * fma(z, fma(z, 1.0 / 120.0, -1.0 / 6.0), 1.0);
+                        cdl = fma(z, fma(z, fma(z, -1.0 / 720.0, 1.0 / 24.0), -0.5), 1.0);
+                    } else {
+                        det_sincos(dw, sdl, cdl);
+                    }
+                    const double sw = fma(b_sw, cdl, b_cw * sdl), cw = fma(b_cw, cdl, -(b_sw * sdl));
+                    const double b00 = -sa, b01 = ca;
+                    const double b10 = -(sd * ca), b11 = -(sd * sa), b12 = cd;
+                    R[0] = fma(cw, b00, sw * b10); R[1] = fma(cw, b01, sw * b11); R[2] = sw * b12;
+                    R[3] = fma(cw, b10, -(sw * b00)); R[4] = fma(cw, b11, -(sw * b01)); R[5] = cw * b12;
+                    R[6] = cd * ca; R[7] = cd * sa; R[8] = sd;
+                }
+                nb_sync(BAR_HB + c, 96);   // the three position components of the stage state are in shared memory
 
-                // ---- every warp: body-fixed position, 1/r, recursion scalars, powers of its columns, column walk
+                // ---- body-fixed position, 1/r, recursion scalars, power tables -> walker inputs
+                const double p0 = sm.ys[lane], p1 = sm.ys[NL + lane], p2 = sm.ys[2 * NL + lane];
+                double y0 = p0, y1 = p1, y2 = p2;
+                double ir_c = 0.0;   // 1/|r| about the integration centre (two-body term)
+                if (S.grav_body >= 0) {   // field of another body: the state is translated to it first (gravity_field.rs:149-154)
+                    ir_c = rsqrt(fma(y2, y2, fma(y1, y1, y0 * y0)));
+                    tx_field_offset(S, epoch + off_ns, y0, y1, y2);
+                }
+                const double rb0 = fma(R[2], y2, fma(R[1], y1, R[0] * y0));
+                const double rb1 = fma(R[5], y2, fma(R[4], y1, R[3] * y0));
+                const double rb2 = fma(R[8], y2, fma(R[7], y1, R[6] * y0));
+                const double inv_r = rsqrt(fma(rb2, rb2, fma(rb1, rb1, rb0 * rb0)));
+                if (S.grav_body < 0) ir_c = inv_r;
+                const double rho = gv.r_eq * inv_r;
+                const double s_ = rb0 * inv_r, t_ = rb1 * inv_r, u_ = rb2 * inv_r;
+                if (lead) { sm.ub[lane] = u_ * rho; sm.r2[lane] = rho * rho; }
+                {   // z^k = (cos, sin)(k lambda) cos^k(phi), rho^k (2k-1)!! for k = j, j+3, ... <= N+1 (ratio z^3, rho^3)
+                    const double z2r = fma(s_, s_, -(t_ * t_)), z2i = 2.0 * s_ * t_;
+                    const double z3r = fma(z2r, s_, -(z2i * t_)), z3i = fma(z2r, t_, z2i * s_);
+                    const double rho2 = rho * rho, rho3 = rho2 * rho;
+                    double zr = (j == 0) ? 1.0 : (j == 1 ? s_ : z2r), zi = (j == 0) ? 0.0 : (j == 1 ? t_ : z2i);
+                    double pr = (j == 0) ? 1.0 : (j == 1 ? rho : rho2);
+                    for (int k = j; k <= N + 1; k += 3) {
+                        sm.rm[k * NL + lane] = zr; sm.im[k * NL + lane] = zi; sm.rp[k * NL + lane] = pr * colseed[4 * k];
+                        const double nr = fma(zr, z3r, -(zi * z3i));
+                        zi = fma(zr, z3i, zi * z3r); zr = nr; pr *= rho3;
+                    }
+                }
+                nb_arrive(BAR_READY + c, NT_RW);   // walker inputs of this stage are published
+                nb_sync(BAR_DONE + c, NT_RW);      // ... the walkers' partial sums are back
+
+                // ---- reduce the partial sums, assemble the acceleration component j (spacecraft.rs:216-247)
+                double X, Y, Z, Wt;
                 {
-                    double y0 = ysb[lane], y1 = ysb[NL + lane], y2 = ysb[2 * NL + lane];
-                    if (S.grav_body >= 0) tx_field_offset(S, epoch + ((i > 0) ? dur_from_seconds(S.tb.c[i - 1] * h) : 0), y0, y1, y2);
-                    const double rb0 = fma(rmb[2 * NL + lane], y2, fma(rmb[NL + lane], y1, rmb[lane] * y0));
-                    const double rb1 = fma(rmb[5 * NL + lane], y2, fma(rmb[4 * NL + lane], y1, rmb[3 * NL + lane] * y0));
-                    const double rb2 = fma(rmb[8 * NL + lane], y2, fma(rmb[7 * NL + lane], y1, rmb[6 * NL + lane] * y0));
-                    const double inv_r = rsqrt(fma(rb2, rb2, fma(rb1, rb1, rb0 * rb0)));
-                    const double rho = gv.r_eq * inv_r;
-                    const double ub = (rb2 * inv_r) * rho;
-                    const double r2 = rho * rho;
-                    // z^e = (cos, sin)(e lambda) cos^e(phi) and rho^(e+1) for the two interleaved exponent sequences of this position:
-                    // e = w + 2P j (za, pa) and e = 2P-1-w + 2P j (zb, pb); binary powering with warp-uniform bits, the squarings end at
-                    // the common ratio z^(2P), rho^(2P)
-                    double br = rb0 * inv_r, bi = rb1 * inv_r, bp = rho;
-                    double zar = 1.0, zai = 0.0, zbr = 1.0, zbi = 0.0, pa = rho, pb = rho;
-                    const int ea = w, eb = 2 * P - 1 - w;
+                    double ax[4] = {0.0, 0.0, 0.0, 0.0}, ay[4] = {0.0, 0.0, 0.0, 0.0}, az[4] = {0.0, 0.0, 0.0, 0.0}, aw4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-                    for (int bit = 1; bit < 2 * P; bit <<= 1) {
-                        if (ea & bit) {
-                            const double nr = fma(zar, br, -(zai * bi));
-                            zai = fma(zar, bi, zai * br); zar = nr; pa *= bp;
-                        }
-                        if (eb & bit) {
-                            const double nr = fma(zbr, br, -(zbi * bi));
-                            zbi = fma(zbr, bi, zbi * br); zbr = nr; pb *= bp;
-                        }
-                        const double nb = fma(br, br, -(bi * bi));
-                        bi = 2.0 * br * bi; br = nb; bp *= bp;
+                    for (int p = 0; p < P; ++p) {
+                        const double* pt = sm.part + (p * 4) * NL + lane;
+                        ax[p & 3] += pt[0]; ay[p & 3] += pt[NL]; az[p & 3] += pt[2 * NL]; aw4[p & 3] += pt[3 * NL];
                     }
-                    double X = 0.0, Y = 0.0, Z = 0.0, W = 0.0;
-                    const double2* A = sm.recA + 2 * rec_off;
-                    const double* K = sm.recK + rec_off;
-                    double2 a01 = A[0], a23 = A[1];
-                    double kk = K[0];
-                    for (int k = 0; k < ncol; k += 2) {
-                        {   // column of the first sequence
-                            const int m = my[2 + 2 * k], len = my[3 + 2 * k];
-                            const double* sd = sm.colseed + 4 * m;
-                            tx_column(A, K, a01, a23, kk, len, pa * sd[0], sd[1], sd[2], sd[3], ub, r2, zar, zai, X, Y, Z, W);
-                            const double nr = fma(zar, br, -(zai * bi));
-                            zai = fma(zar, bi, zai * br); zar = nr; pa *= bp;
-                        }
-                        if (k + 1 < ncol) {   // column of the second sequence
-                            const int m = my[4 + 2 * k], len = my[5 + 2 * k];
-                            const double* sd = sm.colseed + 4 * m;
-                            tx_column(A, K, a01, a23, kk, len, pb * sd[0], sd[1], sd[2], sd[3], ub, r2, zbr, zbi, X, Y, Z, W);
-                            const double nr = fma(zbr, br, -(zbi * bi));
-                            zbi = fma(zbr, bi, zbi * br); zbr = nr; pb *= bp;
-                        }
-                    }
-                    double* pt = sm.part + (w * 4) * NL + lane;
-                    pt[0] = X; pt[NL] = Y; pt[2 * NL] = Z; pt[3 * NL] = W;
+                    X = (ax[0] + ax[1]) + (ax[2] + ax[3]); Y = (ay[0] + ay[1]) + (ay[2] + ay[3]);
+                    Z = (az[0] + az[1]) + (az[2] + az[3]); Wt = (aw4[0] + aw4[1]) + (aw4[2] + aw4[3]);
                 }
-                __syncthreads();   // (C) partial sums of all positions are in shared memory
-
-                if (w < 6) {
-                    double kval;
-                    if (w < 3) {
-                        kval = ysb[(3 + w) * NL + lane];   // dr/dt = v
-                    } else {
-                        // ---- reduce the partial sums, assemble the acceleration component j (spacecraft.rs:216-247)
-                        const int j = w - 3;
-                        double X = 0.0, Y = 0.0, Z = 0.0, Wt = 0.0;
+                // rr_n A[n][m] = K0 rho (rho^n A),  rr_{n-1} A[n][m] = K0 (rho^n A),  K0 = mu / (r R_eq)
+                const double K0 = (gv.mu * gv.inv_r_eq) * inv_r;
+                const double K1 = K0 * rho;
+                const double aw = -K0 * Wt;
+                const double ab0 = fma(aw, s_, K1 * X), ab1 = fma(aw, t_, K1 * Y), ab2 = fma(aw, u_, K1 * Z);
+                const double fac = -S.mu_central * ir_c * ir_c * ir_c;   // two-body (orbital.rs:86-92), from the same 1/r when the field is the centre's
+                const double pj = (j == 0) ? p0 : (j == 1 ? p1 : p2);
+                double acc = fma(fac, pj, fma(R[6 + j], ab2, fma(R[3 + j], ab1, R[j] * ab0)));
+                if (has_extra) {
+                    double yy[9], aa[3] = {0.0, 0.0, 0.0};
+                    const double hz = (i > 0) ? h * 0.0 : 0.0;
 #pragma unroll
-                        for (int p = 0; p < P; ++p) {
-                            const double* pt = sm.part + (p * 4) * NL + lane;
-                            X += pt[0]; Y += pt[NL]; Z += pt[2 * NL]; Wt += pt[3 * NL];
-                        }
-                        double y0 = ysb[lane], y1 = ysb[NL + lane], y2 = ysb[2 * NL + lane];
-                        double ir_c = 0.0;   // 1/|r| about the integration centre (two-body term)
-                        if (S.grav_body >= 0) {
-                            ir_c = rsqrt(fma(y2, y2, fma(y1, y1, y0 * y0)));
-                            tx_field_offset(S, epoch + ((i > 0) ? dur_from_seconds(S.tb.c[i - 1] * h) : 0), y0, y1, y2);
-                        }
-                        const double rb0 = fma(rmb[2 * NL + lane], y2, fma(rmb[NL + lane], y1, rmb[lane] * y0));
-                        const double rb1 = fma(rmb[5 * NL + lane], y2, fma(rmb[4 * NL + lane], y1, rmb[3 * NL + lane] * y0));
-                        const double rb2 = fma(rmb[8 * NL + lane], y2, fma(rmb[7 * NL + lane], y1, rmb[6 * NL + lane] * y0));
-                        const double inv_r = rsqrt(fma(rb2, rb2, fma(rb1, rb1, rb0 * rb0)));
-                        if (S.grav_body < 0) ir_c = inv_r;
-                        const double rho = gv.r_eq * inv_r;
-                        const double s_ = rb0 * inv_r, t_ = rb1 * inv_r, u_ = rb2 * inv_r;
-                        // rr_n A[n][m] = K0 rho (rho^n A),  rr_{n-1} A[n][m] = K0 (rho^n A),  K0 = mu / (r R_eq)
-                        const double K0 = (gv.mu * gv.inv_r_eq) * inv_r;
-                        const double K1 = K0 * rho;
-                        const double aw = -K0 * Wt;
-                        const double ab0 = fma(aw, s_, K1 * X), ab1 = fma(aw, t_, K1 * Y), ab2 = fma(aw, u_, K1 * Z);
-                        const double fac = -S.mu_central * ir_c * ir_c * ir_c;   // two-body (orbital.rs:86-92), from the same 1/r when the field is the centre's
-                        const double yj = ysb[j * NL + lane];
-                        kval = fma(fac, yj, fma(rmb[(6 + j) * NL + lane], ab2, fma(rmb[(3 + j) * NL + lane], ab1, rmb[j * NL + lane] * ab0)));
-                        if (has_extra) {
-                            double yy[9], aa[3] = {0.0, 0.0, 0.0};
-                            const double hz = (i > 0) ? h * 0.0 : 0.0;
-#pragma unroll
-                            for (int e = 0; e < 6; ++e) yy[e] = ysb[e * NL + lane];
-                            yy[6] = sm.f64[TXF_CR * NL + lane] + hz; yy[7] = sm.f64[TXF_CD * NL + lane] + hz; yy[8] = sm.f64[TXF_PM * NL + lane] + hz;
-                            const long long off_ns = (i > 0) ? dur_from_seconds(S.tb.c[i - 1] * h) : 0;
-                            const int rcx = tx_extra(S, sm.f64[TXF_DRY * NL + lane], sm.f64[TXF_EXTRA * NL + lane], sm.f64[TXF_SRPA * NL + lane],
-                                                     sm.f64[TXF_DRAGA * NL + lane], epoch + off_ns, yy, aa);
-                            kval += (j == 0) ? aa[0] : (j == 1 ? aa[1] : aa[2]);
-                            if (rcx && !rc_acc) rc_acc = rcx | ((i + 1) << 8);
-                        }
-                    }
-                    sm.kst[(i * 6 + w) * NL + lane] = kval;
+                    for (int e = 0; e < 6; ++e) yy[e] = sm.ys[e * NL + lane];
+                    yy[6] = sm.f64[TXF_CR * NL + lane] + hz; yy[7] = sm.f64[TXF_CD * NL + lane] + hz; yy[8] = sm.f64[TXF_PM * NL + lane] + hz;
+                    const int rcx = tx_extra(S, sm.f64[TXF_DRY * NL + lane], sm.f64[TXF_EXTRA * NL + lane], sm.f64[TXF_SRPA * NL + lane],
+                                             sm.f64[TXF_DRAGA * NL + lane], epoch + off_ns, yy, aa);
+                    acc += (j == 0) ? aa[0] : (j == 1 ? aa[1] : aa[2]);
+                    if (rcx && !rc_acc) rc_acc = rcx | ((i + 1) << 8);
                 }
+                sm.kst[(i * 6 + j) * NL + lane] = ysv[1];      // dr_j/dt = v_j
+                sm.kst[(i * 6 + 3 + j) * NL + lane] = acc;     // dv_j/dt
             }
             // ---- candidate state and error estimate of this attempt (instance.rs:402-414)
-            if (w < 6) {
-                const double yc = sm.ycur[w * NL + lane];
+            {
                 const bool fixed = sm.i32[TXW_FLAGS * NL + lane] & F_FIXED;
-                double nx = yc, er = 0.0;
-                for (int i = 0; i < stages; ++i) {
-                    const double ki = sm.kst[(i * 6 + w) * NL + lane];
-                    if (!fixed) er = fma(h * S.tb.e[i], ki, er);
-                    nx = fma(h * S.tb.b[i], ki, nx);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int cc = j + 3 * half;
+                    double nx = sm.ycur[cc * NL + lane], er = 0.0;
+                    for (int i = 0; i < stages; ++i) {
+                        const double ki = sm.kst[(i * 6 + cc) * NL + lane];
+                        if (!fixed) er = fma(h * S.tb.e[i], ki, er);
+                        nx = fma(h * S.tb.b[i], ki, nx);
+                    }
+                    sm.nxt[cc * NL + lane] = nx;
+                    sm.er[cc * NL + lane] = er;
                 }
-                sm.nxt[w * NL + lane] = nx;
-                sm.er[w * NL + lane] = er;
-                if (w == 3) sm.i32[TXW_RCST * NL + lane] = rc_acc;
+                if (lead) sm.i32[TXW_RCST * NL + lane] = rc_acc;
             }
-            __syncthreads();   // (D)
-            if (w == W_CTL) {
+            nb_sync(BAR_HB + c, 96);
+            if (lead) {
                 tx_controller(S, sink, sm, lane, n, tr, stages);
                 const bool slice_end = q.slice > 0 && it + 1 >= q.slice;
                 if (!slice_end) tx_pick_step(sm, lane, end_epoch);
                 const bool done = sm.i32[TXW_FLAGS * NL + lane] & F_DONE;
                 const bool all = __all_sync(FULL, done);
-                if (lane == 0) { s_all_done = all; s_slice_end = slice_end; }
+                if (lane == 0) { s_all_done[c] = all; s_slice_end[c] = slice_end; }
             }
-            __syncthreads();   // (E)
-            if (w < 6 && sm.i32[TXW_ACC * NL + lane]) {
-                const double nx = sm.nxt[w * NL + lane];
-                sm.ycur[w * NL + lane] = nx;
+            nb_sync(BAR_HB + c, 96);
+            if (sm.i32[TXW_ACC * NL + lane]) {
                 const long long ns = sm.i64[TXI_NSTEPS * NL + lane];
-                // the channel send of instance.rs:186-193 / 255-259: lanes are consecutive trajectories, one 256-byte store per warp
-                if (valid && ns < sink.cap) sink.state[((size_t)w * sink.cap + (size_t)ns) * n + tr] = nx;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int cc = j + 3 * half;
+                    const double nx = sm.nxt[cc * NL + lane];
+                    sm.ycur[cc * NL + lane] = nx;
+                    // the channel send of instance.rs:186-193 / 255-259: lanes are consecutive trajectories, one 256-byte store per warp
+                    if (valid && ns < sink.cap) sink.state[((size_t)cc * sink.cap + (size_t)ns) * n + tr] = nx;
+                }
             }
-            if (s_slice_end) break;
+            if (s_slice_end[c]) break;
         }
 
         // ---------------------------------------------------------------- park the set (== final outputs when it is done)
-        if (w < 6) {
-            if (valid) out_state[(size_t)w * n + tr] = sm.ycur[w * NL + lane];
-        } else if (w == W_CTL) {
-            tx_park_ctl(sink, q, sm, lane, n, tr, step_io, out_state, out_epoch, out_status);
+        if (valid) {
+            out_state[(size_t)j * n + tr] = sm.ycur[j * NL + lane];
+            out_state[(size_t)(j + 3) * n + tr] = sm.ycur[(j + 3) * NL + lane];
         }
+        if (lead) tx_park_ctl(sink, q, sm, lane, n, tr, step_io, out_state, out_epoch, out_status);
         __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-            if (s_all_done) {
+        nb_sync(BAR_HB + c, 96);
+        if (lead && lane == 0) {
+            if (s_all_done[c]) {
                 atomicExch(q.finished + set, 1);
                 atomicAdd(q.n_finished, 1);
             }
             __threadfence();
             atomicExch(q.slices_done + set, round + 1);
         }
-        // s_* are rewritten by thread 0 only after the barrier at the top of the next ticket
-        __syncthreads();
+        nb_sync(BAR_HB + c, 96);   // s_* of this context are rewritten by its lead lane only after this barrier
     }
 }
 
-template <int P>
+// walker positions and set contexts for a field of degree N: two sets in flight while both fit in shared memory
+template <int P, int NCTX>
 cudaError_t tx_launch_p(const DevSetup* S, const DevTx* Tx, const DevTxQueue* q, size_t n, const double* state, const double* consts,
                         const long long* epoch0, long long end_epoch, long long* step_io, double* out_state, long long* out_epoch,
                         int* out_status, const DevSink* sink, int grid, size_t smem, unsigned blob_bytes, unsigned off_recK,
                         unsigned off_seed, unsigned off_sched, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(nyxb_k_tx<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(nyxb_k_tx<P, NCTX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    nyxb_k_tx<P><<<grid, P * 32, smem, stream>>>(*S, *Tx, *q, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_status,
-                                                 *sink, blob_bytes, off_recK, off_seed, off_sched);
+    nyxb_k_tx<P, NCTX><<<grid, (P + 3 * NCTX) * 32, smem, stream>>>(*S, *Tx, *q, n, state, consts, epoch0, end_epoch, step_io, out_state,
+                                                                  out_epoch, out_status, *sink, blob_bytes, off_recK, off_seed, off_sched);
     return cudaGetLastError();
 }
 
@@ -804,37 +837,36 @@ void nyxb_tx_build_host(int N, int M, const double* c_nm, const double* s_nm, in
     }
 }
 
-extern "C" int nyxb_tx_occupancy(const DevSetup* S, const DevTx* Tx, size_t* smem_bytes) {
+// set contexts per CTA: two sets in flight while both fit beside the table (P = 8: degrees up to ~40), one otherwise
+static int tx_contexts(const DevSetup* S, const DevTx* Tx, size_t* smem_bytes) {
     const TxBlob b = tx_blob(S->grav.N, Tx->P, Tx->n_rec, Tx->kmax);
-    const size_t smem = tx_layout(b.bytes, Tx->P).total;
-    if (smem_bytes) *smem_bytes = smem;
-    if (smem > 227 * 1024) return 0;
-    int occ = 0;
-    cudaError_t e = cudaErrorInvalidValue;
-    if (Tx->P == 8) {
-        if (cudaFuncSetAttribute(nyxb_k_tx<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nyxb_k_tx<8>, 8 * 32, smem);
-    } else if (Tx->P == 16) {
-        if (cudaFuncSetAttribute(nyxb_k_tx<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nyxb_k_tx<16>, 16 * 32, smem);
+    for (int nctx = (Tx->P == 8 ? 2 : 1); nctx >= 1; --nctx) {
+        const size_t smem = tx_layout(b.bytes, Tx->P, S->grav.N, nctx).total;
+        if (smem <= 227 * 1024) { if (smem_bytes) *smem_bytes = smem; return nctx; }
     }
-    return e == cudaSuccess ? occ : 0;
+    return 0;
 }
 
+// set contexts one SM holds for this setup (one persistent CTA per SM; 0: the tables do not fit) and its dynamic shared memory
+extern "C" int nyxb_tx_occupancy(const DevSetup* S, const DevTx* Tx, size_t* smem_bytes) {
+    if (Tx->P != 8 && Tx->P != 16) return 0;
+    return tx_contexts(S, Tx, smem_bytes);
+}
+
+// `grid` CTAs, each with nyxb_tx_occupancy() set contexts
 extern "C" cudaError_t nyxb_launch_tx(const DevSetup* S, const DevTx* Tx, const DevTxQueue* q, size_t n, const double* state,
                                       const double* consts, const long long* epoch0, long long end_epoch, long long* step_io,
                                       double* out_state, long long* out_epoch, int* out_status, const DevSink* sink,
                                       int grid, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     const TxBlob b = tx_blob(S->grav.N, Tx->P, Tx->n_rec, Tx->kmax);
-    const size_t smem = tx_layout(b.bytes, Tx->P).total;
-    if (smem > 227 * 1024 || grid < 1) return cudaErrorInvalidConfiguration;
-#define NYXB_TX_GO(PP) tx_launch_p<PP>(S, Tx, q, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_status, sink, grid, smem, b.bytes, b.off_recK, b.off_seed, b.off_sched, stream)
-    switch (Tx->P) {
-    case 8: return NYXB_TX_GO(8);
-    case 16: return NYXB_TX_GO(16);
-    default: return cudaErrorInvalidValue;
-    }
+    size_t smem = 0;
+    const int nctx = tx_contexts(S, Tx, &smem);
+    if (nctx < 1 || grid < 1) return cudaErrorInvalidConfiguration;
+#define NYXB_TX_GO(PP, CC) tx_launch_p<PP, CC>(S, Tx, q, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_status, sink, grid, smem, b.bytes, b.off_recK, b.off_seed, b.off_sched, stream)
+    if (Tx->P == 8) return nctx == 2 ? NYXB_TX_GO(8, 2) : NYXB_TX_GO(8, 1);
+    if (Tx->P == 16) return NYXB_TX_GO(16, 1);
+    return cudaErrorInvalidValue;
 #undef NYXB_TX_GO
 }
 

@@ -55,5 +55,5 @@ extern "C" cudaError_t nyxb_launch_tx(const DevSetup* S, const DevTx* Tx, const 
                                       const double* consts, const long long* epoch0, long long end_epoch, long long* step_io,
                                       double* out_state, long long* out_epoch, int* out_status, const DevSink* sink,
                                       int grid, cudaStream_t stream);
-// resident CTAs per SM the kernel can hold for this setup (0: the tables do not fit) and its dynamic shared memory
+// set contexts per SM (one persistent CTA per SM holding 1 or 2 sets; 0: the tables do not fit) and the CTA's dynamic shared memory
 extern "C" int nyxb_tx_occupancy(const DevSetup* S, const DevTx* Tx, size_t* smem_bytes);

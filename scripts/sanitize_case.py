@@ -35,7 +35,7 @@ def run(which):
         eng = prop.engine(nb.EARTH_J2000, None)
         eng.set_kernel({"coop": nb.KERNEL_COOP, "tx": nb.KERNEL_TRANSPOSED, "thread": nb.KERNEL_THREAD}[which])
         if which == "tx":
-            eng.set_tx_tuning(3, 2)   # 3 sets on 2 CTAs: parking and ticket hand-over are exercised
+            eng.set_tx_tuning(3, 1)   # 3 sets on one CTA (two set contexts): parking and ticket hand-over are exercised
         out = eng.propagate_batch(st, cs, ep, 1500 * S, traj_capacity=40)
         assert (out[3] == 0).all(), out[3]
         print(which, "steps", int(out[2]["n_steps"].sum()), "rejected", int(out[2]["n_rejected"].sum()))

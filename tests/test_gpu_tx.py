@@ -1,5 +1,5 @@
-"""GPU parity of the TRANSPOSED kernel (csrc/nyxb_tx.cu: lane = trajectory, warp = column position, persistent CTAs with
-(set, time-slice) tickets) against the CPU oracle, through the C ABI with `nyxb_engine_set_kernel(NYXB_KERNEL_TRANSPOSED)`.
+"""GPU parity of the TRANSPOSED kernel (csrc/nyxb_tx.cu: lane = trajectory, walker warp = column position, helper warps for the serial
+phases, two sets in flight per persistent CTA, (set, time-slice) tickets) against the CPU oracle, through the C ABI with `nyxb_engine_set_kernel(NYXB_KERNEL_TRANSPOSED)`.
 Tolerances as for the lane-cooperative FAST kernel: adaptive runs differ from the oracle by the integrator's own step-sequence
 sensitivity (5e-7 km over 4-6 h, 1e-6 km being the north-star bound); a FIXED step pins the regrouped harmonic sum to round-off
 (5e-9 km).  Time slicing must not change a single bit (same arithmetic, state parked and restored exactly)."""
@@ -97,7 +97,7 @@ def test_transposed_kernel_time_slicing_is_bit_invisible(oracle):
     step0 = np.full(n, 600 * S, dtype=np.int64)   # the PropInstance step carried in and out (instance.rs:56)
     base = eng.propagate_batch(st, cs, ep, end, step_ns=step0.copy(), traj_capacity=400)
     assert (base[3] == 0).all() and base[2]["n_rejected"].sum() > 0
-    for slice_attempts, max_ctas in ((7, 2), (1, 3), (64, 1), (5, 6)):
+    for slice_attempts, max_ctas in ((7, 2), (1, 3), (64, 1), (5, 6)):   # CTAs of two set contexts each: 4, 6, 2 contexts for 7 sets; all resident
         eng.set_tx_tuning(slice_attempts, max_ctas)
         got = eng.propagate_batch(st, cs, ep, end, step_ns=step0.copy(), traj_capacity=400)
         assert np.array_equal(got[0], base[0]) and np.array_equal(got[1], base[1]) and np.array_equal(got[3], base[3])
@@ -114,12 +114,12 @@ def test_transposed_kernel_time_slicing_is_bit_invisible(oracle):
 
 
 def test_transposed_kernel_backward_events_and_statuses(oracle):
-    n = 64
+    n = 96
     mc, (st, cs, ep) = leo_ensemble(n, seed=5)
     dyn, _ = _leo_dyn(12)
     prop = nb.Propagator.default(dyn, mode=nb.MODE_FAST)
     eng = _tx_engine(prop)
-    eng.set_tx_tuning(9, 1)   # one CTA, two sets: every slice boundary is exercised as well
+    eng.set_tx_tuning(9, 1)   # one CTA (two set contexts), three sets: every slice boundary is exercised as well
     # forward, then backward to the start
     fwd, fep, _, fst = eng.propagate_batch(st, cs, ep, 3 * 3600 * S)
     back, bep, _, bst = eng.propagate_batch(fwd, cs, fep, 0)
