@@ -61,6 +61,8 @@ def parse_args():
     p.add_argument("--no-strict", action="store_true", help="skip the extra bit-parity (STRICT mode) pass at N=1")
     p.add_argument("--record", type=int, default=0, metavar="CAP",
                    help="also time one pass with trajectory recording (CAP records per trajectory, device-resident sink)")
+    p.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                   help="weak: --n-traj trajectories PER GPU (the driver's scaling run); strong: --n-traj in total, sharded over the GPUs")
     p.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
                    help="c2 = BASELINE configs[1] (the metric's workload); c3/c4/c5 = configs[2]/[3]/[4], reported for context only")
     a = p.parse_args()
@@ -201,7 +203,8 @@ def bench_c5_reference(args, nb):
     import multiprocessing as mp
 
     global _C5_SC
-    cores = os.cpu_count() or 8
+    host = host_cores()
+    cores = host["usable"]
     m_s = 60
     args_small = argparse.Namespace(**vars(args))
     args_small.span_days = max(m_s * 60 / 86400.0 + 0.01, 0.05)
@@ -220,7 +223,7 @@ def bench_c5_reference(args, nb):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"C5 sample: {cores} LRO-like EKFs (GRAIL {_C5_SC['deg']}x{_C5_SC['deg']} + Earth/Sun + SRP), first {m_s} measurement epochs"},
-            "cpu_baseline": {"value": value, "unit": "trajectory-steps/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": value, "unit": "trajectory-steps/s", "cores": cores, "host": host, "kind": "port",
                              "sample": f"{cores} filters x {m_s} measurement epochs per step, one process per filter (numpy + C oracle)"},
             "e2e": {"value": value, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -298,6 +301,10 @@ def bench_c5(args, nb, local_rank):
     return 0
 
 
+# bounded CPU samples of the reference arm (trajectories over the FULL span): fixed, so that runs are comparable
+REF_SAMPLE = {"c2": 1024, "c3": 8192, "c4": 64}
+PARITY_BOUND_KM = 1e-6   # north-star: sub-mm position over the benchmark span
+
 WORKLOAD_TEXT = {
     "c2": "C2: {n} LEO trajectories/GPU (alt 300 km, e 0.015, i 68.5 deg; N(0, 1 km / 1 m/s) dispersions), two-body + JGM-3 {deg}x{deg}, "
           "adaptive RK89 (IntegratorOptions::default), {span:g}-day span",
@@ -340,7 +347,39 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-def cpu_reference_leg(args, nb, sample_n, repeats=1):
+def host_cores():
+    """What the CPU arm really gets: logical CPUs the process may run on (affinity mask), the cgroup CPU quota if any, and the
+    machine's nominal count.  os.cpu_count() alone said 128 on two boxes whose CPU arms differed 5.6x."""
+    info = {"logical": os.cpu_count()}
+    try:
+        info["affinity"] = len(os.sched_getaffinity(0))
+    except Exception:
+        info["affinity"] = info["logical"]
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = Path(path).read_text().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    quota = float(txt[0]) / float(txt[1])
+            else:
+                q = float(txt[0])
+                if q > 0:
+                    quota = q / float(Path("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read_text())
+            break
+        except Exception:
+            continue
+    info["cgroup_quota_cpus"] = quota
+    usable = info["affinity"] if quota is None else max(1, min(info["affinity"], int(quota)))
+    info["usable"] = usable
+    try:
+        info["loadavg_1m"] = os.getloadavg()[0]
+    except Exception:
+        pass
+    return info
+
+
+def cpu_reference_leg(args, nb, sample_n, repeats=1, speed_build=False):
     """The reference's CPU path for the same workload: the C restatement of the reference algorithm
     (oracle/, OpenMP over trajectories == the rayon par_iter of mc/montecarlo.rs:233-253), all host cores,
     on a bounded sample of the same ensemble."""
@@ -350,15 +389,17 @@ def cpu_reference_leg(args, nb, sample_n, repeats=1):
     prop = nb.Propagator.default(dyn)
     packed = dyn.pack(frame, almanac)
     end = int(args.span_days * DAY)
-    cores = os.cpu_count() or pyoracle.num_threads()  # explicit: torchrun exports OMP_NUM_THREADS=1
+    host = host_cores()
+    cores = host["usable"]  # explicit thread count: torchrun exports OMP_NUM_THREADS=1
     times, steps = [], 0
     out = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        out, _, det, status = pyoracle.propagate_batch(packed.c, prop.opts.to_c(prop.method), st, cs, ep, end, n_threads=cores)
+        out, _, det, status = pyoracle.propagate_batch(packed.c, prop.opts.to_c(prop.method), st, cs, ep, end, n_threads=cores,
+                                                       speed_build=speed_build)
         times.append(time.perf_counter() - t0)
         steps = int(det["n_steps"].sum())
-    return {"steps": steps, "times": times, "cores": cores, "final": out, "inputs": (st, cs, ep)}
+    return {"steps": steps, "times": times, "cores": cores, "host": host, "final": out, "inputs": (st, cs, ep)}
 
 
 def main():
@@ -369,7 +410,7 @@ def main():
     import nyx_b200 as nb
 
     if args.cpu_sample <= 0:
-        args.cpu_sample = 32 * (os.cpu_count() or 8)
+        args.cpu_sample = 32 * host_cores()["usable"]
     if args.workload == "c5":
         if rank != 0:
             return 0
@@ -382,25 +423,25 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        sample_n = args.cpu_sample
-        # calibration / warm-up leg: two trajectories per host thread; it also sizes the sample so that the K timed steps stay
-        # within ~2 minutes whatever K the caller asks for (each step is a bounded sample of the same workload)
-        cores = os.cpu_count() or 8
-        cal = cpu_reference_leg(args, nb, min(sample_n, 2 * cores))
-        rate = cal["steps"] / max(cal["times"][0], 1e-6)                       # trajectory-steps per second, all threads
-        per_traj = cal["steps"] / max(min(sample_n, 2 * cores), 1)
-        fit = int(rate * 120.0 / (max(args.steps, 1) * max(per_traj, 1.0)))
-        sample_n = max(cores, min(sample_n, (fit // cores) * cores if fit >= cores else cores))
+        # FIXED bounded sample: the first REF_SAMPLE trajectories of the same ensemble over the full span, every step; one untimed
+        # warm-up pass (page-in of the library, thread pool).  Both oracle builds are timed: the parity build (-O2, no FMA
+        # contraction: rustc never contracts) is the line's value, the speed build (-O3, AVX2 + FMA) is reported beside it.
+        sample_n = REF_SAMPLE[args.workload]
+        cpu_reference_leg(args, nb, min(sample_n, 64))
         leg = cpu_reference_leg(args, nb, sample_n, repeats=args.steps)
         total_t = sum(leg["times"])
         value = leg["steps"] * args.steps / total_t
+        fast = cpu_reference_leg(args, nb, sample_n, repeats=1, speed_build=True)
         line = {
             "impl": "reference", "metric": "trajectory-steps/sec (ensemble)", "value": value, "unit": "trajectory-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "sample": f"{sample_n} trajectories of the same ensemble, full span"},
-            "cpu_baseline": {"value": value, "unit": "trajectory-steps/s", "cores": leg["cores"], "kind": "port",
-                             "sample": f"{sample_n} trajectories x {args.span_days:g} days per step, OpenMP over trajectories"},
+            "config": {"workload": workload, "sample": f"first {sample_n} trajectories of the same ensemble, full span"},
+            "cpu_baseline": {"value": value, "unit": "trajectory-steps/s", "cores": leg["cores"], "host": leg["host"], "kind": "port",
+                             "build": "-O2 -ffp-contract=off (parity build, the checker)",
+                             "speed_build": {"value": fast["steps"] / fast["times"][0], "build": "-O3 -march=x86-64-v3 -ffp-contract=fast"},
+                             "sample": f"{sample_n} trajectories x {args.span_days:g} days per step, OpenMP schedule(dynamic) over trajectories, "
+                                       f"{leg['cores']} threads"},
             "e2e": {"value": value, "unit": "trajectory-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
         print(json.dumps(line))
@@ -418,7 +459,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     from nyx_b200.dist import all_gather_final_states, shard_bounds
 
-    n_total = args.n_traj * world  # weak scaling: per-GPU work fixed
+    n_total = args.n_traj * world if args.scaling == "weak" else args.n_traj  # weak: per-GPU work fixed; strong: total fixed
     frame, dyn, almanac, st, cs, ep = build_workload(args, n_total, nb)
     lo, hi = shard_bounds(n_total, world, rank)
     n = hi - lo
@@ -510,6 +551,7 @@ def main():
     total_ms, e2e_s, kern_ms = (float(v) for v in t_dev.cpu())
     all_steps, all_rej, all_ok, all_launches = (int(v) for v in cnt.cpu())
 
+    parity_failed = False
     if rank == 0:
         value = all_steps * args.steps / (total_ms * 1e-3)
         e2e_value = all_steps / e2e_s
@@ -522,10 +564,14 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        traffic = None  # dram__bytes_read + dram__bytes_write of one launch of this workload, from the committed ncu capture
+        # dram__bytes_read + dram__bytes_write of ONE launch of this workload by the kernel used here, from the ncu capture committed
+        # with the kernel (profiles/r02_traffic.json, written by scripts/make_traffic_json.py from the same gpurun call as the bench)
+        traffic = None
         try:
-            tj = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
-            if args.workload == "c2" and args.n_traj == 10_000 and args.span_days == 3.0 and args.degree == 21:
+            tj = json.loads((ROOT / "profiles" / "r02_traffic.json").read_text())
+            kname = {nb.KERNEL_THREAD: "nyxb_k_thread", nb.KERNEL_COOP: "nyxb_k_coop", nb.KERNEL_TRANSPOSED: "nyxb_k_tx"}.get(eng.last_kernel())
+            if (args.workload == tj.get("workload") and n == tj.get("n_traj") and args.span_days == tj.get("span_days")
+                    and args.degree == tj.get("degree") and kname and kname in tj.get("kernel", "")):
                 traffic = tj["dram_bytes_per_launch"]
         except Exception:
             pass
@@ -533,7 +579,7 @@ def main():
         line = {
             "metric": "trajectory-steps/sec (ensemble)", "value": value, "unit": "trajectory-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "trajectories_total": n_total, "accepted_steps_per_pass": all_steps,
                        "rejected_attempts_per_pass": all_rej, "ok_trajectories": all_ok, "mode": args.mode,
                        "kernel": {nb.KERNEL_THREAD: "nyxb_k_thread (1 thread = 1 trajectory)", nb.KERNEL_COOP: f"nyxb_k_coop ({eng.lanes()} lanes = 1 trajectory)",
@@ -607,9 +653,18 @@ def main():
             cpu_value = leg["steps"] / leg["times"][0]
             dr = np.sqrt(((out_h[:3, :sample_n] - leg["final"][:3]) ** 2).sum(0))
             dv = np.sqrt(((out_h[3:6, :sample_n] - leg["final"][3:6]) ** 2).sum(0))
-            line["cpu_baseline"] = {"value": cpu_value, "unit": "trajectory-steps/s", "cores": leg["cores"], "kind": "port",
+            fast = cpu_reference_leg(args, nb, min(sample_n, 1024), speed_build=True)
+            line["cpu_baseline"] = {"value": cpu_value, "unit": "trajectory-steps/s", "cores": leg["cores"], "host": leg["host"], "kind": "port",
+                                    "build": "-O2 -ffp-contract=off (parity build, the checker)",
+                                    "speed_build": {"value": fast["steps"] / fast["times"][0], "build": "-O3 -march=x86-64-v3 -ffp-contract=fast",
+                                                    "sample": min(sample_n, 1024)},
                                     "sample": f"first {sample_n} trajectories of the same ensemble, full {args.span_days:g}-day span, "
-                                              f"{leg['times'][0]:.1f} s"}
+                                              f"{leg['times'][0]:.1f} s, {leg['cores']} OpenMP threads"}
+            q = np.percentile(dr, [50, 99])
+            line["parity"] = {"max_dr_km": float(dr.max()), "median_dr_km": float(q[0]), "p99_dr_km": float(q[1]), "max_dv_km_s": float(dv.max()),
+                              "bound_km": PARITY_BOUND_KM, "pass": bool(dr.max() < PARITY_BOUND_KM), "sample": sample_n,
+                              "against": "CPU oracle (parity build), same inputs, full span; the oracle against its own one-ulp-perturbed "
+                                         "error norm moves by up to 7.3e-7 km on this workload (profiles/r02_oracle_sensitivity_c2.json)"}
             line["max_dr_km"] = float(dr.max())
             line["max_dv_km_s"] = float(dv.max())
             line["parity_sample"] = sample_n
@@ -628,9 +683,11 @@ def main():
                                   "lanes_per_trajectory": seng.lanes(),
                                   "note": "NYXB_MODE_STRICT kernel (no FMA, reference operation order) over the full ensemble vs the CPU oracle sample"}
         print(json.dumps(line))
+        if "parity" in line and not line["parity"]["pass"]:
+            parity_failed = True
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return 3 if parity_failed else 0
 
 
 if __name__ == "__main__":

@@ -34,7 +34,8 @@
 extern "C" {
 #endif
 
-#define NYXB_ABI_VERSION 4 /* 4: nyxb_engine_set_kernel / nyxb_engine_last_kernel / nyxb_engine_set_tx_tuning, nyxb_tx_table_dump.  Earlier: 2: nyxb_srp gained `estimate`; STM, filter and dispersion entry points.  3: nyxb_traj_resample[_dev], nyxb_event_locate[_dev] */
+#define NYXB_ABI_VERSION 4 /* 4: nyxb_engine_set_kernel / nyxb_engine_last_kernel / nyxb_engine_set_tx_tuning, nyxb_tx_table_dump, nyxb_propagate_batch_multi, nyxb_reference_normals;
+                              nyxb_integ_opts.state_center, nyxb_gravity_field.body, nyxb_dynamics.n_gravity / n_point_masses / point_mass_order.  Earlier: 2: nyxb_srp gained `estimate`; STM, filter and dispersion entry points.  3: nyxb_traj_resample[_dev], nyxb_event_locate[_dev] */
 
 /* ---- IntegratorMethod — propagators/rk_methods/mod.rs:65-79 (same order) ---- */
 enum nyxb_method {
@@ -256,6 +257,18 @@ int32_t nyxb_propagate_batch_dev(nyxb_engine* eng, size_t n,
                                  nyxb_details* out_details, int32_t* out_status,
                                  void* cuda_stream);
 
+/* Multi-GPU fan-out of one ensemble behind the boundary (mc/montecarlo.rs:233-253: runs are independent, shards are contiguous
+ * run-index ranges, nothing is exchanged while integrating).  `engines[g]`: one engine per device, all created from the same
+ * (dynamics, options, mode); shard g = runs [g n / G, (g+1) n / G).  HOST arrays exactly as nyxb_propagate_batch; every device
+ * integrates concurrently and its results land directly in the caller's [9][n] arrays — for a host caller this is the gather of
+ * final states (device-resident callers launch nyxb_propagate_batch_dev per rank and all-gather, see nyx_b200/dist.py).
+ * `mc.run_until_epoch(prop, almanac, end, num_runs)` on G GPUs is ONE call of this function. */
+int32_t nyxb_propagate_batch_multi(nyxb_engine* const* engines, int32_t n_engines, size_t n,
+                                   const double* state_soa, const double* consts_soa,
+                                   const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
+                                   double* out_state_soa, int64_t* out_epoch_ns,
+                                   nyxb_details* out_details, int32_t* out_status);
+
 /* ---- Trajectory recording (next row (f)-1 of SURVEY.md §8): what `for_duration_with_traj` / `until_epoch_with_traj`
  * (propagators/instance.rs:297-340) collect through the mpsc channel (instance.rs:186-193, 255-259): the start state and
  * the state after every accepted step, final partial step included.  Record s of trajectory i lives at
@@ -472,6 +485,15 @@ int32_t nyxb_mvn_sample(int32_t device, uint64_t seed, uint64_t first_index, siz
 int32_t nyxb_mvn_sample_dev(int32_t device, uint64_t seed, uint64_t first_index, size_t n,
                             const double* template_state, const double* mean, const double* sqrt_s_v,
                             double* out_state_soa, double* out_dispersion_soa, void* cuda_stream);
+
+/* ---- The reference's own dispersion stream (row a2; host code, no device needed): `MonteCarlo::generate_states`
+ * (mc/montecarlo.rs:277-296) = one serial `Pcg64Mcg::new(seed)` (seed: u128 = seed_hi * 2^64 + seed_lo) feeding rand_distr's ziggurat
+ * `StandardNormal`, nine normals per run, the first `skip` runs dropped.  out_z [n][9] row-major: x_i = sqrt_s_v z_i + mean
+ * (multivariate.rs:298-302).  Pcg64Mcg is pinned on the generator's official known-answer vector; the ziggurat tables are regenerated
+ * from the published formulas (see nyx_b200/csrc/nyxb_rng.cu). */
+int32_t nyxb_reference_normals(uint64_t seed_lo, uint64_t seed_hi, uint64_t skip, size_t n, double* out_z);
+int32_t nyxb_pcg64mcg_u64(uint64_t seed_lo, uint64_t seed_hi, size_t n, uint64_t* out);   /* raw generator output (known-answer tests) */
+int32_t nyxb_ziggurat_tables(double* x257, double* f257);                                  /* the layer tables (inspection) */
 
 /* Tuning / introspection. */
 /* Kernel families behind nyxb_propagate_batch*.  AUTO picks by mode, degree and ensemble size:

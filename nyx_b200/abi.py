@@ -269,6 +269,8 @@ def _declare(lib):
     batch_args = [vp, C.c_size_t, vp, vp, vp, C.c_int64, vp, vp, vp, vp, vp]
     lib.nyxb_propagate_batch.restype = C.c_int32
     lib.nyxb_propagate_batch.argtypes = batch_args
+    lib.nyxb_propagate_batch_multi.restype = C.c_int32
+    lib.nyxb_propagate_batch_multi.argtypes = [C.POINTER(vp), C.c_int32] + batch_args[1:]
     lib.nyxb_propagate_batch_dev.restype = C.c_int32
     lib.nyxb_propagate_batch_dev.argtypes = batch_args + [vp]
     lib.nyxb_propagate_batch_traj.restype = C.c_int32
@@ -294,6 +296,12 @@ def _declare(lib):
     lib.nyxb_mvn_sample.argtypes = [C.c_int32, C.c_uint64, C.c_uint64, C.c_size_t, vp, vp, vp, vp, vp]
     lib.nyxb_mvn_sample_dev.restype = C.c_int32
     lib.nyxb_mvn_sample_dev.argtypes = [C.c_int32, C.c_uint64, C.c_uint64, C.c_size_t, vp, vp, vp, vp, vp, vp]
+    lib.nyxb_reference_normals.restype = C.c_int32
+    lib.nyxb_reference_normals.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_size_t, vp]
+    lib.nyxb_pcg64mcg_u64.restype = C.c_int32
+    lib.nyxb_pcg64mcg_u64.argtypes = [C.c_uint64, C.c_uint64, C.c_size_t, vp]
+    lib.nyxb_ziggurat_tables.restype = C.c_int32
+    lib.nyxb_ziggurat_tables.argtypes = [vp, vp]
     lib.nyxb_engine_set_lanes.restype = C.c_int32
     lib.nyxb_engine_set_lanes.argtypes = [vp, C.c_int32]
     lib.nyxb_engine_get_lanes.restype = C.c_int32
@@ -325,6 +333,7 @@ EXPORTED_SYMBOLS = [
     "nyxb_engine_create",
     "nyxb_engine_destroy",
     "nyxb_propagate_batch",
+    "nyxb_propagate_batch_multi",
     "nyxb_propagate_batch_dev",
     "nyxb_propagate_batch_traj",
     "nyxb_propagate_batch_traj_dev",
@@ -337,6 +346,9 @@ EXPORTED_SYMBOLS = [
     "nyxb_od_ekf_batch",
     "nyxb_mvn_sample",
     "nyxb_mvn_sample_dev",
+    "nyxb_reference_normals",
+    "nyxb_pcg64mcg_u64",
+    "nyxb_ziggurat_tables",
     "nyxb_engine_set_lanes",
     "nyxb_engine_get_lanes",
     "nyxb_engine_launch_count",

@@ -663,6 +663,90 @@ extern "C" int32_t nyxb_propagate_batch(nyxb_engine* eng, size_t n, const double
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Multi-GPU fan-out behind the boundary (mc/montecarlo.rs:233-253: contiguous run-index ranges, no exchange while
+// integrating).  engines[g] must have been created from the same (dynamics, options) on DIFFERENT devices (or the same device, for
+// tests); shard g = runs [g n / G, (g+1) n / G).  All uploads and launches are enqueued first, then the results of every shard are
+// copied straight into the caller's [9][n] arrays — for a host caller that IS the gather of final states.
+// ---------------------------------------------------------------------------------------------------------------------
+static int32_t ensure_slab(nyxb_engine* eng, size_t n) {
+    cudaError_t ce;
+#define TRY3(x) do { ce = (x); if (ce != cudaSuccess) { set_err(std::string(#x) + ": " + cudaGetErrorString(ce)); return NYXB_RC_CUDA; } } while (0)
+    if (!eng->stream) TRY3(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+    if (n > eng->cap) {
+        cudaFree(eng->d_f64); cudaFree(eng->d_i64); cudaFree(eng->d_det); cudaFree(eng->d_status);
+        eng->d_f64 = nullptr; eng->d_i64 = nullptr; eng->d_det = nullptr; eng->d_status = nullptr; eng->cap = 0;
+        TRY3(cudaMalloc(&eng->d_f64, sizeof(double) * 22 * n));
+        TRY3(cudaMalloc(&eng->d_i64, sizeof(long long) * 3 * n));
+        TRY3(cudaMalloc(&eng->d_det, sizeof(nyxb_details) * n));
+        TRY3(cudaMalloc(&eng->d_status, sizeof(int) * 2 * n));
+        eng->cap = n;
+    }
+    return NYXB_RC_OK;
+#undef TRY3
+}
+
+extern "C" int32_t nyxb_propagate_batch_multi(nyxb_engine* const* engines, int32_t n_engines, size_t n, const double* state_soa,
+                                              const double* consts_soa, const int64_t* epoch0_ns, int64_t end_epoch_ns, int64_t* step_ns,
+                                              double* out_state_soa, int64_t* out_epoch_ns, nyxb_details* out_details, int32_t* out_status) {
+    if (!engines || n_engines < 1 || !state_soa || !consts_soa || !epoch0_ns || !out_state_soa || !out_epoch_ns || !out_status) {
+        set_err("null argument");
+        return NYXB_RC_BAD_ARG;
+    }
+    for (int32_t g = 0; g < n_engines; ++g)
+        if (!engines[g]) { set_err("null engine"); return NYXB_RC_BAD_ARG; }
+    if (n == 0) return NYXB_RC_OK;
+    const size_t G = (size_t)n_engines;
+    auto lo_of = [&](size_t g) { return g * n / G; };
+    cudaError_t ce;
+#define TRY4(x) do { ce = (x); if (ce != cudaSuccess) { set_err(std::string(#x) + ": " + cudaGetErrorString(ce)); return NYXB_RC_CUDA; } } while (0)
+    // ---- phase 1: uploads + launches on every device (asynchronous: the devices integrate concurrently)
+    for (size_t g = 0; g < G; ++g) {
+        nyxb_engine* eng = engines[g];
+        const size_t lo = lo_of(g), m = lo_of(g + 1) - lo;
+        if (m == 0) continue;
+        TRY4(cudaSetDevice(eng->device));
+        int32_t rc = ensure_slab(eng, m);
+        if (rc != NYXB_RC_OK) return rc;
+        cudaStream_t st = eng->stream;
+        // strided rows of the caller's [rows][n] arrays -> dense [rows][m] shards
+        TRY4(cudaMemcpy2DAsync(eng->d_f64, m * 8, state_soa + lo, n * 8, m * 8, 9, cudaMemcpyHostToDevice, st));
+        TRY4(cudaMemcpy2DAsync(eng->d_f64 + 9 * m, m * 8, consts_soa + lo, n * 8, m * 8, 4, cudaMemcpyHostToDevice, st));
+        TRY4(cudaMemcpyAsync(eng->d_i64, epoch0_ns + lo, m * 8, cudaMemcpyHostToDevice, st));
+        if (step_ns) TRY4(cudaMemcpyAsync(eng->d_i64 + 2 * m, step_ns + lo, m * 8, cudaMemcpyHostToDevice, st));
+        eng->rec_n = 0; eng->rec_cap = 0;
+        TRY4(cudaEventRecord(eng->ev0, st));
+        rc = launch(eng, m, eng->d_f64, eng->d_f64 + 9 * m, (const int64_t*)eng->d_i64, end_epoch_ns,
+                    step_ns ? (int64_t*)(eng->d_i64 + 2 * m) : nullptr, eng->d_f64 + 13 * m, (int64_t*)(eng->d_i64 + m), eng->d_det,
+                    eng->d_status, DevSink{}, st);
+        if (rc != NYXB_RC_OK) return rc;
+        TRY4(cudaEventRecord(eng->ev1, st));
+    }
+    // ---- phase 2: every shard's results straight into the caller's arrays (the gather), then one synchronisation per device
+    for (size_t g = 0; g < G; ++g) {
+        nyxb_engine* eng = engines[g];
+        const size_t lo = lo_of(g), m = lo_of(g + 1) - lo;
+        if (m == 0) continue;
+        TRY4(cudaSetDevice(eng->device));
+        cudaStream_t st = eng->stream;
+        TRY4(cudaMemcpy2DAsync(out_state_soa + lo, n * 8, eng->d_f64 + 13 * m, m * 8, m * 8, 9, cudaMemcpyDeviceToHost, st));
+        TRY4(cudaMemcpyAsync(out_epoch_ns + lo, eng->d_i64 + m, m * 8, cudaMemcpyDeviceToHost, st));
+        if (step_ns) TRY4(cudaMemcpyAsync(step_ns + lo, eng->d_i64 + 2 * m, m * 8, cudaMemcpyDeviceToHost, st));
+        if (out_details) TRY4(cudaMemcpyAsync(out_details + lo, eng->d_det, sizeof(nyxb_details) * m, cudaMemcpyDeviceToHost, st));
+        TRY4(cudaMemcpyAsync(out_status + lo, eng->d_status, sizeof(int) * m, cudaMemcpyDeviceToHost, st));
+    }
+    for (size_t g = 0; g < G; ++g) {
+        nyxb_engine* eng = engines[g];
+        if (lo_of(g + 1) == lo_of(g)) continue;
+        TRY4(cudaSetDevice(eng->device));
+        TRY4(cudaStreamSynchronize(eng->stream));
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, eng->ev0, eng->ev1) == cudaSuccess) eng->last_ms = ms;
+    }
+    return NYXB_RC_OK;
+#undef TRY4
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // (f)-2: STM propagation and the batched sequential filter (kernels in nyxb_od.cu).  Host-pointer entry points with
 // per-call device buffers (these calls run for seconds; allocation cost is irrelevant).
 // ---------------------------------------------------------------------------------------------------------------------

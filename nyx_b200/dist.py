@@ -20,6 +20,31 @@ def shard_bounds(n: int, world_size: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def propagate_batch_multi(engines, state_soa, consts_soa, epoch0_ns, end_epoch_ns, step_ns=None):
+    """ONE ensemble over several GPUs of this process through the C ABI (`nyxb_propagate_batch_multi`): `engines` = one
+    `nyx_b200.Engine` per device, all built from the same propagator; contiguous run-index shards, every device integrates
+    concurrently, results land directly in the returned host arrays.  Same return value as `Engine.propagate_batch`."""
+    import ctypes as C
+
+    from . import abi
+    from .propagator import PropagationError
+
+    lib = abi.load_library()
+    state_soa = np.ascontiguousarray(state_soa, dtype=np.float64)
+    consts_soa = np.ascontiguousarray(consts_soa, dtype=np.float64)
+    epoch0_ns = np.ascontiguousarray(epoch0_ns, dtype=np.int64)
+    n = state_soa.shape[1]
+    out = np.empty((9, n)); out_ep = np.empty(n, dtype=np.int64)
+    det = np.zeros(n, dtype=abi.DETAILS_DTYPE); status = np.zeros(n, dtype=np.int32)
+    handles = (C.c_void_p * len(engines))(*[e.handle for e in engines])
+    rc = lib.nyxb_propagate_batch_multi(handles, len(engines), n, state_soa.ctypes.data, consts_soa.ctypes.data, epoch0_ns.ctypes.data,
+                                        int(end_epoch_ns), step_ns.ctypes.data if step_ns is not None else None, out.ctypes.data,
+                                        out_ep.ctypes.data, det.ctypes.data, status.ctypes.data)
+    if rc != 0:
+        raise PropagationError(f"nyxb_propagate_batch_multi failed ({rc}): {abi.last_error()}")
+    return out, out_ep, det, status
+
+
 def shard_soa(arr: np.ndarray, world_size: int, rank: int) -> np.ndarray:
     lo, hi = shard_bounds(arr.shape[-1], world_size, rank)
     return np.ascontiguousarray(arr[..., lo:hi])

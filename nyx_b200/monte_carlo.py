@@ -11,7 +11,7 @@ reference's own MC tests assert no numbers).
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import List, Optional, Tuple
+from typing import Sequence, List, Optional, Tuple
 
 import numpy as np
 
@@ -147,6 +147,19 @@ class MvnSpacecraft:
     def sample_vectors(self, rng: np.random.Generator, num: int) -> np.ndarray:
         """[num, 9] perturbation vectors (one row per run, draw order = run index)."""
         z = rng.standard_normal((num, 9))
+        return z @ self.sqrt_s_v.T + self.mean[None, :]
+
+    def sample_vectors_reference(self, seed: int, num: int, skip: int = 0) -> np.ndarray:
+        """[num, 9] perturbation vectors from the REFERENCE's stream: one serial `Pcg64Mcg::new(seed)` through rand_distr's ziggurat
+        `StandardNormal`, nine normals per run in component order (mc/montecarlo.rs:277-296, multivariate.rs:298-302;
+        `nyxb_reference_normals`, host code of libnyxb.so).  The same z_i as nyx draws for that seed; x_i = sqrt_s_v z_i + mean then
+        equals nyx's whenever the two SVDs agree on the sign and order of the singular vectors."""
+        lib = abi.load_library()
+        z = np.empty((num, 9))
+        seed = int(seed) & ((1 << 128) - 1)
+        rc = lib.nyxb_reference_normals(seed & 0xFFFFFFFFFFFFFFFF, seed >> 64, int(skip), num, z.ctypes.data)
+        if rc != 0:
+            raise PropagationError(f"nyxb_reference_normals rc={rc}")
         return z @ self.sqrt_s_v.T + self.mean[None, :]
 
     def sample_on_device(self, seed: int, num: int, first_index: int = 0, device: int = 0):
@@ -404,15 +417,24 @@ class MonteCarlo:
         self.random_state = random_variable
         self.scenario = scenario
         self.seed = seed
+        self.stream = "numpy"   # or "reference": see generate_states
 
     @classmethod
     def new(cls, nominal_state, random_variable, scenario, seed=None) -> "MonteCarlo":
         return cls(nominal_state, random_variable, scenario, seed)
 
-    def generate_states(self, skip: int, num_runs: int, seed: Optional[int] = None) -> List[Tuple[int, DispersedState]]:
-        """mc/montecarlo.rs:277-296: one serial stream; `skip` discards the first draws."""
-        rng = np.random.Generator(np.random.PCG64(self.seed if seed is None else seed))
-        x = self.random_state.sample_vectors(rng, skip + num_runs)[skip:]
+    def generate_states(self, skip: int, num_runs: int, seed: Optional[int] = None, stream: Optional[str] = None) -> List[Tuple[int, DispersedState]]:
+        """mc/montecarlo.rs:277-296: one serial stream; `skip` discards the first draws.  `stream` (default: `self.stream`):
+        "numpy" = numpy's PCG64 + its normal sampler (vectorised; what the benchmarks and tests of this repo feed to CPU oracle and
+        GPU alike), "reference" = the reference's own Pcg64Mcg + ziggurat stream (`sample_vectors_reference`)."""
+        sd = self.seed if seed is None else seed
+        if (stream or self.stream) == "reference":
+            if sd is None:
+                raise MonteCarloError("the reference stream needs a seed (the reference draws one from the OS otherwise)")
+            x = self.random_state.sample_vectors_reference(sd, num_runs, skip)
+        else:
+            rng = np.random.Generator(np.random.PCG64(sd))
+            x = self.random_state.sample_vectors(rng, skip + num_runs)[skip:]
         return [(i, self.random_state.apply(x[i])) for i in range(num_runs)]
 
     def generate_states_on_device(self, skip: int, num_runs: int, seed: Optional[int] = None, device: int = 0):
@@ -422,9 +444,28 @@ class MonteCarlo:
         return st, disp
 
     def run_until_epoch(self, prop: Propagator, almanac: Optional[Almanac], end_epoch_ns: int, num_runs: int,
-                        device_dispersions: bool = False, traj_capacity: int = 0) -> Results:
+                        device_dispersions: bool = False, traj_capacity: int = 0, devices: Optional[Sequence[int]] = None) -> Results:
         """mc/montecarlo.rs:188-203.  `traj_capacity` > 0 also records every accepted step of every run (what the reference
-        always keeps in `PropResult.traj`, results.rs:74-81) for the report accessors of `Results`."""
+        always keeps in `PropResult.traj`, results.rs:74-81) for the report accessors of `Results`.  `devices` = CUDA ordinals:
+        the ensemble is sharded over them inside ONE C-ABI call (`nyxb_propagate_batch_multi`; final states only)."""
+        if devices is not None and len(devices) > 1:
+            if device_dispersions or traj_capacity:
+                raise MonteCarloError("multi-device runs return final states only")
+            from .dist import propagate_batch_multi
+
+            init_states = self.generate_states(0, num_runs, self.seed)
+            st, cs, ep = pack_spacecraft(ds.state for _, ds in init_states)
+            engs = prop.engines(self.nominal_state.orbit.frame, almanac, devices)
+            try:
+                out, out_ep, det, status = propagate_batch_multi(engs, st, cs, ep, end_epoch_ns)
+            finally:
+                for e in engs:
+                    e.close()
+            runs = []
+            for (idx, ds) in init_states:
+                err = status_error(status[idx])
+                runs.append(Run(idx, ds, err if err is not None else ds.state.with_vector(int(out_ep[idx]), out[:, idx])))
+            return Results(runs, self.scenario, out, det, status, None, None)
         if device_dispersions:
             return self._run_device_dispersions(prop, almanac, 0, end_epoch_ns, num_runs, traj_capacity)
         return self.resume_run_until_epoch(prop, almanac, 0, end_epoch_ns, num_runs, traj_capacity)

@@ -451,6 +451,11 @@ class Propagator:
         self._engines[key] = (eng, almanac, self.dynamics)
         return eng
 
+    def engines(self, frame: Frame, almanac: Optional[Almanac], devices: Sequence[int]) -> List[Engine]:
+        """One engine per CUDA device for `nyx_b200.dist.propagate_batch_multi` (a fresh, uncached engine per device)."""
+        packed, opts_c = self.lower(frame, almanac)
+        return [Engine(packed, opts_c, self.mode, int(d)) for d in devices]
+
     def lower(self, frame: Frame, almanac: Optional[Almanac]):
         """(nyxb_dynamics, nyxb_integ_opts) for states expressed in `frame`.  With `opts.integration_frame` set to another frame
         the dynamics are lowered for THAT frame (its own mu / shape when given, instance.rs:131-137) and `state_center` tells the

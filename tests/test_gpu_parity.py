@@ -317,3 +317,29 @@ def test_monte_carlo_api_and_resume(oracle):
     assert np.array_equal(full.final_state_soa[:, 40:], tail.final_state_soa)
     assert all(isinstance(r.result, nb.Spacecraft) for r in full.runs)
     assert full.total_steps() == int(full.details["n_steps"].sum()) > 48 * 20
+
+
+def test_multi_device_call_shards_and_gathers(oracle):
+    """`nyxb_propagate_batch_multi`: one ensemble over several engines (one per GPU; two engines on device 0 when the box has a
+    single GPU — the sharding, strided uploads and the gather into the caller's [9][n] arrays are the same code)."""
+    import torch
+    from nyx_b200.dist import propagate_batch_multi
+
+    n = 777   # not a multiple of anything
+    mc, (st, cs, ep) = leo_ensemble(n, seed=31)
+    gd = nb.GravityFieldData.from_fixture("jgm3_70x70", 12, 12, nb.IAU_EARTH_FRAME)
+    dyn = nb.SpacecraftDynamics.new(nb.OrbitalDynamics.from_model(nb.GravityField.new(gd)))
+    prop = nb.Propagator.default(dyn, mode=nb.MODE_STRICT)
+    ndev = torch.cuda.device_count()
+    for devices in ([0, 0, 0], list(range(ndev)) if ndev > 1 else [0, 0]):
+        engs = prop.engines(nb.EARTH_J2000, None, devices)
+        step = np.full(n, 60 * S, dtype=np.int64)
+        out, oep, det, status = propagate_batch_multi(engs, st, cs, ep, 2 * 3600 * S, step_ns=step)
+        one = prop.engine(nb.EARTH_J2000, None).propagate_batch(st, cs, ep, 2 * 3600 * S, step_ns=np.full(n, 60 * S, dtype=np.int64))
+        assert np.array_equal(out, one[0]) and np.array_equal(oep, one[1]) and np.array_equal(status, one[3])
+        assert np.array_equal(det["n_steps"], one[2]["n_steps"])
+        for e in engs:
+            e.close()
+    res = nb.MonteCarlo(mc.nominal_state, mc.random_state, "multi", seed=31).run_until_epoch(prop, None, 3600 * S, 100, devices=[0, 0])
+    ref = nb.MonteCarlo(mc.nominal_state, mc.random_state, "multi", seed=31).run_until_epoch(prop, None, 3600 * S, 100)
+    assert all(np.array_equal(a.result.orbit.to_cartesian_pos_vel(), b.result.orbit.to_cartesian_pos_vel()) for a, b in zip(res.runs, ref.runs))
