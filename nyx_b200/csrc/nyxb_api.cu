@@ -433,8 +433,8 @@ static int32_t launch_tx(nyxb_engine* e, size_t n, const double* state, const do
     ctas = std::min(ctas, (n_sets + occ - 1) / occ);
     const size_t slots = ctas * occ;
     const int grid = (int)ctas;
-    // workspace: [ticket u64 | n_finished i32 (+pad) | slices_done n_sets | finished n_sets | ws_step n i64 | ws_f64 2n | ws_flags n | details n]
-    const size_t ctl_bytes = (16 + 8 * n_sets + 15) & ~(size_t)15;
+    // workspace: [ctl 4 x i32 | ring n_sets x i32 | ws_step n i64 | ws_f64 2n | ws_flags n | details n]
+    const size_t ctl_bytes = (16 + 4 * n_sets + 15) & ~(size_t)15;
     const size_t need = ctl_bytes + n * (8 + 16 + 8) + n * sizeof(nyxb_details);
     if (need > e->txq_bytes) {
         cudaFree(e->d_txq); e->d_txq = nullptr; e->txq_bytes = 0;
@@ -443,10 +443,8 @@ static int32_t launch_tx(nyxb_engine* e, size_t n, const double* state, const do
     }
     CUDA_TRY(cudaMemsetAsync(e->d_txq, 0, ctl_bytes, stream));
     DevTxQueue q;
-    q.ticket = reinterpret_cast<unsigned long long*>(e->d_txq);
-    q.n_finished = reinterpret_cast<int*>(e->d_txq + 8);
-    q.slices_done = reinterpret_cast<int*>(e->d_txq + 16);
-    q.finished = q.slices_done + n_sets;
+    q.ctl = reinterpret_cast<int*>(e->d_txq);
+    q.ring = q.ctl + 4;
     unsigned char* ws = e->d_txq + ctl_bytes;
     q.ws_step = reinterpret_cast<long long*>(ws);
     q.ws_f64 = reinterpret_cast<double*>(ws + 8 * n);

@@ -421,7 +421,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
     static_assert(P <= NYXB_TX_MAXP && NCTX >= 1 && NCTX <= 2, "walker positions / set contexts");
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long tma_bar;
-    __shared__ int s_set[NCTX], s_round[NCTX], s_skip[NCTX], s_exit[NCTX], s_all_done[NCTX], s_slice_end[NCTX];
+    __shared__ int s_set[NCTX], s_fresh[NCTX], s_exit[NCTX], s_all_done[NCTX], s_slice_end[NCTX];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     constexpr int NT_RW = (P + 3) * 32;   // threads on a READY / DONE barrier: the walkers + the three helpers of the context
     constexpr int BAR_HB = 1, BAR_READY = 1 + NCTX, BAR_DONE = 1 + 2 * NCTX;
@@ -488,31 +488,35 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
     const bool lead = (j == 0);   // helper 0 also runs the controller and the ticket queue of its context
 
     for (;;) {
-        // ---------------------------------------------------------------- acquire a (set, slice) ticket
+        // ---------------------------------------------------------------- acquire a set: a fresh one, else a parked one
         if (lead && lane == 0) {
-            const int fin_all = atomicAdd(q.n_finished, 0);
-            if (fin_all >= q.n_sets) {
-                s_exit[c] = 1;
-            } else {
-                const unsigned long long t = atomicAdd(q.ticket, 1ULL);
-                const int set = (int)(t % (unsigned long long)q.n_sets), round = (int)(t / (unsigned long long)q.n_sets);
-                while (atomicAdd(q.slices_done + set, 0) < round) __nanosleep(256);   // the previous slice of this set is parked
-                __threadfence();
-                s_set[c] = set; s_round[c] = round;
-                s_skip[c] = atomicAdd(q.finished + set, 0);
+            int set = -1, fresh = 0;
+            if (atomicAdd(q.ctl + TXQ_FRESH, 0) < q.n_sets) {
+                const int f = atomicAdd(q.ctl + TXQ_FRESH, 1);
+                if (f < q.n_sets) { set = f; fresh = 1; }
             }
+            if (set < 0 && q.slice > 0) {
+                while (atomicCAS(q.ctl + TXQ_LOCK, 0, 1) != 0) __nanosleep(64);
+                __threadfence();
+                volatile int* vc = q.ctl;
+                const int head = vc[TXQ_HEAD], tail = vc[TXQ_TAIL];
+                if (head < tail) {
+                    set = ((volatile int*)q.ring)[head % q.n_sets];
+                    vc[TXQ_HEAD] = head + 1;
+                }
+                __threadfence();
+                atomicExch(q.ctl + TXQ_LOCK, 0);
+            }
+            s_set[c] = set; s_fresh[c] = fresh;
+            s_exit[c] = set < 0;   // nothing fresh, nothing parked: every unfinished set is in progress in another context
         }
         nb_sync(BAR_HB + c, 96);
         if (s_exit[c]) {
             nb_arrive(BAR_READY + c, NT_RW);   // releases the walkers, which read s_exit and drop this context
             return;
         }
-        const int set = s_set[c], round = s_round[c];
-        if (s_skip[c]) {
-            nb_sync(BAR_HB + c, 96);
-            if (lead && lane == 0) atomicExch(q.slices_done + set, round + 1);
-            continue;
-        }
+        const int set = s_set[c];
+        const int round = s_fresh[c] ? 0 : 1;   // 0: initial state from the inputs; otherwise from the parking area
         const size_t traj_raw = (size_t)set * NL + lane;
         const bool valid = traj_raw < n;
         const size_t tr = valid ? traj_raw : (size_t)set * NL;   // an absent lane shadows the set's first trajectory, never committed
@@ -717,13 +721,15 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
         if (lead) tx_park_ctl(sink, q, sm, lane, n, tr, step_io, out_state, out_epoch, out_status);
         __threadfence();
         nb_sync(BAR_HB + c, 96);
-        if (lead && lane == 0) {
-            if (s_all_done[c]) {
-                atomicExch(q.finished + set, 1);
-                atomicAdd(q.n_finished, 1);
-            }
+        if (lead && lane == 0 && !s_all_done[c]) {   // park: the set becomes resumable by any context
+            while (atomicCAS(q.ctl + TXQ_LOCK, 0, 1) != 0) __nanosleep(64);
             __threadfence();
-            atomicExch(q.slices_done + set, round + 1);
+            volatile int* vc = q.ctl;
+            const int tail = vc[TXQ_TAIL];
+            ((volatile int*)q.ring)[tail % q.n_sets] = set;
+            vc[TXQ_TAIL] = tail + 1;
+            __threadfence();
+            atomicExch(q.ctl + TXQ_LOCK, 0);
         }
         nb_sync(BAR_HB + c, 96);   // s_* of this context are rewritten by its lead lane only after this barrier
     }

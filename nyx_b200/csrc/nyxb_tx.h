@@ -38,18 +38,21 @@ void nyxb_tx_build_host(int N, int M, const double* c_nm, const double* s_nm, in
 // packs the tables into the blob the kernel expects; returns its size (dst == NULL: size only)
 size_t nyxb_tx_pack_blob(const TxHost* h, int N, unsigned char* dst);
 
-// work queue + parking area of the persistent kernel (device pointers, owned by the engine)
+// work queue + parking area of the persistent kernel (device pointers, owned by the engine; `ctl` and `ring` zeroed before a launch).
+// Fresh sets are handed out by a counter; a set parked at the end of a time slice is pushed on a ring of resumable sets and popped
+// by whichever context asks next (spin lock around the two ring indices: one push + one pop per context and slice).  A context
+// that finds neither a fresh nor a parked set exits: every unfinished set is then in progress in some other context, which will
+// pop it again itself after parking it — nothing ever waits for another context's slice to end.
 struct DevTxQueue {
-    unsigned long long* ticket;   // [1]
-    int* n_finished;              // [1]
-    int* slices_done;             // [n_sets]
-    int* finished;                // [n_sets]
+    int* ctl;                     // [4]: next fresh set, lock, ring head, ring tail
+    int* ring;                    // [n_sets] parked sets
     long long* ws_step;           // [n]   adapted step of a parked trajectory
     double* ws_f64;               // [2][n] raw retry step h, previous event value
     int* ws_flags;                // [n]   fixed | retry << 1 | done << 2 | warn << 3 | rc << 8
     nyxb_details* details;        // [n]   never NULL inside the kernel (user buffer or engine scratch)
     int n_sets, slice;            // slice: step attempts per slice (0: run every set to completion)
 };
+enum { TXQ_FRESH = 0, TXQ_LOCK = 1, TXQ_HEAD = 2, TXQ_TAIL = 3 };
 
 extern "C" cudaError_t nyxb_launch_tx(const DevSetup* S, const DevTx* Tx, const DevTxQueue* q, size_t n, const double* state,
                                       const double* consts, const long long* epoch0, long long end_epoch, long long* step_io,
