@@ -99,6 +99,7 @@ struct RotBase { double sa, ca, sd, cd, sw, cw; };
 // third bodies + SRP + drag: a few hundred flops, evaluated redundantly by every lane, kept out of line so that
 // the ephemeris scratch does not inflate the register count of the harmonic sum
 // (scalars, not the TrajCtx, are passed: taking the struct's address would force it into local memory)
+template <bool GEN>
 static __device__ __noinline__ int coop_extra(const DevSetup& S, double dry_mass, double extra_mass, double srp_area, double drag_area,
                                               long long t_ns, const double y[9], double acc[3]) {
     double mass = dry_mass + y[8] + extra_mass;
@@ -107,13 +108,20 @@ static __device__ __noinline__ int coop_extra(const DevSetup& S, double dry_mass
     double bpos[NYXB_MAX_BODIES][3];
     int rc = accel_point_masses(S, t_ns, y, bpos, acc);
     if (rc) return rc;
-    accel_extra_fields(S, t_ns, y, bpos, acc);
+    if (GEN && S.n_xgrav > 0) accel_extra_fields(S, t_ns, y, bpos, acc);
     if (has_force) accel_post(S, t_ns, y, bpos, mass, srp_area, drag_area, acc);
     return 0;
 }
 
+// position relative to the body the primary field belongs to (gravity_field.rs:149-154); kept out of line: the Clenshaw scratch must
+// not inflate the register count of the harmonic sum.  An epoch outside the ephemeris is reported by coop_extra (every body).
+static __device__ __noinline__ void coop_field_offset(const DevSetup& S, long long t_ns, double& y0, double& y1, double& y2) {
+    double bp[3];
+    if (body_position(S.bodies[S.grav_body], t_ns, bp)) { y0 -= bp[0]; y1 -= bp[1]; y2 -= bp[2]; }
+}
+
 // Cooperative SpacecraftDynamics::eom for the T stage states held in g[t].ys; lane c < 6 receives dy[c] of each.
-template <int G, int T>
+template <int G, int T, bool NC>   // NC ("general fields"): the primary field may belong to another body, further fields may exist
 __device__ __forceinline__ void coop_rhs(const DevSetup& S, const double* __restrict__ recs, int L,
                                          const double* __restrict__ colseed, unsigned a_cs, unsigned cm_off,
                                          TrajCtx (&g)[T], const RotBase (&rbase)[T], const double (&dt_s)[T],
@@ -150,10 +158,7 @@ __device__ __forceinline__ void coop_rhs(const DevSetup& S, const double* __rest
             R[6] = cd * ca; R[7] = cd * sa; R[8] = sd;
         }
         double y0 = g[t].ys[0], y1 = g[t].ys[1], y2 = g[t].ys[2];
-        if (S.grav_body >= 0) {   // field of another body: the state is translated to it first (gravity_field.rs:149-154)
-            double bp[3];
-            if (body_position(S.bodies[S.grav_body], t_ns[t], bp)) { y0 -= bp[0]; y1 -= bp[1]; y2 -= bp[2]; }   // out of coverage: reported by coop_extra
-        }
+        if (NC && S.grav_body >= 0) coop_field_offset(S, t_ns[t], y0, y1, y2);   // field of another body: the state is translated to it first
         const double rb0 = fma(R[2], y2, fma(R[1], y1, R[0] * y0));
         const double rb1 = fma(R[5], y2, fma(R[4], y1, R[3] * y0));
         const double rb2 = fma(R[8], y2, fma(R[7], y1, R[6] * y0));
@@ -304,34 +309,38 @@ __device__ __forceinline__ void coop_rhs(const DevSetup& S, const double* __rest
         double R[9];
 #pragma unroll
         for (int q = 0; q < 9; ++q) R[q] = g[t].nxt[q];
-        double q0 = y[0], q1 = y[1], q2 = y[2];   // position relative to the field's body
-        if (S.grav_body >= 0) {
-            double bp[3];
-            if (body_position(S.bodies[S.grav_body], t_ns[t], bp)) { q0 -= bp[0]; q1 -= bp[1]; q2 -= bp[2]; }
+        double s_, t_, u_;
+        if (NC) {
+            double q0 = y[0], q1 = y[1], q2 = y[2];   // position relative to the field's body
+            if (S.grav_body >= 0) coop_field_offset(S, t_ns[t], q0, q1, q2);
+            s_ = fma(R[2], q2, fma(R[1], q1, R[0] * q0)) * inv_r[t];
+            t_ = fma(R[5], q2, fma(R[4], q1, R[3] * q0)) * inv_r[t];
+            u_ = fma(R[8], q2, fma(R[7], q1, R[6] * q0)) * inv_r[t];
+        } else {
+            s_ = fma(R[2], y[2], fma(R[1], y[1], R[0] * y[0])) * inv_r[t];
+            t_ = fma(R[5], y[2], fma(R[4], y[1], R[3] * y[0])) * inv_r[t];
+            u_ = fma(R[8], y[2], fma(R[7], y[1], R[6] * y[0])) * inv_r[t];
         }
-        const double s_ = fma(R[2], q2, fma(R[1], q1, R[0] * q0)) * inv_r[t];
-        const double t_ = fma(R[5], q2, fma(R[4], q1, R[3] * q0)) * inv_r[t];
-        const double u_ = fma(R[8], q2, fma(R[7], q1, R[6] * q0)) * inv_r[t];
         // rr_n A[n][m] = K0 rho (rho^n A),  rr_{n-1} A[n][m] = K0 (rho^n A),  K0 = mu / (r R_eq)
         const double K0 = (gv.mu * gv.inv_r_eq) * inv_r[t];
         const double K1 = K0 * rho[t];
         const double aw = -K0 * W[t];
         const double ab0 = fma(aw, s_, K1 * X[t]), ab1 = fma(aw, t_, K1 * Y[t]), ab2 = fma(aw, u_, K1 * Z[t]);
         // two-body (orbital.rs:86-92): from the same 1/r when the field belongs to the centre
-        const double ir_c = (S.grav_body >= 0) ? rsqrt(fma(y[2], y[2], fma(y[1], y[1], y[0] * y[0]))) : inv_r[t];
+        const double ir_c = (NC && S.grav_body >= 0) ? rsqrt(fma(y[2], y[2], fma(y[1], y[1], y[0] * y[0]))) : inv_r[t];
         const double fac = -S.mu_central * ir_c * ir_c * ir_c;
         double acc[3];
         acc[0] = fma(fac, y[0], fma(R[6], ab2, fma(R[3], ab1, R[0] * ab0)));
         acc[1] = fma(fac, y[1], fma(R[7], ab2, fma(R[4], ab1, R[1] * ab0)));
         acc[2] = fma(fac, y[2], fma(R[8], ab2, fma(R[5], ab1, R[2] * ab0)));
         rc[t] = 0;
-        if (S.n_bodies > 0 || S.has_srp || S.has_drag || S.n_xgrav > 0) {
+        if (S.n_bodies > 0 || S.has_srp || S.has_drag || (NC && S.n_xgrav > 0)) {
             // cold path: private copies, so that y/acc of the common path are never address-taken (they stay in registers)
             double yy[9], aa[3];
 #pragma unroll
             for (int e = 0; e < 9; ++e) yy[e] = y[e];
             aa[0] = acc[0]; aa[1] = acc[1]; aa[2] = acc[2];
-            rc[t] = coop_extra(S, g[t].dry_mass, g[t].extra_mass, g[t].srp_area, g[t].drag_area, t_ns[t], yy, aa);
+            rc[t] = coop_extra<NC>(S, g[t].dry_mass, g[t].extra_mass, g[t].srp_area, g[t].drag_area, t_ns[t], yy, aa);
             acc[0] = aa[0]; acc[1] = aa[1]; acc[2] = aa[2];
         }
         // lane c < 3 keeps the velocity component c, lanes 3..5 the acceleration components (selects, no jump table)
@@ -342,7 +351,7 @@ __device__ __forceinline__ void coop_rhs(const DevSetup& S, const double* __rest
     }
 }
 
-template <int G, int T, bool SMEM_TABLE>
+template <int G, int T, bool SMEM_TABLE, bool NC = false>
 #ifndef COOP_MINB1
 #define COOP_MINB1 5
 #endif
@@ -524,7 +533,7 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
                 t_ns[t] = epoch[t] + off_ns;
             }
             __syncwarp(FULL);
-            coop_rhs<G, T>(S, recs, Cp.L, sm_seed, a_cs, cm_off, g, rbase, dt_s, t_ns, lane,
+            coop_rhs<G, T, NC>(S, recs, Cp.L, sm_seed, a_cs, cm_off, g, rbase, dt_s, t_ns, lane,
                            (unsigned)(tstride * 8), dyc, rcs);
 #pragma unroll
             for (int t = 0; t < T; ++t) {
@@ -655,17 +664,17 @@ nyxb_k_coop(const __grid_constant__ DevSetup S, const __grid_constant__ DevCoop 
     }
 }
 
-template <int G, int T, bool TAB>
+template <int G, int T, bool TAB, bool NC>
 static cudaError_t launch_gt(const DevSetup* S, const DevCoop* Cp, size_t n, size_t smem, const double* state,
                              const double* consts, const long long* epoch0, long long end_epoch, long long* step_io,
                              double* out_state, long long* out_epoch, nyxb_details* out_details, int* out_status,
                              const DevSink* sink, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(nyxb_k_coop<G, T, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(nyxb_k_coop<G, T, TAB, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 0, occ = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nyxb_k_coop<G, T, TAB>, COOP_CTA, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nyxb_k_coop<G, T, TAB, NC>, COOP_CTA, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
     const size_t groups = COOP_CTA / G;
@@ -674,7 +683,7 @@ static cudaError_t launch_gt(const DevSetup* S, const DevCoop* Cp, size_t n, siz
     size_t grid = (n_sets + groups - 1) / groups;
     const size_t wave = (size_t)sms * occ;
     if (grid <= wave) grid = ((grid + sms - 1) / sms) * sms;  // one resident wave, same CTA count on every SM
-    nyxb_k_coop<G, T, TAB><<<(unsigned)grid, COOP_CTA, smem, stream>>>(*S, *Cp, n, state, consts, epoch0, end_epoch, step_io,
+    nyxb_k_coop<G, T, TAB, NC><<<(unsigned)grid, COOP_CTA, smem, stream>>>(*S, *Cp, n, state, consts, epoch0, end_epoch, step_io,
                                                                        out_state, out_epoch, out_details, out_status, *sink);
     return cudaGetLastError();
 }
@@ -691,7 +700,7 @@ cudaError_t nyxb_launch_coop_g(const DevSetup* S, const DevCoop* Cp, int T, size
     const bool tab = with_table * 2 <= 227 * 1024;
     const size_t smem = tab ? with_table : grp_bytes;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-#define NYXB_COOP_GO(TT, TAB) launch_gt<G, TT, TAB>(S, Cp, n, smem, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, sink, stream)
+#define NYXB_COOP_GO(TT, TAB) ((S->grav_body >= 0 || S->n_xgrav > 0) ? launch_gt<G, TT, TAB, true>(S, Cp, n, smem, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, sink, stream) : launch_gt<G, TT, TAB, false>(S, Cp, n, smem, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_details, out_status, sink, stream))
     if (T != 1) return cudaErrorInvalidValue;   // T = 2 (register blocking over two trajectories) lost at every size and is not instantiated
     return tab ? NYXB_COOP_GO(1, true) : NYXB_COOP_GO(1, false);
 #undef NYXB_COOP_GO

@@ -721,8 +721,9 @@ __device__ __forceinline__ void grav_rel(int body, const double y[9], const doub
 
 // harmonic fields beyond the primary one (OrbitalDynamics holds a Vec of accel models, orbital.rs:44-46, 102-107), summed per
 // trajectory in list order
-__device__ inline void accel_extra_fields(const DevSetup& S, long long t_ns, const double y[9],
-                                          const double bpos[NYXB_MAX_BODIES][3], double acc[3]) {
+// (out of line: the per-thread harmonic evaluation carries a large register / stack footprint that must not leak into its callers)
+__device__ __noinline__ void accel_extra_fields(const DevSetup& S, long long t_ns, const double y[9],
+                                                const double bpos[NYXB_MAX_BODIES][3], double acc[3]) {
     for (int f = 0; f < S.n_xgrav; ++f) {
         double rel[3], ga[3];
         grav_rel(S.xgrav_body[f], y, bpos, rel);
@@ -758,7 +759,7 @@ __device__ inline int eom_full(const DevSetup& S, long long epoch_ns, double del
         grav_accel_cols(S.grav, t_ns, rel, ga);
 #endif
         acc[0] += ga[0]; acc[1] += ga[1]; acc[2] += ga[2];
-        accel_extra_fields(S, t_ns, y, bpos, acc);
+        if (S.n_xgrav > 0) accel_extra_fields(S, t_ns, y, bpos, acc);
     }
     if (has_force) accel_post(S, t_ns, y, bpos, mass, srp_area, drag_area, acc);
     dy[0] = y[3]; dy[1] = y[4]; dy[2] = y[5];

@@ -130,7 +130,7 @@ __device__ __noinline__ int tx_extra(const DevSetup& S, double dry_mass, double 
     double bpos[NYXB_MAX_BODIES][3];
     const int rc = accel_point_masses(S, t_ns, y, bpos, acc);
     if (rc) return rc;
-    accel_extra_fields(S, t_ns, y, bpos, acc);
+    if (S.n_xgrav > 0) accel_extra_fields(S, t_ns, y, bpos, acc);
     if (has_force) accel_post(S, t_ns, y, bpos, mass, srp_area, drag_area, acc);
     return 0;
 }
