@@ -722,7 +722,7 @@ __device__ __forceinline__ void grav_rel(int body, const double y[9], const doub
 // harmonic fields beyond the primary one (OrbitalDynamics holds a Vec of accel models, orbital.rs:44-46, 102-107), summed per
 // trajectory in list order
 // (out of line: the per-thread harmonic evaluation carries a large register / stack footprint that must not leak into its callers)
-__device__ __noinline__ void accel_extra_fields(const DevSetup& S, long long t_ns, const double y[9],
+static __device__ __noinline__ void accel_extra_fields(const DevSetup& S, long long t_ns, const double y[9],
                                                 const double bpos[NYXB_MAX_BODIES][3], double acc[3]) {
     for (int f = 0; f < S.n_xgrav; ++f) {
         double rel[3], ga[3];

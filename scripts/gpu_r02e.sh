@@ -3,6 +3,7 @@
 set -u
 cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
+python -c "import nyx_b200.abi as a; a.load_library()" || { echo "libnyxb.so missing or stale"; exit 9; }
 timeout 150 python -m pytest tests/test_gpu_tx.py -x -q -p no:cacheprovider > gpurun_out/r02e_pytest_tx.log 2>&1; echo "pytest tx rc=$?"; tail -6 gpurun_out/r02e_pytest_tx.log
 B="python bench.py --no-cpu-baseline --no-strict --steps 3 --warmup 3"
 run() { tag=$1; shift; timeout 90 "$@" > gpurun_out/r02e_$tag.json 2> gpurun_out/r02e_$tag.err; echo "$tag rc=$?"; }
