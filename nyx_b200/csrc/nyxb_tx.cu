@@ -46,23 +46,27 @@ enum { TXI_EPOCH = 0, TXI_STEP, TXI_PREV_STEP, TXI_DET_STEP, TXI_NSTEPS, TXI_NRE
 enum { TXW_FLAGS = 0, TXW_STATUS, TXW_RC, TXW_ATT, TXW_EVCNT, TXW_ACC, TXW_RCST, TXW_COUNT };
 enum { F_FIXED = 1, F_PREVFIXED = 2, F_RETRY = 4, F_LAST = 8, F_DONE = 16, F_BACK = 32, F_VALID = 64 };
 
-// dynamic shared memory: [table blob | NCTX set contexts]; one context:
-//   walker inputs  ub, r2 [32]; rm, im, rp [N+2][32]   (written by the helpers before READY, read by the walkers)
-//   part [P][4][32]                                     (written by the walkers before DONE, read by the helpers)
-//   helper-private: ys [6][32], kst [16][6][32], nxt / er / ycur [6][32], controller fields
+// dynamic shared memory: [table blob | NCTX set contexts]; one context (buffers of consecutive stages alternate by parity):
+//   wk   [2][5][32]      walker inputs of a stage: ub, r2, z = (cos, sin)(lambda) cos(phi), rho   (lead helper -> walkers)
+//   part [2][P][4][32]   partial sums of a stage                                                   (walkers -> helpers)
+//   as   [2][18][32]     what the helpers need to assemble that stage's acceleration later (DCM, unit vector, K0, K1, two-body factor, position)
+//   ysp  [2][3][32]      position components of a coming stage, exchanged between the three helpers
+//   helper-private: kst [16][6][32] (k_i = (V_i, A_i)), nxt / er / ycur [6][32], controller fields
 struct TxLayout {
-    unsigned blob, ctx0, ctx_stride;                       // bytes
-    unsigned wk, part, ys, kst, nxt, er, ycur, f64, i64, i32;   // offsets inside a context
+    unsigned blob, ctx0, ctx_stride;                                  // bytes
+    unsigned wk, part, as, ysp, kst, nxt, er, ycur, f64, i64, i32;    // offsets inside a context
     unsigned total;
 };
 __host__ __device__ inline TxLayout tx_layout(unsigned blob_bytes, int P, int N, int nctx) {
+    (void)N;
     TxLayout L;
     L.blob = 0;
     L.ctx0 = (blob_bytes + 127u) & ~127u;
     unsigned o = 0;
-    L.wk = o; o += (2u + 3u * (unsigned)(N + 2)) * NL * 8;
-    L.part = o; o += (unsigned)P * 4 * NL * 8;
-    L.ys = o; o += 6 * NL * 8;
+    L.wk = o; o += 2u * 5u * NL * 8;
+    L.part = o; o += 2u * (unsigned)P * 4 * NL * 8;
+    L.as = o; o += 2u * 18u * NL * 8;
+    L.ysp = o; o += 2u * 3u * NL * 8;
     L.kst = o; o += NYXB_MAX_STAGES * 6 * NL * 8;
     L.nxt = o; o += 6 * NL * 8;
     L.er = o; o += 6 * NL * 8;
@@ -76,16 +80,16 @@ __host__ __device__ inline TxLayout tx_layout(unsigned blob_bytes, int P, int N,
 }
 
 struct TxSm {   // typed views of one set context
-    double *ub, *r2, *rm, *im, *rp;    // walker inputs
-    double *part, *ys, *kst, *nxt, *er, *ycur, *f64;
+    double *wk, *part, *as, *ysp, *kst, *nxt, *er, *ycur, *f64;
     long long* i64;
     int* i32;
 };
 __device__ __forceinline__ TxSm tx_views(unsigned char* smem, const TxLayout& L, int ctx, int N) {
+    (void)N;
     unsigned char* b = smem + L.ctx0 + (unsigned)ctx * L.ctx_stride;
     TxSm sm;
-    sm.ub = reinterpret_cast<double*>(b + L.wk); sm.r2 = sm.ub + NL; sm.rm = sm.r2 + NL; sm.im = sm.rm + (N + 2) * NL; sm.rp = sm.im + (N + 2) * NL;
-    sm.part = reinterpret_cast<double*>(b + L.part); sm.ys = reinterpret_cast<double*>(b + L.ys);
+    sm.wk = reinterpret_cast<double*>(b + L.wk); sm.part = reinterpret_cast<double*>(b + L.part);
+    sm.as = reinterpret_cast<double*>(b + L.as); sm.ysp = reinterpret_cast<double*>(b + L.ysp);
     sm.kst = reinterpret_cast<double*>(b + L.kst); sm.nxt = reinterpret_cast<double*>(b + L.nxt);
     sm.er = reinterpret_cast<double*>(b + L.er); sm.ycur = reinterpret_cast<double*>(b + L.ycur);
     sm.f64 = reinterpret_cast<double*>(b + L.f64); sm.i64 = reinterpret_cast<long long*>(b + L.i64);
@@ -412,6 +416,68 @@ __device__ __noinline__ void tx_park_ctl(const DevSink& sink, const DevTxQueue& 
     if (sink.cap > 0) sink.count[tr] = (d.n_steps + 1 < sink.cap) ? d.n_steps + 1 : sink.cap;
 }
 
+// ---- prologue of stage q for the 32 trajectories of a set, run by the lead helper: body-fixed position, 1/r, the recursion
+// scalars the walkers need, and everything the three helpers need to assemble the acceleration of that stage later
+enum { AS_R = 0, AS_S = 9, AS_T, AS_U, AS_K0, AS_K1, AS_FAC, AS_P0, AS_P1, AS_P2, AS_COUNT };
+enum { WK_UB = 0, WK_R2, WK_ZR, WK_ZI, WK_RHO, WK_COUNT };
+__device__ __forceinline__ void tx_prologue(const DevSetup& S, const TxSm& sm, int lane, int par, const double* ysp, const double (&R)[9],
+                                            long long t_ns) {
+    const DevGrav& gv = S.grav;
+    const double p0 = ysp[lane], p1 = ysp[NL + lane], p2 = ysp[2 * NL + lane];
+    double y0 = p0, y1 = p1, y2 = p2;
+    double ir_c = 0.0;   // 1/|r| about the integration centre (two-body term)
+    if (S.grav_body >= 0) {   // field of another body: the state is translated to it first (gravity_field.rs:149-154)
+        ir_c = rsqrt(fma(y2, y2, fma(y1, y1, y0 * y0)));
+        tx_field_offset(S, t_ns, y0, y1, y2);
+    }
+    const double rb0 = fma(R[2], y2, fma(R[1], y1, R[0] * y0));
+    const double rb1 = fma(R[5], y2, fma(R[4], y1, R[3] * y0));
+    const double rb2 = fma(R[8], y2, fma(R[7], y1, R[6] * y0));
+    const double inv_r = rsqrt(fma(rb2, rb2, fma(rb1, rb1, rb0 * rb0)));
+    if (S.grav_body < 0) ir_c = inv_r;
+    const double rho = gv.r_eq * inv_r;
+    const double s_ = rb0 * inv_r, t_ = rb1 * inv_r, u_ = rb2 * inv_r;
+    double* wk = sm.wk + par * WK_COUNT * NL + lane;
+    wk[WK_UB * NL] = u_ * rho; wk[WK_R2 * NL] = rho * rho; wk[WK_ZR * NL] = s_; wk[WK_ZI * NL] = t_; wk[WK_RHO * NL] = rho;
+    double* as = sm.as + par * AS_COUNT * NL + lane;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) as[(AS_R + k) * NL] = R[k];
+    as[AS_S * NL] = s_; as[AS_T * NL] = t_; as[AS_U * NL] = u_;
+    // rr_n A[n][m] = K0 rho (rho^n A),  rr_{n-1} A[n][m] = K0 (rho^n A),  K0 = mu / (r R_eq)
+    const double K0 = (gv.mu * gv.inv_r_eq) * inv_r;
+    as[AS_K0 * NL] = K0; as[AS_K1 * NL] = K0 * rho;
+    as[AS_FAC * NL] = -S.mu_central * ir_c * ir_c * ir_c;   // two-body (orbital.rs:86-92), from the same 1/r when the field is the centre's
+    as[AS_P0 * NL] = p0; as[AS_P1 * NL] = p1; as[AS_P2 * NL] = p2;
+}
+
+// inertial -> body-fixed DCM at the stage time: first-order update of the (slow) pole angles, exact angle addition for the
+// prime-meridian angle (the stage epoch is ns-truncated, cosmic/mod.rs:102)
+struct TxRotBase { double sa, ca, sd, cd, sw, cw; };
+__device__ __forceinline__ void tx_dcm(const DevRotation& rot, const TxRotBase& b, long long off_ns, double (&R)[9]) {
+    if (rot.kind == 0) {
+        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+        return;
+    }
+    const double dt_s = (double)off_ns * 1e-9;
+    const double da = rot.ra_dot * dt_s, dd = rot.dec_dot * dt_s, dw = rot.wdot * dt_s;
+    const double sa = fma(b.ca, da, b.sa), ca = fma(-b.sa, da, b.ca);
+    const double sd = fma(b.cd, dd, b.sd), cd = fma(-b.sd, dd, b.cd);
+    double sdl, cdl;
+    if (fabs(dw) < 0.02) {
+        const double z = dw * dw;
+        sdl = dw * fma(z, fma(z, 1.0 / 120.0, -1.0 / 6.0), 1.0);
+        cdl = fma(z, fma(z, fma(z, -1.0 / 720.0, 1.0 / 24.0), -0.5), 1.0);
+    } else {
+        det_sincos(dw, sdl, cdl);
+    }
+    const double sw = fma(b.sw, cdl, b.cw * sdl), cw = fma(b.cw, cdl, -(b.sw * sdl));
+    const double b00 = -sa, b01 = ca;
+    const double b10 = -(sd * ca), b11 = -(sd * sa), b12 = cd;
+    R[0] = fma(cw, b00, sw * b10); R[1] = fma(cw, b01, sw * b11); R[2] = sw * b12;
+    R[3] = fma(cw, b10, -(sw * b00)); R[4] = fma(cw, b11, -(sw * b01)); R[5] = cw * b12;
+    R[6] = cd * ca; R[7] = cd * sa; R[8] = sd;
+}
+
 template <int P, int NCTX>
 __global__ void __launch_bounds__((P + 3 * NCTX) * 32, 1)
 nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, const __grid_constant__ DevTxQueue q, size_t n,
@@ -424,8 +490,10 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
     __shared__ int s_set[NCTX], s_fresh[NCTX], s_exit[NCTX], s_all_done[NCTX], s_slice_end[NCTX];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     constexpr int NT_RW = (P + 3) * 32;   // threads on a READY / DONE barrier: the walkers + the three helpers of the context
-    constexpr int BAR_HB = 1, BAR_READY = 1 + NCTX, BAR_DONE = 1 + 2 * NCTX;
+    // named barriers of context c: HB (helpers among themselves), READY[parity], DONE[parity]
+    constexpr int BAR_PER_CTX = 5;
     const int N = S.grav.N;
+    const int stages = S.tb.stages;
     const TxLayout L = tx_layout(blob_bytes, P, N, NCTX);
     const double2* recA = reinterpret_cast<const double2*>(smem + L.blob);
     const double* recK = reinterpret_cast<const double*>(smem + L.blob + off_recK);
@@ -448,32 +516,70 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
 
     if (w < P) {
         // =============================================================================================== WALKER
+        // Walks its columns for stage 0, 1, 2, ... of whichever set each context holds; the inputs of stage i live in the
+        // parity-(i & 1) buffers.  The harmonic sum of stage i+1 needs only the POSITION of that stage, which depends on the
+        // accelerations up to stage i-1 (second-order system): the helpers publish it one walk ahead, so the walkers never wait for
+        // the stage they have just finished — only, once per step, for the controller.
         const int* my = sched + w * (2 + 2 * Tx.kmax);
         const int rec_off = my[0], ncol = my[1];
         unsigned active = (1u << NCTX) - 1u;
+        int stage[NCTX];
+#pragma unroll
+        for (int c = 0; c < NCTX; ++c) stage[c] = 0;
         while (active) {
 #pragma unroll
             for (int c = 0; c < NCTX; ++c) {
                 if (!((active >> c) & 1u)) continue;
-                nb_sync(BAR_READY + c, NT_RW);   // the helpers published this stage's inputs of set context c
-                if (*(volatile int*)&s_exit[c]) { active &= ~(1u << c); continue; }
+                const int par = stage[c] & 1;
+                nb_sync(1 + c * BAR_PER_CTX + 1 + par, NT_RW);   // READY[par]: this stage's inputs of context c are published
+                if (stage[c] == 0 && *(volatile int*)&s_exit[c]) { active &= ~(1u << c); continue; }
                 const TxSm sm = tx_views(smem, L, c, N);
-                const double ub = sm.ub[lane], r2 = sm.r2[lane];
+                const double* wk = sm.wk + par * WK_COUNT * NL + lane;
+                const double ub = wk[WK_UB * NL], r2 = wk[WK_R2 * NL];
+                // z^e = (cos, sin)(e lambda) cos^e(phi) and rho^(e+1) for the two interleaved exponent sequences of this position:
+                // e = w + 2P j (za, pa) and e = 2P-1-w + 2P j (zb, pb); binary powering with warp-uniform bits, the squarings end at
+                // the common ratio z^(2P), rho^(2P)
+                double br = wk[WK_ZR * NL], bi = wk[WK_ZI * NL], bp = wk[WK_RHO * NL];
+                double zar = 1.0, zai = 0.0, zbr = 1.0, zbi = 0.0, pa = bp, pb = bp;
+                const int ea = w, eb = 2 * P - 1 - w;
+#pragma unroll
+                for (int bit = 1; bit < 2 * P; bit <<= 1) {
+                    if (ea & bit) {
+                        const double nr = fma(zar, br, -(zai * bi));
+                        zai = fma(zar, bi, zai * br); zar = nr; pa *= bp;
+                    }
+                    if (eb & bit) {
+                        const double nr = fma(zbr, br, -(zbi * bi));
+                        zbi = fma(zbr, bi, zbi * br); zbr = nr; pb *= bp;
+                    }
+                    const double nb = fma(br, br, -(bi * bi));
+                    bi = 2.0 * br * bi; br = nb; bp *= bp;
+                }
                 double X = 0.0, Y = 0.0, Z = 0.0, W = 0.0;
                 const double2* A = recA + 2 * rec_off;
                 const double* K = recK + rec_off;
                 double2 a01 = A[0], a23 = A[1];
                 double kk = K[0];
-                for (int k = 0; k < ncol; ++k) {
-                    const int m = my[2 + 2 * k], len = my[3 + 2 * k];
-                    const double* sd = colseed + 4 * m;
-                    // seed Q[m][m] rho^m, W term of the first entry, 2m+1; (cos, sin)((m-1) lambda) cos^(m-1)(phi) closes the column
-                    tx_column(A, K, a01, a23, kk, len, sm.rp[m * NL + lane], sd[1], sd[2], sd[3], ub, r2, sm.rm[(m - 1) * NL + lane],
-                              sm.im[(m - 1) * NL + lane], X, Y, Z, W);
+                for (int k = 0; k < ncol; k += 2) {
+                    {   // column of the first sequence
+                        const int m = my[2 + 2 * k], len = my[3 + 2 * k];
+                        const double* sd = colseed + 4 * m;
+                        tx_column(A, K, a01, a23, kk, len, pa * sd[0], sd[1], sd[2], sd[3], ub, r2, zar, zai, X, Y, Z, W);
+                        const double nr = fma(zar, br, -(zai * bi));
+                        zai = fma(zar, bi, zai * br); zar = nr; pa *= bp;
+                    }
+                    if (k + 1 < ncol) {   // column of the second sequence
+                        const int m = my[4 + 2 * k], len = my[5 + 2 * k];
+                        const double* sd = colseed + 4 * m;
+                        tx_column(A, K, a01, a23, kk, len, pb * sd[0], sd[1], sd[2], sd[3], ub, r2, zbr, zbi, X, Y, Z, W);
+                        const double nr = fma(zbr, br, -(zbi * bi));
+                        zbi = fma(zbr, bi, zbi * br); zbr = nr; pb *= bp;
+                    }
                 }
-                double* pt = sm.part + (w * 4) * NL + lane;
+                double* pt = sm.part + ((par * P + w) * 4) * NL + lane;
                 pt[0] = X; pt[NL] = Y; pt[2 * NL] = Z; pt[3 * NL] = W;
-                nb_arrive(BAR_DONE + c, NT_RW);   // partial sums of this position are in shared memory
+                nb_arrive(1 + c * BAR_PER_CTX + 3 + par, NT_RW);   // DONE[par]: the partial sums of this position are in shared memory
+                stage[c] = (stage[c] + 1 == stages) ? 0 : stage[c] + 1;
             }
         }
         return;
@@ -482,10 +588,11 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
     // =================================================================================================== HELPER
     const int c = (w - P) / 3, j = (w - P) % 3;   // set context, helper index: owns state components j (position) and j + 3 (velocity)
     const TxSm sm = tx_views(smem, L, c, N);
-    const int stages = S.tb.stages;
+    const int BAR_HB = 1 + c * BAR_PER_CTX, BAR_READY = BAR_HB + 1, BAR_DONE = BAR_HB + 3;
     const DevGrav& gv = S.grav;
     const bool has_extra = S.n_bodies > 0 || S.has_srp || S.has_drag || S.n_xgrav > 0;
-    const bool lead = (j == 0);   // helper 0 also runs the controller and the ticket queue of its context
+    const bool lead = (j == 0);   // helper 0 also runs the DCM, the stage prologues, the controller and the set queue of its context
+    const double* ta = S.tb.a;    // a_{q,m} (stage q >= 1, m < q) = ta[(q - 1) * NYXB_MAX_STAGES + m]
 
     for (;;) {
         // ---------------------------------------------------------------- acquire a set: a fresh one, else a parked one
@@ -510,9 +617,9 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
             s_set[c] = set; s_fresh[c] = fresh;
             s_exit[c] = set < 0;   // nothing fresh, nothing parked: every unfinished set is in progress in another context
         }
-        nb_sync(BAR_HB + c, 96);
+        nb_sync(BAR_HB, 96);
         if (s_exit[c]) {
-            nb_arrive(BAR_READY + c, NT_RW);   // releases the walkers, which read s_exit and drop this context
+            nb_arrive(BAR_READY + 0, NT_RW);   // releases the walkers (they expect stage 0), which read s_exit and drop this context
             return;
         }
         const int set = s_set[c];
@@ -536,141 +643,115 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
             const bool all = __all_sync(FULL, done);
             if (lane == 0) { s_all_done[c] = all; s_slice_end[c] = 0; }
         }
-        nb_sync(BAR_HB + c, 96);
+        nb_sync(BAR_HB, 96);
 
         // ---------------------------------------------------------------- step attempts of this slice
         for (int it = 0; !s_all_done[c]; ++it) {
             const double h = sm.f64[TXF_H * NL + lane];
             const long long epoch = sm.i64[TXI_EPOCH * NL + lane];
-            // orientation angles at the step epoch (every helper keeps its own copy: no exchange)
-            double b_sa = 0.0, b_ca = 1.0, b_sd = 1.0, b_cd = 0.0, b_sw = 0.0, b_cw = 1.0;
-            if (gv.rot.kind != 0) {
+            const double r_own = sm.ycur[j * NL + lane], v_own = sm.ycur[(3 + j) * NL + lane];
+            // orientation angles at the step epoch (lead only: it evaluates every DCM of the attempt)
+            TxRotBase rb_;
+            rb_.sa = 0.0; rb_.ca = 1.0; rb_.sd = 1.0; rb_.cd = 0.0; rb_.sw = 0.0; rb_.cw = 1.0;
+            if (lead && gv.rot.kind != 0) {
                 const double t_s = dur_to_seconds(epoch);
                 const double d = t_s / 86400.0;
                 const double Tc = d / 36525.0;
-                det_sincos((gv.rot.ra0 + gv.rot.ra1 * Tc) * NYXB_DEG2RAD, b_sa, b_ca);
-                det_sincos((gv.rot.dec0 + gv.rot.dec1 * Tc) * NYXB_DEG2RAD, b_sd, b_cd);
-                det_sincos(fmod(gv.rot.w0 + gv.rot.w1 * d, 360.0) * NYXB_DEG2RAD, b_sw, b_cw);
+                det_sincos((gv.rot.ra0 + gv.rot.ra1 * Tc) * NYXB_DEG2RAD, rb_.sa, rb_.ca);
+                det_sincos((gv.rot.dec0 + gv.rot.dec1 * Tc) * NYXB_DEG2RAD, rb_.sd, rb_.cd);
+                det_sincos(fmod(gv.rot.w0 + gv.rot.w1 * d, 360.0) * NYXB_DEG2RAD, rb_.sw, rb_.cw);
             }
             int rc_acc = 0;
-            // ---- derive(): one attempt for the 32 trajectories (instance.rs:358-493)
+            double Rn[9];
+            // ---- prime the pipeline: stage 0 (the state itself) and stage 1 (needs only V_0 = v): instance.rs:369-394
+            sm.kst[(0 * 6 + j) * NL + lane] = v_own;                 // k_0[j] = V_0
+            sm.ysp[(0 * 3 + j) * NL + lane] = r_own;                 // P_0
+            nb_sync(BAR_HB, 96);
+            if (lead) {
+                tx_dcm(gv.rot, rb_, 0, Rn);
+                tx_prologue(S, sm, lane, 0, sm.ysp, Rn, epoch);
+            }
+            nb_arrive(BAR_READY + 0, NT_RW);
+            if (stages > 1) {
+                const long long off1 = dur_from_seconds(S.tb.c[0] * h);
+                sm.ysp[(1 * 3 + j) * NL + lane] = fma(h, ta[0] * v_own, r_own);   // P_1 = r + h a_10 V_0
+                nb_sync(BAR_HB, 96);
+                if (lead) {
+                    tx_dcm(gv.rot, rb_, off1, Rn);
+                    tx_prologue(S, sm, lane, 1, sm.ysp + 3 * NL, Rn, epoch + off1);
+                }
+                nb_arrive(BAR_READY + 1, NT_RW);
+            }
+            // ---- derive(): the stages of one attempt for the 32 trajectories (instance.rs:358-493), one walk ahead of the walkers
             for (int i = 0; i < stages; ++i) {
-                // stage state y + h * sum_j a_ij k_j (instance.rs:376-394) of components j and j + 3; stage 0 is y itself
-                double ysv[2];
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int cc = j + 3 * half;
-                    const double yc = sm.ycur[cc * NL + lane];
-                    double v = yc;
-                    if (i > 0) {
-                        const double* arow = &S.tb.a[(i - 1) * NYXB_MAX_STAGES];
-                        const double* kc = sm.kst + cc * NL + lane;
-                        double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;   // four chains: the sum is latency-bound otherwise
-                        int jj = 0;
-                        for (; jj + 3 < i; jj += 4) {
-                            w0 = fma(arow[jj], kc[jj * 6 * NL], w0);
-                            w1 = fma(arow[jj + 1], kc[(jj + 1) * 6 * NL], w1);
-                            w2 = fma(arow[jj + 2], kc[(jj + 2) * 6 * NL], w2);
-                            w3 = fma(arow[jj + 3], kc[(jj + 3) * 6 * NL], w3);
-                        }
-                        for (; jj < i; ++jj) w0 = fma(arow[jj], kc[jj * 6 * NL], w0);
-                        v = fma(h, (w0 + w1) + (w2 + w3), yc);
-                    }
-                    ysv[half] = v;
-                    sm.ys[cc * NL + lane] = v;
+                const int par = i & 1;
+                // -- slack: everything that does not need the acceleration of stage i
+                double preV = 0.0, preP = 0.0;
+                long long off2 = 0;
+                if (i + 1 < stages) {   // V_{i+1} = v + h sum_{l<=i} a_{i+1,l} A_l: all terms but the last
+                    const double* arow = ta + i * NYXB_MAX_STAGES;
+                    const double* kc = sm.kst + (3 + j) * NL + lane;
+                    double w0 = 0.0, w1 = 0.0;
+                    int l = 0;
+                    for (; l + 1 < i; l += 2) { w0 = fma(arow[l], kc[l * 6 * NL], w0); w1 = fma(arow[l + 1], kc[(l + 1) * 6 * NL], w1); }
+                    if (l < i) w0 = fma(arow[l], kc[l * 6 * NL], w0);
+                    preV = w0 + w1;
                 }
-                // inertial -> body-fixed DCM at the stage time: first-order update of the (slow) pole angles, exact angle addition
-                // for the prime-meridian angle (the stage epoch is ns-truncated, cosmic/mod.rs:102)
-                const long long off_ns = (i > 0) ? dur_from_seconds(S.tb.c[i - 1] * h) : 0;
-                double R[9];
-                if (gv.rot.kind == 0) {
-                    R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
-                } else {
-                    const double dt_s = (double)off_ns * 1e-9;
-                    const double da = gv.rot.ra_dot * dt_s, dd = gv.rot.dec_dot * dt_s, dw = gv.rot.wdot * dt_s;
-                    const double sa = fma(b_ca, da, b_sa), ca = fma(-b_sa, da, b_ca);
-                    const double sd = fma(b_cd, dd, b_sd), cd = fma(-b_sd, dd, b_cd);
-                    double sdl, cdl;
-                    if (fabs(dw) < 0.02) {
-                        const double z = dw * dw;
-                        sdl = dw * fma(z, fma(z, 1.0 / 120.0, -1.0 / 6.0), 1.0);
-                        cdl = fma(z, fma(z, fma(z, -1.0 / 720.0, 1.0 / 24.0), -0.5), 1.0);
-                    } else {
-                        det_sincos(dw, sdl, cdl);
-                    }
-                    const double sw = fma(b_sw, cdl, b_cw * sdl), cw = fma(b_cw, cdl, -(b_sw * sdl));
-                    const double b00 = -sa, b01 = ca;
-                    const double b10 = -(sd * ca), b11 = -(sd * sa), b12 = cd;
-                    R[0] = fma(cw, b00, sw * b10); R[1] = fma(cw, b01, sw * b11); R[2] = sw * b12;
-                    R[3] = fma(cw, b10, -(sw * b00)); R[4] = fma(cw, b11, -(sw * b01)); R[5] = cw * b12;
-                    R[6] = cd * ca; R[7] = cd * sa; R[8] = sd;
+                if (i + 2 < stages) {   // P_{i+2} = r + h sum_{m<=i+1} a_{i+2,m} V_m: all terms but the last (V_i is known)
+                    const double* arow = ta + (i + 1) * NYXB_MAX_STAGES;
+                    const double* kc = sm.kst + j * NL + lane;
+                    double w0 = 0.0, w1 = 0.0;
+                    int m = 0;
+                    for (; m + 1 <= i; m += 2) { w0 = fma(arow[m], kc[m * 6 * NL], w0); w1 = fma(arow[m + 1], kc[(m + 1) * 6 * NL], w1); }
+                    if (m <= i) w0 = fma(arow[m], kc[m * 6 * NL], w0);
+                    preP = w0 + w1;
+                    off2 = dur_from_seconds(S.tb.c[i + 1] * h);
+                    if (lead) tx_dcm(gv.rot, rb_, off2, Rn);
                 }
-                nb_sync(BAR_HB + c, 96);   // the three position components of the stage state are in shared memory
+                nb_sync(BAR_DONE + par, NT_RW);   // the walkers' partial sums of stage i are back
 
-                // ---- body-fixed position, 1/r, recursion scalars, power tables -> walker inputs
-                const double p0 = sm.ys[lane], p1 = sm.ys[NL + lane], p2 = sm.ys[2 * NL + lane];
-                double y0 = p0, y1 = p1, y2 = p2;
-                double ir_c = 0.0;   // 1/|r| about the integration centre (two-body term)
-                if (S.grav_body >= 0) {   // field of another body: the state is translated to it first (gravity_field.rs:149-154)
-                    ir_c = rsqrt(fma(y2, y2, fma(y1, y1, y0 * y0)));
-                    tx_field_offset(S, epoch + off_ns, y0, y1, y2);
-                }
-                const double rb0 = fma(R[2], y2, fma(R[1], y1, R[0] * y0));
-                const double rb1 = fma(R[5], y2, fma(R[4], y1, R[3] * y0));
-                const double rb2 = fma(R[8], y2, fma(R[7], y1, R[6] * y0));
-                const double inv_r = rsqrt(fma(rb2, rb2, fma(rb1, rb1, rb0 * rb0)));
-                if (S.grav_body < 0) ir_c = inv_r;
-                const double rho = gv.r_eq * inv_r;
-                const double s_ = rb0 * inv_r, t_ = rb1 * inv_r, u_ = rb2 * inv_r;
-                if (lead) { sm.ub[lane] = u_ * rho; sm.r2[lane] = rho * rho; }
-                {   // z^k = (cos, sin)(k lambda) cos^k(phi), rho^k (2k-1)!! for k = j, j+3, ... <= N+1 (ratio z^3, rho^3)
-                    const double z2r = fma(s_, s_, -(t_ * t_)), z2i = 2.0 * s_ * t_;
-                    const double z3r = fma(z2r, s_, -(z2i * t_)), z3i = fma(z2r, t_, z2i * s_);
-                    const double rho2 = rho * rho, rho3 = rho2 * rho;
-                    double zr = (j == 0) ? 1.0 : (j == 1 ? s_ : z2r), zi = (j == 0) ? 0.0 : (j == 1 ? t_ : z2i);
-                    double pr = (j == 0) ? 1.0 : (j == 1 ? rho : rho2);
-                    for (int k = j; k <= N + 1; k += 3) {
-                        sm.rm[k * NL + lane] = zr; sm.im[k * NL + lane] = zi; sm.rp[k * NL + lane] = pr * colseed[4 * k];
-                        const double nr = fma(zr, z3r, -(zi * z3i));
-                        zi = fma(zr, z3i, zi * z3r); zr = nr; pr *= rho3;
-                    }
-                }
-                nb_arrive(BAR_READY + c, NT_RW);   // walker inputs of this stage are published
-                nb_sync(BAR_DONE + c, NT_RW);      // ... the walkers' partial sums are back
-
-                // ---- reduce the partial sums, assemble the acceleration component j (spacecraft.rs:216-247)
+                // -- reduce the partial sums, assemble the acceleration component j of stage i (spacecraft.rs:216-247)
                 double X, Y, Z, Wt;
                 {
                     double ax[4] = {0.0, 0.0, 0.0, 0.0}, ay[4] = {0.0, 0.0, 0.0, 0.0}, az[4] = {0.0, 0.0, 0.0, 0.0}, aw4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
                     for (int p = 0; p < P; ++p) {
-                        const double* pt = sm.part + (p * 4) * NL + lane;
+                        const double* pt = sm.part + ((par * P + p) * 4) * NL + lane;
                         ax[p & 3] += pt[0]; ay[p & 3] += pt[NL]; az[p & 3] += pt[2 * NL]; aw4[p & 3] += pt[3 * NL];
                     }
                     X = (ax[0] + ax[1]) + (ax[2] + ax[3]); Y = (ay[0] + ay[1]) + (ay[2] + ay[3]);
                     Z = (az[0] + az[1]) + (az[2] + az[3]); Wt = (aw4[0] + aw4[1]) + (aw4[2] + aw4[3]);
                 }
-                // rr_n A[n][m] = K0 rho (rho^n A),  rr_{n-1} A[n][m] = K0 (rho^n A),  K0 = mu / (r R_eq)
-                const double K0 = (gv.mu * gv.inv_r_eq) * inv_r;
-                const double K1 = K0 * rho;
+                const double* as = sm.as + par * AS_COUNT * NL + lane;
+                const double K0 = as[AS_K0 * NL], K1 = as[AS_K1 * NL];
                 const double aw = -K0 * Wt;
-                const double ab0 = fma(aw, s_, K1 * X), ab1 = fma(aw, t_, K1 * Y), ab2 = fma(aw, u_, K1 * Z);
-                const double fac = -S.mu_central * ir_c * ir_c * ir_c;   // two-body (orbital.rs:86-92), from the same 1/r when the field is the centre's
-                const double pj = (j == 0) ? p0 : (j == 1 ? p1 : p2);
-                double acc = fma(fac, pj, fma(R[6 + j], ab2, fma(R[3 + j], ab1, R[j] * ab0)));
+                const double ab0 = fma(aw, as[AS_S * NL], K1 * X), ab1 = fma(aw, as[AS_T * NL], K1 * Y), ab2 = fma(aw, as[AS_U * NL], K1 * Z);
+                double acc = fma(as[AS_FAC * NL], as[(AS_P0 + j) * NL],
+                                 fma(as[(AS_R + 6 + j) * NL], ab2, fma(as[(AS_R + 3 + j) * NL], ab1, as[(AS_R + j) * NL] * ab0)));
                 if (has_extra) {
                     double yy[9], aa[3] = {0.0, 0.0, 0.0};
                     const double hz = (i > 0) ? h * 0.0 : 0.0;
+                    yy[0] = as[AS_P0 * NL]; yy[1] = as[AS_P1 * NL]; yy[2] = as[AS_P2 * NL];
 #pragma unroll
-                    for (int e = 0; e < 6; ++e) yy[e] = sm.ys[e * NL + lane];
+                    for (int e = 0; e < 3; ++e) yy[3 + e] = sm.kst[(i * 6 + e) * NL + lane];   // V_i
                     yy[6] = sm.f64[TXF_CR * NL + lane] + hz; yy[7] = sm.f64[TXF_CD * NL + lane] + hz; yy[8] = sm.f64[TXF_PM * NL + lane] + hz;
+                    const long long offi = (i > 0) ? dur_from_seconds(S.tb.c[i - 1] * h) : 0;
                     const int rcx = tx_extra(S, sm.f64[TXF_DRY * NL + lane], sm.f64[TXF_EXTRA * NL + lane], sm.f64[TXF_SRPA * NL + lane],
-                                             sm.f64[TXF_DRAGA * NL + lane], epoch + off_ns, yy, aa);
+                                             sm.f64[TXF_DRAGA * NL + lane], epoch + offi, yy, aa);
                     acc += (j == 0) ? aa[0] : (j == 1 ? aa[1] : aa[2]);
                     if (rcx && !rc_acc) rc_acc = rcx | ((i + 1) << 8);
                 }
-                sm.kst[(i * 6 + j) * NL + lane] = ysv[1];      // dr_j/dt = v_j
-                sm.kst[(i * 6 + 3 + j) * NL + lane] = acc;     // dv_j/dt
+                sm.kst[(i * 6 + 3 + j) * NL + lane] = acc;     // k_i[3+j] = A_i
+                if (i + 1 < stages) {
+                    const double vn = fma(h, fma(ta[i * NYXB_MAX_STAGES + i], acc, preV), v_own);   // V_{i+1}
+                    sm.kst[((i + 1) * 6 + j) * NL + lane] = vn;                                    // k_{i+1}[j]
+                    if (i + 2 < stages) {
+                        sm.ysp[(par * 3 + j) * NL + lane] = fma(h, fma(ta[(i + 1) * NYXB_MAX_STAGES + i + 1], vn, preP), r_own);   // P_{i+2}
+                        nb_sync(BAR_HB, 96);   // the three position components of stage i+2 are in shared memory
+                        if (lead) tx_prologue(S, sm, lane, par, sm.ysp + par * 3 * NL, Rn, epoch + off2);
+                        nb_arrive(BAR_READY + par, NT_RW);   // walker inputs of stage i+2 are published
+                    }
+                }
             }
             // ---- candidate state and error estimate of this attempt (instance.rs:402-414)
             {
@@ -689,7 +770,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                 }
                 if (lead) sm.i32[TXW_RCST * NL + lane] = rc_acc;
             }
-            nb_sync(BAR_HB + c, 96);
+            nb_sync(BAR_HB, 96);
             if (lead) {
                 tx_controller(S, sink, sm, lane, n, tr, stages);
                 const bool slice_end = q.slice > 0 && it + 1 >= q.slice;
@@ -698,7 +779,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                 const bool all = __all_sync(FULL, done);
                 if (lane == 0) { s_all_done[c] = all; s_slice_end[c] = slice_end; }
             }
-            nb_sync(BAR_HB + c, 96);
+            nb_sync(BAR_HB, 96);
             if (sm.i32[TXW_ACC * NL + lane]) {
                 const long long ns = sm.i64[TXI_NSTEPS * NL + lane];
 #pragma unroll
@@ -720,7 +801,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
         }
         if (lead) tx_park_ctl(sink, q, sm, lane, n, tr, step_io, out_state, out_epoch, out_status);
         __threadfence();
-        nb_sync(BAR_HB + c, 96);
+        nb_sync(BAR_HB, 96);
         if (lead && lane == 0 && !s_all_done[c]) {   // park: the set becomes resumable by any context
             while (atomicCAS(q.ctl + TXQ_LOCK, 0, 1) != 0) __nanosleep(64);
             __threadfence();
@@ -731,7 +812,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
             __threadfence();
             atomicExch(q.ctl + TXQ_LOCK, 0);
         }
-        nb_sync(BAR_HB + c, 96);   // s_* of this context are rewritten by its lead lane only after this barrier
+        nb_sync(BAR_HB, 96);   // s_* of this context are rewritten by its lead lane only after this barrier
     }
 }
 
