@@ -745,9 +745,10 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                 if (i + 1 < stages) {
                     const double vn = fma(h, fma(ta[i * NYXB_MAX_STAGES + i], acc, preV), v_own);   // V_{i+1}
                     sm.kst[((i + 1) * 6 + j) * NL + lane] = vn;                                    // k_{i+1}[j]
-                    if (i + 2 < stages) {
+                    if (i + 2 < stages)
                         sm.ysp[(par * 3 + j) * NL + lane] = fma(h, fma(ta[(i + 1) * NYXB_MAX_STAGES + i + 1], vn, preP), r_own);   // P_{i+2}
-                        nb_sync(BAR_HB, 96);   // the three position components of stage i+2 are in shared memory
+                    nb_sync(BAR_HB, 96);   // V_{i+1} and the position components of stage i+2 of all three helpers are in shared memory
+                    if (i + 2 < stages) {
                         if (lead) tx_prologue(S, sm, lane, par, sm.ysp + par * 3 * NL, Rn, epoch + off2);
                         nb_arrive(BAR_READY + par, NT_RW);   // walker inputs of stage i+2 are published
                     }
