@@ -54,6 +54,7 @@ def parse_args():
     p.add_argument("--lanes", type=int, default=0)
     p.add_argument("--kernel", default="auto", choices=["auto", "thread", "coop", "transposed"],
                    help="kernel family (nyxb_engine_set_kernel); auto = the library's own dispatch")
+    p.add_argument("--tx-positions", type=int, default=0, help="transposed kernel: walker warps per set (0 = library default)")
     p.add_argument("--tx-slice", type=int, default=0, help="transposed kernel: step attempts per time slice (0 = library default)")
     p.add_argument("--cpu-sample", type=int, default=0,
                    help="trajectories in the bounded CPU-baseline sample (0: 32 per host core, ~10 s of CPU work)")
@@ -472,6 +473,8 @@ def main():
         eng.set_kernel({"thread": nb.KERNEL_THREAD, "coop": nb.KERNEL_COOP, "transposed": nb.KERNEL_TRANSPOSED}[args.kernel])
     if args.tx_slice:
         eng.set_tx_tuning(args.tx_slice, 0)
+    if args.tx_positions:
+        eng.set_tx_positions(args.tx_positions)
     end = int(args.span_days * DAY)
 
     # pinned host inputs of this rank's shard (e2e leg) and HBM-resident copies (value leg)

@@ -320,6 +320,8 @@ def _declare(lib):
     lib.nyxb_engine_set_kernel.argtypes = [vp, C.c_int32]
     lib.nyxb_engine_last_kernel.restype = C.c_int32
     lib.nyxb_engine_last_kernel.argtypes = [vp]
+    lib.nyxb_engine_set_tx_positions.restype = C.c_int32
+    lib.nyxb_engine_set_tx_positions.argtypes = [vp, C.c_int32]
     lib.nyxb_engine_set_tx_tuning.restype = C.c_int32
     lib.nyxb_engine_set_tx_tuning.argtypes = [vp, C.c_int32, C.c_int32]
     lib.nyxb_abi_version.restype = C.c_int32
@@ -359,6 +361,7 @@ EXPORTED_SYMBOLS = [
     "nyxb_engine_set_kernel",
     "nyxb_engine_last_kernel",
     "nyxb_engine_set_tx_tuning",
+    "nyxb_engine_set_tx_positions",
     "nyxb_abi_version",
     "nyxb_last_error",
 ]

@@ -77,6 +77,7 @@ struct nyxb_engine {
     int last_kernel = NYXB_KERNEL_AUTO;    // family the last launch used
     std::map<int, DevTx> tx;               // positions -> tables of the transposed kernel
     int tx_slice = 64;                     // step attempts per time slice of the persistent transposed kernel
+    int tx_positions = 0;                  // walker warps per set (0: by degree)
     int tx_max_ctas = 0;                   // 0: every resident slot (SMs x occupancy); tests shrink it to force time slicing
     size_t txq_bytes = 0;                  // grow-only queue + parking workspace of the transposed kernel
     unsigned char* d_txq = nullptr;
@@ -410,7 +411,10 @@ static const DevTx* get_tx(nyxb_engine* e, int P) {
 }
 
 // positions of the transposed kernel for this field: 8 warps per set up to degree 40, 16 beyond (shared-memory footprint of the table)
-static int tx_positions(const nyxb_engine* e) { return e->S.grav.N <= 40 ? 8 : 16; }
+static int tx_positions(const nyxb_engine* e) {
+    if (e->tx_positions) return e->tx_positions;
+    return e->S.grav.N <= 40 ? 8 : 16;
+}
 
 static bool tx_supported(const nyxb_engine* e) {
     return e->mode == NYXB_MODE_FAST && e->S.has_grav && e->S.grav.N >= 8 && e->S.grav.N <= 70;
@@ -1139,6 +1143,11 @@ extern "C" int32_t nyxb_engine_set_tx_tuning(nyxb_engine* eng, int32_t slice_att
     eng->tx_max_ctas = max_ctas;
     return NYXB_RC_OK;
 }
+extern "C" int32_t nyxb_engine_set_tx_positions(nyxb_engine* eng, int32_t positions) {
+    if (!eng || (positions != 0 && positions != 8 && positions != 12 && positions != 16)) { set_err("positions: 0 (auto), 8, 12, 16"); return NYXB_RC_BAD_ARG; }
+    eng->tx_positions = positions;
+    return NYXB_RC_OK;
+}
 extern "C" int32_t nyxb_engine_get_lanes(const nyxb_engine* eng) { return eng ? pick_lanes(eng, 0) : 0; }
 extern "C" int64_t nyxb_engine_launch_count(const nyxb_engine* eng) { return eng ? eng->launches : 0; }
 extern "C" double nyxb_engine_last_kernel_ms(const nyxb_engine* eng) { return eng ? eng->last_ms : 0.0; }
@@ -1161,7 +1170,7 @@ extern "C" int32_t nyxb_coop_table_dump(const nyxb_gravity_field* f, int32_t lan
 
 extern "C" int32_t nyxb_tx_table_dump(const nyxb_gravity_field* f, int32_t positions, int32_t* out_n_rec, int32_t* out_kmax,
                                       double* recA, double* recK, double* colseed, int32_t* sched) {
-    if (!f || !f->c_nm || !f->s_nm || f->degree < 2 || (positions != 8 && positions != 16) || !out_n_rec || !out_kmax) {
+    if (!f || !f->c_nm || !f->s_nm || f->degree < 2 || (positions != 8 && positions != 12 && positions != 16) || !out_n_rec || !out_kmax) {
         set_err("bad argument");
         return NYXB_RC_BAD_ARG;
     }

@@ -146,36 +146,54 @@ __device__ __noinline__ void tx_field_offset(const DevSetup& S, long long t_ns, 
     if (body_position(S.bodies[S.grav_body], t_ns, bp)) { y0 -= bp[0]; y1 -= bp[1]; y2 -= bp[2]; }
 }
 
-// ---- one column of the walk.  (a01, a23, kk) hold the NEXT record (prefetched); A / K point at it.
+// ---- one column of the walk.  (a01, a23, kk) hold the column's first record (prefetched); A / K point at it; on return they hold
+// the first record of the next column.
+// Entry n of column m (record p1..p4, kappa; Q = Q[n], Qn = Q[n+1]):
+//     S1..S4 += Q p1..p4          W-term: S5, S6 += (kappa Qn) (p3, p4)
+//     Qn = c1 Q - m2              c1 = (2n+1) u rho,  m2 = (n+m)(n-m) rho^2 Q[n-1]
+// The loop-carried FP64 dependency is ONE DFMA per entry: c1 and m2 are formed one entry ahead and advanced by additions
+// (c1 += 2 u rho; d += g, g += 2 rho^2 with d = (n+m)(n-m) rho^2), everything else in an entry is off the chain, so two walker
+// warps per scheduler keep the FP64 pipe fed.  12 FP64 instructions per entry.  The loop is unrolled by hand over two register
+// sets for the prefetched record so that no register-to-register moves are left in it (the compiler's own rotation cost 14
+// IMAD.MOV per two entries and made the loop issue-bound, profiles/r02g_tx_ncu_summary.txt).
+#define NYXB_TX_ENTRY(P01, P23, PK)                         \
+    {                                                       \
+        const double Qn = fma(c1, Q, -m2);                  \
+        c1 += dc; d += g; g += dg;                          \
+        m2 = d * Q;                                         \
+        S1 = fma(Q, (P01).x, S1);                           \
+        S2 = fma(Q, (P01).y, S2);                           \
+        S3 = fma(Q, (P23).x, S3);                           \
+        S4 = fma(Q, (P23).y, S4);                           \
+        const double wv = (PK) * Qn;                        \
+        S5 = fma(wv, (P23).x, S5);                          \
+        S6 = fma(wv, (P23).y, S6);                          \
+        Q = Qn;                                             \
+    }
 __device__ __forceinline__ void tx_column(const double2*& A, const double*& K, double2& a01, double2& a23, double& kk, int len,
                                           double q, double pd1, double pd2, double al, double ub, double r2, double rr, double ii,
                                           double& X, double& Y, double& Z, double& W) {
-    double Q = q, Qm1 = 0.0, be = 0.0;
-    double kp = 1.0, p3p = pd1, p4p = pd2;   // "previous record" of the first entry: the column's seed W term (kappa = 1)
-    double S1 = 0.0, S2 = 0.0, S3 = 0.0, S4 = 0.0, S5 = 0.0, S6 = 0.0;
-#pragma unroll 2
-    for (int e = 0; e < len; ++e) {
-        const double2 c01 = a01, c23 = a23;
-        const double ck = kk;
-        A += 2; K += 1;
-        a01 = A[0]; a23 = A[1]; kk = K[0];   // the table ends with a null record
-        const double t1 = al * ub;
-        const double t2 = (be * r2) * Qm1;
-        const double Qn = fma(t1, Q, -t2);   // Q[n+1] = (2n+1) u Q[n] - (n+m)(n-m) r^2 Q[n-1]: the only dependent chain
-        S1 = fma(Q, c01.x, S1);
-        S2 = fma(Q, c01.y, S2);
-        S3 = fma(Q, c23.x, S3);
-        S4 = fma(Q, c23.y, S4);
-        const double wv = kp * Q;            // W term of degree n: kappa(n-1) Q[n] (p3, p4)(n-1)
-        S5 = fma(wv, p3p, S5);
-        S6 = fma(wv, p4p, S6);
-        kp = ck; p3p = c23.x; p4p = c23.y;
-        be += al; al += 2.0;                 // (n+1)^2 - m^2 = n^2 - m^2 + (2n+1)
-        Qm1 = Q; Q = Qn;
+    double Q = q;
+    double c1 = al * ub, m2 = 0.0, d = 0.0, g = al * r2;   // entry n = m: (2m+1) u rho, and (n+m)(n-m) = 0
+    const double dc = ub + ub, dg = r2 + r2;
+    double S1 = 0.0, S2 = 0.0, S3 = 0.0, S4 = 0.0;
+    double S5 = Q * pd1, S6 = Q * pd2;                     // the column's seed W term
+    double2 b01, b23;
+    double bk;
+    int e = len;
+    for (; e >= 2; e -= 2) {
+        b01 = A[2]; b23 = A[3]; bk = K[1];
+        NYXB_TX_ENTRY(a01, a23, kk)
+        a01 = A[4]; a23 = A[5]; kk = K[2];   // the table ends with null records
+        NYXB_TX_ENTRY(b01, b23, bk)
+        A += 4; K += 2;
     }
-    const double wv = kp * Q;                // W term carried by the column's last entry
-    S5 = fma(wv, p3p, S5);
-    S6 = fma(wv, p4p, S6);
+    if (e) {
+        b01 = A[2]; b23 = A[3]; bk = K[1];
+        NYXB_TX_ENTRY(a01, a23, kk)
+        A += 2; K += 1;
+        a01 = b01; a23 = b23; kk = bk;
+    }
     // close the column: apply its (cos, sin)((m-1) lambda) cos^(m-1)(phi)
     X = fma(rr, S1, fma(ii, S2, X));
     Y = fma(rr, S2, fma(-ii, S1, Y));
@@ -928,7 +946,7 @@ void nyxb_tx_build_host(int N, int M, const double* c_nm, const double* s_nm, in
 // set contexts per CTA: two sets in flight while both fit beside the table (P = 8: degrees up to ~40), one otherwise
 static int tx_contexts(const DevSetup* S, const DevTx* Tx, size_t* smem_bytes) {
     const TxBlob b = tx_blob(S->grav.N, Tx->P, Tx->n_rec, Tx->kmax);
-    for (int nctx = (Tx->P == 8 ? 2 : 1); nctx >= 1; --nctx) {
+    for (int nctx = (Tx->P <= 12 ? 2 : 1); nctx >= 1; --nctx) {
         const size_t smem = tx_layout(b.bytes, Tx->P, S->grav.N, nctx).total;
         if (smem <= 227 * 1024) { if (smem_bytes) *smem_bytes = smem; return nctx; }
     }
@@ -937,7 +955,7 @@ static int tx_contexts(const DevSetup* S, const DevTx* Tx, size_t* smem_bytes) {
 
 // set contexts one SM holds for this setup (one persistent CTA per SM; 0: the tables do not fit) and its dynamic shared memory
 extern "C" int nyxb_tx_occupancy(const DevSetup* S, const DevTx* Tx, size_t* smem_bytes) {
-    if (Tx->P != 8 && Tx->P != 16) return 0;
+    if (Tx->P != 8 && Tx->P != 12 && Tx->P != 16) return 0;
     return tx_contexts(S, Tx, smem_bytes);
 }
 
@@ -953,6 +971,7 @@ extern "C" cudaError_t nyxb_launch_tx(const DevSetup* S, const DevTx* Tx, const 
     if (nctx < 1 || grid < 1) return cudaErrorInvalidConfiguration;
 #define NYXB_TX_GO(PP, CC) tx_launch_p<PP, CC>(S, Tx, q, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_status, sink, grid, smem, b.bytes, b.off_recK, b.off_seed, b.off_sched, stream)
     if (Tx->P == 8) return nctx == 2 ? NYXB_TX_GO(8, 2) : NYXB_TX_GO(8, 1);
+    if (Tx->P == 12) return nctx == 2 ? NYXB_TX_GO(12, 2) : NYXB_TX_GO(12, 1);
     if (Tx->P == 16) return NYXB_TX_GO(16, 1);
     return cudaErrorInvalidValue;
 #undef NYXB_TX_GO

@@ -197,6 +197,11 @@ class Engine:
     def last_kernel(self) -> int:
         return self._lib.nyxb_engine_last_kernel(self._h)
 
+    def set_tx_positions(self, positions: int):
+        """Transposed kernel: walker warps per set of 32 trajectories (0 = chosen by the field's degree)."""
+        if self._lib.nyxb_engine_set_tx_positions(self._h, positions) != 0:
+            raise PropagationError(f"set_tx_positions({positions}): {abi.last_error()}")
+
     def set_tx_tuning(self, slice_attempts: int = 64, max_ctas: int = 0):
         """Transposed kernel: step attempts per time slice and a bound on the persistent CTAs (0: every resident slot)."""
         if self._lib.nyxb_engine_set_tx_tuning(self._h, slice_attempts, max_ctas) != 0:
