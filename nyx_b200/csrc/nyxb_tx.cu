@@ -54,7 +54,7 @@ enum { F_FIXED = 1, F_PREVFIXED = 2, F_RETRY = 4, F_LAST = 8, F_DONE = 16, F_BAC
 //   helper-private: kst [16][6][32] (k_i = (V_i, A_i)), nxt / er / ycur [6][32], controller fields
 struct TxLayout {
     unsigned blob, ctx0, ctx_stride;                                  // bytes
-    unsigned wk, part, as, ysp, kst, nxt, er, ycur, f64, i64, i32;    // offsets inside a context
+    unsigned wk, part, as, ysp, kst, nxt, er, ycur, rot, f64, i64, i32;   // offsets inside a context
     unsigned total;
 };
 __host__ __device__ inline TxLayout tx_layout(unsigned blob_bytes, int P, int N, int nctx) {
@@ -71,6 +71,7 @@ __host__ __device__ inline TxLayout tx_layout(unsigned blob_bytes, int P, int N,
     L.nxt = o; o += 6 * NL * 8;
     L.er = o; o += 6 * NL * 8;
     L.ycur = o; o += 6 * NL * 8;
+    L.rot = o; o += 6 * NL * 8;
     L.f64 = o; o += TXF_COUNT * NL * 8;
     L.i64 = o; o += TXI_COUNT * NL * 8;
     L.i32 = o; o += TXW_COUNT * NL * 4;
@@ -80,7 +81,7 @@ __host__ __device__ inline TxLayout tx_layout(unsigned blob_bytes, int P, int N,
 }
 
 struct TxSm {   // typed views of one set context
-    double *wk, *part, *as, *ysp, *kst, *nxt, *er, *ycur, *f64;
+    double *wk, *part, *as, *ysp, *kst, *nxt, *er, *ycur, *rot, *f64;
     long long* i64;
     int* i32;
 };
@@ -92,6 +93,7 @@ __device__ __forceinline__ TxSm tx_views(unsigned char* smem, const TxLayout& L,
     sm.as = reinterpret_cast<double*>(b + L.as); sm.ysp = reinterpret_cast<double*>(b + L.ysp);
     sm.kst = reinterpret_cast<double*>(b + L.kst); sm.nxt = reinterpret_cast<double*>(b + L.nxt);
     sm.er = reinterpret_cast<double*>(b + L.er); sm.ycur = reinterpret_cast<double*>(b + L.ycur);
+    sm.rot = reinterpret_cast<double*>(b + L.rot);
     sm.f64 = reinterpret_cast<double*>(b + L.f64); sm.i64 = reinterpret_cast<long long*>(b + L.i64);
     sm.i32 = reinterpret_cast<int*>(b + L.i32);
     return sm;
@@ -123,6 +125,20 @@ __device__ __forceinline__ void tx_mbar_wait(unsigned long long* bar, unsigned p
         "bra TX_WAIT_LOOP;\n"
         "TX_WAIT_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void tx_mbar_arrive(unsigned long long* bar) {   // release.cta: the thread's earlier shared stores are published
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool tx_mbar_test(unsigned long long* bar, unsigned parity) {   // non-blocking; acquire.cta when it succeeds
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
 }
 
 // third bodies + SRP + drag for one trajectory (cold path of the harmonics-dominated ensembles this kernel serves)
@@ -496,6 +512,22 @@ __device__ __forceinline__ void tx_dcm(const DevRotation& rot, const TxRotBase& 
     R[6] = cd * ca; R[7] = cd * sa; R[8] = sd;
 }
 
+// orientation angles of the field's body-fixed frame at `epoch` (deterministic sin / cos: the per-step evaluation of the oracle)
+__device__ __forceinline__ TxRotBase tx_rot_base(const DevRotation& rot, long long epoch) {
+    TxRotBase b;
+    const double t_s = dur_to_seconds(epoch);
+    const double d = t_s / 86400.0;
+    const double Tc = d / 36525.0;
+    det_sincos((rot.ra0 + rot.ra1 * Tc) * NYXB_DEG2RAD, b.sa, b.ca);
+    det_sincos((rot.dec0 + rot.dec1 * Tc) * NYXB_DEG2RAD, b.sd, b.cd);
+    det_sincos(fmod(rot.w0 + rot.w1 * d, 360.0) * NYXB_DEG2RAD, b.sw, b.cw);
+    return b;
+}
+__device__ __forceinline__ void tx_rot_store(double* rot, int lane, const TxRotBase& b) {
+    rot[lane] = b.sa; rot[NL + lane] = b.ca; rot[2 * NL + lane] = b.sd; rot[3 * NL + lane] = b.cd; rot[4 * NL + lane] = b.sw;
+    rot[5 * NL + lane] = b.cw;
+}
+
 template <int P, int NCTX>
 __global__ void __launch_bounds__((P + 3 * NCTX) * 32, 1)
 nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, const __grid_constant__ DevTxQueue q, size_t n,
@@ -505,6 +537,11 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
     static_assert(P <= NYXB_TX_MAXP && NCTX >= 1 && NCTX <= 2, "walker positions / set contexts");
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long tma_bar;
+    // READY[context][parity]: "the walker inputs of the next stage with this parity are published" — an mbarrier (32 arrivals: the
+    // lanes of the context's lead helper) rather than a named barrier, because the walkers POLL it: a walker warp takes whichever
+    // context has a stage ready, so the serial stretch between two step attempts of one set (error norm, controller, commit,
+    // first prologue) is covered by the other set's stages instead of stalling the walkers.
+    __shared__ __align__(8) unsigned long long ready_bar[NCTX][2];
     __shared__ int s_set[NCTX], s_fresh[NCTX], s_exit[NCTX], s_all_done[NCTX], s_slice_end[NCTX];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     constexpr int NT_RW = (P + 3) * 32;   // threads on a READY / DONE barrier: the walkers + the three helpers of the context
@@ -522,7 +559,11 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
     if (tid == 0) {
         tx_mbar_init(&tma_bar, 1);
 #pragma unroll
-        for (int c = 0; c < NCTX; ++c) s_exit[c] = 0;
+        for (int c = 0; c < NCTX; ++c) {
+            s_exit[c] = 0;
+            tx_mbar_init(&ready_bar[c][0], 32);
+            tx_mbar_init(&ready_bar[c][1], 32);
+        }
     }
     __syncthreads();
     if (tid == 0) {
@@ -541,16 +582,30 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
         const int* my = sched + w * (2 + 2 * Tx.kmax);
         const int rec_off = my[0], ncol = my[1];
         unsigned active = (1u << NCTX) - 1u;
-        int stage[NCTX];
-#pragma unroll
-        for (int c = 0; c < NCTX; ++c) stage[c] = 0;
+        unsigned phases = 0;   // bit 2c + par: parity of the READY[c][par] phase this warp waits for next
+        int stage0 = 0, stage1 = 0, pref = 0;
         while (active) {
+            {
+                // pick a context whose next stage is published: the one not served last first
+                int c = -1, par = 0;
+                for (;;) {
 #pragma unroll
-            for (int c = 0; c < NCTX; ++c) {
-                if (!((active >> c) & 1u)) continue;
-                const int par = stage[c] & 1;
-                nb_sync(1 + c * BAR_PER_CTX + 1 + par, NT_RW);   // READY[par]: this stage's inputs of context c are published
-                if (stage[c] == 0 && *(volatile int*)&s_exit[c]) { active &= ~(1u << c); continue; }
+                    for (int k = 0; k < NCTX; ++k) {
+                        const int cc = (pref + k) % NCTX;
+                        if (c >= 0 || !((active >> cc) & 1u)) continue;
+                        const int pp = (cc == 0 ? stage0 : stage1) & 1;
+                        const bool ok = tx_mbar_test(&ready_bar[cc][pp], (phases >> (2 * cc + pp)) & 1u);
+                        if (__all_sync(FULL, ok)) { c = cc; par = pp; }
+                    }
+                    if (c >= 0) break;
+                    __nanosleep(20);
+                }
+                phases ^= 1u << (2 * c + par);
+                const int st = (c == 0) ? stage0 : stage1;
+                if (st == 0 && *(volatile int*)&s_exit[c]) { active &= ~(1u << c); continue; }
+                const int stn = (st + 1 == stages) ? 0 : st + 1;
+                if (c == 0) stage0 = stn; else stage1 = stn;
+                pref = (c + 1) % NCTX;
                 const TxSm sm = tx_views(smem, L, c, N);
                 const double* wk = sm.wk + par * WK_COUNT * NL + lane;
                 const double ub = wk[WK_UB * NL], r2 = wk[WK_R2 * NL];
@@ -597,7 +652,6 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                 double* pt = sm.part + ((par * P + w) * 4) * NL + lane;
                 pt[0] = X; pt[NL] = Y; pt[2 * NL] = Z; pt[3 * NL] = W;
                 nb_arrive(1 + c * BAR_PER_CTX + 3 + par, NT_RW);   // DONE[par]: the partial sums of this position are in shared memory
-                stage[c] = (stage[c] + 1 == stages) ? 0 : stage[c] + 1;
             }
         }
         return;
@@ -606,7 +660,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
     // =================================================================================================== HELPER
     const int c = (w - P) / 3, j = (w - P) % 3;   // set context, helper index: owns state components j (position) and j + 3 (velocity)
     const TxSm sm = tx_views(smem, L, c, N);
-    const int BAR_HB = 1 + c * BAR_PER_CTX, BAR_READY = BAR_HB + 1, BAR_DONE = BAR_HB + 3;
+    const int BAR_HB = 1 + c * BAR_PER_CTX, BAR_DONE = BAR_HB + 3;
     const DevGrav& gv = S.grav;
     const bool has_extra = S.n_bodies > 0 || S.has_srp || S.has_drag || S.n_xgrav > 0;
     const bool lead = (j == 0);   // helper 0 also runs the DCM, the stage prologues, the controller and the set queue of its context
@@ -637,7 +691,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
         }
         nb_sync(BAR_HB, 96);
         if (s_exit[c]) {
-            nb_arrive(BAR_READY + 0, NT_RW);   // releases the walkers (they expect stage 0), which read s_exit and drop this context
+            if (lead) tx_mbar_arrive(&ready_bar[c][0]);   // releases the walkers (they expect stage 0), which read s_exit and drop this context
             return;
         }
         const int set = s_set[c];
@@ -660,6 +714,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
             const bool done = sm.i32[TXW_FLAGS * NL + lane] & F_DONE;
             const bool all = __all_sync(FULL, done);
             if (lane == 0) { s_all_done[c] = all; s_slice_end[c] = 0; }
+            if (gv.rot.kind != 0) tx_rot_store(sm.rot, lane, tx_rot_base(gv.rot, sm.i64[TXI_EPOCH * NL + lane]));
         }
         nb_sync(BAR_HB, 96);
 
@@ -668,28 +723,30 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
             const double h = sm.f64[TXF_H * NL + lane];
             const long long epoch = sm.i64[TXI_EPOCH * NL + lane];
             const double r_own = sm.ycur[j * NL + lane], v_own = sm.ycur[(3 + j) * NL + lane];
-            // orientation angles at the step epoch (lead only: it evaluates every DCM of the attempt)
+            // orientation angles at the step epoch (the lead evaluates every DCM of the attempt).  They are NOT evaluated here, on the
+            // serial path between two attempts: helper 1 evaluates them for the epoch this attempt leads to while the walkers are
+            // busy, and commits them to sm.rot when the controller accepts the step (a rejected step keeps its epoch).
             TxRotBase rb_;
             rb_.sa = 0.0; rb_.ca = 1.0; rb_.sd = 1.0; rb_.cd = 0.0; rb_.sw = 0.0; rb_.cw = 1.0;
-            if (lead && gv.rot.kind != 0) {
-                const double t_s = dur_to_seconds(epoch);
-                const double d = t_s / 86400.0;
-                const double Tc = d / 36525.0;
-                det_sincos((gv.rot.ra0 + gv.rot.ra1 * Tc) * NYXB_DEG2RAD, rb_.sa, rb_.ca);
-                det_sincos((gv.rot.dec0 + gv.rot.dec1 * Tc) * NYXB_DEG2RAD, rb_.sd, rb_.cd);
-                det_sincos(fmod(gv.rot.w0 + gv.rot.w1 * d, 360.0) * NYXB_DEG2RAD, rb_.sw, rb_.cw);
-            }
+            TxRotBase rb_next = rb_;
+            const bool fixed = sm.i32[TXW_FLAGS * NL + lane] & F_FIXED;
+            // candidate state and error estimate (instance.rs:402-414), accumulated stage by stage in the reference's order
+            double nx_r = r_own, nx_v = v_own, er_r = 0.0, er_v = 0.0;
             int rc_acc = 0;
             double Rn[9];
             // ---- prime the pipeline: stage 0 (the state itself) and stage 1 (needs only V_0 = v): instance.rs:369-394
             sm.kst[(0 * 6 + j) * NL + lane] = v_own;                 // k_0[j] = V_0
             sm.ysp[(0 * 3 + j) * NL + lane] = r_own;                 // P_0
             nb_sync(BAR_HB, 96);
+            if (lead && gv.rot.kind != 0) {
+                rb_.sa = sm.rot[lane]; rb_.ca = sm.rot[NL + lane]; rb_.sd = sm.rot[2 * NL + lane]; rb_.cd = sm.rot[3 * NL + lane];
+                rb_.sw = sm.rot[4 * NL + lane]; rb_.cw = sm.rot[5 * NL + lane];
+            }
             if (lead) {
                 tx_dcm(gv.rot, rb_, 0, Rn);
                 tx_prologue(S, sm, lane, 0, sm.ysp, Rn, epoch);
             }
-            nb_arrive(BAR_READY + 0, NT_RW);
+            if (lead) tx_mbar_arrive(&ready_bar[c][0]);
             if (stages > 1) {
                 const long long off1 = dur_from_seconds(S.tb.c[0] * h);
                 sm.ysp[(1 * 3 + j) * NL + lane] = fma(h, ta[0] * v_own, r_own);   // P_1 = r + h a_10 V_0
@@ -698,7 +755,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                     tx_dcm(gv.rot, rb_, off1, Rn);
                     tx_prologue(S, sm, lane, 1, sm.ysp + 3 * NL, Rn, epoch + off1);
                 }
-                nb_arrive(BAR_READY + 1, NT_RW);
+                if (lead) tx_mbar_arrive(&ready_bar[c][1]);
             }
             // ---- derive(): the stages of one attempt for the 32 trajectories (instance.rs:358-493), one walk ahead of the walkers
             for (int i = 0; i < stages; ++i) {
@@ -706,6 +763,13 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                 // -- slack: everything that does not need the acceleration of stage i
                 double preV = 0.0, preP = 0.0;
                 long long off2 = 0;
+                {
+                    const double vi = sm.kst[(i * 6 + j) * NL + lane];   // V_i
+                    if (!fixed) er_r = fma(h * S.tb.e[i], vi, er_r);
+                    nx_r = fma(h * S.tb.b[i], vi, nx_r);
+                }
+                if (j == 1 && i == 0 && gv.rot.kind != 0)
+                    rb_next = tx_rot_base(gv.rot, epoch + (fixed ? sm.i64[TXI_STEP * NL + lane] : dur_from_seconds(h)));
                 if (i + 1 < stages) {   // V_{i+1} = v + h sum_{l<=i} a_{i+1,l} A_l: all terms but the last
                     const double* arow = ta + i * NYXB_MAX_STAGES;
                     const double* kc = sm.kst + (3 + j) * NL + lane;
@@ -760,6 +824,8 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                     if (rcx && !rc_acc) rc_acc = rcx | ((i + 1) << 8);
                 }
                 sm.kst[(i * 6 + 3 + j) * NL + lane] = acc;     // k_i[3+j] = A_i
+                if (!fixed) er_v = fma(h * S.tb.e[i], acc, er_v);
+                nx_v = fma(h * S.tb.b[i], acc, nx_v);
                 if (i + 1 < stages) {
                     const double vn = fma(h, fma(ta[i * NYXB_MAX_STAGES + i], acc, preV), v_own);   // V_{i+1}
                     sm.kst[((i + 1) * 6 + j) * NL + lane] = vn;                                    // k_{i+1}[j]
@@ -768,27 +834,13 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                     nb_sync(BAR_HB, 96);   // V_{i+1} and the position components of stage i+2 of all three helpers are in shared memory
                     if (i + 2 < stages) {
                         if (lead) tx_prologue(S, sm, lane, par, sm.ysp + par * 3 * NL, Rn, epoch + off2);
-                        nb_arrive(BAR_READY + par, NT_RW);   // walker inputs of stage i+2 are published
+                        if (lead) tx_mbar_arrive(&ready_bar[c][par]);   // walker inputs of stage i+2 are published
                     }
                 }
             }
-            // ---- candidate state and error estimate of this attempt (instance.rs:402-414)
-            {
-                const bool fixed = sm.i32[TXW_FLAGS * NL + lane] & F_FIXED;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int cc = j + 3 * half;
-                    double nx = sm.ycur[cc * NL + lane], er = 0.0;
-                    for (int i = 0; i < stages; ++i) {
-                        const double ki = sm.kst[(i * 6 + cc) * NL + lane];
-                        if (!fixed) er = fma(h * S.tb.e[i], ki, er);
-                        nx = fma(h * S.tb.b[i], ki, nx);
-                    }
-                    sm.nxt[cc * NL + lane] = nx;
-                    sm.er[cc * NL + lane] = er;
-                }
-                if (lead) sm.i32[TXW_RCST * NL + lane] = rc_acc;
-            }
+            sm.nxt[j * NL + lane] = nx_r; sm.nxt[(3 + j) * NL + lane] = nx_v;
+            sm.er[j * NL + lane] = er_r; sm.er[(3 + j) * NL + lane] = er_v;
+            if (lead) sm.i32[TXW_RCST * NL + lane] = rc_acc;
             nb_sync(BAR_HB, 96);
             if (lead) {
                 tx_controller(S, sink, sm, lane, n, tr, stages);
@@ -800,6 +852,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
             }
             nb_sync(BAR_HB, 96);
             if (sm.i32[TXW_ACC * NL + lane]) {
+                if (j == 1 && gv.rot.kind != 0) tx_rot_store(sm.rot, lane, rb_next);   // read by the lead after the next HB barrier
                 const long long ns = sm.i64[TXI_NSTEPS * NL + lane];
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
