@@ -47,7 +47,8 @@ enum { TXW_FLAGS = 0, TXW_STATUS, TXW_RC, TXW_ATT, TXW_EVCNT, TXW_ACC, TXW_RCST,
 enum { F_FIXED = 1, F_PREVFIXED = 2, F_RETRY = 4, F_LAST = 8, F_DONE = 16, F_BACK = 32, F_VALID = 64 };
 
 // dynamic shared memory: [table blob | NCTX set contexts]; one context (buffers of consecutive stages alternate by parity):
-//   wk   [2][5][32]      walker inputs of a stage: ub, r2, z = (cos, sin)(lambda) cos(phi), rho   (lead helper -> walkers)
+//   wk   [2][20][32]     walker inputs of a stage: ub, r2, and z^(2^k), rho^(2^k) for k = 0..5 with z = (cos, sin)(lambda) cos(phi)
+//                        (lead helper -> walkers)
 //   part [2][P][4][32]   partial sums of a stage                                                   (walkers -> helpers)
 //   as   [2][18][32]     what the helpers need to assemble that stage's acceleration later (DCM, unit vector, K0, K1, two-body factor, position)
 //   ysp  [2][3][32]      position components of a coming stage, exchanged between the three helpers
@@ -63,7 +64,7 @@ __host__ __device__ inline TxLayout tx_layout(unsigned blob_bytes, int P, int N,
     L.blob = 0;
     L.ctx0 = (blob_bytes + 127u) & ~127u;
     unsigned o = 0;
-    L.wk = o; o += 2u * 5u * NL * 8;
+    L.wk = o; o += 2u * 20u * NL * 8;
     L.part = o; o += 2u * (unsigned)P * 4 * NL * 8;
     L.as = o; o += 2u * 18u * NL * 8;
     L.ysp = o; o += 2u * 3u * NL * 8;
@@ -196,19 +197,13 @@ __device__ __forceinline__ void tx_column(const double2*& A, const double*& K, d
     double S5 = Q * pd1, S6 = Q * pd2;                     // the column's seed W term
     double2 b01, b23;
     double bk;
-    int e = len;
-    for (; e >= 2; e -= 2) {
+#pragma unroll 2
+    for (int e = len; e > 0; e -= 2) {   // columns are padded to an even number of entries (null records)
         b01 = A[2]; b23 = A[3]; bk = K[1];
         NYXB_TX_ENTRY(a01, a23, kk)
         a01 = A[4]; a23 = A[5]; kk = K[2];   // the table ends with null records
         NYXB_TX_ENTRY(b01, b23, bk)
         A += 4; K += 2;
-    }
-    if (e) {
-        b01 = A[2]; b23 = A[3]; bk = K[1];
-        NYXB_TX_ENTRY(a01, a23, kk)
-        A += 2; K += 1;
-        a01 = b01; a23 = b23; kk = bk;
     }
     // close the column: apply its (cos, sin)((m-1) lambda) cos^(m-1)(phi)
     X = fma(rr, S1, fma(ii, S2, X));
@@ -453,7 +448,8 @@ __device__ __noinline__ void tx_park_ctl(const DevSink& sink, const DevTxQueue& 
 // ---- prologue of stage q for the 32 trajectories of a set, run by the lead helper: body-fixed position, 1/r, the recursion
 // scalars the walkers need, and everything the three helpers need to assemble the acceleration of that stage later
 enum { AS_R = 0, AS_S = 9, AS_T, AS_U, AS_K0, AS_K1, AS_FAC, AS_P0, AS_P1, AS_P2, AS_COUNT };
-enum { WK_UB = 0, WK_R2, WK_ZR, WK_ZI, WK_RHO, WK_COUNT };
+enum { WK_UB = 0, WK_R2, WK_POW, WK_COUNT = WK_POW + 18 };   // WK_POW + 3k: Re z^(2^k), Im z^(2^k), rho^(2^k)
+template <int NPOW>
 __device__ __forceinline__ void tx_prologue(const DevSetup& S, const TxSm& sm, int lane, int par, const double* ysp, const double (&R)[9],
                                             long long t_ns) {
     const DevGrav& gv = S.grav;
@@ -472,7 +468,16 @@ __device__ __forceinline__ void tx_prologue(const DevSetup& S, const TxSm& sm, i
     const double rho = gv.r_eq * inv_r;
     const double s_ = rb0 * inv_r, t_ = rb1 * inv_r, u_ = rb2 * inv_r;
     double* wk = sm.wk + par * WK_COUNT * NL + lane;
-    wk[WK_UB * NL] = u_ * rho; wk[WK_R2 * NL] = rho * rho; wk[WK_ZR * NL] = s_; wk[WK_ZI * NL] = t_; wk[WK_RHO * NL] = rho;
+    wk[WK_UB * NL] = u_ * rho; wk[WK_R2 * NL] = rho * rho;
+    {   // z^(2^k), rho^(2^k): the walkers assemble z^e, rho^(e+1) of their columns from these (one multiplication per set bit of e)
+        double zr = s_, zi = t_, rp = rho;
+#pragma unroll
+        for (int k = 0; k < NPOW; ++k) {
+            wk[(WK_POW + 3 * k) * NL] = zr; wk[(WK_POW + 3 * k + 1) * NL] = zi; wk[(WK_POW + 3 * k + 2) * NL] = rp;
+            const double nr = fma(zr, zr, -(zi * zi));
+            zi = 2.0 * zr * zi; zr = nr; rp *= rp;
+        }
+    }
     double* as = sm.as + par * AS_COUNT * NL + lane;
 #pragma unroll
     for (int k = 0; k < 9; ++k) as[(AS_R + k) * NL] = R[k];
@@ -528,6 +533,28 @@ __device__ __forceinline__ void tx_rot_store(double* rot, int lane, const TxRotB
     rot[5 * NL + lane] = b.cw;
 }
 
+// z^W, rho^(W+1) (sequence a) and z^(2^NB - 1 - W), rho^(2^NB - W) (sequence b) from the published z^(2^k), rho^(2^k): W and its
+// complement split the NB powers between them; the first factor of each product is a copy
+template <int W, int NB>
+__device__ __forceinline__ void tx_start_powers(const double* wk, double& zar, double& zai, double& pa, double& zbr, double& zbi, double& pb) {
+    const double rho = wk[(WK_POW + 2) * NL];
+    bool fa = true, fb = true;
+    zar = 1.0; zai = 0.0; zbr = 1.0; zbi = 0.0; pa = rho; pb = rho;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        const double br = wk[(WK_POW + 3 * k) * NL], bi = wk[(WK_POW + 3 * k + 1) * NL], bp = wk[(WK_POW + 3 * k + 2) * NL];
+        if ((W >> k) & 1) {
+            if (fa) { zar = br; zai = bi; fa = false; }
+            else { const double nr = fma(zar, br, -(zai * bi)); zai = fma(zar, bi, zai * br); zar = nr; }
+            pa *= bp;
+        } else {
+            if (fb) { zbr = br; zbi = bi; fb = false; }
+            else { const double nr = fma(zbr, br, -(zbi * bi)); zbi = fma(zbr, bi, zbi * br); zbr = nr; }
+            pb *= bp;
+        }
+    }
+}
+
 template <int P, int NCTX>
 __global__ void __launch_bounds__((P + 3 * NCTX) * 32, 1)
 nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, const __grid_constant__ DevTxQueue q, size_t n,
@@ -544,6 +571,8 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
     __shared__ __align__(8) unsigned long long ready_bar[NCTX][2];
     __shared__ int s_set[NCTX], s_fresh[NCTX], s_exit[NCTX], s_all_done[NCTX], s_slice_end[NCTX];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    constexpr int NPOW = (P == 8) ? 5 : 6;   // z^(2^k), k < NPOW: bits of the exponents below 2P, and the common ratio z^(2P)
+    static_assert(P == 8 || P == 16, "2P must be a power of two");
     constexpr int NT_RW = (P + 3) * 32;   // threads on a READY / DONE barrier: the walkers + the three helpers of the context
     // named barriers of context c: HB (helpers among themselves), READY[parity], DONE[parity]
     constexpr int BAR_PER_CTX = 5;
@@ -610,44 +639,44 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                 const double* wk = sm.wk + par * WK_COUNT * NL + lane;
                 const double ub = wk[WK_UB * NL], r2 = wk[WK_R2 * NL];
                 // z^e = (cos, sin)(e lambda) cos^e(phi) and rho^(e+1) for the two interleaved exponent sequences of this position:
-                // e = w + 2P j (za, pa) and e = 2P-1-w + 2P j (zb, pb); binary powering with warp-uniform bits, the squarings end at
-                // the common ratio z^(2P), rho^(2P)
-                double br = wk[WK_ZR * NL], bi = wk[WK_ZI * NL], bp = wk[WK_RHO * NL];
-                double zar = 1.0, zai = 0.0, zbr = 1.0, zbi = 0.0, pa = bp, pb = bp;
-                const int ea = w, eb = 2 * P - 1 - w;
-#pragma unroll
-                for (int bit = 1; bit < 2 * P; bit <<= 1) {
-                    if (ea & bit) {
-                        const double nr = fma(zar, br, -(zai * bi));
-                        zai = fma(zar, bi, zai * br); zar = nr; pa *= bp;
-                    }
-                    if (eb & bit) {
-                        const double nr = fma(zbr, br, -(zbi * bi));
-                        zbi = fma(zbr, bi, zbi * br); zbr = nr; pb *= bp;
-                    }
-                    const double nb = fma(br, br, -(bi * bi));
-                    bi = 2.0 * br * bi; br = nb; bp *= bp;
+                // e = w + 2P j (za, pa) and e = 2P-1-w + 2P j (zb, pb).  The two start exponents are bit complements: every published
+                // power z^(2^k) goes into exactly one of them (warp-uniform choice).
+                double zar, zai, zbr, zbi, pa, pb;
+                switch (w) {   // one specialised copy per position: the choices below are compile-time there
+#define NYXB_TX_CASE(WW) case WW: tx_start_powers<WW, NPOW - 1>(wk, zar, zai, pa, zbr, zbi, pb); break;
+                    NYXB_TX_CASE(0) NYXB_TX_CASE(1) NYXB_TX_CASE(2) NYXB_TX_CASE(3) NYXB_TX_CASE(4) NYXB_TX_CASE(5) NYXB_TX_CASE(6) NYXB_TX_CASE(7)
+                    default:
+                        if constexpr (P == 16) {
+                            switch (w) {
+                                NYXB_TX_CASE(8) NYXB_TX_CASE(9) NYXB_TX_CASE(10) NYXB_TX_CASE(11) NYXB_TX_CASE(12) NYXB_TX_CASE(13) NYXB_TX_CASE(14)
+                                default: tx_start_powers<15, NPOW - 1>(wk, zar, zai, pa, zbr, zbi, pb); break;
+                            }
+                        } else {
+                            tx_start_powers<7, NPOW - 1>(wk, zar, zai, pa, zbr, zbi, pb);
+                        }
+                        break;
+#undef NYXB_TX_CASE
                 }
+                const double qr = wk[(WK_POW + 3 * (NPOW - 1)) * NL], qi = wk[(WK_POW + 3 * (NPOW - 1) + 1) * NL];   // z^(2P)
+                const double qp = wk[(WK_POW + 3 * (NPOW - 1) + 2) * NL];                                            // rho^(2P)
                 double X = 0.0, Y = 0.0, Z = 0.0, W = 0.0;
                 const double2* A = recA + 2 * rec_off;
                 const double* K = recK + rec_off;
                 double2 a01 = A[0], a23 = A[1];
                 double kk = K[0];
-                for (int k = 0; k < ncol; k += 2) {
-                    {   // column of the first sequence
-                        const int m = my[2 + 2 * k], len = my[3 + 2 * k];
-                        const double* sd = colseed + 4 * m;
-                        tx_column(A, K, a01, a23, kk, len, pa * sd[0], sd[1], sd[2], sd[3], ub, r2, zar, zai, X, Y, Z, W);
-                        const double nr = fma(zar, br, -(zai * bi));
-                        zai = fma(zar, bi, zai * br); zar = nr; pa *= bp;
-                    }
-                    if (k + 1 < ncol) {   // column of the second sequence
-                        const int m = my[4 + 2 * k], len = my[5 + 2 * k];
-                        const double* sd = colseed + 4 * m;
-                        tx_column(A, K, a01, a23, kk, len, pb * sd[0], sd[1], sd[2], sd[3], ub, r2, zbr, zbi, X, Y, Z, W);
-                        const double nr = fma(zbr, br, -(zbi * bi));
-                        zbi = fma(zbr, bi, zbi * br); zbr = nr; pb *= bp;
-                    }
+                // one loop over the columns; the roles of the two sequences are swapped after every column.  The seeds of the next
+                // column are fetched before the current one is walked.
+                int len = my[3];
+                double4 sd = *reinterpret_cast<const double4*>(colseed + 4 * my[2]);
+                for (int k = 0; k < ncol; ++k) {
+                    const int len_n = my[5 + 2 * k];   // the schedule rows end with a null column
+                    const double4 sd_n = *reinterpret_cast<const double4*>(colseed + 4 * my[4 + 2 * k]);
+                    tx_column(A, K, a01, a23, kk, len, pa * sd.x, sd.y, sd.z, sd.w, ub, r2, zar, zai, X, Y, Z, W);
+                    const double nr = fma(zar, qr, -(zai * qi));
+                    const double ni = fma(zar, qi, zai * qr), np = pa * qp;
+                    zar = zbr; zai = zbi; pa = pb;
+                    zbr = nr; zbi = ni; pb = np;
+                    len = len_n; sd = sd_n;
                 }
                 double* pt = sm.part + ((par * P + w) * 4) * NL + lane;
                 pt[0] = X; pt[NL] = Y; pt[2 * NL] = Z; pt[3 * NL] = W;
@@ -744,7 +773,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
             }
             if (lead) {
                 tx_dcm(gv.rot, rb_, 0, Rn);
-                tx_prologue(S, sm, lane, 0, sm.ysp, Rn, epoch);
+                tx_prologue<NPOW>(S, sm, lane, 0, sm.ysp, Rn, epoch);
             }
             if (lead) tx_mbar_arrive(&ready_bar[c][0]);
             if (stages > 1) {
@@ -753,7 +782,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                 nb_sync(BAR_HB, 96);
                 if (lead) {
                     tx_dcm(gv.rot, rb_, off1, Rn);
-                    tx_prologue(S, sm, lane, 1, sm.ysp + 3 * NL, Rn, epoch + off1);
+                    tx_prologue<NPOW>(S, sm, lane, 1, sm.ysp + 3 * NL, Rn, epoch + off1);
                 }
                 if (lead) tx_mbar_arrive(&ready_bar[c][1]);
             }
@@ -833,7 +862,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                         sm.ysp[(par * 3 + j) * NL + lane] = fma(h, fma(ta[(i + 1) * NYXB_MAX_STAGES + i + 1], vn, preP), r_own);   // P_{i+2}
                     nb_sync(BAR_HB, 96);   // V_{i+1} and the position components of stage i+2 of all three helpers are in shared memory
                     if (i + 2 < stages) {
-                        if (lead) tx_prologue(S, sm, lane, par, sm.ysp + par * 3 * NL, Rn, epoch + off2);
+                        if (lead) tx_prologue<NPOW>(S, sm, lane, par, sm.ysp + par * 3 * NL, Rn, epoch + off2);
                         if (lead) tx_mbar_arrive(&ready_bar[c][par]);   // walker inputs of stage i+2 are published
                     }
                 }
@@ -941,7 +970,9 @@ void nyxb_tx_build_host(int N, int M, const double* c_nm, const double* s_nm, in
         return g;
     };
     const int mcols = std::min(M + 1, N + 1);   // columns m = 1..mcols
-    auto col_len = [&](int m) { return std::max(N + 1 - m, 1); };   // entries n = m..N; column N+1 keeps one null entry (seed W term)
+    // entries n = m..N, padded with null records to an even count (the walk takes two entries per iteration); column N+1 is all
+    // null entries (only its seed W term counts)
+    auto col_len = [&](int m) { return (std::max(N + 1 - m, 1) + 1) & ~1; };
     std::vector<std::vector<int>> cols(P);
     for (int m = 1; m <= mcols; ++m) {
         const int r = (m - 1) % (2 * P);
@@ -950,6 +981,7 @@ void nyxb_tx_build_host(int N, int M, const double* c_nm, const double* s_nm, in
     out.P = P;
     out.kmax = 1;
     for (auto& cl : cols) out.kmax = std::max(out.kmax, (int)cl.size());
+    out.kmax += 1;   // every schedule row ends with a null column (m = 0, len = 0): the walk prefetches the next column's seeds
     out.n_rec = 0;
     for (int m = 1; m <= mcols; ++m) out.n_rec += col_len(m);
     out.recA.assign((size_t)(out.n_rec + 1) * 4, 0.0);
@@ -982,8 +1014,8 @@ void nyxb_tx_build_host(int N, int M, const double* c_nm, const double* s_nm, in
             auto kappa = [&](int n) -> double {   // W term of degree n = kappa * (Z term of degree n-1), n > m
                 return (double)(((long double)vr11(n - 1, m - 1) * scale(n, m)) / ((long double)vr01(n - 1, m - 1) * scale(n - 1, m)));
             };
-            for (int n = m; n <= std::max(N, m); ++n, ++e) {
-                if (n > N) continue;   // null entry of column N+1
+            for (int n = m; n < m + col_len(m); ++n, ++e) {
+                if (n > N) continue;   // null entry (padding, column N+1)
                 const long double sc_ = scale(n, m);
                 double* a = &out.recA[(size_t)e * 4];
                 a[0] = (double)(sc_ * sqrt2 * (double)m * C(n, m));
@@ -999,7 +1031,7 @@ void nyxb_tx_build_host(int N, int M, const double* c_nm, const double* s_nm, in
 // set contexts per CTA: two sets in flight while both fit beside the table (P = 8: degrees up to ~40), one otherwise
 static int tx_contexts(const DevSetup* S, const DevTx* Tx, size_t* smem_bytes) {
     const TxBlob b = tx_blob(S->grav.N, Tx->P, Tx->n_rec, Tx->kmax);
-    for (int nctx = (Tx->P <= 12 ? 2 : 1); nctx >= 1; --nctx) {
+    for (int nctx = (Tx->P == 8 ? 2 : 1); nctx >= 1; --nctx) {
         const size_t smem = tx_layout(b.bytes, Tx->P, S->grav.N, nctx).total;
         if (smem <= 227 * 1024) { if (smem_bytes) *smem_bytes = smem; return nctx; }
     }
@@ -1008,7 +1040,7 @@ static int tx_contexts(const DevSetup* S, const DevTx* Tx, size_t* smem_bytes) {
 
 // set contexts one SM holds for this setup (one persistent CTA per SM; 0: the tables do not fit) and its dynamic shared memory
 extern "C" int nyxb_tx_occupancy(const DevSetup* S, const DevTx* Tx, size_t* smem_bytes) {
-    if (Tx->P != 8 && Tx->P != 12 && Tx->P != 16) return 0;
+    if (Tx->P != 8 && Tx->P != 16) return 0;
     return tx_contexts(S, Tx, smem_bytes);
 }
 
@@ -1024,7 +1056,6 @@ extern "C" cudaError_t nyxb_launch_tx(const DevSetup* S, const DevTx* Tx, const 
     if (nctx < 1 || grid < 1) return cudaErrorInvalidConfiguration;
 #define NYXB_TX_GO(PP, CC) tx_launch_p<PP, CC>(S, Tx, q, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_status, sink, grid, smem, b.bytes, b.off_recK, b.off_seed, b.off_sched, stream)
     if (Tx->P == 8) return nctx == 2 ? NYXB_TX_GO(8, 2) : NYXB_TX_GO(8, 1);
-    if (Tx->P == 12) return nctx == 2 ? NYXB_TX_GO(12, 2) : NYXB_TX_GO(12, 1);
     if (Tx->P == 16) return NYXB_TX_GO(16, 1);
     return cudaErrorInvalidValue;
 #undef NYXB_TX_GO

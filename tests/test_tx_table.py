@@ -1,6 +1,7 @@
 """Host logic of the transposed kernel (csrc/nyxb_tx.cu), checked on the CPU: the zigzag column -> position schedule and the
 records of `nyxb_tx_build_host` are walked here exactly as `nyxb_k_tx` walks them — binary powering with the position's two
-interleaved exponent sequences, one complex multiplication per column, the W term taken one entry late from the previous record —
+interleaved exponent sequences assembled from z^(2^k), one complex multiplication per column, recursion coefficients advanced by
+additions, columns padded to an even number of entries —
 and the resulting acceleration is compared with the oracle's `GravityField::eom` restatement (gravity_field.rs:148-268).
 No device is needed: `nyxb_tx_table_dump` is host-only."""
 import ctypes as C
@@ -34,50 +35,45 @@ def _walk(gf, P, tables, rb):
     rho = gf.r_eq_km * inv_r
     ub, r2 = rb[2] * inv_r * rho, rho * rho
     X = Y = Z = W = 0.0
+    nbits = (2 * P).bit_length() - 1
+    zp = [complex(rb[0] * inv_r, rb[1] * inv_r)]
+    rp = [rho]
+    for _ in range(nbits):
+        zp.append(zp[-1] * zp[-1]); rp.append(rp[-1] * rp[-1])
     for w in range(P):
-        # powers: za = z^w, zb = z^(2P-1-w), pa = rho^(w+1), pb = rho^(2P-w); squarings end at z^(2P), rho^(2P)
-        b, bp = complex(rb[0] * inv_r, rb[1] * inv_r), rho
+        # za = z^w, zb = z^(2P-1-w), pa = rho^(w+1), pb = rho^(2P-w): each published power z^(2^k) goes into exactly one of them
         za = zb = complex(1.0, 0.0)
         pa = pb = rho
-        ea, eb = w, 2 * P - 1 - w
-        bit = 1
-        while bit < 2 * P:
-            if ea & bit:
-                za *= b; pa *= bp
-            if eb & bit:
-                zb *= b; pb *= bp
-            b *= b; bp *= bp
-            bit <<= 1
+        for k in range(nbits):
+            if (w >> k) & 1:
+                za *= zp[k]; pa *= rp[k]
+            else:
+                zb *= zp[k]; pb *= rp[k]
         e = int(sched[w, 0])
         for k in range(int(sched[w, 1])):
             m, ln = int(sched[w, 2 + 2 * k]), int(sched[w, 3 + 2 * k])
-            z, pr = (za, pa) if k % 2 == 0 else (zb, pb)
-            assert abs(z - complex(rb[0] * inv_r, rb[1] * inv_r) ** (m - 1)) < 1e-12 and abs(pr / rho ** m - 1.0) < 1e-12
-            Q, Qm1, al, be = pr * seed[m, 0], 0.0, seed[m, 3], 0.0
-            kp, p3p, p4p = 1.0, seed[m, 1], seed[m, 2]
-            S = [0.0] * 6
+            assert abs(za - zp[0] ** (m - 1)) < 1e-12 and abs(pa / rho ** m - 1.0) < 1e-12
+            Q = pa * seed[m, 0]
+            al = seed[m, 3]
+            c1, m2, d, g = al * ub, 0.0, 0.0, al * r2
+            S = [0.0, 0.0, 0.0, 0.0, Q * seed[m, 1], Q * seed[m, 2]]
             for _ in range(ln):
                 p1, p2, p3, p4 = recA[e]
                 ck = recK[e]
                 e += 1
-                Qn = al * ub * Q - be * r2 * Qm1
+                Qn = c1 * Q - m2
+                c1 += 2 * ub; d += g; g += 2 * r2
+                m2 = d * Q
                 S[0] += Q * p1; S[1] += Q * p2; S[2] += Q * p3; S[3] += Q * p4
-                wv = kp * Q
-                S[4] += wv * p3p; S[5] += wv * p4p
-                kp, p3p, p4p = ck, p3, p4
-                be += al; al += 2.0
-                Qm1, Q = Q, Qn
-            wv = kp * Q
-            S[4] += wv * p3p; S[5] += wv * p4p
-            rr, ii = z.real, z.imag
+                wv = ck * Qn
+                S[4] += wv * p3; S[5] += wv * p4
+                Q = Qn
+            rr, ii = za.real, za.imag
             X += rr * S[0] + ii * S[1]
             Y += rr * S[1] - ii * S[0]
             Z += rr * S[2] + ii * S[3]
             W += rr * S[4] + ii * S[5]
-            if k % 2 == 0:
-                za *= b; pa *= bp
-            else:
-                zb *= b; pb *= bp
+            za, zb, pa, pb = zb, za * zp[nbits], pb, pa * rp[nbits]
     s_, t_, u_ = rb * inv_r
     K0 = gf.mu_km3_s2 / gf.r_eq_km * inv_r
     K1 = K0 * rho
@@ -103,9 +99,10 @@ def test_transposed_table_reproduces_oracle_gravity(oracle, fixture, degree, ord
     ms, e = [], 0
     for w in range(P):
         assert sched[w, 0] == e
+        assert sched[w, 2 + 2 * sched[w, 1]] == 0 and sched[w, 3 + 2 * sched[w, 1]] == 0   # null column behind the last one
         for k in range(sched[w, 1]):
             m, ln = int(sched[w, 2 + 2 * k]), int(sched[w, 3 + 2 * k])
-            assert ln == max(degree + 1 - m, 1)
+            assert ln == (max(degree + 1 - m, 1) + 1) // 2 * 2
             assert (m - 1) == (w if k % 2 == 0 else 2 * P - 1 - w) + 2 * P * (k // 2)
             ms.append(m); e += ln
     assert e == n_rec and sorted(ms) == list(range(1, min(gf.order + 1, gf.degree + 1) + 1))
