@@ -456,9 +456,28 @@ static int32_t launch_tx(nyxb_engine* e, size_t n, const double* state, const do
     q.details = out_details ? out_details : reinterpret_cast<nyxb_details*>(ws + 32 * n);
     q.n_sets = (int)n_sets;
     q.slice = (n_sets > slots) ? e->tx_slice : 0;   // every set resident: no parking
+    q.trace = nullptr;
+#ifdef NYXB_TX_TRACE
+    // diagnostic build: timeline of CTA 0, dumped to $NYXB_TX_TRACE_FILE after the launch (synchronises the stream)
+    const size_t trace_bytes = (size_t)32 * NYXB_TX_TRACE_CAP * sizeof(unsigned long long);
+    const char* trace_file = getenv("NYXB_TX_TRACE_FILE");
+    if (trace_file) {
+        CUDA_TRY(cudaMalloc(&q.trace, trace_bytes));
+        CUDA_TRY(cudaMemsetAsync(q.trace, 0, trace_bytes, stream));
+    }
+#endif
     cudaError_t err = nyxb_launch_tx(&e->S, tx, &q, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io, out_state,
                                      (long long*)out_epoch, out_status, &sink, grid, stream);
     if (err != cudaSuccess) { set_err(std::string("kernel launch: ") + cudaGetErrorString(err)); return NYXB_RC_CUDA; }
+#ifdef NYXB_TX_TRACE
+    if (q.trace) {
+        std::vector<unsigned long long> host((size_t)32 * NYXB_TX_TRACE_CAP);
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        CUDA_TRY(cudaMemcpy(host.data(), q.trace, trace_bytes, cudaMemcpyDeviceToHost));
+        cudaFree(q.trace);
+        if (FILE* f = fopen(trace_file, "wb")) { fwrite(host.data(), 1, trace_bytes, f); fclose(f); }
+    }
+#endif
     e->launches += 1;
     e->last_kernel = NYXB_KERNEL_TRANSPOSED;
     return NYXB_RC_OK;

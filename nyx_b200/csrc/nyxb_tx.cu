@@ -142,6 +142,20 @@ __device__ __forceinline__ bool tx_mbar_test(unsigned long long* bar, unsigned p
     return ok != 0;
 }
 
+// Diagnostic timeline of CTA 0 (built with -DNYXB_TX_TRACE only; scripts/tx_trace.py reads it): lane 0 of every warp appends
+// (clock << 20 | code << 12 | context << 8 | stage) records to its own strip.
+enum { TR_POLL = 1, TR_WALK = 2, TR_WALK_END = 3, TR_DONE_WAIT = 4, TR_DONE_SEEN = 5, TR_READY = 6, TR_STAGES_END = 7, TR_CTRL_END = 8, TR_TOP = 9 };
+#ifdef NYXB_TX_TRACE
+#define TX_TRACE(code, ctx, stg)                                                                                              \
+    do {                                                                                                                      \
+        if (q.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && tr_n < NYXB_TX_TRACE_CAP)                                   \
+            q.trace[(size_t)(threadIdx.x >> 5) * NYXB_TX_TRACE_CAP + tr_n++] =                                                  \
+                ((unsigned long long)clock64() << 20) | ((unsigned long long)(code) << 12) | ((unsigned long long)(ctx) << 8) | (unsigned long long)(stg); \
+    } while (0)
+#else
+#define TX_TRACE(code, ctx, stg) do { } while (0)
+#endif
+
 // third bodies + SRP + drag for one trajectory (cold path of the harmonics-dominated ensembles this kernel serves)
 __device__ __noinline__ int tx_extra(const DevSetup& S, double dry_mass, double extra_mass, double srp_area, double drag_area,
                                      long long t_ns, const double y[9], double acc[3]) {
@@ -571,6 +585,9 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
     __shared__ __align__(8) unsigned long long ready_bar[NCTX][2];
     __shared__ int s_set[NCTX], s_fresh[NCTX], s_exit[NCTX], s_all_done[NCTX], s_slice_end[NCTX];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+#ifdef NYXB_TX_TRACE
+    int tr_n = 0;
+#endif
     constexpr int NPOW = (P == 8) ? 5 : 6;   // z^(2^k), k < NPOW: bits of the exponents below 2P, and the common ratio z^(2P)
     static_assert(P == 8 || P == 16, "2P must be a power of two");
     constexpr int NT_RW = (P + 3) * 32;   // threads on a READY / DONE barrier: the walkers + the three helpers of the context
@@ -617,6 +634,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
             {
                 // pick a context whose next stage is published: the one not served last first
                 int c = -1, par = 0;
+                TX_TRACE(TR_POLL, 0, 0);
                 for (;;) {
 #pragma unroll
                     for (int k = 0; k < NCTX; ++k) {
@@ -635,6 +653,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                 const int stn = (st + 1 == stages) ? 0 : st + 1;
                 if (c == 0) stage0 = stn; else stage1 = stn;
                 pref = (c + 1) % NCTX;
+                TX_TRACE(TR_WALK, c, st);
                 const TxSm sm = tx_views(smem, L, c, N);
                 const double* wk = sm.wk + par * WK_COUNT * NL + lane;
                 const double ub = wk[WK_UB * NL], r2 = wk[WK_R2 * NL];
@@ -681,6 +700,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                 double* pt = sm.part + ((par * P + w) * 4) * NL + lane;
                 pt[0] = X; pt[NL] = Y; pt[2 * NL] = Z; pt[3 * NL] = W;
                 nb_arrive(1 + c * BAR_PER_CTX + 3 + par, NT_RW);   // DONE[par]: the partial sums of this position are in shared memory
+                TX_TRACE(TR_WALK_END, c, st);
             }
         }
         return;
@@ -749,6 +769,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
 
         // ---------------------------------------------------------------- step attempts of this slice
         for (int it = 0; !s_all_done[c]; ++it) {
+            TX_TRACE(TR_TOP, c, 0);
             const double h = sm.f64[TXF_H * NL + lane];
             const long long epoch = sm.i64[TXI_EPOCH * NL + lane];
             const double r_own = sm.ycur[j * NL + lane], v_own = sm.ycur[(3 + j) * NL + lane];
@@ -776,6 +797,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                 tx_prologue<NPOW>(S, sm, lane, 0, sm.ysp, Rn, epoch);
             }
             if (lead) tx_mbar_arrive(&ready_bar[c][0]);
+            TX_TRACE(TR_READY, c, 0);
             if (stages > 1) {
                 const long long off1 = dur_from_seconds(S.tb.c[0] * h);
                 sm.ysp[(1 * 3 + j) * NL + lane] = fma(h, ta[0] * v_own, r_own);   // P_1 = r + h a_10 V_0
@@ -785,6 +807,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                     tx_prologue<NPOW>(S, sm, lane, 1, sm.ysp + 3 * NL, Rn, epoch + off1);
                 }
                 if (lead) tx_mbar_arrive(&ready_bar[c][1]);
+                TX_TRACE(TR_READY, c, 1);
             }
             // ---- derive(): the stages of one attempt for the 32 trajectories (instance.rs:358-493), one walk ahead of the walkers
             for (int i = 0; i < stages; ++i) {
@@ -819,7 +842,9 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                     off2 = dur_from_seconds(S.tb.c[i + 1] * h);
                     if (lead) tx_dcm(gv.rot, rb_, off2, Rn);
                 }
+                TX_TRACE(TR_DONE_WAIT, c, i);
                 nb_sync(BAR_DONE + par, NT_RW);   // the walkers' partial sums of stage i are back
+                TX_TRACE(TR_DONE_SEEN, c, i);
 
                 // -- reduce the partial sums, assemble the acceleration component j of stage i (spacecraft.rs:216-247)
                 double X, Y, Z, Wt;
@@ -864,9 +889,11 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                     if (i + 2 < stages) {
                         if (lead) tx_prologue<NPOW>(S, sm, lane, par, sm.ysp + par * 3 * NL, Rn, epoch + off2);
                         if (lead) tx_mbar_arrive(&ready_bar[c][par]);   // walker inputs of stage i+2 are published
+                        TX_TRACE(TR_READY, c, i + 2);
                     }
                 }
             }
+            TX_TRACE(TR_STAGES_END, c, 0);
             sm.nxt[j * NL + lane] = nx_r; sm.nxt[(3 + j) * NL + lane] = nx_v;
             sm.er[j * NL + lane] = er_r; sm.er[(3 + j) * NL + lane] = er_v;
             if (lead) sm.i32[TXW_RCST * NL + lane] = rc_acc;
@@ -880,6 +907,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                 if (lane == 0) { s_all_done[c] = all; s_slice_end[c] = slice_end; }
             }
             nb_sync(BAR_HB, 96);
+            TX_TRACE(TR_CTRL_END, c, 0);
             if (sm.i32[TXW_ACC * NL + lane]) {
                 if (j == 1 && gv.rot.kind != 0) tx_rot_store(sm.rot, lane, rb_next);   // read by the lead after the next HB barrier
                 const long long ns = sm.i64[TXI_NSTEPS * NL + lane];

@@ -51,7 +51,9 @@ struct DevTxQueue {
     int* ws_flags;                // [n]   fixed | retry << 1 | done << 2 | warn << 3 | rc << 8
     nyxb_details* details;        // [n]   never NULL inside the kernel (user buffer or engine scratch)
     int n_sets, slice;            // slice: step attempts per slice (0: run every set to completion)
+    unsigned long long* trace;    // diagnostic builds (-DNYXB_TX_TRACE) only: [warps of CTA 0][NYXB_TX_TRACE_CAP] timeline records
 };
+#define NYXB_TX_TRACE_CAP 8192
 enum { TXQ_FRESH = 0, TXQ_LOCK = 1, TXQ_HEAD = 2, TXQ_TAIL = 3 };
 
 extern "C" cudaError_t nyxb_launch_tx(const DevSetup* S, const DevTx* Tx, const DevTxQueue* q, size_t n, const double* state,

@@ -83,7 +83,7 @@ def test_dual_number_gradient_of_the_harmonics_against_finite_differences_of_the
         G_tb = -mu / r ** 3 * (np.eye(3) - 3.0 * np.outer(rb, rb) / r ** 2)
         got_h = A[3:6, 0:3] - G_tb
         assert np.abs(got_h - G_h).max() < 2e-6 * np.abs(G_h).max(), (got_h, G_h)
-        assert np.abs(A[3:6, 0:3] - (G_tb + G_h)).max() < 1e-9 * np.abs(G_tb).max()
+        assert np.abs(A[3:6, 0:3] - (G_tb + G_h)).max() < 1e-8 * np.abs(G_tb).max()   # the quotient's own noise is ~1e-15
 
 
 def test_brent_and_hermite_against_scipy():
