@@ -47,15 +47,17 @@ enum { TXW_FLAGS = 0, TXW_STATUS, TXW_RC, TXW_ATT, TXW_EVCNT, TXW_ACC, TXW_RCST,
 enum { F_FIXED = 1, F_PREVFIXED = 2, F_RETRY = 4, F_LAST = 8, F_DONE = 16, F_BACK = 32, F_VALID = 64 };
 
 // dynamic shared memory: [table blob | NCTX set contexts]; one context (buffers of consecutive stages alternate by parity):
-//   wk   [2][20][32]     walker inputs of a stage: ub, r2, and z^(2^k), rho^(2^k) for k = 0..5 with z = (cos, sin)(lambda) cos(phi)
-//                        (lead helper -> walkers)
+//   wk   [2][WK][32]     walker inputs of a stage: ub, r2, and the powers of z = (cos, sin)(lambda) cos(phi) and rho it starts its
+//                        columns from — P = 8: every z^e, e = 0..16, and rho^e, e = 1..16 (WK = 52; the walkers only load);
+//                        P = 16: z^(2^k), rho^(2^k), k = 0..5 (WK = 20; the walkers multiply them together)   (helpers -> walkers)
+//   rn   [2][9][32]      DCM of the stage being prepared (lead helper -> all helpers)
 //   part [2][P][4][32]   partial sums of a stage                                                   (walkers -> helpers)
 //   as   [2][18][32]     what the helpers need to assemble that stage's acceleration later (DCM, unit vector, K0, K1, two-body factor, position)
 //   ysp  [2][3][32]      position components of a coming stage, exchanged between the three helpers
 //   helper-private: kst [16][6][32] (k_i = (V_i, A_i)), nxt / er / ycur [6][32], controller fields
 struct TxLayout {
     unsigned blob, ctx0, ctx_stride;                                  // bytes
-    unsigned wk, part, as, ysp, kst, nxt, er, ycur, rot, f64, i64, i32;   // offsets inside a context
+    unsigned wk, part, as, ysp, kst, nxt, er, ycur, rot, rn, f64, i64, i32;   // offsets inside a context
     unsigned total;
 };
 __host__ __device__ inline TxLayout tx_layout(unsigned blob_bytes, int P, int N, int nctx) {
@@ -64,7 +66,7 @@ __host__ __device__ inline TxLayout tx_layout(unsigned blob_bytes, int P, int N,
     L.blob = 0;
     L.ctx0 = (blob_bytes + 127u) & ~127u;
     unsigned o = 0;
-    L.wk = o; o += 2u * 20u * NL * 8;
+    L.wk = o; o += 2u * (P == 8 ? 52u : 20u) * NL * 8;
     L.part = o; o += 2u * (unsigned)P * 4 * NL * 8;
     L.as = o; o += 2u * 18u * NL * 8;
     L.ysp = o; o += 2u * 3u * NL * 8;
@@ -73,6 +75,7 @@ __host__ __device__ inline TxLayout tx_layout(unsigned blob_bytes, int P, int N,
     L.er = o; o += 6 * NL * 8;
     L.ycur = o; o += 6 * NL * 8;
     L.rot = o; o += 6 * NL * 8;
+    L.rn = o; o += 2u * 9u * NL * 8;
     L.f64 = o; o += TXF_COUNT * NL * 8;
     L.i64 = o; o += TXI_COUNT * NL * 8;
     L.i32 = o; o += TXW_COUNT * NL * 4;
@@ -82,7 +85,7 @@ __host__ __device__ inline TxLayout tx_layout(unsigned blob_bytes, int P, int N,
 }
 
 struct TxSm {   // typed views of one set context
-    double *wk, *part, *as, *ysp, *kst, *nxt, *er, *ycur, *rot, *f64;
+    double *wk, *part, *as, *ysp, *kst, *nxt, *er, *ycur, *rot, *rn, *f64;
     long long* i64;
     int* i32;
 };
@@ -94,7 +97,7 @@ __device__ __forceinline__ TxSm tx_views(unsigned char* smem, const TxLayout& L,
     sm.as = reinterpret_cast<double*>(b + L.as); sm.ysp = reinterpret_cast<double*>(b + L.ysp);
     sm.kst = reinterpret_cast<double*>(b + L.kst); sm.nxt = reinterpret_cast<double*>(b + L.nxt);
     sm.er = reinterpret_cast<double*>(b + L.er); sm.ycur = reinterpret_cast<double*>(b + L.ycur);
-    sm.rot = reinterpret_cast<double*>(b + L.rot);
+    sm.rot = reinterpret_cast<double*>(b + L.rot); sm.rn = reinterpret_cast<double*>(b + L.rn);
     sm.f64 = reinterpret_cast<double*>(b + L.f64); sm.i64 = reinterpret_cast<long long*>(b + L.i64);
     sm.i32 = reinterpret_cast<int*>(b + L.i32);
     return sm;
@@ -462,11 +465,18 @@ __device__ __noinline__ void tx_park_ctl(const DevSink& sink, const DevTxQueue& 
 // ---- prologue of stage q for the 32 trajectories of a set, run by the lead helper: body-fixed position, 1/r, the recursion
 // scalars the walkers need, and everything the three helpers need to assemble the acceleration of that stage later
 enum { AS_R = 0, AS_S = 9, AS_T, AS_U, AS_K0, AS_K1, AS_FAC, AS_P0, AS_P1, AS_P2, AS_COUNT };
-enum { WK_UB = 0, WK_R2, WK_POW, WK_COUNT = WK_POW + 18 };   // WK_POW + 3k: Re z^(2^k), Im z^(2^k), rho^(2^k)
-template <int NPOW>
-__device__ __forceinline__ void tx_prologue(const DevSetup& S, const TxSm& sm, int lane, int par, const double* ysp, const double (&R)[9],
-                                            long long t_ns) {
+// walker inputs.  P = 8: WK_POW + e = Re z^e, WK_POW + 17 + e = Im z^e (e = 0..16), WK_POW + 34 + e = rho^(e+1) (e = 0..15);
+// P = 16: WK_POW + 3k = Re z^(2^k), + 1 = Im, + 2 = rho^(2^k)
+enum { WK_UB = 0, WK_R2, WK_POW };
+template <int P> struct TxWk { static constexpr int COUNT = (P == 8) ? WK_POW + 50 : WK_POW + 18; };
+
+// Stage prologue, run by the three helpers of the context once the position of the stage (ysp) and its DCM (rn) are in shared
+// memory: each helper derives (s, t, u, rho) itself, then helper 0 publishes the scalars of the acceleration assembly (as) and
+// ub, r2; helpers 1 and 2 publish the powers the walkers start their columns from.
+template <int P>
+__device__ __forceinline__ void tx_prologue(const DevSetup& S, const TxSm& sm, int lane, int par, int j, const double* ysp, long long t_ns) {
     const DevGrav& gv = S.grav;
+    const double* rn = sm.rn + par * 9 * NL + lane;
     const double p0 = ysp[lane], p1 = ysp[NL + lane], p2 = ysp[2 * NL + lane];
     double y0 = p0, y1 = p1, y2 = p2;
     double ir_c = 0.0;   // 1/|r| about the integration centre (two-body term)
@@ -474,33 +484,70 @@ __device__ __forceinline__ void tx_prologue(const DevSetup& S, const TxSm& sm, i
         ir_c = rsqrt(fma(y2, y2, fma(y1, y1, y0 * y0)));
         tx_field_offset(S, t_ns, y0, y1, y2);
     }
-    const double rb0 = fma(R[2], y2, fma(R[1], y1, R[0] * y0));
-    const double rb1 = fma(R[5], y2, fma(R[4], y1, R[3] * y0));
-    const double rb2 = fma(R[8], y2, fma(R[7], y1, R[6] * y0));
+    const double rb0 = fma(rn[2 * NL], y2, fma(rn[1 * NL], y1, rn[0] * y0));
+    const double rb1 = fma(rn[5 * NL], y2, fma(rn[4 * NL], y1, rn[3 * NL] * y0));
+    const double rb2 = fma(rn[8 * NL], y2, fma(rn[7 * NL], y1, rn[6 * NL] * y0));
     const double inv_r = rsqrt(fma(rb2, rb2, fma(rb1, rb1, rb0 * rb0)));
     if (S.grav_body < 0) ir_c = inv_r;
     const double rho = gv.r_eq * inv_r;
     const double s_ = rb0 * inv_r, t_ = rb1 * inv_r, u_ = rb2 * inv_r;
-    double* wk = sm.wk + par * WK_COUNT * NL + lane;
-    wk[WK_UB * NL] = u_ * rho; wk[WK_R2 * NL] = rho * rho;
-    {   // z^(2^k), rho^(2^k): the walkers assemble z^e, rho^(e+1) of their columns from these (one multiplication per set bit of e)
-        double zr = s_, zi = t_, rp = rho;
+    double* wk = sm.wk + par * TxWk<P>::COUNT * NL + lane;
+    if (j == 0) {
+        wk[WK_UB * NL] = u_ * rho; wk[WK_R2 * NL] = rho * rho;
+        double* as = sm.as + par * AS_COUNT * NL + lane;
 #pragma unroll
-        for (int k = 0; k < NPOW; ++k) {
-            wk[(WK_POW + 3 * k) * NL] = zr; wk[(WK_POW + 3 * k + 1) * NL] = zi; wk[(WK_POW + 3 * k + 2) * NL] = rp;
-            const double nr = fma(zr, zr, -(zi * zi));
-            zi = 2.0 * zr * zi; zr = nr; rp *= rp;
+        for (int k = 0; k < 9; ++k) as[(AS_R + k) * NL] = rn[k * NL];
+        as[AS_S * NL] = s_; as[AS_T * NL] = t_; as[AS_U * NL] = u_;
+        // rr_n A[n][m] = K0 rho (rho^n A),  rr_{n-1} A[n][m] = K0 (rho^n A),  K0 = mu / (r R_eq)
+        const double K0 = (gv.mu * gv.inv_r_eq) * inv_r;
+        as[AS_K0 * NL] = K0; as[AS_K1 * NL] = K0 * rho;
+        as[AS_FAC * NL] = -S.mu_central * ir_c * ir_c * ir_c;   // two-body (orbital.rs:86-92), from the same 1/r when the field is the centre's
+        as[AS_P0 * NL] = p0; as[AS_P1 * NL] = p1; as[AS_P2 * NL] = p2;
+        if constexpr (P != 8) {   // z^(2^k), rho^(2^k): the walkers assemble z^e, rho^(e+1) of their columns from these
+            double zr = s_, zi = t_, rp = rho;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                wk[(WK_POW + 3 * k) * NL] = zr; wk[(WK_POW + 3 * k + 1) * NL] = zi; wk[(WK_POW + 3 * k + 2) * NL] = rp;
+                const double nr = fma(zr, zr, -(zi * zi));
+                zi = 2.0 * zr * zi; zr = nr; rp *= rp;
+            }
+        }
+    } else if constexpr (P == 8) {
+        // z^1..z^8 by doubling (z^2; z^3, z^4; z^5..z^8), helper 2 goes on to z^9..z^16 = z^8 z^k; helper 1 adds rho^1..rho^16
+        double zr[9], zi[9];
+        zr[1] = s_; zi[1] = t_;
+#pragma unroll
+        for (int lo = 1; lo < 8; lo *= 2) {
+#pragma unroll
+            for (int k = 1; k <= lo; ++k) {
+                zr[lo + k] = fma(zr[lo], zr[k], -(zi[lo] * zi[k]));
+                zi[lo + k] = fma(zr[lo], zi[k], zi[lo] * zr[k]);
+            }
+        }
+        double* wr = wk + WK_POW * NL;
+        double* wi = wk + (WK_POW + 17) * NL;
+        if (j == 1) {
+            wr[0] = 1.0; wi[0] = 0.0;
+#pragma unroll
+            for (int k = 1; k <= 8; ++k) { wr[k * NL] = zr[k]; wi[k * NL] = zi[k]; }
+            double rp[17];
+            rp[1] = rho;
+#pragma unroll
+            for (int lo = 1; lo < 16; lo *= 2) {
+#pragma unroll
+                for (int k = 1; k <= lo; ++k) rp[lo + k] = rp[lo] * rp[k];
+            }
+            double* wp = wk + (WK_POW + 34) * NL;
+#pragma unroll
+            for (int k = 1; k <= 16; ++k) wp[(k - 1) * NL] = rp[k];
+        } else {
+#pragma unroll
+            for (int k = 1; k <= 8; ++k) {
+                wr[(8 + k) * NL] = fma(zr[8], zr[k], -(zi[8] * zi[k]));
+                wi[(8 + k) * NL] = fma(zr[8], zi[k], zi[8] * zr[k]);
+            }
         }
     }
-    double* as = sm.as + par * AS_COUNT * NL + lane;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) as[(AS_R + k) * NL] = R[k];
-    as[AS_S * NL] = s_; as[AS_T * NL] = t_; as[AS_U * NL] = u_;
-    // rr_n A[n][m] = K0 rho (rho^n A),  rr_{n-1} A[n][m] = K0 (rho^n A),  K0 = mu / (r R_eq)
-    const double K0 = (gv.mu * gv.inv_r_eq) * inv_r;
-    as[AS_K0 * NL] = K0; as[AS_K1 * NL] = K0 * rho;
-    as[AS_FAC * NL] = -S.mu_central * ir_c * ir_c * ir_c;   // two-body (orbital.rs:86-92), from the same 1/r when the field is the centre's
-    as[AS_P0 * NL] = p0; as[AS_P1 * NL] = p1; as[AS_P2 * NL] = p2;
 }
 
 // inertial -> body-fixed DCM at the stage time: first-order update of the (slow) pole angles, exact angle addition for the
@@ -578,8 +625,8 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
     static_assert(P <= NYXB_TX_MAXP && NCTX >= 1 && NCTX <= 2, "walker positions / set contexts");
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long tma_bar;
-    // READY[context][parity]: "the walker inputs of the next stage with this parity are published" — an mbarrier (32 arrivals: the
-    // lanes of the context's lead helper) rather than a named barrier, because the walkers POLL it: a walker warp takes whichever
+    // READY[context][parity]: "the walker inputs of the next stage with this parity are published" — an mbarrier (96 arrivals: the
+    // three helpers of the context) rather than a named barrier, because the walkers POLL it: a walker warp takes whichever
     // context has a stage ready, so the serial stretch between two step attempts of one set (error norm, controller, commit,
     // first prologue) is covered by the other set's stages instead of stalling the walkers.
     __shared__ __align__(8) unsigned long long ready_bar[NCTX][2];
@@ -607,8 +654,8 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
 #pragma unroll
         for (int c = 0; c < NCTX; ++c) {
             s_exit[c] = 0;
-            tx_mbar_init(&ready_bar[c][0], 32);
-            tx_mbar_init(&ready_bar[c][1], 32);
+            tx_mbar_init(&ready_bar[c][0], 96);
+            tx_mbar_init(&ready_bar[c][1], 96);
         }
     }
     __syncthreads();
@@ -655,29 +702,27 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                 pref = (c + 1) % NCTX;
                 TX_TRACE(TR_WALK, c, st);
                 const TxSm sm = tx_views(smem, L, c, N);
-                const double* wk = sm.wk + par * WK_COUNT * NL + lane;
+                const double* wk = sm.wk + par * TxWk<P>::COUNT * NL + lane;
                 const double ub = wk[WK_UB * NL], r2 = wk[WK_R2 * NL];
                 // z^e = (cos, sin)(e lambda) cos^e(phi) and rho^(e+1) for the two interleaved exponent sequences of this position:
                 // e = w + 2P j (za, pa) and e = 2P-1-w + 2P j (zb, pb).  The two start exponents are bit complements: every published
                 // power z^(2^k) goes into exactly one of them (warp-uniform choice).
-                double zar, zai, zbr, zbi, pa, pb;
-                switch (w) {   // one specialised copy per position: the choices below are compile-time there
+                double zar, zai, zbr, zbi, pa, pb, qr, qi, qp;
+                if constexpr (P == 8) {   // published: z^w, z^(15-w), z^16, rho^(w+1), rho^(16-w), rho^16
+                    zar = wk[(WK_POW + w) * NL]; zai = wk[(WK_POW + 17 + w) * NL]; pa = wk[(WK_POW + 34 + w) * NL];
+                    zbr = wk[(WK_POW + 15 - w) * NL]; zbi = wk[(WK_POW + 17 + 15 - w) * NL]; pb = wk[(WK_POW + 34 + 15 - w) * NL];
+                    qr = wk[(WK_POW + 16) * NL]; qi = wk[(WK_POW + 17 + 16) * NL]; qp = wk[(WK_POW + 34 + 15) * NL];
+                } else {
+                    switch (w) {   // one specialised copy per position: the choices below are compile-time there
 #define NYXB_TX_CASE(WW) case WW: tx_start_powers<WW, NPOW - 1>(wk, zar, zai, pa, zbr, zbi, pb); break;
-                    NYXB_TX_CASE(0) NYXB_TX_CASE(1) NYXB_TX_CASE(2) NYXB_TX_CASE(3) NYXB_TX_CASE(4) NYXB_TX_CASE(5) NYXB_TX_CASE(6) NYXB_TX_CASE(7)
-                    default:
-                        if constexpr (P == 16) {
-                            switch (w) {
-                                NYXB_TX_CASE(8) NYXB_TX_CASE(9) NYXB_TX_CASE(10) NYXB_TX_CASE(11) NYXB_TX_CASE(12) NYXB_TX_CASE(13) NYXB_TX_CASE(14)
-                                default: tx_start_powers<15, NPOW - 1>(wk, zar, zai, pa, zbr, zbi, pb); break;
-                            }
-                        } else {
-                            tx_start_powers<7, NPOW - 1>(wk, zar, zai, pa, zbr, zbi, pb);
-                        }
-                        break;
+                        NYXB_TX_CASE(0) NYXB_TX_CASE(1) NYXB_TX_CASE(2) NYXB_TX_CASE(3) NYXB_TX_CASE(4) NYXB_TX_CASE(5) NYXB_TX_CASE(6) NYXB_TX_CASE(7)
+                        NYXB_TX_CASE(8) NYXB_TX_CASE(9) NYXB_TX_CASE(10) NYXB_TX_CASE(11) NYXB_TX_CASE(12) NYXB_TX_CASE(13) NYXB_TX_CASE(14)
+                        default: tx_start_powers<15, NPOW - 1>(wk, zar, zai, pa, zbr, zbi, pb); break;
 #undef NYXB_TX_CASE
+                    }
+                    qr = wk[(WK_POW + 3 * (NPOW - 1)) * NL]; qi = wk[(WK_POW + 3 * (NPOW - 1) + 1) * NL];   // z^(2P)
+                    qp = wk[(WK_POW + 3 * (NPOW - 1) + 2) * NL];                                          // rho^(2P)
                 }
-                const double qr = wk[(WK_POW + 3 * (NPOW - 1)) * NL], qi = wk[(WK_POW + 3 * (NPOW - 1) + 1) * NL];   // z^(2P)
-                const double qp = wk[(WK_POW + 3 * (NPOW - 1) + 2) * NL];                                            // rho^(2P)
                 double X = 0.0, Y = 0.0, Z = 0.0, W = 0.0;
                 const double2* A = recA + 2 * rec_off;
                 const double* K = recK + rec_off;
@@ -740,7 +785,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
         }
         nb_sync(BAR_HB, 96);
         if (s_exit[c]) {
-            if (lead) tx_mbar_arrive(&ready_bar[c][0]);   // releases the walkers (they expect stage 0), which read s_exit and drop this context
+            tx_mbar_arrive(&ready_bar[c][0]);   // releases the walkers (they expect stage 0), which read s_exit and drop this context
             return;
         }
         const int set = s_set[c];
@@ -787,26 +832,30 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
             // ---- prime the pipeline: stage 0 (the state itself) and stage 1 (needs only V_0 = v): instance.rs:369-394
             sm.kst[(0 * 6 + j) * NL + lane] = v_own;                 // k_0[j] = V_0
             sm.ysp[(0 * 3 + j) * NL + lane] = r_own;                 // P_0
+            const long long off1 = (stages > 1) ? dur_from_seconds(S.tb.c[0] * h) : 0;
+            if (stages > 1) sm.ysp[(1 * 3 + j) * NL + lane] = fma(h, ta[0] * v_own, r_own);   // P_1 = r + h a_10 V_0
             nb_sync(BAR_HB, 96);
-            if (lead && gv.rot.kind != 0) {
-                rb_.sa = sm.rot[lane]; rb_.ca = sm.rot[NL + lane]; rb_.sd = sm.rot[2 * NL + lane]; rb_.cd = sm.rot[3 * NL + lane];
-                rb_.sw = sm.rot[4 * NL + lane]; rb_.cw = sm.rot[5 * NL + lane];
-            }
             if (lead) {
+                if (gv.rot.kind != 0) {
+                    rb_.sa = sm.rot[lane]; rb_.ca = sm.rot[NL + lane]; rb_.sd = sm.rot[2 * NL + lane]; rb_.cd = sm.rot[3 * NL + lane];
+                    rb_.sw = sm.rot[4 * NL + lane]; rb_.cw = sm.rot[5 * NL + lane];
+                }
                 tx_dcm(gv.rot, rb_, 0, Rn);
-                tx_prologue<NPOW>(S, sm, lane, 0, sm.ysp, Rn, epoch);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) sm.rn[k * NL + lane] = Rn[k];
+                if (stages > 1) {
+                    tx_dcm(gv.rot, rb_, off1, Rn);
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) sm.rn[(9 + k) * NL + lane] = Rn[k];
+                }
             }
-            if (lead) tx_mbar_arrive(&ready_bar[c][0]);
+            nb_sync(BAR_HB, 96);
+            tx_prologue<P>(S, sm, lane, 0, j, sm.ysp, epoch);
+            tx_mbar_arrive(&ready_bar[c][0]);
             TX_TRACE(TR_READY, c, 0);
             if (stages > 1) {
-                const long long off1 = dur_from_seconds(S.tb.c[0] * h);
-                sm.ysp[(1 * 3 + j) * NL + lane] = fma(h, ta[0] * v_own, r_own);   // P_1 = r + h a_10 V_0
-                nb_sync(BAR_HB, 96);
-                if (lead) {
-                    tx_dcm(gv.rot, rb_, off1, Rn);
-                    tx_prologue<NPOW>(S, sm, lane, 1, sm.ysp + 3 * NL, Rn, epoch + off1);
-                }
-                if (lead) tx_mbar_arrive(&ready_bar[c][1]);
+                tx_prologue<P>(S, sm, lane, 1, j, sm.ysp + 3 * NL, epoch + off1);
+                tx_mbar_arrive(&ready_bar[c][1]);
                 TX_TRACE(TR_READY, c, 1);
             }
             // ---- derive(): the stages of one attempt for the 32 trajectories (instance.rs:358-493), one walk ahead of the walkers
@@ -840,7 +889,11 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                     if (m <= i) w0 = fma(arow[m], kc[m * 6 * NL], w0);
                     preP = w0 + w1;
                     off2 = dur_from_seconds(S.tb.c[i + 1] * h);
-                    if (lead) tx_dcm(gv.rot, rb_, off2, Rn);
+                    if (lead) {   // DCM of stage i+2 (its parity buffer was last read in the prologue of stage i, two barriers ago)
+                        tx_dcm(gv.rot, rb_, off2, Rn);
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) sm.rn[(par * 9 + k) * NL + lane] = Rn[k];
+                    }
                 }
                 TX_TRACE(TR_DONE_WAIT, c, i);
                 nb_sync(BAR_DONE + par, NT_RW);   // the walkers' partial sums of stage i are back
@@ -887,8 +940,8 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                         sm.ysp[(par * 3 + j) * NL + lane] = fma(h, fma(ta[(i + 1) * NYXB_MAX_STAGES + i + 1], vn, preP), r_own);   // P_{i+2}
                     nb_sync(BAR_HB, 96);   // V_{i+1} and the position components of stage i+2 of all three helpers are in shared memory
                     if (i + 2 < stages) {
-                        if (lead) tx_prologue<NPOW>(S, sm, lane, par, sm.ysp + par * 3 * NL, Rn, epoch + off2);
-                        if (lead) tx_mbar_arrive(&ready_bar[c][par]);   // walker inputs of stage i+2 are published
+                        tx_prologue<P>(S, sm, lane, par, j, sm.ysp + par * 3 * NL, epoch + off2);
+                        tx_mbar_arrive(&ready_bar[c][par]);   // walker inputs of stage i+2 are published
                         TX_TRACE(TR_READY, c, i + 2);
                     }
                 }

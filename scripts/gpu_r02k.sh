@@ -30,3 +30,9 @@ timeout 200 ncu --set full --clock-control none --import-source on -k regex:nyxb
     python bench.py --steps 1 --warmup 0 --span-days 0.1 --n-traj 10000 --no-cpu-baseline --no-strict --kernel transposed > gpurun_out/${T}_tx_bench.log 2>&1
 ls -la gpurun_out/${T}_tx.ncu-rep
 fi
+if [ "${TRACE:-0}" = 1 ]; then   # diagnostic timeline, built on the box (overwrites the box's copy of libnyxb.so: keep this step last)
+touch nyx_b200/csrc/nyxb_tx.cu nyx_b200/csrc/nyxb_api.cu
+timeout 400 make -C nyx_b200/csrc EXTRA=-DNYXB_TX_TRACE > gpurun_out/${T}_make.log 2>&1; echo "make rc=$?"
+NYXB_TX_TRACE_FILE=gpurun_out/${T}_trace.bin timeout 120 python bench.py --steps 1 --warmup 0 --span-days 0.05 --n-traj 10000 --no-cpu-baseline --no-strict --kernel transposed > gpurun_out/${T}_trace_bench.log 2>&1; echo "trace bench rc=$?"
+python scripts/tx_trace.py gpurun_out/${T}_trace.bin 8 | grep -v "helper [12])" | grep -E "walk|wait|busy|post|slack|between|context|helper warp (8|9|10)" | head -24
+fi
