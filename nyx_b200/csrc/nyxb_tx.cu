@@ -631,6 +631,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
     // first prologue) is covered by the other set's stages instead of stalling the walkers.
     __shared__ __align__(8) unsigned long long ready_bar[NCTX][2];
     __shared__ int s_set[NCTX], s_fresh[NCTX], s_exit[NCTX], s_all_done[NCTX], s_slice_end[NCTX];
+    __shared__ int s_kick;   // set by context 0 half-way through its first attempt: context 1 starts then (see below)
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 #ifdef NYXB_TX_TRACE
     int tr_n = 0;
@@ -651,6 +652,8 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
     // ---- CTA-shared tables (records, column seeds, schedule): ONE TMA bulk copy
     if (tid == 0) {
         tx_mbar_init(&tma_bar, 1);
+#pragma unroll
+        s_kick = 0;
 #pragma unroll
         for (int c = 0; c < NCTX; ++c) {
             s_exit[c] = 0;
@@ -760,6 +763,16 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
     const bool lead = (j == 0);   // helper 0 also runs the DCM, the stage prologues, the controller and the set queue of its context
     const double* ta = S.tb.a;    // a_{q,m} (stage q >= 1, m < q) = ta[(q - 1) * NYXB_MAX_STAGES + m]
 
+    // The two sets of a CTA must not reach the serial stretch between two attempts (error norm, controller, commit, first
+    // prologues: ~11 000 clocks without work for the walkers) at the same time, and nothing pulls them apart once they run in
+    // phase (measured: both contexts started together stayed within 1 % of an attempt of each other, and the walkers idled through
+    // every such stretch).  Context 1 therefore starts when context 0 is half-way through its first attempt.
+    bool kick_pending = (NCTX > 1 && c == 0);
+    if (NCTX > 1 && c == 1) {
+        if (lead && lane == 0) { while (!*(volatile int*)&s_kick) __nanosleep(200); }
+        nb_sync(BAR_HB, 96);
+    }
+
     for (;;) {
         // ---------------------------------------------------------------- acquire a set: a fresh one, else a parked one
         if (lead && lane == 0) {
@@ -784,6 +797,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
             s_exit[c] = set < 0;   // nothing fresh, nothing parked: every unfinished set is in progress in another context
         }
         nb_sync(BAR_HB, 96);
+        if (s_exit[c] && kick_pending && lead && lane == 0) *(volatile int*)&s_kick = 1;
         if (s_exit[c]) {
             tx_mbar_arrive(&ready_bar[c][0]);   // releases the walkers (they expect stage 0), which read s_exit and drop this context
             return;
@@ -858,6 +872,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                 tx_mbar_arrive(&ready_bar[c][1]);
                 TX_TRACE(TR_READY, c, 1);
             }
+            nb_sync(BAR_HB, 96);   // the lead overwrites rn[0] (DCM of stage 2) in the first slack below: every helper has read it by now
             // ---- derive(): the stages of one attempt for the 32 trajectories (instance.rs:358-493), one walk ahead of the walkers
             for (int i = 0; i < stages; ++i) {
                 const int par = i & 1;
@@ -894,6 +909,10 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
 #pragma unroll
                         for (int k = 0; k < 9; ++k) sm.rn[(par * 9 + k) * NL + lane] = Rn[k];
                     }
+                }
+                if (kick_pending && i == stages / 2) {
+                    if (lead && lane == 0) *(volatile int*)&s_kick = 1;
+                    kick_pending = false;
                 }
                 TX_TRACE(TR_DONE_WAIT, c, i);
                 nb_sync(BAR_DONE + par, NT_RW);   // the walkers' partial sums of stage i are back
@@ -976,6 +995,10 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
             if (s_slice_end[c]) break;
         }
 
+        if (kick_pending) {
+            if (lead && lane == 0) *(volatile int*)&s_kick = 1;
+            kick_pending = false;
+        }
         // ---------------------------------------------------------------- park the set (== final outputs when it is done)
         if (valid) {
             out_state[(size_t)j * n + tr] = sm.ycur[j * NL + lane];
