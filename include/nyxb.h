@@ -507,7 +507,7 @@ int32_t nyxb_engine_last_kernel(const nyxb_engine* eng);                   /* fa
 /* TRANSPOSED kernel: step attempts per time slice (default 64) and an upper bound on the persistent CTAs (0 = SMs x occupancy).
  * Sets are only parked when there are more sets than CTAs. */
 int32_t nyxb_engine_set_tx_tuning(nyxb_engine* eng, int32_t slice_attempts, int32_t max_ctas);
-int32_t nyxb_engine_set_tx_positions(nyxb_engine* eng, int32_t positions);   /* walker warps per set: 0 = by degree, 8, 12, 16 */
+int32_t nyxb_engine_set_tx_positions(nyxb_engine* eng, int32_t positions);   /* walker warps per set: 0 = by degree, 8, 10, 16 */
 int32_t nyxb_engine_set_lanes(nyxb_engine* eng, int32_t lanes_per_trajectory); /* 0 = auto */
 int32_t nyxb_engine_get_lanes(const nyxb_engine* eng);
 int64_t nyxb_engine_launch_count(const nyxb_engine* eng); /* kernels launched so far */
@@ -524,7 +524,7 @@ double nyxb_measure_fp64_tflops(int32_t device, int32_t iters);
 int32_t nyxb_coop_table_dump(const nyxb_gravity_field* field, int32_t lanes, int32_t* out_L, int32_t* out_kmax,
                              double* recs, int32_t* col_start, int32_t* col_m, double* colseed);
 
-/* Same for the transposed kernel (`positions` in {8,12,16}): recA [(n_rec+1)][4], recK [n_rec+2], colseed [N+2][4],
+/* Same for the transposed kernel (`positions` in {8,10,16}): recA [(n_rec+1)][4], recK [n_rec+2], colseed [N+2][4],
  * sched [positions][2 + 2*kmax] = {first record, columns, (m, entries) per column} (see nyx_b200/csrc/nyxb_tx.h). */
 int32_t nyxb_tx_table_dump(const nyxb_gravity_field* field, int32_t positions, int32_t* out_n_rec, int32_t* out_kmax,
                            double* recA, double* recK, double* colseed, int32_t* sched);

@@ -1163,7 +1163,7 @@ extern "C" int32_t nyxb_engine_set_tx_tuning(nyxb_engine* eng, int32_t slice_att
     return NYXB_RC_OK;
 }
 extern "C" int32_t nyxb_engine_set_tx_positions(nyxb_engine* eng, int32_t positions) {
-    if (!eng || (positions != 0 && positions != 8 && positions != 12 && positions != 16)) { set_err("positions: 0 (auto), 8, 12, 16"); return NYXB_RC_BAD_ARG; }
+    if (!eng || (positions != 0 && positions != 8 && positions != 10 && positions != 16)) { set_err("positions: 0 (auto), 8, 10, 16"); return NYXB_RC_BAD_ARG; }
     eng->tx_positions = positions;
     return NYXB_RC_OK;
 }
@@ -1189,7 +1189,7 @@ extern "C" int32_t nyxb_coop_table_dump(const nyxb_gravity_field* f, int32_t lan
 
 extern "C" int32_t nyxb_tx_table_dump(const nyxb_gravity_field* f, int32_t positions, int32_t* out_n_rec, int32_t* out_kmax,
                                       double* recA, double* recK, double* colseed, int32_t* sched) {
-    if (!f || !f->c_nm || !f->s_nm || f->degree < 2 || (positions != 8 && positions != 12 && positions != 16) || !out_n_rec || !out_kmax) {
+    if (!f || !f->c_nm || !f->s_nm || f->degree < 2 || (positions != 8 && positions != 10 && positions != 16) || !out_n_rec || !out_kmax) {
         set_err("bad argument");
         return NYXB_RC_BAD_ARG;
     }

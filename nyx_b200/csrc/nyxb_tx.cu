@@ -48,7 +48,7 @@ enum { F_FIXED = 1, F_PREVFIXED = 2, F_RETRY = 4, F_LAST = 8, F_DONE = 16, F_BAC
 
 // dynamic shared memory: [table blob | NCTX set contexts]; one context (buffers of consecutive stages alternate by parity):
 //   wk   [2][WK][32]     walker inputs of a stage: ub, r2, and the powers of z = (cos, sin)(lambda) cos(phi) and rho it starts its
-//                        columns from — P = 8: every z^e, e = 0..16, and rho^e, e = 1..16 (WK = 52; the walkers only load);
+//                        columns from — P = 8, 10: every z^e, e = 0..2P, and rho^e, e = 1..2P (WK = 6P + 4; the walkers only load);
 //                        P = 16: z^(2^k), rho^(2^k), k = 0..5 (WK = 20; the walkers multiply them together)   (helpers -> walkers)
 //   rn   [2][9][32]      DCM of the stage being prepared (lead helper -> all helpers)
 //   part [2][P][4][32]   partial sums of a stage                                                   (walkers -> helpers)
@@ -66,7 +66,7 @@ __host__ __device__ inline TxLayout tx_layout(unsigned blob_bytes, int P, int N,
     L.blob = 0;
     L.ctx0 = (blob_bytes + 127u) & ~127u;
     unsigned o = 0;
-    L.wk = o; o += 2u * (P == 8 ? 52u : 20u) * NL * 8;
+    L.wk = o; o += 2u * (P == 16 ? 20u : 6u * (unsigned)P + 4u) * NL * 8;
     L.part = o; o += 2u * (unsigned)P * 4 * NL * 8;
     L.as = o; o += 2u * 18u * NL * 8;
     L.ysp = o; o += 2u * 3u * NL * 8;
@@ -147,7 +147,8 @@ __device__ __forceinline__ bool tx_mbar_test(unsigned long long* bar, unsigned p
 
 // Diagnostic timeline of CTA 0 (built with -DNYXB_TX_TRACE only; scripts/tx_trace.py reads it): lane 0 of every warp appends
 // (clock << 20 | code << 12 | context << 8 | stage) records to its own strip.
-enum { TR_POLL = 1, TR_WALK = 2, TR_WALK_END = 3, TR_DONE_WAIT = 4, TR_DONE_SEEN = 5, TR_READY = 6, TR_STAGES_END = 7, TR_CTRL_END = 8, TR_TOP = 9 };
+enum { TR_POLL = 1, TR_WALK = 2, TR_WALK_END = 3, TR_DONE_WAIT = 4, TR_DONE_SEEN = 5, TR_READY = 6, TR_STAGES_END = 7, TR_CTRL_END = 8, TR_TOP = 9,
+       TR_PRE_DONE = 10, TR_DCM_DONE = 11, TR_REDUCED = 12, TR_ACC_DONE = 13, TR_HB_PASSED = 14 };
 #ifdef NYXB_TX_TRACE
 #define TX_TRACE(code, ctx, stg)                                                                                              \
     do {                                                                                                                      \
@@ -465,10 +466,15 @@ __device__ __noinline__ void tx_park_ctl(const DevSink& sink, const DevTxQueue& 
 // ---- prologue of stage q for the 32 trajectories of a set, run by the lead helper: body-fixed position, 1/r, the recursion
 // scalars the walkers need, and everything the three helpers need to assemble the acceleration of that stage later
 enum { AS_R = 0, AS_S = 9, AS_T, AS_U, AS_K0, AS_K1, AS_FAC, AS_P0, AS_P1, AS_P2, AS_COUNT };
-// walker inputs.  P = 8: WK_POW + e = Re z^e, WK_POW + 17 + e = Im z^e (e = 0..16), WK_POW + 34 + e = rho^(e+1) (e = 0..15);
+// walker inputs.  P = 8, 10 (E = 2P): WK_POW + e = Re z^e, WK_POW + E + 1 + e = Im z^e (e = 0..E), WK_POW + 2E + 1 + e = rho^e (e = 1..E);
 // P = 16: WK_POW + 3k = Re z^(2^k), + 1 = Im, + 2 = rho^(2^k)
 enum { WK_UB = 0, WK_R2, WK_POW };
-template <int P> struct TxWk { static constexpr int COUNT = (P == 8) ? WK_POW + 50 : WK_POW + 18; };
+template <int P> struct TxWk {
+    static constexpr bool ALL = (P != 16);   // every starting power is published
+    static constexpr int E = 2 * P;
+    static constexpr int COUNT = ALL ? WK_POW + 3 * E + 2 : WK_POW + 18;
+    static constexpr int ZR = WK_POW, ZI = WK_POW + E + 1, RH = WK_POW + 2 * E + 1;   // RH + e = rho^e
+};
 
 // Stage prologue, run by the three helpers of the context once the position of the stage (ysp) and its DCM (rn) are in shared
 // memory: each helper derives (s, t, u, rho) itself, then helper 0 publishes the scalars of the acceleration assembly (as) and
@@ -503,7 +509,7 @@ __device__ __forceinline__ void tx_prologue(const DevSetup& S, const TxSm& sm, i
         as[AS_K0 * NL] = K0; as[AS_K1 * NL] = K0 * rho;
         as[AS_FAC * NL] = -S.mu_central * ir_c * ir_c * ir_c;   // two-body (orbital.rs:86-92), from the same 1/r when the field is the centre's
         as[AS_P0 * NL] = p0; as[AS_P1 * NL] = p1; as[AS_P2 * NL] = p2;
-        if constexpr (P != 8) {   // z^(2^k), rho^(2^k): the walkers assemble z^e, rho^(e+1) of their columns from these
+        if constexpr (!TxWk<P>::ALL) {   // z^(2^k), rho^(2^k): the walkers assemble z^e, rho^(e+1) of their columns from these
             double zr = s_, zi = t_, rp = rho;
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
@@ -512,8 +518,13 @@ __device__ __forceinline__ void tx_prologue(const DevSetup& S, const TxSm& sm, i
                 zi = 2.0 * zr * zi; zr = nr; rp *= rp;
             }
         }
-    } else if constexpr (P == 8) {
-        // z^1..z^8 by doubling (z^2; z^3, z^4; z^5..z^8), helper 2 goes on to z^9..z^16 = z^8 z^k; helper 1 adds rho^1..rho^16
+    } else if constexpr (TxWk<P>::ALL) {
+        // z^1..z^8 by doubling (z^2; z^3, z^4; z^5..z^8); helper 2 goes on to z^(8+k) = z^8 z^k, z^(16+k) = z^16 z^k; helper 1 adds
+        // the powers of rho the same way
+        constexpr int E = TxWk<P>::E;
+        static_assert(E > 8 && E <= 24, "published powers");
+        double* wr = wk + TxWk<P>::ZR * NL;
+        double* wi = wk + TxWk<P>::ZI * NL;
         double zr[9], zi[9];
         zr[1] = s_; zi[1] = t_;
 #pragma unroll
@@ -524,27 +535,37 @@ __device__ __forceinline__ void tx_prologue(const DevSetup& S, const TxSm& sm, i
                 zi[lo + k] = fma(zr[lo], zi[k], zi[lo] * zr[k]);
             }
         }
-        double* wr = wk + WK_POW * NL;
-        double* wi = wk + (WK_POW + 17) * NL;
         if (j == 1) {
             wr[0] = 1.0; wi[0] = 0.0;
 #pragma unroll
             for (int k = 1; k <= 8; ++k) { wr[k * NL] = zr[k]; wi[k * NL] = zi[k]; }
-            double rp[17];
+            double rp[9];
             rp[1] = rho;
 #pragma unroll
-            for (int lo = 1; lo < 16; lo *= 2) {
+            for (int lo = 1; lo < 8; lo *= 2) {
 #pragma unroll
                 for (int k = 1; k <= lo; ++k) rp[lo + k] = rp[lo] * rp[k];
             }
-            double* wp = wk + (WK_POW + 34) * NL;
-#pragma unroll
-            for (int k = 1; k <= 16; ++k) wp[(k - 1) * NL] = rp[k];
-        } else {
+            double* wp = wk + TxWk<P>::RH * NL;
+            const double r16 = rp[8] * rp[8];
 #pragma unroll
             for (int k = 1; k <= 8; ++k) {
-                wr[(8 + k) * NL] = fma(zr[8], zr[k], -(zi[8] * zi[k]));
-                wi[(8 + k) * NL] = fma(zr[8], zi[k], zi[8] * zr[k]);
+                wp[k * NL] = rp[k];
+                if (8 + k <= E) wp[(8 + k) * NL] = (k == 8) ? r16 : rp[8] * rp[k];
+                if (16 + k <= E) wp[(16 + k) * NL] = r16 * rp[k];
+            }
+        } else {
+            const double z16r = fma(zr[8], zr[8], -(zi[8] * zi[8])), z16i = 2.0 * zr[8] * zi[8];
+#pragma unroll
+            for (int k = 1; k <= 8; ++k) {
+                if (8 + k <= E) {
+                    wr[(8 + k) * NL] = (k == 8) ? z16r : fma(zr[8], zr[k], -(zi[8] * zi[k]));
+                    wi[(8 + k) * NL] = (k == 8) ? z16i : fma(zr[8], zi[k], zi[8] * zr[k]);
+                }
+                if (16 + k <= E) {
+                    wr[(16 + k) * NL] = fma(z16r, zr[k], -(z16i * zi[k]));
+                    wi[(16 + k) * NL] = fma(z16r, zi[k], z16i * zr[k]);
+                }
             }
         }
     }
@@ -636,8 +657,8 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
 #ifdef NYXB_TX_TRACE
     int tr_n = 0;
 #endif
-    constexpr int NPOW = (P == 8) ? 5 : 6;   // z^(2^k), k < NPOW: bits of the exponents below 2P, and the common ratio z^(2P)
-    static_assert(P == 8 || P == 16, "2P must be a power of two");
+    constexpr int NPOW = 6;   // P = 16: z^(2^k), k < NPOW: bits of the exponents below 2P, and the common ratio z^(2P)
+    static_assert(P == 8 || P == 10 || P == 16, "walker positions");
     constexpr int NT_RW = (P + 3) * 32;   // threads on a READY / DONE barrier: the walkers + the three helpers of the context
     // named barriers of context c: HB (helpers among themselves), READY[parity], DONE[parity]
     constexpr int BAR_PER_CTX = 5;
@@ -675,7 +696,12 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
         // parity-(i & 1) buffers.  The harmonic sum of stage i+1 needs only the POSITION of that stage, which depends on the
         // accelerations up to stage i-1 (second-order system): the helpers publish it one walk ahead, so the walkers never wait for
         // the stage they have just finished — only, once per step, for the controller.
-        const int* my = sched + w * (2 + 2 * Tx.kmax);
+        // column position of this warp.  A warp's scheduler is warp id mod 4, and the six helper warps land 2-2-1-1 on the four
+        // schedulers (P = 8: warps 8 and 12, 9 and 13, 10, 11); the zigzag gives the low positions a third column and a few more
+        // padded entries (N = 21: 34 32 32 30 30 30 28 28).  The lightest pairs go to the schedulers that also host two helpers
+        // (measured before: walks of 3 380 clocks on those against 2 590 on the others, and a stage ends with its slowest walk).
+        const int pos = (P == 8) ? ((0x23571046u >> (4 * w)) & 0xfu) : w;   // warp 0..7 -> 6 4 0 1 7 5 3 2
+        const int* my = sched + pos * (2 + 2 * Tx.kmax);
         const int rec_off = my[0], ncol = my[1];
         unsigned active = (1u << NCTX) - 1u;
         unsigned phases = 0;   // bit 2c + par: parity of the READY[c][par] phase this warp waits for next
@@ -711,12 +737,13 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                 // e = w + 2P j (za, pa) and e = 2P-1-w + 2P j (zb, pb).  The two start exponents are bit complements: every published
                 // power z^(2^k) goes into exactly one of them (warp-uniform choice).
                 double zar, zai, zbr, zbi, pa, pb, qr, qi, qp;
-                if constexpr (P == 8) {   // published: z^w, z^(15-w), z^16, rho^(w+1), rho^(16-w), rho^16
-                    zar = wk[(WK_POW + w) * NL]; zai = wk[(WK_POW + 17 + w) * NL]; pa = wk[(WK_POW + 34 + w) * NL];
-                    zbr = wk[(WK_POW + 15 - w) * NL]; zbi = wk[(WK_POW + 17 + 15 - w) * NL]; pb = wk[(WK_POW + 34 + 15 - w) * NL];
-                    qr = wk[(WK_POW + 16) * NL]; qi = wk[(WK_POW + 17 + 16) * NL]; qp = wk[(WK_POW + 34 + 15) * NL];
+                if constexpr (TxWk<P>::ALL) {   // published: z^w, z^(2P-1-w), z^(2P), rho^(w+1), rho^(2P-w), rho^(2P)
+                    constexpr int E = TxWk<P>::E;
+                    zar = wk[(TxWk<P>::ZR + pos) * NL]; zai = wk[(TxWk<P>::ZI + pos) * NL]; pa = wk[(TxWk<P>::RH + pos + 1) * NL];
+                    zbr = wk[(TxWk<P>::ZR + E - 1 - pos) * NL]; zbi = wk[(TxWk<P>::ZI + E - 1 - pos) * NL]; pb = wk[(TxWk<P>::RH + E - pos) * NL];
+                    qr = wk[(TxWk<P>::ZR + E) * NL]; qi = wk[(TxWk<P>::ZI + E) * NL]; qp = wk[(TxWk<P>::RH + E) * NL];
                 } else {
-                    switch (w) {   // one specialised copy per position: the choices below are compile-time there
+                    switch (pos) {   // one specialised copy per position: the choices below are compile-time there
 #define NYXB_TX_CASE(WW) case WW: tx_start_powers<WW, NPOW - 1>(wk, zar, zai, pa, zbr, zbi, pb); break;
                         NYXB_TX_CASE(0) NYXB_TX_CASE(1) NYXB_TX_CASE(2) NYXB_TX_CASE(3) NYXB_TX_CASE(4) NYXB_TX_CASE(5) NYXB_TX_CASE(6) NYXB_TX_CASE(7)
                         NYXB_TX_CASE(8) NYXB_TX_CASE(9) NYXB_TX_CASE(10) NYXB_TX_CASE(11) NYXB_TX_CASE(12) NYXB_TX_CASE(13) NYXB_TX_CASE(14)
@@ -745,7 +772,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                     zbr = nr; zbi = ni; pb = np;
                     len = len_n; sd = sd_n;
                 }
-                double* pt = sm.part + ((par * P + w) * 4) * NL + lane;
+                double* pt = sm.part + ((par * P + pos) * 4) * NL + lane;
                 pt[0] = X; pt[NL] = Y; pt[2 * NL] = Z; pt[3 * NL] = W;
                 nb_arrive(1 + c * BAR_PER_CTX + 3 + par, NT_RW);   // DONE[par]: the partial sums of this position are in shared memory
                 TX_TRACE(TR_WALK_END, c, st);
@@ -904,12 +931,14 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                     if (m <= i) w0 = fma(arow[m], kc[m * 6 * NL], w0);
                     preP = w0 + w1;
                     off2 = dur_from_seconds(S.tb.c[i + 1] * h);
+                    TX_TRACE(TR_PRE_DONE, c, i);
                     if (lead) {   // DCM of stage i+2 (its parity buffer was last read in the prologue of stage i, two barriers ago)
                         tx_dcm(gv.rot, rb_, off2, Rn);
 #pragma unroll
                         for (int k = 0; k < 9; ++k) sm.rn[(par * 9 + k) * NL + lane] = Rn[k];
                     }
                 }
+                TX_TRACE(TR_DCM_DONE, c, i);
                 if (kick_pending && i == stages / 2) {
                     if (lead && lane == 0) *(volatile int*)&s_kick = 1;
                     kick_pending = false;
@@ -930,6 +959,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                     X = (ax[0] + ax[1]) + (ax[2] + ax[3]); Y = (ay[0] + ay[1]) + (ay[2] + ay[3]);
                     Z = (az[0] + az[1]) + (az[2] + az[3]); Wt = (aw4[0] + aw4[1]) + (aw4[2] + aw4[3]);
                 }
+                TX_TRACE(TR_REDUCED, c, i);
                 const double* as = sm.as + par * AS_COUNT * NL + lane;
                 const double K0 = as[AS_K0 * NL], K1 = as[AS_K1 * NL];
                 const double aw = -K0 * Wt;
@@ -957,7 +987,9 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                     sm.kst[((i + 1) * 6 + j) * NL + lane] = vn;                                    // k_{i+1}[j]
                     if (i + 2 < stages)
                         sm.ysp[(par * 3 + j) * NL + lane] = fma(h, fma(ta[(i + 1) * NYXB_MAX_STAGES + i + 1], vn, preP), r_own);   // P_{i+2}
+                    TX_TRACE(TR_ACC_DONE, c, i);
                     nb_sync(BAR_HB, 96);   // V_{i+1} and the position components of stage i+2 of all three helpers are in shared memory
+                    TX_TRACE(TR_HB_PASSED, c, i);
                     if (i + 2 < stages) {
                         tx_prologue<P>(S, sm, lane, par, j, sm.ysp + par * 3 * NL, epoch + off2);
                         tx_mbar_arrive(&ready_bar[c][par]);   // walker inputs of stage i+2 are published
@@ -1135,7 +1167,7 @@ void nyxb_tx_build_host(int N, int M, const double* c_nm, const double* s_nm, in
 // set contexts per CTA: two sets in flight while both fit beside the table (P = 8: degrees up to ~40), one otherwise
 static int tx_contexts(const DevSetup* S, const DevTx* Tx, size_t* smem_bytes) {
     const TxBlob b = tx_blob(S->grav.N, Tx->P, Tx->n_rec, Tx->kmax);
-    for (int nctx = (Tx->P == 8 ? 2 : 1); nctx >= 1; --nctx) {
+    for (int nctx = (Tx->P <= 10 ? 2 : 1); nctx >= 1; --nctx) {
         const size_t smem = tx_layout(b.bytes, Tx->P, S->grav.N, nctx).total;
         if (smem <= 227 * 1024) { if (smem_bytes) *smem_bytes = smem; return nctx; }
     }
@@ -1144,7 +1176,7 @@ static int tx_contexts(const DevSetup* S, const DevTx* Tx, size_t* smem_bytes) {
 
 // set contexts one SM holds for this setup (one persistent CTA per SM; 0: the tables do not fit) and its dynamic shared memory
 extern "C" int nyxb_tx_occupancy(const DevSetup* S, const DevTx* Tx, size_t* smem_bytes) {
-    if (Tx->P != 8 && Tx->P != 16) return 0;
+    if (Tx->P != 8 && Tx->P != 10 && Tx->P != 16) return 0;
     return tx_contexts(S, Tx, smem_bytes);
 }
 
@@ -1160,6 +1192,7 @@ extern "C" cudaError_t nyxb_launch_tx(const DevSetup* S, const DevTx* Tx, const 
     if (nctx < 1 || grid < 1) return cudaErrorInvalidConfiguration;
 #define NYXB_TX_GO(PP, CC) tx_launch_p<PP, CC>(S, Tx, q, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_status, sink, grid, smem, b.bytes, b.off_recK, b.off_seed, b.off_sched, stream)
     if (Tx->P == 8) return nctx == 2 ? NYXB_TX_GO(8, 2) : NYXB_TX_GO(8, 1);
+    if (Tx->P == 10) return nctx == 2 ? NYXB_TX_GO(10, 2) : NYXB_TX_GO(10, 1);
     if (Tx->P == 16) return NYXB_TX_GO(16, 1);
     return cudaErrorInvalidValue;
 #undef NYXB_TX_GO

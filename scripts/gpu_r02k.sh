@@ -11,7 +11,9 @@ run() { tag=$1; shift; timeout 90 "$@" > gpurun_out/${T}_$tag.json 2> gpurun_out
 run tx_n10000 $B --kernel transposed
 run tx_n9472 $B --kernel transposed --n-traj 9472
 run tx_100k $B --kernel transposed --n-traj 100000 --steps 2 --warmup 1
-for f in tx_n10000 tx_n9472 tx_100k; do python - "$T" "$f" <<'PY'
+run tx10_n10000 $B --kernel transposed --tx-positions 10
+run tx10_100k $B --kernel transposed --n-traj 100000 --steps 2 --warmup 1 --tx-positions 10
+for f in tx_n10000 tx_n9472 tx_100k tx10_n10000 tx10_100k; do python - "$T" "$f" <<'PY'
 import json, sys
 try:
     d = json.load(open(f"gpurun_out/{sys.argv[1]}_{sys.argv[2]}.json"))
@@ -34,5 +36,5 @@ if [ "${TRACE:-0}" = 1 ]; then   # diagnostic timeline, built on the box (overwr
 touch nyx_b200/csrc/nyxb_tx.cu nyx_b200/csrc/nyxb_api.cu
 timeout 400 make -C nyx_b200/csrc EXTRA=-DNYXB_TX_TRACE > gpurun_out/${T}_make.log 2>&1; echo "make rc=$?"
 NYXB_TX_TRACE_FILE=gpurun_out/${T}_trace.bin timeout 120 python bench.py --steps 1 --warmup 0 --span-days 0.05 --n-traj 10000 --no-cpu-baseline --no-strict --kernel transposed > gpurun_out/${T}_trace_bench.log 2>&1; echo "trace bench rc=$?"
-python scripts/tx_trace.py gpurun_out/${T}_trace.bin 8 | grep -v "helper [12])" | grep -E "walk|wait|busy|post|slack|between|context|helper warp (8|9|10)" | head -24
+python scripts/tx_trace.py gpurun_out/${T}_trace.bin 8 | grep -E "walk|wait|busy|post|slack|between|context|helper warp|->" | head -44
 fi

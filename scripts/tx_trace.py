@@ -6,7 +6,7 @@ import sys
 import numpy as np
 
 CAP = 8192
-NAMES = {1: "POLL", 2: "WALK", 3: "WALK_END", 4: "DONE_WAIT", 5: "DONE_SEEN", 6: "READY", 7: "STAGES_END", 8: "CTRL_END", 9: "TOP"}
+NAMES = {1: "POLL", 2: "WALK", 3: "WALK_END", 4: "DONE_WAIT", 5: "DONE_SEEN", 6: "READY", 7: "STAGES_END", 8: "CTRL_END", 9: "TOP", 10: "PRE_DONE", 11: "DCM_DONE", 12: "REDUCED", 13: "ACC_DONE", 14: "HB_PASSED"}
 raw = np.fromfile(sys.argv[1], dtype=np.uint64).reshape(32, CAP)
 P = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 
@@ -64,6 +64,12 @@ for h in range(P, P + 6):
         if code[i] == 6: last_ready = t[i]
     bound = [t[j] - t[i] for i in range(len(t)) if code[i] == 7 for j in range(i + 1, min(i + 6, len(t))) if code[j] == 6 and stg[j] == 0][:10000]
     print(f" helper warp {h} (context {c}, helper {(h - P) % 3}):")
+    seg = {}
+    for i in range(len(t) - 1):
+        if code[i] in (6, 10, 11, 5, 12, 13, 14) and code[i + 1] in (10, 11, 4, 12, 13, 14, 6) and stg[i] == stg[i + 1] or (code[i] == 6 and code[i + 1] == 10):
+            seg.setdefault((NAMES[code[i]], NAMES[code[i + 1]]), []).append(t[i + 1] - t[i])
+    for k in (("READY", "PRE_DONE"), ("PRE_DONE", "DCM_DONE"), ("DONE_SEEN", "REDUCED"), ("REDUCED", "ACC_DONE"), ("ACC_DONE", "HB_PASSED"), ("HB_PASSED", "READY")):
+        if k in seg: stats("  " + k[0] + " -> " + k[1], seg[k])
     stats("wait for DONE", dwait); stats("post: DONE seen -> READY(i+2) published", post); stats("slack: READY published -> next DONE wait", slack)
     stats("between attempts: last stage done -> READY(0)", bound)
 # how long does a published stage wait for the walkers? lead's READY(c, stage) vs first walker start of that walk

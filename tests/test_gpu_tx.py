@@ -84,6 +84,23 @@ def test_transposed_kernel_fixed_step_tight_with_third_bodies(oracle):
         assert dr < (5e-9 if method != nb.IntegratorMethod.RungeKutta4 else 5e-8) and dv < 5e-11, (method, dr, dv)
 
 
+@pytest.mark.parametrize("positions,degree", [(10, 21), (10, 16), (8, 21), (16, 21)])
+def test_transposed_kernel_walker_positions(oracle, positions, degree):
+    """The same field walked by 8, 10 or 16 warps per set (different column schedules, published or assembled start powers):
+    fixed steps, 6 h, agreement with the oracle to round-off."""
+    mc, (st, cs, ep) = leo_ensemble(70, seed=14)
+    dyn, _ = _leo_dyn(degree)
+    prop = nb.Propagator.new(dyn, nb.IntegratorMethod.RungeKutta89, nb.IntegratorOptions.with_fixed_step_s(60.0), mode=nb.MODE_FAST)
+    eng = _tx_engine(prop)
+    eng.set_tx_positions(positions)
+    out, out_ep, det, status = eng.propagate_batch(st, cs, ep, 6 * 3600 * S)
+    assert eng.last_kernel() == nb.KERNEL_TRANSPOSED
+    ref, ref_ep, ref_det, _ = oracle_run(oracle, prop, nb.EARTH_J2000, None, st, cs, ep, 6 * 3600 * S)
+    assert (status == 0).all() and np.array_equal(det["n_steps"], ref_det["n_steps"])
+    dr, dv = max_dr_dv(out, ref)
+    assert dr < 5e-9 and dv < 5e-11, (positions, dr, dv)
+
+
 def test_transposed_kernel_time_slicing_is_bit_invisible(oracle):
     """More sets than persistent CTAs: sets are parked after every slice and resumed by whichever CTA draws their next ticket.
     Results, details and the recorded trajectories must equal the all-resident run bit for bit."""
