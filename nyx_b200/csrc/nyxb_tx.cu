@@ -54,10 +54,12 @@ enum { F_FIXED = 1, F_PREVFIXED = 2, F_RETRY = 4, F_LAST = 8, F_DONE = 16, F_BAC
 //   part [2][P][4][32]   partial sums of a stage                                                   (walkers -> helpers)
 //   as   [2][18][32]     what the helpers need to assemble that stage's acceleration later (DCM, unit vector, K0, K1, two-body factor, position)
 //   ysp  [2][3][32]      position components of a coming stage, exchanged between the three helpers
-//   helper-private: kst [16][6][32] (k_i = (V_i, A_i)), nxt / er / ycur [6][32], controller fields
+//   helper-private: kst [16][6][32] running sums of the stage states: kst[q][j] = sum_m a(q,m) V_m[j], kst[q][3+j] = sum_l a(q,l) A_l[j]
+//                   (every term but the last one of stage q); vsp [2][3][32] stage velocity (parity); nxt / er / ycur [6][32];
+//                   controller fields
 struct TxLayout {
     unsigned blob, ctx0, ctx_stride;                                  // bytes
-    unsigned wk, part, as, ysp, kst, nxt, er, ycur, rot, rn, f64, i64, i32;   // offsets inside a context
+    unsigned wk, part, as, ysp, vsp, kst, nxt, er, ycur, rot, rn, f64, i64, i32;   // offsets inside a context
     unsigned total;
 };
 __host__ __device__ inline TxLayout tx_layout(unsigned blob_bytes, int P, int N, int nctx) {
@@ -70,6 +72,7 @@ __host__ __device__ inline TxLayout tx_layout(unsigned blob_bytes, int P, int N,
     L.part = o; o += 2u * (unsigned)P * 4 * NL * 8;
     L.as = o; o += 2u * 18u * NL * 8;
     L.ysp = o; o += 2u * 3u * NL * 8;
+    L.vsp = o; o += 2u * 3u * NL * 8;
     L.kst = o; o += NYXB_MAX_STAGES * 6 * NL * 8;
     L.nxt = o; o += 6 * NL * 8;
     L.er = o; o += 6 * NL * 8;
@@ -85,7 +88,7 @@ __host__ __device__ inline TxLayout tx_layout(unsigned blob_bytes, int P, int N,
 }
 
 struct TxSm {   // typed views of one set context
-    double *wk, *part, *as, *ysp, *kst, *nxt, *er, *ycur, *rot, *rn, *f64;
+    double *wk, *part, *as, *ysp, *vsp, *kst, *nxt, *er, *ycur, *rot, *rn, *f64;
     long long* i64;
     int* i32;
 };
@@ -96,6 +99,7 @@ __device__ __forceinline__ TxSm tx_views(unsigned char* smem, const TxLayout& L,
     sm.wk = reinterpret_cast<double*>(b + L.wk); sm.part = reinterpret_cast<double*>(b + L.part);
     sm.as = reinterpret_cast<double*>(b + L.as); sm.ysp = reinterpret_cast<double*>(b + L.ysp);
     sm.kst = reinterpret_cast<double*>(b + L.kst); sm.nxt = reinterpret_cast<double*>(b + L.nxt);
+    sm.vsp = reinterpret_cast<double*>(b + L.vsp);
     sm.er = reinterpret_cast<double*>(b + L.er); sm.ycur = reinterpret_cast<double*>(b + L.ycur);
     sm.rot = reinterpret_cast<double*>(b + L.rot); sm.rn = reinterpret_cast<double*>(b + L.rn);
     sm.f64 = reinterpret_cast<double*>(b + L.f64); sm.i64 = reinterpret_cast<long long*>(b + L.i64);
@@ -652,7 +656,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
     // first prologue) is covered by the other set's stages instead of stalling the walkers.
     __shared__ __align__(8) unsigned long long ready_bar[NCTX][2];
     __shared__ int s_set[NCTX], s_fresh[NCTX], s_exit[NCTX], s_all_done[NCTX], s_slice_end[NCTX];
-    __shared__ int s_kick;   // set by context 0 half-way through its first attempt: context 1 starts then (see below)
+    __shared__ __align__(8) unsigned long long kick_bar;   // context 0 arrives half-way through its first attempt: context 1 starts then
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 #ifdef NYXB_TX_TRACE
     int tr_n = 0;
@@ -674,7 +678,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
     if (tid == 0) {
         tx_mbar_init(&tma_bar, 1);
 #pragma unroll
-        s_kick = 0;
+        tx_mbar_init(&kick_bar, 1);
 #pragma unroll
         for (int c = 0; c < NCTX; ++c) {
             s_exit[c] = 0;
@@ -796,7 +800,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
     // every such stretch).  Context 1 therefore starts when context 0 is half-way through its first attempt.
     bool kick_pending = (NCTX > 1 && c == 0);
     if (NCTX > 1 && c == 1) {
-        if (lead && lane == 0) { while (!*(volatile int*)&s_kick) __nanosleep(200); }
+        if (lead && lane == 0) tx_mbar_wait(&kick_bar, 0);
         nb_sync(BAR_HB, 96);
     }
 
@@ -824,7 +828,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
             s_exit[c] = set < 0;   // nothing fresh, nothing parked: every unfinished set is in progress in another context
         }
         nb_sync(BAR_HB, 96);
-        if (s_exit[c] && kick_pending && lead && lane == 0) *(volatile int*)&s_kick = 1;
+        if (s_exit[c] && kick_pending && lead && lane == 0) tx_mbar_arrive(&kick_bar);
         if (s_exit[c]) {
             tx_mbar_arrive(&ready_bar[c][0]);   // releases the walkers (they expect stage 0), which read s_exit and drop this context
             return;
@@ -868,10 +872,11 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
             const bool fixed = sm.i32[TXW_FLAGS * NL + lane] & F_FIXED;
             // candidate state and error estimate (instance.rs:402-414), accumulated stage by stage in the reference's order
             double nx_r = r_own, nx_v = v_own, er_r = 0.0, er_v = 0.0;
+            double v_i = v_own, acc_prev = 0.0;   // V_i of the stage being prepared, A_{i-1}
             int rc_acc = 0;
             double Rn[9];
             // ---- prime the pipeline: stage 0 (the state itself) and stage 1 (needs only V_0 = v): instance.rs:369-394
-            sm.kst[(0 * 6 + j) * NL + lane] = v_own;                 // k_0[j] = V_0
+            sm.vsp[(0 * 3 + j) * NL + lane] = v_own;                 // V_0
             sm.ysp[(0 * 3 + j) * NL + lane] = r_own;                 // P_0
             const long long off1 = (stages > 1) ? dur_from_seconds(S.tb.c[0] * h) : 0;
             if (stages > 1) sm.ysp[(1 * 3 + j) * NL + lane] = fma(h, ta[0] * v_own, r_own);   // P_1 = r + h a_10 V_0
@@ -906,30 +911,31 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                 // -- slack: everything that does not need the acceleration of stage i
                 double preV = 0.0, preP = 0.0;
                 long long off2 = 0;
-                {
-                    const double vi = sm.kst[(i * 6 + j) * NL + lane];   // V_i
-                    if (!fixed) er_r = fma(h * S.tb.e[i], vi, er_r);
-                    nx_r = fma(h * S.tb.b[i], vi, nx_r);
-                }
+                if (!fixed) er_r = fma(h * S.tb.e[i], v_i, er_r);
+                nx_r = fma(h * S.tb.b[i], v_i, nx_r);
                 if (j == 1 && i == 0 && gv.rot.kind != 0)
                     rb_next = tx_rot_base(gv.rot, epoch + (fixed ? sm.i64[TXI_STEP * NL + lane] : dur_from_seconds(h)));
-                if (i + 1 < stages) {   // V_{i+1} = v + h sum_{l<=i} a_{i+1,l} A_l: all terms but the last
-                    const double* arow = ta + i * NYXB_MAX_STAGES;
-                    const double* kc = sm.kst + (3 + j) * NL + lane;
-                    double w0 = 0.0, w1 = 0.0;
-                    int l = 0;
-                    for (; l + 1 < i; l += 2) { w0 = fma(arow[l], kc[l * 6 * NL], w0); w1 = fma(arow[l + 1], kc[(l + 1) * 6 * NL], w1); }
-                    if (l < i) w0 = fma(arow[l], kc[l * 6 * NL], w0);
-                    preV = w0 + w1;
+                // Stage states (instance.rs:369-394) as running sums: what became known in the previous stage, A_{i-1} and V_i, is added
+                // to the sum of every later stage q (independent updates, ascending index as in the reference); the sums of the
+                // stages needed next — V_{i+1}: all A_l, l < i; P_{i+2}: all V_m, m <= i — are complete after this and stay in
+                // registers; their last terms are added when the acceleration of stage i arrives.
+                if (i >= 1) {
+                    double* sv = sm.kst + (3 + j) * NL + lane;
+                    for (int q = i + 1; q < stages; ++q) {
+                        const double a = ta[(q - 1) * NYXB_MAX_STAGES + i - 1];
+                        const double sum = (i == 1) ? a * acc_prev : fma(a, acc_prev, sv[q * 6 * NL]);
+                        sv[q * 6 * NL] = sum;
+                        if (q == i + 1) preV = sum;
+                    }
                 }
-                if (i + 2 < stages) {   // P_{i+2} = r + h sum_{m<=i+1} a_{i+2,m} V_m: all terms but the last (V_i is known)
-                    const double* arow = ta + (i + 1) * NYXB_MAX_STAGES;
-                    const double* kc = sm.kst + j * NL + lane;
-                    double w0 = 0.0, w1 = 0.0;
-                    int m = 0;
-                    for (; m + 1 <= i; m += 2) { w0 = fma(arow[m], kc[m * 6 * NL], w0); w1 = fma(arow[m + 1], kc[(m + 1) * 6 * NL], w1); }
-                    if (m <= i) w0 = fma(arow[m], kc[m * 6 * NL], w0);
-                    preP = w0 + w1;
+                if (i + 2 < stages) {
+                    double* sp = sm.kst + j * NL + lane;
+                    for (int q = i + 2; q < stages; ++q) {
+                        const double a = ta[(q - 1) * NYXB_MAX_STAGES + i];
+                        const double sum = (i == 0) ? a * v_i : fma(a, v_i, sp[q * 6 * NL]);
+                        sp[q * 6 * NL] = sum;
+                        if (q == i + 2) preP = sum;
+                    }
                     off2 = dur_from_seconds(S.tb.c[i + 1] * h);
                     TX_TRACE(TR_PRE_DONE, c, i);
                     if (lead) {   // DCM of stage i+2 (its parity buffer was last read in the prologue of stage i, two barriers ago)
@@ -940,7 +946,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                 }
                 TX_TRACE(TR_DCM_DONE, c, i);
                 if (kick_pending && i == stages / 2) {
-                    if (lead && lane == 0) *(volatile int*)&s_kick = 1;
+                    if (lead && lane == 0) tx_mbar_arrive(&kick_bar);
                     kick_pending = false;
                 }
                 TX_TRACE(TR_DONE_WAIT, c, i);
@@ -971,7 +977,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                     const double hz = (i > 0) ? h * 0.0 : 0.0;
                     yy[0] = as[AS_P0 * NL]; yy[1] = as[AS_P1 * NL]; yy[2] = as[AS_P2 * NL];
 #pragma unroll
-                    for (int e = 0; e < 3; ++e) yy[3 + e] = sm.kst[(i * 6 + e) * NL + lane];   // V_i
+                    for (int e = 0; e < 3; ++e) yy[3 + e] = sm.vsp[(par * 3 + e) * NL + lane];   // V_i
                     yy[6] = sm.f64[TXF_CR * NL + lane] + hz; yy[7] = sm.f64[TXF_CD * NL + lane] + hz; yy[8] = sm.f64[TXF_PM * NL + lane] + hz;
                     const long long offi = (i > 0) ? dur_from_seconds(S.tb.c[i - 1] * h) : 0;
                     const int rcx = tx_extra(S, sm.f64[TXF_DRY * NL + lane], sm.f64[TXF_EXTRA * NL + lane], sm.f64[TXF_SRPA * NL + lane],
@@ -979,12 +985,13 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                     acc += (j == 0) ? aa[0] : (j == 1 ? aa[1] : aa[2]);
                     if (rcx && !rc_acc) rc_acc = rcx | ((i + 1) << 8);
                 }
-                sm.kst[(i * 6 + 3 + j) * NL + lane] = acc;     // k_i[3+j] = A_i
+                acc_prev = acc;                                 // A_i
                 if (!fixed) er_v = fma(h * S.tb.e[i], acc, er_v);
                 nx_v = fma(h * S.tb.b[i], acc, nx_v);
                 if (i + 1 < stages) {
                     const double vn = fma(h, fma(ta[i * NYXB_MAX_STAGES + i], acc, preV), v_own);   // V_{i+1}
-                    sm.kst[((i + 1) * 6 + j) * NL + lane] = vn;                                    // k_{i+1}[j]
+                    sm.vsp[((par ^ 1) * 3 + j) * NL + lane] = vn;                                  // V_{i+1}
+                    v_i = vn;
                     if (i + 2 < stages)
                         sm.ysp[(par * 3 + j) * NL + lane] = fma(h, fma(ta[(i + 1) * NYXB_MAX_STAGES + i + 1], vn, preP), r_own);   // P_{i+2}
                     TX_TRACE(TR_ACC_DONE, c, i);
@@ -1028,7 +1035,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
         }
 
         if (kick_pending) {
-            if (lead && lane == 0) *(volatile int*)&s_kick = 1;
+            if (lead && lane == 0) tx_mbar_arrive(&kick_bar);
             kick_pending = false;
         }
         // ---------------------------------------------------------------- park the set (== final outputs when it is done)
