@@ -54,12 +54,10 @@ enum { F_FIXED = 1, F_PREVFIXED = 2, F_RETRY = 4, F_LAST = 8, F_DONE = 16, F_BAC
 //   part [2][P][4][32]   partial sums of a stage                                                   (walkers -> helpers)
 //   as   [2][18][32]     what the helpers need to assemble that stage's acceleration later (DCM, unit vector, K0, K1, two-body factor, position)
 //   ysp  [2][3][32]      position components of a coming stage, exchanged between the three helpers
-//   helper-private: kst [16][6][32] running sums of the stage states: kst[q][j] = sum_m a(q,m) V_m[j], kst[q][3+j] = sum_l a(q,l) A_l[j]
-//                   (every term but the last one of stage q); vsp [2][3][32] stage velocity (parity); nxt / er / ycur [6][32];
-//                   controller fields
+//   helper-private: kst [16][6][32] (k_i = (V_i, A_i)), nxt / er / ycur [6][32], controller fields
 struct TxLayout {
     unsigned blob, ctx0, ctx_stride;                                  // bytes
-    unsigned wk, part, as, ysp, vsp, kst, nxt, er, ycur, rot, rn, f64, i64, i32;   // offsets inside a context
+    unsigned wk, part, as, ysp, kst, nxt, er, ycur, rot, rn, f64, i64, i32;   // offsets inside a context
     unsigned total;
 };
 __host__ __device__ inline TxLayout tx_layout(unsigned blob_bytes, int P, int N, int nctx) {
@@ -72,7 +70,6 @@ __host__ __device__ inline TxLayout tx_layout(unsigned blob_bytes, int P, int N,
     L.part = o; o += 2u * (unsigned)P * 4 * NL * 8;
     L.as = o; o += 2u * 18u * NL * 8;
     L.ysp = o; o += 2u * 3u * NL * 8;
-    L.vsp = o; o += 2u * 3u * NL * 8;
     L.kst = o; o += NYXB_MAX_STAGES * 6 * NL * 8;
     L.nxt = o; o += 6 * NL * 8;
     L.er = o; o += 6 * NL * 8;
@@ -88,7 +85,7 @@ __host__ __device__ inline TxLayout tx_layout(unsigned blob_bytes, int P, int N,
 }
 
 struct TxSm {   // typed views of one set context
-    double *wk, *part, *as, *ysp, *vsp, *kst, *nxt, *er, *ycur, *rot, *rn, *f64;
+    double *wk, *part, *as, *ysp, *kst, *nxt, *er, *ycur, *rot, *rn, *f64;
     long long* i64;
     int* i32;
 };
@@ -99,7 +96,6 @@ __device__ __forceinline__ TxSm tx_views(unsigned char* smem, const TxLayout& L,
     sm.wk = reinterpret_cast<double*>(b + L.wk); sm.part = reinterpret_cast<double*>(b + L.part);
     sm.as = reinterpret_cast<double*>(b + L.as); sm.ysp = reinterpret_cast<double*>(b + L.ysp);
     sm.kst = reinterpret_cast<double*>(b + L.kst); sm.nxt = reinterpret_cast<double*>(b + L.nxt);
-    sm.vsp = reinterpret_cast<double*>(b + L.vsp);
     sm.er = reinterpret_cast<double*>(b + L.er); sm.ycur = reinterpret_cast<double*>(b + L.ycur);
     sm.rot = reinterpret_cast<double*>(b + L.rot); sm.rn = reinterpret_cast<double*>(b + L.rn);
     sm.f64 = reinterpret_cast<double*>(b + L.f64); sm.i64 = reinterpret_cast<long long*>(b + L.i64);
@@ -209,14 +205,14 @@ __device__ __noinline__ void tx_field_offset(const DevSetup& S, long long t_ns, 
         S6 = fma(wv, (P23).y, S6);                          \
         Q = Qn;                                             \
     }
+// (Q, c1, g, S5, S6) arrive set up for this column — Q = rho^m x seed, c1 = (2m+1) u rho, g = (2m+1) rho^2, S5 / S6 the column's seed
+// W term — because the caller sets the NEXT column up right behind the close of this one, in the same basic block, so the two
+// short dependent chains overlap.
 __device__ __forceinline__ void tx_column(const double2*& A, const double*& K, double2& a01, double2& a23, double& kk, int len,
-                                          double q, double pd1, double pd2, double al, double ub, double r2, double rr, double ii,
+                                          double Q, double c1, double g, double S5, double S6, double dc, double dg, double rr, double ii,
                                           double& X, double& Y, double& Z, double& W) {
-    double Q = q;
-    double c1 = al * ub, m2 = 0.0, d = 0.0, g = al * r2;   // entry n = m: (2m+1) u rho, and (n+m)(n-m) = 0
-    const double dc = ub + ub, dg = r2 + r2;
+    double m2 = 0.0, d = 0.0;   // entry n = m: (n+m)(n-m) = 0
     double S1 = 0.0, S2 = 0.0, S3 = 0.0, S4 = 0.0;
-    double S5 = Q * pd1, S6 = Q * pd2;                     // the column's seed W term
     double2 b01, b23;
     double bk;
 #pragma unroll 2
@@ -765,16 +761,22 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                 // one loop over the columns; the roles of the two sequences are swapped after every column.  The seeds of the next
                 // column are fetched before the current one is walked.
                 int len = my[3];
-                double4 sd = *reinterpret_cast<const double4*>(colseed + 4 * my[2]);
+                const double dc = ub + ub, dg = r2 + r2;
+                double cQ, cc1, cg, cS5, cS6;   // set-up of the column about to be walked
+                {
+                    const double4 sd = *reinterpret_cast<const double4*>(colseed + 4 * my[2]);
+                    cQ = pa * sd.x; cc1 = sd.w * ub; cg = sd.w * r2; cS5 = cQ * sd.y; cS6 = cQ * sd.z;
+                }
                 for (int k = 0; k < ncol; ++k) {
-                    const int len_n = my[5 + 2 * k];   // the schedule rows end with a null column
+                    const int len_n = my[5 + 2 * k];   // the schedule rows end with a null column (all-zero seeds)
                     const double4 sd_n = *reinterpret_cast<const double4*>(colseed + 4 * my[4 + 2 * k]);
-                    tx_column(A, K, a01, a23, kk, len, pa * sd.x, sd.y, sd.z, sd.w, ub, r2, zar, zai, X, Y, Z, W);
+                    tx_column(A, K, a01, a23, kk, len, cQ, cc1, cg, cS5, cS6, dc, dg, zar, zai, X, Y, Z, W);
                     const double nr = fma(zar, qr, -(zai * qi));
                     const double ni = fma(zar, qi, zai * qr), np = pa * qp;
                     zar = zbr; zai = zbi; pa = pb;
                     zbr = nr; zbi = ni; pb = np;
-                    len = len_n; sd = sd_n;
+                    cQ = pa * sd_n.x; cc1 = sd_n.w * ub; cg = sd_n.w * r2; cS5 = cQ * sd_n.y; cS6 = cQ * sd_n.z;
+                    len = len_n;
                 }
                 double* pt = sm.part + ((par * P + pos) * 4) * NL + lane;
                 pt[0] = X; pt[NL] = Y; pt[2 * NL] = Z; pt[3 * NL] = W;
@@ -872,11 +874,10 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
             const bool fixed = sm.i32[TXW_FLAGS * NL + lane] & F_FIXED;
             // candidate state and error estimate (instance.rs:402-414), accumulated stage by stage in the reference's order
             double nx_r = r_own, nx_v = v_own, er_r = 0.0, er_v = 0.0;
-            double v_i = v_own, acc_prev = 0.0;   // V_i of the stage being prepared, A_{i-1}
             int rc_acc = 0;
             double Rn[9];
             // ---- prime the pipeline: stage 0 (the state itself) and stage 1 (needs only V_0 = v): instance.rs:369-394
-            sm.vsp[(0 * 3 + j) * NL + lane] = v_own;                 // V_0
+            sm.kst[(0 * 6 + j) * NL + lane] = v_own;                 // k_0[j] = V_0
             sm.ysp[(0 * 3 + j) * NL + lane] = r_own;                 // P_0
             const long long off1 = (stages > 1) ? dur_from_seconds(S.tb.c[0] * h) : 0;
             if (stages > 1) sm.ysp[(1 * 3 + j) * NL + lane] = fma(h, ta[0] * v_own, r_own);   // P_1 = r + h a_10 V_0
@@ -911,31 +912,30 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                 // -- slack: everything that does not need the acceleration of stage i
                 double preV = 0.0, preP = 0.0;
                 long long off2 = 0;
-                if (!fixed) er_r = fma(h * S.tb.e[i], v_i, er_r);
-                nx_r = fma(h * S.tb.b[i], v_i, nx_r);
+                {
+                    const double vi = sm.kst[(i * 6 + j) * NL + lane];   // V_i
+                    if (!fixed) er_r = fma(h * S.tb.e[i], vi, er_r);
+                    nx_r = fma(h * S.tb.b[i], vi, nx_r);
+                }
                 if (j == 1 && i == 0 && gv.rot.kind != 0)
                     rb_next = tx_rot_base(gv.rot, epoch + (fixed ? sm.i64[TXI_STEP * NL + lane] : dur_from_seconds(h)));
-                // Stage states (instance.rs:369-394) as running sums: what became known in the previous stage, A_{i-1} and V_i, is added
-                // to the sum of every later stage q (independent updates, ascending index as in the reference); the sums of the
-                // stages needed next — V_{i+1}: all A_l, l < i; P_{i+2}: all V_m, m <= i — are complete after this and stay in
-                // registers; their last terms are added when the acceleration of stage i arrives.
-                if (i >= 1) {
-                    double* sv = sm.kst + (3 + j) * NL + lane;
-                    for (int q = i + 1; q < stages; ++q) {
-                        const double a = ta[(q - 1) * NYXB_MAX_STAGES + i - 1];
-                        const double sum = (i == 1) ? a * acc_prev : fma(a, acc_prev, sv[q * 6 * NL]);
-                        sv[q * 6 * NL] = sum;
-                        if (q == i + 1) preV = sum;
-                    }
+                if (i + 1 < stages) {   // V_{i+1} = v + h sum_{l<=i} a_{i+1,l} A_l: all terms but the last
+                    const double* arow = ta + i * NYXB_MAX_STAGES;
+                    const double* kc = sm.kst + (3 + j) * NL + lane;
+                    double w0 = 0.0, w1 = 0.0;
+                    int l = 0;
+                    for (; l + 1 < i; l += 2) { w0 = fma(arow[l], kc[l * 6 * NL], w0); w1 = fma(arow[l + 1], kc[(l + 1) * 6 * NL], w1); }
+                    if (l < i) w0 = fma(arow[l], kc[l * 6 * NL], w0);
+                    preV = w0 + w1;
                 }
-                if (i + 2 < stages) {
-                    double* sp = sm.kst + j * NL + lane;
-                    for (int q = i + 2; q < stages; ++q) {
-                        const double a = ta[(q - 1) * NYXB_MAX_STAGES + i];
-                        const double sum = (i == 0) ? a * v_i : fma(a, v_i, sp[q * 6 * NL]);
-                        sp[q * 6 * NL] = sum;
-                        if (q == i + 2) preP = sum;
-                    }
+                if (i + 2 < stages) {   // P_{i+2} = r + h sum_{m<=i+1} a_{i+2,m} V_m: all terms but the last (V_i is known)
+                    const double* arow = ta + (i + 1) * NYXB_MAX_STAGES;
+                    const double* kc = sm.kst + j * NL + lane;
+                    double w0 = 0.0, w1 = 0.0;
+                    int m = 0;
+                    for (; m + 1 <= i; m += 2) { w0 = fma(arow[m], kc[m * 6 * NL], w0); w1 = fma(arow[m + 1], kc[(m + 1) * 6 * NL], w1); }
+                    if (m <= i) w0 = fma(arow[m], kc[m * 6 * NL], w0);
+                    preP = w0 + w1;
                     off2 = dur_from_seconds(S.tb.c[i + 1] * h);
                     TX_TRACE(TR_PRE_DONE, c, i);
                     if (lead) {   // DCM of stage i+2 (its parity buffer was last read in the prologue of stage i, two barriers ago)
@@ -977,7 +977,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                     const double hz = (i > 0) ? h * 0.0 : 0.0;
                     yy[0] = as[AS_P0 * NL]; yy[1] = as[AS_P1 * NL]; yy[2] = as[AS_P2 * NL];
 #pragma unroll
-                    for (int e = 0; e < 3; ++e) yy[3 + e] = sm.vsp[(par * 3 + e) * NL + lane];   // V_i
+                    for (int e = 0; e < 3; ++e) yy[3 + e] = sm.kst[(i * 6 + e) * NL + lane];   // V_i
                     yy[6] = sm.f64[TXF_CR * NL + lane] + hz; yy[7] = sm.f64[TXF_CD * NL + lane] + hz; yy[8] = sm.f64[TXF_PM * NL + lane] + hz;
                     const long long offi = (i > 0) ? dur_from_seconds(S.tb.c[i - 1] * h) : 0;
                     const int rcx = tx_extra(S, sm.f64[TXF_DRY * NL + lane], sm.f64[TXF_EXTRA * NL + lane], sm.f64[TXF_SRPA * NL + lane],
@@ -985,13 +985,12 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                     acc += (j == 0) ? aa[0] : (j == 1 ? aa[1] : aa[2]);
                     if (rcx && !rc_acc) rc_acc = rcx | ((i + 1) << 8);
                 }
-                acc_prev = acc;                                 // A_i
+                sm.kst[(i * 6 + 3 + j) * NL + lane] = acc;     // k_i[3+j] = A_i
                 if (!fixed) er_v = fma(h * S.tb.e[i], acc, er_v);
                 nx_v = fma(h * S.tb.b[i], acc, nx_v);
                 if (i + 1 < stages) {
                     const double vn = fma(h, fma(ta[i * NYXB_MAX_STAGES + i], acc, preV), v_own);   // V_{i+1}
-                    sm.vsp[((par ^ 1) * 3 + j) * NL + lane] = vn;                                  // V_{i+1}
-                    v_i = vn;
+                    sm.kst[((i + 1) * 6 + j) * NL + lane] = vn;                                    // k_{i+1}[j]
                     if (i + 2 < stages)
                         sm.ysp[(par * 3 + j) * NL + lane] = fma(h, fma(ta[(i + 1) * NYXB_MAX_STAGES + i + 1], vn, preP), r_own);   // P_{i+2}
                     TX_TRACE(TR_ACC_DONE, c, i);
