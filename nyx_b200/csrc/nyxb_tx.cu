@@ -36,8 +36,17 @@
 #define TX_MINB 2   /* resident CTAs per SM the kernel is compiled for (register cap 65536 / (256 * TX_MINB)) */
 #endif
 
+#ifndef NYXB_TX_TT
+#define NYXB_TX_TT 1
+#endif
+
 namespace {
-constexpr int NL = 32;
+// Built twice (Makefile): TT = 1 — a set is 32 trajectories, a walker lane carries one; TT = 2 — a set is 64 trajectories, a walker
+// lane carries trajectories l and l + 32 through the same record loads (half the shared-memory wavefronts and non-FP64 issue slots
+// per FP64 instruction), and every helper role is played by two warps, one per half of the set.
+constexpr int TT = NYXB_TX_TT;
+constexpr int NL = 32 * TT;    // trajectories per set: stride of every per-trajectory shared-memory array
+constexpr int HW = 3 * TT;     // helper warps per set context
 constexpr unsigned FULL = 0xffffffffu;
 
 // ---- per-trajectory controller state kept in shared memory ([field][lane])
@@ -191,28 +200,40 @@ __device__ __noinline__ void tx_field_offset(const DevSetup& S, long long t_ns, 
 // warps per scheduler keep the FP64 pipe fed.  12 FP64 instructions per entry.  The loop is unrolled by hand over two register
 // sets for the prefetched record so that no register-to-register moves are left in it (the compiler's own rotation cost 14
 // IMAD.MOV per two entries and made the loop issue-bound, profiles/r02g_tx_ncu_summary.txt).
-#define NYXB_TX_ENTRY(P01, P23, PK)                         \
-    {                                                       \
-        const double Qn = fma(c1, Q, -m2);                  \
-        c1 += dc; d += g; g += dg;                          \
-        m2 = d * Q;                                         \
-        S1 = fma(Q, (P01).x, S1);                           \
-        S2 = fma(Q, (P01).y, S2);                           \
-        S3 = fma(Q, (P23).x, S3);                           \
-        S4 = fma(Q, (P23).y, S4);                           \
-        const double wv = (PK) * Qn;                        \
-        S5 = fma(wv, (P23).x, S5);                          \
-        S6 = fma(wv, (P23).y, S6);                          \
-        Q = Qn;                                             \
+// per-trajectory registers of a walker lane (TT of them)
+struct TxLaneState {
+    double ub, r2, dc, dg;                  // u rho, rho^2 and their doubles
+    double zar, zai, pa, zbr, zbi, pb;      // current powers of the two exponent sequences
+    double qr, qi, qp;                      // common ratio z^(2P), rho^(2P)
+    double X, Y, Z, W;                      // partial sums of this position
+    double cQ, cc1, cg, cS5, cS6;           // set-up of the column about to be walked
+};
+#define NYXB_TX_ENTRY(P01, P23, PK)                             \
+    _Pragma("unroll") for (int u = 0; u < TT; ++u) {            \
+        const double Qn = fma(c1[u], Q[u], -m2[u]);             \
+        c1[u] += t[u].dc; d[u] += g[u]; g[u] += t[u].dg;        \
+        m2[u] = d[u] * Q[u];                                    \
+        S1[u] = fma(Q[u], (P01).x, S1[u]);                      \
+        S2[u] = fma(Q[u], (P01).y, S2[u]);                      \
+        S3[u] = fma(Q[u], (P23).x, S3[u]);                      \
+        S4[u] = fma(Q[u], (P23).y, S4[u]);                      \
+        const double wv = (PK) * Qn;                            \
+        S5[u] = fma(wv, (P23).x, S5[u]);                        \
+        S6[u] = fma(wv, (P23).y, S6[u]);                        \
+        Q[u] = Qn;                                              \
     }
-// (Q, c1, g, S5, S6) arrive set up for this column — Q = rho^m x seed, c1 = (2m+1) u rho, g = (2m+1) rho^2, S5 / S6 the column's seed
-// W term — because the caller sets the NEXT column up right behind the close of this one, in the same basic block, so the two
-// short dependent chains overlap.
+// t[u].(cQ, cc1, cg, cS5, cS6) arrive set up for this column — Q = rho^m x seed, c1 = (2m+1) u rho, g = (2m+1) rho^2, S5 / S6 the
+// column's seed W term — because the caller sets the NEXT column up right behind the close of this one, in the same basic block, so
+// the two short dependent chains overlap.  Every record load serves the TT trajectories of the lane.
 __device__ __forceinline__ void tx_column(const double2*& A, const double*& K, double2& a01, double2& a23, double& kk, int len,
-                                          double Q, double c1, double g, double S5, double S6, double dc, double dg, double rr, double ii,
-                                          double& X, double& Y, double& Z, double& W) {
-    double m2 = 0.0, d = 0.0;   // entry n = m: (n+m)(n-m) = 0
-    double S1 = 0.0, S2 = 0.0, S3 = 0.0, S4 = 0.0;
+                                          TxLaneState (&t)[TT]) {
+    double Q[TT], c1[TT], g[TT], m2[TT], d[TT], S1[TT], S2[TT], S3[TT], S4[TT], S5[TT], S6[TT];
+#pragma unroll
+    for (int u = 0; u < TT; ++u) {
+        Q[u] = t[u].cQ; c1[u] = t[u].cc1; g[u] = t[u].cg; S5[u] = t[u].cS5; S6[u] = t[u].cS6;
+        m2[u] = 0.0; d[u] = 0.0;   // entry n = m: (n+m)(n-m) = 0
+        S1[u] = 0.0; S2[u] = 0.0; S3[u] = 0.0; S4[u] = 0.0;
+    }
     double2 b01, b23;
     double bk;
 #pragma unroll 2
@@ -224,10 +245,14 @@ __device__ __forceinline__ void tx_column(const double2*& A, const double*& K, d
         A += 4; K += 2;
     }
     // close the column: apply its (cos, sin)((m-1) lambda) cos^(m-1)(phi)
-    X = fma(rr, S1, fma(ii, S2, X));
-    Y = fma(rr, S2, fma(-ii, S1, Y));
-    Z = fma(rr, S3, fma(ii, S4, Z));
-    W = fma(rr, S5, fma(ii, S6, W));
+#pragma unroll
+    for (int u = 0; u < TT; ++u) {
+        const double rr = t[u].zar, ii = t[u].zai;
+        t[u].X = fma(rr, S1[u], fma(ii, S2[u], t[u].X));
+        t[u].Y = fma(rr, S2[u], fma(-ii, S1[u], t[u].Y));
+        t[u].Z = fma(rr, S3[u], fma(ii, S4[u], t[u].Z));
+        t[u].W = fma(rr, S5[u], fma(ii, S6[u], t[u].W));
+    }
 }
 
 // ---- instance.rs:149-196: choose the step of the next attempt (regular, or the final fixed step to the stop time)
@@ -638,7 +663,7 @@ __device__ __forceinline__ void tx_start_powers(const double* wk, double& zar, d
 }
 
 template <int P, int NCTX>
-__global__ void __launch_bounds__((P + 3 * NCTX) * 32, 1)
+__global__ void __launch_bounds__((P + HW * NCTX) * 32, 1)
 nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, const __grid_constant__ DevTxQueue q, size_t n,
           const double* __restrict__ state, const double* __restrict__ consts, const long long* __restrict__ epoch0,
           long long end_epoch, long long* step_io, double* out_state, long long* out_epoch, int* out_status, const DevSink sink,
@@ -651,7 +676,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
     // context has a stage ready, so the serial stretch between two step attempts of one set (error norm, controller, commit,
     // first prologue) is covered by the other set's stages instead of stalling the walkers.
     __shared__ __align__(8) unsigned long long ready_bar[NCTX][2];
-    __shared__ int s_set[NCTX], s_fresh[NCTX], s_exit[NCTX], s_all_done[NCTX], s_slice_end[NCTX];
+    __shared__ int s_set[NCTX], s_fresh[NCTX], s_exit[NCTX], s_done_half[NCTX][TT], s_slice_end[NCTX];
     __shared__ __align__(8) unsigned long long kick_bar;   // context 0 arrives half-way through its first attempt: context 1 starts then
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 #ifdef NYXB_TX_TRACE
@@ -659,7 +684,9 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
 #endif
     constexpr int NPOW = 6;   // P = 16: z^(2^k), k < NPOW: bits of the exponents below 2P, and the common ratio z^(2P)
     static_assert(P == 8 || P == 10 || P == 16, "walker positions");
-    constexpr int NT_RW = (P + 3) * 32;   // threads on a READY / DONE barrier: the walkers + the three helpers of the context
+    static_assert(TT == 1 || NCTX == 1, "sets of 64 trajectories: one set context per CTA");
+    constexpr int NT_RW = (P + HW) * 32;
+    constexpr int NT_HB = HW * 32;   // threads on the helpers' own barrier   // threads on a READY / DONE barrier: the walkers + the three helpers of the context
     // named barriers of context c: HB (helpers among themselves), READY[parity], DONE[parity]
     constexpr int BAR_PER_CTX = 5;
     const int N = S.grav.N;
@@ -678,8 +705,8 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
 #pragma unroll
         for (int c = 0; c < NCTX; ++c) {
             s_exit[c] = 0;
-            tx_mbar_init(&ready_bar[c][0], 96);
-            tx_mbar_init(&ready_bar[c][1], 96);
+            tx_mbar_init(&ready_bar[c][0], NT_HB);
+            tx_mbar_init(&ready_bar[c][1], NT_HB);
         }
     }
     __syncthreads();
@@ -731,29 +758,34 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                 pref = (c + 1) % NCTX;
                 TX_TRACE(TR_WALK, c, st);
                 const TxSm sm = tx_views(smem, L, c, N);
-                const double* wk = sm.wk + par * TxWk<P>::COUNT * NL + lane;
-                const double ub = wk[WK_UB * NL], r2 = wk[WK_R2 * NL];
                 // z^e = (cos, sin)(e lambda) cos^e(phi) and rho^(e+1) for the two interleaved exponent sequences of this position:
-                // e = w + 2P j (za, pa) and e = 2P-1-w + 2P j (zb, pb).  The two start exponents are bit complements: every published
-                // power z^(2^k) goes into exactly one of them (warp-uniform choice).
-                double zar, zai, zbr, zbi, pa, pb, qr, qi, qp;
-                if constexpr (TxWk<P>::ALL) {   // published: z^w, z^(2P-1-w), z^(2P), rho^(w+1), rho^(2P-w), rho^(2P)
-                    constexpr int E = TxWk<P>::E;
-                    zar = wk[(TxWk<P>::ZR + pos) * NL]; zai = wk[(TxWk<P>::ZI + pos) * NL]; pa = wk[(TxWk<P>::RH + pos + 1) * NL];
-                    zbr = wk[(TxWk<P>::ZR + E - 1 - pos) * NL]; zbi = wk[(TxWk<P>::ZI + E - 1 - pos) * NL]; pb = wk[(TxWk<P>::RH + E - pos) * NL];
-                    qr = wk[(TxWk<P>::ZR + E) * NL]; qi = wk[(TxWk<P>::ZI + E) * NL]; qp = wk[(TxWk<P>::RH + E) * NL];
-                } else {
-                    switch (pos) {   // one specialised copy per position: the choices below are compile-time there
-#define NYXB_TX_CASE(WW) case WW: tx_start_powers<WW, NPOW - 1>(wk, zar, zai, pa, zbr, zbi, pb); break;
-                        NYXB_TX_CASE(0) NYXB_TX_CASE(1) NYXB_TX_CASE(2) NYXB_TX_CASE(3) NYXB_TX_CASE(4) NYXB_TX_CASE(5) NYXB_TX_CASE(6) NYXB_TX_CASE(7)
-                        NYXB_TX_CASE(8) NYXB_TX_CASE(9) NYXB_TX_CASE(10) NYXB_TX_CASE(11) NYXB_TX_CASE(12) NYXB_TX_CASE(13) NYXB_TX_CASE(14)
-                        default: tx_start_powers<15, NPOW - 1>(wk, zar, zai, pa, zbr, zbi, pb); break;
+                // e = pos + 2P j (za, pa) and e = 2P-1-pos + 2P j (zb, pb)
+                TxLaneState t[TT];
+#pragma unroll
+                for (int u = 0; u < TT; ++u) {
+                    const double* wk = sm.wk + par * TxWk<P>::COUNT * NL + u * 32 + lane;
+                    t[u].ub = wk[WK_UB * NL]; t[u].r2 = wk[WK_R2 * NL];
+                    t[u].dc = t[u].ub + t[u].ub; t[u].dg = t[u].r2 + t[u].r2;
+                    if constexpr (TxWk<P>::ALL) {   // published: z^pos, z^(2P-1-pos), z^(2P), rho^(pos+1), rho^(2P-pos), rho^(2P)
+                        constexpr int E = TxWk<P>::E;
+                        t[u].zar = wk[(TxWk<P>::ZR + pos) * NL]; t[u].zai = wk[(TxWk<P>::ZI + pos) * NL];
+                        t[u].pa = wk[(TxWk<P>::RH + pos + 1) * NL];
+                        t[u].zbr = wk[(TxWk<P>::ZR + E - 1 - pos) * NL]; t[u].zbi = wk[(TxWk<P>::ZI + E - 1 - pos) * NL];
+                        t[u].pb = wk[(TxWk<P>::RH + E - pos) * NL];
+                        t[u].qr = wk[(TxWk<P>::ZR + E) * NL]; t[u].qi = wk[(TxWk<P>::ZI + E) * NL]; t[u].qp = wk[(TxWk<P>::RH + E) * NL];
+                    } else {
+                        switch (pos) {   // one specialised copy per position: the choices below are compile-time there
+#define NYXB_TX_CASE(WW) case WW: tx_start_powers<WW, NPOW - 1>(wk, t[u].zar, t[u].zai, t[u].pa, t[u].zbr, t[u].zbi, t[u].pb); break;
+                            NYXB_TX_CASE(0) NYXB_TX_CASE(1) NYXB_TX_CASE(2) NYXB_TX_CASE(3) NYXB_TX_CASE(4) NYXB_TX_CASE(5) NYXB_TX_CASE(6) NYXB_TX_CASE(7)
+                            NYXB_TX_CASE(8) NYXB_TX_CASE(9) NYXB_TX_CASE(10) NYXB_TX_CASE(11) NYXB_TX_CASE(12) NYXB_TX_CASE(13) NYXB_TX_CASE(14)
+                            default: tx_start_powers<15, NPOW - 1>(wk, t[u].zar, t[u].zai, t[u].pa, t[u].zbr, t[u].zbi, t[u].pb); break;
 #undef NYXB_TX_CASE
+                        }
+                        t[u].qr = wk[(WK_POW + 3 * (NPOW - 1)) * NL]; t[u].qi = wk[(WK_POW + 3 * (NPOW - 1) + 1) * NL];   // z^(2P)
+                        t[u].qp = wk[(WK_POW + 3 * (NPOW - 1) + 2) * NL];                                             // rho^(2P)
                     }
-                    qr = wk[(WK_POW + 3 * (NPOW - 1)) * NL]; qi = wk[(WK_POW + 3 * (NPOW - 1) + 1) * NL];   // z^(2P)
-                    qp = wk[(WK_POW + 3 * (NPOW - 1) + 2) * NL];                                          // rho^(2P)
+                    t[u].X = 0.0; t[u].Y = 0.0; t[u].Z = 0.0; t[u].W = 0.0;
                 }
-                double X = 0.0, Y = 0.0, Z = 0.0, W = 0.0;
                 const double2* A = recA + 2 * rec_off;
                 const double* K = recK + rec_off;
                 double2 a01 = A[0], a23 = A[1];
@@ -761,25 +793,34 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                 // one loop over the columns; the roles of the two sequences are swapped after every column.  The seeds of the next
                 // column are fetched before the current one is walked.
                 int len = my[3];
-                const double dc = ub + ub, dg = r2 + r2;
-                double cQ, cc1, cg, cS5, cS6;   // set-up of the column about to be walked
                 {
                     const double4 sd = *reinterpret_cast<const double4*>(colseed + 4 * my[2]);
-                    cQ = pa * sd.x; cc1 = sd.w * ub; cg = sd.w * r2; cS5 = cQ * sd.y; cS6 = cQ * sd.z;
+#pragma unroll
+                    for (int u = 0; u < TT; ++u) {
+                        t[u].cQ = t[u].pa * sd.x; t[u].cc1 = sd.w * t[u].ub; t[u].cg = sd.w * t[u].r2;
+                        t[u].cS5 = t[u].cQ * sd.y; t[u].cS6 = t[u].cQ * sd.z;
+                    }
                 }
                 for (int k = 0; k < ncol; ++k) {
                     const int len_n = my[5 + 2 * k];   // the schedule rows end with a null column (all-zero seeds)
                     const double4 sd_n = *reinterpret_cast<const double4*>(colseed + 4 * my[4 + 2 * k]);
-                    tx_column(A, K, a01, a23, kk, len, cQ, cc1, cg, cS5, cS6, dc, dg, zar, zai, X, Y, Z, W);
-                    const double nr = fma(zar, qr, -(zai * qi));
-                    const double ni = fma(zar, qi, zai * qr), np = pa * qp;
-                    zar = zbr; zai = zbi; pa = pb;
-                    zbr = nr; zbi = ni; pb = np;
-                    cQ = pa * sd_n.x; cc1 = sd_n.w * ub; cg = sd_n.w * r2; cS5 = cQ * sd_n.y; cS6 = cQ * sd_n.z;
+                    tx_column(A, K, a01, a23, kk, len, t);
+#pragma unroll
+                    for (int u = 0; u < TT; ++u) {
+                        const double nr = fma(t[u].zar, t[u].qr, -(t[u].zai * t[u].qi));
+                        const double ni = fma(t[u].zar, t[u].qi, t[u].zai * t[u].qr), np = t[u].pa * t[u].qp;
+                        t[u].zar = t[u].zbr; t[u].zai = t[u].zbi; t[u].pa = t[u].pb;
+                        t[u].zbr = nr; t[u].zbi = ni; t[u].pb = np;
+                        t[u].cQ = t[u].pa * sd_n.x; t[u].cc1 = sd_n.w * t[u].ub; t[u].cg = sd_n.w * t[u].r2;
+                        t[u].cS5 = t[u].cQ * sd_n.y; t[u].cS6 = t[u].cQ * sd_n.z;
+                    }
                     len = len_n;
                 }
-                double* pt = sm.part + ((par * P + pos) * 4) * NL + lane;
-                pt[0] = X; pt[NL] = Y; pt[2 * NL] = Z; pt[3 * NL] = W;
+#pragma unroll
+                for (int u = 0; u < TT; ++u) {
+                    double* pt = sm.part + ((par * P + pos) * 4) * NL + u * 32 + lane;
+                    pt[0] = t[u].X; pt[NL] = t[u].Y; pt[2 * NL] = t[u].Z; pt[3 * NL] = t[u].W;
+                }
                 nb_arrive(1 + c * BAR_PER_CTX + 3 + par, NT_RW);   // DONE[par]: the partial sums of this position are in shared memory
                 TX_TRACE(TR_WALK_END, c, st);
             }
@@ -788,12 +829,21 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
     }
 
     // =================================================================================================== HELPER
-    const int c = (w - P) / 3, j = (w - P) % 3;   // set context, helper index: owns state components j (position) and j + 3 (velocity)
+    // set context; helper role j: owns state components j (position) and j + 3 (velocity); TT = 2: half of the set this warp serves
+    const int c = (w - P) / HW, j = ((w - P) % HW) % 3, half = ((w - P) % HW) / 3;
+    const int tl = half * 32 + lane;   // trajectory of this thread inside the set
     const TxSm sm = tx_views(smem, L, c, N);
     const int BAR_HB = 1 + c * BAR_PER_CTX, BAR_DONE = BAR_HB + 3;
     const DevGrav& gv = S.grav;
     const bool has_extra = S.n_bodies > 0 || S.has_srp || S.has_drag || S.n_xgrav > 0;
-    const bool lead = (j == 0);   // helper 0 also runs the DCM, the stage prologues, the controller and the set queue of its context
+    const bool lead = (j == 0);   // helper 0 also runs the DCM, the controller (of its half of the set) and, half 0, the set queue
+    const bool lead0 = lead && half == 0;
+    // every trajectory of the set is done (read between the helpers' barriers that follow the votes of the leads)
+    auto set_done = [&]() {
+        bool d = s_done_half[c][0] != 0;
+        if (TT == 2) d = d && s_done_half[c][TT - 1] != 0;
+        return d;
+    };
     const double* ta = S.tb.a;    // a_{q,m} (stage q >= 1, m < q) = ta[(q - 1) * NYXB_MAX_STAGES + m]
 
     // The two sets of a CTA must not reach the serial stretch between two attempts (error norm, controller, commit, first
@@ -802,13 +852,13 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
     // every such stretch).  Context 1 therefore starts when context 0 is half-way through its first attempt.
     bool kick_pending = (NCTX > 1 && c == 0);
     if (NCTX > 1 && c == 1) {
-        if (lead && lane == 0) tx_mbar_wait(&kick_bar, 0);
-        nb_sync(BAR_HB, 96);
+        if (lead0 && lane == 0) tx_mbar_wait(&kick_bar, 0);
+        nb_sync(BAR_HB, NT_HB);
     }
 
     for (;;) {
         // ---------------------------------------------------------------- acquire a set: a fresh one, else a parked one
-        if (lead && lane == 0) {
+        if (lead0 && lane == 0) {
             int set = -1, fresh = 0;
             if (atomicAdd(q.ctl + TXQ_FRESH, 0) < q.n_sets) {
                 const int f = atomicAdd(q.ctl + TXQ_FRESH, 1);
@@ -829,83 +879,83 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
             s_set[c] = set; s_fresh[c] = fresh;
             s_exit[c] = set < 0;   // nothing fresh, nothing parked: every unfinished set is in progress in another context
         }
-        nb_sync(BAR_HB, 96);
-        if (s_exit[c] && kick_pending && lead && lane == 0) tx_mbar_arrive(&kick_bar);
+        nb_sync(BAR_HB, NT_HB);
+        if (s_exit[c] && kick_pending && lead0 && lane == 0) tx_mbar_arrive(&kick_bar);
         if (s_exit[c]) {
             tx_mbar_arrive(&ready_bar[c][0]);   // releases the walkers (they expect stage 0), which read s_exit and drop this context
             return;
         }
         const int set = s_set[c];
         const int round = s_fresh[c] ? 0 : 1;   // 0: initial state from the inputs; otherwise from the parking area
-        const size_t traj_raw = (size_t)set * NL + lane;
+        const size_t traj_raw = (size_t)set * NL + tl;
         const bool valid = traj_raw < n;
         const size_t tr = valid ? traj_raw : (size_t)set * NL;   // an absent lane shadows the set's first trajectory, never committed
 
         // ---------------------------------------------------------------- load the set
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int cc = j + 3 * half;
+        for (int hh = 0; hh < 2; ++hh) {
+            const int cc = j + 3 * hh;
             const double yc = (round == 0) ? state[(size_t)cc * n + tr] : __ldcg(out_state + (size_t)cc * n + tr);
-            sm.ycur[cc * NL + lane] = yc;
+            sm.ycur[cc * NL + tl] = yc;
             if (round == 0 && valid && sink.cap > 0) sink.state[((size_t)cc * sink.cap) * n + tr] = yc;
         }
         if (lead) {
-            tx_load_ctl(S, sink, q, sm, lane, n, tr, valid, round, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch);
-            tx_pick_step(sm, lane, end_epoch);
-            const bool done = sm.i32[TXW_FLAGS * NL + lane] & F_DONE;
+            tx_load_ctl(S, sink, q, sm, tl, n, tr, valid, round, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch);
+            tx_pick_step(sm, tl, end_epoch);
+            const bool done = sm.i32[TXW_FLAGS * NL + tl] & F_DONE;
             const bool all = __all_sync(FULL, done);
-            if (lane == 0) { s_all_done[c] = all; s_slice_end[c] = 0; }
-            if (gv.rot.kind != 0) tx_rot_store(sm.rot, lane, tx_rot_base(gv.rot, sm.i64[TXI_EPOCH * NL + lane]));
+            if (lane == 0) { s_done_half[c][half] = all; if (half == 0) s_slice_end[c] = 0; }
+            if (gv.rot.kind != 0) tx_rot_store(sm.rot, tl, tx_rot_base(gv.rot, sm.i64[TXI_EPOCH * NL + tl]));
         }
-        nb_sync(BAR_HB, 96);
+        nb_sync(BAR_HB, NT_HB);
 
         // ---------------------------------------------------------------- step attempts of this slice
-        for (int it = 0; !s_all_done[c]; ++it) {
+        for (int it = 0; !set_done(); ++it) {
             TX_TRACE(TR_TOP, c, 0);
-            const double h = sm.f64[TXF_H * NL + lane];
-            const long long epoch = sm.i64[TXI_EPOCH * NL + lane];
-            const double r_own = sm.ycur[j * NL + lane], v_own = sm.ycur[(3 + j) * NL + lane];
+            const double h = sm.f64[TXF_H * NL + tl];
+            const long long epoch = sm.i64[TXI_EPOCH * NL + tl];
+            const double r_own = sm.ycur[j * NL + tl], v_own = sm.ycur[(3 + j) * NL + tl];
             // orientation angles at the step epoch (the lead evaluates every DCM of the attempt).  They are NOT evaluated here, on the
             // serial path between two attempts: helper 1 evaluates them for the epoch this attempt leads to while the walkers are
             // busy, and commits them to sm.rot when the controller accepts the step (a rejected step keeps its epoch).
             TxRotBase rb_;
             rb_.sa = 0.0; rb_.ca = 1.0; rb_.sd = 1.0; rb_.cd = 0.0; rb_.sw = 0.0; rb_.cw = 1.0;
             TxRotBase rb_next = rb_;
-            const bool fixed = sm.i32[TXW_FLAGS * NL + lane] & F_FIXED;
+            const bool fixed = sm.i32[TXW_FLAGS * NL + tl] & F_FIXED;
             // candidate state and error estimate (instance.rs:402-414), accumulated stage by stage in the reference's order
             double nx_r = r_own, nx_v = v_own, er_r = 0.0, er_v = 0.0;
             int rc_acc = 0;
             double Rn[9];
             // ---- prime the pipeline: stage 0 (the state itself) and stage 1 (needs only V_0 = v): instance.rs:369-394
-            sm.kst[(0 * 6 + j) * NL + lane] = v_own;                 // k_0[j] = V_0
-            sm.ysp[(0 * 3 + j) * NL + lane] = r_own;                 // P_0
+            sm.kst[(0 * 6 + j) * NL + tl] = v_own;                 // k_0[j] = V_0
+            sm.ysp[(0 * 3 + j) * NL + tl] = r_own;                 // P_0
             const long long off1 = (stages > 1) ? dur_from_seconds(S.tb.c[0] * h) : 0;
-            if (stages > 1) sm.ysp[(1 * 3 + j) * NL + lane] = fma(h, ta[0] * v_own, r_own);   // P_1 = r + h a_10 V_0
-            nb_sync(BAR_HB, 96);
+            if (stages > 1) sm.ysp[(1 * 3 + j) * NL + tl] = fma(h, ta[0] * v_own, r_own);   // P_1 = r + h a_10 V_0
+            nb_sync(BAR_HB, NT_HB);
             if (lead) {
                 if (gv.rot.kind != 0) {
-                    rb_.sa = sm.rot[lane]; rb_.ca = sm.rot[NL + lane]; rb_.sd = sm.rot[2 * NL + lane]; rb_.cd = sm.rot[3 * NL + lane];
-                    rb_.sw = sm.rot[4 * NL + lane]; rb_.cw = sm.rot[5 * NL + lane];
+                    rb_.sa = sm.rot[lane]; rb_.ca = sm.rot[NL + tl]; rb_.sd = sm.rot[2 * NL + tl]; rb_.cd = sm.rot[3 * NL + tl];
+                    rb_.sw = sm.rot[4 * NL + tl]; rb_.cw = sm.rot[5 * NL + tl];
                 }
                 tx_dcm(gv.rot, rb_, 0, Rn);
 #pragma unroll
-                for (int k = 0; k < 9; ++k) sm.rn[k * NL + lane] = Rn[k];
+                for (int k = 0; k < 9; ++k) sm.rn[k * NL + tl] = Rn[k];
                 if (stages > 1) {
                     tx_dcm(gv.rot, rb_, off1, Rn);
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) sm.rn[(9 + k) * NL + lane] = Rn[k];
+                    for (int k = 0; k < 9; ++k) sm.rn[(9 + k) * NL + tl] = Rn[k];
                 }
             }
-            nb_sync(BAR_HB, 96);
-            tx_prologue<P>(S, sm, lane, 0, j, sm.ysp, epoch);
+            nb_sync(BAR_HB, NT_HB);
+            tx_prologue<P>(S, sm, tl, 0, j, sm.ysp, epoch);
             tx_mbar_arrive(&ready_bar[c][0]);
             TX_TRACE(TR_READY, c, 0);
             if (stages > 1) {
-                tx_prologue<P>(S, sm, lane, 1, j, sm.ysp + 3 * NL, epoch + off1);
+                tx_prologue<P>(S, sm, tl, 1, j, sm.ysp + 3 * NL, epoch + off1);
                 tx_mbar_arrive(&ready_bar[c][1]);
                 TX_TRACE(TR_READY, c, 1);
             }
-            nb_sync(BAR_HB, 96);   // the lead overwrites rn[0] (DCM of stage 2) in the first slack below: every helper has read it by now
+            nb_sync(BAR_HB, NT_HB);   // the lead overwrites rn[0] (DCM of stage 2) in the first slack below: every helper has read it by now
             // ---- derive(): the stages of one attempt for the 32 trajectories (instance.rs:358-493), one walk ahead of the walkers
             for (int i = 0; i < stages; ++i) {
                 const int par = i & 1;
@@ -913,15 +963,15 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                 double preV = 0.0, preP = 0.0;
                 long long off2 = 0;
                 {
-                    const double vi = sm.kst[(i * 6 + j) * NL + lane];   // V_i
+                    const double vi = sm.kst[(i * 6 + j) * NL + tl];   // V_i
                     if (!fixed) er_r = fma(h * S.tb.e[i], vi, er_r);
                     nx_r = fma(h * S.tb.b[i], vi, nx_r);
                 }
                 if (j == 1 && i == 0 && gv.rot.kind != 0)
-                    rb_next = tx_rot_base(gv.rot, epoch + (fixed ? sm.i64[TXI_STEP * NL + lane] : dur_from_seconds(h)));
+                    rb_next = tx_rot_base(gv.rot, epoch + (fixed ? sm.i64[TXI_STEP * NL + tl] : dur_from_seconds(h)));
                 if (i + 1 < stages) {   // V_{i+1} = v + h sum_{l<=i} a_{i+1,l} A_l: all terms but the last
                     const double* arow = ta + i * NYXB_MAX_STAGES;
-                    const double* kc = sm.kst + (3 + j) * NL + lane;
+                    const double* kc = sm.kst + (3 + j) * NL + tl;
                     double w0 = 0.0, w1 = 0.0;
                     int l = 0;
                     for (; l + 1 < i; l += 2) { w0 = fma(arow[l], kc[l * 6 * NL], w0); w1 = fma(arow[l + 1], kc[(l + 1) * 6 * NL], w1); }
@@ -930,7 +980,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                 }
                 if (i + 2 < stages) {   // P_{i+2} = r + h sum_{m<=i+1} a_{i+2,m} V_m: all terms but the last (V_i is known)
                     const double* arow = ta + (i + 1) * NYXB_MAX_STAGES;
-                    const double* kc = sm.kst + j * NL + lane;
+                    const double* kc = sm.kst + j * NL + tl;
                     double w0 = 0.0, w1 = 0.0;
                     int m = 0;
                     for (; m + 1 <= i; m += 2) { w0 = fma(arow[m], kc[m * 6 * NL], w0); w1 = fma(arow[m + 1], kc[(m + 1) * 6 * NL], w1); }
@@ -941,12 +991,12 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                     if (lead) {   // DCM of stage i+2 (its parity buffer was last read in the prologue of stage i, two barriers ago)
                         tx_dcm(gv.rot, rb_, off2, Rn);
 #pragma unroll
-                        for (int k = 0; k < 9; ++k) sm.rn[(par * 9 + k) * NL + lane] = Rn[k];
+                        for (int k = 0; k < 9; ++k) sm.rn[(par * 9 + k) * NL + tl] = Rn[k];
                     }
                 }
                 TX_TRACE(TR_DCM_DONE, c, i);
                 if (kick_pending && i == stages / 2) {
-                    if (lead && lane == 0) tx_mbar_arrive(&kick_bar);
+                    if (lead0 && lane == 0) tx_mbar_arrive(&kick_bar);
                     kick_pending = false;
                 }
                 TX_TRACE(TR_DONE_WAIT, c, i);
@@ -959,14 +1009,14 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                     double ax[4] = {0.0, 0.0, 0.0, 0.0}, ay[4] = {0.0, 0.0, 0.0, 0.0}, az[4] = {0.0, 0.0, 0.0, 0.0}, aw4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
                     for (int p = 0; p < P; ++p) {
-                        const double* pt = sm.part + ((par * P + p) * 4) * NL + lane;
+                        const double* pt = sm.part + ((par * P + p) * 4) * NL + tl;
                         ax[p & 3] += pt[0]; ay[p & 3] += pt[NL]; az[p & 3] += pt[2 * NL]; aw4[p & 3] += pt[3 * NL];
                     }
                     X = (ax[0] + ax[1]) + (ax[2] + ax[3]); Y = (ay[0] + ay[1]) + (ay[2] + ay[3]);
                     Z = (az[0] + az[1]) + (az[2] + az[3]); Wt = (aw4[0] + aw4[1]) + (aw4[2] + aw4[3]);
                 }
                 TX_TRACE(TR_REDUCED, c, i);
-                const double* as = sm.as + par * AS_COUNT * NL + lane;
+                const double* as = sm.as + par * AS_COUNT * NL + tl;
                 const double K0 = as[AS_K0 * NL], K1 = as[AS_K1 * NL];
                 const double aw = -K0 * Wt;
                 const double ab0 = fma(aw, as[AS_S * NL], K1 * X), ab1 = fma(aw, as[AS_T * NL], K1 * Y), ab2 = fma(aw, as[AS_U * NL], K1 * Z);
@@ -977,55 +1027,55 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                     const double hz = (i > 0) ? h * 0.0 : 0.0;
                     yy[0] = as[AS_P0 * NL]; yy[1] = as[AS_P1 * NL]; yy[2] = as[AS_P2 * NL];
 #pragma unroll
-                    for (int e = 0; e < 3; ++e) yy[3 + e] = sm.kst[(i * 6 + e) * NL + lane];   // V_i
-                    yy[6] = sm.f64[TXF_CR * NL + lane] + hz; yy[7] = sm.f64[TXF_CD * NL + lane] + hz; yy[8] = sm.f64[TXF_PM * NL + lane] + hz;
+                    for (int e = 0; e < 3; ++e) yy[3 + e] = sm.kst[(i * 6 + e) * NL + tl];   // V_i
+                    yy[6] = sm.f64[TXF_CR * NL + tl] + hz; yy[7] = sm.f64[TXF_CD * NL + tl] + hz; yy[8] = sm.f64[TXF_PM * NL + tl] + hz;
                     const long long offi = (i > 0) ? dur_from_seconds(S.tb.c[i - 1] * h) : 0;
-                    const int rcx = tx_extra(S, sm.f64[TXF_DRY * NL + lane], sm.f64[TXF_EXTRA * NL + lane], sm.f64[TXF_SRPA * NL + lane],
-                                             sm.f64[TXF_DRAGA * NL + lane], epoch + offi, yy, aa);
+                    const int rcx = tx_extra(S, sm.f64[TXF_DRY * NL + tl], sm.f64[TXF_EXTRA * NL + tl], sm.f64[TXF_SRPA * NL + tl],
+                                             sm.f64[TXF_DRAGA * NL + tl], epoch + offi, yy, aa);
                     acc += (j == 0) ? aa[0] : (j == 1 ? aa[1] : aa[2]);
                     if (rcx && !rc_acc) rc_acc = rcx | ((i + 1) << 8);
                 }
-                sm.kst[(i * 6 + 3 + j) * NL + lane] = acc;     // k_i[3+j] = A_i
+                sm.kst[(i * 6 + 3 + j) * NL + tl] = acc;     // k_i[3+j] = A_i
                 if (!fixed) er_v = fma(h * S.tb.e[i], acc, er_v);
                 nx_v = fma(h * S.tb.b[i], acc, nx_v);
                 if (i + 1 < stages) {
                     const double vn = fma(h, fma(ta[i * NYXB_MAX_STAGES + i], acc, preV), v_own);   // V_{i+1}
-                    sm.kst[((i + 1) * 6 + j) * NL + lane] = vn;                                    // k_{i+1}[j]
+                    sm.kst[((i + 1) * 6 + j) * NL + tl] = vn;                                    // k_{i+1}[j]
                     if (i + 2 < stages)
-                        sm.ysp[(par * 3 + j) * NL + lane] = fma(h, fma(ta[(i + 1) * NYXB_MAX_STAGES + i + 1], vn, preP), r_own);   // P_{i+2}
+                        sm.ysp[(par * 3 + j) * NL + tl] = fma(h, fma(ta[(i + 1) * NYXB_MAX_STAGES + i + 1], vn, preP), r_own);   // P_{i+2}
                     TX_TRACE(TR_ACC_DONE, c, i);
-                    nb_sync(BAR_HB, 96);   // V_{i+1} and the position components of stage i+2 of all three helpers are in shared memory
+                    nb_sync(BAR_HB, NT_HB);   // V_{i+1} and the position components of stage i+2 of all three helpers are in shared memory
                     TX_TRACE(TR_HB_PASSED, c, i);
                     if (i + 2 < stages) {
-                        tx_prologue<P>(S, sm, lane, par, j, sm.ysp + par * 3 * NL, epoch + off2);
+                        tx_prologue<P>(S, sm, tl, par, j, sm.ysp + par * 3 * NL, epoch + off2);
                         tx_mbar_arrive(&ready_bar[c][par]);   // walker inputs of stage i+2 are published
                         TX_TRACE(TR_READY, c, i + 2);
                     }
                 }
             }
             TX_TRACE(TR_STAGES_END, c, 0);
-            sm.nxt[j * NL + lane] = nx_r; sm.nxt[(3 + j) * NL + lane] = nx_v;
-            sm.er[j * NL + lane] = er_r; sm.er[(3 + j) * NL + lane] = er_v;
-            if (lead) sm.i32[TXW_RCST * NL + lane] = rc_acc;
-            nb_sync(BAR_HB, 96);
+            sm.nxt[j * NL + tl] = nx_r; sm.nxt[(3 + j) * NL + tl] = nx_v;
+            sm.er[j * NL + tl] = er_r; sm.er[(3 + j) * NL + tl] = er_v;
+            if (lead) sm.i32[TXW_RCST * NL + tl] = rc_acc;
+            nb_sync(BAR_HB, NT_HB);
             if (lead) {
-                tx_controller(S, sink, sm, lane, n, tr, stages);
+                tx_controller(S, sink, sm, tl, n, tr, stages);
                 const bool slice_end = q.slice > 0 && it + 1 >= q.slice;
-                if (!slice_end) tx_pick_step(sm, lane, end_epoch);
-                const bool done = sm.i32[TXW_FLAGS * NL + lane] & F_DONE;
+                if (!slice_end) tx_pick_step(sm, tl, end_epoch);
+                const bool done = sm.i32[TXW_FLAGS * NL + tl] & F_DONE;
                 const bool all = __all_sync(FULL, done);
-                if (lane == 0) { s_all_done[c] = all; s_slice_end[c] = slice_end; }
+                if (lane == 0) { s_done_half[c][half] = all; if (half == 0) s_slice_end[c] = slice_end; }
             }
-            nb_sync(BAR_HB, 96);
+            nb_sync(BAR_HB, NT_HB);
             TX_TRACE(TR_CTRL_END, c, 0);
-            if (sm.i32[TXW_ACC * NL + lane]) {
-                if (j == 1 && gv.rot.kind != 0) tx_rot_store(sm.rot, lane, rb_next);   // read by the lead after the next HB barrier
-                const long long ns = sm.i64[TXI_NSTEPS * NL + lane];
+            if (sm.i32[TXW_ACC * NL + tl]) {
+                if (j == 1 && gv.rot.kind != 0) tx_rot_store(sm.rot, tl, rb_next);   // read by the lead after the next HB barrier
+                const long long ns = sm.i64[TXI_NSTEPS * NL + tl];
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int cc = j + 3 * half;
-                    const double nx = sm.nxt[cc * NL + lane];
-                    sm.ycur[cc * NL + lane] = nx;
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int cc = j + 3 * hh;
+                    const double nx = sm.nxt[cc * NL + tl];
+                    sm.ycur[cc * NL + tl] = nx;
                     // the channel send of instance.rs:186-193 / 255-259: lanes are consecutive trajectories, one 256-byte store per warp
                     if (valid && ns < sink.cap) sink.state[((size_t)cc * sink.cap + (size_t)ns) * n + tr] = nx;
                 }
@@ -1034,18 +1084,18 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
         }
 
         if (kick_pending) {
-            if (lead && lane == 0) tx_mbar_arrive(&kick_bar);
+            if (lead0 && lane == 0) tx_mbar_arrive(&kick_bar);
             kick_pending = false;
         }
         // ---------------------------------------------------------------- park the set (== final outputs when it is done)
         if (valid) {
-            out_state[(size_t)j * n + tr] = sm.ycur[j * NL + lane];
-            out_state[(size_t)(j + 3) * n + tr] = sm.ycur[(j + 3) * NL + lane];
+            out_state[(size_t)j * n + tr] = sm.ycur[j * NL + tl];
+            out_state[(size_t)(j + 3) * n + tr] = sm.ycur[(j + 3) * NL + tl];
         }
-        if (lead) tx_park_ctl(sink, q, sm, lane, n, tr, step_io, out_state, out_epoch, out_status);
+        if (lead) tx_park_ctl(sink, q, sm, tl, n, tr, step_io, out_state, out_epoch, out_status);
         __threadfence();
-        nb_sync(BAR_HB, 96);
-        if (lead && lane == 0 && !s_all_done[c]) {   // park: the set becomes resumable by any context
+        nb_sync(BAR_HB, NT_HB);
+        if (lead0 && lane == 0 && !set_done()) {   // park: the set becomes resumable by any context
             while (atomicCAS(q.ctl + TXQ_LOCK, 0, 1) != 0) __nanosleep(64);
             __threadfence();
             volatile int* vc = q.ctl;
@@ -1055,7 +1105,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
             __threadfence();
             atomicExch(q.ctl + TXQ_LOCK, 0);
         }
-        nb_sync(BAR_HB, 96);   // s_* of this context are rewritten by its lead lane only after this barrier
+        nb_sync(BAR_HB, NT_HB);   // s_* of this context are rewritten by its lead lane only after this barrier
     }
 }
 
@@ -1067,7 +1117,7 @@ cudaError_t tx_launch_p(const DevSetup* S, const DevTx* Tx, const DevTxQueue* q,
                         unsigned off_seed, unsigned off_sched, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(nyxb_k_tx<P, NCTX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    nyxb_k_tx<P, NCTX><<<grid, (P + 3 * NCTX) * 32, smem, stream>>>(*S, *Tx, *q, n, state, consts, epoch0, end_epoch, step_io, out_state,
+    nyxb_k_tx<P, NCTX><<<grid, (P + HW * NCTX) * 32, smem, stream>>>(*S, *Tx, *q, n, state, consts, epoch0, end_epoch, step_io, out_state,
                                                                   out_epoch, out_status, *sink, blob_bytes, off_recK, off_seed, off_sched);
     return cudaGetLastError();
 }
@@ -1088,6 +1138,7 @@ TxBlob tx_blob(int N, int P, int n_rec, int kmax) {
 // ------------------------------------------------------------------------------------------------
 // host: zigzag column -> position schedule and record table
 // ------------------------------------------------------------------------------------------------
+#if NYXB_TX_TT == 1
 void nyxb_tx_build_host(int N, int M, const double* c_nm, const double* s_nm, int P, TxHost& out) {
     const double sqrt2 = std::sqrt(2.0);
     auto C = [&](int n, int m) { return (n <= N && m <= M && m <= n) ? c_nm[(size_t)n * (N + 1) + m] : 0.0; };
@@ -1170,10 +1221,12 @@ void nyxb_tx_build_host(int N, int M, const double* c_nm, const double* s_nm, in
     }
 }
 
+#endif   // NYXB_TX_TT == 1 (host-only table builder)
+
 // set contexts per CTA: two sets in flight while both fit beside the table (P = 8: degrees up to ~40), one otherwise
 static int tx_contexts(const DevSetup* S, const DevTx* Tx, size_t* smem_bytes) {
     const TxBlob b = tx_blob(S->grav.N, Tx->P, Tx->n_rec, Tx->kmax);
-    for (int nctx = (Tx->P <= 10 ? 2 : 1); nctx >= 1; --nctx) {
+    for (int nctx = (TT == 1 && Tx->P <= 10 ? 2 : 1); nctx >= 1; --nctx) {
         const size_t smem = tx_layout(b.bytes, Tx->P, S->grav.N, nctx).total;
         if (smem <= 227 * 1024) { if (smem_bytes) *smem_bytes = smem; return nctx; }
     }
@@ -1181,13 +1234,20 @@ static int tx_contexts(const DevSetup* S, const DevTx* Tx, size_t* smem_bytes) {
 }
 
 // set contexts one SM holds for this setup (one persistent CTA per SM; 0: the tables do not fit) and its dynamic shared memory
-extern "C" int nyxb_tx_occupancy(const DevSetup* S, const DevTx* Tx, size_t* smem_bytes) {
-    if (Tx->P != 8 && Tx->P != 10 && Tx->P != 16) return 0;
+#if NYXB_TX_TT == 1
+#define NYXB_TX_OCCUPANCY nyxb_tx_occupancy
+#define NYXB_TX_LAUNCH nyxb_launch_tx
+#else   // sets of 64 trajectories (8 walker positions only)
+#define NYXB_TX_OCCUPANCY nyxb_tx2_occupancy
+#define NYXB_TX_LAUNCH nyxb_launch_tx2
+#endif
+extern "C" int NYXB_TX_OCCUPANCY(const DevSetup* S, const DevTx* Tx, size_t* smem_bytes) {
+    if (TT == 1 ? (Tx->P != 8 && Tx->P != 10 && Tx->P != 16) : Tx->P != 8) return 0;
     return tx_contexts(S, Tx, smem_bytes);
 }
 
 // `grid` CTAs, each with nyxb_tx_occupancy() set contexts
-extern "C" cudaError_t nyxb_launch_tx(const DevSetup* S, const DevTx* Tx, const DevTxQueue* q, size_t n, const double* state,
+extern "C" cudaError_t NYXB_TX_LAUNCH(const DevSetup* S, const DevTx* Tx, const DevTxQueue* q, size_t n, const double* state,
                                       const double* consts, const long long* epoch0, long long end_epoch, long long* step_io,
                                       double* out_state, long long* out_epoch, int* out_status, const DevSink* sink,
                                       int grid, cudaStream_t stream) {
@@ -1197,13 +1257,18 @@ extern "C" cudaError_t nyxb_launch_tx(const DevSetup* S, const DevTx* Tx, const 
     const int nctx = tx_contexts(S, Tx, &smem);
     if (nctx < 1 || grid < 1) return cudaErrorInvalidConfiguration;
 #define NYXB_TX_GO(PP, CC) tx_launch_p<PP, CC>(S, Tx, q, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch, out_status, sink, grid, smem, b.bytes, b.off_recK, b.off_seed, b.off_sched, stream)
+#if NYXB_TX_TT == 1
     if (Tx->P == 8) return nctx == 2 ? NYXB_TX_GO(8, 2) : NYXB_TX_GO(8, 1);
     if (Tx->P == 10) return nctx == 2 ? NYXB_TX_GO(10, 2) : NYXB_TX_GO(10, 1);
     if (Tx->P == 16) return NYXB_TX_GO(16, 1);
+#else
+    if (Tx->P == 8) return NYXB_TX_GO(8, 1);
+#endif
     return cudaErrorInvalidValue;
 #undef NYXB_TX_GO
 }
 
+#if NYXB_TX_TT == 1
 // host-side view of the blob (nyxb_api.cu uploads it as one allocation; the kernel copies it with one TMA bulk copy)
 size_t nyxb_tx_pack_blob(const TxHost* h, int N, unsigned char* dst) {
     const TxBlob b = tx_blob(N, h->P, h->n_rec, h->kmax);
@@ -1216,3 +1281,4 @@ size_t nyxb_tx_pack_blob(const TxHost* h, int N, unsigned char* dst) {
     }
     return b.bytes;
 }
+#endif   // NYXB_TX_TT == 1

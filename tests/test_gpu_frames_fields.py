@@ -95,7 +95,7 @@ def test_integration_frame_translations_match_the_oracle(oracle, mode, kernel):
     else:
         assert dr < 1e-6 and dv < 1e-9, (dr, dv)
     # results are Moon-relative (|r| ~ 1 900 km), the recording is in the integration frame (|r| ~ 4e5 km)
-    assert np.linalg.norm(out[:3], axis=0).max() < 3000.0 and np.linalg.norm(t_st[:3, 0, :], axis=0).min() > 3e5
+    assert np.linalg.norm(out[:3], axis=0).max() < 1.0e4 and np.linalg.norm(t_st[:3, 0, :], axis=0).min() > 3e5
     # an epoch outside the ephemeris is a per-trajectory almanac error, not an abort
     ep_bad = ep.copy(); ep_bad[2] = -400 * DAY
     s_bad = eng.propagate_batch(st_m, cs, ep_bad, end)[3]
