@@ -55,7 +55,6 @@ def parse_args():
     p.add_argument("--kernel", default="auto", choices=["auto", "thread", "coop", "transposed"],
                    help="kernel family (nyxb_engine_set_kernel); auto = the library's own dispatch")
     p.add_argument("--tx-positions", type=int, default=0, help="transposed kernel: walker warps per set (0 = library default)")
-    p.add_argument("--tx-set", type=int, default=0, choices=[0, 32, 64], help="transposed kernel: trajectories per set (0 = library default)")
     p.add_argument("--tx-slice", type=int, default=0, help="transposed kernel: step attempts per time slice (0 = library default)")
     p.add_argument("--cpu-sample", type=int, default=0,
                    help="trajectories in the bounded CPU-baseline sample (0: 32 per host core, ~10 s of CPU work)")
@@ -476,8 +475,6 @@ def main():
         eng.set_tx_tuning(args.tx_slice, 0)
     if args.tx_positions:
         eng.set_tx_positions(args.tx_positions)
-    if args.tx_set:
-        eng.set_tx_set_length(args.tx_set)
     end = int(args.span_days * DAY)
 
     # pinned host inputs of this rank's shard (e2e leg) and HBM-resident copies (value leg)

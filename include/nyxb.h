@@ -507,8 +507,7 @@ int32_t nyxb_engine_last_kernel(const nyxb_engine* eng);                   /* fa
 /* TRANSPOSED kernel: step attempts per time slice (default 64) and an upper bound on the persistent CTAs (0 = SMs x occupancy).
  * Sets are only parked when there are more sets than CTAs. */
 int32_t nyxb_engine_set_tx_tuning(nyxb_engine* eng, int32_t slice_attempts, int32_t max_ctas);
-int32_t nyxb_engine_set_tx_positions(nyxb_engine* eng, int32_t positions);
-int32_t nyxb_engine_set_tx_set_length(nyxb_engine* eng, int32_t trajectories);   /* trajectories per set: 32, or 64 (8 positions only; falls back to 32 when one such set does not fit) */   /* walker warps per set: 0 = by degree, 8, 10, 16 */
+int32_t nyxb_engine_set_tx_positions(nyxb_engine* eng, int32_t positions);   /* walker warps per set: 0 = by degree, 8, 10, 16 */
 int32_t nyxb_engine_set_lanes(nyxb_engine* eng, int32_t lanes_per_trajectory); /* 0 = auto */
 int32_t nyxb_engine_get_lanes(const nyxb_engine* eng);
 int64_t nyxb_engine_launch_count(const nyxb_engine* eng); /* kernels launched so far */

@@ -320,8 +320,6 @@ def _declare(lib):
     lib.nyxb_engine_set_kernel.argtypes = [vp, C.c_int32]
     lib.nyxb_engine_last_kernel.restype = C.c_int32
     lib.nyxb_engine_last_kernel.argtypes = [vp]
-    lib.nyxb_engine_set_tx_set_length.restype = C.c_int32
-    lib.nyxb_engine_set_tx_set_length.argtypes = [vp, C.c_int32]
     lib.nyxb_engine_set_tx_positions.restype = C.c_int32
     lib.nyxb_engine_set_tx_positions.argtypes = [vp, C.c_int32]
     lib.nyxb_engine_set_tx_tuning.restype = C.c_int32
@@ -364,7 +362,6 @@ EXPORTED_SYMBOLS = [
     "nyxb_engine_last_kernel",
     "nyxb_engine_set_tx_tuning",
     "nyxb_engine_set_tx_positions",
-    "nyxb_engine_set_tx_set_length",
     "nyxb_abi_version",
     "nyxb_last_error",
 ]

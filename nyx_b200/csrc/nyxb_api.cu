@@ -78,7 +78,6 @@ struct nyxb_engine {
     std::map<int, DevTx> tx;               // positions -> tables of the transposed kernel
     int tx_slice = 64;                     // step attempts per time slice of the persistent transposed kernel
     int tx_positions = 0;                  // walker warps per set (0: by degree)
-    int tx_set_len = 32;                   // trajectories per set of the transposed kernel: 32 or 64
     int tx_max_ctas = 0;                   // 0: every resident slot (SMs x occupancy); tests shrink it to force time slicing
     size_t txq_bytes = 0;                  // grow-only queue + parking workspace of the transposed kernel
     unsigned char* d_txq = nullptr;
@@ -428,15 +427,11 @@ static int32_t launch_tx(nyxb_engine* e, size_t n, const double* state, const do
     const DevTx* tx = get_tx(e, tx_positions(e));
     if (!tx) { set_err("transposed-kernel table upload failed"); return NYXB_RC_CUDA; }
     size_t smem = 0;
-    // set length: 64 trajectories (a walker lane carries two through every record load) when asked for and the 8-position table
-    // plus one such set fit in shared memory, else 32
-    int set_len = 32;
-    int occ = 0;
-    if (e->tx_set_len == 64 && tx->P == 8) {
-        occ = nyxb_tx2_occupancy(&e->S, tx, &smem);
-        if (occ >= 1) set_len = 64;
-    }
-    if (set_len == 32) occ = nyxb_tx_occupancy(&e->S, tx, &smem);
+    // sets of 32 trajectories.  Sets of 64 (a walker lane carrying two trajectories through every record load: half the shared-
+    // memory wavefronts per FP64 instruction, but only one set context fits a CTA, so nothing covers the serial stretch between two
+    // attempts) were built and measured slower: 1.36e8 against 1.51e8 steps/s on C2 (profiles/r02s_tx_variants.md); not dispatched.
+    const int set_len = 32;
+    const int occ = nyxb_tx_occupancy(&e->S, tx, &smem);
     if (occ < 1) { set_err("transposed kernel: tables do not fit in shared memory"); return NYXB_RC_UNSUPPORTED; }
     if (!e->sms) CUDA_TRY(cudaDeviceGetAttribute(&e->sms, cudaDevAttrMultiProcessorCount, e->device));
     const size_t n_sets = (n + set_len - 1) / set_len;
@@ -475,9 +470,8 @@ static int32_t launch_tx(nyxb_engine* e, size_t n, const double* state, const do
         CUDA_TRY(cudaMemsetAsync(q.trace, 0, trace_bytes, stream));
     }
 #endif
-    cudaError_t err = (set_len == 64 ? nyxb_launch_tx2 : nyxb_launch_tx)(&e->S, tx, &q, n, state, consts, (const long long*)epoch0, end_epoch,
-                                                                        (long long*)step_io, out_state, (long long*)out_epoch, out_status,
-                                                                        &sink, grid, stream);
+    cudaError_t err = nyxb_launch_tx(&e->S, tx, &q, n, state, consts, (const long long*)epoch0, end_epoch, (long long*)step_io, out_state,
+                                     (long long*)out_epoch, out_status, &sink, grid, stream);
     if (err != cudaSuccess) { set_err(std::string("kernel launch: ") + cudaGetErrorString(err)); return NYXB_RC_CUDA; }
 #ifdef NYXB_TX_TRACE
     if (q.trace) {
@@ -650,6 +644,8 @@ extern "C" int32_t nyxb_propagate_batch_event(nyxb_engine* eng, size_t n, const 
         dsink.state = (double*)(eng->d_sink + cap * n * 8);
         dsink.count = (long long*)(eng->d_sink + cap * n * 56);
         eng->rec_n = n; eng->rec_cap = sink->capacity;
+        // slots past count[i] come back as zeros, not as whatever the allocation held (the whole sink is copied to the caller)
+        TRY2(cudaMemsetAsync(eng->d_sink, 0, cap * n * 56, st));
     }
     TRY2(cudaEventRecord(eng->ev0, st));
     rc = launch(eng, n, d_f64, d_f64 + 9 * n, (const int64_t*)d_i64, end_epoch_ns, step_ns ? (int64_t*)(d_i64 + 2 * n) : nullptr,
@@ -1170,11 +1166,6 @@ extern "C" int32_t nyxb_engine_set_tx_tuning(nyxb_engine* eng, int32_t slice_att
     if (!eng || slice_attempts < 1 || max_ctas < 0) { set_err("slice_attempts >= 1, max_ctas >= 0"); return NYXB_RC_BAD_ARG; }
     eng->tx_slice = slice_attempts;
     eng->tx_max_ctas = max_ctas;
-    return NYXB_RC_OK;
-}
-extern "C" int32_t nyxb_engine_set_tx_set_length(nyxb_engine* eng, int32_t trajectories) {
-    if (!eng || (trajectories != 32 && trajectories != 64)) { set_err("set length: 32 or 64 trajectories"); return NYXB_RC_BAD_ARG; }
-    eng->tx_set_len = trajectories;
     return NYXB_RC_OK;
 }
 extern "C" int32_t nyxb_engine_set_tx_positions(nyxb_engine* eng, int32_t positions) {

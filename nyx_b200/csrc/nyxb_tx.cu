@@ -41,9 +41,11 @@
 #endif
 
 namespace {
-// Built twice (Makefile): TT = 1 — a set is 32 trajectories, a walker lane carries one; TT = 2 — a set is 64 trajectories, a walker
-// lane carries trajectories l and l + 32 through the same record loads (half the shared-memory wavefronts and non-FP64 issue slots
-// per FP64 instruction), and every helper role is played by two warps, one per half of the set.
+// TT = 1 (the build): a set is 32 trajectories, a walker lane carries one.  TT = 2 (-DNYXB_TX_TT=2, not built, not dispatched): a set
+// is 64 trajectories, a walker lane carries trajectories l and l + 32 through the same record loads (half the shared-memory
+// wavefronts per FP64 instruction) and every helper role is played by two warps — but then only ONE set context fits a CTA's
+// registers, the serial stretch between two attempts is no longer covered by a second set, and the variant measured 10 % slower
+// (C2, B200: 1.36e8 against 1.51e8 steps/s, profiles/r02s_tx_variants.md).
 constexpr int TT = NYXB_TX_TT;
 constexpr int NL = 32 * TT;    // trajectories per set: stride of every per-trajectory shared-memory array
 constexpr int HW = 3 * TT;     // helper warps per set context
@@ -934,7 +936,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
             nb_sync(BAR_HB, NT_HB);
             if (lead) {
                 if (gv.rot.kind != 0) {
-                    rb_.sa = sm.rot[lane]; rb_.ca = sm.rot[NL + tl]; rb_.sd = sm.rot[2 * NL + tl]; rb_.cd = sm.rot[3 * NL + tl];
+                    rb_.sa = sm.rot[tl]; rb_.ca = sm.rot[NL + tl]; rb_.sd = sm.rot[2 * NL + tl]; rb_.cd = sm.rot[3 * NL + tl];
                     rb_.sw = sm.rot[4 * NL + tl]; rb_.cw = sm.rot[5 * NL + tl];
                 }
                 tx_dcm(gv.rot, rb_, 0, Rn);

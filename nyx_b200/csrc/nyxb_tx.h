@@ -56,13 +56,6 @@ struct DevTxQueue {
 #define NYXB_TX_TRACE_CAP 8192
 enum { TXQ_FRESH = 0, TXQ_LOCK = 1, TXQ_HEAD = 2, TXQ_TAIL = 3 };
 
-// nyxb_tx.cu is built twice: sets of 32 trajectories (nyxb_launch_tx, nyxb_tx_occupancy) and sets of 64 (nyxb_launch_tx2,
-// nyxb_tx2_occupancy: a walker lane carries two trajectories through every record load; 8 positions, one set per CTA)
-extern "C" cudaError_t nyxb_launch_tx2(const DevSetup* S, const DevTx* Tx, const DevTxQueue* q, size_t n, const double* state,
-                                       const double* consts, const long long* epoch0, long long end_epoch, long long* step_io,
-                                       double* out_state, long long* out_epoch, int* out_status, const DevSink* sink,
-                                       int grid, cudaStream_t stream);
-extern "C" int nyxb_tx2_occupancy(const DevSetup* S, const DevTx* Tx, size_t* smem_bytes);
 extern "C" cudaError_t nyxb_launch_tx(const DevSetup* S, const DevTx* Tx, const DevTxQueue* q, size_t n, const double* state,
                                       const double* consts, const long long* epoch0, long long end_epoch, long long* step_io,
                                       double* out_state, long long* out_epoch, int* out_status, const DevSink* sink,

@@ -197,11 +197,6 @@ class Engine:
     def last_kernel(self) -> int:
         return self._lib.nyxb_engine_last_kernel(self._h)
 
-    def set_tx_set_length(self, trajectories: int):
-        """Transposed kernel: trajectories per set, 32 or 64 (64: a walker lane carries two trajectories through every record load)."""
-        if self._lib.nyxb_engine_set_tx_set_length(self._h, trajectories) != 0:
-            raise PropagationError(f"set_tx_set_length({trajectories}): {abi.last_error()}")
-
     def set_tx_positions(self, positions: int):
         """Transposed kernel: walker warps per set of 32 trajectories (0 = chosen by the field's degree)."""
         if self._lib.nyxb_engine_set_tx_positions(self._h, positions) != 0:

@@ -1,0 +1,12 @@
+#!/bin/bash
+# Round 2, GPU call U: failing tests of call S after the fixes, then the clock64 timeline of CTA 0 of the transposed kernel.
+set -u
+cd "${GRAFT_REPO_ROOT:-.}"
+mkdir -p gpurun_out
+T=${TAG:-r02u}
+python -c "import nyx_b200.abi as a; a.load_library()" || { echo "libnyxb.so missing or stale"; exit 9; }
+timeout 900 python -m pytest -q -p no:cacheprovider -m gpu tests/test_gpu_frames_fields.py tests/test_gpu_tx.py tests/test_trajectory.py tests/test_gpu_fullsize.py > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/${T}_pytest.log
+touch nyx_b200/csrc/nyxb_tx.cu nyx_b200/csrc/nyxb_api.cu
+timeout 400 make -C nyx_b200/csrc EXTRA=-DNYXB_TX_TRACE > gpurun_out/${T}_make.log 2>&1; echo "make rc=$?"
+NYXB_TX_TRACE_FILE=gpurun_out/${T}_trace.bin timeout 120 python bench.py --steps 1 --warmup 0 --span-days 0.05 --n-traj 9472 --no-cpu-baseline --no-strict --kernel transposed > gpurun_out/${T}_trace_bench.log 2>&1; echo "trace bench rc=$?"
+python scripts/tx_trace.py gpurun_out/${T}_trace.bin 8 > gpurun_out/${T}_trace.txt 2>&1; tail -60 gpurun_out/${T}_trace.txt

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small launches of every shared-memory-cooperating kernel, meant to run under compute-sanitizer:
 
-    compute-sanitizer --tool racecheck python scripts/sanitize_case.py coop|strict|tx|tx64|od
+    compute-sanitizer --tool racecheck python scripts/sanitize_case.py coop|strict|tx|od
     compute-sanitizer --tool memcheck  python scripts/sanitize_case.py all
 
 Sizes are tiny (the tools slow kernels down ~100x): a few trajectories over a few steps, with rejections and a recording sink."""
@@ -29,14 +29,12 @@ def run(which):
     gd = nb.GravityFieldData.from_fixture("jgm3_70x70", 12, 12, nb.IAU_EARTH_FRAME)
     dyn = nb.SpacecraftDynamics.new(nb.OrbitalDynamics.from_model(nb.GravityField.new(gd)))
     opts = nb.IntegratorOptions(init_step=400 * nb.Unit.Second, tolerance=1e-12)   # the first attempts are rejected
-    if which in ("coop", "tx", "tx64", "thread"):
-        st, cs, ep = ensemble(70 if which != "tx64" else 150)
+    if which in ("coop", "tx", "thread"):
+        st, cs, ep = ensemble(70)
         prop = nb.Propagator.rk89(dyn, opts, mode=nb.MODE_FAST)
         eng = prop.engine(nb.EARTH_J2000, None)
-        eng.set_kernel({"coop": nb.KERNEL_COOP, "tx": nb.KERNEL_TRANSPOSED, "tx64": nb.KERNEL_TRANSPOSED, "thread": nb.KERNEL_THREAD}[which])
-        if which == "tx64":
-            eng.set_tx_set_length(64)   # 3 sets of 64 on one CTA (one set context)
-        if which in ("tx", "tx64"):
+        eng.set_kernel({"coop": nb.KERNEL_COOP, "tx": nb.KERNEL_TRANSPOSED, "thread": nb.KERNEL_THREAD}[which])
+        if which == "tx":
             eng.set_tx_tuning(3, 1)   # 3 sets on one CTA (two set contexts): parking and ticket hand-over are exercised
         out = eng.propagate_batch(st, cs, ep, 1500 * S, traj_capacity=40)
         assert (out[3] == 0).all(), out[3]
@@ -63,5 +61,5 @@ def run(which):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
-    for w in (["thread", "coop", "strict", "tx", "tx64", "od"] if which == "all" else [which]):
+    for w in (["thread", "coop", "strict", "tx", "od"] if which == "all" else [which]):
         run(w)

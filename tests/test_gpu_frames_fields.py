@@ -76,9 +76,11 @@ def test_integration_frame_translations_match_the_oracle(oracle, mode, kernel):
     prop = nb.Propagator.default(dyn, mode=mode)
     prop.opts.integration_frame = nb.EARTH_J2000
     moon = alm.bodies[alm.body_index(MOON)]
+    # Moon-frame states: the low lunar orbits of _cislunar relative to the Moon (position and velocity of the Moon at the epoch the
+    # Earth-frame states were built for, velocity by central differences of the same table) — valid LLOs at any start epoch
     st_m = st_e.copy()
-    for i in range(n):   # Moon-frame copies of the Earth-frame states (any consistent choice will do: both sides get the same input)
-        st_m[:3, i] -= moon.position(int(ep[i]))
+    st_m[:3] -= moon.position(0)[:, None]
+    st_m[3:6] -= ((moon.position(S) - moon.position(-S)) / 2.0)[:, None]
     eng = prop.engine(nb.MOON_J2000, alm)
     if has_field:
         eng.set_kernel(kernel)

@@ -22,23 +22,9 @@ def _leo_dyn(degree=21, order=None, extras=False, days=1.0):
     return nb.SpacecraftDynamics.new(orb), almanac
 
 
-_SET_LEN = 32
-
-
-@pytest.fixture(params=[32, 64], autouse=True, ids=["sets-of-32", "sets-of-64"])
-def set_length(request):
-    """Every test of this module runs with sets of 32 trajectories (two sets per CTA) and with sets of 64 (a walker lane carries two
-    trajectories through every record load; falls back to 32 where the 8-position table plus one such set do not fit)."""
-    global _SET_LEN
-    _SET_LEN = request.param
-    yield request.param
-    _SET_LEN = 32
-
-
 def _tx_engine(prop, almanac=None, frame=None):
     eng = prop.engine(frame or nb.EARTH_J2000, almanac)
     eng.set_kernel(nb.KERNEL_TRANSPOSED)
-    eng.set_tx_set_length(_SET_LEN)
     return eng
 
 

@@ -121,9 +121,11 @@ def test_prop_instance_with_traj_api(oracle):
     st, cs, ep = nb.pack_spacecraft([sc])
     direct, *_ = oracle_run(oracle, prop, frame, None, st, cs, ep, 10_000 * S)
     assert np.linalg.norm(tr.at(10_000 * S).orbit.radius_km - direct[:3, 0]) < 2e-7
-    # explicit small capacity: truncated recording, same final state
-    f2, tr2 = prop.with_(sc).for_duration_with_traj(6 * 3600 * S, capacity=16)
-    assert len(tr2) == 16 and np.array_equal(f2.orbit.to_cartesian_pos_vel(), final.orbit.to_cartesian_pos_vel())
+    # explicit capacity that the run overflows: an error, never a silently truncated Traj (the reference's Traj holds every step)
+    with pytest.raises(nb.PropagationError, match="capacity 16 too small"):
+        prop.with_(sc).for_duration_with_traj(6 * 3600 * S, capacity=16)
+    f2, tr2 = prop.with_(sc).for_duration_with_traj(6 * 3600 * S, capacity=len(tr))
+    assert len(tr2) == len(tr) and np.array_equal(f2.orbit.to_cartesian_pos_vel(), final.orbit.to_cartesian_pos_vel())
 
 
 # ---- batched resampling (nyxb_traj_resample): the kernel's per-(query, trajectory) function on the CPU
