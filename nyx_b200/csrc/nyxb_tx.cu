@@ -284,6 +284,37 @@ __device__ __forceinline__ void tx_pick_step(const TxSm& sm, int lane, long long
     }
 }
 
+// x^(1/n), n = 2..9, for the step-size controller of this tolerance-parity kernel: a single-precision seed (MUFU lg2 / ex2) and two
+// Newton steps on q^n = x in double (relative error ~1e-6 -> 4e-12 -> rounding level).  The correctly rounded pow_inv_int of the
+// STRICT kernels (CUDA pow + a double-double Newton step + log) is a ~600-instruction dependent chain; it sat on the serial path
+// between two attempts of a set — 9 600 of the 14 800 clocks between the last DONE of an attempt and READY(0) of the next
+// (profiles/r02u_tx_trace.txt) — while the error norm that feeds it already differs from the reference's by ~1e-4 relative in FAST
+// mode.
+__device__ __forceinline__ double tx_pow_inv_int(double x, int n) {
+    if (!(x > 1e-30) || !(x < 1e30) || n < 2 || n > 9) return pow_inv_int(x, n);
+    const double inv_n = 1.0 / (double)n;
+    const double inv_x = 1.0 / x;
+    double q = (double)exp2f(log2f((float)x) * (float)inv_n);
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const double q2 = q * q, q4 = q2 * q2, q8 = q4 * q4;
+        double qn;   // q^n
+        switch (n) {
+        case 2: qn = q2; break;
+        case 3: qn = q2 * q; break;
+        case 4: qn = q4; break;
+        case 5: qn = q4 * q; break;
+        case 6: qn = q4 * q2; break;
+        case 7: qn = q4 * (q2 * q); break;
+        case 8: qn = q8; break;
+        default: qn = q8 * q; break;
+        }
+        const double r = fma(qn, inv_x, -1.0);   // q^n / x - 1
+        q = fma(-(r * inv_n), q, q);             // Newton: q (1 - r / n)
+    }
+    return q;
+}
+
 // ---- error norm, accept / reject, next step (instance.rs:416-490), single_step bookkeeping (instance.rs:343-352), recording
 // and stop condition; executed by the controller warp for its 32 trajectories
 __device__ __noinline__ void tx_controller(const DevSetup& S, const DevSink& sink, TxSm sm, int lane, size_t n, size_t tr, int stages) {
@@ -335,7 +366,7 @@ __device__ __noinline__ void tx_controller(const DevSetup& S, const DevSink& sin
             sm.i64[TXI_DET_STEP * NL + lane] = det_step;
             double hn = h;
             if (err < S.tolerance) {
-                const double proposed = 0.9 * h * pow_inv_int(S.tolerance / err, S.tb.order);
+                const double proposed = 0.9 * h * tx_pow_inv_int(S.tolerance / err, S.tb.order);
                 if (fabs(proposed) > fabs(S.max_step_s)) {
                     const double sg = (proposed != proposed) ? proposed : (signbit(proposed) ? -1.0 : 1.0);
                     hn = S.max_step_s * sg;
@@ -350,7 +381,7 @@ __device__ __noinline__ void tx_controller(const DevSetup& S, const DevSink& sin
         } else {
             sm.i32[TXW_ATT * NL + lane] = att + 1;
             sm.i64[TXI_NREJ * NL + lane] += 1;
-            const double proposed = 0.9 * h * pow_inv_int(S.tolerance / err, S.tb.order - 1);
+            const double proposed = 0.9 * h * tx_pow_inv_int(S.tolerance / err, S.tb.order - 1);
             sm.f64[TXF_H * NL + lane] = (proposed < S.min_step_s) ? S.min_step_s : proposed;
             sm.i32[TXW_FLAGS * NL + lane] = fl | F_RETRY;
             return;
