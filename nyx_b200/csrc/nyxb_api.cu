@@ -438,7 +438,9 @@ static int32_t launch_tx(nyxb_engine* e, size_t n, const double* state, const do
     // one persistent CTA per SM, `occ` set contexts each; tx_max_ctas (tests) shrinks the grid to force time slicing
     size_t ctas = (size_t)e->sms;
     if (e->tx_max_ctas > 0 && (size_t)e->tx_max_ctas < ctas) ctas = (size_t)e->tx_max_ctas;
-    ctas = std::min(ctas, (n_sets + occ - 1) / occ);
+    // fewer sets than SMs x contexts: spread them over all SMs (one set per CTA runs its stages at the helpers' pace instead of
+    // alternating with a second set, and twice as many SMs work: 5 000 trajectories 239 ms with 79 CTAs, profiles/r02y_shards.md)
+    ctas = std::min(ctas, n_sets);
     const size_t slots = ctas * occ;
     const int grid = (int)ctas;
     // workspace: [ctl 4 x i32 | ring n_sets x i32 | ws_step n i64 | ws_f64 2n | ws_flags n | details n]
@@ -492,9 +494,10 @@ static int pick_kernel(const nyxb_engine* e, size_t n) {
     if (e->kernel == NYXB_KERNEL_TRANSPOSED) return tx_supported(e) ? NYXB_KERNEL_TRANSPOSED : NYXB_KERNEL_COOP;
     if (e->kernel != NYXB_KERNEL_AUTO) return e->kernel;
     if (e->lanes > 0) return e->lanes == 1 ? NYXB_KERNEL_THREAD : NYXB_KERNEL_COOP;
-    // auto: the transposed kernel needs every resident CTA busy with a set of 32 trajectories (2 CTAs per SM: 9 472 trajectories on
-    // 148 SMs); smaller ensembles keep the lane-cooperative kernel, whose unit is one trajectory per 8 / 16 / 32 lanes
-    if (tx_supported(e) && e->S.grav.N <= 40 && n >= (size_t)9472) return NYXB_KERNEL_TRANSPOSED;
+    // auto: transposed kernel from 32 sets up (measured on B200, 21x21, 3 days: 1 250 trajectories 3.31e7 against 2.69e7 steps/s for the
+    // lane-cooperative kernel at its best lane count, 2 500: 6.65e7 / 4.65e7, 5 000: 8.44e7 / 7.33e7, 10 000: 1.58e8 / 0.96e8;
+    // profiles/r02y_shards.md)
+    if (tx_supported(e) && e->S.grav.N <= 40 && n >= (size_t)1024) return NYXB_KERNEL_TRANSPOSED;
     return NYXB_KERNEL_AUTO;
 }
 

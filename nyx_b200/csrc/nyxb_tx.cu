@@ -145,21 +145,22 @@ __device__ __forceinline__ void tx_mbar_wait(unsigned long long* bar, unsigned p
 __device__ __forceinline__ void tx_mbar_arrive(unsigned long long* bar) {   // release.cta: the thread's earlier shared stores are published
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ bool tx_mbar_test(unsigned long long* bar, unsigned parity) {   // non-blocking; acquire.cta when it succeeds
+__device__ __forceinline__ bool tx_mbar_test(unsigned bar_smem, unsigned parity) {   // non-blocking; acquire.cta when it succeeds
     unsigned ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
         "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" : "=r"(ok) : "r"(bar_smem), "r"(parity) : "memory");
     return ok != 0;
 }
 
 // Diagnostic timeline of CTA 0 (built with -DNYXB_TX_TRACE only; scripts/tx_trace.py reads it): lane 0 of every warp appends
 // (clock << 20 | code << 12 | context << 8 | stage) records to its own strip.
 enum { TR_POLL = 1, TR_WALK = 2, TR_WALK_END = 3, TR_DONE_WAIT = 4, TR_DONE_SEEN = 5, TR_READY = 6, TR_STAGES_END = 7, TR_CTRL_END = 8, TR_TOP = 9,
-       TR_PRE_DONE = 10, TR_DCM_DONE = 11, TR_REDUCED = 12, TR_ACC_DONE = 13, TR_HB_PASSED = 14 };
+       TR_PRE_DONE = 10, TR_DCM_DONE = 11, TR_REDUCED = 12, TR_ACC_DONE = 13, TR_HB_PASSED = 14, TR_CTRL_IN = 15, TR_CTRL_OUT = 16,
+       TR_PICKED = 17, TR_COMMITTED = 18, TR_PRIMED = 19, TR_DCM01 = 20 };
 #ifdef NYXB_TX_TRACE
 #define TX_TRACE(code, ctx, stg)                                                                                              \
     do {                                                                                                                      \
@@ -227,6 +228,7 @@ struct TxLaneState {
 // t[u].(cQ, cc1, cg, cS5, cS6) arrive set up for this column — Q = rho^m x seed, c1 = (2m+1) u rho, g = (2m+1) rho^2, S5 / S6 the
 // column's seed W term — because the caller sets the NEXT column up right behind the close of this one, in the same basic block, so
 // the two short dependent chains overlap.  Every record load serves the TT trajectories of the lane.
+template <bool SEQ_B>
 __device__ __forceinline__ void tx_column(const double2*& A, const double*& K, double2& a01, double2& a23, double& kk, int len,
                                           TxLaneState (&t)[TT]) {
     double Q[TT], c1[TT], g[TT], m2[TT], d[TT], S1[TT], S2[TT], S3[TT], S4[TT], S5[TT], S6[TT];
@@ -249,7 +251,7 @@ __device__ __forceinline__ void tx_column(const double2*& A, const double*& K, d
     // close the column: apply its (cos, sin)((m-1) lambda) cos^(m-1)(phi)
 #pragma unroll
     for (int u = 0; u < TT; ++u) {
-        const double rr = t[u].zar, ii = t[u].zai;
+        const double rr = SEQ_B ? t[u].zbr : t[u].zar, ii = SEQ_B ? t[u].zbi : t[u].zai;
         t[u].X = fma(rr, S1[u], fma(ii, S2[u], t[u].X));
         t[u].Y = fma(rr, S2[u], fma(-ii, S1[u], t[u].Y));
         t[u].Z = fma(rr, S3[u], fma(ii, S4[u], t[u].Z));
@@ -765,6 +767,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
         const int rec_off = my[0], ncol = my[1];
         unsigned active = (1u << NCTX) - 1u;
         unsigned phases = 0;   // bit 2c + par: parity of the READY[c][par] phase this warp waits for next
+        const unsigned ready0 = smem_u32(&ready_bar[0][0]);   // READY[c][par] lives at ready0 + 8 (2 c + par)
         int stage0 = 0, stage1 = 0, pref = 0;
         while (active) {
             {
@@ -777,7 +780,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                         const int cc = (pref + k) % NCTX;
                         if (c >= 0 || !((active >> cc) & 1u)) continue;
                         const int pp = (cc == 0 ? stage0 : stage1) & 1;
-                        const bool ok = tx_mbar_test(&ready_bar[cc][pp], (phases >> (2 * cc + pp)) & 1u);
+                        const bool ok = tx_mbar_test(ready0 + 8u * (unsigned)(2 * cc + pp), (phases >> (2 * cc + pp)) & 1u);
                         if (__all_sync(FULL, ok)) { c = cc; par = pp; }
                     }
                     if (c >= 0) break;
@@ -834,20 +837,37 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                         t[u].cS5 = t[u].cQ * sd.y; t[u].cS6 = t[u].cQ * sd.z;
                     }
                 }
-                for (int k = 0; k < ncol; ++k) {
-                    const int len_n = my[5 + 2 * k];   // the schedule rows end with a null column (all-zero seeds)
-                    const double4 sd_n = *reinterpret_cast<const double4*>(colseed + 4 * my[4 + 2 * k]);
-                    tx_column(A, K, a01, a23, kk, len, t);
+                // two columns per trip: the first belongs to sequence a, the second to sequence b (no exchange of the two register
+                // sets); the set-up of the next column needs only the OTHER sequence's rho power, which is already there, and the
+                // advance of the sequence just used (one complex product) is off every dependent path until two columns later
+                for (int k = 0; k < ncol; k += 2) {
+                    {
+                        const int len_n = my[5 + 2 * k];   // the schedule rows end with a null column (all-zero seeds)
+                        const double4 sd_n = *reinterpret_cast<const double4*>(colseed + 4 * my[4 + 2 * k]);
+                        tx_column<false>(A, K, a01, a23, kk, len, t);
 #pragma unroll
-                    for (int u = 0; u < TT; ++u) {
-                        const double nr = fma(t[u].zar, t[u].qr, -(t[u].zai * t[u].qi));
-                        const double ni = fma(t[u].zar, t[u].qi, t[u].zai * t[u].qr), np = t[u].pa * t[u].qp;
-                        t[u].zar = t[u].zbr; t[u].zai = t[u].zbi; t[u].pa = t[u].pb;
-                        t[u].zbr = nr; t[u].zbi = ni; t[u].pb = np;
-                        t[u].cQ = t[u].pa * sd_n.x; t[u].cc1 = sd_n.w * t[u].ub; t[u].cg = sd_n.w * t[u].r2;
-                        t[u].cS5 = t[u].cQ * sd_n.y; t[u].cS6 = t[u].cQ * sd_n.z;
+                        for (int u = 0; u < TT; ++u) {
+                            t[u].cQ = t[u].pb * sd_n.x; t[u].cc1 = sd_n.w * t[u].ub; t[u].cg = sd_n.w * t[u].r2;
+                            t[u].cS5 = t[u].cQ * sd_n.y; t[u].cS6 = t[u].cQ * sd_n.z;
+                            const double nr = fma(t[u].zar, t[u].qr, -(t[u].zai * t[u].qi));
+                            t[u].zai = fma(t[u].zar, t[u].qi, t[u].zai * t[u].qr); t[u].zar = nr; t[u].pa *= t[u].qp;
+                        }
+                        len = len_n;
                     }
-                    len = len_n;
+                    if (k + 1 >= ncol) break;
+                    {
+                        const int len_n = my[7 + 2 * k];
+                        const double4 sd_n = *reinterpret_cast<const double4*>(colseed + 4 * my[6 + 2 * k]);
+                        tx_column<true>(A, K, a01, a23, kk, len, t);
+#pragma unroll
+                        for (int u = 0; u < TT; ++u) {
+                            t[u].cQ = t[u].pa * sd_n.x; t[u].cc1 = sd_n.w * t[u].ub; t[u].cg = sd_n.w * t[u].r2;
+                            t[u].cS5 = t[u].cQ * sd_n.y; t[u].cS6 = t[u].cQ * sd_n.z;
+                            const double nr = fma(t[u].zbr, t[u].qr, -(t[u].zbi * t[u].qi));
+                            t[u].zbi = fma(t[u].zbr, t[u].qi, t[u].zbi * t[u].qr); t[u].zbr = nr; t[u].pb *= t[u].qp;
+                        }
+                        len = len_n;
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < TT; ++u) {
@@ -965,6 +985,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
             const long long off1 = (stages > 1) ? dur_from_seconds(S.tb.c[0] * h) : 0;
             if (stages > 1) sm.ysp[(1 * 3 + j) * NL + tl] = fma(h, ta[0] * v_own, r_own);   // P_1 = r + h a_10 V_0
             nb_sync(BAR_HB, NT_HB);
+            TX_TRACE(TR_PRIMED, c, 0);
             if (lead) {
                 if (gv.rot.kind != 0) {
                     rb_.sa = sm.rot[tl]; rb_.ca = sm.rot[NL + tl]; rb_.sd = sm.rot[2 * NL + tl]; rb_.cd = sm.rot[3 * NL + tl];
@@ -973,13 +994,18 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                 tx_dcm(gv.rot, rb_, 0, Rn);
 #pragma unroll
                 for (int k = 0; k < 9; ++k) sm.rn[k * NL + tl] = Rn[k];
-                if (stages > 1) {
-                    tx_dcm(gv.rot, rb_, off1, Rn);
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) sm.rn[(9 + k) * NL + tl] = Rn[k];
+            } else if (j == 1 && stages > 1) {   // the DCM of stage 1 in parallel with the lead's (both sat on the serial path between attempts)
+                TxRotBase rb1 = rb_;
+                if (gv.rot.kind != 0) {
+                    rb1.sa = sm.rot[tl]; rb1.ca = sm.rot[NL + tl]; rb1.sd = sm.rot[2 * NL + tl]; rb1.cd = sm.rot[3 * NL + tl];
+                    rb1.sw = sm.rot[4 * NL + tl]; rb1.cw = sm.rot[5 * NL + tl];
                 }
+                tx_dcm(gv.rot, rb1, off1, Rn);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) sm.rn[(9 + k) * NL + tl] = Rn[k];
             }
             nb_sync(BAR_HB, NT_HB);
+            TX_TRACE(TR_DCM01, c, 0);
             tx_prologue<P>(S, sm, tl, 0, j, sm.ysp, epoch);
             tx_mbar_arrive(&ready_bar[c][0]);
             TX_TRACE(TR_READY, c, 0);
@@ -1091,10 +1117,13 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
             sm.er[j * NL + tl] = er_r; sm.er[(3 + j) * NL + tl] = er_v;
             if (lead) sm.i32[TXW_RCST * NL + tl] = rc_acc;
             nb_sync(BAR_HB, NT_HB);
+            TX_TRACE(TR_CTRL_IN, c, 0);
             if (lead) {
                 tx_controller(S, sink, sm, tl, n, tr, stages);
+                TX_TRACE(TR_CTRL_OUT, c, 0);
                 const bool slice_end = q.slice > 0 && it + 1 >= q.slice;
                 if (!slice_end) tx_pick_step(sm, tl, end_epoch);
+                TX_TRACE(TR_PICKED, c, 0);
                 const bool done = sm.i32[TXW_FLAGS * NL + tl] & F_DONE;
                 const bool all = __all_sync(FULL, done);
                 if (lane == 0) { s_done_half[c][half] = all; if (half == 0) s_slice_end[c] = slice_end; }
@@ -1113,6 +1142,7 @@ nyxb_k_tx(const __grid_constant__ DevSetup S, const __grid_constant__ DevTx Tx, 
                     if (valid && ns < sink.cap) sink.state[((size_t)cc * sink.cap + (size_t)ns) * n + tr] = nx;
                 }
             }
+            TX_TRACE(TR_COMMITTED, c, 0);
             if (s_slice_end[c]) break;
         }
 

@@ -25,3 +25,20 @@ timeout 400 make -C nyx_b200/csrc EXTRA=-DNYXB_TX_TRACE > gpurun_out/${T}_make.l
 NYXB_TX_TRACE_FILE=gpurun_out/${T}_trace.bin timeout 120 python bench.py --steps 1 --warmup 0 --span-days 0.05 --n-traj 9472 --no-cpu-baseline --no-strict --kernel transposed > gpurun_out/${T}_trace_bench.log 2>&1; echo "trace bench rc=$?"
 python scripts/tx_trace.py gpurun_out/${T}_trace.bin 8 > gpurun_out/${T}_trace.txt 2>&1; head -16 gpurun_out/${T}_trace.txt
 fi
+if [ "${SHARDS:-0}" = "1" ]; then
+# strong-scaling shard sizes (10 000 trajectories over 4 / 8 GPUs): which lane count serves a small shard best
+S2="python bench.py --no-cpu-baseline --no-strict --steps 3 --warmup 3"
+for n in 1250 2500; do
+  for l in 8 16 32; do run shard_n${n}_l$l $S2 --n-traj $n --kernel coop --lanes $l; done
+  run shard_n${n}_tx $S2 --n-traj $n --kernel transposed
+done
+for f in gpurun_out/${T}_shard_*.json; do python - "$f" <<'PY'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(sys.argv[1].split('/')[-1], f"{d['value']:.4g} steps/s  ms {d['ms_per_step']:.1f}")
+except Exception as e:
+    print(sys.argv[1], "failed:", e)
+PY
+done
+fi
