@@ -238,37 +238,8 @@ __device__ __forceinline__ void rotation_dcm(const DevRotation& rot, long long t
     R[6] = b20; R[7] = b21; R[8] = b22;
 }
 
-// ---- TMA 1-D bulk copy global -> shared with mbarrier completion (SASS: UBLKCP + SYNCS); used to stage read-only tables
-__device__ __forceinline__ unsigned dev_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void dev_mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dev_smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void dev_mbar_expect(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dev_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void dev_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dev_smem_u32(dst)), "l"(src), "r"(bytes), "r"(dev_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void dev_mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "DEV_WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DEV_WAIT_DONE;\n"
-        "bra DEV_WAIT_LOOP;\n"
-        "DEV_WAIT_DONE:\n"
-        "}\n" ::"r"(dev_smem_u32(bar)), "r"(parity) : "memory");
-}
-
-// Ephemeris tables staged in shared memory by the kernel (one TMA bulk copy per body at CTA start): base[j] replaces
-// bodies[j].coeffs, NULL = read from global memory.  All lanes of a warp are usually in the same interval: uniform LDS.
-struct EphemSmem { const double* base[NYXB_MAX_BODIES]; };
-
 // Piecewise-Chebyshev body position (Clenshaw); returns false when outside coverage.
-__device__ __forceinline__ bool body_position(const DevBody& b, long long t_ns, double pos[3], const double* staged = nullptr) {
+__device__ __forceinline__ bool body_position(const DevBody& b, long long t_ns, double pos[3]) {
     long long dt = t_ns - b.t0_ns;
     if (dt < 0) return false;
 #if NYXB_STRICT
@@ -299,22 +270,6 @@ __device__ __forceinline__ bool body_position(const DevBody& b, long long t_ns, 
     const double tau = fma(2.0 * (double)off, b.inv_interval, -1.0);
     const double tau2 = 2.0 * tau;
     const int nc = b.n_coeffs;
-    if (staged) {   // the table sits in shared memory: plain (LDS) loads
-        const double* cx = staged + (size_t)idx * 3 * (size_t)nc;
-        const double* cy = cx + nc;
-        const double* cz = cy + nc;
-        double x1 = 0.0, x2 = 0.0, y1 = 0.0, y2 = 0.0, z1 = 0.0, z2 = 0.0;
-        for (int k = nc - 1; k >= 1; --k) {
-            const double xk = fma(tau2, x1, cx[k] - x2);
-            const double yk = fma(tau2, y1, cy[k] - y2);
-            const double zk = fma(tau2, z1, cz[k] - z2);
-            x2 = x1; x1 = xk; y2 = y1; y1 = yk; z2 = z1; z1 = zk;
-        }
-        pos[0] = fma(tau, x1, cx[0] - x2);
-        pos[1] = fma(tau, y1, cy[0] - y2);
-        pos[2] = fma(tau, z1, cz[0] - z2);
-        return true;
-    }
     const double* cx = b.coeffs + (size_t)idx * 3 * (size_t)nc;
     const double* cy = cx + nc;
     const double* cz = cy + nc;
@@ -594,9 +549,9 @@ __device__ __forceinline__ void accel_two_body(const DevSetup& S, const double y
 
 // body positions at t_ns + PointMasses::eom added to acc (orbital.rs:213-247)
 __device__ inline int accel_point_masses(const DevSetup& S, long long t_ns, const double y[9],
-                                         double bpos[NYXB_MAX_BODIES][3], double acc[3], const EphemSmem* es = nullptr) {
+                                         double bpos[NYXB_MAX_BODIES][3], double acc[3]) {
     for (int j = 0; j < S.n_bodies; ++j)
-        if (!body_position(S.bodies[j], t_ns, bpos[j], es ? es->base[j] : nullptr)) return NYXB_ERR_EPHEMERIS;
+        if (!body_position(S.bodies[j], t_ns, bpos[j])) return NYXB_ERR_EPHEMERIS;
     if (S.n_pm) {
         double dx[3] = {0.0, 0.0, 0.0};
         for (int q = 0; q < S.n_pm; ++q) {
@@ -627,9 +582,9 @@ __device__ inline int accel_point_masses(const DevSetup& S, long long t_ns, cons
 }
 
 __device__ inline int accel_pre(const DevSetup& S, long long t_ns, const double y[9],
-                                double bpos[NYXB_MAX_BODIES][3], double acc[3], const EphemSmem* es = nullptr) {
+                                double bpos[NYXB_MAX_BODIES][3], double acc[3]) {
     accel_two_body(S, y, acc);
-    return accel_point_masses(S, t_ns, y, bpos, acc, es);
+    return accel_point_masses(S, t_ns, y, bpos, acc);
 }
 
 __device__ inline void accel_post(const DevSetup& S, long long t_ns, const double y[9],
@@ -740,15 +695,14 @@ static __device__ __noinline__ void accel_extra_fields(const DevSetup& S, long l
 // Returns 0 or an nyxb_status error code.
 template <bool GRAV = true>
 __device__ inline int eom_full(const DevSetup& S, long long epoch_ns, double delta_t_s, const double y[9],
-                               double dry_mass, double extra_mass, double srp_area, double drag_area, double dy[6],
-                               const EphemSmem* es = nullptr) {
+                               double dry_mass, double extra_mass, double srp_area, double drag_area, double dy[6]) {
     long long t_ns = epoch_ns + dur_from_seconds(delta_t_s);
     double mass = dry_mass + y[8] + extra_mass;
     bool has_force = S.has_srp || S.has_drag;
     if (has_force && !(mass > 0.0)) return NYXB_ERR_MASSLESS;
     double acc[3];
     double bpos[NYXB_MAX_BODIES][3];
-    int rc = accel_pre(S, t_ns, y, bpos, acc, es);
+    int rc = accel_pre(S, t_ns, y, bpos, acc);
     if (rc) return rc;
     if (GRAV && S.has_grav) {
         double ga[3], rel[3];

@@ -39,7 +39,6 @@ struct Inst {
     size_t idx, n;
     double ev_prev;
     int ev_count;
-    const EphemSmem* es;   // ephemeris tables staged in shared memory (FAST build), or NULL
 };
 
 // instance.rs:358-493
@@ -50,7 +49,7 @@ __device__ static int derive(const DevSetup& S, Inst& in, long long& dt_ns, doub
     in.det_attempts = 1;
     double h = dur_to_seconds(in.step_ns);
     for (;;) {
-        int rc = eom_full<GRAV>(S, in.epoch_ns, 0.0, in.y, in.dry_mass, in.extra_mass, in.srp_area, in.drag_area, k[0], in.es);
+        int rc = eom_full<GRAV>(S, in.epoch_ns, 0.0, in.y, in.dry_mass, in.extra_mass, in.srp_area, in.drag_area, k[0]);
         in.n_rhs++;
         if (rc) return rc;
         for (int i = 0; i < stages - 1; ++i) {
@@ -70,7 +69,7 @@ __device__ static int derive(const DevSetup& S, Inst& in, long long& dt_ns, doub
             // components 6..8 have zero derivative: y + h*0 (NaN-propagating like the reference's 90-vector algebra, instance.rs:394)
             const double hz = h * 0.0;
             ys[6] = in.y[6] + hz; ys[7] = in.y[7] + hz; ys[8] = in.y[8] + hz;
-            rc = eom_full<GRAV>(S, in.epoch_ns, S.tb.c[i] * h, ys, in.dry_mass, in.extra_mass, in.srp_area, in.drag_area, k[i + 1], in.es);
+            rc = eom_full<GRAV>(S, in.epoch_ns, S.tb.c[i] * h, ys, in.dry_mass, in.extra_mass, in.srp_area, in.drag_area, k[i + 1]);
             in.n_rhs++;
             if (rc) return rc;
         }
@@ -188,37 +187,10 @@ NYXB_KTHREAD(const __grid_constant__ DevSetup S, size_t n,
              const long long* __restrict__ epoch0, long long end_epoch,
              long long* __restrict__ step_io,
              double* __restrict__ out_state, long long* __restrict__ out_epoch,
-             nyxb_details* __restrict__ out_details, int* __restrict__ out_status, const DevSink sink, unsigned eph_bytes) {
-    // ---- ephemeris tables of every body -> shared memory, one TMA bulk copy per body (north-star: "ephemeris samples staged
-    // through TMA").  A Chebyshev table is 3 x n_coeffs doubles per interval (C3: Moon 9 x 336 B, Sun 3 x 288 B); every stage of
-    // every trajectory evaluates it, and the lanes of a warp sit in the same interval: uniform LDS instead of global loads.
-    extern __shared__ __align__(16) unsigned char eph_sm[];
-    __shared__ __align__(8) unsigned long long eph_bar;
-    EphemSmem es;
-    bool staged = false;
-#if !NYXB_STRICT
-    if (eph_bytes > 0) {
-        if (threadIdx.x == 0) dev_mbar_init(&eph_bar, 1);
-        __syncthreads();
-        unsigned off = 0;
-        if (threadIdx.x == 0) dev_mbar_expect(&eph_bar, eph_bytes);
-        for (int j = 0; j < NYXB_MAX_BODIES; ++j) {
-            es.base[j] = nullptr;
-            if (j < S.n_bodies) {
-                const unsigned bytes = (unsigned)S.bodies[j].n_intervals * 3u * (unsigned)S.bodies[j].n_coeffs * 8u;
-                if (threadIdx.x == 0) dev_bulk_g2s(eph_sm + off, S.bodies[j].coeffs, bytes, &eph_bar);
-                es.base[j] = reinterpret_cast<const double*>(eph_sm + off);
-                off += bytes;
-            }
-        }
-        dev_mbar_wait(&eph_bar, 0);
-        staged = true;
-    }
-#endif
+             nyxb_details* __restrict__ out_details, int* __restrict__ out_status, const DevSink sink) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Inst in;
-    in.es = staged ? &es : nullptr;
 #pragma unroll
     for (int e = 0; e < 9; ++e) in.y[e] = state[(size_t)e * n + i];  // coalesced SoA loads
     in.dry_mass = consts[i]; in.extra_mass = consts[n + i]; in.srp_area = consts[2 * n + i]; in.drag_area = consts[3 * n + i];
@@ -257,23 +229,12 @@ extern "C" cudaError_t NYXB_LAUNCH_THREAD(const DevSetup* S, size_t n, const dou
                                           int* out_status, int block, const DevSink* sink, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     unsigned grid = (unsigned)((n + block - 1) / block);
-    // shared-memory staging of the ephemeris tables (FAST build): every table must be a multiple of 16 bytes (TMA) and all of them
-    // together small enough to leave the occupancy alone (40 KB: ~120 Moon intervals of 4 days)
-    unsigned eph_bytes = 0;
-#if !NYXB_STRICT
-    for (int j = 0; j < S->n_bodies; ++j) {
-        const unsigned bytes = (unsigned)S->bodies[j].n_intervals * 3u * (unsigned)S->bodies[j].n_coeffs * 8u;
-        if (bytes % 16u) { eph_bytes = 0; break; }
-        eph_bytes += bytes;
-    }
-    if (eph_bytes > 40u * 1024u) eph_bytes = 0;
-#endif
     if (S->has_grav)
-        NYXB_KTHREAD<true><<<grid, block, eph_bytes, stream>>>(*S, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch,
-                                                               out_details, out_status, *sink, eph_bytes);
+        NYXB_KTHREAD<true><<<grid, block, 0, stream>>>(*S, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch,
+                                                       out_details, out_status, *sink);
     else
-        NYXB_KTHREAD<false><<<grid, block, eph_bytes, stream>>>(*S, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch,
-                                                                out_details, out_status, *sink, eph_bytes);
+        NYXB_KTHREAD<false><<<grid, block, 0, stream>>>(*S, n, state, consts, epoch0, end_epoch, step_io, out_state, out_epoch,
+                                                        out_details, out_status, *sink);
     return cudaGetLastError();
 }
 
