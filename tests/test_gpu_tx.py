@@ -163,3 +163,29 @@ def test_transposed_kernel_backward_events_and_statuses(oracle):
     o2, e2, d2, s2 = eng.propagate_batch(st2, cs, ep2, 3600 * S)
     r2 = oracle_run(oracle, prop, nb.EARTH_J2000, None, st2, cs, ep2, 3600 * S)
     assert np.array_equal(s2, r2[3]) and s2[3] == 2 and d2["n_steps"][5] == 0 and np.array_equal(o2[:, 5], st2[:, 5])
+
+
+def test_automatic_dispatch_and_set_spreading(oracle):
+    """The library's own choice: FAST ensembles with a field of degree 8-40 go to the transposed kernel from 1 024 trajectories
+    (below: the lane-cooperative kernel; STRICT never).  1 100 trajectories = 35 sets on 35 CTAs (one set per CTA, the second set
+    context of every CTA finds nothing and leaves): same bits as the kernel forced explicitly, parity with the oracle."""
+    n = 1100
+    mc, (st, cs, ep) = leo_ensemble(n, seed=17)
+    dyn, _ = _leo_dyn()
+    end = 2 * 3600 * S
+    prop = nb.Propagator.default(dyn, mode=nb.MODE_FAST)
+    eng = prop.engine(nb.EARTH_J2000, None)
+    out, out_ep, det, status = eng.propagate_batch(st, cs, ep, end)
+    assert eng.last_kernel() == nb.KERNEL_TRANSPOSED
+    small = eng.propagate_batch(st[:, :1000].copy(), cs[:, :1000].copy(), ep[:1000].copy(), end)[0]
+    assert eng.last_kernel() == nb.KERNEL_COOP
+    assert max_dr_dv(small, out[:, :1000])[0] < 1e-6
+    eng.set_kernel(nb.KERNEL_TRANSPOSED)
+    forced = eng.propagate_batch(st, cs, ep, end)[0]
+    assert np.array_equal(forced, out)
+    ref, ref_ep, ref_det, ref_status = oracle_run(oracle, prop, nb.EARTH_J2000, None, st, cs, ep, end)
+    assert np.array_equal(status, ref_status) and np.array_equal(out_ep, ref_ep)
+    assert max_dr_dv(out, ref)[0] < 5e-7
+    strict = nb.Propagator.default(dyn, mode=nb.MODE_STRICT).engine(nb.EARTH_J2000, None)
+    strict.propagate_batch(st, cs, ep, 600 * S)
+    assert strict.last_kernel() != nb.KERNEL_TRANSPOSED
