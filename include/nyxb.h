@@ -500,7 +500,7 @@ int32_t nyxb_ziggurat_tables(double* x257, double* f257);                       
  *   THREAD      one thread per trajectory (no or low-degree gravity field; STRICT and FAST)
  *   COOP        8 / 16 / 32 lanes of a warp per trajectory, harmonic sum split by columns over the lanes (STRICT and FAST)
  *   TRANSPOSED  FAST only, degree 8..70: one CTA per set of 32 trajectories, lane = trajectory, warp = column position, persistent
- *               CTAs with (set, time-slice) tickets — the kernel of large harmonics-dominated ensembles (>= 1 024 trajectories; smaller ensembles go to the lane-cooperative kernel) */
+ *               CTAs with (set, time-slice) tickets — the kernel of large harmonics-dominated ensembles (>= 1 024 trajectories, field of degree 8..70; smaller ensembles go to the lane-cooperative kernel) */
 enum nyxb_kernel { NYXB_KERNEL_AUTO = 0, NYXB_KERNEL_THREAD = 1, NYXB_KERNEL_COOP = 2, NYXB_KERNEL_TRANSPOSED = 3 };
 int32_t nyxb_engine_set_kernel(nyxb_engine* eng, int32_t kernel);          /* enum nyxb_kernel; NYXB_RC_UNSUPPORTED if the setup cannot use it */
 int32_t nyxb_engine_last_kernel(const nyxb_engine* eng);                   /* family used by the last propagation launch */

@@ -497,7 +497,10 @@ static int pick_kernel(const nyxb_engine* e, size_t n) {
     // auto: transposed kernel from 32 sets up (measured on B200, 21x21, 3 days: 1 250 trajectories 3.31e7 against 2.69e7 steps/s for the
     // lane-cooperative kernel at its best lane count, 2 500: 6.65e7 / 4.65e7, 5 000: 8.44e7 / 7.33e7, 10 000: 1.58e8 / 0.96e8;
     // profiles/r02y_shards.md)
-    if (tx_supported(e) && e->S.grav.N <= 40 && n >= (size_t)1024) return NYXB_KERNEL_TRANSPOSED;
+    // every degree the transposed kernel serves (8..70; 16 walker positions and one set context per CTA above degree 40): GRAIL 70x70,
+    // 10 000 low lunar orbits 2.23e7 against 7.6e6 steps/s for the lane-cooperative kernel at 32 lanes, 2 000: 9.4e6 / 6.7e6
+    // (profiles/r02c4_kernels.md)
+    if (tx_supported(e) && n >= (size_t)1024) return NYXB_KERNEL_TRANSPOSED;
     return NYXB_KERNEL_AUTO;
 }
 

@@ -32,11 +32,16 @@ def _workload(name, n, span_days):
     return bench.build_workload(args, n, nb)
 
 
-def _fast_vs_oracle(oracle, name, n, span_days):
+def _fast_vs_oracle(oracle, name, n, span_days, kernel=None):
     frame, dyn, alm, st, cs, ep = _workload(name, n, span_days)
     prop = nb.Propagator.default(dyn, mode=nb.MODE_FAST)
     end = int(span_days * DAY)
-    out, oep, det, status = prop.engine(frame, alm).propagate_batch(st, cs, ep, end)
+    eng = prop.engine(frame, alm)
+    if kernel is not None:
+        eng.set_kernel(kernel)
+    out, oep, det, status = eng.propagate_batch(st, cs, ep, end)
+    if kernel is not None:
+        assert eng.last_kernel() == kernel
     ref, rep, rdet, rstatus = oracle.propagate_batch(dyn.pack(frame, alm).c, prop.opts.to_c(prop.method), st, cs, ep, end)
     assert (status == 0).all() and (rstatus == 0).all()
     assert np.array_equal(oep, rep)
@@ -64,9 +69,12 @@ def test_c3_fast_30_days_vs_oracle(oracle):
     assert dv.max() < 1e-12
 
 
-def test_c4_fast_7_days_vs_oracle(oracle):
-    """BASELINE configs[3]: low lunar orbit, GRAIL 70x70 + Earth / Sun point masses, 7 days (cooperative kernel, 32 lanes)."""
-    dr, dv = _fast_vs_oracle(oracle, "c4", 48, 7.0)
+@pytest.mark.parametrize("kernel", [nb.KERNEL_COOP, nb.KERNEL_TRANSPOSED], ids=["cooperative-32-lanes", "transposed-16-positions"])
+def test_c4_fast_7_days_vs_oracle(oracle, kernel):
+    """BASELINE configs[3]: low lunar orbit, GRAIL 70x70 + Earth / Sun point masses, 7 days — with the lane-cooperative kernel (what
+    ensembles below 1 024 trajectories get) and with the transposed kernel (16 walker positions, one set context per CTA: what the
+    dispatch picks from 1 024 trajectories)."""
+    dr, dv = _fast_vs_oracle(oracle, "c4", 48, 7.0, kernel)
     assert dr.max() < BOUND_KM, dr.max()   # one ulp in the oracle's own error norm: 1.6e-7 km
     assert dv.max() < 1e-9
 
