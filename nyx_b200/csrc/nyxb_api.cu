@@ -943,10 +943,10 @@ extern "C" int32_t nyxb_od_ekf_batch(nyxb_engine* eng, const nyxb_od_config* cfg
     if (od.est_state) CUDA_TRY(cudaMemsetAsync(od.est_state, 0xFF, sizeof(double) * m * 9 * n, st));
     if (od.est_cov) CUDA_TRY(cudaMemsetAsync(od.est_cov, 0xFF, sizeof(double) * m * 9 * n, st));
     // FAST mode with a gravity field: one WARP per filter, the harmonic gradient split by columns over the lanes
-    // (nyxb_od_coop.cu); columns -> lanes by longest-processing-time.  NYXB_OD_COOP=0 forces the per-thread kernel.
+    // (nyxb_od_coop.cu); columns -> lanes by longest-processing-time.  nyxb_engine_set_kernel(NYXB_KERNEL_THREAD) forces the
+    // per-thread kernel.
     const int* d_cols = nullptr;
-    bool coop = eng->mode == NYXB_MODE_FAST && eng->S.has_grav && eng->S.grav.N >= 8;
-    if (const char* ev = getenv("NYXB_OD_COOP")) coop = coop && atoi(ev) != 0;
+    bool coop = eng->mode == NYXB_MODE_FAST && eng->S.has_grav && eng->S.grav.N >= 8 && eng->kernel != NYXB_KERNEL_THREAD;
     if (coop) {
         const int N = eng->S.grav.N, mtop = eng->S.grav.M < N ? eng->S.grav.M : N, kmax = nyxb_od_coop_kmax();
         std::vector<int> cols(32 * (size_t)kmax, -1), cnt(32, 0);

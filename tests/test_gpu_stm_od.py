@@ -211,11 +211,13 @@ def test_warp_cooperative_filter_matches_oracle_and_per_thread_kernel(oracle, or
     n = 5
     sc = leo_od_scenario(oracle, n=n, n_msr=20, seed=9, degree=degree, msr_size=msr_size, reject=3.0 if msr_size == 2 else None)
     sc["prop"].mode = nb.MODE_FAST
-    monkeypatch.delenv("NYXB_OD_COOP", raising=False)
+    eng = sc["odp"].prop.engine(sc["frame"], sc["odp"].almanac)
+    eng.set_kernel(nb.KERNEL_AUTO)
     sol = sc["odp"].process_arcs(sc["ests"], sc["arc"], record_estimates=True)
     _compare_filters(sol, sc, oracle_od, 1e-4, 1e-7, n)
-    monkeypatch.setenv("NYXB_OD_COOP", "0")
+    eng.set_kernel(nb.KERNEL_THREAD)   # the same engine (cached per frame / options): per-thread filter kernel
     ref = sc["odp"].process_arcs(sc["ests"], sc["arc"], record_estimates=True)
+    eng.set_kernel(nb.KERNEL_AUTO)
     assert np.array_equal(sol.msr_flags, ref.msr_flags) and np.array_equal(sol.details["n_steps"], ref.details["n_steps"])
     assert np.abs(sol.final_state_soa[:3] - ref.final_state_soa[:3]).max() < 1e-7
     assert np.abs(sol.covar - ref.covar).max() <= 1e-7 * np.abs(ref.covar).max()
