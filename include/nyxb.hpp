@@ -227,6 +227,7 @@ class Propagator {
     IntegratorOptions opts;
     IntegratorMethod method = IntegratorMethod::RungeKutta89;
     int32_t mode = NYXB_MODE_STRICT, device = 0;
+    int32_t kernel = NYXB_KERNEL_AUTO;   // nyxb_engine_set_kernel: AUTO = the library's dispatch (by mode, field degree, ensemble size)
     static Propagator new_(SpacecraftDynamics d, IntegratorMethod m, IntegratorOptions o) { Propagator p; p.dynamics = std::move(d); p.method = m; p.opts = o; return p; }
     static Propagator rk89(SpacecraftDynamics d, IntegratorOptions o) { return new_(std::move(d), IntegratorMethod::RungeKutta89, o); }
     static Propagator dp78(SpacecraftDynamics d, IntegratorOptions o) { return new_(std::move(d), IntegratorMethod::DormandPrince78, o); }
@@ -243,10 +244,36 @@ class Propagator {
         r.state.resize(9 * n); r.epoch.resize(n); r.details.resize(n); r.status.resize(n);
         if (n == 0) return r;
         auto eng = detail::make_engine(dynamics, v[0].frame, almanac, method, opts, mode, device);
+        if (kernel != NYXB_KERNEL_AUTO && nyxb_engine_set_kernel(eng.get(), kernel) != NYXB_RC_OK)
+            throw std::runtime_error(std::string("nyxb_engine_set_kernel: ") + nyxb_last_error());
         detail::Soa soa(v);
         int32_t rc = nyxb_propagate_batch(eng.get(), n, soa.state.data(), soa.consts.data(), soa.epoch.data(), end_epoch_ns,
                                           step_io ? step_io->data() : nullptr, r.state.data(), r.epoch.data(), r.details.data(), r.status.data());
         if (rc != NYXB_RC_OK) throw std::runtime_error(std::string("nyxb_propagate_batch: ") + nyxb_last_error());
+        return r;
+    }
+    // the same fan-out over several GPUs of this process: one engine per device, contiguous run-index shards, results copied
+    // straight into the caller's arrays (nyxb_propagate_batch_multi; mc/montecarlo.rs:188-203 on G GPUs is ONE call of it)
+    BatchResult propagate_batch_multi(const std::vector<Spacecraft>& v, int64_t end_epoch_ns, const std::vector<int32_t>& devices,
+                                      const Almanac* almanac = nullptr, std::vector<int64_t>* step_io = nullptr) const {
+        BatchResult r;
+        const size_t n = v.size();
+        r.state.resize(9 * n); r.epoch.resize(n); r.details.resize(n); r.status.resize(n);
+        if (n == 0) return r;
+        if (devices.empty()) throw std::runtime_error("propagate_batch_multi: no devices");
+        std::vector<detail::EnginePtr> engs;
+        std::vector<nyxb_engine*> raw;
+        for (int32_t d : devices) {
+            engs.push_back(detail::make_engine(dynamics, v[0].frame, almanac, method, opts, mode, d));
+            if (kernel != NYXB_KERNEL_AUTO && nyxb_engine_set_kernel(engs.back().get(), kernel) != NYXB_RC_OK)
+                throw std::runtime_error(std::string("nyxb_engine_set_kernel: ") + nyxb_last_error());
+            raw.push_back(engs.back().get());
+        }
+        detail::Soa soa(v);
+        int32_t rc = nyxb_propagate_batch_multi(raw.data(), (int32_t)raw.size(), n, soa.state.data(), soa.consts.data(), soa.epoch.data(),
+                                                end_epoch_ns, step_io ? step_io->data() : nullptr, r.state.data(), r.epoch.data(),
+                                                r.details.data(), r.status.data());
+        if (rc != NYXB_RC_OK) throw std::runtime_error(std::string("nyxb_propagate_batch_multi: ") + nyxb_last_error());
         return r;
     }
     // Spacecraft::with_stm() + until_epoch for a batch: final states and the 9x9 STMs (column-major per trajectory, [81][n])

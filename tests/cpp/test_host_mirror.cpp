@@ -61,6 +61,19 @@ int main() {
         CHECK(std::get<Spacecraft>(tail.runs[0].result).x_km == std::get<Spacecraft>(res.runs[90].result).x_km);
         CHECK(res.total_steps > 100 * 30);
     }
+    {   // multi-device fan-out behind the ABI (two engines on device 0 here): contiguous shards, same results as the single call
+        const double sd2[9] = {1.0, 1.0, 1.0, 1e-3, 1e-3, 1e-3, 0, 0, 0};
+        MonteCarlo mc2(init, sd2, "multi", 7);
+        auto states = mc2.generate_states(0, 37);
+        auto prop2 = Propagator::default_(dynamics);
+        auto one = prop2.propagate_batch(states, 1800 * NS_PER_S);
+        auto two = prop2.propagate_batch_multi(states, 1800 * NS_PER_S, {0, 0});
+        CHECK(std::memcmp(one.state.data(), two.state.data(), one.state.size() * sizeof(double)) == 0);
+        CHECK(one.epoch == two.epoch && one.status == two.status);
+        prop2.kernel = NYXB_KERNEL_THREAD;   // explicit kernel family through nyxb_engine_set_kernel
+        auto thr = prop2.propagate_batch(states, 1800 * NS_PER_S);
+        CHECK(std::memcmp(one.state.data(), thr.state.data(), one.state.size() * sizeof(double)) == 0);   // two-body: the per-thread kernel either way
+    }
     {   // FuelExhausted surfaces as a PropagationError from PropInstance (spacecraft.rs:163-168)
         Spacecraft bad = init; bad.prop_mass_kg = -1.0;
         bool threw = false;
